@@ -1,0 +1,131 @@
+"""TEST INFRASTRUCTURE — ctypes loader for oracle/kao_ref.c (the plain-C restatement of the
+search path).  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libkao_ref.so")
+
+
+class RefProblem(C.Structure):
+    _fields_ = [("P", C.c_int32), ("B", C.c_int32), ("R", C.c_int32), ("RF", C.c_int32),
+                ("RFcur", C.c_int32),
+                ("rack_of", C.c_void_p), ("wF", C.c_void_p), ("wL", C.c_void_p),
+                ("rep_lo", C.c_void_p), ("rep_hi", C.c_void_p),
+                ("ldr_lo", C.c_void_p), ("ldr_hi", C.c_void_p),
+                ("rack_lo", C.c_void_p), ("rack_hi", C.c_void_p),
+                ("ppr_lo", C.c_int32), ("ppr_hi", C.c_int32), ("cur", C.c_void_p)]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "kao_ref.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.kao_ref_pack.restype = C.c_uint64
+        _lib.kao_ref_pack.argtypes = [C.c_int64, C.c_int64, C.c_uint32]
+        _lib.kao_ref_candidate_key.restype = C.c_uint64
+        _lib.kao_ref_search.restype = C.c_uint64
+    return _lib
+
+
+def _arr(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Ref:
+    """Holds the numpy buffers alive and exposes the C restatement on one oracle.model.Problem."""
+
+    def __init__(self, pb):
+        self.pb = pb
+        self.W = (pb.B + 31) // 32
+        self._keep = dict(
+            rack_of=_arr(pb.rack_of, np.uint8), wF=_arr(pb.wF, np.uint16), wL=_arr(pb.wL, np.uint16),
+            rep_lo=_arr(pb.rep_lo, np.int32), rep_hi=_arr(pb.rep_hi, np.int32),
+            ldr_lo=_arr(pb.ldr_lo, np.int32), ldr_hi=_arr(pb.ldr_hi, np.int32),
+            rack_lo=_arr(pb.rack_lo, np.int32), rack_hi=_arr(pb.rack_hi, np.int32),
+            cur=_arr(pb.cur, np.int32))
+        k = self._keep
+        self.c = RefProblem(pb.P, pb.B, pb.R, pb.RF, pb.cur.shape[1],
+                            *(k[n].ctypes.data for n in ("rack_of", "wF", "wL", "rep_lo", "rep_hi",
+                                                        "ldr_lo", "ldr_hi", "rack_lo", "rack_hi")),
+                            int(pb.ppr_lo), int(pb.ppr_hi), k["cur"].ctypes.data)
+
+    def _p(self):
+        return C.byref(self.c)
+
+    def new_candidate(self):
+        return np.zeros((self.pb.P, self.W), np.uint32), np.zeros(self.pb.P, np.uint8)
+
+    def init_base(self):
+        bits, ld = self.new_candidate()
+        lib().kao_ref_init_base(self._p(), C.c_void_p(bits.ctypes.data), C.c_void_p(ld.ctypes.data))
+        return bits, ld
+
+    def evaluate(self, bits, ld):
+        v, o = C.c_int64(), C.c_int64()
+        lib().kao_ref_eval(self._p(), C.c_void_p(bits.ctypes.data), C.c_void_p(ld.ctypes.data),
+                           C.byref(v), C.byref(o))
+        return v.value, o.value
+
+    def gen(self, bits, ld, seed, rnd, idx, round_size):
+        ob, ol = self.new_candidate()
+        lib().kao_ref_gen(self._p(), C.c_void_p(bits.ctypes.data), C.c_void_p(ld.ctypes.data),
+                          C.c_uint64(seed), C.c_uint32(rnd), C.c_uint32(idx), C.c_uint32(round_size),
+                          C.c_void_p(ob.ctypes.data), C.c_void_p(ol.ctypes.data))
+        return ob, ol
+
+    def candidate_keys(self, bits, ld, seed, rnd, idxs, round_size):
+        sb, sl = self.new_candidate()
+        out = np.empty(len(idxs), np.uint64)
+        f = lib().kao_ref_candidate_key
+        for i, idx in enumerate(idxs):
+            out[i] = f(self._p(), C.c_void_p(bits.ctypes.data), C.c_void_p(ld.ctypes.data),
+                       C.c_uint64(seed), C.c_uint32(rnd), C.c_uint32(int(idx)),
+                       C.c_uint32(round_size), C.c_void_p(sb.ctypes.data), C.c_void_p(sl.ctypes.data))
+        return out
+
+    def search(self, bits, ld, seed, first_round, rounds, round_size, nthreads=0):
+        """In-place on (bits, ld).  Returns (last key, per-round keys)."""
+        keys = np.zeros(rounds, np.uint64)
+        last = lib().kao_ref_search(self._p(), C.c_void_p(bits.ctypes.data),
+                                    C.c_void_p(ld.ctypes.data), C.c_uint64(seed),
+                                    C.c_uint32(first_round), C.c_uint32(rounds),
+                                    C.c_uint32(round_size), C.c_void_p(keys.ctypes.data),
+                                    C.c_int(nthreads))
+        return last, keys
+
+    def decode(self, bits, ld):
+        out = np.empty((self.pb.P, self.pb.RF), np.int32)
+        lib().kao_ref_decode(self._p(), C.c_void_p(bits.ctypes.data), C.c_void_p(ld.ctypes.data),
+                             C.c_void_p(out.ctypes.data))
+        return out
+
+    @staticmethod
+    def philox(ctr, key):
+        c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
+        lib().kao_ref_philox(c, k, o)
+        return list(o)
+
+    @staticmethod
+    def max_threads():
+        return lib().kao_ref_max_threads()
+
+
+def unpack_key(key):
+    key = int(key)
+    return key >> 48, 0xFFFFFF - ((key >> 24) & 0xFFFFFF), key & 0xFFFFFF
