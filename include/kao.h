@@ -1,0 +1,149 @@
+/*
+ * kao.h — C ABI of the B200-native Kafka assignment-search engine (libkao.so).
+ *
+ * This is the drop-in boundary for the solver step of killerwhile/kafka-assignment-optimizer:
+ * where the reference builds an lp_solve model from (current assignment, broker list, rack map,
+ * RF) and reads the 0/1 solution back (/root/reference/README.md:135-136 "lp_solve is used
+ * behind the scene", model at README.md:139-185), a caller fills a kao_problem with the same
+ * model data as dense integer tables and calls kao_solve().  The reference snapshot contains no
+ * source, hence no FFI declarations to cite; every entry point cites the README lines whose
+ * behaviour it replaces.  The binding a maintainer adds (JNI / java.lang.foreign / ctypes) is
+ * shown in INTEGRATION.md.
+ *
+ * Conventions: plain C types only; the caller owns every buffer; nothing is retained after a
+ * call returns except inside an explicit kao_handle; functions return 0 on success, > 0 for a
+ * model-level outcome (KAO_INFEASIBLE), < 0 for argument / CUDA errors, and never throw or exit.
+ * kao_last_error() returns a thread-local message for the last non-zero return.
+ *
+ * Brokers are dense indices 0..B-1 = position in the *target* broker list (README.md:48);
+ * mapping Kafka broker ids <-> dense indices is host-side work (JSON codec).
+ */
+#ifndef KAO_H_
+#define KAO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KAO_VERSION 0x00010000 /* major.minor.patch = 0.1.0 */
+
+/* return codes */
+#define KAO_OK 0
+#define KAO_INFEASIBLE 1      /* search ended without a candidate satisfying C1..C7 */
+#define KAO_E_ARG (-1)        /* bad argument / unsupported problem shape */
+#define KAO_E_CUDA (-2)       /* CUDA runtime error (no device, launch failure, OOM) */
+#define KAO_E_STATE (-3)      /* handle used in the wrong state */
+
+/* limits of this build */
+#define KAO_MAX_SLOTS 256     /* racks * pow2ceil(max(8, largest rack)) must not exceed this */
+#define KAO_MAX_RACKS 32
+#define KAO_MAX_RF 8
+#define KAO_MAX_ROUND_SIZE (1u << 24)
+
+/*
+ * The model, README.md:139-185.  x[b,p] / l[b,p] are the reference's binaries t1b{b}p{p} /
+ * t1b{b}p{p}_l (README.md:146, :182-184); an assignment is exchanged as replica lists.
+ */
+typedef struct kao_problem {
+    int32_t P;                /* partitions (rows; multi-topic input is flattened host-side) */
+    int32_t B;                /* brokers in the target list, README.md:48 */
+    int32_t R;                /* racks / AZs, README.md:27-29 */
+    int32_t RF;               /* target replication factor, C1 README.md:148-151 */
+    int32_t RFcur;            /* row length of `cur` */
+    const uint8_t *rack_of;   /* [B] rack index of each broker */
+    const uint16_t *wF;       /* [P*B] objective weight of a follower replica, README.md:145-146 */
+    const uint16_t *wL;       /* [P*B] objective weight of the leader replica, README.md:131-133 */
+    const int32_t *rep_lo;    /* [B] C3 min replicas per broker, README.md:158-161 */
+    const int32_t *rep_hi;    /* [B] C3 max */
+    const int32_t *ldr_lo;    /* [B] C4 min leaders per broker, README.md:163-166 */
+    const int32_t *ldr_hi;    /* [B] C4 max */
+    const int32_t *rack_lo;   /* [R] C6 min total replicas per rack, README.md:173-176 */
+    const int32_t *rack_hi;   /* [R] C6 max */
+    int32_t ppr_lo;           /* C7 min replicas of one partition in one rack, README.md:178-180 */
+    int32_t ppr_hi;           /* C7 max */
+    const int32_t *cur;       /* [P*RFcur] current assignment, leader first (README.md:52-63),
+                                 dense indices; -1 = padding or a broker not in the target list */
+} kao_problem;
+
+typedef struct kao_options {
+    uint64_t seed;            /* Philox key of the candidate stream */
+    uint32_t rounds;          /* search rounds; candidates evaluated = rounds * round_size */
+    uint32_t round_size;      /* candidates per round, 2 .. KAO_MAX_ROUND_SIZE */
+    int32_t device;           /* CUDA device ordinal */
+    uint32_t flags;           /* reserved, 0 */
+} kao_options;
+
+typedef struct kao_result {
+    int32_t *replicas;        /* [P*RF] caller-allocated; leader first, then followers by
+                                 ascending dense index (README.md:65-78, :88); -1 padded */
+    int64_t objective;        /* README.md:145-146 value of the returned assignment */
+    int64_t violation;        /* 0 <=> C1..C7 all hold */
+    int32_t moves;            /* replicas placed on a broker that did not hold the partition */
+    int32_t feasible;
+    uint64_t key;             /* packed (violation, cost, index) of the last winning candidate */
+    uint64_t n_candidates;    /* candidates generated and fully evaluated */
+    uint32_t rounds_run;
+    uint32_t reserved;
+    double device_ms;         /* CUDA-event time of the search kernels */
+    double total_ms;          /* wall time of the call incl. host<->device copies */
+} kao_result;
+
+int kao_version(void);
+const char *kao_last_error(void);
+
+/* One blocking solve from host buffers: tables -> device, `rounds` search rounds, winner -> host.
+ * Replaces "emit LP + run lp_solve + parse variables" (README.md:135-136, :139-185). */
+int kao_solve(const kao_problem *pb, const kao_options *opt, kao_result *res);
+
+/* Evaluate n explicit assignments (each [P*RF] replica lists, leader first, -1 padded) on the
+ * GPU with the same evaluator the search uses: C1..C7 violation amount and objective. */
+int kao_eval(const kao_problem *pb, int32_t device, const int32_t *replicas, int32_t n,
+             int64_t *violation, int64_t *objective);
+
+/* ---- device-resident session: tables stay in HBM between calls (multi-round, multi-GPU) ---- */
+typedef struct kao_handle kao_handle;
+
+int kao_create(const kao_problem *pb, int32_t device, kao_handle **out);
+int kao_destroy(kao_handle *h);
+/* base <- current assignment restricted to the target brokers and completed to RF (MODEL §4) */
+int kao_reset(kao_handle *h);
+int kao_set_base(kao_handle *h, const int32_t *replicas);
+int kao_get_base(kao_handle *h, int32_t *replicas, int64_t *violation, int64_t *objective,
+                 int32_t *moves);
+
+/* rounds first_round .. first_round+rounds-1 on this GPU alone; round_keys (optional, host,
+ * [rounds]) receives each round's winning key; device_ms (optional) the CUDA-event time. */
+int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+               uint32_t round_size, uint64_t *round_keys, double *device_ms);
+
+/* keys of candidates idx_begin .. idx_begin+count-1 of `round` against the current base (host
+ * buffer) — the per-candidate parity vector. */
+int kao_candidate_keys(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                       uint32_t idx_begin, uint32_t count, uint64_t *keys);
+
+/* sharded round, asynchronous on `stream` (a cudaStream_t, 0 = default):
+ *   kao_round_launch  evaluates idx_lo..idx_hi-1 and atomically min-reduces the packed key into
+ *                     *d_key (DEVICE pointer, caller pre-sets it to ~0ull);
+ *   [caller min-all-reduces *d_key across ranks: one 8-byte collective]
+ *   kao_round_apply   re-materialises the winning candidate from (seed, round, index) and makes
+ *                     it the base.  Every rank applies the same key => identical bases. */
+int kao_round_launch(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                     uint32_t idx_lo, uint32_t idx_hi, uint64_t *d_key, void *stream);
+int kao_round_apply(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                    const uint64_t *d_key, void *stream);
+
+/* introspection for benchmarks: kernel launches issued by this handle so far, words per row */
+int kao_stats(kao_handle *h, uint64_t *kernel_launches, int32_t *words_per_row,
+              int32_t *slots, int32_t *dense_weights);
+
+/* key layout helpers: key = violation(16, saturating) | (0xFFFFFF - objective)(24) | index(24) */
+#define KAO_KEY_VIOLATION(k) ((uint32_t)((k) >> 48))
+#define KAO_KEY_OBJECTIVE(k) (0xFFFFFFu - (uint32_t)(((k) >> 24) & 0xFFFFFFu))
+#define KAO_KEY_INDEX(k) ((uint32_t)((k) & 0xFFFFFFu))
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAO_H_ */

@@ -1,0 +1,724 @@
+// kao_device.cuh — device side of the assignment-search engine (sm_100a).
+//
+// One warp owns one candidate at a time.  The base assignment (replica bit-plane over rack-aligned
+// broker slots, leader slot per partition) and the per-partition weight entries live in shared
+// memory for the whole kernel, staged once with TMA bulk copies; a candidate is the base plus up
+// to three row patches derived from (seed, round, index) by Philox4x32-10, and is evaluated IN
+// FULL: every row's C1/C2/C5/C7 terms and weight, every broker column's replica and leader counts
+// (C3/C4, carry-save bit-sliced counters + a cross-lane reduce-scatter), every rack total (C6).
+// Model: /root/reference/README.md:139-185; search/generator spec: docs/MODEL.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kao {
+
+constexpr int kMaxOps = 3;
+constexpr uint32_t kIdxBits = 24;
+constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1;
+constexpr uint32_t kObjCap = 0xFFFFFFu;
+constexpr uint32_t kViolCap = 0xFFFFu;
+constexpr uint32_t kTag = 0x4B414F21u;
+constexpr int kRowsPerLane = 4;            // rows handled per lane per 128-row tile
+constexpr int kTileRows = 32 * kRowsPerLane;
+
+// Small read-only tables, one 16-byte-aligned blob (one bulk copy into shared memory).
+struct Consts {
+    uint32_t bnd_rep[256];       // C3  lo | hi << 16 per slot (padding slots 0|0)
+    uint32_t bnd_ldr[256];       // C4
+    int32_t rack_lo[32];         // C6
+    int32_t rack_hi[32];
+    uint8_t slot_of_order[256];  // rack-major order index -> slot
+    uint8_t order_of_slot[256];  // slot -> order index, 0xFF for padding slots
+};
+static_assert(sizeof(Consts) % 16 == 0, "bulk copy size");
+
+struct Params {
+    int P, Ppad, B, R, RF, NS, log2S;
+    int ppr_lo, ppr_hi;
+    int dense;                   // 1: weights come from dense_w (general tables), 0: from swT
+    uint32_t *bitsT;             // base replica bit-plane, word-major [W][Ppad]
+    uint8_t *leader;             // base leader slot [Ppad] (0xFF = none)
+    const uint32_t *swT;         // sparse weight entries [4][Ppad]: slot | wF << 8 | wL << 20
+    const uint32_t *dense_w;     // [P][NS] wF | wL << 16, or nullptr
+    const uint32_t *homeT;       // [Ppad] 4 x u8 home slots (0xFF = none)
+    uint16_t *D;                 // displaced partitions of the base, ascending
+    uint16_t *DL;                // leader-displaced partitions of the base, ascending
+    int *nD;                     // [0] = |D|, [1] = |DL|
+    const Consts *consts;
+};
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack_key(int viol, int obj, uint32_t idx)
+{
+    const uint32_t v = viol > (int)kViolCap ? kViolCap : (uint32_t)viol;
+    const uint32_t c = (uint32_t)obj > kObjCap ? 0u : kObjCap - (uint32_t)obj;
+    return ((uint64_t)v << 48) | ((uint64_t)c << kIdxBits) | (uint64_t)(idx & kIdxMask);
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&o)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+template <int W> __device__ __forceinline__ uint32_t row_word(const uint32_t (&w)[W], int j)
+{
+    uint32_t x = w[0];
+#pragma unroll
+    for (int t = 1; t < W; ++t) x = (j == t) ? w[t] : x;
+    return x;
+}
+template <int W> __device__ __forceinline__ bool row_has(const uint32_t (&w)[W], int s)
+{
+    return ((s >> 5) < W) && ((row_word<W>(w, s >> 5) >> (s & 31)) & 1u);
+}
+template <int W> __device__ __forceinline__ void row_flip(uint32_t (&w)[W], int s)
+{
+    const uint32_t m = 1u << (s & 31);
+#pragma unroll
+    for (int t = 0; t < W; ++t) w[t] ^= ((s >> 5) == t) ? m : 0u;
+}
+template <int W> __device__ __forceinline__ int row_count(const uint32_t (&w)[W])
+{
+    int n = 0;
+#pragma unroll
+    for (int t = 0; t < W; ++t) n += __popc(w[t]);
+    return n;
+}
+// k-th (0-based) set bit in ascending slot order, -1 if fewer
+template <int W> __device__ __forceinline__ int row_kth(const uint32_t (&w)[W], int k)
+{
+    int res = -1;
+#pragma unroll
+    for (int t = 0; t < W; ++t) {
+        const int c = __popc(w[t]);
+        if (res < 0 && k < c) {
+            uint32_t m = w[t];
+            for (int i = 0; i < k; ++i) m &= m - 1;
+            res = t * 32 + __ffs(m) - 1;
+        }
+        k -= c;
+    }
+    return res;
+}
+__device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t n) { return __umulhi(a, n); }
+
+// ------------------------------------------------------------------------------------------
+// candidate generator (docs/MODEL.md §5): warp-uniform, every lane computes the same patches
+// ------------------------------------------------------------------------------------------
+struct PatchSet {
+    int n;
+    int p[kMaxOps];
+    uint32_t ld[kMaxOps];
+};
+
+template <int W> struct Gen {
+    const uint32_t *bitsT;   // base (shared or global)
+    const uint8_t *leader;
+    const Consts *cs;
+    const Params *d;
+    uint32_t *prow;          // [kMaxOps * W] warp scratch for patched rows
+    int lane;
+
+    __device__ __forceinline__ void read_row(int p, uint32_t (&row)[W], uint32_t &ld) const
+    {
+#pragma unroll
+        for (int t = 0; t < W; ++t) row[t] = bitsT[(size_t)t * d->Ppad + p];
+        ld = leader[p];
+    }
+    __device__ __forceinline__ void push(PatchSet &ps, int p, const uint32_t (&row)[W], uint32_t ld) const
+    {
+        int slot = ps.n;
+#pragma unroll
+        for (int i = 0; i < kMaxOps; ++i) if (ps.p[i] == p) slot = i;   // unused entries hold -1
+        if (slot == ps.n) ++ps.n;
+        // static stores keep ps in registers
+#pragma unroll
+        for (int i = 0; i < kMaxOps; ++i) if (i == slot) { ps.p[i] = p; ps.ld[i] = ld; }
+        if (lane == 0) {
+#pragma unroll
+            for (int t = 0; t < W; ++t) prow[slot * W + t] = row[t];
+        }
+    }
+    // REPLACE on a row held in registers: replica on slot a moves to the first free broker in
+    // rack-major order starting at order index o (cyclic); leadership follows the replica.
+    __device__ __forceinline__ int replace(uint32_t (&row)[W], uint32_t &ld, int a, int o) const
+    {
+        const int B = d->B;
+        int s = cs->slot_of_order[o];
+        for (int tries = 0; tries < B && row_has<W>(row, s); ++tries) {
+            o = (o + 1 == B) ? 0 : o + 1;
+            s = cs->slot_of_order[o];
+        }
+        row_flip<W>(row, a);
+        row_flip<W>(row, s);
+        if ((int)ld == a) ld = (uint32_t)s;
+        return s;
+    }
+    // LEADER: the partition is led from `want` if that is one of its non-leader replicas, else
+    // from its k-th (ascending slot) non-leader replica.  Returns the new leader slot or -1.
+    __device__ __forceinline__ int pick_leader(const uint32_t (&row)[W], uint32_t &ld, int want, uint32_t rnd) const
+    {
+        uint32_t m[W];
+        const bool has = ((int)ld < W * 32) && row_has<W>(row, (int)ld);
+#pragma unroll
+        for (int t = 0; t < W; ++t) m[t] = row[t];
+        if (has) row_flip<W>(m, (int)ld);
+        const int cnt = row_count<W>(m);
+        if (cnt < 1) return -1;
+        if (want >= 0 && want < W * 32 && want != (int)ld && row_has<W>(row, want)) { ld = (uint32_t)want; return want; }
+        ld = (uint32_t)row_kth<W>(m, (int)mulhi32(rnd, (uint32_t)cnt));
+        return (int)ld;
+    }
+    // first partition q >= p0 (cyclic), not yet patched, for which pred(q) holds; kind 0: holds a
+    // replica on slot src; 1: is led from src; 2: follows (holds, not led) on src
+    template <int KIND>
+    __device__ __forceinline__ int find_from(const PatchSet &ps, int p0, int src) const
+    {
+        const int P = d->P;
+        if (src < 0 || src >= W * 32) return -1;
+        const uint32_t *col = bitsT + (size_t)(src >> 5) * d->Ppad;
+        const uint32_t bit = 1u << (src & 31);
+        for (int k = 0; k < P; k += 32) {
+            const int off = k + lane;
+            int q = p0 + off;
+            if (q >= P) q -= P;
+            bool hit = false;
+            if (off < P) {
+                bool t = false;
+#pragma unroll
+                for (int i = 0; i < kMaxOps; ++i) t |= (ps.p[i] == q);
+                if (KIND == 0) hit = !t && (col[q] & bit);
+                if (KIND == 1) hit = !t && ((int)leader[q] == src);
+                if (KIND == 2) hit = !t && ((int)leader[q] != src) && (col[q] & bit);
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+            if (m) {
+                int r = p0 + k + (__ffs(m) - 1);
+                if (r >= P) r -= P;
+                return r;
+            }
+        }
+        return -1;
+    }
+
+    // docs/MODEL.md §5 — must stay bit-identical to the restated generator the tests check against
+    __device__ void run(uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size, PatchSet &ps) const
+    {
+        ps.n = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
+        if (idx + 1 == round_size) return;                       // identity candidate
+        const int P = d->P, B = d->B;
+        uint32_t r[4], s[4];
+        philox4x32_10(idx, round, 0u, kTag, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        const uint32_t ctl = r[0];
+        const int nops = (ctl & 3u) == 0 ? 1 : ((ctl & 3u) == 3 ? 3 : 2);
+        const bool first_leader = (ctl >> 2) & 1u, gbit = (ctl >> 3) & 1u;
+        uint32_t row[W], ld;
+        int lo, hi;
+        if (first_leader) {
+            const int nL = d->nD[1];
+            const bool guided = gbit && nL > 0;
+            const int p = guided ? (int)d->DL[mulhi32(r[1], (uint32_t)nL)] : (int)mulhi32(r[1], (uint32_t)P);
+            read_row(p, row, ld);
+            lo = (int)ld;
+            int want = -1;
+            if (guided) { const int h0 = d->homeT[p] & 0xFF; want = (h0 == 0xFF) ? -1 : h0; }
+            hi = pick_leader(row, ld, want, r[2]);
+            if (hi < 0) return;
+            push(ps, p, row, ld);
+        } else {
+            const int nD = d->nD[0];
+            const bool guided = gbit && nD > 0;
+            const int p = guided ? (int)d->D[mulhi32(r[1], (uint32_t)nD)] : (int)mulhi32(r[1], (uint32_t)P);
+            read_row(p, row, ld);
+            const int n = row_count<W>(row);
+            if (n == 0) return;
+            int a = row_kth<W>(row, (int)mulhi32(r[2], (uint32_t)n));
+            int o = (int)mulhi32(r[3], (uint32_t)B);
+            if (guided) {
+                const uint32_t h4 = d->homeT[p];
+                uint32_t home[W], miss[W], nonhome[W];
+#pragma unroll
+                for (int t = 0; t < W; ++t) home[t] = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int hs = (h4 >> (8 * i)) & 0xFF;
+                    if (hs != 0xFF && !row_has<W>(home, hs)) row_flip<W>(home, hs);
+                }
+#pragma unroll
+                for (int t = 0; t < W; ++t) { miss[t] = home[t] & ~row[t]; nonhome[t] = row[t] & ~home[t]; }
+                const int nm = row_count<W>(miss), nn = row_count<W>(nonhome);
+                if (nm > 0) {
+                    o = cs->order_of_slot[row_kth<W>(miss, (int)mulhi32(r[3], (uint32_t)nm))];
+                    if (nn > 0) a = row_kth<W>(nonhome, (int)mulhi32(r[2], (uint32_t)nn));
+                }
+            }
+            hi = replace(row, ld, a, o);
+            lo = a;
+            push(ps, p, row, ld);
+        }
+        if (nops == 1) return;
+        philox4x32_10(idx, round, 1u, kTag, (uint32_t)seed, (uint32_t)(seed >> 32), s);
+        for (int k = 1; k < nops; ++k) {
+            const uint32_t link = (ctl >> (4 + 3 * (k - 1))) & 3u;
+            const bool close = (ctl >> (6 + 3 * (k - 1))) & 1u;
+            const uint32_t ra = (k == 1) ? s[0] : s[2], rb = (k == 1) ? s[1] : s[3];
+            const int start = (int)mulhi32(ra, (uint32_t)P);
+            int olo = (lo >= 0 && lo < 256) ? (int)cs->order_of_slot[lo] : 0xFF;
+            if (olo >= B) olo = 0;
+            uint32_t rq[W], lq;
+            if (link == 0) {                                   // R-push
+                const int q = find_from<0>(ps, start, hi);
+                if (q < 0) return;
+                read_row(q, rq, lq);
+                hi = replace(rq, lq, hi, close ? olo : (int)mulhi32(rb, (uint32_t)B));
+                push(ps, q, rq, lq);
+            } else if (link == 1) {                            // R-pull
+                const int q = start;
+                bool t = false;
+#pragma unroll
+                for (int i = 0; i < kMaxOps; ++i) t |= (ps.p[i] == q);
+                if (t) return;
+                read_row(q, rq, lq);
+                const int nq = row_count<W>(rq);
+                if (nq == 0) return;
+                int src = row_kth<W>(rq, (int)mulhi32(rb, (uint32_t)nq));
+                if (close && (int)lq < W * 32 && row_has<W>(rq, (int)lq)) src = (int)lq;
+                replace(rq, lq, src, olo);
+                lo = src;
+                push(ps, q, rq, lq);
+            } else if (link == 2) {                            // L-push
+                const int q = find_from<1>(ps, start, hi);
+                if (q < 0) return;
+                read_row(q, rq, lq);
+                int want = lo;
+                if (!close) { const int h0 = d->homeT[q] & 0xFF; want = (h0 == 0xFF) ? -1 : h0; }
+                const int t = pick_leader(rq, lq, want, rb);
+                if (t < 0) return;
+                hi = t;
+                push(ps, q, rq, lq);
+            } else {                                           // L-pull
+                const int q = find_from<2>(ps, start, lo);
+                if (q < 0) return;
+                read_row(q, rq, lq);
+                const int old = (int)lq;
+                if (pick_leader(rq, lq, lo, rb) < 0) return;
+                lo = old;
+                push(ps, q, rq, lq);
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// full evaluation of one candidate by one warp (docs/MODEL.md §3)
+// ------------------------------------------------------------------------------------------
+// Carry-save adder: (h, l) = a + b + c  bitwise; two LOP3.
+__device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32_t b, uint32_t c)
+{
+    const uint32_t u = a ^ b;
+    h = (a & b) | (u & c);
+    l = u ^ c;
+}
+
+// Bit-sliced per-lane column counter: planes 1,2,4 + NPH high planes (8,16,...).  Inputs are
+// pushed in blocks of 8 (Harley-Seal): ~2.5 LOP3 per pushed word.
+template <int W, int NPH> struct ColCounter {
+    uint32_t ones[W], twos[W], fours[W], hi[NPH][W];
+    uint32_t hold[W], twosA[W], foursA[W];
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            ones[t] = twos[t] = fours[t] = hold[t] = twosA[t] = foursA[t] = 0;
+#pragma unroll
+            for (int k = 0; k < NPH; ++k) hi[k][t] = 0;
+        }
+    }
+    template <int I> __device__ __forceinline__ void push(const uint32_t (&x)[W])
+    {
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            if constexpr ((I & 1) == 0) {
+                hold[t] = x[t];
+            } else {
+                uint32_t t2;
+                csa(t2, ones[t], ones[t], hold[t], x[t]);
+                if constexpr ((I & 3) == 1) {
+                    twosA[t] = t2;
+                } else {
+                    uint32_t t4;
+                    csa(t4, twos[t], twos[t], twosA[t], t2);
+                    if constexpr (I == 3) {
+                        foursA[t] = t4;
+                    } else {
+                        uint32_t t8;
+                        csa(t8, fours[t], fours[t], foursA[t], t4);
+#pragma unroll
+                        for (int k = 0; k < NPH; ++k) {
+                            const uint32_t cy = hi[k][t] & t8;
+                            hi[k][t] ^= t8;
+                            t8 = cy;
+                        }
+                    }
+                }
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ uint32_t bytecounts(uint32_t x)
+{
+    uint32_t c = x - ((x >> 1) & 0x55555555u);
+    c = (c & 0x33333333u) + ((c >> 2) & 0x33333333u);
+    return (c + (c >> 4)) & 0x0F0F0F0Fu;
+}
+
+template <bool kShared> __device__ __forceinline__ uint4 ld128(const void *p)
+{
+    if constexpr (kShared) {
+        uint4 v;
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+        return v;
+    } else {
+        return __ldg(reinterpret_cast<const uint4 *>(p));
+    }
+}
+template <bool kShared> __device__ __forceinline__ uint32_t ld32(const void *p)
+{
+    if constexpr (kShared) {
+        uint32_t v;
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+        return v;
+    } else {
+        return __ldg(reinterpret_cast<const uint32_t *>(p));
+    }
+}
+
+__device__ __forceinline__ uint32_t comp(const uint4 &v, int i)
+{
+    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+}
+
+// Per-row terms: C1 (replica count), C7 (per-rack spread) and the rack-total accumulators, by
+// SWAR over the rack-aligned slot fields (S = 8: bytes, 16: halfwords, >= 32: whole words).
+template <int W>
+__device__ __forceinline__ int row_rack_terms(const uint32_t (&x)[W], int log2S, int R, int lo, int hi,
+                                              int RF, uint32_t (&racc)[W])
+{
+    int n = 0, pen = 0;
+    if (log2S == 3) {
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const uint32_t c = bytecounts(x[t]);
+            const int pc = __popc(x[t]);
+            racc[t] += c;
+            n += pc;
+            if (hi == 1) {
+                pen += pc - __popc((c + 0x7F7F7F7Fu) & 0x80808080u);
+            } else {
+                const uint32_t dd = (c | 0x80808080u) - (uint32_t)hi * 0x01010101u;
+                const uint32_t m = ((dd >> 7) & 0x01010101u) * 0xFFu;
+                pen += (int)(((dd & m & 0x7F7F7F7Fu) * 0x01010101u) >> 24);
+            }
+            if (lo > 0) {
+                const int nv = min(max(R - 4 * t, 0), 4);
+                const uint32_t vm = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
+                const uint32_t dd = (((uint32_t)lo * 0x01010101u) | 0x80808080u) - c;
+                const uint32_t m = ((dd >> 7) & 0x01010101u) * 0xFFu;
+                pen += (int)(((dd & m & 0x7F7F7F7Fu & vm) * 0x01010101u) >> 24);
+            }
+        }
+    } else if (log2S == 4) {
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            uint32_t c = bytecounts(x[t]);
+            c = (c + (c >> 8)) & 0x00FF00FFu;
+            racc[t] += c;
+            n += __popc(x[t]);
+            {
+                const uint32_t dd = (c | 0x80008000u) - (uint32_t)hi * 0x00010001u;
+                const uint32_t m = ((dd >> 15) & 0x00010001u) * 0xFFFFu;
+                pen += (int)(((dd & m & 0x7FFF7FFFu) * 0x00010001u) >> 16);
+            }
+            if (lo > 0) {
+                const int nv = min(max(R - 2 * t, 0), 2);
+                const uint32_t vm = nv >= 2 ? 0xFFFFFFFFu : (nv == 1 ? 0xFFFFu : 0u);
+                const uint32_t dd = (((uint32_t)lo * 0x00010001u) | 0x80008000u) - c;
+                const uint32_t m = ((dd >> 15) & 0x00010001u) * 0xFFFFu;
+                pen += (int)(((dd & m & 0x7FFF7FFFu & vm) * 0x00010001u) >> 16);
+            }
+        }
+    } else {
+        const int wpr = 1 << (log2S - 5);
+        int c = 0;
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const int pc = __popc(x[t]);
+            racc[t] += (uint32_t)pc;
+            n += pc;
+            c += pc;
+            if (((t + 1) & (wpr - 1)) == 0) {
+                if ((t >> (log2S - 5)) < R) pen += max(c - hi, 0) + max(lo - c, 0);
+                c = 0;
+            }
+        }
+    }
+    return abs(n - RF) + pen;
+}
+
+constexpr int kPlanes = 13;                 // 8 per-lane planes + 5 butterfly steps: counts < 8192
+
+template <int W, int NPH>
+__device__ __forceinline__ void load_planes(uint32_t (&pl)[kPlanes], const ColCounter<W, NPH> &c, int t)
+{
+    pl[0] = c.ones[t]; pl[1] = c.twos[t]; pl[2] = c.fours[t];
+#pragma unroll
+    for (int k = 0; k < NPH; ++k) pl[3 + k] = c.hi[k][t];
+#pragma unroll
+    for (int k = 3 + NPH; k < kPlanes; ++k) pl[k] = 0;
+}
+
+// C3 / C4: broker columns.  pl[i] = bit-sliced per-lane counts of NI 32-column items (items
+// < nA are checked against bndA, the others against bndB; item i covers slots 32*(i mod nA)..).
+// Reduce-scatter over lanes: log2(NI) halving steps (a lane keeps half of its items and adds the
+// partner's copy of them), then plain butterfly steps; every lane ends with ONE item summed over
+// all 32 lanes and checks NI of its 32 columns against the bounds.  Returns this lane's share
+// of the violation.
+template <int NI, int NP0>
+__device__ __forceinline__ int column_violation(uint32_t (&pl)[NI][kPlanes], int lane, int nA,
+                                                const uint32_t *bndA, const uint32_t *bndB)
+{
+    static_assert(NP0 + 5 <= kPlanes, "plane budget");
+    int item = 0;
+    int nact = NI;
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+        const int mask = 1 << step;
+        const bool up = (lane >> step) & 1;
+        const int np = NP0 + step;                        // planes held before this step
+        if ((NI >> step) >= 2) {
+            const int half = NI >> (step + 1);
+            item += up ? half : 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                uint32_t carry = 0;
+#pragma unroll
+                for (int k = 0; k < np; ++k) {
+                    const uint32_t a = pl[i][k], b = pl[i + half][k];
+                    const uint32_t keep = up ? b : a, send = up ? a : b;
+                    const uint32_t rcv = __shfl_xor_sync(0xFFFFFFFFu, send, mask);
+                    uint32_t h, l;
+                    csa(h, l, keep, rcv, carry);
+                    pl[i][k] = l;
+                    carry = h;
+                }
+                pl[i][np] = carry;
+            }
+            nact = half;
+        } else {
+            uint32_t carry = 0;
+#pragma unroll
+            for (int k = 0; k < np; ++k) {
+                const uint32_t rcv = __shfl_xor_sync(0xFFFFFFFFu, pl[0][k], mask);
+                uint32_t h, l;
+                csa(h, l, pl[0][k], rcv, carry);
+                pl[0][k] = l;
+                carry = h;
+            }
+            pl[0][np] = carry;
+        }
+    }
+    (void)nact;
+    constexpr int nsplit = (NI == 1) ? 0 : (NI == 2) ? 1 : (NI == 4) ? 2 : (NI == 8) ? 3 : 4;
+    constexpr int NPF = NP0 + 5;
+    const int t0 = (lane >> nsplit) * NI;                 // first of this lane's NI columns
+    const bool second = item >= nA;
+    const int word = second ? item - nA : item;
+    const uint32_t *bnd = second ? bndB : bndA;
+    uint32_t sh[NPF];
+#pragma unroll
+    for (int k = 0; k < NPF; ++k) sh[k] = pl[0][k] >> t0;
+    int viol = 0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        uint32_t c = 0;
+#pragma unroll
+        for (int k = 0; k < NPF; ++k) c |= ((sh[k] >> i) & 1u) << k;
+        const uint32_t b = bnd[word * 32 + t0 + i];
+        const int lo = (int)(b & 0xFFFFu), hi = (int)(b >> 16);
+        viol += max((int)c - hi, 0) + max(lo - (int)c, 0);
+    }
+    return viol;
+}
+
+// Evaluates candidate = base + patches.  kShared: base/weights are in shared memory.
+// Outputs (same value in every lane): total violation amount and objective.
+template <int W, int NPH, bool kShared>
+__device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
+                               const uint32_t *swT, const Consts *cs, const PatchSet &ps,
+                               const uint32_t *prow, int lane, int &viol_out, int &obj_out)
+{
+    const int P = d.P, Ppad = d.Ppad, R = d.R, RF = d.RF, log2S = d.log2S;
+    const int lo7 = d.ppr_lo, hi7 = d.ppr_hi;
+    ColCounter<W, NPH> rc, lc;
+    rc.clear();
+    lc.clear();
+    uint32_t racc[W], rwide[2 * W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) { racc[t] = 0; rwide[2 * t] = rwide[2 * t + 1] = 0; }
+    int viol = 0, obj = 0;
+
+    const int ntiles = Ppad / kTileRows;                 // even: Ppad is a multiple of 256
+    for (int u0 = 0; u0 < ntiles; u0 += 2) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int u = u0 + half;
+            const int r0 = u * kTileRows + lane * kRowsPerLane;
+            uint4 xv[W], sv[4];
+#pragma unroll
+            for (int t = 0; t < W; ++t) xv[t] = ld128<kShared>(bitsT + (size_t)t * Ppad + r0);
+            uint32_t ld4 = ld32<kShared>(leader + r0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sv[k] = ld128<kShared>(swT + (size_t)k * Ppad + r0);
+            // rare: a patched row lives in this tile
+#pragma unroll
+            for (int i = 0; i < kMaxOps; ++i) {
+                const int pp = ps.p[i];                   // -1 when unused: never matches a tile
+                const uint32_t pl = ps.ld[i];
+                if ((pp >> 7) == u && ((pp & 127) >> 2) == lane) {
+                    const int rr = pp & 3;
+#pragma unroll
+                    for (int t = 0; t < W; ++t) {
+                        const uint32_t v = prow[i * W + t];
+                        if (rr == 0) xv[t].x = v; else if (rr == 1) xv[t].y = v;
+                        else if (rr == 2) xv[t].z = v; else xv[t].w = v;
+                    }
+                    ld4 = (ld4 & ~(0xFFu << (8 * rr))) | (pl << (8 * rr));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+                uint32_t x[W], oh[W];
+#pragma unroll
+                for (int t = 0; t < W; ++t) x[t] = comp(xv[t], i);
+                const uint32_t ld = (ld4 >> (8 * i)) & 0xFFu;
+                const bool valid = (r0 + i) < P;
+                // leader one-hot restricted to the row: C2/C5 by construction of the encoding
+                const uint32_t ldbit = 1u << (ld & 31);
+                uint32_t any = 0;
+#pragma unroll
+                for (int t = 0; t < W; ++t) { oh[t] = ((int)(ld >> 5) == t) ? (x[t] & ldbit) : 0u; any |= oh[t]; }
+                int rv = row_rack_terms<W>(x, log2S, R, lo7, hi7, RF, racc) + (any ? 0 : 1);
+                viol += valid ? rv : 0;
+                // objective: sparse weight entries of this partition
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t e = comp(sv[k], i);
+                    const uint32_t slot = e & 0xFFu;
+                    const uint32_t xw = row_word<W>(x, (int)(slot >> 5));
+                    const bool bit = (xw >> (slot & 31)) & 1u;
+                    const uint32_t w = (slot == ld) ? (e >> 20) : ((e >> 8) & 0xFFFu);
+                    obj += bit ? (int)w : 0;
+                }
+                if (d.dense && valid) {
+                    const uint32_t *wrow = d.dense_w + (size_t)(r0 + i) * d.NS;
+#pragma unroll
+                    for (int t = 0; t < W; ++t) {
+                        for (uint32_t m = x[t]; m; m &= m - 1) {
+                            const int s = t * 32 + __ffs(m) - 1;
+                            if (s < d.NS) {
+                                const uint32_t w = __ldg(wrow + s);
+                                obj += (s == (int)ld) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
+                            }
+                        }
+                    }
+                }
+                if (half == 0) {
+                    if (i == 0) { rc.template push<0>(x); lc.template push<0>(oh); }
+                    if (i == 1) { rc.template push<1>(x); lc.template push<1>(oh); }
+                    if (i == 2) { rc.template push<2>(x); lc.template push<2>(oh); }
+                    if (i == 3) { rc.template push<3>(x); lc.template push<3>(oh); }
+                } else {
+                    if (i == 0) { rc.template push<4>(x); lc.template push<4>(oh); }
+                    if (i == 1) { rc.template push<5>(x); lc.template push<5>(oh); }
+                    if (i == 2) { rc.template push<6>(x); lc.template push<6>(oh); }
+                    if (i == 3) { rc.template push<7>(x); lc.template push<7>(oh); }
+                }
+            }
+        }
+        if (log2S == 3) {            // widen the byte-packed rack accumulators before they can overflow
+#pragma unroll
+            for (int t = 0; t < W; ++t) {
+                rwide[2 * t] += racc[t] & 0x00FF00FFu;
+                rwide[2 * t + 1] += (racc[t] >> 8) & 0x00FF00FFu;
+                racc[t] = 0;
+            }
+        }
+    }
+
+    // ---- C6: rack totals = sum over lanes of the per-lane rack accumulators
+    int pen_u = 0;                                        // warp-uniform part of the violation
+    {
+        constexpr int kMaxR = 4 * W;
+#pragma unroll
+        for (int r = 0; r < kMaxR; ++r) {
+            if (r < R) {
+                uint32_t v = 0;
+                if (log2S == 3) {
+                    v = (rwide[2 * (r >> 2) + (r & 1)] >> (16 * ((r >> 1) & 1))) & 0xFFFFu;
+                } else if (log2S == 4) {
+                    if (r < 2 * W) v = (racc[(r >> 1) < W ? (r >> 1) : 0] >> (16 * (r & 1))) & 0xFFFFu;
+                } else {
+                    const int sh = log2S - 5;
+#pragma unroll
+                    for (int t = 0; t < W; ++t) v += ((t >> sh) == r) ? racc[t] : 0u;
+                }
+                const int tot = __reduce_add_sync(0xFFFFFFFFu, (int)v);
+                pen_u += max(tot - cs->rack_hi[r], 0) + max(cs->rack_lo[r] - tot, 0);
+            }
+        }
+    }
+
+    // ---- C3 / C4: broker columns.  Items 0..W-1 = replica words, W..2W-1 = leader words, each a
+    // bit-sliced per-lane count.  Reduce-scatter over lanes: log2(2W) halving steps (each lane keeps
+    // half of the items), then plain butterfly steps; every lane ends with ONE item summed over
+    // all 32 lanes and extracts 2W of its 32 columns.
+    constexpr int NP0 = 3 + NPH;
+    if constexpr (W <= 2) {
+        // both counter sets in one pass: items 0..W-1 replica words, W..2W-1 leader words
+        uint32_t pl[2 * W][kPlanes];
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            load_planes<W, NPH>(pl[t], rc, t);
+            load_planes<W, NPH>(pl[W + t], lc, t);
+        }
+        viol += column_violation<2 * W, NP0>(pl, lane, W, cs->bnd_rep, cs->bnd_ldr);
+    } else {
+        uint32_t pl[W][kPlanes];
+#pragma unroll
+        for (int t = 0; t < W; ++t) load_planes<W, NPH>(pl[t], rc, t);
+        viol += column_violation<W, NP0>(pl, lane, W, cs->bnd_rep, cs->bnd_rep);
+#pragma unroll
+        for (int t = 0; t < W; ++t) load_planes<W, NPH>(pl[t], lc, t);
+        viol += column_violation<W, NP0>(pl, lane, W, cs->bnd_ldr, cs->bnd_ldr);
+    }
+    viol_out = __reduce_add_sync(0xFFFFFFFFu, viol) + pen_u;
+    obj_out = __reduce_add_sync(0xFFFFFFFFu, obj);
+}
+
+}  // namespace kao

@@ -1,0 +1,600 @@
+// kao_engine.cu — kernels, device session and the C ABI (include/kao.h) of libkao.so.
+//
+// Replaces the reference's "emit the LP of README.md:139-185, run lp_solve, read the binaries
+// back" step (/root/reference/README.md:135-136) with a GPU candidate search over the same model.
+// There is no CPU fallback: every entry point fails with KAO_E_CUDA when no device is usable.
+#include "kao_device.cuh"
+#include "kao_host.hpp"
+#include "../../include/kao.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace kao;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA bulk copy (SASS: SYNCS / UBLKCP)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory plan of the search kernel
+// ------------------------------------------------------------------------------------------
+struct SmemPlan {
+    uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, total;
+};
+static SmemPlan make_plan(int W, int Ppad, int warps)
+{
+    SmemPlan s;
+    uint32_t o = 0;
+    s.off_bits = o;   o += (uint32_t)W * Ppad * 4;
+    s.off_sw = o;     o += 4u * Ppad * 4;
+    s.off_leader = o; o += (uint32_t)Ppad;
+    s.off_consts = o; o += (uint32_t)sizeof(Consts);
+    s.off_prow = o;   o += (uint32_t)warps * kMaxOps * W * 4;
+    o = (o + 15u) & ~15u;
+    s.off_red = o;    o += (uint32_t)warps * 8;
+    s.off_bar = o;    o += 16;
+    s.total = o;
+    return s;
+}
+
+// One search round (or a slice of it): every warp walks candidate indices idx_lo + gw, + stride ...,
+// generates the candidate from the shared-memory base, evaluates it in full and keeps the minimum
+// packed key; the block minimum goes to *out_key with one atomicMin.  all_keys (optional)
+// receives every candidate's key (parity tests).
+template <int W, int NPH, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint32_t round_size,
+                    uint32_t idx_lo, uint32_t idx_hi, unsigned long long *out_key,
+                    unsigned long long *all_keys)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(smem + plan.off_bits);
+    uint32_t *s_sw = reinterpret_cast<uint32_t *>(smem + plan.off_sw);
+    uint8_t *s_leader = smem + plan.off_leader;
+    Consts *s_cs = reinterpret_cast<Consts *>(smem + plan.off_consts);
+    uint32_t *s_prow = reinterpret_cast<uint32_t *>(smem + plan.off_prow);
+    unsigned long long *s_red = reinterpret_cast<unsigned long long *>(smem + plan.off_red);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + plan.off_bar);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = THREADS / 32;
+
+    // stage base + tables: HBM/L2 -> shared memory with TMA bulk copies, one mbarrier
+    if (tid == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t nb = (uint32_t)W * d.Ppad * 4, ns = 4u * d.Ppad * 4, nl = (uint32_t)d.Ppad;
+        mbar_expect_tx(s_bar, nb + ns + nl + (uint32_t)sizeof(Consts));
+        bulk_g2s(s_bits, d.bitsT, nb, s_bar);
+        bulk_g2s(s_sw, d.swT, ns, s_bar);
+        bulk_g2s(s_leader, d.leader, nl, s_bar);
+        bulk_g2s(s_cs, d.consts, (uint32_t)sizeof(Consts), s_bar);
+    }
+    mbar_wait(s_bar, 0);
+
+    Gen<W> gen;
+    gen.bitsT = s_bits; gen.leader = s_leader; gen.cs = s_cs; gen.d = &d;
+    gen.prow = s_prow + warp * kMaxOps * W; gen.lane = lane;
+
+    unsigned long long best = ~0ull;
+    const uint32_t stride = gridDim.x * kWarps;
+    for (uint32_t idx = idx_lo + blockIdx.x * kWarps + warp; idx < idx_hi; idx += stride) {
+        PatchSet ps;
+        gen.run(seed, round, idx, round_size, ps);
+        __syncwarp();
+        int viol, obj;
+        eval_candidate<W, NPH, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
+        const unsigned long long key = pack_key(viol, obj, idx);
+        if (all_keys && lane == 0) all_keys[idx - idx_lo] = key;
+        best = key < best ? key : best;
+        __syncwarp();
+    }
+    if (lane == 0) s_red[warp] = best;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = lane < kWarps ? s_red[lane] : ~0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long w = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            v = w < v ? w : v;
+        }
+        if (lane == 0 && v != ~0ull) atomicMin(out_key, v);
+    }
+}
+
+// Winner of a round becomes the base: re-materialise its patches from (seed, round, index), write
+// the patched rows to the base in HBM, then rebuild the displaced list D.  One block.
+template <int W>
+__global__ void __launch_bounds__(1024, 1)
+apply_winner_kernel(Params d, uint64_t seed, uint32_t round, uint32_t round_size,
+                    const unsigned long long *key, int regen_only)
+{
+    __shared__ uint32_t s_prow[kMaxOps * W];
+    __shared__ int s_cnt[33], s_cntL[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0 && !regen_only) {
+        const unsigned long long k = *key;
+        if (k != ~0ull) {
+            Gen<W> gen;
+            gen.bitsT = d.bitsT; gen.leader = d.leader; gen.cs = d.consts; gen.d = &d;
+            gen.prow = s_prow; gen.lane = lane;
+            PatchSet ps;
+            gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps);
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < kMaxOps; ++i) {
+                    if (i < ps.n) {
+                        for (int t = 0; t < W; ++t) d.bitsT[(size_t)t * d.Ppad + ps.p[i]] = s_prow[i * W + t];
+                        d.leader[ps.p[i]] = (uint8_t)ps.ld[i];
+                    }
+                }
+            }
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // D  = ascending list of partitions whose row lacks one of its home slots
+    // DL = ascending list of partitions that hold their first home broker but are led from elsewhere
+    int baseD = 0, baseL = 0;
+    for (int p0 = 0; p0 < d.P; p0 += 1024) {
+        const int p = p0 + tid;
+        bool miss = false, ldis = false;
+        if (p < d.P) {
+            const uint32_t h4 = d.homeT[p];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int hs = (h4 >> (8 * i)) & 0xFF;
+                if (hs != 0xFF) {
+                    const bool has = (d.bitsT[(size_t)(hs >> 5) * d.Ppad + p] >> (hs & 31)) & 1u;
+                    miss |= !has;
+                    if (i == 0) ldis = has && ((int)d.leader[p] != hs);
+                }
+            }
+        }
+        const uint32_t mD = __ballot_sync(0xFFFFFFFFu, miss);
+        const uint32_t mL = __ballot_sync(0xFFFFFFFFu, ldis);
+        if (lane == 0) { s_cnt[warp] = __popc(mD); s_cntL[warp] = __popc(mL); }
+        __syncthreads();
+        if (warp == 0) {
+            int c = s_cnt[lane], incl = c, cl = s_cntL[lane], incl2 = cl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                const int v2 = __shfl_up_sync(0xFFFFFFFFu, incl2, o);
+                if (lane >= o) { incl += v; incl2 += v2; }
+            }
+            s_cnt[lane] = incl - c;
+            s_cntL[lane] = incl2 - cl;
+            if (lane == 31) { s_cnt[32] = incl; s_cntL[32] = incl2; }
+        }
+        __syncthreads();
+        const uint32_t below = (1u << lane) - 1u;
+        if (miss) d.D[baseD + s_cnt[warp] + __popc(mD & below)] = (uint16_t)p;
+        if (ldis) d.DL[baseL + s_cntL[warp] + __popc(mL & below)] = (uint16_t)p;
+        baseD += s_cnt[32];
+        baseL += s_cntL[32];
+        __syncthreads();
+    }
+    if (tid == 0) { d.nD[0] = baseD; d.nD[1] = baseL; }
+}
+
+// Explicit population: one warp per candidate, rows read straight from HBM (coalesced 128-bit
+// loads), same evaluator.  cand_bits [n][W][Ppad], cand_leader [n][Ppad].
+template <int W, int NPH>
+__global__ void __launch_bounds__(256)
+eval_batch_kernel(Params d, const uint32_t *cand_bits, const uint8_t *cand_leader, int n,
+                  long long *viol_out, long long *obj_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n) return;
+    PatchSet ps;
+    ps.n = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
+    int viol, obj;
+    eval_candidate<W, NPH, false>(d, cand_bits + (size_t)w * W * d.Ppad, cand_leader + (size_t)w * d.Ppad,
+                                  d.swT, d.consts, ps, nullptr, lane, viol, obj);
+    if (lane == 0) { viol_out[w] = viol; obj_out[w] = obj; }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(KAO_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+struct kao_handle {
+    HostModel hm;               // layout, tables, host copy of problem data
+    int device = 0;
+    int sms = 0;
+    Params prm{};
+    SmemPlan plan{};
+    int threads = 0, grid = 0;
+    // device buffers
+    uint32_t *d_bits = nullptr; uint8_t *d_leader = nullptr; uint32_t *d_sw = nullptr;
+    uint32_t *d_dense = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
+    Consts *d_consts = nullptr; unsigned long long *d_key = nullptr; unsigned long long *d_keys = nullptr;
+    size_t keys_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+};
+
+template <int W> static constexpr int threads_for() { return W <= 2 ? 512 : 256; }
+
+template <int W>
+static cudaError_t launch_round_t(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                  uint32_t lo, uint32_t hi, unsigned long long *d_key,
+                                  unsigned long long *d_all, cudaStream_t st)
+{
+    constexpr int T = threads_for<W>();
+    auto kern = search_round_kernel<W, 5, T>;
+    static bool attr_done[64] = {};
+    if (!attr_done[h->device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done[h->device & 63] = true;
+    }
+    const uint32_t n = hi - lo;
+    const uint32_t warps = T / 32;
+    uint32_t grid = (n + warps - 1) / warps;
+    if (grid > (uint32_t)h->grid) grid = (uint32_t)h->grid;
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, T, h->plan.total, st>>>(h->prm, h->plan, seed, round, round_size, lo, hi, d_key, d_all);
+    ++h->launches;
+    return cudaGetLastError();
+}
+static cudaError_t launch_round(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                uint32_t lo, uint32_t hi, unsigned long long *d_key,
+                                unsigned long long *d_all, cudaStream_t st)
+{
+    switch (h->hm.W) {
+    case 1: return launch_round_t<1>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+    case 2: return launch_round_t<2>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+    case 4: return launch_round_t<4>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+    default: return launch_round_t<8>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+    }
+}
+static cudaError_t launch_apply(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                const unsigned long long *d_key, int regen_only, cudaStream_t st)
+{
+    switch (h->hm.W) {
+    case 1: apply_winner_kernel<1><<<1, 1024, 0, st>>>(h->prm, seed, round, round_size, d_key, regen_only); break;
+    case 2: apply_winner_kernel<2><<<1, 1024, 0, st>>>(h->prm, seed, round, round_size, d_key, regen_only); break;
+    case 4: apply_winner_kernel<4><<<1, 1024, 0, st>>>(h->prm, seed, round, round_size, d_key, regen_only); break;
+    default: apply_winner_kernel<8><<<1, 1024, 0, st>>>(h->prm, seed, round, round_size, d_key, regen_only); break;
+    }
+    ++h->launches;
+    return cudaGetLastError();
+}
+
+static int upload_base(kao_handle *h, const std::vector<uint32_t> &bitsT, const std::vector<uint8_t> &leader)
+{
+    CUDA_TRY(cudaMemcpy(h->d_bits, bitsT.data(), bitsT.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_leader, leader.data(), leader.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(launch_apply(h, 0, 0, 2, h->d_key, /*regen_only=*/1, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return KAO_OK;
+}
+
+extern "C" int kao_version(void) { return KAO_VERSION; }
+extern "C" const char *kao_last_error(void) { return g_err.c_str(); }
+
+extern "C" int kao_destroy(kao_handle *h)
+{
+    if (!h) return KAO_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_bits); cudaFree(h->d_leader); cudaFree(h->d_sw); cudaFree(h->d_dense);
+    cudaFree(h->d_home); cudaFree(h->d_D); cudaFree(h->d_DL); cudaFree(h->d_nD); cudaFree(h->d_consts);
+    cudaFree(h->d_key); cudaFree(h->d_keys);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return KAO_OK;
+}
+
+extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **out)
+{
+    if (!pb || !out) return fail(KAO_E_ARG, "null argument");
+    *out = nullptr;
+    kao_handle *h = new kao_handle();
+    std::string why;
+    if (!build_host_model(*pb, h->hm, why)) { delete h; return fail(KAO_E_ARG, why); }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        delete h;
+        return fail(KAO_E_CUDA, "no CUDA device: libkao has no CPU path");
+    }
+    if (device < 0 || device >= ndev) { delete h; return fail(KAO_E_ARG, "bad device ordinal"); }
+    h->device = device;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    h->sms = prop.multiProcessorCount;
+    const HostModel &m = h->hm;
+    const int W = m.W, Ppad = m.Ppad;
+    h->threads = W <= 2 ? 512 : 256;
+    h->plan = make_plan(W, Ppad, h->threads / 32);
+    if (h->plan.total > 227u * 1024u) {
+        kao_destroy(h);
+        return fail(KAO_E_ARG, "problem too large for the shared-memory resident search kernel");
+    }
+    h->grid = h->sms;
+    CUDA_TRY(cudaMalloc(&h->d_bits, (size_t)W * Ppad * 4));
+    CUDA_TRY(cudaMalloc(&h->d_leader, (size_t)Ppad));
+    CUDA_TRY(cudaMalloc(&h->d_sw, (size_t)4 * Ppad * 4));
+    CUDA_TRY(cudaMalloc(&h->d_home, (size_t)Ppad * 4));
+    CUDA_TRY(cudaMalloc(&h->d_D, (size_t)Ppad * 2));
+    CUDA_TRY(cudaMalloc(&h->d_DL, (size_t)Ppad * 2));
+    CUDA_TRY(cudaMalloc(&h->d_nD, 16));
+    CUDA_TRY(cudaMalloc(&h->d_consts, sizeof(Consts)));
+    CUDA_TRY(cudaMalloc(&h->d_key, 16));
+    CUDA_TRY(cudaMemset(h->d_nD, 0, 16));
+    CUDA_TRY(cudaMemset(h->d_key, 0xFF, 16));
+    if (m.dense) {
+        CUDA_TRY(cudaMalloc(&h->d_dense, m.dense_w.size() * 4));
+        CUDA_TRY(cudaMemcpy(h->d_dense, m.dense_w.data(), m.dense_w.size() * 4, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemcpy(h->d_sw, m.swT.data(), m.swT.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_home, m.homeT.data(), m.homeT.size() * 4, cudaMemcpyHostToDevice));
+    Consts cs;
+    fill_consts(m, cs);
+    CUDA_TRY(cudaMemcpy(h->d_consts, &cs, sizeof cs, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaEventCreate(&h->ev0));
+    CUDA_TRY(cudaEventCreate(&h->ev1));
+    Params &p = h->prm;
+    p.P = m.P; p.Ppad = Ppad; p.B = m.B; p.R = m.R; p.RF = m.RF; p.NS = m.NS; p.log2S = m.log2S;
+    p.ppr_lo = m.ppr_lo; p.ppr_hi = m.ppr_hi; p.dense = m.dense ? 1 : 0;
+    p.bitsT = h->d_bits; p.leader = h->d_leader; p.swT = h->d_sw; p.dense_w = h->d_dense;
+    p.homeT = h->d_home; p.D = h->d_D; p.DL = h->d_DL; p.nD = h->d_nD; p.consts = h->d_consts;
+    int rc = kao_reset(h);
+    if (rc != KAO_OK) { kao_destroy(h); return rc; }
+    *out = h;
+    return KAO_OK;
+}
+
+extern "C" int kao_reset(kao_handle *h)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<uint32_t> bitsT; std::vector<uint8_t> leader;
+    initial_base(h->hm, bitsT, leader);
+    return upload_base(h, bitsT, leader);
+}
+
+extern "C" int kao_set_base(kao_handle *h, const int32_t *replicas)
+{
+    if (!h || !replicas) return fail(KAO_E_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<uint32_t> bitsT; std::vector<uint8_t> leader;
+    encode_replicas(h->hm, replicas, bitsT, leader);
+    return upload_base(h, bitsT, leader);
+}
+
+static int eval_on_device(kao_handle *h, const uint32_t *d_bits, const uint8_t *d_leader, int n,
+                          long long *d_viol, long long *d_obj)
+{
+    const int blocks = (n * 32 + 255) / 256;
+    switch (h->hm.W) {
+    case 1: eval_batch_kernel<1, 5><<<blocks, 256>>>(h->prm, d_bits, d_leader, n, d_viol, d_obj); break;
+    case 2: eval_batch_kernel<2, 5><<<blocks, 256>>>(h->prm, d_bits, d_leader, n, d_viol, d_obj); break;
+    case 4: eval_batch_kernel<4, 5><<<blocks, 256>>>(h->prm, d_bits, d_leader, n, d_viol, d_obj); break;
+    default: eval_batch_kernel<8, 5><<<blocks, 256>>>(h->prm, d_bits, d_leader, n, d_viol, d_obj); break;
+    }
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    return KAO_OK;
+}
+
+extern "C" int kao_get_base(kao_handle *h, int32_t *replicas, int64_t *violation, int64_t *objective,
+                            int32_t *moves)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const HostModel &m = h->hm;
+    std::vector<uint32_t> bitsT((size_t)m.W * m.Ppad);
+    std::vector<uint8_t> leader((size_t)m.Ppad);
+    CUDA_TRY(cudaMemcpy(bitsT.data(), h->d_bits, bitsT.size() * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(leader.data(), h->d_leader, leader.size(), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> reps((size_t)m.P * m.RF);
+    decode_replicas(m, bitsT, leader, reps.data());
+    if (replicas) std::memcpy(replicas, reps.data(), reps.size() * 4);
+    if (moves) *moves = count_moves(m, reps.data());
+    if (violation || objective) {
+        long long *d_vo = nullptr;
+        CUDA_TRY(cudaMalloc(&d_vo, 16));
+        int rc = eval_on_device(h, h->d_bits, h->d_leader, 1, d_vo, d_vo + 1);
+        long long vo[2] = {0, 0};
+        if (rc == KAO_OK && cudaMemcpy(vo, d_vo, 16, cudaMemcpyDeviceToHost) != cudaSuccess) rc = KAO_E_CUDA;
+        cudaFree(d_vo);
+        if (rc != KAO_OK) return rc;
+        if (violation) *violation = vo[0];
+        if (objective) *objective = vo[1];
+    }
+    return KAO_OK;
+}
+
+static bool check_round_args(uint32_t round_size)
+{
+    return round_size >= 2 && round_size <= KAO_MAX_ROUND_SIZE;
+}
+
+extern "C" int kao_round_launch(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                uint32_t idx_lo, uint32_t idx_hi, uint64_t *d_key, void *stream)
+{
+    if (!h || !d_key) return fail(KAO_E_ARG, "null argument");
+    if (!check_round_args(round_size) || idx_lo > idx_hi || idx_hi > round_size)
+        return fail(KAO_E_ARG, "bad round_size / index range");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(launch_round(h, seed, round, round_size, idx_lo, idx_hi,
+                          reinterpret_cast<unsigned long long *>(d_key), nullptr, (cudaStream_t)stream));
+    return KAO_OK;
+}
+
+extern "C" int kao_round_apply(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                               const uint64_t *d_key, void *stream)
+{
+    if (!h || !d_key) return fail(KAO_E_ARG, "null argument");
+    if (!check_round_args(round_size)) return fail(KAO_E_ARG, "bad round_size");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(launch_apply(h, seed, round, round_size, reinterpret_cast<const unsigned long long *>(d_key), 0,
+                          (cudaStream_t)stream));
+    return KAO_OK;
+}
+
+extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                          uint32_t round_size, uint64_t *round_keys, double *device_ms)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    if (!check_round_args(round_size)) return fail(KAO_E_ARG, "round_size must be 2..2^24");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->keys_cap < rounds) {
+        cudaFree(h->d_keys);
+        h->d_keys = nullptr;
+        CUDA_TRY(cudaMalloc(&h->d_keys, (size_t)(rounds > 0 ? rounds : 1) * 8));
+        h->keys_cap = rounds;
+    }
+    if (rounds) CUDA_TRY(cudaMemsetAsync(h->d_keys, 0xFF, (size_t)rounds * 8, 0));
+    CUDA_TRY(cudaEventRecord(h->ev0, 0));
+    for (uint32_t t = 0; t < rounds; ++t) {
+        CUDA_TRY(launch_round(h, seed, first_round + t, round_size, 0, round_size, h->d_keys + t, nullptr, 0));
+        CUDA_TRY(launch_apply(h, seed, first_round + t, round_size, h->d_keys + t, 0, 0));
+    }
+    CUDA_TRY(cudaEventRecord(h->ev1, 0));
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    if (device_ms) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *device_ms = ms;
+    }
+    if (round_keys && rounds)
+        CUDA_TRY(cudaMemcpy(round_keys, h->d_keys, (size_t)rounds * 8, cudaMemcpyDeviceToHost));
+    return KAO_OK;
+}
+
+extern "C" int kao_candidate_keys(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                  uint32_t idx_begin, uint32_t count, uint64_t *keys)
+{
+    if (!h || !keys) return fail(KAO_E_ARG, "null argument");
+    if (!check_round_args(round_size) || idx_begin > round_size || count > round_size - idx_begin)
+        return fail(KAO_E_ARG, "bad index range");
+    if (count == 0) return KAO_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long *d_all = nullptr;
+    CUDA_TRY(cudaMalloc(&d_all, (size_t)count * 8));
+    CUDA_TRY(cudaMemset(h->d_key, 0xFF, 8));
+    cudaError_t e = launch_round(h, seed, round, round_size, idx_begin, idx_begin + count, h->d_key, d_all, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(keys, d_all, (size_t)count * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_all);
+    CUDA_TRY(e);
+    return KAO_OK;
+}
+
+extern "C" int kao_stats(kao_handle *h, uint64_t *kernel_launches, int32_t *words_per_row,
+                         int32_t *slots, int32_t *dense_weights)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    if (kernel_launches) *kernel_launches = h->launches;
+    if (words_per_row) *words_per_row = h->hm.W;
+    if (slots) *slots = h->hm.NS;
+    if (dense_weights) *dense_weights = h->hm.dense ? 1 : 0;
+    return KAO_OK;
+}
+
+extern "C" int kao_eval(const kao_problem *pb, int32_t device, const int32_t *replicas, int32_t n,
+                        int64_t *violation, int64_t *objective)
+{
+    if (!pb || !replicas || n < 0 || !violation || !objective) return fail(KAO_E_ARG, "bad argument");
+    kao_handle *h = nullptr;
+    int rc = kao_create(pb, device, &h);
+    if (rc != KAO_OK) return rc;
+    const HostModel &m = h->hm;
+    const size_t nb = (size_t)m.W * m.Ppad, nl = (size_t)m.Ppad;
+    std::vector<uint32_t> bits(nb * n), one;
+    std::vector<uint8_t> lead(nl * n), onel;
+    for (int i = 0; i < n; ++i) {
+        encode_replicas(m, replicas + (size_t)i * m.P * m.RF, one, onel);
+        std::memcpy(bits.data() + nb * i, one.data(), nb * 4);
+        std::memcpy(lead.data() + nl * i, onel.data(), nl);
+    }
+    uint32_t *d_b = nullptr; uint8_t *d_l = nullptr; long long *d_v = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (n > 0) {
+        if ((e = cudaMalloc(&d_b, bits.size() * 4)) == cudaSuccess &&
+            (e = cudaMalloc(&d_l, lead.size())) == cudaSuccess &&
+            (e = cudaMalloc(&d_v, (size_t)n * 16)) == cudaSuccess &&
+            (e = cudaMemcpy(d_b, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice)) == cudaSuccess &&
+            (e = cudaMemcpy(d_l, lead.data(), lead.size(), cudaMemcpyHostToDevice)) == cudaSuccess) {
+            rc = eval_on_device(h, d_b, d_l, n, d_v, d_v + n);
+            if (rc == KAO_OK) {
+                static_assert(sizeof(long long) == sizeof(int64_t), "abi");
+                e = cudaMemcpy(violation, d_v, (size_t)n * 8, cudaMemcpyDeviceToHost);
+                if (e == cudaSuccess) e = cudaMemcpy(objective, d_v + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
+            }
+        }
+        cudaFree(d_b); cudaFree(d_l); cudaFree(d_v);
+    }
+    kao_destroy(h);
+    if (e != cudaSuccess) return fail(KAO_E_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+
+extern "C" int kao_solve(const kao_problem *pb, const kao_options *opt, kao_result *res)
+{
+    if (!pb || !opt || !res || !res->replicas) return fail(KAO_E_ARG, "null argument");
+    const auto t0 = std::chrono::steady_clock::now();
+    kao_handle *h = nullptr;
+    int rc = kao_create(pb, opt->device, &h);
+    if (rc != KAO_OK) return rc;
+    std::vector<uint64_t> keys(opt->rounds ? opt->rounds : 1, ~0ull);
+    double dev_ms = 0;
+    rc = kao_search(h, opt->seed, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms);
+    if (rc == KAO_OK) rc = kao_get_base(h, res->replicas, &res->violation, &res->objective, &res->moves);
+    if (rc == KAO_OK) {
+        res->feasible = res->violation == 0;
+        res->key = opt->rounds ? keys[opt->rounds - 1] : ~0ull;
+        res->n_candidates = (uint64_t)opt->rounds * opt->round_size;
+        res->rounds_run = opt->rounds;
+        res->reserved = 0;
+        res->device_ms = dev_ms;
+    }
+    kao_destroy(h);
+    res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (rc != KAO_OK) return rc;
+    if (!res->feasible) { g_err = "no candidate satisfying C1..C7 was found"; return KAO_INFEASIBLE; }
+    return KAO_OK;
+}

@@ -1,0 +1,245 @@
+// kao_host.hpp — host-side preparation of a kao_problem for the device engine: validation,
+// rack-aligned slot layout (docs/MODEL.md §2), weight-table compaction, bounds in slot space,
+// the initial base (docs/MODEL.md §4) and replica-list <-> bit-plane conversion.
+// Model citations: /root/reference/README.md:139-185.
+#pragma once
+#include "../../include/kao.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace kao {
+
+struct HostModel {
+    int P = 0, B = 0, R = 0, RF = 0, RFcur = 0;
+    int S = 0, log2S = 0, NS = 0, W = 0, Ppad = 0;
+    int ppr_lo = 0, ppr_hi = 0;
+    bool dense = false;
+    std::vector<int> slot_of_broker, broker_of_slot, slot_of_order, order_of_slot;
+    std::vector<uint8_t> rack_of;
+    std::vector<int32_t> cur;                 // [P*RFcur]
+    std::vector<int32_t> rack_lo, rack_hi;
+    std::vector<uint32_t> bnd_rep, bnd_ldr;   // [256] lo | hi << 16 in slot space
+    std::vector<uint32_t> swT;                // [4][Ppad]
+    std::vector<uint32_t> dense_w;            // [P][NS] when dense
+    std::vector<uint32_t> homeT;              // [Ppad]
+};
+
+inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &why)
+{
+    auto bad = [&](const char *s) { why = s; return false; };
+    if (pb.P < 1 || pb.P > 8160) return bad("P must be 1..8160");
+    if (pb.B < 2 || pb.B > KAO_MAX_SLOTS) return bad("B must be 2..256");
+    if (pb.R < 1 || pb.R > KAO_MAX_RACKS) return bad("R must be 1..32");
+    if (pb.RF < 1 || pb.RF > KAO_MAX_RF || pb.RF >= pb.B) return bad("RF must be 1..8 and < B");
+    if (pb.RFcur < 1 || pb.RFcur > 64) return bad("RFcur must be 1..64");
+    if (!pb.rack_of || !pb.wF || !pb.wL || !pb.rep_lo || !pb.rep_hi || !pb.ldr_lo || !pb.ldr_hi ||
+        !pb.rack_lo || !pb.rack_hi || !pb.cur)
+        return bad("null table pointer");
+    if (pb.ppr_lo < 0 || pb.ppr_lo > pb.ppr_hi || pb.ppr_hi > 127) return bad("bad per-partition-per-rack bounds");
+    m.P = pb.P; m.B = pb.B; m.R = pb.R; m.RF = pb.RF; m.RFcur = pb.RFcur;
+    m.ppr_lo = pb.ppr_lo; m.ppr_hi = pb.ppr_hi;
+    m.rack_of.assign(pb.rack_of, pb.rack_of + pb.B);
+    std::vector<int> size(pb.R, 0);
+    for (int b = 0; b < pb.B; ++b) {
+        if (m.rack_of[b] >= pb.R) return bad("rack_of entry out of range");
+        ++size[m.rack_of[b]];
+    }
+    // rack-aligned slots: slot = rack * S + rank in rack, S = pow2 >= max(8, largest rack)
+    int S = 8, lg = 3;
+    const int largest = *std::max_element(size.begin(), size.end());
+    while (S < largest) { S <<= 1; ++lg; }
+    m.S = S; m.log2S = lg; m.NS = pb.R * S;
+    if (m.NS > KAO_MAX_SLOTS) return bad("racks * pow2ceil(max(8, largest rack)) exceeds 256 slots");
+    int W = 1;
+    while (W * 32 < m.NS) W <<= 1;
+    m.W = W;
+    m.Ppad = (pb.P + 255) / 256 * 256;
+    m.slot_of_broker.assign(pb.B, -1);
+    m.broker_of_slot.assign(256, -1);
+    m.slot_of_order.assign(256, 0);
+    m.order_of_slot.assign(256, -1);
+    {
+        std::vector<int> rank(pb.R, 0);
+        for (int b = 0; b < pb.B; ++b) {
+            const int s = m.rack_of[b] * S + rank[m.rack_of[b]]++;
+            m.slot_of_broker[b] = s;
+            m.broker_of_slot[s] = b;
+        }
+        int o = 0;
+        for (int s = 0; s < m.NS; ++s)
+            if (m.broker_of_slot[s] >= 0) { m.slot_of_order[o] = s; m.order_of_slot[s] = o; ++o; }
+    }
+    // bounds, slot space; padding slots keep [0,0] so a replica there violates C3
+    m.bnd_rep.assign(256, 0);
+    m.bnd_ldr.assign(256, 0);
+    for (int b = 0; b < pb.B; ++b) {
+        if (pb.rep_lo[b] < 0 || pb.rep_lo[b] > pb.rep_hi[b] || pb.rep_hi[b] > 65535 ||
+            pb.ldr_lo[b] < 0 || pb.ldr_lo[b] > pb.ldr_hi[b] || pb.ldr_hi[b] > 65535)
+            return bad("per-broker bounds must satisfy 0 <= lo <= hi <= 65535");
+        m.bnd_rep[m.slot_of_broker[b]] = (uint32_t)pb.rep_lo[b] | ((uint32_t)pb.rep_hi[b] << 16);
+        m.bnd_ldr[m.slot_of_broker[b]] = (uint32_t)pb.ldr_lo[b] | ((uint32_t)pb.ldr_hi[b] << 16);
+    }
+    m.rack_lo.assign(pb.rack_lo, pb.rack_lo + pb.R);
+    m.rack_hi.assign(pb.rack_hi, pb.rack_hi + pb.R);
+    for (int r = 0; r < pb.R; ++r)
+        if (m.rack_lo[r] < 0 || m.rack_lo[r] > m.rack_hi[r]) return bad("rack bounds must satisfy 0 <= lo <= hi");
+    m.cur.assign(pb.cur, pb.cur + (size_t)pb.P * pb.RFcur);
+    for (int32_t &b : m.cur) if (b < 0 || b >= pb.B) b = -1;
+    // weights: at most 4 non-zero cells per partition and 12-bit values -> packed entries staged
+    // in shared memory; anything else -> dense table in HBM
+    uint32_t maxw = 0;
+    bool sparse_ok = true;
+    for (int p = 0; p < pb.P && sparse_ok; ++p) {
+        int nnz = 0;
+        for (int b = 0; b < pb.B; ++b) {
+            const uint32_t f = pb.wF[(size_t)p * pb.B + b], l = pb.wL[(size_t)p * pb.B + b];
+            if (f | l) ++nnz;
+            if (f > 4095 || l > 4095) sparse_ok = false;
+        }
+        if (nnz > 4) sparse_ok = false;
+    }
+    for (size_t i = 0; i < (size_t)pb.P * pb.B; ++i) maxw = std::max<uint32_t>(maxw, std::max(pb.wF[i], pb.wL[i]));
+    if ((uint64_t)pb.P * pb.RF * maxw > 0xFFFFFFull) return bad("objective range exceeds 24 bits");
+    m.dense = !sparse_ok;
+    m.swT.assign((size_t)4 * m.Ppad, 0);
+    if (m.dense) {
+        m.dense_w.assign((size_t)pb.P * m.NS, 0);
+        for (int p = 0; p < pb.P; ++p)
+            for (int b = 0; b < pb.B; ++b)
+                m.dense_w[(size_t)p * m.NS + m.slot_of_broker[b]] =
+                    (uint32_t)pb.wF[(size_t)p * pb.B + b] | ((uint32_t)pb.wL[(size_t)p * pb.B + b] << 16);
+    } else {
+        for (int p = 0; p < pb.P; ++p) {
+            int k = 0;
+            for (int b = 0; b < pb.B; ++b) {
+                const uint32_t f = pb.wF[(size_t)p * pb.B + b], l = pb.wL[(size_t)p * pb.B + b];
+                if (f | l) m.swT[(size_t)k++ * m.Ppad + p] = (uint32_t)m.slot_of_broker[b] | (f << 8) | (l << 20);
+            }
+        }
+    }
+    // home slots: the first four surviving entries of cur[p]
+    m.homeT.assign((size_t)m.Ppad, 0xFFFFFFFFu);
+    for (int p = 0; p < pb.P; ++p) {
+        uint32_t h = 0xFFFFFFFFu;
+        for (int i = 0; i < pb.RFcur && i < 4; ++i) {
+            const int b = m.cur[(size_t)p * pb.RFcur + i];
+            if (b >= 0) h = (h & ~(0xFFu << (8 * i))) | ((uint32_t)m.slot_of_broker[b] << (8 * i));
+        }
+        m.homeT[p] = h;
+    }
+    return true;
+}
+
+// word-major bit-plane helpers
+struct Plane {
+    const HostModel &m;
+    std::vector<uint32_t> &bitsT;
+    bool has(int p, int s) const { return (bitsT[(size_t)(s >> 5) * m.Ppad + p] >> (s & 31)) & 1u; }
+    void set(int p, int s) { bitsT[(size_t)(s >> 5) * m.Ppad + p] |= 1u << (s & 31); }
+};
+
+// docs/MODEL.md §4: keep what survives of cur (order kept, leader = first survivor, tail dropped
+// beyond RF), then complete short rows greedily: fewest replicas of p in the rack, then least
+// loaded broker, then lowest dense index.
+inline void initial_base(const HostModel &m, std::vector<uint32_t> &bitsT, std::vector<uint8_t> &leader)
+{
+    bitsT.assign((size_t)m.W * m.Ppad, 0);
+    leader.assign((size_t)m.Ppad, 0xFF);
+    Plane pl{m, bitsT};
+    std::vector<int> load(m.B, 0), count(m.P, 0);
+    for (int p = 0; p < m.P; ++p) {
+        for (int i = 0; i < m.RFcur && count[p] < m.RF; ++i) {
+            const int b = m.cur[(size_t)p * m.RFcur + i];
+            if (b < 0 || pl.has(p, m.slot_of_broker[b])) continue;
+            pl.set(p, m.slot_of_broker[b]);
+            ++load[b];
+            if (count[p]++ == 0) leader[p] = (uint8_t)m.slot_of_broker[b];
+        }
+    }
+    std::vector<int> in_rack(m.R);
+    for (int p = 0; p < m.P; ++p) {
+        while (count[p] < m.RF) {
+            std::fill(in_rack.begin(), in_rack.end(), 0);
+            for (int b = 0; b < m.B; ++b) if (pl.has(p, m.slot_of_broker[b])) ++in_rack[m.rack_of[b]];
+            int best = -1;
+            for (int b = 0; b < m.B; ++b) {
+                if (pl.has(p, m.slot_of_broker[b])) continue;
+                if (best < 0 ||
+                    std::make_pair(in_rack[m.rack_of[b]], load[b]) < std::make_pair(in_rack[m.rack_of[best]], load[best]))
+                    best = b;
+            }
+            pl.set(p, m.slot_of_broker[best]);
+            ++load[best];
+            ++count[p];
+            if (leader[p] == 0xFF) leader[p] = (uint8_t)m.slot_of_broker[best];
+        }
+    }
+}
+
+// replica lists (dense indices, leader first, -1 padded; README.md:52-63) -> bit-plane
+inline void encode_replicas(const HostModel &m, const int32_t *replicas, std::vector<uint32_t> &bitsT,
+                            std::vector<uint8_t> &leader)
+{
+    bitsT.assign((size_t)m.W * m.Ppad, 0);
+    leader.assign((size_t)m.Ppad, 0xFF);
+    Plane pl{m, bitsT};
+    for (int p = 0; p < m.P; ++p) {
+        bool have = false;
+        for (int i = 0; i < m.RF; ++i) {
+            const int b = replicas[(size_t)p * m.RF + i];
+            if (b < 0 || b >= m.B) continue;
+            pl.set(p, m.slot_of_broker[b]);
+            if (!have) { leader[p] = (uint8_t)m.slot_of_broker[b]; have = true; }
+        }
+    }
+}
+
+// bit-plane -> replica lists: leader first, followers by ascending dense index (README.md:65-78, :88)
+inline void decode_replicas(const HostModel &m, std::vector<uint32_t> &bitsT, const std::vector<uint8_t> &leader,
+                            int32_t *replicas)
+{
+    Plane pl{m, bitsT};
+    for (int p = 0; p < m.P; ++p) {
+        int32_t *out = replicas + (size_t)p * m.RF;
+        std::fill(out, out + m.RF, -1);
+        int n = 0, lb = -1;
+        const int ld = leader[p];
+        if (ld < m.W * 32 && pl.has(p, ld) && m.broker_of_slot[ld] >= 0) out[n++] = lb = m.broker_of_slot[ld];
+        for (int b = 0; b < m.B && n < m.RF; ++b)
+            if (b != lb && pl.has(p, m.slot_of_broker[b])) out[n++] = b;
+    }
+}
+
+// replicas placed on a broker that did not hold the partition (data that must be copied)
+inline int count_moves(const HostModel &m, const int32_t *replicas)
+{
+    int moves = 0;
+    for (int p = 0; p < m.P; ++p)
+        for (int i = 0; i < m.RF; ++i) {
+            const int b = replicas[(size_t)p * m.RF + i];
+            if (b < 0) continue;
+            bool had = false;
+            for (int k = 0; k < m.RFcur; ++k) had |= (m.cur[(size_t)p * m.RFcur + k] == b);
+            moves += had ? 0 : 1;
+        }
+    return moves;
+}
+
+inline void fill_consts(const HostModel &m, Consts &cs)
+{
+    for (int s = 0; s < 256; ++s) {
+        cs.bnd_rep[s] = m.bnd_rep[s];
+        cs.bnd_ldr[s] = m.bnd_ldr[s];
+        cs.slot_of_order[s] = (uint8_t)m.slot_of_order[s];
+        cs.order_of_slot[s] = m.order_of_slot[s] < 0 ? 0xFF : (uint8_t)m.order_of_slot[s];
+    }
+    for (int r = 0; r < 32; ++r) {
+        cs.rack_lo[r] = r < m.R ? m.rack_lo[r] : 0;
+        cs.rack_hi[r] = r < m.R ? m.rack_hi[r] : 0;
+    }
+}
+
+}  // namespace kao

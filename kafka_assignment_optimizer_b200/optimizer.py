@@ -1,0 +1,217 @@
+"""ctypes binding of ``libkao.so`` (include/kao.h) and the Python mirror of the reference's
+operator surface: assignment JSON + broker list + rack map in, reassignment JSON out
+(/root/reference/README.md:52-63 -> :67-78).  No CPU path: a missing library or GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import os
+from typing import Optional
+
+import numpy as np
+
+from .problem import (Problem, build_problem, parse_assignment_json, parse_broker_list, parse_rack_map,
+                      reassignment_json)
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkao.so")
+KAO_OK, KAO_INFEASIBLE = 0, 1
+
+
+class KaoError(RuntimeError):
+    pass
+
+
+class _KaoProblem(C.Structure):
+    _fields_ = [("P", C.c_int32), ("B", C.c_int32), ("R", C.c_int32), ("RF", C.c_int32),
+                ("RFcur", C.c_int32), ("rack_of", C.c_void_p), ("wF", C.c_void_p), ("wL", C.c_void_p),
+                ("rep_lo", C.c_void_p), ("rep_hi", C.c_void_p), ("ldr_lo", C.c_void_p),
+                ("ldr_hi", C.c_void_p), ("rack_lo", C.c_void_p), ("rack_hi", C.c_void_p),
+                ("ppr_lo", C.c_int32), ("ppr_hi", C.c_int32), ("cur", C.c_void_p)]
+
+
+class _KaoOptions(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("rounds", C.c_uint32), ("round_size", C.c_uint32),
+                ("device", C.c_int32), ("flags", C.c_uint32)]
+
+
+class _KaoResult(C.Structure):
+    _fields_ = [("replicas", C.c_void_p), ("objective", C.c_int64), ("violation", C.c_int64),
+                ("moves", C.c_int32), ("feasible", C.c_int32), ("key", C.c_uint64),
+                ("n_candidates", C.c_uint64), ("rounds_run", C.c_uint32), ("reserved", C.c_uint32),
+                ("device_ms", C.c_double), ("total_ms", C.c_double)]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libkao.so from the package directory.  Raises KaoError if it has not been built
+    (``python -c 'import __graft_entry__ as g; g.build()'`` or ``make -C .../csrc``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise KaoError("libkao.so is not built (%s); there is no CPU fallback" % _LIB_PATH)
+        lib = C.CDLL(_LIB_PATH)
+        lib.kao_last_error.restype = C.c_char_p
+        lib.kao_version.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def _check(rc, allow_infeasible=False):
+    if rc == KAO_OK or (allow_infeasible and rc == KAO_INFEASIBLE):
+        return rc
+    raise KaoError("libkao error %d: %s" % (rc, load_library().kao_last_error().decode()))
+
+
+def unpack_key(key: int):
+    """packed key -> (violation, objective, index)  (include/kao.h KAO_KEY_*)."""
+    key = int(key)
+    return key >> 48, 0xFFFFFF - ((key >> 24) & 0xFFFFFF), key & 0xFFFFFF
+
+
+class _CProblem:
+    """Keeps contiguous numpy buffers alive next to the C struct that points into them."""
+
+    def __init__(self, pb: Problem):
+        a = lambda x, dt: np.ascontiguousarray(x, dtype=dt)
+        self.keep = [a(pb.rack_of, np.uint8), a(pb.wF, np.uint16), a(pb.wL, np.uint16),
+                     a(pb.rep_lo, np.int32), a(pb.rep_hi, np.int32), a(pb.ldr_lo, np.int32),
+                     a(pb.ldr_hi, np.int32), a(pb.rack_lo, np.int32), a(pb.rack_hi, np.int32),
+                     a(pb.cur, np.int32)]
+        k = self.keep
+        self.c = _KaoProblem(pb.P, pb.B, pb.R, pb.RF, pb.cur.shape[1],
+                             *(x.ctypes.data for x in k[:9]), int(pb.ppr_lo), int(pb.ppr_hi),
+                             k[9].ctypes.data)
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+@dataclasses.dataclass
+class SolveResult:
+    replicas: np.ndarray      # int32 [P, RF] dense broker indices, leader first
+    objective: int
+    violation: int
+    moves: int
+    feasible: bool
+    key: int
+    n_candidates: int
+    rounds: int
+    device_ms: float
+    total_ms: float
+
+
+class Session:
+    """Device-resident problem (kao_create .. kao_destroy)."""
+
+    def __init__(self, pb: Problem, device: int = 0):
+        self.pb = pb
+        self._cp = _CProblem(pb)
+        self._h = C.c_void_p()
+        self._lib = load_library()
+        _check(self._lib.kao_create(self._cp.ref(), C.c_int32(device), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.kao_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(self._lib.kao_reset(self._h))
+
+    def set_base(self, replicas):
+        r = np.ascontiguousarray(replicas, dtype=np.int32)
+        assert r.shape == (self.pb.P, self.pb.RF)
+        _check(self._lib.kao_set_base(self._h, C.c_void_p(r.ctypes.data)))
+
+    def get_base(self):
+        """-> (replicas [P,RF], violation, objective, moves)"""
+        r = np.empty((self.pb.P, self.pb.RF), np.int32)
+        v, o, mv = C.c_int64(), C.c_int64(), C.c_int32()
+        _check(self._lib.kao_get_base(self._h, C.c_void_p(r.ctypes.data), C.byref(v), C.byref(o), C.byref(mv)))
+        return r, v.value, o.value, mv.value
+
+    def search(self, seed: int, first_round: int, rounds: int, round_size: int):
+        """-> (per-round winning keys uint64[rounds], device milliseconds)"""
+        keys = np.zeros(max(rounds, 1), np.uint64)
+        ms = C.c_double()
+        _check(self._lib.kao_search(self._h, C.c_uint64(seed), C.c_uint32(first_round), C.c_uint32(rounds),
+                                    C.c_uint32(round_size), C.c_void_p(keys.ctypes.data), C.byref(ms)))
+        return keys[:rounds], ms.value
+
+    def candidate_keys(self, seed: int, rnd: int, round_size: int, idx_begin: int, count: int):
+        keys = np.zeros(max(count, 1), np.uint64)
+        _check(self._lib.kao_candidate_keys(self._h, C.c_uint64(seed), C.c_uint32(rnd), C.c_uint32(round_size),
+                                            C.c_uint32(idx_begin), C.c_uint32(count),
+                                            C.c_void_p(keys.ctypes.data)))
+        return keys[:count]
+
+    def round_launch(self, seed, rnd, round_size, idx_lo, idx_hi, d_key_ptr: int, stream: int = 0):
+        _check(self._lib.kao_round_launch(self._h, C.c_uint64(seed), C.c_uint32(rnd), C.c_uint32(round_size),
+                                          C.c_uint32(idx_lo), C.c_uint32(idx_hi), C.c_void_p(d_key_ptr),
+                                          C.c_void_p(stream)))
+
+    def round_apply(self, seed, rnd, round_size, d_key_ptr: int, stream: int = 0):
+        _check(self._lib.kao_round_apply(self._h, C.c_uint64(seed), C.c_uint32(rnd), C.c_uint32(round_size),
+                                         C.c_void_p(d_key_ptr), C.c_void_p(stream)))
+
+    def stats(self):
+        n, w, s, dn = C.c_uint64(), C.c_int32(), C.c_int32(), C.c_int32()
+        _check(self._lib.kao_stats(self._h, C.byref(n), C.byref(w), C.byref(s), C.byref(dn)))
+        return {"kernel_launches": n.value, "words_per_row": w.value, "slots": s.value,
+                "dense_weights": bool(dn.value)}
+
+
+def solve(pb: Problem, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15,
+          device: int = 0, require_feasible: bool = False) -> SolveResult:
+    """One blocking kao_solve from host buffers (tables up, winner down)."""
+    lib = load_library()
+    cp = _CProblem(pb)
+    reps = np.full((pb.P, pb.RF), -1, np.int32)
+    opt = _KaoOptions(seed, rounds, round_size, device, 0)
+    res = _KaoResult()
+    res.replicas = reps.ctypes.data
+    rc = _check(lib.kao_solve(cp.ref(), C.byref(opt), C.byref(res)), allow_infeasible=not require_feasible)
+    return SolveResult(reps, res.objective, res.violation, res.moves, rc == KAO_OK, res.key,
+                       res.n_candidates, res.rounds_run, res.device_ms, res.total_ms)
+
+
+def evaluate(pb: Problem, replicas, device: int = 0):
+    """GPU evaluation of explicit assignments: replicas [n, P, RF] (or [P, RF]) -> (violation[n],
+    objective[n])."""
+    lib = load_library()
+    cp = _CProblem(pb)
+    r = np.ascontiguousarray(replicas, dtype=np.int32)
+    if r.ndim == 2:
+        r = r[None]
+    n = r.shape[0]
+    v = np.zeros(n, np.int64)
+    o = np.zeros(n, np.int64)
+    _check(lib.kao_eval(cp.ref(), C.c_int32(device), C.c_void_p(r.ctypes.data), C.c_int32(n),
+                        C.c_void_p(v.ctypes.data), C.c_void_p(o.ctypes.data)))
+    return v, o
+
+
+class AssignmentOptimizer:
+    """Operator-level mirror of the reference: feed it what `kafka-reassign-partitions --generate`
+    printed plus the target broker list and topology, get the reassignment JSON back."""
+
+    def __init__(self, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15, device: int = 0):
+        self.seed, self.rounds, self.round_size, self.device = seed, rounds, round_size, device
+
+    def optimize(self, assignment_json, broker_list, rack_map, rf: Optional[int] = None):
+        rows, topics = parse_assignment_json(assignment_json)
+        brokers = parse_broker_list(broker_list) if isinstance(broker_list, str) else list(broker_list)
+        racks = parse_rack_map(rack_map) if isinstance(rack_map, str) else dict(rack_map)
+        if rf is None:
+            rf = max(len(r) for r in rows)
+        pb = build_problem(rows, brokers, racks, rf, topics)
+        res = solve(pb, self.seed, self.rounds, self.round_size, self.device)
+        return reassignment_json(pb, res.replicas), res

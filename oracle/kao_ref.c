@@ -5,16 +5,17 @@
  * build, load or call this file.  The product (kafka_assignment_optimizer_b200/csrc) never links
  * it and has no CPU fallback.
  *
- * PARITY STATUS: parity unpinned against lp_solve (see oracle/model.py header).  This file
- * restates, with scalar loops and no bit tricks, the SAME deterministic search the CUDA engine
- * runs (docs/MODEL.md §3-§5): counter-based candidate stream (Philox4x32-10 keyed by seed,
+ * PARITY STATUS: parity unpinned against lp_solve (see oracle/model.py header: the reference
+ * snapshot holds no code; lp_solve 5.5, /root/reference/README.md:135-136, is not available).
+ * This file restates, with scalar loops and no bit tricks, the SAME deterministic search the CUDA
+ * engine runs (docs/MODEL.md): counter-based candidate stream (Philox4x32-10 keyed by seed,
  * counter = (index, round)), full evaluation of C1..C7 + objective per candidate
- * (/root/reference/README.md:144-185), packed (violation, cost, index) argmin per round, winner
- * becomes the next base.  Same seed => bit-identical winner, per-candidate keys and trajectory.
- * The model semantics are validated against oracle/model.py (HiGHS), which is pinned on the
- * README known-answer vector (README.md:83-91).
+ * (README.md:144-185), packed (violation, cost, index) argmin per round, winner becomes the next
+ * base.  Same seed => bit-identical winner, per-candidate keys and trajectory.  The model
+ * semantics are validated against oracle/model.py (HiGHS), which is pinned on the README
+ * known-answer vector (README.md:83-91).
  *
- * Build: see oracle/Makefile (gcc -O2 -fopenmp -shared).
+ * Build: oracle/Makefile (gcc -O2 -fopenmp -shared).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -23,10 +24,11 @@
 #include <omp.h>
 #endif
 
-#define KAO_MAX_B 256
-#define KAO_MAX_R 16
+#define KAO_MAX_SLOTS 256
+#define KAO_MAX_R 32
 #define KAO_MAX_W 8
 #define KAO_MAX_OPS 3
+#define KAO_HOME 4
 
 typedef struct {
     int32_t P, B, R, RF, RFcur;
@@ -43,7 +45,40 @@ typedef struct {
 #define VIOL_CAP 0xFFFFu
 #define IDX_BITS 24
 
-static int W_of(const ref_problem *pb) { return (pb->B + 31) / 32; }
+/* ---------------------------------------------------------------- slot space (docs/MODEL.md §2) */
+/* Brokers are re-indexed rack-major into aligned slots: slot = rack*S + rank-in-rack, S = the
+ * smallest power of two >= max(8, largest rack).  `order` = position in rack-major order. */
+typedef struct {
+    int S, NS, W;
+    int slot_of_broker[KAO_MAX_SLOTS];
+    int broker_of_slot[KAO_MAX_SLOTS]; /* -1 = padding slot */
+    int slot_of_order[KAO_MAX_SLOTS];
+    int order_of_slot[KAO_MAX_SLOTS];
+} ref_layout;
+
+int kao_ref_layout(const ref_problem *pb, ref_layout *L)
+{
+    int size[KAO_MAX_R] = {0}, maxsz = 0;
+    if (pb->R < 1 || pb->R > KAO_MAX_R || pb->B < 1 || pb->B > KAO_MAX_SLOTS) return -1;
+    for (int b = 0; b < pb->B; ++b) { if (pb->rack_of[b] >= pb->R) return -1; ++size[pb->rack_of[b]]; }
+    for (int r = 0; r < pb->R; ++r) if (size[r] > maxsz) maxsz = size[r];
+    int S = 8; while (S < maxsz) S <<= 1;
+    L->S = S; L->NS = pb->R * S;
+    if (L->NS > KAO_MAX_SLOTS) return -1;
+    int w = (L->NS + 31) / 32, W = 1; while (W < w) W <<= 1;
+    L->W = W;
+    for (int s = 0; s < KAO_MAX_SLOTS; ++s) { L->broker_of_slot[s] = -1; L->order_of_slot[s] = -1; }
+    int rank[KAO_MAX_R] = {0};
+    for (int b = 0; b < pb->B; ++b) {
+        int r = pb->rack_of[b], s = r * S + rank[r]++;
+        L->slot_of_broker[b] = s; L->broker_of_slot[s] = b;
+    }
+    int o = 0;
+    for (int s = 0; s < L->NS; ++s)
+        if (L->broker_of_slot[s] >= 0) { L->slot_of_order[o] = s; L->order_of_slot[s] = o; ++o; }
+    return 0;
+}
+int kao_ref_words(const ref_problem *pb) { ref_layout L; return kao_ref_layout(pb, &L) ? -1 : L.W; }
 
 /* ---------------------------------------------------------------- Philox4x32-10 (Random123) */
 void kao_ref_philox(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
@@ -64,59 +99,68 @@ void kao_ref_philox(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t
 }
 
 /* ---------------------------------------------------------------- bit helpers (scalar) */
-static int row_has(const uint32_t *row, int b) { return (row[b >> 5] >> (b & 31)) & 1u; }
-static void row_set(uint32_t *row, int b) { row[b >> 5] |= 1u << (b & 31); }
-static void row_clr(uint32_t *row, int b) { row[b >> 5] &= ~(1u << (b & 31)); }
+static int row_has(const uint32_t *row, int s) { return (row[s >> 5] >> (s & 31)) & 1u; }
+static void row_set(uint32_t *row, int s) { row[s >> 5] |= 1u << (s & 31); }
+static void row_clr(uint32_t *row, int s) { row[s >> 5] &= ~(1u << (s & 31)); }
 static int row_count(const uint32_t *row, int W)
 {
     int n = 0;
     for (int j = 0; j < W; ++j) n += __builtin_popcount(row[j]);
     return n;
 }
-/* k-th (0-based) set bit in ascending broker order, -1 if fewer */
-static int row_kth(const uint32_t *row, int B, int k)
+/* k-th (0-based) set bit in ascending slot order, -1 if fewer */
+static int row_kth(const uint32_t *row, int W, int k)
 {
-    for (int b = 0; b < B; ++b)
-        if (row_has(row, b)) { if (k == 0) return b; --k; }
+    for (int s = 0; s < W * 32; ++s)
+        if (row_has(row, s)) { if (k == 0) return s; --k; }
     return -1;
 }
 
 /* ---------------------------------------------------------------- full evaluation (docs/MODEL.md §3) */
-/* violation = sum over every row of C1..C7 of the amount by which it is missed; objective =
- * README.md:145-146.  A leader that is not one of the partition's replicas violates C2 by 1 and
- * earns no leader weight. */
+/* Candidate = bits[P][W] over slots + leader slot per partition.  violation = sum over every row
+ * of C1..C7 of the amount by which it is missed; objective = README.md:145-146.  A leader that is
+ * not one of the partition's replicas violates C2 by 1 and earns no leader weight.  Replicas on
+ * padding slots count for C1/C7/C6 and violate C3 (their bound is [0,0]). */
 void kao_ref_eval(const ref_problem *pb, const uint32_t *bits, const uint8_t *leader,
                   int64_t *viol_out, int64_t *obj_out)
 {
-    const int P = pb->P, B = pb->B, R = pb->R, W = W_of(pb);
+    ref_layout L;
+    if (kao_ref_layout(pb, &L)) { *viol_out = -1; *obj_out = -1; return; }
+    const int P = pb->P, R = pb->R, W = L.W, S = L.S;
     int64_t viol = 0, obj = 0;
-    int32_t cnt[KAO_MAX_B] = {0}, lcnt[KAO_MAX_B] = {0}, rc[KAO_MAX_R] = {0};
+    int32_t cnt[KAO_MAX_SLOTS] = {0}, lcnt[KAO_MAX_SLOTS] = {0}, rc[KAO_MAX_R] = {0};
     for (int p = 0; p < P; ++p) {
         const uint32_t *row = bits + (size_t)p * W;
         int pr[KAO_MAX_R] = {0};
         int n = 0, ld = leader[p];
-        int ld_ok = (ld < B) && row_has(row, ld);
-        for (int b = 0; b < B; ++b) {
-            if (!row_has(row, b)) continue;
-            ++n; ++cnt[b]; ++pr[pb->rack_of[b]];
-            if (!(ld_ok && b == ld)) obj += pb->wF[(size_t)p * B + b];
+        int ld_ok = (ld < W * 32) && row_has(row, ld);
+        for (int j = 0; j < W; ++j) {
+            for (uint32_t w = row[j]; w; w &= w - 1) {              /* every replica of p */
+                int s = j * 32 + __builtin_ctz(w);
+                ++n; ++cnt[s];
+                if (s / S < R) { ++pr[s / S]; ++rc[s / S]; }
+                int b = L.broker_of_slot[s];
+                if (b >= 0 && !(ld_ok && s == ld)) obj += pb->wF[(size_t)p * pb->B + b];
+            }
         }
-        /* bits at positions >= B (padding) are replicas on non-existent brokers: count for C1 */
-        for (int b = B; b < W * 32; ++b) if (row_has(row, b)) ++n;
         viol += abs(n - pb->RF);                                   /* C1 */
-        if (ld_ok) { ++lcnt[ld]; obj += pb->wL[(size_t)p * B + ld]; }
-        else viol += 1;                                            /* C2 (+C5) */
+        if (ld_ok) {
+            ++lcnt[ld];
+            if (L.broker_of_slot[ld] >= 0) obj += pb->wL[(size_t)p * pb->B + L.broker_of_slot[ld]];
+        } else viol += 1;                                          /* C2 (+C5) */
         for (int r = 0; r < R; ++r) {                              /* C7 */
             if (pr[r] > pb->ppr_hi) viol += pr[r] - pb->ppr_hi;
             if (pr[r] < pb->ppr_lo) viol += pb->ppr_lo - pr[r];
         }
     }
-    for (int b = 0; b < B; ++b) {
-        if (cnt[b] > pb->rep_hi[b]) viol += cnt[b] - pb->rep_hi[b];  /* C3 */
-        if (cnt[b] < pb->rep_lo[b]) viol += pb->rep_lo[b] - cnt[b];
-        if (lcnt[b] > pb->ldr_hi[b]) viol += lcnt[b] - pb->ldr_hi[b];/* C4 */
-        if (lcnt[b] < pb->ldr_lo[b]) viol += pb->ldr_lo[b] - lcnt[b];
-        rc[pb->rack_of[b]] += cnt[b];
+    for (int s = 0; s < W * 32; ++s) {
+        int b = (s < KAO_MAX_SLOTS) ? L.broker_of_slot[s] : -1;
+        int rlo = b >= 0 ? pb->rep_lo[b] : 0, rhi = b >= 0 ? pb->rep_hi[b] : 0;
+        int llo = b >= 0 ? pb->ldr_lo[b] : 0, lhi = b >= 0 ? pb->ldr_hi[b] : 0;
+        if (cnt[s] > rhi) viol += cnt[s] - rhi;                    /* C3 */
+        if (cnt[s] < rlo) viol += rlo - cnt[s];
+        if (lcnt[s] > lhi) viol += lcnt[s] - lhi;                  /* C4 */
+        if (lcnt[s] < llo) viol += llo - lcnt[s];
     }
     for (int r = 0; r < R; ++r) {                                  /* C6 */
         if (rc[r] > pb->rack_hi[r]) viol += rc[r] - pb->rack_hi[r];
@@ -132,45 +176,120 @@ uint64_t kao_ref_pack(int64_t viol, int64_t obj, uint32_t idx)
     return (v << 48) | (c << IDX_BITS) | (idx & ((1u << IDX_BITS) - 1));
 }
 
+/* ---------------------------------------------------------------- replica lists <-> bit-plane */
+/* replicas[P*RF]: dense broker indices, leader first, -1 padded (README.md:52-63 order) */
+void kao_ref_encode(const ref_problem *pb, const int32_t *replicas, uint32_t *bits, uint8_t *leader)
+{
+    ref_layout L; kao_ref_layout(pb, &L);
+    memset(bits, 0, (size_t)pb->P * L.W * 4);
+    for (int p = 0; p < pb->P; ++p) {
+        int have = 0;
+        leader[p] = 0xFF;
+        for (int i = 0; i < pb->RF; ++i) {
+            int b = replicas[(size_t)p * pb->RF + i];
+            if (b < 0 || b >= pb->B) continue;
+            row_set(bits + (size_t)p * L.W, L.slot_of_broker[b]);
+            if (!have) { leader[p] = (uint8_t)L.slot_of_broker[b]; have = 1; }
+        }
+    }
+}
+/* leader first, then followers in ascending dense broker index (README.md:65-78,:88) */
+void kao_ref_decode(const ref_problem *pb, const uint32_t *bits, const uint8_t *leader,
+                    int32_t *replicas)
+{
+    ref_layout L; kao_ref_layout(pb, &L);
+    for (int p = 0; p < pb->P; ++p) {
+        const uint32_t *row = bits + (size_t)p * L.W;
+        int32_t *out = replicas + (size_t)p * pb->RF;
+        int n = 0, ld = leader[p], ldb = -1;
+        for (int i = 0; i < pb->RF; ++i) out[i] = -1;
+        if (ld < L.W * 32 && row_has(row, ld) && L.broker_of_slot[ld] >= 0)
+            out[n++] = ldb = L.broker_of_slot[ld];
+        for (int b = 0; b < pb->B && n < pb->RF; ++b)
+            if (b != ldb && row_has(row, L.slot_of_broker[b])) out[n++] = b;
+    }
+}
+
 /* ---------------------------------------------------------------- initial base (docs/MODEL.md §4) */
 /* cur restricted to the target brokers, order kept (leader = first survivor); surplus replicas
  * (RF lowered) dropped from the tail; missing replicas (broker removed / RF raised) added one at
- * a time on the broker minimising (replicas of p already in that rack, current load, index). */
+ * a time, partitions in ascending order, on the broker minimising (replicas of p already in that
+ * rack, current load, dense broker index). */
 void kao_ref_init_base(const ref_problem *pb, uint32_t *bits, uint8_t *leader)
 {
-    const int P = pb->P, B = pb->B, W = W_of(pb);
-    int32_t load[KAO_MAX_B] = {0};
+    ref_layout L; kao_ref_layout(pb, &L);
+    const int P = pb->P, B = pb->B, W = L.W;
+    int32_t load[KAO_MAX_SLOTS] = {0};
     memset(bits, 0, (size_t)P * W * 4);
     for (int p = 0; p < P; ++p) {
         uint32_t *row = bits + (size_t)p * W;
         int n = 0, ld = -1;
         for (int i = 0; i < pb->RFcur && n < pb->RF; ++i) {
             int b = pb->cur[(size_t)p * pb->RFcur + i];
-            if (b < 0 || b >= B || row_has(row, b)) continue;
-            row_set(row, b); ++n; ++load[b];
-            if (ld < 0) ld = b;
+            if (b < 0 || b >= B || row_has(row, L.slot_of_broker[b])) continue;
+            row_set(row, L.slot_of_broker[b]); ++n; ++load[b];
+            if (ld < 0) ld = L.slot_of_broker[b];
         }
-        leader[p] = (uint8_t)(ld < 0 ? 0 : ld);
+        leader[p] = (uint8_t)(ld < 0 ? 0xFF : ld);
     }
     for (int p = 0; p < P; ++p) {
         uint32_t *row = bits + (size_t)p * W;
         int n = row_count(row, W);
-        int had_leader = n > 0;
         while (n < pb->RF && n < B) {
             int pr[KAO_MAX_R] = {0};
-            for (int b = 0; b < B; ++b) if (row_has(row, b)) ++pr[pb->rack_of[b]];
+            for (int b = 0; b < B; ++b) if (row_has(row, L.slot_of_broker[b])) ++pr[pb->rack_of[b]];
             int best = -1;
             for (int b = 0; b < B; ++b) {
-                if (row_has(row, b)) continue;
+                if (row_has(row, L.slot_of_broker[b])) continue;
                 if (best < 0) { best = b; continue; }
                 int ra = pr[pb->rack_of[b]], rb = pr[pb->rack_of[best]];
                 if (ra < rb || (ra == rb && load[b] < load[best])) best = b;
             }
-            row_set(row, best); ++load[best]; ++n;
-            if (!had_leader) { leader[p] = (uint8_t)best; had_leader = 1; }
+            row_set(row, L.slot_of_broker[best]); ++load[best]; ++n;
+            if (leader[p] == 0xFF) leader[p] = (uint8_t)L.slot_of_broker[best];
         }
     }
 }
+
+/* ---------------------------------------------------------------- base analysis (docs/MODEL.md §5.1) */
+/* home[p] = slots of the first KAO_HOME surviving entries of cur[p]; home0[p] = slot of cur[p][0]
+ * if that broker survives, else -1.  D = ascending list of the partitions whose row lacks at
+ * least one home slot ("displaced"); DL = ascending list of the partitions that hold a replica on
+ * home0 but are led from elsewhere ("leader displaced"). */
+typedef struct { int nD, nL; int32_t *D, *DL; uint32_t *home; /* [P*W] home masks */ int32_t *home0; /* [P] */ } ref_aux;
+
+static void home_mask(const ref_problem *pb, const ref_layout *L, int p, uint32_t *m)
+{
+    memset(m, 0, (size_t)L->W * 4);
+    for (int i = 0; i < pb->RFcur && i < KAO_HOME; ++i) {
+        int b = pb->cur[(size_t)p * pb->RFcur + i];
+        if (b >= 0 && b < pb->B) row_set(m, L->slot_of_broker[b]);
+    }
+}
+static void analyse(const ref_problem *pb, const ref_layout *L, const uint32_t *bits,
+                    const uint8_t *leader, ref_aux *ax)
+{
+    ax->nD = ax->nL = 0;
+    for (int p = 0; p < pb->P; ++p) {
+        uint32_t *m = ax->home + (size_t)p * L->W;
+        home_mask(pb, L, p, m);
+        int miss = 0;
+        for (int j = 0; j < L->W; ++j) if (m[j] & ~bits[(size_t)p * L->W + j]) miss = 1;
+        if (miss) ax->D[ax->nD++] = p;
+        int b0 = pb->cur[(size_t)p * pb->RFcur];
+        int h0 = (b0 >= 0 && b0 < pb->B) ? L->slot_of_broker[b0] : -1;
+        ax->home0[p] = h0;
+        if (h0 >= 0 && row_has(bits + (size_t)p * L->W, h0) && leader[p] != h0) ax->DL[ax->nL++] = p;
+    }
+}
+static void aux_alloc(const ref_problem *pb, int W, ref_aux *ax)
+{
+    ax->D = (int32_t *)malloc((size_t)pb->P * 4);
+    ax->DL = (int32_t *)malloc((size_t)pb->P * 4);
+    ax->home0 = (int32_t *)malloc((size_t)pb->P * 4);
+    ax->home = (uint32_t *)malloc((size_t)pb->P * W * 4);
+}
+static void aux_free(ref_aux *ax) { free(ax->D); free(ax->DL); free(ax->home0); free(ax->home); }
 
 /* ---------------------------------------------------------------- candidate generator (docs/MODEL.md §5) */
 static uint32_t mulhi32(uint32_t a, uint32_t n) { return (uint32_t)(((uint64_t)a * n) >> 32); }
@@ -178,11 +297,9 @@ static uint32_t mulhi32(uint32_t a, uint32_t n) { return (uint32_t)(((uint64_t)a
 typedef struct { int32_t p; uint32_t row[KAO_MAX_W]; uint8_t leader; } ref_patch;
 typedef struct { int n; ref_patch e[KAO_MAX_OPS]; } ref_patchset;
 
-/* current view of row p under the patches made so far */
-static void view_row(const ref_problem *pb, const uint32_t *bits, const uint8_t *leader,
+static void view_row(int W, const uint32_t *bits, const uint8_t *leader,
                      const ref_patchset *ps, int p, uint32_t *row, int *ld)
 {
-    const int W = W_of(pb);
     memcpy(row, bits + (size_t)p * W, (size_t)W * 4);
     *ld = leader[p];
     for (int i = 0; i < ps->n; ++i)
@@ -193,36 +310,79 @@ static int touched(const ref_patchset *ps, int p)
     for (int i = 0; i < ps->n; ++i) if (ps->e[i].p == p) return 1;
     return 0;
 }
-static void push_patch(const ref_problem *pb, ref_patchset *ps, int p, const uint32_t *row, int ld)
+static void push_patch(int W, ref_patchset *ps, int p, const uint32_t *row, int ld)
 {
-    const int W = W_of(pb);
     for (int i = 0; i < ps->n; ++i)
         if (ps->e[i].p == p) { memcpy(ps->e[i].row, row, (size_t)W * 4); ps->e[i].leader = (uint8_t)ld; return; }
     ref_patch *e = &ps->e[ps->n++];
     e->p = p; memset(e->row, 0, sizeof e->row); memcpy(e->row, row, (size_t)W * 4); e->leader = (uint8_t)ld;
 }
 
-/* REPLACE: in partition p, the replica on broker a moves to the first broker >= bt (cyclic) that
- * p does not already use; if a was the leader, the new broker inherits leadership. */
-static int op_replace(const ref_problem *pb, const uint32_t *bits, const uint8_t *leader,
-                      ref_patchset *ps, int p, int a, int bt, int *b_out)
+/* REPLACE: in partition p the replica on slot a moves to the first broker, in rack-major order
+ * starting at order index o (cyclic), that p does not already use; a leader replica keeps its
+ * leadership on the new broker. */
+static int op_replace(const ref_problem *pb, const ref_layout *L, const uint32_t *bits,
+                      const uint8_t *leader, ref_patchset *ps, int p, int a, int o, int *s_out)
 {
     uint32_t row[KAO_MAX_W]; int ld;
-    view_row(pb, bits, leader, ps, p, row, &ld);
-    if (!row_has(row, a)) return 0;
-    int b = bt, tries = 0;
-    while (row_has(row, b)) { b = (b + 1 == pb->B) ? 0 : b + 1; if (++tries > pb->B) return 0; }
-    row_clr(row, a); row_set(row, b);
-    if (ld == a) ld = b;
-    push_patch(pb, ps, p, row, ld);
-    *b_out = b;
+    view_row(L->W, bits, leader, ps, p, row, &ld);
+    if (a < 0 || !row_has(row, a)) return 0;
+    int tries = 0;
+    while (row_has(row, L->slot_of_order[o])) { o = (o + 1 == pb->B) ? 0 : o + 1; if (++tries > pb->B) return 0; }
+    int s = L->slot_of_order[o];
+    row_clr(row, a); row_set(row, s);
+    if (ld == a) ld = s;
+    push_patch(L->W, ps, p, row, ld);
+    *s_out = s;
     return 1;
 }
-/* first partition q >= p0 (cyclic), not yet patched, that has a replica on broker src */
-static int find_holder(const ref_problem *pb, const uint32_t *bits, const ref_patchset *ps,
+/* LEADER: partition p is led from slot `want` if that is one of its non-leader replicas, else
+ * from its k-th (ascending slot) non-leader replica.  Returns the new leader slot or -1. */
+static int op_leader(const ref_layout *L, const uint32_t *bits, const uint8_t *leader,
+                     ref_patchset *ps, int p, int want, uint32_t rnd)
+{
+    uint32_t row[KAO_MAX_W]; int ld;
+    view_row(L->W, bits, leader, ps, p, row, &ld);
+    int n = row_count(row, L->W);
+    int has_ld = (ld < L->W * 32) && row_has(row, ld);
+    int m = n - (has_ld ? 1 : 0);
+    if (m < 1) return -1;
+    if (want >= 0 && want < L->W * 32 && want != ld && row_has(row, want)) { push_patch(L->W, ps, p, row, want); return want; }
+    int k = (int)mulhi32(rnd, (uint32_t)m);
+    for (int s = 0; s < L->W * 32; ++s) {
+        if (!row_has(row, s) || s == ld) continue;
+        if (k-- == 0) { push_patch(L->W, ps, p, row, s); return s; }
+    }
+    return -1;
+}
+/* first partition q >= p0 (cyclic), not yet patched, with a non-leader replica on slot src */
+static int find_follower(const ref_problem *pb, int W, const uint32_t *bits, const uint8_t *leader,
+                         const ref_patchset *ps, int p0, int src)
+{
+    if (src < 0 || src >= W * 32) return -1;
+    for (int k = 0; k < pb->P; ++k) {
+        int q = p0 + k; if (q >= pb->P) q -= pb->P;
+        if (touched(ps, q)) continue;
+        if (leader[q] != src && row_has(bits + (size_t)q * W, src)) return q;
+    }
+    return -1;
+}
+/* first partition q >= p0 (cyclic), not yet patched, whose leader is slot src */
+static int find_led_by(const ref_problem *pb, const uint8_t *leader, const ref_patchset *ps,
                        int p0, int src)
 {
-    const int W = W_of(pb);
+    for (int k = 0; k < pb->P; ++k) {
+        int q = p0 + k; if (q >= pb->P) q -= pb->P;
+        if (touched(ps, q)) continue;
+        if (leader[q] == src) return q;
+    }
+    return -1;
+}
+/* first partition q >= p0 (cyclic), not yet patched, that has a replica on slot src */
+static int find_holder(const ref_problem *pb, int W, const uint32_t *bits, const ref_patchset *ps,
+                       int p0, int src)
+{
+    if (src < 0 || src >= W * 32) return -1;
     for (int k = 0; k < pb->P; ++k) {
         int q = p0 + k; if (q >= pb->P) q -= pb->P;
         if (touched(ps, q)) continue;
@@ -231,13 +391,25 @@ static int find_holder(const ref_problem *pb, const uint32_t *bits, const ref_pa
     return -1;
 }
 
-/* Fills `ps` with the row patches that turn the base into candidate (round, idx).  idx ==
- * round_size-1 is the identity.  Pure function of (base, seed, round, idx). */
-void kao_ref_gen_patches(const ref_problem *pb, const uint32_t *bits, const uint8_t *leader,
-                         uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size,
-                         ref_patchset *ps)
+/* Row patches that turn the base into candidate (round, idx).  idx == round_size-1 is the
+ * identity.  Pure function of (base, seed, round, idx).  docs/MODEL.md §5:
+ *   control word c = r0:  bits 0-1 -> number of ops (0:1, 1-2:2, 3:3); bit 2 first op is LEADER;
+ *   bit 3 guided first op; per later op k: 2 bits link type (0 R-push, 1 R-pull, 2 L-push,
+ *   3 L-pull) and 1 bit "close".
+ * The chain keeps (lo, hi) = (slot that lost, slot that gained) a replica / a leadership:
+ *   R-push  a holder of hi moves that replica to lo (close) or to a random broker   -> hi = target
+ *   R-pull  a random partition moves a replica (its leader replica if close) to lo  -> lo = source
+ *   L-push  a partition led by hi is led by lo (close, if lo follows there) / its first broker /
+ *           a random follower                                                        -> hi = new leader
+ *   L-pull  a partition where lo follows is led by lo                                -> lo = old leader
+ * Guided first op: REPLACE restores a displaced partition (list D) to a missing home broker;
+ * LEADER hands a leader-displaced partition (list DL) back to its first broker. */
+static void gen_patches(const ref_problem *pb, const ref_layout *L, const ref_aux *ax,
+                        const uint32_t *bits, const uint8_t *leader,
+                        uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size,
+                        ref_patchset *ps)
 {
-    const int P = pb->P, B = pb->B, W = W_of(pb);
+    const int P = pb->P, B = pb->B, W = L->W;
     ps->n = 0;
     if (idx + 1 == round_size) return;
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
@@ -245,129 +417,159 @@ void kao_ref_gen_patches(const ref_problem *pb, const uint32_t *bits, const uint
     uint32_t r[4], s[4];
     kao_ref_philox(c0, key, r);
     kao_ref_philox(c1, key, s);
-    const uint32_t sel = r[0] & 15u;
-    const int p = (int)mulhi32(r[1], (uint32_t)P);
+    const uint32_t ctl = r[0];
+    const int nops = (ctl & 3u) == 0 ? 1 : ((ctl & 3u) == 3 ? 3 : 2);
+    const int first_leader = (ctl >> 2) & 1u, gbit = (ctl >> 3) & 1u;
     uint32_t row[KAO_MAX_W]; int ld;
-    view_row(pb, bits, leader, ps, p, row, &ld);
-    const int n = row_count(row, W);
-    if (n == 0) return;
-    if (sel == 5 || sel == 6) {
-        /* LEADER: the k-th non-leader replica of p becomes its leader (no data moves) */
-        if (n < 2) return;
-        int k = (int)mulhi32(r[2], (uint32_t)(n - 1));
-        for (int b = 0; b < B; ++b) {
-            if (!row_has(row, b) || b == ld) continue;
-            if (k-- == 0) { push_patch(pb, ps, p, row, b); return; }
+    int lo, hi;
+    if (first_leader) {
+        const int guided = gbit && ax->nL > 0;
+        const int p = guided ? ax->DL[mulhi32(r[1], (uint32_t)ax->nL)] : (int)mulhi32(r[1], (uint32_t)P);
+        lo = leader[p];
+        hi = op_leader(L, bits, leader, ps, p, guided ? ax->home0[p] : -1, r[2]);
+        if (hi < 0) return;
+    } else {
+        const int guided = gbit && ax->nD > 0;
+        const int p = guided ? ax->D[mulhi32(r[1], (uint32_t)ax->nD)] : (int)mulhi32(r[1], (uint32_t)P);
+        view_row(W, bits, leader, ps, p, row, &ld);
+        const int n = row_count(row, W);
+        if (n == 0) return;
+        int a = row_kth(row, W, (int)mulhi32(r[2], (uint32_t)n));
+        int o = (int)mulhi32(r[3], (uint32_t)B);
+        if (guided) {
+            uint32_t miss[KAO_MAX_W], nonhome[KAO_MAX_W];
+            const uint32_t *hm = ax->home + (size_t)p * W;
+            for (int j = 0; j < W; ++j) { miss[j] = hm[j] & ~row[j]; nonhome[j] = row[j] & ~hm[j]; }
+            int nm = row_count(miss, W), nn = row_count(nonhome, W);
+            if (nm > 0) {
+                o = L->order_of_slot[row_kth(miss, W, (int)mulhi32(r[3], (uint32_t)nm))];
+                if (nn > 0) a = row_kth(nonhome, W, (int)mulhi32(r[2], (uint32_t)nn));
+            }
         }
-        return;
+        if (!op_replace(pb, L, bits, leader, ps, p, a, o, &hi)) return;
+        lo = a;
     }
-    const int a = row_kth(row, W * 32, (int)mulhi32(r[2], (uint32_t)n));
-    int b = -1;
-    if (!op_replace(pb, bits, leader, ps, p, a, (int)mulhi32(r[3], (uint32_t)B), &b)) return;
-    if (sel <= 4) return;                                   /* single REPLACE */
-    if (sel == 7) {                                         /* REPLACE + LEADER on the same p */
-        view_row(pb, bits, leader, ps, p, row, &ld);
-        if (n < 2) return;
-        int k = (int)mulhi32(s[0], (uint32_t)(n - 1));
-        for (int c = 0; c < B; ++c) {
-            if (!row_has(row, c) || c == ld) continue;
-            if (k-- == 0) { push_patch(pb, ps, p, row, c); return; }
+    for (int k = 1; k < nops; ++k) {
+        const uint32_t link = (ctl >> (4 + 3 * (k - 1))) & 3u;
+        const int close = (ctl >> (6 + 3 * (k - 1))) & 1u;
+        const uint32_t ra = s[2 * (k - 1)], rb = s[2 * (k - 1) + 1];
+        const int start = (int)mulhi32(ra, (uint32_t)P);
+        int olo = (lo < KAO_MAX_SLOTS) ? L->order_of_slot[lo] : -1;
+        if (olo < 0) olo = 0;
+        if (link == 0) {                                   /* R-push */
+            int q = find_holder(pb, W, bits, ps, start, hi), t;
+            if (q < 0) return;
+            if (!op_replace(pb, L, bits, leader, ps, q, hi, close ? olo : (int)mulhi32(rb, (uint32_t)B), &t)) return;
+            hi = t;
+        } else if (link == 1) {                            /* R-pull */
+            int q = start, lq, t;
+            if (touched(ps, q)) return;
+            uint32_t rq[KAO_MAX_W];
+            view_row(W, bits, leader, ps, q, rq, &lq);
+            const int nq = row_count(rq, W);
+            if (nq == 0) return;
+            int src = row_kth(rq, W, (int)mulhi32(rb, (uint32_t)nq));
+            if (close && lq < W * 32 && row_has(rq, lq)) src = lq;
+            if (!op_replace(pb, L, bits, leader, ps, q, src, olo, &t)) return;
+            lo = src;
+        } else if (link == 2) {                            /* L-push */
+            int q = find_led_by(pb, leader, ps, start, hi);
+            if (q < 0) return;
+            int t = op_leader(L, bits, leader, ps, q, close ? lo : ax->home0[q], rb);
+            if (t < 0) return;
+            hi = t;
+        } else {                                           /* L-pull */
+            int q = find_follower(pb, W, bits, leader, ps, start, lo);
+            if (q < 0) return;
+            const int old = leader[q];
+            if (op_leader(L, bits, leader, ps, q, lo, rb) < 0) return;
+            lo = old;
         }
-        return;
     }
-    /* chains: the broker that just gained a replica (b) gives one up from another partition */
-    int q = find_holder(pb, bits, ps, (int)mulhi32(s[0], (uint32_t)P), b);
-    if (q < 0) return;
-    int c = -1;
-    const int closed2 = (sel <= 11);                        /* 8..11: swap  a<->b */
-    if (!op_replace(pb, bits, leader, ps, q, b, closed2 ? a : (int)mulhi32(s[1], (uint32_t)B), &c))
-        return;
-    if (sel <= 13) return;                                  /* 12,13: open 2-chain */
-    int q2 = find_holder(pb, bits, ps, (int)mulhi32(s[2], (uint32_t)P), c);   /* 14,15: 3-cycle */
-    if (q2 < 0) return;
-    int d;
-    op_replace(pb, bits, leader, ps, q2, c, a, &d);
 }
 
+static void apply_patches(int W, const ref_patchset *ps, uint32_t *bits, uint8_t *leader)
+{
+    for (int i = 0; i < ps->n; ++i) {
+        memcpy(bits + (size_t)ps->e[i].p * W, ps->e[i].row, (size_t)W * 4);
+        leader[ps->e[i].p] = ps->e[i].leader;
+    }
+}
+
+/* materialise candidate (round, idx) of base (bits, leader) into (out_bits, out_leader) */
 void kao_ref_gen(const ref_problem *pb, const uint32_t *bits, const uint8_t *leader,
                  uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size,
                  uint32_t *out_bits, uint8_t *out_leader)
 {
-    const int W = W_of(pb);
-    ref_patchset ps;
-    kao_ref_gen_patches(pb, bits, leader, seed, round, idx, round_size, &ps);
-    if (out_bits != bits) memcpy(out_bits, bits, (size_t)pb->P * W * 4);
+    ref_layout L; kao_ref_layout(pb, &L);
+    ref_aux ax; ref_patchset ps;
+    aux_alloc(pb, L.W, &ax);
+    analyse(pb, &L, bits, leader, &ax);
+    gen_patches(pb, &L, &ax, bits, leader, seed, round, idx, round_size, &ps);
+    if (out_bits != bits) memcpy(out_bits, bits, (size_t)pb->P * L.W * 4);
     if (out_leader != leader) memcpy(out_leader, leader, (size_t)pb->P);
-    for (int i = 0; i < ps.n; ++i) {
-        memcpy(out_bits + (size_t)ps.e[i].p * W, ps.e[i].row, (size_t)W * 4);
-        out_leader[ps.e[i].p] = ps.e[i].leader;
-    }
+    apply_patches(L.W, &ps, out_bits, out_leader);
+    aux_free(&ax);
 }
 
-/* key of candidate (round, idx) by materialising it and evaluating it in full */
-uint64_t kao_ref_candidate_key(const ref_problem *pb, const uint32_t *bits, const uint8_t *leader,
-                               uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size,
-                               uint32_t *scratch_bits, uint8_t *scratch_leader)
+/* keys of candidates idx_begin..idx_begin+count-1 of one round, each materialised and evaluated
+ * in full (the per-candidate parity vector, T3) */
+void kao_ref_candidate_keys(const ref_problem *pb, const uint32_t *bits, const uint8_t *leader,
+                            uint64_t seed, uint32_t round, uint32_t round_size,
+                            uint32_t idx_begin, uint32_t count, uint64_t *keys, int nthreads)
 {
-    int64_t v, o;
-    kao_ref_gen(pb, bits, leader, seed, round, idx, round_size, scratch_bits, scratch_leader);
-    kao_ref_eval(pb, scratch_bits, scratch_leader, &v, &o);
-    return kao_ref_pack(v, o, idx);
+    ref_layout L; kao_ref_layout(pb, &L);
+    const size_t nb = (size_t)pb->P * L.W;
+    ref_aux ax;
+    aux_alloc(pb, L.W, &ax);
+    analyse(pb, &L, bits, leader, &ax);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel
+    {
+        uint32_t *sb = (uint32_t *)malloc(nb * 4);
+        uint8_t *sl = (uint8_t *)malloc((size_t)pb->P);
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < (int64_t)count; ++i) {
+            ref_patchset ps; int64_t v, o;
+            uint32_t idx = idx_begin + (uint32_t)i;
+            gen_patches(pb, &L, &ax, bits, leader, seed, round, idx, round_size, &ps);
+            memcpy(sb, bits, nb * 4); memcpy(sl, leader, (size_t)pb->P);
+            apply_patches(L.W, &ps, sb, sl);
+            kao_ref_eval(pb, sb, sl, &v, &o);
+            keys[i] = kao_ref_pack(v, o, idx);
+        }
+        free(sb); free(sl);
+    }
+    aux_free(&ax);
 }
 
 /* ---------------------------------------------------------------- search (docs/MODEL.md §6) */
 /* rounds x round_size candidates; per round the minimum key wins and becomes the next base.
- * bits/leader: in = base, out = final base.  round_keys (optional) receives each round's key.
- * Returns the key of the final base's winning candidate (idx field = winner's index). */
+ * bits/leader: in = base, out = final base.  round_keys (optional) receives each round's key. */
 uint64_t kao_ref_search(const ref_problem *pb, uint32_t *bits, uint8_t *leader, uint64_t seed,
                         uint32_t first_round, uint32_t rounds, uint32_t round_size,
                         uint64_t *round_keys, int nthreads)
 {
-    const int W = W_of(pb);
-    const size_t nb = (size_t)pb->P * W;
+    ref_layout L; kao_ref_layout(pb, &L);
+    const size_t nb = (size_t)pb->P * L.W;
     uint64_t last = ~0ull;
-#ifdef _OPENMP
-    if (nthreads > 0) omp_set_num_threads(nthreads);
-#endif
+    uint64_t *keys = (uint64_t *)malloc((size_t)round_size * 8);
     for (uint32_t t = first_round; t < first_round + rounds; ++t) {
         uint64_t best = ~0ull;
-#pragma omp parallel
-        {
-            uint32_t *sb = (uint32_t *)malloc(nb * 4);
-            uint8_t *sl = (uint8_t *)malloc((size_t)pb->P);
-            uint64_t mine = ~0ull;
-#pragma omp for schedule(static)
-            for (int64_t i = 0; i < (int64_t)round_size; ++i) {
-                uint64_t k = kao_ref_candidate_key(pb, bits, leader, seed, t, (uint32_t)i,
-                                                   round_size, sb, sl);
-                if (k < mine) mine = k;
-            }
-#pragma omp critical
-            if (mine < best) best = mine;
-            free(sb); free(sl);
-        }
+        kao_ref_candidate_keys(pb, bits, leader, seed, t, round_size, 0, round_size, keys, nthreads);
+        for (uint32_t i = 0; i < round_size; ++i) if (keys[i] < best) best = keys[i];
         uint32_t widx = (uint32_t)(best & ((1u << IDX_BITS) - 1));
         kao_ref_gen(pb, bits, leader, seed, t, widx, round_size, bits, leader);
         if (round_keys) round_keys[t - first_round] = best;
         last = best;
     }
+    free(keys);
+    (void)nb;
     return last;
-}
-
-/* bit-plane + leader -> replica lists, leader first then followers ascending (README.md:65-78,:88) */
-void kao_ref_decode(const ref_problem *pb, const uint32_t *bits, const uint8_t *leader,
-                    int32_t *replicas /* [P*RF], -1 padded */)
-{
-    const int W = W_of(pb);
-    for (int p = 0; p < pb->P; ++p) {
-        const uint32_t *row = bits + (size_t)p * W;
-        int32_t *out = replicas + (size_t)p * pb->RF;
-        int n = 0, ld = leader[p];
-        for (int i = 0; i < pb->RF; ++i) out[i] = -1;
-        if (ld < pb->B && row_has(row, ld)) out[n++] = ld;
-        for (int b = 0; b < pb->B && n < pb->RF; ++b)
-            if (row_has(row, b) && b != ld) out[n++] = b;
-    }
 }
 
 int kao_ref_max_threads(void)

@@ -38,7 +38,6 @@ def lib():
         _lib = C.CDLL(build())
         _lib.kao_ref_pack.restype = C.c_uint64
         _lib.kao_ref_pack.argtypes = [C.c_int64, C.c_int64, C.c_uint32]
-        _lib.kao_ref_candidate_key.restype = C.c_uint64
         _lib.kao_ref_search.restype = C.c_uint64
     return _lib
 
@@ -52,7 +51,6 @@ class Ref:
 
     def __init__(self, pb):
         self.pb = pb
-        self.W = (pb.B + 31) // 32
         self._keep = dict(
             rack_of=_arr(pb.rack_of, np.uint8), wF=_arr(pb.wF, np.uint16), wL=_arr(pb.wL, np.uint16),
             rep_lo=_arr(pb.rep_lo, np.int32), rep_hi=_arr(pb.rep_hi, np.int32),
@@ -64,6 +62,9 @@ class Ref:
                             *(k[n].ctypes.data for n in ("rack_of", "wF", "wL", "rep_lo", "rep_hi",
                                                         "ldr_lo", "ldr_hi", "rack_lo", "rack_hi")),
                             int(pb.ppr_lo), int(pb.ppr_hi), k["cur"].ctypes.data)
+        self.W = lib().kao_ref_words(C.byref(self.c))
+        if self.W < 1:
+            raise ValueError("unsupported topology (more than 256 rack-aligned broker slots)")
 
     def _p(self):
         return C.byref(self.c)
@@ -89,14 +90,13 @@ class Ref:
                           C.c_void_p(ob.ctypes.data), C.c_void_p(ol.ctypes.data))
         return ob, ol
 
-    def candidate_keys(self, bits, ld, seed, rnd, idxs, round_size):
-        sb, sl = self.new_candidate()
-        out = np.empty(len(idxs), np.uint64)
-        f = lib().kao_ref_candidate_key
-        for i, idx in enumerate(idxs):
-            out[i] = f(self._p(), C.c_void_p(bits.ctypes.data), C.c_void_p(ld.ctypes.data),
-                       C.c_uint64(seed), C.c_uint32(rnd), C.c_uint32(int(idx)),
-                       C.c_uint32(round_size), C.c_void_p(sb.ctypes.data), C.c_void_p(sl.ctypes.data))
+    def candidate_keys(self, bits, ld, seed, rnd, round_size, idx_begin, count, nthreads=0):
+        out = np.empty(count, np.uint64)
+        lib().kao_ref_candidate_keys(self._p(), C.c_void_p(bits.ctypes.data),
+                                     C.c_void_p(ld.ctypes.data), C.c_uint64(seed), C.c_uint32(rnd),
+                                     C.c_uint32(round_size), C.c_uint32(idx_begin),
+                                     C.c_uint32(count), C.c_void_p(out.ctypes.data),
+                                     C.c_int(nthreads))
         return out
 
     def search(self, bits, ld, seed, first_round, rounds, round_size, nthreads=0):
@@ -110,10 +110,19 @@ class Ref:
         return last, keys
 
     def decode(self, bits, ld):
+        """bit-plane -> replica lists (dense broker indices, leader first)."""
         out = np.empty((self.pb.P, self.pb.RF), np.int32)
         lib().kao_ref_decode(self._p(), C.c_void_p(bits.ctypes.data), C.c_void_p(ld.ctypes.data),
                              C.c_void_p(out.ctypes.data))
         return out
+
+    def encode(self, replicas):
+        """replica lists (dense broker indices, leader first, -1 padded) -> bit-plane."""
+        reps = np.ascontiguousarray(replicas, dtype=np.int32)
+        bits, ld = self.new_candidate()
+        lib().kao_ref_encode(self._p(), C.c_void_p(reps.ctypes.data), C.c_void_p(bits.ctypes.data),
+                             C.c_void_p(ld.ctypes.data))
+        return bits, ld
 
     @staticmethod
     def philox(ctr, key):
