@@ -125,7 +125,7 @@ int kao_candidate_keys(kao_handle *h, uint64_t seed, uint32_t round, uint32_t ro
 
 /* sharded round, asynchronous on `stream` (a cudaStream_t, 0 = default):
  *   kao_round_launch  evaluates idx_lo..idx_hi-1 and atomically min-reduces the packed key into
- *                     *d_key (DEVICE pointer, caller pre-sets it to ~0ull);
+ *                     *d_key (DEVICE pointer, caller pre-sets it to KAO_KEY_NONE);
  *   [caller min-all-reduces *d_key across ranks: one 8-byte collective]
  *   kao_round_apply   re-materialises the winning candidate from (seed, round, index) and makes
  *                     it the base.  Every rank applies the same key => identical bases. */
@@ -138,7 +138,13 @@ int kao_round_apply(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round
 int kao_stats(kao_handle *h, uint64_t *kernel_launches, int32_t *words_per_row,
               int32_t *slots, int32_t *dense_weights);
 
-/* key layout helpers: key = violation(16, saturating) | (0xFFFFFF - objective)(24) | index(24) */
+/* benchmark aid: `rounds` rounds with CUDA events around every kernel; sums per kernel kind */
+int kao_profile_rounds(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                       uint32_t round_size, double *search_ms, double *apply_ms);
+
+/* key layout: violation(15 bits, saturating; bit 63 is always 0 so keys order the same as signed
+ * int64) | (0xFFFFFF - objective)(24) | index(24).  KAO_KEY_NONE = "no candidate evaluated". */
+#define KAO_KEY_NONE 0x7FFFFFFFFFFFFFFFull
 #define KAO_KEY_VIOLATION(k) ((uint32_t)((k) >> 48))
 #define KAO_KEY_OBJECTIVE(k) (0xFFFFFFu - (uint32_t)(((k) >> 24) & 0xFFFFFFu))
 #define KAO_KEY_INDEX(k) ((uint32_t)((k) & 0xFFFFFFu))

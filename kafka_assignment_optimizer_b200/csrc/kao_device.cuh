@@ -17,7 +17,8 @@ constexpr int kMaxOps = 3;
 constexpr uint32_t kIdxBits = 24;
 constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1;
 constexpr uint32_t kObjCap = 0xFFFFFFu;
-constexpr uint32_t kViolCap = 0xFFFFu;
+constexpr uint32_t kViolCap = 0x7FFFu;      // keys < 2^63: same order as signed int64 (NCCL min)
+constexpr unsigned long long kKeyNone = 0x7FFFFFFFFFFFFFFFull;
 constexpr uint32_t kTag = 0x4B414F21u;
 constexpr int kRowsPerLane = 4;            // rows handled per lane per 128-row tile
 constexpr int kTileRows = 32 * kRowsPerLane;

@@ -103,7 +103,7 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
     gen.bitsT = s_bits; gen.leader = s_leader; gen.cs = s_cs; gen.d = &d;
     gen.prow = s_prow + warp * kMaxOps * W; gen.lane = lane;
 
-    unsigned long long best = ~0ull;
+    unsigned long long best = kKeyNone;
     const uint32_t stride = gridDim.x * kWarps;
     for (uint32_t idx = idx_lo + blockIdx.x * kWarps + warp; idx < idx_hi; idx += stride) {
         PatchSet ps;
@@ -119,13 +119,13 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
     if (lane == 0) s_red[warp] = best;
     __syncthreads();
     if (warp == 0) {
-        unsigned long long v = lane < kWarps ? s_red[lane] : ~0ull;
+        unsigned long long v = lane < kWarps ? s_red[lane] : kKeyNone;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long w = __shfl_xor_sync(0xFFFFFFFFu, v, o);
             v = w < v ? w : v;
         }
-        if (lane == 0 && v != ~0ull) atomicMin(out_key, v);
+        if (lane == 0 && v != kKeyNone) atomicMin(out_key, v);
     }
 }
 
@@ -141,7 +141,7 @@ apply_winner_kernel(Params d, uint64_t seed, uint32_t round, uint32_t round_size
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp == 0 && !regen_only) {
         const unsigned long long k = *key;
-        if (k != ~0ull) {
+        if (k != kKeyNone) {
             Gen<W> gen;
             gen.bitsT = d.bitsT; gen.leader = d.leader; gen.cs = d.consts; gen.d = &d;
             gen.prow = s_prow; gen.lane = lane;
@@ -364,7 +364,7 @@ extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **ou
     CUDA_TRY(cudaMalloc(&h->d_consts, sizeof(Consts)));
     CUDA_TRY(cudaMalloc(&h->d_key, 16));
     CUDA_TRY(cudaMemset(h->d_nD, 0, 16));
-    CUDA_TRY(cudaMemset(h->d_key, 0xFF, 16));
+    { const unsigned long long none[2] = {kKeyNone, kKeyNone}; CUDA_TRY(cudaMemcpy(h->d_key, none, 16, cudaMemcpyHostToDevice)); }
     if (m.dense) {
         CUDA_TRY(cudaMalloc(&h->d_dense, m.dense_w.size() * 4));
         CUDA_TRY(cudaMemcpy(h->d_dense, m.dense_w.data(), m.dense_w.size() * 4, cudaMemcpyHostToDevice));
@@ -488,7 +488,10 @@ extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, ui
         CUDA_TRY(cudaMalloc(&h->d_keys, (size_t)(rounds > 0 ? rounds : 1) * 8));
         h->keys_cap = rounds;
     }
-    if (rounds) CUDA_TRY(cudaMemsetAsync(h->d_keys, 0xFF, (size_t)rounds * 8, 0));
+    if (rounds) {
+        std::vector<unsigned long long> none(rounds, kKeyNone);
+        CUDA_TRY(cudaMemcpy(h->d_keys, none.data(), (size_t)rounds * 8, cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaEventRecord(h->ev0, 0));
     for (uint32_t t = 0; t < rounds; ++t) {
         CUDA_TRY(launch_round(h, seed, first_round + t, round_size, 0, round_size, h->d_keys + t, nullptr, 0));
@@ -506,6 +509,40 @@ extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, ui
     return KAO_OK;
 }
 
+extern "C" int kao_profile_rounds(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                                  uint32_t round_size, double *search_ms, double *apply_ms)
+{
+    if (!h || !rounds) return fail(KAO_E_ARG, "bad argument");
+    if (!check_round_args(round_size)) return fail(KAO_E_ARG, "bad round_size");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<cudaEvent_t> ev(3 * (size_t)rounds);
+    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+    unsigned long long *d_k = nullptr;
+    CUDA_TRY(cudaMalloc(&d_k, (size_t)rounds * 8));
+    std::vector<unsigned long long> none(rounds, kKeyNone);
+    CUDA_TRY(cudaMemcpy(d_k, none.data(), (size_t)rounds * 8, cudaMemcpyHostToDevice));
+    for (uint32_t t = 0; t < rounds; ++t) {
+        CUDA_TRY(cudaEventRecord(ev[3 * t], 0));
+        CUDA_TRY(launch_round(h, seed, first_round + t, round_size, 0, round_size, d_k + t, nullptr, 0));
+        CUDA_TRY(cudaEventRecord(ev[3 * t + 1], 0));
+        CUDA_TRY(launch_apply(h, seed, first_round + t, round_size, d_k + t, 0, 0));
+        CUDA_TRY(cudaEventRecord(ev[3 * t + 2], 0));
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    double s_ms = 0, a_ms = 0;
+    for (uint32_t t = 0; t < rounds; ++t) {
+        float a = 0, b = 0;
+        CUDA_TRY(cudaEventElapsedTime(&a, ev[3 * t], ev[3 * t + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&b, ev[3 * t + 1], ev[3 * t + 2]));
+        s_ms += a; a_ms += b;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    cudaFree(d_k);
+    if (search_ms) *search_ms = s_ms;
+    if (apply_ms) *apply_ms = a_ms;
+    return KAO_OK;
+}
+
 extern "C" int kao_candidate_keys(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
                                   uint32_t idx_begin, uint32_t count, uint64_t *keys)
 {
@@ -516,7 +553,7 @@ extern "C" int kao_candidate_keys(kao_handle *h, uint64_t seed, uint32_t round, 
     CUDA_TRY(cudaSetDevice(h->device));
     unsigned long long *d_all = nullptr;
     CUDA_TRY(cudaMalloc(&d_all, (size_t)count * 8));
-    CUDA_TRY(cudaMemset(h->d_key, 0xFF, 8));
+    { const unsigned long long none = kKeyNone; CUDA_TRY(cudaMemcpy(h->d_key, &none, 8, cudaMemcpyHostToDevice)); }
     cudaError_t e = launch_round(h, seed, round, round_size, idx_begin, idx_begin + count, h->d_key, d_all, 0);
     if (e == cudaSuccess) e = cudaMemcpy(keys, d_all, (size_t)count * 8, cudaMemcpyDeviceToHost);
     cudaFree(d_all);
@@ -580,13 +617,13 @@ extern "C" int kao_solve(const kao_problem *pb, const kao_options *opt, kao_resu
     kao_handle *h = nullptr;
     int rc = kao_create(pb, opt->device, &h);
     if (rc != KAO_OK) return rc;
-    std::vector<uint64_t> keys(opt->rounds ? opt->rounds : 1, ~0ull);
+    std::vector<uint64_t> keys(opt->rounds ? opt->rounds : 1, kKeyNone);
     double dev_ms = 0;
     rc = kao_search(h, opt->seed, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms);
     if (rc == KAO_OK) rc = kao_get_base(h, res->replicas, &res->violation, &res->objective, &res->moves);
     if (rc == KAO_OK) {
         res->feasible = res->violation == 0;
-        res->key = opt->rounds ? keys[opt->rounds - 1] : ~0ull;
+        res->key = opt->rounds ? keys[opt->rounds - 1] : kKeyNone;
         res->n_candidates = (uint64_t)opt->rounds * opt->round_size;
         res->rounds_run = opt->rounds;
         res->reserved = 0;

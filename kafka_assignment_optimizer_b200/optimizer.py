@@ -15,6 +15,7 @@ from .problem import (Problem, build_problem, parse_assignment_json, parse_broke
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkao.so")
 KAO_OK, KAO_INFEASIBLE = 0, 1
+KEY_NONE = 0x7FFFFFFFFFFFFFFF
 
 
 class KaoError(RuntimeError):
@@ -161,6 +162,13 @@ class Session:
     def round_apply(self, seed, rnd, round_size, d_key_ptr: int, stream: int = 0):
         _check(self._lib.kao_round_apply(self._h, C.c_uint64(seed), C.c_uint32(rnd), C.c_uint32(round_size),
                                          C.c_void_p(d_key_ptr), C.c_void_p(stream)))
+
+    def profile_rounds(self, seed, first_round, rounds, round_size):
+        """-> (sum of search-kernel ms, sum of apply-kernel ms), CUDA events around every launch"""
+        a, b = C.c_double(), C.c_double()
+        _check(self._lib.kao_profile_rounds(self._h, C.c_uint64(seed), C.c_uint32(first_round), C.c_uint32(rounds),
+                                            C.c_uint32(round_size), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def stats(self):
         n, w, s, dn = C.c_uint64(), C.c_int32(), C.c_int32(), C.c_int32()

@@ -42,8 +42,9 @@ typedef struct {
 } ref_problem;
 
 #define OBJ_CAP 0xFFFFFFu
-#define VIOL_CAP 0xFFFFu
+#define VIOL_CAP 0x7FFFu        /* keys stay below 2^63: they order the same as signed int64 */
 #define IDX_BITS 24
+#define KEY_NONE 0x7FFFFFFFFFFFFFFFull
 
 /* ---------------------------------------------------------------- slot space (docs/MODEL.md §2) */
 /* Brokers are re-indexed rack-major into aligned slots: slot = rack*S + rank-in-rack, S = the
@@ -556,10 +557,10 @@ uint64_t kao_ref_search(const ref_problem *pb, uint32_t *bits, uint8_t *leader, 
 {
     ref_layout L; kao_ref_layout(pb, &L);
     const size_t nb = (size_t)pb->P * L.W;
-    uint64_t last = ~0ull;
+    uint64_t last = KEY_NONE;
     uint64_t *keys = (uint64_t *)malloc((size_t)round_size * 8);
     for (uint32_t t = first_round; t < first_round + rounds; ++t) {
-        uint64_t best = ~0ull;
+        uint64_t best = KEY_NONE;
         kao_ref_candidate_keys(pb, bits, leader, seed, t, round_size, 0, round_size, keys, nthreads);
         for (uint32_t i = 0; i < round_size; ++i) if (keys[i] < best) best = keys[i];
         uint32_t widx = (uint32_t)(best & ((1u << IDX_BITS) - 1));

@@ -183,6 +183,24 @@ def with_tiebreak(pb: Problem, K: Optional[int] = None) -> Problem:
     return dataclasses.replace(pb, wF=wF.astype(np.uint16), wL=wL.astype(np.uint16))
 
 
+def with_random_tiebreak(pb: Problem, seed: int = 0) -> Problem:
+    """T2 instances with a unique optimum on small problems: weights scaled by K plus a seeded
+    random per-(p,b) preference whose total over any assignment stays below K, so only ties are
+    broken.  Uniqueness is then *checked* with :func:`is_unique_optimum`, never assumed."""
+    maxw = int(max(pb.wF.max(), pb.wL.max()))
+    K = 1
+    while (2 * K) * (maxw + 1) <= 65535:
+        K *= 2
+    q = (K - 1) // (pb.P * pb.RF)
+    if q < 8:
+        raise ValueError("problem too large for a 16-bit random tie-break")
+    rng = np.random.RandomState(seed)
+    wF = pb.wF.astype(np.int64) * K + rng.randint(0, q + 1, size=(pb.P, pb.B))
+    wL = pb.wL.astype(np.int64) * K + rng.randint(0, q + 1, size=(pb.P, pb.B))
+    assert wL.max() <= 65535 and wF.max() <= 65535
+    return dataclasses.replace(pb, wF=wF.astype(np.uint16), wL=wL.astype(np.uint16))
+
+
 # --------------------------------------------------------------------------------------
 # Plain evaluation of one assignment (the model's semantics; loops, small cases)
 # --------------------------------------------------------------------------------------

@@ -29,7 +29,9 @@ def make_problem(P, rack_sizes, RF, RFcur=None, seed=0, removed=0, tiebreak=Fals
     B0 = len(racks)
     current = [list(map(int, rng.choice(B0, size=RFcur, replace=False))) for _ in range(P)]
     pb = m.build_problem(current, list(range(B0 - removed)), rack_by_broker, RF)
-    if tiebreak:
+    if tiebreak == "random":
+        pb = m.with_random_tiebreak(pb, seed)
+    elif tiebreak:
         pb = m.with_tiebreak(pb)
     return pb
 

@@ -18,6 +18,10 @@ SHAPES = {
     "s64_r1": lambda: make_problem(90, [40], 3, seed=4),                        # one rack of 40: C7 lo = hi = 3
     "rf_up": lambda: make_problem(100, [6, 6, 6], 4, RFcur=2, seed=5),          # RF raised, ppr [1,2]
     "rf_down": lambda: make_problem(100, [8, 8, 8, 8], 2, RFcur=4, seed=6),     # RF lowered
-    "dense_small": lambda: make_problem(24, [5, 5, 4], 3, seed=7, tiebreak=True),
+    "dense_small": lambda: make_problem(24, [4, 4, 4], 3, seed=7, tiebreak=True),
+    # unique optimum (checked with the exact model in the test): round robin, one broker removed,
+    # weights scaled + seeded random per-cell preference
+    "dense_unique": lambda: m.with_random_tiebreak(m.synthetic_problem(20, 12, 4, 3, 1), 0),
+    "dense_unique2": lambda: m.with_random_tiebreak(m.synthetic_problem(12, 9, 3, 2, 1), 1),
     "tiny": lambda: make_problem(3, [2, 2], 2, seed=8),
 }

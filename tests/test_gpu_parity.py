@@ -118,7 +118,7 @@ def test_readme_vector_through_the_abi():
     assert doc["partitions"][1]["replicas"][0] == 8 and doc["partitions"][0]["replicas"] == [7, 18]
 
 
-@pytest.mark.parametrize("name", ["dense_small", "readme_tb"])
+@pytest.mark.parametrize("name", ["dense_unique", "dense_unique2", "readme_tb"])
 def test_unique_optimum_bit_exact_winner(name):
     """T2: on instances whose optimum is unique the winner equals the exact solver's, bit for bit."""
     pb = SHAPES[name]()
@@ -176,7 +176,7 @@ def test_sharded_round_equals_unsharded():
     key = torch.empty(1, dtype=torch.int64, device="cuda")
     got = []
     for rnd in range(6):
-        key.fill_(-1)                                          # ~0ull
+        key.fill_(kopt.KEY_NONE)
         for lo, hi in [(0, 700), (700, 701), (701, 2048), (2048, 3000)]:
             parts.round_launch(42, rnd, 3000, lo, hi, key.data_ptr())
         parts.round_apply(42, rnd, 3000, key.data_ptr())
