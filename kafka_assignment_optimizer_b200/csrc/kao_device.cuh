@@ -37,10 +37,15 @@ static_assert(sizeof(Consts) % 16 == 0, "bulk copy size");
 struct Params {
     int P, Ppad, B, R, RF, NS, log2S;
     int ppr_lo, ppr_hi;
-    int dense;                   // 1: weights come from dense_w (general tables), 0: from swT
+    int dense;                   // 1: weights come from dense_w (general tables in HBM)
+    int nentries;                // packed weight entries per partition in use (0..4)
+    int nplanes;                 // weighted mask planes in use (0 = objective uses entries / dense)
+    int plane_on_leader;         // bit c set: plane c applies to the leader one-hot, else to the row
+    int plane_value[6];          // weight of each plane
     uint32_t *bitsT;             // base replica bit-plane, word-major [W][Ppad]
     uint8_t *leader;             // base leader slot [Ppad] (0xFF = none)
-    const uint32_t *swT;         // sparse weight entries [4][Ppad]: slot | wF << 8 | wL << 20
+    const uint32_t *swT;         // packed weight entries [4][Ppad]: slot | wF << 8 | wL << 20
+    const uint32_t *planesT;     // weighted mask planes [nplanes][W][Ppad], or nullptr
     const uint32_t *dense_w;     // [P][NS] wF | wL << 16, or nullptr
     const uint32_t *homeT;       // [Ppad] 4 x u8 home slots (0xFF = none)
     uint16_t *D;                 // displaced partitions of the base, ascending
@@ -415,53 +420,60 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int i)
     return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
 }
 
-// Per-row terms: C1 (replica count), C7 (per-rack spread) and the rack-total accumulators, by
-// SWAR over the rack-aligned slot fields (S = 8: bytes, 16: halfwords, >= 32: whole words).
-template <int W>
-__device__ __forceinline__ int row_rack_terms(const uint32_t (&x)[W], int log2S, int R, int lo, int hi,
-                                              int RF, uint32_t (&racc)[W])
+// ------------------------------------------------------------------------------------------
+// per-row terms.  Two compile-time variants of the rack part:
+//   kHi1 (ppr_lo == 0, ppr_hi == 1, the common "replicas of a partition sit in distinct racks"):
+//        excess = popc(row) - #non-empty rack fields, with the classic non-zero-field mask;
+//   general bounds: SWAR field counts and saturating field-wise subtraction.
+// The slot layout makes a rack an aligned field of S = 8 / 16 slots or 1..8 whole words.
+// ------------------------------------------------------------------------------------------
+template <int W, bool kHi1>
+__device__ __forceinline__ int row_rack_terms(const uint32_t (&x)[W], int log2S, int R, int lo, int hi, int RF)
 {
     int n = 0, pen = 0;
     if (log2S == 3) {
 #pragma unroll
         for (int t = 0; t < W; ++t) {
-            const uint32_t c = bytecounts(x[t]);
             const int pc = __popc(x[t]);
-            racc[t] += c;
             n += pc;
-            if (hi == 1) {
-                pen += pc - __popc((c + 0x7F7F7F7Fu) & 0x80808080u);
+            if constexpr (kHi1) {
+                const uint32_t nz = (((x[t] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x[t]) & 0x80808080u;
+                pen += pc - __popc(nz);
             } else {
+                const uint32_t c = bytecounts(x[t]);
                 const uint32_t dd = (c | 0x80808080u) - (uint32_t)hi * 0x01010101u;
                 const uint32_t m = ((dd >> 7) & 0x01010101u) * 0xFFu;
                 pen += (int)(((dd & m & 0x7F7F7F7Fu) * 0x01010101u) >> 24);
-            }
-            if (lo > 0) {
-                const int nv = min(max(R - 4 * t, 0), 4);
-                const uint32_t vm = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
-                const uint32_t dd = (((uint32_t)lo * 0x01010101u) | 0x80808080u) - c;
-                const uint32_t m = ((dd >> 7) & 0x01010101u) * 0xFFu;
-                pen += (int)(((dd & m & 0x7F7F7F7Fu & vm) * 0x01010101u) >> 24);
+                if (lo > 0) {
+                    const int nv = min(max(R - 4 * t, 0), 4);
+                    const uint32_t vm = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
+                    const uint32_t d2 = (((uint32_t)lo * 0x01010101u) | 0x80808080u) - c;
+                    const uint32_t m2 = ((d2 >> 7) & 0x01010101u) * 0xFFu;
+                    pen += (int)(((d2 & m2 & 0x7F7F7F7Fu & vm) * 0x01010101u) >> 24);
+                }
             }
         }
     } else if (log2S == 4) {
 #pragma unroll
         for (int t = 0; t < W; ++t) {
-            uint32_t c = bytecounts(x[t]);
-            c = (c + (c >> 8)) & 0x00FF00FFu;
-            racc[t] += c;
-            n += __popc(x[t]);
-            {
+            const int pc = __popc(x[t]);
+            n += pc;
+            if constexpr (kHi1) {
+                const uint32_t nz = (((x[t] & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x[t]) & 0x80008000u;
+                pen += pc - __popc(nz);
+            } else {
+                uint32_t c = bytecounts(x[t]);
+                c = (c + (c >> 8)) & 0x00FF00FFu;
                 const uint32_t dd = (c | 0x80008000u) - (uint32_t)hi * 0x00010001u;
                 const uint32_t m = ((dd >> 15) & 0x00010001u) * 0xFFFFu;
                 pen += (int)(((dd & m & 0x7FFF7FFFu) * 0x00010001u) >> 16);
-            }
-            if (lo > 0) {
-                const int nv = min(max(R - 2 * t, 0), 2);
-                const uint32_t vm = nv >= 2 ? 0xFFFFFFFFu : (nv == 1 ? 0xFFFFu : 0u);
-                const uint32_t dd = (((uint32_t)lo * 0x00010001u) | 0x80008000u) - c;
-                const uint32_t m = ((dd >> 15) & 0x00010001u) * 0xFFFFu;
-                pen += (int)(((dd & m & 0x7FFF7FFFu & vm) * 0x00010001u) >> 16);
+                if (lo > 0) {
+                    const int nv = min(max(R - 2 * t, 0), 2);
+                    const uint32_t vm = nv >= 2 ? 0xFFFFFFFFu : (nv == 1 ? 0xFFFFu : 0u);
+                    const uint32_t d2 = (((uint32_t)lo * 0x00010001u) | 0x80008000u) - c;
+                    const uint32_t m2 = ((d2 >> 15) & 0x00010001u) * 0xFFFFu;
+                    pen += (int)(((d2 & m2 & 0x7FFF7FFFu & vm) * 0x00010001u) >> 16);
+                }
             }
         }
     } else {
@@ -470,7 +482,6 @@ __device__ __forceinline__ int row_rack_terms(const uint32_t (&x)[W], int log2S,
 #pragma unroll
         for (int t = 0; t < W; ++t) {
             const int pc = __popc(x[t]);
-            racc[t] += (uint32_t)pc;
             n += pc;
             c += pc;
             if (((t + 1) & (wpr - 1)) == 0) {
@@ -494,19 +505,20 @@ __device__ __forceinline__ void load_planes(uint32_t (&pl)[kPlanes], const ColCo
     for (int k = 3 + NPH; k < kPlanes; ++k) pl[k] = 0;
 }
 
-// C3 / C4: broker columns.  pl[i] = bit-sliced per-lane counts of NI 32-column items (items
-// < nA are checked against bndA, the others against bndB; item i covers slots 32*(i mod nA)..).
+// C3 / C4 / C6: broker columns.  pl[i] = bit-sliced per-lane counts of NI 32-column items (items
+// < nA are replica words checked against bndA, the others leader words checked against bndB).
 // Reduce-scatter over lanes: log2(NI) halving steps (a lane keeps half of its items and adds the
 // partner's copy of them), then plain butterfly steps; every lane ends with ONE item summed over
-// all 32 lanes and checks NI of its 32 columns against the bounds.  Returns this lane's share
-// of the violation.
+// all 32 lanes and checks NI of its 32 columns against the bounds.  A lane's NI columns lie in
+// one rack (NI <= S), so the rack totals of C6 are a segmented warp sum of the replica columns.
+// Returns this lane's share of the violation.
 template <int NI, int NP0>
 __device__ __forceinline__ int column_violation(uint32_t (&pl)[NI][kPlanes], int lane, int nA,
-                                                const uint32_t *bndA, const uint32_t *bndB)
+                                                const uint32_t *bndA, const uint32_t *bndB,
+                                                bool racks, int log2S, int R, const Consts *cs)
 {
     static_assert(NP0 + 5 <= kPlanes, "plane budget");
     int item = 0;
-    int nact = NI;
 #pragma unroll
     for (int step = 0; step < 5; ++step) {
         const int mask = 1 << step;
@@ -530,7 +542,6 @@ __device__ __forceinline__ int column_violation(uint32_t (&pl)[NI][kPlanes], int
                 }
                 pl[i][np] = carry;
             }
-            nact = half;
         } else {
             uint32_t carry = 0;
 #pragma unroll
@@ -544,7 +555,6 @@ __device__ __forceinline__ int column_violation(uint32_t (&pl)[NI][kPlanes], int
             pl[0][np] = carry;
         }
     }
-    (void)nact;
     constexpr int nsplit = (NI == 1) ? 0 : (NI == 2) ? 1 : (NI == 4) ? 2 : (NI == 8) ? 3 : 4;
     constexpr int NPF = NP0 + 5;
     const int t0 = (lane >> nsplit) * NI;                 // first of this lane's NI columns
@@ -554,7 +564,7 @@ __device__ __forceinline__ int column_violation(uint32_t (&pl)[NI][kPlanes], int
     uint32_t sh[NPF];
 #pragma unroll
     for (int k = 0; k < NPF; ++k) sh[k] = pl[0][k] >> t0;
-    int viol = 0;
+    int viol = 0, csum = 0;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
         uint32_t c = 0;
@@ -563,45 +573,56 @@ __device__ __forceinline__ int column_violation(uint32_t (&pl)[NI][kPlanes], int
         const uint32_t b = bnd[word * 32 + t0 + i];
         const int lo = (int)(b & 0xFFFFu), hi = (int)(b >> 16);
         viol += max((int)c - hi, 0) + max(lo - (int)c, 0);
+        csum += (int)c;
+    }
+    if (racks) {
+        // C6: replica columns summed per rack; leader items and padding racks form ignored groups
+        const int rk = (word * 32 + t0) >> log2S;
+        const int grp = (second || rk >= R) ? 0x7FFF : rk;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, grp);
+        const int tot = __reduce_add_sync(peers, csum);
+        if (grp != 0x7FFF && (__ffs(peers) - 1) == lane)
+            viol += max(tot - cs->rack_hi[rk], 0) + max(cs->rack_lo[rk] - tot, 0);
     }
     return viol;
 }
 
-// Evaluates candidate = base + patches.  kShared: base/weights are in shared memory.
-// Outputs (same value in every lane): total violation amount and objective.
-template <int W, int NPH, bool kShared>
-__device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
-                               const uint32_t *swT, const Consts *cs, const PatchSet &ps,
-                               const uint32_t *prow, int lane, int &viol_out, int &obj_out)
-{
-    const int P = d.P, Ppad = d.Ppad, R = d.R, RF = d.RF, log2S = d.log2S;
-    const int lo7 = d.ppr_lo, hi7 = d.ppr_hi;
-    ColCounter<W, NPH> rc, lc;
-    rc.clear();
-    lc.clear();
-    uint32_t racc[W], rwide[2 * W];
-#pragma unroll
-    for (int t = 0; t < W; ++t) { racc[t] = 0; rwide[2 * t] = rwide[2 * t + 1] = 0; }
-    int viol = 0, obj = 0;
+// Objective, three encodings of the weight tables (host picks, docs/MODEL.md §3.2):
+//   kObjPlanes  up to kMaxWPlanes "weighted mask planes": objective = sum_c v_c * popc(part_c & M_c[p]),
+//               part = the row (follower-weight classes) or the leader one-hot (leader bonus classes)
+//   kObjEntries up to 4 packed (slot, wF, wL) entries per partition
+//   dense       (inside kObjEntries, runtime flag) general [P][slots] table in HBM
+constexpr int kObjEntries = 0;   // kObj > 0: that many weighted mask planes (3 or 6, zero-padded)
+constexpr int kMaxWPlanes = 6;
 
-    const int ntiles = Ppad / kTileRows;                 // even: Ppad is a multiple of 256
-    for (int u0 = 0; u0 < ntiles; u0 += 2) {
+template <int W_, int NPH_, bool kHi1_, int kObj_> struct EvalCfg {
+    static constexpr int W = W_, NPH = NPH_, kObj = kObj_;
+    static constexpr bool kHi1 = kHi1_;
+};
+
+// one 128-row tile pair = 8 rows per lane = one carry-save block
+template <class Cfg, bool kShared, bool kCheckValid>
+__device__ __forceinline__ void eval_block(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
+                                           const uint32_t *objT, const PatchSet &ps, const uint32_t *prow,
+                                           int lane, int u0, ColCounter<Cfg::W, Cfg::NPH> &rc,
+                                           ColCounter<Cfg::W, Cfg::NPH> &lc, int &viol, int &obj)
+{
+    constexpr int W = Cfg::W;
+    const int Ppad = d.Ppad;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int u = u0 + half;
-            const int r0 = u * kTileRows + lane * kRowsPerLane;
-            uint4 xv[W], sv[4];
+    for (int half = 0; half < 2; ++half) {
+        const int u = u0 + half;
+        const int r0 = u * kTileRows + lane * kRowsPerLane;
+        uint4 xv[W];
 #pragma unroll
-            for (int t = 0; t < W; ++t) xv[t] = ld128<kShared>(bitsT + (size_t)t * Ppad + r0);
-            uint32_t ld4 = ld32<kShared>(leader + r0);
+        for (int t = 0; t < W; ++t) xv[t] = ld128<kShared>(bitsT + (size_t)t * Ppad + r0);
+        uint32_t ld4 = ld32<kShared>(leader + r0);
+        // rare: a patched row lives in this tile
 #pragma unroll
-            for (int k = 0; k < 4; ++k) sv[k] = ld128<kShared>(swT + (size_t)k * Ppad + r0);
-            // rare: a patched row lives in this tile
-#pragma unroll
-            for (int i = 0; i < kMaxOps; ++i) {
-                const int pp = ps.p[i];                   // -1 when unused: never matches a tile
-                const uint32_t pl = ps.ld[i];
-                if ((pp >> 7) == u && ((pp & 127) >> 2) == lane) {
+        for (int i = 0; i < kMaxOps; ++i) {
+            const int pp = ps.p[i];                       // -1 when unused: never matches a tile
+            if ((pp >> 7) == u) {
+                if (((pp & 127) >> 2) == lane) {
                     const int rr = pp & 3;
 #pragma unroll
                     for (int t = 0; t < W; ++t) {
@@ -609,34 +630,58 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
                         if (rr == 0) xv[t].x = v; else if (rr == 1) xv[t].y = v;
                         else if (rr == 2) xv[t].z = v; else xv[t].w = v;
                     }
-                    ld4 = (ld4 & ~(0xFFu << (8 * rr))) | (pl << (8 * rr));
+                    ld4 = (ld4 & ~(0xFFu << (8 * rr))) | (ps.ld[i] << (8 * rr));
                 }
             }
+        }
+        uint4 ov[Cfg::kObj > 0 ? Cfg::kObj * W : 4];
+        if constexpr (Cfg::kObj > 0) {
 #pragma unroll
-            for (int i = 0; i < kRowsPerLane; ++i) {
-                uint32_t x[W], oh[W];
+            for (int c = 0; c < Cfg::kObj; ++c) {
 #pragma unroll
-                for (int t = 0; t < W; ++t) x[t] = comp(xv[t], i);
-                const uint32_t ld = (ld4 >> (8 * i)) & 0xFFu;
-                const bool valid = (r0 + i) < P;
-                // leader one-hot restricted to the row: C2/C5 by construction of the encoding
-                const uint32_t ldbit = 1u << (ld & 31);
-                uint32_t any = 0;
+                for (int t = 0; t < W; ++t) ov[c * W + t] = ld128<kShared>(objT + (size_t)(c * W + t) * Ppad + r0);
+            }
+        } else {
 #pragma unroll
-                for (int t = 0; t < W; ++t) { oh[t] = ((int)(ld >> 5) == t) ? (x[t] & ldbit) : 0u; any |= oh[t]; }
-                int rv = row_rack_terms<W>(x, log2S, R, lo7, hi7, RF, racc) + (any ? 0 : 1);
-                viol += valid ? rv : 0;
-                // objective: sparse weight entries of this partition
+            for (int k = 0; k < 4; ++k)
+                if (k < d.nentries) ov[k] = ld128<kShared>(objT + (size_t)k * Ppad + r0);
+        }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t e = comp(sv[k], i);
-                    const uint32_t slot = e & 0xFFu;
-                    const uint32_t xw = row_word<W>(x, (int)(slot >> 5));
-                    const bool bit = (xw >> (slot & 31)) & 1u;
-                    const uint32_t w = (slot == ld) ? (e >> 20) : ((e >> 8) & 0xFFFu);
-                    obj += bit ? (int)w : 0;
+        for (int i = 0; i < kRowsPerLane; ++i) {
+            uint32_t x[W], oh[W];
+#pragma unroll
+            for (int t = 0; t < W; ++t) x[t] = comp(xv[t], i);
+            const uint32_t ld = (ld4 >> (8 * i)) & 0xFFu;
+            // leader one-hot restricted to the row: C2/C5 hold by construction of the encoding
+            const uint32_t ldbit = __funnelshift_l(0u, 1u, ld);      // 1 << (ld & 31)
+            uint32_t any = 0;
+#pragma unroll
+            for (int t = 0; t < W; ++t) { oh[t] = ((int)(ld >> 5) == t) ? (x[t] & ldbit) : 0u; any |= oh[t]; }
+            int rv = row_rack_terms<W, Cfg::kHi1>(x, d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF) + (any ? 0 : 1);
+            if constexpr (kCheckValid) rv = ((r0 + i) < d.P) ? rv : 0;
+            viol += rv;
+            if constexpr (Cfg::kObj > 0) {
+#pragma unroll
+                for (int c = 0; c < Cfg::kObj; ++c) {
+                    int cnt = 0;
+                    const bool on_leader = (d.plane_on_leader >> c) & 1;
+#pragma unroll
+                    for (int t = 0; t < W; ++t)
+                        cnt += __popc((on_leader ? oh[t] : x[t]) & comp(ov[c * W + t], i));
+                    obj += cnt * d.plane_value[c];
                 }
-                if (d.dense && valid) {
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < d.nentries) {
+                        const uint32_t e = comp(ov[k], i);
+                        const uint32_t slot = e & 0xFFu;
+                        const uint32_t xw = row_word<W>(x, (int)(slot >> 5));
+                        const bool bit = __funnelshift_r(xw, 0u, slot) & 1u;
+                        const uint32_t w = (slot == ld) ? (e >> 20) : ((e >> 8) & 0xFFFu);
+                        obj += bit ? (int)w : 0;
+                    }
+                if (d.dense && (!kCheckValid || (r0 + i) < d.P)) {
                     const uint32_t *wrow = d.dense_w + (size_t)(r0 + i) * d.NS;
 #pragma unroll
                     for (int t = 0; t < W; ++t) {
@@ -649,56 +694,42 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
                         }
                     }
                 }
-                if (half == 0) {
-                    if (i == 0) { rc.template push<0>(x); lc.template push<0>(oh); }
-                    if (i == 1) { rc.template push<1>(x); lc.template push<1>(oh); }
-                    if (i == 2) { rc.template push<2>(x); lc.template push<2>(oh); }
-                    if (i == 3) { rc.template push<3>(x); lc.template push<3>(oh); }
-                } else {
-                    if (i == 0) { rc.template push<4>(x); lc.template push<4>(oh); }
-                    if (i == 1) { rc.template push<5>(x); lc.template push<5>(oh); }
-                    if (i == 2) { rc.template push<6>(x); lc.template push<6>(oh); }
-                    if (i == 3) { rc.template push<7>(x); lc.template push<7>(oh); }
-                }
             }
-        }
-        if (log2S == 3) {            // widen the byte-packed rack accumulators before they can overflow
-#pragma unroll
-            for (int t = 0; t < W; ++t) {
-                rwide[2 * t] += racc[t] & 0x00FF00FFu;
-                rwide[2 * t + 1] += (racc[t] >> 8) & 0x00FF00FFu;
-                racc[t] = 0;
+            if (half == 0) {
+                if (i == 0) { rc.template push<0>(x); lc.template push<0>(oh); }
+                if (i == 1) { rc.template push<1>(x); lc.template push<1>(oh); }
+                if (i == 2) { rc.template push<2>(x); lc.template push<2>(oh); }
+                if (i == 3) { rc.template push<3>(x); lc.template push<3>(oh); }
+            } else {
+                if (i == 0) { rc.template push<4>(x); lc.template push<4>(oh); }
+                if (i == 1) { rc.template push<5>(x); lc.template push<5>(oh); }
+                if (i == 2) { rc.template push<6>(x); lc.template push<6>(oh); }
+                if (i == 3) { rc.template push<7>(x); lc.template push<7>(oh); }
             }
         }
     }
+}
 
-    // ---- C6: rack totals = sum over lanes of the per-lane rack accumulators
-    int pen_u = 0;                                        // warp-uniform part of the violation
-    {
-        constexpr int kMaxR = 4 * W;
-#pragma unroll
-        for (int r = 0; r < kMaxR; ++r) {
-            if (r < R) {
-                uint32_t v = 0;
-                if (log2S == 3) {
-                    v = (rwide[2 * (r >> 2) + (r & 1)] >> (16 * ((r >> 1) & 1))) & 0xFFFFu;
-                } else if (log2S == 4) {
-                    if (r < 2 * W) v = (racc[(r >> 1) < W ? (r >> 1) : 0] >> (16 * (r & 1))) & 0xFFFFu;
-                } else {
-                    const int sh = log2S - 5;
-#pragma unroll
-                    for (int t = 0; t < W; ++t) v += ((t >> sh) == r) ? racc[t] : 0u;
-                }
-                const int tot = __reduce_add_sync(0xFFFFFFFFu, (int)v);
-                pen_u += max(tot - cs->rack_hi[r], 0) + max(cs->rack_lo[r] - tot, 0);
-            }
-        }
-    }
+// Evaluates candidate = base + patches.  kShared: base/weights are in shared memory.
+// Outputs (same value in every lane): total violation amount and objective.
+template <class Cfg, bool kShared>
+__device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
+                               const uint32_t *objT, const Consts *cs, const PatchSet &ps,
+                               const uint32_t *prow, int lane, int &viol_out, int &obj_out)
+{
+    constexpr int W = Cfg::W, NPH = Cfg::NPH;
+    ColCounter<W, NPH> rc, lc;
+    rc.clear();
+    lc.clear();
+    int viol = 0, obj = 0;
+    const int ntiles = d.Ppad / kTileRows;               // even: Ppad is a multiple of 256
+    const int nfull = (d.P / (2 * kTileRows)) * 2;        // tiles of blocks made of real rows only
+    int u0 = 0;
+    for (; u0 < nfull; u0 += 2)
+        eval_block<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u0, rc, lc, viol, obj);
+    for (; u0 < ntiles; u0 += 2)
+        eval_block<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u0, rc, lc, viol, obj);
 
-    // ---- C3 / C4: broker columns.  Items 0..W-1 = replica words, W..2W-1 = leader words, each a
-    // bit-sliced per-lane count.  Reduce-scatter over lanes: log2(2W) halving steps (each lane keeps
-    // half of the items), then plain butterfly steps; every lane ends with ONE item summed over
-    // all 32 lanes and extracts 2W of its 32 columns.
     constexpr int NP0 = 3 + NPH;
     if constexpr (W <= 2) {
         // both counter sets in one pass: items 0..W-1 replica words, W..2W-1 leader words
@@ -708,17 +739,17 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
             load_planes<W, NPH>(pl[t], rc, t);
             load_planes<W, NPH>(pl[W + t], lc, t);
         }
-        viol += column_violation<2 * W, NP0>(pl, lane, W, cs->bnd_rep, cs->bnd_ldr);
+        viol += column_violation<2 * W, NP0>(pl, lane, W, cs->bnd_rep, cs->bnd_ldr, true, d.log2S, d.R, cs);
     } else {
         uint32_t pl[W][kPlanes];
 #pragma unroll
         for (int t = 0; t < W; ++t) load_planes<W, NPH>(pl[t], rc, t);
-        viol += column_violation<W, NP0>(pl, lane, W, cs->bnd_rep, cs->bnd_rep);
+        viol += column_violation<W, NP0>(pl, lane, W, cs->bnd_rep, cs->bnd_rep, true, d.log2S, d.R, cs);
 #pragma unroll
         for (int t = 0; t < W; ++t) load_planes<W, NPH>(pl[t], lc, t);
-        viol += column_violation<W, NP0>(pl, lane, W, cs->bnd_ldr, cs->bnd_ldr);
+        viol += column_violation<W, NP0>(pl, lane, W, cs->bnd_ldr, cs->bnd_ldr, false, d.log2S, d.R, cs);
     }
-    viol_out = __reduce_add_sync(0xFFFFFFFFu, viol) + pen_u;
+    viol_out = __reduce_add_sync(0xFFFFFFFFu, viol);
     obj_out = __reduce_add_sync(0xFFFFFFFFu, obj);
 }
 

@@ -48,12 +48,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 struct SmemPlan {
     uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, total;
 };
-static SmemPlan make_plan(int W, int Ppad, int warps)
+static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row)
 {
     SmemPlan s;
     uint32_t o = 0;
     s.off_bits = o;   o += (uint32_t)W * Ppad * 4;
-    s.off_sw = o;     o += 4u * Ppad * 4;
+    s.off_sw = o;     o += (uint32_t)obj_words_per_row * Ppad * 4;
     s.off_leader = o; o += (uint32_t)Ppad;
     s.off_consts = o; o += (uint32_t)sizeof(Consts);
     s.off_prow = o;   o += (uint32_t)warps * kMaxOps * W * 4;
@@ -68,7 +68,7 @@ static SmemPlan make_plan(int W, int Ppad, int warps)
 // generates the candidate from the shared-memory base, evaluates it in full and keeps the minimum
 // packed key; the block minimum goes to *out_key with one atomicMin.  all_keys (optional)
 // receives every candidate's key (parity tests).
-template <int W, int NPH, int THREADS>
+template <class Cfg, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint32_t round_size,
                     uint32_t idx_lo, uint32_t idx_hi, unsigned long long *out_key,
@@ -85,15 +85,18 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = THREADS / 32;
+    constexpr int W = Cfg::W;
+    const uint32_t *g_obj = Cfg::kObj > 0 ? d.planesT : d.swT;
+    const uint32_t obj_words = Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries;
 
     // stage base + tables: HBM/L2 -> shared memory with TMA bulk copies, one mbarrier
     if (tid == 0) mbar_init(s_bar, 1);
     __syncthreads();
     if (tid == 0) {
-        const uint32_t nb = (uint32_t)W * d.Ppad * 4, ns = 4u * d.Ppad * 4, nl = (uint32_t)d.Ppad;
+        const uint32_t nb = (uint32_t)W * d.Ppad * 4, ns = obj_words * d.Ppad * 4, nl = (uint32_t)d.Ppad;
         mbar_expect_tx(s_bar, nb + ns + nl + (uint32_t)sizeof(Consts));
         bulk_g2s(s_bits, d.bitsT, nb, s_bar);
-        bulk_g2s(s_sw, d.swT, ns, s_bar);
+        if (ns) bulk_g2s(s_sw, g_obj, ns, s_bar);
         bulk_g2s(s_leader, d.leader, nl, s_bar);
         bulk_g2s(s_cs, d.consts, (uint32_t)sizeof(Consts), s_bar);
     }
@@ -110,7 +113,7 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
         gen.run(seed, round, idx, round_size, ps);
         __syncwarp();
         int viol, obj;
-        eval_candidate<W, NPH, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
+        eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
         const unsigned long long key = pack_key(viol, obj, idx);
         if (all_keys && lane == 0) all_keys[idx - idx_lo] = key;
         best = key < best ? key : best;
@@ -221,8 +224,9 @@ eval_batch_kernel(Params d, const uint32_t *cand_bits, const uint8_t *cand_leade
 #pragma unroll
     for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
     int viol, obj;
-    eval_candidate<W, NPH, false>(d, cand_bits + (size_t)w * W * d.Ppad, cand_leader + (size_t)w * d.Ppad,
-                                  d.swT, d.consts, ps, nullptr, lane, viol, obj);
+    eval_candidate<EvalCfg<W, NPH, false, kObjEntries>, false>(d, cand_bits + (size_t)w * W * d.Ppad,
+                                                               cand_leader + (size_t)w * d.Ppad, d.swT, d.consts, ps,
+                                                               nullptr, lane, viol, obj);
     if (lane == 0) { viol_out[w] = viol; obj_out[w] = obj; }
 }
 
@@ -247,7 +251,7 @@ struct kao_handle {
     int threads = 0, grid = 0;
     // device buffers
     uint32_t *d_bits = nullptr; uint8_t *d_leader = nullptr; uint32_t *d_sw = nullptr;
-    uint32_t *d_dense = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
+    uint32_t *d_dense = nullptr; uint32_t *d_planes = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
     Consts *d_consts = nullptr; unsigned long long *d_key = nullptr; unsigned long long *d_keys = nullptr;
     size_t keys_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -256,13 +260,13 @@ struct kao_handle {
 
 template <int W> static constexpr int threads_for() { return W <= 2 ? 512 : 256; }
 
-template <int W>
-static cudaError_t launch_round_t(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
-                                  uint32_t lo, uint32_t hi, unsigned long long *d_key,
-                                  unsigned long long *d_all, cudaStream_t st)
+template <class Cfg>
+static cudaError_t launch_round_cfg(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                    uint32_t lo, uint32_t hi, unsigned long long *d_key,
+                                    unsigned long long *d_all, cudaStream_t st)
 {
-    constexpr int T = threads_for<W>();
-    auto kern = search_round_kernel<W, 5, T>;
+    constexpr int T = threads_for<Cfg::W>();
+    auto kern = search_round_kernel<Cfg, T>;
     static bool attr_done[64] = {};
     if (!attr_done[h->device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -278,16 +282,36 @@ static cudaError_t launch_round_t(kao_handle *h, uint64_t seed, uint32_t round, 
     ++h->launches;
     return cudaGetLastError();
 }
+template <int W, int NPH>
+static cudaError_t launch_round_w(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                  uint32_t lo, uint32_t hi, unsigned long long *d_key,
+                                  unsigned long long *d_all, cudaStream_t st)
+{
+    const int planes = h->prm.nplanes;
+    const bool hi1 = h->hm.hi1;
+    if constexpr (W <= 2) {
+        if (planes == 3 && hi1) return launch_round_cfg<EvalCfg<W, NPH, true, 3>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+        if (planes == 3) return launch_round_cfg<EvalCfg<W, NPH, false, 3>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+        if (planes == 6 && hi1) return launch_round_cfg<EvalCfg<W, NPH, true, 6>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+        if (planes == 6) return launch_round_cfg<EvalCfg<W, NPH, false, 6>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+    }
+    if (hi1) return launch_round_cfg<EvalCfg<W, NPH, true, kObjEntries>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+    return launch_round_cfg<EvalCfg<W, NPH, false, kObjEntries>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+}
 static cudaError_t launch_round(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
                                 uint32_t lo, uint32_t hi, unsigned long long *d_key,
                                 unsigned long long *d_all, cudaStream_t st)
 {
+    const bool small = h->hm.Ppad / 32 <= 63;             // per-lane column counts fit 6 planes
+#define KAO_ROUND(Wv) (small ? launch_round_w<Wv, 3>(h, seed, round, round_size, lo, hi, d_key, d_all, st) \
+                             : launch_round_w<Wv, 5>(h, seed, round, round_size, lo, hi, d_key, d_all, st))
     switch (h->hm.W) {
-    case 1: return launch_round_t<1>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
-    case 2: return launch_round_t<2>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
-    case 4: return launch_round_t<4>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
-    default: return launch_round_t<8>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+    case 1: return KAO_ROUND(1);
+    case 2: return KAO_ROUND(2);
+    case 4: return KAO_ROUND(4);
+    default: return KAO_ROUND(8);
     }
+#undef KAO_ROUND
 }
 static cudaError_t launch_apply(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
                                 const unsigned long long *d_key, int regen_only, cudaStream_t st)
@@ -318,7 +342,7 @@ extern "C" int kao_destroy(kao_handle *h)
 {
     if (!h) return KAO_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->d_bits); cudaFree(h->d_leader); cudaFree(h->d_sw); cudaFree(h->d_dense);
+    cudaFree(h->d_bits); cudaFree(h->d_leader); cudaFree(h->d_sw); cudaFree(h->d_dense); cudaFree(h->d_planes);
     cudaFree(h->d_home); cudaFree(h->d_D); cudaFree(h->d_DL); cudaFree(h->d_nD); cudaFree(h->d_consts);
     cudaFree(h->d_key); cudaFree(h->d_keys);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -348,7 +372,7 @@ extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **ou
     const HostModel &m = h->hm;
     const int W = m.W, Ppad = m.Ppad;
     h->threads = W <= 2 ? 512 : 256;
-    h->plan = make_plan(W, Ppad, h->threads / 32);
+    h->plan = make_plan(W, Ppad, h->threads / 32, m.nplanes > 0 ? m.nplanes * W : 4);
     if (h->plan.total > 227u * 1024u) {
         kao_destroy(h);
         return fail(KAO_E_ARG, "problem too large for the shared-memory resident search kernel");
@@ -370,6 +394,10 @@ extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **ou
         CUDA_TRY(cudaMemcpy(h->d_dense, m.dense_w.data(), m.dense_w.size() * 4, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemcpy(h->d_sw, m.swT.data(), m.swT.size() * 4, cudaMemcpyHostToDevice));
+    if (m.nplanes > 0) {
+        CUDA_TRY(cudaMalloc(&h->d_planes, m.planesT.size() * 4));
+        CUDA_TRY(cudaMemcpy(h->d_planes, m.planesT.data(), m.planesT.size() * 4, cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMemcpy(h->d_home, m.homeT.data(), m.homeT.size() * 4, cudaMemcpyHostToDevice));
     Consts cs;
     fill_consts(m, cs);
@@ -379,6 +407,9 @@ extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **ou
     Params &p = h->prm;
     p.P = m.P; p.Ppad = Ppad; p.B = m.B; p.R = m.R; p.RF = m.RF; p.NS = m.NS; p.log2S = m.log2S;
     p.ppr_lo = m.ppr_lo; p.ppr_hi = m.ppr_hi; p.dense = m.dense ? 1 : 0;
+    p.nentries = m.nentries; p.nplanes = m.nplanes; p.plane_on_leader = m.plane_on_leader;
+    for (int c = 0; c < 6; ++c) p.plane_value[c] = m.plane_value[c];
+    p.planesT = h->d_planes;
     p.bitsT = h->d_bits; p.leader = h->d_leader; p.swT = h->d_sw; p.dense_w = h->d_dense;
     p.homeT = h->d_home; p.D = h->d_D; p.DL = h->d_DL; p.nD = h->d_nD; p.consts = h->d_consts;
     int rc = kao_reset(h);

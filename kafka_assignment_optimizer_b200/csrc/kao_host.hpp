@@ -23,6 +23,12 @@ struct HostModel {
     std::vector<int32_t> rack_lo, rack_hi;
     std::vector<uint32_t> bnd_rep, bnd_ldr;   // [256] lo | hi << 16 in slot space
     std::vector<uint32_t> swT;                // [4][Ppad]
+    int nentries = 0;                         // entries per partition in use
+    // weighted mask planes (docs/MODEL.md §3.2): objective = sum_c value_c * popc(part_c & M_c[p])
+    int nplanes = 0, plane_on_leader = 0;
+    int plane_value[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<uint32_t> planesT;            // [nplanes][W][Ppad]
+    bool hi1 = false;                         // C7 is exactly "at most one replica per rack"
     std::vector<uint32_t> dense_w;            // [P][NS] when dense
     std::vector<uint32_t> homeT;              // [Ppad]
 };
@@ -120,6 +126,47 @@ inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &w
             }
         }
     }
+    m.nentries = 0;
+    if (!m.dense)
+        for (int k = 0; k < 4; ++k)
+            for (int p = 0; p < pb.P; ++p)
+                if (m.swT[(size_t)k * m.Ppad + p]) m.nentries = k + 1;
+    // mask planes: one per distinct follower weight (applied to the row) and one per distinct
+    // leader bonus wL - wF (applied to the leader one-hot); needs wL >= wF everywhere and at most
+    // six distinct values in total, and only pays off for narrow rows
+    {
+        std::vector<uint32_t> vf, vd;
+        bool ok = (m.W <= 2);
+        for (size_t i = 0; ok && i < (size_t)pb.P * pb.B; ++i) {
+            const uint32_t f = pb.wF[i], l = pb.wL[i];
+            if (l < f) { ok = false; break; }
+            if (f && std::find(vf.begin(), vf.end(), f) == vf.end()) vf.push_back(f);
+            if (l - f && std::find(vd.begin(), vd.end(), l - f) == vd.end()) vd.push_back(l - f);
+            if (vf.size() + vd.size() > 6) ok = false;
+        }
+        if (ok && vf.size() + vd.size() > 0) {
+            std::sort(vf.begin(), vf.end());
+            std::sort(vd.begin(), vd.end());
+            const int used = (int)(vf.size() + vd.size());
+            m.nplanes = used <= 3 ? 3 : 6;                 // kernels exist for 3 and 6 planes; pad with empty ones
+            m.planesT.assign((size_t)m.nplanes * m.W * m.Ppad, 0);
+            for (int c = 0; c < used; ++c) {
+                const bool on_leader = c >= (int)vf.size();
+                const uint32_t val = on_leader ? vd[c - vf.size()] : vf[c];
+                m.plane_value[c] = (int)val;
+                if (on_leader) m.plane_on_leader |= 1 << c;
+                for (int p = 0; p < pb.P; ++p)
+                    for (int b = 0; b < pb.B; ++b) {
+                        const uint32_t f = pb.wF[(size_t)p * pb.B + b], l = pb.wL[(size_t)p * pb.B + b];
+                        if ((on_leader ? l - f : f) == val) {
+                            const int s = m.slot_of_broker[b];
+                            m.planesT[((size_t)c * m.W + (s >> 5)) * m.Ppad + p] |= 1u << (s & 31);
+                        }
+                    }
+            }
+        }
+    }
+    m.hi1 = (pb.ppr_lo == 0 && pb.ppr_hi == 1);
     // home slots: the first four surviving entries of cur[p]
     m.homeT.assign((size_t)m.Ppad, 0xFFFFFFFFu);
     for (int p = 0; p < pb.P; ++p) {
