@@ -124,8 +124,8 @@ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t n) { return __u
 // ------------------------------------------------------------------------------------------
 struct PatchSet {
     int n;
-    int p[kMaxOps];
-    uint32_t ld[kMaxOps];
+    int p[kMaxOps];          // patched partition, -1 = unused
+    uint32_t ld[kMaxOps];    // its leader slot in the candidate
 };
 
 template <int W> struct Gen {
@@ -339,47 +339,36 @@ __device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32
     l = u ^ c;
 }
 
-// Bit-sliced per-lane column counter: planes 1,2,4 + NPH high planes (8,16,...).  Inputs are
-// pushed in blocks of 8 (Harley-Seal): ~2.5 LOP3 per pushed word.
+// Bit-sliced per-lane column counter: planes 1,2,4 + NPH high planes (8,16,...).  Rows are pushed
+// four at a time (one 128-row tile): three carry-save adders fold them with the ones/twos planes
+// into one weight-4 word that ripples up the higher planes (~3.5 LOP3 per pushed word).
 template <int W, int NPH> struct ColCounter {
     uint32_t ones[W], twos[W], fours[W], hi[NPH][W];
-    uint32_t hold[W], twosA[W], foursA[W];
     __device__ __forceinline__ void clear()
     {
 #pragma unroll
         for (int t = 0; t < W; ++t) {
-            ones[t] = twos[t] = fours[t] = hold[t] = twosA[t] = foursA[t] = 0;
+            ones[t] = twos[t] = fours[t] = 0;
 #pragma unroll
             for (int k = 0; k < NPH; ++k) hi[k][t] = 0;
         }
     }
-    template <int I> __device__ __forceinline__ void push(const uint32_t (&x)[W])
+    __device__ __forceinline__ void push4(const uint32_t (&x0)[W], const uint32_t (&x1)[W],
+                                          const uint32_t (&x2)[W], const uint32_t (&x3)[W])
     {
 #pragma unroll
         for (int t = 0; t < W; ++t) {
-            if constexpr ((I & 1) == 0) {
-                hold[t] = x[t];
-            } else {
-                uint32_t t2;
-                csa(t2, ones[t], ones[t], hold[t], x[t]);
-                if constexpr ((I & 3) == 1) {
-                    twosA[t] = t2;
-                } else {
-                    uint32_t t4;
-                    csa(t4, twos[t], twos[t], twosA[t], t2);
-                    if constexpr (I == 3) {
-                        foursA[t] = t4;
-                    } else {
-                        uint32_t t8;
-                        csa(t8, fours[t], fours[t], foursA[t], t4);
+            uint32_t a2, b2, c4;
+            csa(a2, ones[t], ones[t], x0[t], x1[t]);
+            csa(b2, ones[t], ones[t], x2[t], x3[t]);
+            csa(c4, twos[t], twos[t], a2, b2);
+            uint32_t cy = fours[t] & c4;
+            fours[t] ^= c4;
 #pragma unroll
-                        for (int k = 0; k < NPH; ++k) {
-                            const uint32_t cy = hi[k][t] & t8;
-                            hi[k][t] ^= t8;
-                            t8 = cy;
-                        }
-                    }
-                }
+            for (int k = 0; k < NPH; ++k) {
+                const uint32_t n = hi[k][t] & cy;
+                hi[k][t] ^= cy;
+                cy = n;
             }
         }
     }
@@ -600,114 +589,101 @@ template <int W_, int NPH_, bool kHi1_, int kObj_> struct EvalCfg {
     static constexpr bool kHi1 = kHi1_;
 };
 
-// one 128-row tile pair = 8 rows per lane = one carry-save block
+// one 128-row tile: 4 consecutive rows per lane (128-bit shared-memory loads, conflict-free)
 template <class Cfg, bool kShared, bool kCheckValid>
-__device__ __forceinline__ void eval_block(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
-                                           const uint32_t *objT, const PatchSet &ps, const uint32_t *prow,
-                                           int lane, int u0, ColCounter<Cfg::W, Cfg::NPH> &rc,
-                                           ColCounter<Cfg::W, Cfg::NPH> &lc, int &viol, int &obj)
+__device__ __forceinline__ void eval_tile(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
+                                          const uint32_t *objT, const PatchSet &ps, const uint32_t *prow,
+                                          int lane, int u, ColCounter<Cfg::W, Cfg::NPH> &rc,
+                                          ColCounter<Cfg::W, Cfg::NPH> &lc, int &viol, int &obj)
 {
     constexpr int W = Cfg::W;
     const int Ppad = d.Ppad;
+    const int r0 = u * kTileRows + lane * kRowsPerLane;
+    uint4 xv[W];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int u = u0 + half;
-        const int r0 = u * kTileRows + lane * kRowsPerLane;
-        uint4 xv[W];
-#pragma unroll
-        for (int t = 0; t < W; ++t) xv[t] = ld128<kShared>(bitsT + (size_t)t * Ppad + r0);
-        uint32_t ld4 = ld32<kShared>(leader + r0);
-        // rare: a patched row lives in this tile
+    for (int t = 0; t < W; ++t) xv[t] = ld128<kShared>(bitsT + (size_t)t * Ppad + r0);
+    uint32_t ld4 = ld32<kShared>(leader + r0);
+    // rare (warp-uniform test): a patched row lives in this tile
+    if (((ps.p[0] >> 7) == u) | ((ps.p[1] >> 7) == u) | ((ps.p[2] >> 7) == u)) {
 #pragma unroll
         for (int i = 0; i < kMaxOps; ++i) {
             const int pp = ps.p[i];                       // -1 when unused: never matches a tile
-            if ((pp >> 7) == u) {
-                if (((pp & 127) >> 2) == lane) {
-                    const int rr = pp & 3;
+            if ((pp >> 7) == u && ((pp & 127) >> 2) == lane) {
+                const int rr = pp & 3;
 #pragma unroll
-                    for (int t = 0; t < W; ++t) {
-                        const uint32_t v = prow[i * W + t];
-                        if (rr == 0) xv[t].x = v; else if (rr == 1) xv[t].y = v;
-                        else if (rr == 2) xv[t].z = v; else xv[t].w = v;
-                    }
-                    ld4 = (ld4 & ~(0xFFu << (8 * rr))) | (ps.ld[i] << (8 * rr));
+                for (int t = 0; t < W; ++t) {
+                    const uint32_t v = prow[i * W + t];
+                    if (rr == 0) xv[t].x = v; else if (rr == 1) xv[t].y = v;
+                    else if (rr == 2) xv[t].z = v; else xv[t].w = v;
                 }
+                ld4 = (ld4 & ~(0xFFu << (8 * rr))) | (ps.ld[i] << (8 * rr));
             }
         }
-        uint4 ov[Cfg::kObj > 0 ? Cfg::kObj * W : 4];
+    }
+    uint4 ov[Cfg::kObj > 0 ? Cfg::kObj * W : 4];
+    if constexpr (Cfg::kObj > 0) {
+#pragma unroll
+        for (int c = 0; c < Cfg::kObj; ++c) {
+#pragma unroll
+            for (int t = 0; t < W; ++t) ov[c * W + t] = ld128<kShared>(objT + (size_t)(c * W + t) * Ppad + r0);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < d.nentries) ov[k] = ld128<kShared>(objT + (size_t)k * Ppad + r0);
+    }
+    uint32_t x[kRowsPerLane][W], oh[kRowsPerLane][W];
+#pragma unroll
+    for (int i = 0; i < kRowsPerLane; ++i) {
+#pragma unroll
+        for (int t = 0; t < W; ++t) x[i][t] = comp(xv[t], i);
+        const uint32_t ld = (ld4 >> (8 * i)) & 0xFFu;
+        // leader one-hot restricted to the row: C2/C5 hold by construction of the encoding
+        const uint32_t ldbit = __funnelshift_l(0u, 1u, ld);      // 1 << (ld & 31)
+        uint32_t any = 0;
+#pragma unroll
+        for (int t = 0; t < W; ++t) { oh[i][t] = ((int)(ld >> 5) == t) ? (x[i][t] & ldbit) : 0u; any |= oh[i][t]; }
+        int rv = row_rack_terms<W, Cfg::kHi1>(x[i], d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF) + (any ? 0 : 1);
+        if constexpr (kCheckValid) rv = ((r0 + i) < d.P) ? rv : 0;
+        viol += rv;
         if constexpr (Cfg::kObj > 0) {
 #pragma unroll
             for (int c = 0; c < Cfg::kObj; ++c) {
+                int cnt = 0;
+                const bool on_leader = (d.plane_on_leader >> c) & 1;
 #pragma unroll
-                for (int t = 0; t < W; ++t) ov[c * W + t] = ld128<kShared>(objT + (size_t)(c * W + t) * Ppad + r0);
+                for (int t = 0; t < W; ++t)
+                    cnt += __popc((on_leader ? oh[i][t] : x[i][t]) & comp(ov[c * W + t], i));
+                obj += cnt * d.plane_value[c];
             }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (k < d.nentries) ov[k] = ld128<kShared>(objT + (size_t)k * Ppad + r0);
-        }
-#pragma unroll
-        for (int i = 0; i < kRowsPerLane; ++i) {
-            uint32_t x[W], oh[W];
-#pragma unroll
-            for (int t = 0; t < W; ++t) x[t] = comp(xv[t], i);
-            const uint32_t ld = (ld4 >> (8 * i)) & 0xFFu;
-            // leader one-hot restricted to the row: C2/C5 hold by construction of the encoding
-            const uint32_t ldbit = __funnelshift_l(0u, 1u, ld);      // 1 << (ld & 31)
-            uint32_t any = 0;
-#pragma unroll
-            for (int t = 0; t < W; ++t) { oh[t] = ((int)(ld >> 5) == t) ? (x[t] & ldbit) : 0u; any |= oh[t]; }
-            int rv = row_rack_terms<W, Cfg::kHi1>(x, d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF) + (any ? 0 : 1);
-            if constexpr (kCheckValid) rv = ((r0 + i) < d.P) ? rv : 0;
-            viol += rv;
-            if constexpr (Cfg::kObj > 0) {
-#pragma unroll
-                for (int c = 0; c < Cfg::kObj; ++c) {
-                    int cnt = 0;
-                    const bool on_leader = (d.plane_on_leader >> c) & 1;
-#pragma unroll
-                    for (int t = 0; t < W; ++t)
-                        cnt += __popc((on_leader ? oh[t] : x[t]) & comp(ov[c * W + t], i));
-                    obj += cnt * d.plane_value[c];
+                if (k < d.nentries) {
+                    const uint32_t e = comp(ov[k], i);
+                    const uint32_t slot = e & 0xFFu;
+                    const uint32_t xw = row_word<W>(x[i], (int)(slot >> 5));
+                    const bool bit = __funnelshift_r(xw, 0u, slot) & 1u;
+                    const uint32_t w = (slot == ld) ? (e >> 20) : ((e >> 8) & 0xFFFu);
+                    obj += bit ? (int)w : 0;
                 }
-            } else {
+            if (d.dense && (!kCheckValid || (r0 + i) < d.P)) {
+                const uint32_t *wrow = d.dense_w + (size_t)(r0 + i) * d.NS;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (k < d.nentries) {
-                        const uint32_t e = comp(ov[k], i);
-                        const uint32_t slot = e & 0xFFu;
-                        const uint32_t xw = row_word<W>(x, (int)(slot >> 5));
-                        const bool bit = __funnelshift_r(xw, 0u, slot) & 1u;
-                        const uint32_t w = (slot == ld) ? (e >> 20) : ((e >> 8) & 0xFFFu);
-                        obj += bit ? (int)w : 0;
-                    }
-                if (d.dense && (!kCheckValid || (r0 + i) < d.P)) {
-                    const uint32_t *wrow = d.dense_w + (size_t)(r0 + i) * d.NS;
-#pragma unroll
-                    for (int t = 0; t < W; ++t) {
-                        for (uint32_t m = x[t]; m; m &= m - 1) {
-                            const int s = t * 32 + __ffs(m) - 1;
-                            if (s < d.NS) {
-                                const uint32_t w = __ldg(wrow + s);
-                                obj += (s == (int)ld) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
-                            }
+                for (int t = 0; t < W; ++t) {
+                    for (uint32_t m = x[i][t]; m; m &= m - 1) {
+                        const int s = t * 32 + __ffs(m) - 1;
+                        if (s < d.NS) {
+                            const uint32_t w = __ldg(wrow + s);
+                            obj += (s == (int)ld) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
                         }
                     }
                 }
             }
-            if (half == 0) {
-                if (i == 0) { rc.template push<0>(x); lc.template push<0>(oh); }
-                if (i == 1) { rc.template push<1>(x); lc.template push<1>(oh); }
-                if (i == 2) { rc.template push<2>(x); lc.template push<2>(oh); }
-                if (i == 3) { rc.template push<3>(x); lc.template push<3>(oh); }
-            } else {
-                if (i == 0) { rc.template push<4>(x); lc.template push<4>(oh); }
-                if (i == 1) { rc.template push<5>(x); lc.template push<5>(oh); }
-                if (i == 2) { rc.template push<6>(x); lc.template push<6>(oh); }
-                if (i == 3) { rc.template push<7>(x); lc.template push<7>(oh); }
-            }
         }
     }
+    rc.push4(x[0], x[1], x[2], x[3]);
+    lc.push4(oh[0], oh[1], oh[2], oh[3]);
 }
 
 // Evaluates candidate = base + patches.  kShared: base/weights are in shared memory.
@@ -722,13 +698,14 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
     rc.clear();
     lc.clear();
     int viol = 0, obj = 0;
-    const int ntiles = d.Ppad / kTileRows;               // even: Ppad is a multiple of 256
-    const int nfull = (d.P / (2 * kTileRows)) * 2;        // tiles of blocks made of real rows only
-    int u0 = 0;
-    for (; u0 < nfull; u0 += 2)
-        eval_block<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u0, rc, lc, viol, obj);
-    for (; u0 < ntiles; u0 += 2)
-        eval_block<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u0, rc, lc, viol, obj);
+    const int ntiles = (d.P + kTileRows - 1) / kTileRows;
+    const int nfull = d.P / kTileRows;                   // tiles made of real rows only
+    int u = 0;
+#pragma unroll 1
+    for (; u < nfull; ++u)
+        eval_tile<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
+    if (u < ntiles)
+        eval_tile<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
 
     constexpr int NP0 = 3 + NPH;
     if constexpr (W <= 2) {
