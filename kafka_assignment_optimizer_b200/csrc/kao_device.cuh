@@ -9,6 +9,15 @@
 // Model: /root/reference/README.md:139-185; search/generator spec: docs/MODEL.md.
 #pragma once
 #include <cuda_runtime.h>
+#ifndef KAO_TWO_PASS
+#define KAO_TWO_PASS 0
+#endif
+#ifndef KAO_LOCKSTEP
+#define KAO_LOCKSTEP 1
+#endif
+#ifndef KAO_TILE_SYNC
+#define KAO_TILE_SYNC 0
+#endif
 #include <stdint.h>
 
 namespace kao {
@@ -589,21 +598,17 @@ template <int W_, int NPH_, bool kHi1_, int kObj_> struct EvalCfg {
     static constexpr bool kHi1 = kHi1_;
 };
 
-// one 128-row tile: 4 consecutive rows per lane (128-bit shared-memory loads, conflict-free)
-template <class Cfg, bool kShared, bool kCheckValid>
-__device__ __forceinline__ void eval_tile(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
-                                          const uint32_t *objT, const PatchSet &ps, const uint32_t *prow,
-                                          int lane, int u, ColCounter<Cfg::W, Cfg::NPH> &rc,
-                                          ColCounter<Cfg::W, Cfg::NPH> &lc, int &viol, int &obj)
+// Loads one 128-row tile of the candidate: 4 consecutive rows per lane (128-bit shared-memory
+// loads, conflict-free), with the candidate's row patches substituted (rare, warp-uniform test).
+template <int W, bool kShared>
+__device__ __forceinline__ void load_tile(const uint32_t *bitsT, const uint8_t *leader, int Ppad,
+                                          const PatchSet &ps, const uint32_t *prow, int lane, int u,
+                                          uint4 (&xv)[W], uint32_t &ld4)
 {
-    constexpr int W = Cfg::W;
-    const int Ppad = d.Ppad;
     const int r0 = u * kTileRows + lane * kRowsPerLane;
-    uint4 xv[W];
 #pragma unroll
     for (int t = 0; t < W; ++t) xv[t] = ld128<kShared>(bitsT + (size_t)t * Ppad + r0);
-    uint32_t ld4 = ld32<kShared>(leader + r0);
-    // rare (warp-uniform test): a patched row lives in this tile
+    ld4 = ld32<kShared>(leader + r0);
     if (((ps.p[0] >> 7) == u) | ((ps.p[1] >> 7) == u) | ((ps.p[2] >> 7) == u)) {
 #pragma unroll
         for (int i = 0; i < kMaxOps; ++i) {
@@ -620,18 +625,24 @@ __device__ __forceinline__ void eval_tile(const Params &d, const uint32_t *bitsT
             }
         }
     }
-    uint4 ov[Cfg::kObj > 0 ? Cfg::kObj * W : 4];
-    if constexpr (Cfg::kObj > 0) {
-#pragma unroll
-        for (int c = 0; c < Cfg::kObj; ++c) {
-#pragma unroll
-            for (int t = 0; t < W; ++t) ov[c * W + t] = ld128<kShared>(objT + (size_t)(c * W + t) * Ppad + r0);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (k < d.nentries) ov[k] = ld128<kShared>(objT + (size_t)k * Ppad + r0);
-    }
+}
+
+// The evaluation walks the candidate twice so that each loop body stays inside the instruction
+// cache (one fused body measured ~27 % "no instruction" stalls, profiles/):
+//   pass A  per row: C1 / C7 terms, leader validity (C2/C5), leader-bonus planes; per tile: the
+//           carry-save column counters of replicas (C3, C6) and leaders (C4)
+//   pass B  per row: the follower-weight part of the objective
+template <class Cfg, bool kShared, bool kCheckValid>
+__device__ __forceinline__ void tile_pass_a(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
+                                            const uint32_t *objT, const PatchSet &ps, const uint32_t *prow,
+                                            int lane, int u, ColCounter<Cfg::W, Cfg::NPH> &rc,
+                                            ColCounter<Cfg::W, Cfg::NPH> &lc, int &viol, int &obj)
+{
+    constexpr int W = Cfg::W;
+    const int r0 = u * kTileRows + lane * kRowsPerLane;
+    uint4 xv[W];
+    uint32_t ld4;
+    load_tile<W, kShared>(bitsT, leader, d.Ppad, ps, prow, lane, u, xv, ld4);
     uint32_t x[kRowsPerLane][W], oh[kRowsPerLane][W];
 #pragma unroll
     for (int i = 0; i < kRowsPerLane; ++i) {
@@ -646,23 +657,67 @@ __device__ __forceinline__ void eval_tile(const Params &d, const uint32_t *bitsT
         int rv = row_rack_terms<W, Cfg::kHi1>(x[i], d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF) + (any ? 0 : 1);
         if constexpr (kCheckValid) rv = ((r0 + i) < d.P) ? rv : 0;
         viol += rv;
-        if constexpr (Cfg::kObj > 0) {
+    }
+    if constexpr (Cfg::kObj > 0) {
 #pragma unroll
-            for (int c = 0; c < Cfg::kObj; ++c) {
+        for (int c = 0; c < Cfg::kObj; ++c) {
+            if ((d.plane_on_leader >> c) & 1) {
                 int cnt = 0;
-                const bool on_leader = (d.plane_on_leader >> c) & 1;
 #pragma unroll
-                for (int t = 0; t < W; ++t)
-                    cnt += __popc((on_leader ? oh[i][t] : x[i][t]) & comp(ov[c * W + t], i));
+                for (int t = 0; t < W; ++t) {
+                    const uint4 m = ld128<kShared>(objT + (size_t)(c * W + t) * d.Ppad + r0);
+#pragma unroll
+                    for (int i = 0; i < kRowsPerLane; ++i) cnt += __popc(oh[i][t] & comp(m, i));
+                }
                 obj += cnt * d.plane_value[c];
             }
-        } else {
+        }
+    }
+    rc.push4(x[0], x[1], x[2], x[3]);
+    lc.push4(oh[0], oh[1], oh[2], oh[3]);
+}
+
+template <class Cfg, bool kShared, bool kCheckValid>
+__device__ __forceinline__ void tile_pass_b(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
+                                            const uint32_t *objT, const PatchSet &ps, const uint32_t *prow,
+                                            int lane, int u, int &obj)
+{
+    constexpr int W = Cfg::W;
+    const int r0 = u * kTileRows + lane * kRowsPerLane;
+    uint4 xv[W];
+    uint32_t ld4;
+    load_tile<W, kShared>(bitsT, leader, d.Ppad, ps, prow, lane, u, xv, ld4);
+    if constexpr (Cfg::kObj > 0) {
+#pragma unroll
+        for (int c = 0; c < Cfg::kObj; ++c) {
+            if (!((d.plane_on_leader >> c) & 1)) {
+                int cnt = 0;
+#pragma unroll
+                for (int t = 0; t < W; ++t) {
+                    const uint4 m = ld128<kShared>(objT + (size_t)(c * W + t) * d.Ppad + r0);
+#pragma unroll
+                    for (int i = 0; i < kRowsPerLane; ++i) cnt += __popc(comp(xv[t], i) & comp(m, i));
+                }
+                obj += cnt * d.plane_value[c];
+            }
+        }
+    } else {
+        uint4 ov[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < d.nentries) ov[k] = ld128<kShared>(objT + (size_t)k * d.Ppad + r0);
+#pragma unroll
+        for (int i = 0; i < kRowsPerLane; ++i) {
+            uint32_t x[W];
+#pragma unroll
+            for (int t = 0; t < W; ++t) x[t] = comp(xv[t], i);
+            const uint32_t ld = (ld4 >> (8 * i)) & 0xFFu;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (k < d.nentries) {
                     const uint32_t e = comp(ov[k], i);
                     const uint32_t slot = e & 0xFFu;
-                    const uint32_t xw = row_word<W>(x[i], (int)(slot >> 5));
+                    const uint32_t xw = row_word<W>(x, (int)(slot >> 5));
                     const bool bit = __funnelshift_r(xw, 0u, slot) & 1u;
                     const uint32_t w = (slot == ld) ? (e >> 20) : ((e >> 8) & 0xFFFu);
                     obj += bit ? (int)w : 0;
@@ -671,7 +726,7 @@ __device__ __forceinline__ void eval_tile(const Params &d, const uint32_t *bitsT
                 const uint32_t *wrow = d.dense_w + (size_t)(r0 + i) * d.NS;
 #pragma unroll
                 for (int t = 0; t < W; ++t) {
-                    for (uint32_t m = x[i][t]; m; m &= m - 1) {
+                    for (uint32_t m = x[t]; m; m &= m - 1) {
                         const int s = t * 32 + __ffs(m) - 1;
                         if (s < d.NS) {
                             const uint32_t w = __ldg(wrow + s);
@@ -682,8 +737,6 @@ __device__ __forceinline__ void eval_tile(const Params &d, const uint32_t *bitsT
             }
         }
     }
-    rc.push4(x[0], x[1], x[2], x[3]);
-    lc.push4(oh[0], oh[1], oh[2], oh[3]);
 }
 
 // Evaluates candidate = base + patches.  kShared: base/weights are in shared memory.
@@ -694,18 +747,44 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
                                const uint32_t *prow, int lane, int &viol_out, int &obj_out)
 {
     constexpr int W = Cfg::W, NPH = Cfg::NPH;
-    ColCounter<W, NPH> rc, lc;
-    rc.clear();
-    lc.clear();
     int viol = 0, obj = 0;
     const int ntiles = (d.P + kTileRows - 1) / kTileRows;
     const int nfull = d.P / kTileRows;                   // tiles made of real rows only
-    int u = 0;
+    ColCounter<W, NPH> rc, lc;
+    rc.clear();
+    lc.clear();
+#if KAO_TWO_PASS
+    {
+        int u = 0;
 #pragma unroll 1
-    for (; u < nfull; ++u)
-        eval_tile<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
-    if (u < ntiles)
-        eval_tile<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
+        for (; u < nfull; ++u) tile_pass_b<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, obj);
+        if (u < ntiles) tile_pass_b<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, obj);
+    }
+    {
+        int u = 0;
+#pragma unroll 1
+        for (; u < nfull; ++u)
+            tile_pass_a<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
+        if (u < ntiles)
+            tile_pass_a<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
+    }
+#else
+    {
+        int u = 0;
+#pragma unroll 1
+        for (; u < nfull; ++u) {
+#if KAO_TILE_SYNC
+            if (kShared && (u % KAO_TILE_SYNC) == 0) __syncthreads();   // keep the block's warps on the same code
+#endif
+            tile_pass_a<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
+            tile_pass_b<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, obj);
+        }
+        if (u < ntiles) {
+            tile_pass_a<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
+            tile_pass_b<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, obj);
+        }
+    }
+#endif
 
     constexpr int NP0 = 3 + NPH;
     if constexpr (W <= 2) {

@@ -108,15 +108,30 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
 
     unsigned long long best = kKeyNone;
     const uint32_t stride = gridDim.x * kWarps;
-    for (uint32_t idx = idx_lo + blockIdx.x * kWarps + warp; idx < idx_hi; idx += stride) {
+    // every warp of the block runs the same number of iterations and meets at a barrier before each
+    // evaluation: the warps of a scheduler then walk the same code together (instruction cache)
+    const uint32_t first = idx_lo + blockIdx.x * kWarps;
+    const uint32_t iters = first < idx_hi ? (idx_hi - first + stride - 1) / stride : 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t idx = first + warp + it * stride;
+        const bool live = idx < idx_hi;
         PatchSet ps;
-        gen.run(seed, round, idx, round_size, ps);
+        ps.n = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
+        if (live) gen.run(seed, round, idx, round_size, ps);
+#if KAO_LOCKSTEP
+        __syncthreads();
+#else
         __syncwarp();
-        int viol, obj;
-        eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
-        const unsigned long long key = pack_key(viol, obj, idx);
-        if (all_keys && lane == 0) all_keys[idx - idx_lo] = key;
-        best = key < best ? key : best;
+#endif
+        if (live || KAO_TILE_SYNC) {                         // idle warps keep the barrier count when tiles sync
+            int viol, obj;
+            eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
+            const unsigned long long key = live ? pack_key(viol, obj, idx) : kKeyNone;
+            if (all_keys && lane == 0) all_keys[idx - idx_lo] = key;
+            best = key < best ? key : best;
+        }
         __syncwarp();
     }
     if (lane == 0) s_red[warp] = best;
@@ -258,7 +273,10 @@ struct kao_handle {
     uint64_t launches = 0;
 };
 
-template <int W> static constexpr int threads_for() { return W <= 2 ? 512 : 256; }
+#ifndef KAO_THREADS
+#define KAO_THREADS 768
+#endif
+template <int W> static constexpr int threads_for() { return W <= 2 ? KAO_THREADS : 256; }
 
 template <class Cfg>
 static cudaError_t launch_round_cfg(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
@@ -371,7 +389,7 @@ extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **ou
     h->sms = prop.multiProcessorCount;
     const HostModel &m = h->hm;
     const int W = m.W, Ppad = m.Ppad;
-    h->threads = W <= 2 ? 512 : 256;
+    h->threads = W <= 2 ? KAO_THREADS : 256;
     h->plan = make_plan(W, Ppad, h->threads / 32, m.nplanes > 0 ? m.nplanes * W : 4);
     if (h->plan.total > 227u * 1024u) {
         kao_destroy(h);

@@ -13,7 +13,7 @@ import numpy as np
 from .problem import (Problem, build_problem, parse_assignment_json, parse_broker_list, parse_rack_map,
                       reassignment_json)
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkao.so")
+_LIB_PATH = os.environ.get("KAO_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkao.so")
 KAO_OK, KAO_INFEASIBLE = 0, 1
 KEY_NONE = 0x7FFFFFFFFFFFFFFF
 
