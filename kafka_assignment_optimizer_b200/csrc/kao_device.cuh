@@ -9,15 +9,10 @@
 // Model: /root/reference/README.md:139-185; search/generator spec: docs/MODEL.md.
 #pragma once
 #include <cuda_runtime.h>
-#ifndef KAO_TWO_PASS
-#define KAO_TWO_PASS 0
-#endif
 #ifndef KAO_LOCKSTEP
 #define KAO_LOCKSTEP 1
 #endif
-#ifndef KAO_TILE_SYNC
-#define KAO_TILE_SYNC 0
-#endif
+
 #include <stdint.h>
 
 namespace kao {
@@ -627,22 +622,19 @@ __device__ __forceinline__ void load_tile(const uint32_t *bitsT, const uint8_t *
     }
 }
 
-// The evaluation walks the candidate twice so that each loop body stays inside the instruction
-// cache (one fused body measured ~27 % "no instruction" stalls, profiles/):
-//   pass A  per row: C1 / C7 terms, leader validity (C2/C5), leader-bonus planes; per tile: the
+// Per tile, two parts over the same loaded rows:
+//   part A  per row: C1 / C7 terms, leader validity (C2/C5), leader-bonus planes; per tile: the
 //           carry-save column counters of replicas (C3, C6) and leaders (C4)
-//   pass B  per row: the follower-weight part of the objective
+//   part B  per row: the follower-weight part of the objective
 template <class Cfg, bool kShared, bool kCheckValid>
 __device__ __forceinline__ void tile_pass_a(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
                                             const uint32_t *objT, const PatchSet &ps, const uint32_t *prow,
                                             int lane, int u, ColCounter<Cfg::W, Cfg::NPH> &rc,
-                                            ColCounter<Cfg::W, Cfg::NPH> &lc, int &viol, int &obj)
+                                            ColCounter<Cfg::W, Cfg::NPH> &lc, int &viol, int &obj,
+                                            const uint4 (&xv)[Cfg::W], uint32_t ld4)
 {
     constexpr int W = Cfg::W;
     const int r0 = u * kTileRows + lane * kRowsPerLane;
-    uint4 xv[W];
-    uint32_t ld4;
-    load_tile<W, kShared>(bitsT, leader, d.Ppad, ps, prow, lane, u, xv, ld4);
     uint32_t x[kRowsPerLane][W], oh[kRowsPerLane][W];
 #pragma unroll
     for (int i = 0; i < kRowsPerLane; ++i) {
@@ -680,13 +672,11 @@ __device__ __forceinline__ void tile_pass_a(const Params &d, const uint32_t *bit
 template <class Cfg, bool kShared, bool kCheckValid>
 __device__ __forceinline__ void tile_pass_b(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
                                             const uint32_t *objT, const PatchSet &ps, const uint32_t *prow,
-                                            int lane, int u, int &obj)
+                                            int lane, int u, int &obj,
+                                            const uint4 (&xv)[Cfg::W], uint32_t ld4)
 {
     constexpr int W = Cfg::W;
     const int r0 = u * kTileRows + lane * kRowsPerLane;
-    uint4 xv[W];
-    uint32_t ld4;
-    load_tile<W, kShared>(bitsT, leader, d.Ppad, ps, prow, lane, u, xv, ld4);
     if constexpr (Cfg::kObj > 0) {
 #pragma unroll
         for (int c = 0; c < Cfg::kObj; ++c) {
@@ -753,38 +743,24 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
     ColCounter<W, NPH> rc, lc;
     rc.clear();
     lc.clear();
-#if KAO_TWO_PASS
-    {
-        int u = 0;
-#pragma unroll 1
-        for (; u < nfull; ++u) tile_pass_b<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, obj);
-        if (u < ntiles) tile_pass_b<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, obj);
-    }
-    {
-        int u = 0;
-#pragma unroll 1
-        for (; u < nfull; ++u)
-            tile_pass_a<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
-        if (u < ntiles)
-            tile_pass_a<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
-    }
-#else
     {
         int u = 0;
 #pragma unroll 1
         for (; u < nfull; ++u) {
-#if KAO_TILE_SYNC
-            if (kShared && (u % KAO_TILE_SYNC) == 0) __syncthreads();   // keep the block's warps on the same code
-#endif
-            tile_pass_a<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
-            tile_pass_b<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, obj);
+            uint4 xv[W];
+            uint32_t ld4;
+            load_tile<W, kShared>(bitsT, leader, d.Ppad, ps, prow, lane, u, xv, ld4);
+            tile_pass_a<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj, xv, ld4);
+            tile_pass_b<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, obj, xv, ld4);
         }
         if (u < ntiles) {
-            tile_pass_a<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj);
-            tile_pass_b<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, obj);
+            uint4 xv[W];
+            uint32_t ld4;
+            load_tile<W, kShared>(bitsT, leader, d.Ppad, ps, prow, lane, u, xv, ld4);
+            tile_pass_a<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj, xv, ld4);
+            tile_pass_b<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, obj, xv, ld4);
         }
     }
-#endif
 
     constexpr int NP0 = 3 + NPH;
     if constexpr (W <= 2) {

@@ -125,7 +125,7 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
 #else
         __syncwarp();
 #endif
-        if (live || KAO_TILE_SYNC) {                         // idle warps keep the barrier count when tiles sync
+        if (live) {
             int viol, obj;
             eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
             const unsigned long long key = live ? pack_key(viol, obj, idx) : kKeyNone;
