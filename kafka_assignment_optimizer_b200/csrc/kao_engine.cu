@@ -8,6 +8,8 @@
 #include "../../include/kao.h"
 
 #include <chrono>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -257,7 +259,37 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
             return fail(KAO_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
     } while (0)
 
+// Device buffers are recycled across handles: kao_solve creates and destroys a session per call,
+// and cudaMalloc / cudaFree (which synchronises the device) would dominate short solves.
+namespace {
+struct DevPool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> free_;
+    size_t held = 0;
+    cudaError_t get(int dev, void **p, size_t n)
+    {
+        n = (n + 255) & ~size_t(255);
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = free_.find({dev, n});
+            if (it != free_.end()) { *p = it->second; free_.erase(it); held -= n; return cudaSuccess; }
+        }
+        return cudaMalloc(p, n);
+    }
+    void put(int dev, void *p, size_t n)
+    {
+        n = (n + 255) & ~size_t(255);
+        std::lock_guard<std::mutex> g(mu);
+        if (held + n > (size_t(1) << 30)) { cudaFree(p); return; }
+        free_.insert({{dev, n}, p});
+        held += n;
+    }
+};
+DevPool g_pool;
+}  // namespace
+
 struct kao_handle {
+    std::vector<std::pair<void *, size_t>> owned;   // device buffers to hand back to the pool
     HostModel hm;               // layout, tables, host copy of problem data
     int device = 0;
     int sms = 0;
@@ -269,6 +301,7 @@ struct kao_handle {
     uint32_t *d_dense = nullptr; uint32_t *d_planes = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
     Consts *d_consts = nullptr; unsigned long long *d_key = nullptr; unsigned long long *d_keys = nullptr;
     size_t keys_cap = 0;
+    long long *d_vo = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
 };
@@ -277,6 +310,14 @@ struct kao_handle {
 #define KAO_THREADS 768
 #endif
 template <int W> static constexpr int threads_for() { return W <= 2 ? KAO_THREADS : 256; }
+
+template <class T> static cudaError_t dalloc(kao_handle *h, T **p, size_t bytes)
+{
+    void *v = nullptr;
+    cudaError_t e = g_pool.get(h->device, &v, bytes);
+    if (e == cudaSuccess) { *p = static_cast<T *>(v); h->owned.emplace_back(v, bytes); }
+    return e;
+}
 
 template <class Cfg>
 static cudaError_t launch_round_cfg(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
@@ -360,28 +401,23 @@ extern "C" int kao_destroy(kao_handle *h)
 {
     if (!h) return KAO_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->d_bits); cudaFree(h->d_leader); cudaFree(h->d_sw); cudaFree(h->d_dense); cudaFree(h->d_planes);
-    cudaFree(h->d_home); cudaFree(h->d_D); cudaFree(h->d_DL); cudaFree(h->d_nD); cudaFree(h->d_consts);
-    cudaFree(h->d_key); cudaFree(h->d_keys);
+    cudaDeviceSynchronize();                   // nothing of this session may still be running on a recycled buffer
+    for (auto &b : h->owned) g_pool.put(h->device, b.first, b.second);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
     return KAO_OK;
 }
 
-extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **out)
+extern "C" int kao_reset(kao_handle *h);
+static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
 {
-    if (!pb || !out) return fail(KAO_E_ARG, "null argument");
-    *out = nullptr;
-    kao_handle *h = new kao_handle();
     std::string why;
-    if (!build_host_model(*pb, h->hm, why)) { delete h; return fail(KAO_E_ARG, why); }
+    if (!build_host_model(*pb, h->hm, why)) return fail(KAO_E_ARG, why);
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
-        delete h;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return fail(KAO_E_CUDA, "no CUDA device: libkao has no CPU path");
-    }
-    if (device < 0 || device >= ndev) { delete h; return fail(KAO_E_ARG, "bad device ordinal"); }
+    if (device < 0 || device >= ndev) return fail(KAO_E_ARG, "bad device ordinal");
     h->device = device;
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -391,29 +427,27 @@ extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **ou
     const int W = m.W, Ppad = m.Ppad;
     h->threads = W <= 2 ? KAO_THREADS : 256;
     h->plan = make_plan(W, Ppad, h->threads / 32, m.nplanes > 0 ? m.nplanes * W : 4);
-    if (h->plan.total > 227u * 1024u) {
-        kao_destroy(h);
+    if (h->plan.total > 227u * 1024u)
         return fail(KAO_E_ARG, "problem too large for the shared-memory resident search kernel");
-    }
     h->grid = h->sms;
-    CUDA_TRY(cudaMalloc(&h->d_bits, (size_t)W * Ppad * 4));
-    CUDA_TRY(cudaMalloc(&h->d_leader, (size_t)Ppad));
-    CUDA_TRY(cudaMalloc(&h->d_sw, (size_t)4 * Ppad * 4));
-    CUDA_TRY(cudaMalloc(&h->d_home, (size_t)Ppad * 4));
-    CUDA_TRY(cudaMalloc(&h->d_D, (size_t)Ppad * 2));
-    CUDA_TRY(cudaMalloc(&h->d_DL, (size_t)Ppad * 2));
-    CUDA_TRY(cudaMalloc(&h->d_nD, 16));
-    CUDA_TRY(cudaMalloc(&h->d_consts, sizeof(Consts)));
-    CUDA_TRY(cudaMalloc(&h->d_key, 16));
+    CUDA_TRY(dalloc(h, &h->d_bits, (size_t)W * Ppad * 4));
+    CUDA_TRY(dalloc(h, &h->d_leader, (size_t)Ppad));
+    CUDA_TRY(dalloc(h, &h->d_sw, (size_t)4 * Ppad * 4));
+    CUDA_TRY(dalloc(h, &h->d_home, (size_t)Ppad * 4));
+    CUDA_TRY(dalloc(h, &h->d_D, (size_t)Ppad * 2));
+    CUDA_TRY(dalloc(h, &h->d_DL, (size_t)Ppad * 2));
+    CUDA_TRY(dalloc(h, &h->d_nD, 16));
+    CUDA_TRY(dalloc(h, &h->d_consts, sizeof(Consts)));
+    CUDA_TRY(dalloc(h, &h->d_key, 16));
     CUDA_TRY(cudaMemset(h->d_nD, 0, 16));
     { const unsigned long long none[2] = {kKeyNone, kKeyNone}; CUDA_TRY(cudaMemcpy(h->d_key, none, 16, cudaMemcpyHostToDevice)); }
     if (m.dense) {
-        CUDA_TRY(cudaMalloc(&h->d_dense, m.dense_w.size() * 4));
+        CUDA_TRY(dalloc(h, &h->d_dense, m.dense_w.size() * 4));
         CUDA_TRY(cudaMemcpy(h->d_dense, m.dense_w.data(), m.dense_w.size() * 4, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemcpy(h->d_sw, m.swT.data(), m.swT.size() * 4, cudaMemcpyHostToDevice));
     if (m.nplanes > 0) {
-        CUDA_TRY(cudaMalloc(&h->d_planes, m.planesT.size() * 4));
+        CUDA_TRY(dalloc(h, &h->d_planes, m.planesT.size() * 4));
         CUDA_TRY(cudaMemcpy(h->d_planes, m.planesT.data(), m.planesT.size() * 4, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemcpy(h->d_home, m.homeT.data(), m.homeT.size() * 4, cudaMemcpyHostToDevice));
@@ -430,8 +464,21 @@ extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **ou
     p.planesT = h->d_planes;
     p.bitsT = h->d_bits; p.leader = h->d_leader; p.swT = h->d_sw; p.dense_w = h->d_dense;
     p.homeT = h->d_home; p.D = h->d_D; p.DL = h->d_DL; p.nD = h->d_nD; p.consts = h->d_consts;
-    int rc = kao_reset(h);
-    if (rc != KAO_OK) { kao_destroy(h); return rc; }
+    return kao_reset(h);
+}
+
+extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **out)
+{
+    if (!pb || !out) return fail(KAO_E_ARG, "null argument");
+    *out = nullptr;
+    kao_handle *h = new kao_handle();
+    const int rc = create_impl(pb, device, h);
+    if (rc != KAO_OK) {
+        const std::string keep = g_err;
+        kao_destroy(h);
+        g_err = keep;
+        return rc;
+    }
     *out = h;
     return KAO_OK;
 }
@@ -484,12 +531,10 @@ extern "C" int kao_get_base(kao_handle *h, int32_t *replicas, int64_t *violation
     if (replicas) std::memcpy(replicas, reps.data(), reps.size() * 4);
     if (moves) *moves = count_moves(m, reps.data());
     if (violation || objective) {
-        long long *d_vo = nullptr;
-        CUDA_TRY(cudaMalloc(&d_vo, 16));
-        int rc = eval_on_device(h, h->d_bits, h->d_leader, 1, d_vo, d_vo + 1);
+        if (!h->d_vo) CUDA_TRY(dalloc(h, &h->d_vo, 16));
+        int rc = eval_on_device(h, h->d_bits, h->d_leader, 1, h->d_vo, h->d_vo + 1);
         long long vo[2] = {0, 0};
-        if (rc == KAO_OK && cudaMemcpy(vo, d_vo, 16, cudaMemcpyDeviceToHost) != cudaSuccess) rc = KAO_E_CUDA;
-        cudaFree(d_vo);
+        if (rc == KAO_OK && cudaMemcpy(vo, h->d_vo, 16, cudaMemcpyDeviceToHost) != cudaSuccess) rc = KAO_E_CUDA;
         if (rc != KAO_OK) return rc;
         if (violation) *violation = vo[0];
         if (objective) *objective = vo[1];
@@ -532,9 +577,8 @@ extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, ui
     if (!check_round_args(round_size)) return fail(KAO_E_ARG, "round_size must be 2..2^24");
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->keys_cap < rounds) {
-        cudaFree(h->d_keys);
-        h->d_keys = nullptr;
-        CUDA_TRY(cudaMalloc(&h->d_keys, (size_t)(rounds > 0 ? rounds : 1) * 8));
+        h->d_keys = nullptr;                   // the old buffer stays owned by the handle until destroy
+        CUDA_TRY(dalloc(h, &h->d_keys, (size_t)(rounds > 0 ? rounds : 1) * 8));
         h->keys_cap = rounds;
     }
     if (rounds) {
