@@ -420,9 +420,12 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     if (device < 0 || device >= ndev) return fail(KAO_E_ARG, "bad device ordinal");
     h->device = device;
     CUDA_TRY(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    h->sms = prop.multiProcessorCount;
+    {   // cudaGetDeviceProperties costs tens of milliseconds per call; one attribute, cached per device
+        static int sm_count[64] = {};
+        if (!sm_count[device & 63])
+            CUDA_TRY(cudaDeviceGetAttribute(&sm_count[device & 63], cudaDevAttrMultiProcessorCount, device));
+        h->sms = sm_count[device & 63];
+    }
     const HostModel &m = h->hm;
     const int W = m.W, Ppad = m.Ppad;
     h->threads = W <= 2 ? KAO_THREADS : 256;
