@@ -231,7 +231,7 @@ def main():
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "search_round_kernel<2,5,512>",
+                    "traffic": traffic, "kernel": "search_round_kernel<EvalCfg<W=2,NPH=3,hi1,planes=3>,768>",
                     "algorithmic_bytes_per_candidate": ALGO_BYTES, "candidates_per_launch": ROUND_SIZE,
                     "kernel_ms_per_launch": s_ms / prof_rounds, "apply_kernel_ms_per_launch": a_ms / prof_rounds,
                     "peak_source": peak_src,

@@ -385,28 +385,37 @@ __device__ __forceinline__ uint32_t bytecounts(uint32_t x)
     return (c + (c >> 4)) & 0x0F0F0F0Fu;
 }
 
-template <bool kShared> __device__ __forceinline__ uint4 ld128(const void *p)
-{
-    if constexpr (kShared) {
-        uint4 v;
-        const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-        return v;
-    } else {
-        return __ldg(reinterpret_cast<const uint4 *>(p));
+// Base address of a table, resolved once per candidate: a 32-bit shared-memory address for the
+// search kernel (no generic->shared conversion per load), a global pointer for explicit populations.
+template <bool kShared> struct MemRef {
+    uint32_t sa;
+    const char *ga;
+    __device__ __forceinline__ explicit MemRef(const void *p)
+    {
+        if constexpr (kShared) { sa = (uint32_t)__cvta_generic_to_shared(p); ga = nullptr; }
+        else { sa = 0; ga = static_cast<const char *>(p); }
     }
-}
-template <bool kShared> __device__ __forceinline__ uint32_t ld32(const void *p)
-{
-    if constexpr (kShared) {
-        uint32_t v;
-        const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-        return v;
-    } else {
-        return __ldg(reinterpret_cast<const uint32_t *>(p));
+    __device__ __forceinline__ uint4 ld128(uint32_t byte_off) const
+    {
+        if constexpr (kShared) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa + byte_off));
+            return v;
+        } else {
+            return __ldg(reinterpret_cast<const uint4 *>(ga + byte_off));
+        }
     }
-}
+    __device__ __forceinline__ uint32_t ld32(uint32_t byte_off) const
+    {
+        if constexpr (kShared) {
+            uint32_t v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa + byte_off));
+            return v;
+        } else {
+            return __ldg(reinterpret_cast<const uint32_t *>(ga + byte_off));
+        }
+    }
+};
 
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int i)
 {
@@ -596,14 +605,14 @@ template <int W_, int NPH_, bool kHi1_, int kObj_> struct EvalCfg {
 // Loads one 128-row tile of the candidate: 4 consecutive rows per lane (128-bit shared-memory
 // loads, conflict-free), with the candidate's row patches substituted (rare, warp-uniform test).
 template <int W, bool kShared>
-__device__ __forceinline__ void load_tile(const uint32_t *bitsT, const uint8_t *leader, int Ppad,
+__device__ __forceinline__ void load_tile(const MemRef<kShared> &bitsT, const MemRef<kShared> &leader, int Ppad,
                                           const PatchSet &ps, const uint32_t *prow, int lane, int u,
                                           uint4 (&xv)[W], uint32_t &ld4)
 {
     const int r0 = u * kTileRows + lane * kRowsPerLane;
 #pragma unroll
-    for (int t = 0; t < W; ++t) xv[t] = ld128<kShared>(bitsT + (size_t)t * Ppad + r0);
-    ld4 = ld32<kShared>(leader + r0);
+    for (int t = 0; t < W; ++t) xv[t] = bitsT.ld128((uint32_t)(t * Ppad + r0) * 4u);
+    ld4 = leader.ld32((uint32_t)r0);
     if (((ps.p[0] >> 7) == u) | ((ps.p[1] >> 7) == u) | ((ps.p[2] >> 7) == u)) {
 #pragma unroll
         for (int i = 0; i < kMaxOps; ++i) {
@@ -627,8 +636,7 @@ __device__ __forceinline__ void load_tile(const uint32_t *bitsT, const uint8_t *
 //           carry-save column counters of replicas (C3, C6) and leaders (C4)
 //   part B  per row: the follower-weight part of the objective
 template <class Cfg, bool kShared, bool kCheckValid>
-__device__ __forceinline__ void tile_pass_a(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
-                                            const uint32_t *objT, const PatchSet &ps, const uint32_t *prow,
+__device__ __forceinline__ void tile_pass_a(const Params &d, const MemRef<kShared> &objT,
                                             int lane, int u, ColCounter<Cfg::W, Cfg::NPH> &rc,
                                             ColCounter<Cfg::W, Cfg::NPH> &lc, int &viol, int &obj,
                                             const uint4 (&xv)[Cfg::W], uint32_t ld4)
@@ -645,7 +653,11 @@ __device__ __forceinline__ void tile_pass_a(const Params &d, const uint32_t *bit
         const uint32_t ldbit = __funnelshift_l(0u, 1u, ld);      // 1 << (ld & 31)
         uint32_t any = 0;
 #pragma unroll
-        for (int t = 0; t < W; ++t) { oh[i][t] = ((int)(ld >> 5) == t) ? (x[i][t] & ldbit) : 0u; any |= oh[i][t]; }
+        for (int t = 0; t < W; ++t) {
+            const uint32_t lm = ((int)(ld >> 5) == t) ? ldbit : 0u;      // mask first: no indexed row access
+            oh[i][t] = x[i][t] & lm;
+            any |= oh[i][t];
+        }
         int rv = row_rack_terms<W, Cfg::kHi1>(x[i], d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF) + (any ? 0 : 1);
         if constexpr (kCheckValid) rv = ((r0 + i) < d.P) ? rv : 0;
         viol += rv;
@@ -657,7 +669,7 @@ __device__ __forceinline__ void tile_pass_a(const Params &d, const uint32_t *bit
                 int cnt = 0;
 #pragma unroll
                 for (int t = 0; t < W; ++t) {
-                    const uint4 m = ld128<kShared>(objT + (size_t)(c * W + t) * d.Ppad + r0);
+                    const uint4 m = objT.ld128((uint32_t)((c * W + t) * d.Ppad + r0) * 4u);
 #pragma unroll
                     for (int i = 0; i < kRowsPerLane; ++i) cnt += __popc(oh[i][t] & comp(m, i));
                 }
@@ -670,8 +682,7 @@ __device__ __forceinline__ void tile_pass_a(const Params &d, const uint32_t *bit
 }
 
 template <class Cfg, bool kShared, bool kCheckValid>
-__device__ __forceinline__ void tile_pass_b(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
-                                            const uint32_t *objT, const PatchSet &ps, const uint32_t *prow,
+__device__ __forceinline__ void tile_pass_b(const Params &d, const MemRef<kShared> &objT,
                                             int lane, int u, int &obj,
                                             const uint4 (&xv)[Cfg::W], uint32_t ld4)
 {
@@ -684,7 +695,7 @@ __device__ __forceinline__ void tile_pass_b(const Params &d, const uint32_t *bit
                 int cnt = 0;
 #pragma unroll
                 for (int t = 0; t < W; ++t) {
-                    const uint4 m = ld128<kShared>(objT + (size_t)(c * W + t) * d.Ppad + r0);
+                    const uint4 m = objT.ld128((uint32_t)((c * W + t) * d.Ppad + r0) * 4u);
 #pragma unroll
                     for (int i = 0; i < kRowsPerLane; ++i) cnt += __popc(comp(xv[t], i) & comp(m, i));
                 }
@@ -695,7 +706,7 @@ __device__ __forceinline__ void tile_pass_b(const Params &d, const uint32_t *bit
         uint4 ov[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (k < d.nentries) ov[k] = ld128<kShared>(objT + (size_t)k * d.Ppad + r0);
+            if (k < d.nentries) ov[k] = objT.ld128((uint32_t)(k * d.Ppad + r0) * 4u);
 #pragma unroll
         for (int i = 0; i < kRowsPerLane; ++i) {
             uint32_t x[W];
@@ -737,6 +748,7 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
                                const uint32_t *prow, int lane, int &viol_out, int &obj_out)
 {
     constexpr int W = Cfg::W, NPH = Cfg::NPH;
+    const MemRef<kShared> m_bits(bitsT), m_leader(leader), m_obj(objT);
     int viol = 0, obj = 0;
     const int ntiles = (d.P + kTileRows - 1) / kTileRows;
     const int nfull = d.P / kTileRows;                   // tiles made of real rows only
@@ -749,16 +761,16 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
         for (; u < nfull; ++u) {
             uint4 xv[W];
             uint32_t ld4;
-            load_tile<W, kShared>(bitsT, leader, d.Ppad, ps, prow, lane, u, xv, ld4);
-            tile_pass_a<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj, xv, ld4);
-            tile_pass_b<Cfg, kShared, false>(d, bitsT, leader, objT, ps, prow, lane, u, obj, xv, ld4);
+            load_tile<W, kShared>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ld4);
+            tile_pass_a<Cfg, kShared, false>(d, m_obj, lane, u, rc, lc, viol, obj, xv, ld4);
+            tile_pass_b<Cfg, kShared, false>(d, m_obj, lane, u, obj, xv, ld4);
         }
         if (u < ntiles) {
             uint4 xv[W];
             uint32_t ld4;
-            load_tile<W, kShared>(bitsT, leader, d.Ppad, ps, prow, lane, u, xv, ld4);
-            tile_pass_a<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, rc, lc, viol, obj, xv, ld4);
-            tile_pass_b<Cfg, kShared, true>(d, bitsT, leader, objT, ps, prow, lane, u, obj, xv, ld4);
+            load_tile<W, kShared>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ld4);
+            tile_pass_a<Cfg, kShared, true>(d, m_obj, lane, u, rc, lc, viol, obj, xv, ld4);
+            tile_pass_b<Cfg, kShared, true>(d, m_obj, lane, u, obj, xv, ld4);
         }
     }
 
