@@ -139,6 +139,8 @@ template <int W> struct Gen {
     const Params *d;
     uint32_t *prow;          // [kMaxOps * W] warp scratch for patched rows
     int lane;
+    const uint16_t *D, *DL;  // displaced / leader-displaced partitions of the base (global or shared)
+    int nD, nL;
 
     __device__ __forceinline__ void read_row(int p, uint32_t (&row)[W], uint32_t &ld) const
     {
@@ -238,9 +240,8 @@ template <int W> struct Gen {
         uint32_t row[W], ld;
         int lo, hi;
         if (first_leader) {
-            const int nL = d->nD[1];
             const bool guided = gbit && nL > 0;
-            const int p = guided ? (int)d->DL[mulhi32(r[1], (uint32_t)nL)] : (int)mulhi32(r[1], (uint32_t)P);
+            const int p = guided ? (int)DL[mulhi32(r[1], (uint32_t)nL)] : (int)mulhi32(r[1], (uint32_t)P);
             read_row(p, row, ld);
             lo = (int)ld;
             int want = -1;
@@ -249,9 +250,8 @@ template <int W> struct Gen {
             if (hi < 0) return;
             push(ps, p, row, ld);
         } else {
-            const int nD = d->nD[0];
             const bool guided = gbit && nD > 0;
-            const int p = guided ? (int)d->D[mulhi32(r[1], (uint32_t)nD)] : (int)mulhi32(r[1], (uint32_t)P);
+            const int p = guided ? (int)D[mulhi32(r[1], (uint32_t)nD)] : (int)mulhi32(r[1], (uint32_t)P);
             read_row(p, row, ld);
             const int n = row_count<W>(row);
             if (n == 0) return;

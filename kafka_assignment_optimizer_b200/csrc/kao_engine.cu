@@ -48,7 +48,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // shared-memory plan of the search kernel
 // ------------------------------------------------------------------------------------------
 struct SmemPlan {
-    uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, total;
+    uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, off_lists, total;
 };
 static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row)
 {
@@ -62,6 +62,7 @@ static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row)
     o = (o + 15u) & ~15u;
     s.off_red = o;    o += (uint32_t)warps * 8;
     s.off_bar = o;    o += 16;
+    s.off_lists = o;  o += (uint32_t)Ppad * 4 + 16 + 2 * 36 * 4;   // D, DL (u16 each), counts, scan scratch
     s.total = o;
     return s;
 }
@@ -107,6 +108,7 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
     Gen<W> gen;
     gen.bitsT = s_bits; gen.leader = s_leader; gen.cs = s_cs; gen.d = &d;
     gen.prow = s_prow + warp * kMaxOps * W; gen.lane = lane;
+    gen.D = d.D; gen.DL = d.DL; gen.nD = d.nD[0]; gen.nL = d.nD[1];
 
     unsigned long long best = kKeyNone;
     const uint32_t stride = gridDim.x * kWarps;
@@ -149,6 +151,59 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
     }
 }
 
+// Rebuilds the displaced lists of a base with the whole block (ballot compaction, ascending
+// order).  cnt: 2 x 36 ints of shared scratch.  counts[0] = |D|, counts[1] = |DL|.
+template <int THREADS>
+__device__ __forceinline__ void rebuild_lists(const uint32_t *bitsT, const uint8_t *leader, const uint32_t *homeT,
+                                              int P, int Ppad, uint16_t *D, uint16_t *DL, int *counts, int *cnt)
+{
+    constexpr int kWarps = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *cD = cnt, *cL = cnt + 36;
+    int baseD = 0, baseL = 0;
+    for (int p0 = 0; p0 < P; p0 += THREADS) {
+        const int p = p0 + tid;
+        bool miss = false, ldis = false;
+        if (p < P) {
+            const uint32_t h4 = homeT[p];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int hs = (h4 >> (8 * i)) & 0xFF;
+                if (hs != 0xFF) {
+                    const bool has = (bitsT[(size_t)(hs >> 5) * Ppad + p] >> (hs & 31)) & 1u;
+                    miss |= !has;
+                    if (i == 0) ldis = has && ((int)leader[p] != hs);
+                }
+            }
+        }
+        const uint32_t mD = __ballot_sync(0xFFFFFFFFu, miss);
+        const uint32_t mL = __ballot_sync(0xFFFFFFFFu, ldis);
+        if (lane == 0) { cD[warp] = __popc(mD); cL[warp] = __popc(mL); }
+        __syncthreads();
+        if (warp == 0) {
+            int c = lane < kWarps ? cD[lane] : 0, incl = c, cl = lane < kWarps ? cL[lane] : 0, incl2 = cl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                const int v2 = __shfl_up_sync(0xFFFFFFFFu, incl2, o);
+                if (lane >= o) { incl += v; incl2 += v2; }
+            }
+            cD[lane] = incl - c;
+            cL[lane] = incl2 - cl;
+            if (lane == 31) { cD[32] = incl; cL[32] = incl2; }
+        }
+        __syncthreads();
+        const uint32_t below = (1u << lane) - 1u;
+        if (miss) D[baseD + cD[warp] + __popc(mD & below)] = (uint16_t)p;
+        if (ldis) DL[baseL + cL[warp] + __popc(mL & below)] = (uint16_t)p;
+        baseD += cD[32];
+        baseL += cL[32];
+        __syncthreads();
+    }
+    if (tid == 0) { counts[0] = baseD; counts[1] = baseL; }
+    __syncthreads();
+}
+
 // Winner of a round becomes the base: re-materialise its patches from (seed, round, index), write
 // the patched rows to the base in HBM, then rebuild the displaced list D.  One block.
 template <int W>
@@ -157,7 +212,7 @@ apply_winner_kernel(Params d, uint64_t seed, uint32_t round, uint32_t round_size
                     const unsigned long long *key, int regen_only)
 {
     __shared__ uint32_t s_prow[kMaxOps * W];
-    __shared__ int s_cnt[33], s_cntL[33];
+    __shared__ int s_scan[72];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp == 0 && !regen_only) {
         const unsigned long long k = *key;
@@ -165,6 +220,7 @@ apply_winner_kernel(Params d, uint64_t seed, uint32_t round, uint32_t round_size
             Gen<W> gen;
             gen.bitsT = d.bitsT; gen.leader = d.leader; gen.cs = d.consts; gen.d = &d;
             gen.prow = s_prow; gen.lane = lane;
+            gen.D = d.D; gen.DL = d.DL; gen.nD = d.nD[0]; gen.nL = d.nD[1];
             PatchSet ps;
             gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps);
             __syncwarp();
@@ -181,49 +237,127 @@ apply_winner_kernel(Params d, uint64_t seed, uint32_t round, uint32_t round_size
     }
     __threadfence_block();
     __syncthreads();
-    // D  = ascending list of partitions whose row lacks one of its home slots
-    // DL = ascending list of partitions that hold their first home broker but are led from elsewhere
-    int baseD = 0, baseL = 0;
-    for (int p0 = 0; p0 < d.P; p0 += 1024) {
-        const int p = p0 + tid;
-        bool miss = false, ldis = false;
-        if (p < d.P) {
-            const uint32_t h4 = d.homeT[p];
+    rebuild_lists<1024>(d.bitsT, d.leader, d.homeT, d.P, d.Ppad, d.D, d.DL, d.nD, s_scan);
+}
+
+// All rounds of a search in ONE launch (cooperative: one CTA per SM, all co-resident).  The base
+// and the tables stay in shared memory for the whole search; per round every CTA evaluates its
+// share of the candidates, min-reduces into keys[t], meets the other CTAs at a grid barrier, then
+// re-materialises the winner itself and patches its own shared-memory copy of the base (<= 3
+// rows) — nothing but one 8-byte key crosses the chip per round.  CTA 0 mirrors the patches into
+// the HBM base.
+template <class Cfg, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                         uint32_t round_size, unsigned long long *keys, unsigned int *grid_bar)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(smem + plan.off_bits);
+    uint32_t *s_sw = reinterpret_cast<uint32_t *>(smem + plan.off_sw);
+    uint8_t *s_leader = smem + plan.off_leader;
+    Consts *s_cs = reinterpret_cast<Consts *>(smem + plan.off_consts);
+    uint32_t *s_prow = reinterpret_cast<uint32_t *>(smem + plan.off_prow);
+    unsigned long long *s_red = reinterpret_cast<unsigned long long *>(smem + plan.off_red);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + plan.off_bar);
+    uint16_t *s_D = reinterpret_cast<uint16_t *>(smem + plan.off_lists);
+    uint16_t *s_DL = s_D + d.Ppad;
+    int *s_counts = reinterpret_cast<int *>(smem + plan.off_lists + (size_t)d.Ppad * 4);
+    int *s_scan = s_counts + 4;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = THREADS / 32;
+    constexpr int W = Cfg::W;
+    const uint32_t *g_obj = Cfg::kObj > 0 ? d.planesT : d.swT;
+    const uint32_t obj_words = Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries;
+
+    if (tid == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t nb = (uint32_t)W * d.Ppad * 4, ns = obj_words * d.Ppad * 4, nl = (uint32_t)d.Ppad;
+        mbar_expect_tx(s_bar, nb + ns + nl + (uint32_t)sizeof(Consts));
+        bulk_g2s(s_bits, d.bitsT, nb, s_bar);
+        if (ns) bulk_g2s(s_sw, g_obj, ns, s_bar);
+        bulk_g2s(s_leader, d.leader, nl, s_bar);
+        bulk_g2s(s_cs, d.consts, (uint32_t)sizeof(Consts), s_bar);
+    }
+    mbar_wait(s_bar, 0);
+    rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
+
+    Gen<W> gen;
+    gen.bitsT = s_bits; gen.leader = s_leader; gen.cs = s_cs; gen.d = &d;
+    gen.prow = s_prow + warp * kMaxOps * W; gen.lane = lane;
+    gen.D = s_D; gen.DL = s_DL;
+
+    const uint32_t stride = gridDim.x * kWarps;
+    const uint32_t first = blockIdx.x * kWarps;
+    const uint32_t iters = first < round_size ? (round_size - first + stride - 1) / stride : 0;
+    for (uint32_t t = 0; t < rounds; ++t) {
+        const uint32_t round = first_round + t;
+        gen.nD = s_counts[0]; gen.nL = s_counts[1];
+        unsigned long long best = kKeyNone;
+        for (uint32_t it = 0; it < iters; ++it) {
+            const uint32_t idx = first + warp + it * stride;
+            const bool live = idx < round_size;
+            PatchSet ps;
+            ps.n = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int hs = (h4 >> (8 * i)) & 0xFF;
-                if (hs != 0xFF) {
-                    const bool has = (d.bitsT[(size_t)(hs >> 5) * d.Ppad + p] >> (hs & 31)) & 1u;
-                    miss |= !has;
-                    if (i == 0) ldis = has && ((int)d.leader[p] != hs);
+            for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
+            if (live) gen.run(seed, round, idx, round_size, ps);
+            __syncthreads();
+            if (live) {
+                int viol, obj;
+                eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
+                const unsigned long long key = pack_key(viol, obj, idx);
+                best = key < best ? key : best;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) s_red[warp] = best;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long v = lane < kWarps ? s_red[lane] : kKeyNone;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long w = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                v = w < v ? w : v;
+            }
+            if (lane == 0) {
+                if (v != kKeyNone) atomicMin(keys + t, v);
+                // grid barrier: every CTA's contribution to keys[t] is visible before anyone reads it
+                __threadfence();
+                atomicAdd(grid_bar, 1u);
+                const unsigned int target = (t + 1) * gridDim.x;
+                while (*reinterpret_cast<volatile unsigned int *>(grid_bar) < target) { }
+                __threadfence();
+            }
+        }
+        __syncthreads();
+        // the winner becomes the base: every CTA patches its own shared-memory copy
+        if (warp == 0) {
+            const unsigned long long k = __ldcg(keys + t);
+            if (k != kKeyNone) {
+                PatchSet ps;
+                gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps);
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < kMaxOps; ++i) {
+                        if (i < ps.n) {
+                            for (int w = 0; w < W; ++w) {
+                                const uint32_t v = gen.prow[i * W + w];
+                                s_bits[(size_t)w * d.Ppad + ps.p[i]] = v;
+                                if (blockIdx.x == 0) d.bitsT[(size_t)w * d.Ppad + ps.p[i]] = v;
+                            }
+                            s_leader[ps.p[i]] = (uint8_t)ps.ld[i];
+                            if (blockIdx.x == 0) d.leader[ps.p[i]] = (uint8_t)ps.ld[i];
+                        }
+                    }
                 }
             }
         }
-        const uint32_t mD = __ballot_sync(0xFFFFFFFFu, miss);
-        const uint32_t mL = __ballot_sync(0xFFFFFFFFu, ldis);
-        if (lane == 0) { s_cnt[warp] = __popc(mD); s_cntL[warp] = __popc(mL); }
         __syncthreads();
-        if (warp == 0) {
-            int c = s_cnt[lane], incl = c, cl = s_cntL[lane], incl2 = cl;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                const int v2 = __shfl_up_sync(0xFFFFFFFFu, incl2, o);
-                if (lane >= o) { incl += v; incl2 += v2; }
-            }
-            s_cnt[lane] = incl - c;
-            s_cntL[lane] = incl2 - cl;
-            if (lane == 31) { s_cnt[32] = incl; s_cntL[32] = incl2; }
-        }
-        __syncthreads();
-        const uint32_t below = (1u << lane) - 1u;
-        if (miss) d.D[baseD + s_cnt[warp] + __popc(mD & below)] = (uint16_t)p;
-        if (ldis) d.DL[baseL + s_cntL[warp] + __popc(mL & below)] = (uint16_t)p;
-        baseD += s_cnt[32];
-        baseL += s_cntL[32];
-        __syncthreads();
+        rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
     }
-    if (tid == 0) { d.nD[0] = baseD; d.nD[1] = baseL; }
 }
 
 // Explicit population: one warp per candidate, rows read straight from HBM (coalesced 128-bit
@@ -302,6 +436,7 @@ struct kao_handle {
     Consts *d_consts = nullptr; unsigned long long *d_key = nullptr; unsigned long long *d_keys = nullptr;
     size_t keys_cap = 0;
     long long *d_vo = nullptr;
+    unsigned int *d_bar = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
 };
@@ -319,58 +454,88 @@ template <class T> static cudaError_t dalloc(kao_handle *h, T **p, size_t bytes)
     return e;
 }
 
-template <class Cfg>
-static cudaError_t launch_round_cfg(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
-                                    uint32_t lo, uint32_t hi, unsigned long long *d_key,
-                                    unsigned long long *d_all, cudaStream_t st)
+struct RoundArgs {
+    uint64_t seed; uint32_t round, round_size, lo, hi; unsigned long long *d_key, *d_all; cudaStream_t st;
+};
+struct PersistArgs {
+    uint64_t seed; uint32_t first_round, rounds, round_size; unsigned long long *d_keys; unsigned int *d_bar; cudaStream_t st;
+};
+
+template <class Cfg> static cudaError_t set_smem_attr(kao_handle *h, const void *kern, bool *done)
 {
-    constexpr int T = threads_for<Cfg::W>();
-    auto kern = search_round_kernel<Cfg, T>;
-    static bool attr_done[64] = {};
-    if (!attr_done[h->device & 63]) {
+    if (!done[h->device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done[h->device & 63] = true;
+        done[h->device & 63] = true;
     }
-    const uint32_t n = hi - lo;
-    const uint32_t warps = T / 32;
-    uint32_t grid = (n + warps - 1) / warps;
-    if (grid > (uint32_t)h->grid) grid = (uint32_t)h->grid;
-    if (grid == 0) return cudaSuccess;
-    kern<<<grid, T, h->plan.total, st>>>(h->prm, h->plan, seed, round, round_size, lo, hi, d_key, d_all);
-    ++h->launches;
-    return cudaGetLastError();
+    return cudaSuccess;
 }
-template <int W, int NPH>
-static cudaError_t launch_round_w(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
-                                  uint32_t lo, uint32_t hi, unsigned long long *d_key,
-                                  unsigned long long *d_all, cudaStream_t st)
+
+struct LaunchRound {
+    template <class Cfg> cudaError_t run(kao_handle *h, const RoundArgs &a) const
+    {
+        constexpr int T = threads_for<Cfg::W>();
+        auto kern = search_round_kernel<Cfg, T>;
+        static bool done[64] = {};
+        cudaError_t e = set_smem_attr<Cfg>(h, reinterpret_cast<const void *>(kern), done);
+        if (e != cudaSuccess) return e;
+        const uint32_t n = a.hi - a.lo, warps = T / 32;
+        uint32_t grid = (n + warps - 1) / warps;
+        if (grid > (uint32_t)h->grid) grid = (uint32_t)h->grid;
+        if (grid == 0) return cudaSuccess;
+        kern<<<grid, T, h->plan.total, a.st>>>(h->prm, h->plan, a.seed, a.round, a.round_size, a.lo, a.hi, a.d_key, a.d_all);
+        ++h->launches;
+        return cudaGetLastError();
+    }
+};
+struct LaunchPersistent {
+    template <class Cfg> cudaError_t run(kao_handle *h, const PersistArgs &a) const
+    {
+        constexpr int T = threads_for<Cfg::W>();
+        auto kern = search_persistent_kernel<Cfg, T>;
+        static bool done[64] = {};
+        cudaError_t e = set_smem_attr<Cfg>(h, reinterpret_cast<const void *>(kern), done);
+        if (e != cudaSuccess) return e;
+        Params prm = h->prm; SmemPlan plan = h->plan;
+        uint64_t seed = a.seed; uint32_t fr = a.first_round, rounds = a.rounds, rs = a.round_size;
+        unsigned long long *keys = a.d_keys; unsigned int *bar = a.d_bar;
+        void *args[] = {&prm, &plan, &seed, &fr, &rounds, &rs, &keys, &bar};
+        ++h->launches;
+        // cooperative launch: all CTAs are guaranteed co-resident, which the grid barrier needs
+        return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(h->grid), dim3(T), args,
+                                           h->plan.total, a.st);
+    }
+};
+
+template <int W, int NPH, class F, class A>
+static cudaError_t dispatch_w(kao_handle *h, const F &f, const A &a)
 {
     const int planes = h->prm.nplanes;
     const bool hi1 = h->hm.hi1;
     if constexpr (W <= 2) {
-        if (planes == 3 && hi1) return launch_round_cfg<EvalCfg<W, NPH, true, 3>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
-        if (planes == 3) return launch_round_cfg<EvalCfg<W, NPH, false, 3>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
-        if (planes == 6 && hi1) return launch_round_cfg<EvalCfg<W, NPH, true, 6>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
-        if (planes == 6) return launch_round_cfg<EvalCfg<W, NPH, false, 6>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+        if (planes == 3 && hi1) return f.template run<EvalCfg<W, NPH, true, 3>>(h, a);
+        if (planes == 3) return f.template run<EvalCfg<W, NPH, false, 3>>(h, a);
+        if (planes == 6 && hi1) return f.template run<EvalCfg<W, NPH, true, 6>>(h, a);
+        if (planes == 6) return f.template run<EvalCfg<W, NPH, false, 6>>(h, a);
     }
-    if (hi1) return launch_round_cfg<EvalCfg<W, NPH, true, kObjEntries>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
-    return launch_round_cfg<EvalCfg<W, NPH, false, kObjEntries>>(h, seed, round, round_size, lo, hi, d_key, d_all, st);
+    if (hi1) return f.template run<EvalCfg<W, NPH, true, kObjEntries>>(h, a);
+    return f.template run<EvalCfg<W, NPH, false, kObjEntries>>(h, a);
+}
+template <class F, class A> static cudaError_t dispatch(kao_handle *h, const F &f, const A &a)
+{
+    const bool small = h->hm.Ppad / 32 <= 63;             // per-lane column counts fit 6 planes
+    switch (h->hm.W) {
+    case 1: return small ? dispatch_w<1, 3>(h, f, a) : dispatch_w<1, 5>(h, f, a);
+    case 2: return small ? dispatch_w<2, 3>(h, f, a) : dispatch_w<2, 5>(h, f, a);
+    case 4: return small ? dispatch_w<4, 3>(h, f, a) : dispatch_w<4, 5>(h, f, a);
+    default: return small ? dispatch_w<8, 3>(h, f, a) : dispatch_w<8, 5>(h, f, a);
+    }
 }
 static cudaError_t launch_round(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
                                 uint32_t lo, uint32_t hi, unsigned long long *d_key,
                                 unsigned long long *d_all, cudaStream_t st)
 {
-    const bool small = h->hm.Ppad / 32 <= 63;             // per-lane column counts fit 6 planes
-#define KAO_ROUND(Wv) (small ? launch_round_w<Wv, 3>(h, seed, round, round_size, lo, hi, d_key, d_all, st) \
-                             : launch_round_w<Wv, 5>(h, seed, round, round_size, lo, hi, d_key, d_all, st))
-    switch (h->hm.W) {
-    case 1: return KAO_ROUND(1);
-    case 2: return KAO_ROUND(2);
-    case 4: return KAO_ROUND(4);
-    default: return KAO_ROUND(8);
-    }
-#undef KAO_ROUND
+    return dispatch(h, LaunchRound{}, RoundArgs{seed, round, round_size, lo, hi, d_key, d_all, st});
 }
 static cudaError_t launch_apply(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
                                 const unsigned long long *d_key, int regen_only, cudaStream_t st)
@@ -588,10 +753,14 @@ extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, ui
         std::vector<unsigned long long> none(rounds, kKeyNone);
         CUDA_TRY(cudaMemcpy(h->d_keys, none.data(), (size_t)rounds * 8, cudaMemcpyHostToDevice));
     }
+    if (!h->d_bar) CUDA_TRY(dalloc(h, &h->d_bar, 16));
+    CUDA_TRY(cudaMemsetAsync(h->d_bar, 0, 16, 0));
     CUDA_TRY(cudaEventRecord(h->ev0, 0));
-    for (uint32_t t = 0; t < rounds; ++t) {
-        CUDA_TRY(launch_round(h, seed, first_round + t, round_size, 0, round_size, h->d_keys + t, nullptr, 0));
-        CUDA_TRY(launch_apply(h, seed, first_round + t, round_size, h->d_keys + t, 0, 0));
+    if (rounds) {
+        // all rounds in one cooperative launch; the HBM base is kept current by CTA 0, the displaced
+        // lists in HBM are rebuilt once at the end for the per-round entry points
+        CUDA_TRY(dispatch(h, LaunchPersistent{}, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0}));
+        CUDA_TRY(launch_apply(h, seed, first_round, round_size, h->d_keys, /*regen_only=*/1, 0));
     }
     CUDA_TRY(cudaEventRecord(h->ev1, 0));
     CUDA_TRY(cudaEventSynchronize(h->ev1));
