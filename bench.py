@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: per-round min inside the kernel over NVLink peer memory (p2p) or NCCL all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -179,11 +181,16 @@ def main():
     launch_cb, apply_cb = kd.session_callbacks(sess, key, SEED, gsize, stream)
     reduce_cb = (lambda k: dist.all_reduce(k, op=dist.ReduceOp.MIN)) if world > 1 else None
 
+    if world > 1 and args.collective == "p2p":
+        sess.p2p_setup_torch(dev)
+
     def step(k):
         """ROUNDS rounds; inputs (tables + base) are already resident in HBM."""
         if world == 1:
             sess.search(SEED, k * ROUNDS, ROUNDS, gsize)
-        else:   # sharded rounds: one 8-byte NCCL min all-reduce of the packed key per round
+        elif args.collective == "p2p":   # one persistent kernel per rank, keys traded over NVLink peer memory
+            sess.search_sharded(SEED, k * ROUNDS, ROUNDS, gsize)
+        else:   # per-round kernels + one 8-byte NCCL min all-reduce of the packed key per round
             kd.run_rounds(launch_cb, apply_cb, key, k * ROUNDS, ROUNDS, gsize, rank, world, reduce_cb)
 
     def barrier():
@@ -267,7 +274,10 @@ def main():
                 "config": {"workload": WORKLOAD, "rounds_per_step": ROUNDS, "round_size_per_gpu": ROUND_SIZE,
                            "candidates_per_step": ROUNDS * gsize, "seed": SEED,
                            "l2": "flushed between timed steps (256 MiB write); working set is shared-memory resident",
-                           "parallelism": "index-range sharding, %d rank(s), one 8-byte NCCL min per round" % world},
+                           "parallelism": ("single GPU" if world == 1 else
+                                           "index-range sharding over %d ranks; per-round 8-byte min %s" % (
+                                               world, "inside the persistent kernel over NVLink peer mailboxes"
+                                               if args.collective == "p2p" else "by NCCL all-reduce"))},
                 "search_state": {"violation": int(viol), "objective": int(obj), "moves": int(moves),
                                  "exact_optimum": {"objective": 6962, "moves": 38,
                                                    "source": "tests/golden/optima.json (HiGHS)"}},

@@ -134,6 +134,19 @@ int kao_round_launch(kao_handle *h, uint64_t seed, uint32_t round, uint32_t roun
 int kao_round_apply(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
                     const uint64_t *d_key, void *stream);
 
+/* sharded search with the reduction INSIDE the kernel: every rank owns a mailbox in its HBM that
+ * the peers map through CUDA IPC; per round the ranks min-reduce their 8-byte keys into every
+ * mailbox with NVLink atomics (no host, no NCCL in the loop).  Setup, once per session:
+ *   kao_p2p_export   -> 64 opaque bytes; all-gather them across the ranks (any transport);
+ *   kao_p2p_connect  <- the world's handles in rank order.
+ * kao_search_sharded must then be called by every rank with identical arguments; each evaluates
+ * its contiguous slice of every round and all end with the same base and the same round_keys. */
+#define KAO_IPC_HANDLE_BYTES 64
+int kao_p2p_export(kao_handle *h, uint8_t *handle_out /* [KAO_IPC_HANDLE_BYTES] */);
+int kao_p2p_connect(kao_handle *h, int32_t rank, int32_t world, const uint8_t *handles /* [world][64] */);
+int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                       uint32_t round_size, uint64_t *round_keys, double *device_ms);
+
 /* introspection for benchmarks: kernel launches issued by this handle so far, words per row */
 int kao_stats(kao_handle *h, uint64_t *kernel_launches, int32_t *words_per_row,
               int32_t *slots, int32_t *dense_weights);

@@ -594,7 +594,8 @@ __device__ __forceinline__ int column_violation(uint32_t (&pl)[NI][kPlanes], int
 //               part = the row (follower-weight classes) or the leader one-hot (leader bonus classes)
 //   kObjEntries up to 4 packed (slot, wF, wL) entries per partition
 //   dense       (inside kObjEntries, runtime flag) general [P][slots] table in HBM
-constexpr int kObjEntries = 0;   // kObj > 0: that many weighted mask planes (3 or 6, zero-padded)
+constexpr int kObjEntries = 0;   // kObj > 0: that many weighted mask planes (3 or 6, zero-padded):
+                                 // the first 2*kObj/3 apply to the row, the last kObj/3 to the leader one-hot
 constexpr int kMaxWPlanes = 6;
 
 template <int W_, int NPH_, bool kHi1_, int kObj_> struct EvalCfg {
@@ -664,8 +665,8 @@ __device__ __forceinline__ void tile_pass_a(const Params &d, const MemRef<kShare
     }
     if constexpr (Cfg::kObj > 0) {
 #pragma unroll
-        for (int c = 0; c < Cfg::kObj; ++c) {
-            if ((d.plane_on_leader >> c) & 1) {
+        for (int c = 2 * Cfg::kObj / 3; c < Cfg::kObj; ++c) {
+            {
                 int cnt = 0;
 #pragma unroll
                 for (int t = 0; t < W; ++t) {
@@ -690,8 +691,8 @@ __device__ __forceinline__ void tile_pass_b(const Params &d, const MemRef<kShare
     const int r0 = u * kTileRows + lane * kRowsPerLane;
     if constexpr (Cfg::kObj > 0) {
 #pragma unroll
-        for (int c = 0; c < Cfg::kObj; ++c) {
-            if (!((d.plane_on_leader >> c) & 1)) {
+        for (int c = 0; c < 2 * Cfg::kObj / 3; ++c) {
+            {
                 int cnt = 0;
 #pragma unroll
                 for (int t = 0; t < W; ++t) {

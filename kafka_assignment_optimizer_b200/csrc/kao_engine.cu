@@ -240,6 +240,34 @@ apply_winner_kernel(Params d, uint64_t seed, uint32_t round, uint32_t round_size
     rebuild_lists<1024>(d.bitsT, d.leader, d.homeT, d.P, d.Ppad, d.D, d.DL, d.nD, s_scan);
 }
 
+// Cross-GPU exchange state of the persistent kernel (docs/MODEL.md §7): every rank owns a mailbox
+// in its HBM that all peers map through CUDA IPC; per round the ranks min-reduce their 8-byte keys
+// into every mailbox with NVLink atomics and count arrivals — no host, no NCCL in the loop.
+constexpr int kMaxPeers = 8;
+constexpr uint32_t kMailRounds = 8192;          // rounds per launch when sharded
+struct Mailbox {
+    unsigned long long keys[2][kMailRounds];    // [bank][round]  min of the ranks' keys
+    unsigned int arrive[2][kMailRounds];        // [bank][round]  ranks that have contributed
+};
+struct P2P {
+    int rank, world, bank;
+    uint32_t idx_lo, idx_hi;                    // this rank's slice of every round
+    Mailbox *mail[kMaxPeers];                   // peer-mapped mailboxes, mail[rank] is local
+    unsigned long long *lkeys;                  // [rounds] this GPU's own minimum per round
+    unsigned int *release;                      // CTA 0 publishes "round t is decided" here
+    int *abort;                                 // set when a wait times out (a peer died): everybody leaves
+};
+
+__device__ __forceinline__ bool spin_until(const unsigned int *p, unsigned int target, int *abort_flag)
+{
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile unsigned int *>(p) < target) {
+        if (*reinterpret_cast<volatile int *>(abort_flag)) return false;
+        if (clock64() - t0 > 6000000000ll) { atomicExch(abort_flag, 1); return false; }   // ~3 s
+    }
+    return true;
+}
+
 // All rounds of a search in ONE launch (cooperative: one CTA per SM, all co-resident).  The base
 // and the tables stay in shared memory for the whole search; per round every CTA evaluates its
 // share of the candidates, min-reduces into keys[t], meets the other CTAs at a grid barrier, then
@@ -249,8 +277,9 @@ apply_winner_kernel(Params d, uint64_t seed, uint32_t round, uint32_t round_size
 template <class Cfg, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_round, uint32_t rounds,
-                         uint32_t round_size, unsigned long long *keys, unsigned int *grid_bar)
+                         uint32_t round_size, unsigned long long *keys, unsigned int *grid_bar, P2P pp)
 {
+    __shared__ int s_abort;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *s_bits = reinterpret_cast<uint32_t *>(smem + plan.off_bits);
     uint32_t *s_sw = reinterpret_cast<uint32_t *>(smem + plan.off_sw);
@@ -289,15 +318,16 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     gen.D = s_D; gen.DL = s_DL;
 
     const uint32_t stride = gridDim.x * kWarps;
-    const uint32_t first = blockIdx.x * kWarps;
-    const uint32_t iters = first < round_size ? (round_size - first + stride - 1) / stride : 0;
+    const uint32_t first = pp.idx_lo + blockIdx.x * kWarps;
+    const uint32_t iters = first < pp.idx_hi ? (pp.idx_hi - first + stride - 1) / stride : 0;
+    if (tid == 0) s_abort = 0;
     for (uint32_t t = 0; t < rounds; ++t) {
         const uint32_t round = first_round + t;
         gen.nD = s_counts[0]; gen.nL = s_counts[1];
         unsigned long long best = kKeyNone;
         for (uint32_t it = 0; it < iters; ++it) {
             const uint32_t idx = first + warp + it * stride;
-            const bool live = idx < round_size;
+            const bool live = idx < pp.idx_hi;
             PatchSet ps;
             ps.n = 0;
 #pragma unroll
@@ -322,16 +352,42 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 v = w < v ? w : v;
             }
             if (lane == 0) {
-                if (v != kKeyNone) atomicMin(keys + t, v);
-                // grid barrier: every CTA's contribution to keys[t] is visible before anyone reads it
-                __threadfence();
-                atomicAdd(grid_bar, 1u);
-                const unsigned int target = (t + 1) * gridDim.x;
-                while (*reinterpret_cast<volatile unsigned int *>(grid_bar) < target) { }
-                __threadfence();
+                if (pp.world == 1) {
+                    if (v != kKeyNone) atomicMin(keys + t, v);
+                    // grid barrier: every CTA's contribution to keys[t] is visible before anyone reads it
+                    __threadfence();
+                    atomicAdd(grid_bar, 1u);
+                    if (!spin_until(grid_bar, (t + 1) * gridDim.x, pp.abort)) s_abort = 1;
+                    __threadfence();
+                } else {
+                    // 1. this GPU's minimum
+                    if (v != kKeyNone) atomicMin(pp.lkeys + t, v);
+                    __threadfence();
+                    atomicAdd(grid_bar, 1u);
+                    if (blockIdx.x == 0) {
+                        // 2. CTA 0 trades it with every peer over NVLink: min into each mailbox, then arrive
+                        bool ok = spin_until(grid_bar, (t + 1) * gridDim.x, pp.abort);
+                        if (ok) {
+                            __threadfence();
+                            const unsigned long long mine = __ldcg(pp.lkeys + t);
+                            for (int r = 0; r < pp.world; ++r) atomicMin_system(&pp.mail[r]->keys[pp.bank][t], mine);
+                            __threadfence_system();
+                            for (int r = 0; r < pp.world; ++r) atomicAdd_system(&pp.mail[r]->arrive[pp.bank][t], 1u);
+                            ok = spin_until(&pp.mail[pp.rank]->arrive[pp.bank][t], (unsigned int)pp.world, pp.abort);
+                        }
+                        if (ok) {
+                            __threadfence_system();
+                            keys[t] = *reinterpret_cast<volatile unsigned long long *>(&pp.mail[pp.rank]->keys[pp.bank][t]);
+                            __threadfence();
+                            atomicExch(pp.release, t + 1);            // 3. local CTAs may read keys[t]
+                        } else s_abort = 1;
+                    } else if (!spin_until(pp.release, t + 1, pp.abort)) s_abort = 1;
+                    __threadfence();
+                }
             }
         }
         __syncthreads();
+        if (s_abort) return;                                        // a peer vanished: leave, the host reports it
         // the winner becomes the base: every CTA patches its own shared-memory copy
         if (warp == 0) {
             const unsigned long long k = __ldcg(keys + t);
@@ -358,6 +414,11 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         __syncthreads();
         rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
     }
+}
+
+__global__ void fill_u64_kernel(unsigned long long *p, unsigned long long v, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // Explicit population: one warp per candidate, rows read straight from HBM (coalesced 128-bit
@@ -436,7 +497,14 @@ struct kao_handle {
     Consts *d_consts = nullptr; unsigned long long *d_key = nullptr; unsigned long long *d_keys = nullptr;
     size_t keys_cap = 0;
     long long *d_vo = nullptr;
-    unsigned int *d_bar = nullptr;
+    unsigned int *d_bar = nullptr;          // [0] grid barrier, [1] release, [2] abort flag
+    // cross-GPU exchange (kao_p2p_*)
+    Mailbox *d_mail = nullptr;              // own mailbox (plain cudaMalloc: exported through CUDA IPC)
+    Mailbox *peer_mail[kMaxPeers] = {};
+    bool peer_opened[kMaxPeers] = {};
+    int p2p_rank = 0, p2p_world = 1;
+    uint64_t p2p_calls = 0;
+    unsigned long long *d_lkeys = nullptr; size_t lkeys_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
 };
@@ -459,6 +527,7 @@ struct RoundArgs {
 };
 struct PersistArgs {
     uint64_t seed; uint32_t first_round, rounds, round_size; unsigned long long *d_keys; unsigned int *d_bar; cudaStream_t st;
+    P2P pp;
 };
 
 template <class Cfg> static cudaError_t set_smem_attr(kao_handle *h, const void *kern, bool *done)
@@ -499,7 +568,8 @@ struct LaunchPersistent {
         Params prm = h->prm; SmemPlan plan = h->plan;
         uint64_t seed = a.seed; uint32_t fr = a.first_round, rounds = a.rounds, rs = a.round_size;
         unsigned long long *keys = a.d_keys; unsigned int *bar = a.d_bar;
-        void *args[] = {&prm, &plan, &seed, &fr, &rounds, &rs, &keys, &bar};
+        P2P pp = a.pp;
+        void *args[] = {&prm, &plan, &seed, &fr, &rounds, &rs, &keys, &bar, &pp};
         ++h->launches;
         // cooperative launch: all CTAs are guaranteed co-resident, which the grid barrier needs
         return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(h->grid), dim3(T), args,
@@ -568,6 +638,9 @@ extern "C" int kao_destroy(kao_handle *h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();                   // nothing of this session may still be running on a recycled buffer
     for (auto &b : h->owned) g_pool.put(h->device, b.first, b.second);
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
+    if (h->d_mail) cudaFree(h->d_mail);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -759,9 +832,107 @@ extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, ui
     if (rounds) {
         // all rounds in one cooperative launch; the HBM base is kept current by CTA 0, the displaced
         // lists in HBM are rebuilt once at the end for the per-round entry points
-        CUDA_TRY(dispatch(h, LaunchPersistent{}, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0}));
+        P2P pp{};
+        pp.rank = 0; pp.world = 1; pp.idx_lo = 0; pp.idx_hi = round_size;
+        pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
+        CUDA_TRY(dispatch(h, LaunchPersistent{}, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0, pp}));
         CUDA_TRY(launch_apply(h, seed, first_round, round_size, h->d_keys, /*regen_only=*/1, 0));
     }
+    CUDA_TRY(cudaEventRecord(h->ev1, 0));
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    if (device_ms) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *device_ms = ms;
+    }
+    if (round_keys && rounds)
+        CUDA_TRY(cudaMemcpy(round_keys, h->d_keys, (size_t)rounds * 8, cudaMemcpyDeviceToHost));
+    return KAO_OK;
+}
+
+// ---- cross-GPU sharded search: the 8-byte min of every round travels through peer-mapped mailboxes
+extern "C" int kao_p2p_export(kao_handle *h, uint8_t *handle_out)
+{
+    if (!h || !handle_out) return fail(KAO_E_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == KAO_IPC_HANDLE_BYTES, "ipc handle size");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->d_mail) {
+        CUDA_TRY(cudaMalloc(&h->d_mail, sizeof(Mailbox)));
+        fill_u64_kernel<<<64, 256>>>(&h->d_mail->keys[0][0], kKeyNone, 2 * (size_t)kMailRounds);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemset(&h->d_mail->arrive[0][0], 0, sizeof(h->d_mail->arrive)));
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t ipc;
+    CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->d_mail));
+    std::memcpy(handle_out, &ipc, sizeof ipc);
+    return KAO_OK;
+}
+
+extern "C" int kao_p2p_connect(kao_handle *h, int32_t rank, int32_t world, const uint8_t *handles)
+{
+    if (!h || !handles) return fail(KAO_E_ARG, "null argument");
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(KAO_E_ARG, "bad rank / world");
+    if (!h->d_mail) return fail(KAO_E_STATE, "call kao_p2p_export first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { h->peer_mail[r] = h->d_mail; continue; }
+        cudaIpcMemHandle_t ipc;
+        std::memcpy(&ipc, handles + (size_t)r * KAO_IPC_HANDLE_BYTES, sizeof ipc);
+        void *p = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_mail[r] = static_cast<Mailbox *>(p);
+        h->peer_opened[r] = true;
+    }
+    h->p2p_rank = rank; h->p2p_world = world; h->p2p_calls = 0;
+    return KAO_OK;
+}
+
+extern "C" int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                                  uint32_t round_size, uint64_t *round_keys, double *device_ms)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    if (!check_round_args(round_size)) return fail(KAO_E_ARG, "round_size must be 2..2^24");
+    if (h->p2p_world < 2 || !h->peer_mail[h->p2p_world - 1]) return fail(KAO_E_STATE, "kao_p2p_connect first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->keys_cap < rounds) {
+        h->d_keys = nullptr;
+        CUDA_TRY(dalloc(h, &h->d_keys, (size_t)(rounds > 0 ? rounds : 1) * 8));
+        h->keys_cap = rounds;
+    }
+    if (h->lkeys_cap < kMailRounds) {
+        CUDA_TRY(dalloc(h, &h->d_lkeys, (size_t)kMailRounds * 8));
+        h->lkeys_cap = kMailRounds;
+    }
+    if (!h->d_bar) CUDA_TRY(dalloc(h, &h->d_bar, 16));
+    const int world = h->p2p_world, rank = h->p2p_rank;
+    // contiguous slice of every round for this rank (same split on every rank)
+    const uint32_t base = round_size / world, extra = round_size % world;
+    const uint32_t lo = rank * base + ((uint32_t)rank < extra ? rank : extra);
+    const uint32_t hi = lo + base + ((uint32_t)rank < extra ? 1 : 0);
+    CUDA_TRY(cudaEventRecord(h->ev0, 0));
+    for (uint32_t done = 0; done < rounds; done += kMailRounds) {
+        const uint32_t n = rounds - done < kMailRounds ? rounds - done : kMailRounds;
+        const int bank = (int)(h->p2p_calls & 1);
+        ++h->p2p_calls;
+        // the OTHER bank is reset now: no peer can reach the next launch before this rank has taken
+        // part in every round of this one (docs/MODEL.md §7), so the reset cannot race with a writer
+        fill_u64_kernel<<<32, 256>>>(&h->d_mail->keys[bank ^ 1][0], kKeyNone, (size_t)kMailRounds);
+        CUDA_TRY(cudaMemsetAsync(&h->d_mail->arrive[bank ^ 1][0], 0, sizeof(unsigned int) * kMailRounds, 0));
+        fill_u64_kernel<<<32, 256>>>(h->d_lkeys, kKeyNone, (size_t)n);
+        CUDA_TRY(cudaMemsetAsync(h->d_bar, 0, 16, 0));
+        h->launches += 2;
+        P2P pp{};
+        pp.rank = rank; pp.world = world; pp.bank = bank; pp.idx_lo = lo; pp.idx_hi = hi;
+        for (int r = 0; r < world; ++r) pp.mail[r] = h->peer_mail[r];
+        pp.lkeys = h->d_lkeys; pp.release = h->d_bar + 1; pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
+        CUDA_TRY(dispatch(h, LaunchPersistent{}, PersistArgs{seed, first_round + done, n, round_size,
+                                                             h->d_keys + done, h->d_bar, 0, pp}));
+        int aborted = 0;
+        CUDA_TRY(cudaMemcpy(&aborted, h->d_bar + 2, 4, cudaMemcpyDeviceToHost));
+        if (aborted) return fail(KAO_E_CUDA, "sharded search timed out waiting for a peer GPU");
+    }
+    if (rounds) CUDA_TRY(launch_apply(h, seed, first_round, round_size, h->d_keys, /*regen_only=*/1, 0));
     CUDA_TRY(cudaEventRecord(h->ev1, 0));
     CUDA_TRY(cudaEventSynchronize(h->ev1));
     if (device_ms) {

@@ -144,15 +144,18 @@ inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &w
             if (l - f && std::find(vd.begin(), vd.end(), l - f) == vd.end()) vd.push_back(l - f);
             if (vf.size() + vd.size() > 6) ok = false;
         }
-        if (ok && vf.size() + vd.size() > 0) {
+        // kernels exist for 3 planes (2 row planes + 1 leader plane) and 6 (4 + 2); empty planes pad
+        if (ok && vf.size() + vd.size() > 0 && vf.size() <= 4 && vd.size() <= 2) {
             std::sort(vf.begin(), vf.end());
             std::sort(vd.begin(), vd.end());
-            const int used = (int)(vf.size() + vd.size());
-            m.nplanes = used <= 3 ? 3 : 6;                 // kernels exist for 3 and 6 planes; pad with empty ones
+            m.nplanes = (vf.size() <= 2 && vd.size() <= 1) ? 3 : 6;
+            const int nrow = 2 * m.nplanes / 3;
             m.planesT.assign((size_t)m.nplanes * m.W * m.Ppad, 0);
-            for (int c = 0; c < used; ++c) {
-                const bool on_leader = c >= (int)vf.size();
-                const uint32_t val = on_leader ? vd[c - vf.size()] : vf[c];
+            for (int c = 0; c < m.nplanes; ++c) {
+                const bool on_leader = c >= nrow;
+                const size_t k = on_leader ? (size_t)(c - nrow) : (size_t)c;
+                if (k >= (on_leader ? vd.size() : vf.size())) continue;        // padding plane
+                const uint32_t val = on_leader ? vd[k] : vf[k];
                 m.plane_value[c] = (int)val;
                 if (on_leader) m.plane_on_leader |= 1 << c;
                 for (int p = 0; p < pb.P; ++p)

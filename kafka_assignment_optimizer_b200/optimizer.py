@@ -163,6 +163,38 @@ class Session:
         _check(self._lib.kao_round_apply(self._h, C.c_uint64(seed), C.c_uint32(rnd), C.c_uint32(round_size),
                                          C.c_void_p(d_key_ptr), C.c_void_p(stream)))
 
+    # ---- sharded search with the per-round reduction inside the kernel (NVLink peer mailboxes)
+    def p2p_export(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        _check(self._lib.kao_p2p_export(self._h, buf))
+        return bytes(buf)
+
+    def p2p_connect(self, rank: int, world: int, handles):
+        """handles: the world's `p2p_export()` blobs in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(self._lib.kao_p2p_connect(self._h, C.c_int32(rank), C.c_int32(world), arr))
+
+    def p2p_setup_torch(self, device):
+        """Exchange the mailbox handles through torch.distributed (any backend) and connect."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        mine = torch.tensor(list(self.p2p_export()), dtype=torch.uint8, device=device)
+        got = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(got, mine)
+        self.p2p_connect(rank, world, [bytes(t.cpu().tolist()) for t in got])
+
+    def search_sharded(self, seed: int, first_round: int, rounds: int, round_size: int):
+        """Every rank calls this with identical arguments -> (per-round keys, device ms)."""
+        keys = np.zeros(max(rounds, 1), np.uint64)
+        ms = C.c_double()
+        _check(self._lib.kao_search_sharded(self._h, C.c_uint64(seed), C.c_uint32(first_round), C.c_uint32(rounds),
+                                            C.c_uint32(round_size), C.c_void_p(keys.ctypes.data), C.byref(ms)))
+        return keys[:rounds], ms.value
+
     def profile_rounds(self, seed, first_round, rounds, round_size):
         """-> (sum of search-kernel ms, sum of apply-kernel ms), CUDA events around every launch"""
         a, b = C.c_double(), C.c_double()

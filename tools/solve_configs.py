@@ -21,16 +21,23 @@ def main():
     opt = json.load(open(os.path.join(ROOT, "tests", "golden", "optima.json")))
     names = sys.argv[1:] or list(CONFIGS)
     for name in names:
+        over = name.split(":")                     # name[:round_size[:rounds[:seed]]]
+        name = over[0]
         args, size, rounds = CONFIGS[name]
+        if len(over) > 1:
+            size = int(over[1])
+        if len(over) > 2:
+            rounds = int(over[2])
+        seed = int(over[3], 0) if len(over) > 3 else 0x5EED
         pb = kao.synthetic_problem(*args)
         sess = kao.Session(pb)
         t0 = time.perf_counter()
         done, first_feasible, best_round = 0, None, None
         last = None
-        chunk = 100
+        chunk = max(100, rounds // 20)
         dev_ms = 0.0
         while done < rounds:
-            keys, ms = sess.search(0x5EED, done, chunk, size)
+            keys, ms = sess.search(seed, done, chunk, size)
             dev_ms += ms
             for i, k in enumerate(keys):
                 v, o, _ = kao.unpack_key(k)
@@ -41,7 +48,7 @@ def main():
             done += chunk
         reps, viol, obj, moves = sess.get_base()
         e = opt.get(name, {})
-        print(json.dumps({"config": name, "args": args, "round_size": size, "rounds": rounds,
+        print(json.dumps({"config": name, "args": args, "round_size": size, "rounds": rounds, "seed": seed,
                           "candidates": rounds * size, "violation": viol, "objective": obj, "moves": moves,
                           "exact_objective": e.get("objective"), "exact_moves": e.get("moves"),
                           "first_feasible_round": first_feasible, "last_improving_round": best_round,
