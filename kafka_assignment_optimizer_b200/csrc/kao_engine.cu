@@ -279,7 +279,6 @@ __global__ void __launch_bounds__(THREADS, 1)
 search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_round, uint32_t rounds,
                          uint32_t round_size, unsigned long long *keys, unsigned int *grid_bar, P2P pp)
 {
-    __shared__ int s_abort;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *s_bits = reinterpret_cast<uint32_t *>(smem + plan.off_bits);
     uint32_t *s_sw = reinterpret_cast<uint32_t *>(smem + plan.off_sw);
@@ -288,6 +287,8 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     uint32_t *s_prow = reinterpret_cast<uint32_t *>(smem + plan.off_prow);
     unsigned long long *s_red = reinterpret_cast<unsigned long long *>(smem + plan.off_red);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + plan.off_bar);
+    int &s_abort = *reinterpret_cast<int *>(smem + plan.off_bar + 8);   // no static shared memory: the
+                                                                        // dynamic limit is the full 227 KB
     uint16_t *s_D = reinterpret_cast<uint16_t *>(smem + plan.off_lists);
     uint16_t *s_DL = s_D + d.Ppad;
     int *s_counts = reinterpret_cast<int *>(smem + plan.off_lists + (size_t)d.Ppad * 4);
