@@ -9,6 +9,7 @@
 // Model: /root/reference/README.md:139-185; search/generator spec: docs/MODEL.md.
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #ifndef KAO_LOCKSTEP
 #define KAO_LOCKSTEP 1
 #endif
@@ -357,6 +358,32 @@ template <int W, int NPH> struct ColCounter {
             for (int k = 0; k < NPH; ++k) hi[k][t] = 0;
         }
     }
+    // Eight rows (two tiles) form one block of seven carry-save adders with a single ripple from
+    // the eights plane; the first tile parks its weight-4 word in `fa` (no row has to stay live).
+    uint32_t fa[W];
+    template <bool kSecond>
+    __device__ __forceinline__ void push_half(const uint32_t (&x)[kRowsPerLane][W])
+    {
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            uint32_t a2, b2, q4;
+            csa(a2, ones[t], ones[t], x[0][t], x[1][t]);
+            csa(b2, ones[t], ones[t], x[2][t], x[3][t]);
+            csa(q4, twos[t], twos[t], a2, b2);
+            if constexpr (!kSecond) {
+                fa[t] = q4;
+            } else {
+                uint32_t cy;
+                csa(cy, fours[t], fours[t], fa[t], q4);
+#pragma unroll
+                for (int k = 0; k < NPH; ++k) {
+                    const uint32_t n = hi[k][t] & cy;
+                    hi[k][t] ^= cy;
+                    cy = n;
+                }
+            }
+        }
+    }
     __device__ __forceinline__ void push4(const uint32_t (&x0)[W], const uint32_t (&x1)[W],
                                           const uint32_t (&x2)[W], const uint32_t (&x3)[W])
     {
@@ -638,50 +665,57 @@ __device__ __forceinline__ void load_tile(const MemRef<kShared> &bitsT, const Me
 //   part B  per row: the follower-weight part of the objective
 template <class Cfg, bool kShared, bool kCheckValid>
 __device__ __forceinline__ void tile_pass_a(const Params &d, const MemRef<kShared> &objT,
-                                            int lane, int u, ColCounter<Cfg::W, Cfg::NPH> &rc,
-                                            ColCounter<Cfg::W, Cfg::NPH> &lc, int &viol, int &obj,
-                                            const uint4 (&xv)[Cfg::W], uint32_t ld4)
+                                            int lane, int u, int &viol, int &obj,
+                                            const uint4 (&xv)[Cfg::W], uint32_t ld4,
+                                            uint32_t (&x)[kRowsPerLane][Cfg::W], uint32_t (&oh)[kRowsPerLane][Cfg::W])
 {
     constexpr int W = Cfg::W;
     const int r0 = u * kTileRows + lane * kRowsPerLane;
-    uint32_t x[kRowsPerLane][W], oh[kRowsPerLane][W];
 #pragma unroll
     for (int i = 0; i < kRowsPerLane; ++i) {
 #pragma unroll
         for (int t = 0; t < W; ++t) x[i][t] = comp(xv[t], i);
         const uint32_t ld = (ld4 >> (8 * i)) & 0xFFu;
         // leader one-hot restricted to the row: C2/C5 hold by construction of the encoding
-        const uint32_t ldbit = __funnelshift_l(0u, 1u, ld);      // 1 << (ld & 31)
         uint32_t any = 0;
+        if constexpr (W == 2) {
+            unsigned long long ob;                               // 1 << ld; PTX shl clamps: ld >= 64 gives 0
+            asm("shl.b64 %0, %1, %2;" : "=l"(ob) : "l"(1ull), "r"(ld));
+            oh[i][0] = x[i][0] & (uint32_t)ob;
+            oh[i][1] = x[i][1] & (uint32_t)(ob >> 32);
+            any = oh[i][0] | oh[i][1];
+        } else {
+            const uint32_t ldbit = __funnelshift_l(0u, 1u, ld);  // 1 << (ld & 31)
 #pragma unroll
-        for (int t = 0; t < W; ++t) {
-            const uint32_t lm = ((int)(ld >> 5) == t) ? ldbit : 0u;      // mask first: no indexed row access
-            oh[i][t] = x[i][t] & lm;
-            any |= oh[i][t];
+            for (int t = 0; t < W; ++t) {
+                const uint32_t lm = ((int)(ld >> 5) == t) ? ldbit : 0u;  // mask first: no indexed row access
+                oh[i][t] = x[i][t] & lm;
+                any |= oh[i][t];
+            }
         }
         int rv = row_rack_terms<W, Cfg::kHi1>(x[i], d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF) + (any ? 0 : 1);
         if constexpr (kCheckValid) rv = ((r0 + i) < d.P) ? rv : 0;
         viol += rv;
     }
     if constexpr (Cfg::kObj > 0) {
+        // leader-bonus planes: the one-hot has at most one bit, so "any overlap" replaces a popcount
 #pragma unroll
         for (int c = 2 * Cfg::kObj / 3; c < Cfg::kObj; ++c) {
-            {
-                int cnt = 0;
+            uint4 m[W];
 #pragma unroll
-                for (int t = 0; t < W; ++t) {
-                    const uint4 m = objT.ld128((uint32_t)((c * W + t) * d.Ppad + r0) * 4u);
+            for (int t = 0; t < W; ++t) m[t] = objT.ld128((uint32_t)((c * W + t) * d.Ppad + r0) * 4u);
+            int cnt = 0;
 #pragma unroll
-                    for (int i = 0; i < kRowsPerLane; ++i) cnt += __popc(oh[i][t] & comp(m, i));
-                }
-                obj += cnt * d.plane_value[c];
+            for (int i = 0; i < kRowsPerLane; ++i) {
+                uint32_t hit = 0;
+#pragma unroll
+                for (int t = 0; t < W; ++t) hit |= oh[i][t] & comp(m[t], i);
+                cnt += hit ? 1 : 0;
             }
+            obj += cnt * d.plane_value[c];
         }
     }
-    rc.push4(x[0], x[1], x[2], x[3]);
-    lc.push4(oh[0], oh[1], oh[2], oh[3]);
 }
-
 template <class Cfg, bool kShared, bool kCheckValid>
 __device__ __forceinline__ void tile_pass_b(const Params &d, const MemRef<kShared> &objT,
                                             int lane, int u, int &obj,
@@ -741,6 +775,53 @@ __device__ __forceinline__ void tile_pass_b(const Params &d, const MemRef<kShare
     }
 }
 
+// Two tiles (8 rows per lane) = one carry-save block.  Ppad is a multiple of 256, so the second
+// tile of the last pair exists in memory even when it holds no real row.
+template <class Cfg, bool kShared, bool kChk>
+__device__ __forceinline__ void eval_pair(const Params &d, const MemRef<kShared> &m_bits,
+                                          const MemRef<kShared> &m_leader, const MemRef<kShared> &m_obj,
+                                          const PatchSet &ps, const uint32_t *prow, int lane, int u,
+                                          ColCounter<Cfg::W, Cfg::NPH> &rc, ColCounter<Cfg::W, Cfg::NPH> &lc,
+                                          int &viol, int &obj)
+{
+    constexpr int W = Cfg::W;
+    {
+        uint4 xv[W];
+        uint32_t ld4, x[kRowsPerLane][W], oh[kRowsPerLane][W];
+        load_tile<W, kShared>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ld4);
+        tile_pass_a<Cfg, kShared, kChk>(d, m_obj, lane, u, viol, obj, xv, ld4, x, oh);
+        tile_pass_b<Cfg, kShared, kChk>(d, m_obj, lane, u, obj, xv, ld4);
+        rc.template push_half<false>(x);
+        lc.template push_half<false>(oh);
+    }
+    {
+        uint4 xv[W];
+        uint32_t ld4, x[kRowsPerLane][W], oh[kRowsPerLane][W];
+        load_tile<W, kShared>(m_bits, m_leader, d.Ppad, ps, prow, lane, u + 1, xv, ld4);
+        tile_pass_a<Cfg, kShared, kChk>(d, m_obj, lane, u + 1, viol, obj, xv, ld4, x, oh);
+        tile_pass_b<Cfg, kShared, kChk>(d, m_obj, lane, u + 1, obj, xv, ld4);
+        rc.template push_half<true>(x);
+        lc.template push_half<true>(oh);
+    }
+}
+
+template <class Cfg, bool kShared, bool kChk>
+__device__ __forceinline__ void eval_single(const Params &d, const MemRef<kShared> &m_bits,
+                                            const MemRef<kShared> &m_leader, const MemRef<kShared> &m_obj,
+                                            const PatchSet &ps, const uint32_t *prow, int lane, int u,
+                                            ColCounter<Cfg::W, Cfg::NPH> &rc, ColCounter<Cfg::W, Cfg::NPH> &lc,
+                                            int &viol, int &obj)
+{
+    constexpr int W = Cfg::W;
+    uint4 xv[W];
+    uint32_t ld4, x[kRowsPerLane][W], oh[kRowsPerLane][W];
+    load_tile<W, kShared>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ld4);
+    tile_pass_a<Cfg, kShared, kChk>(d, m_obj, lane, u, viol, obj, xv, ld4, x, oh);
+    tile_pass_b<Cfg, kShared, kChk>(d, m_obj, lane, u, obj, xv, ld4);
+    rc.push4(x[0], x[1], x[2], x[3]);
+    lc.push4(oh[0], oh[1], oh[2], oh[3]);
+}
+
 // Evaluates candidate = base + patches.  kShared: base/weights are in shared memory.
 // Outputs (same value in every lane): total violation amount and objective.
 template <class Cfg, bool kShared>
@@ -756,23 +837,22 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
     ColCounter<W, NPH> rc, lc;
     rc.clear();
     lc.clear();
-    {
+    if constexpr (W <= 2) {
         int u = 0;
 #pragma unroll 1
-        for (; u < nfull; ++u) {
-            uint4 xv[W];
-            uint32_t ld4;
-            load_tile<W, kShared>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ld4);
-            tile_pass_a<Cfg, kShared, false>(d, m_obj, lane, u, rc, lc, viol, obj, xv, ld4);
-            tile_pass_b<Cfg, kShared, false>(d, m_obj, lane, u, obj, xv, ld4);
-        }
-        if (u < ntiles) {
-            uint4 xv[W];
-            uint32_t ld4;
-            load_tile<W, kShared>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ld4);
-            tile_pass_a<Cfg, kShared, true>(d, m_obj, lane, u, rc, lc, viol, obj, xv, ld4);
-            tile_pass_b<Cfg, kShared, true>(d, m_obj, lane, u, obj, xv, ld4);
-        }
+        for (; u + 2 <= nfull; u += 2)
+            eval_pair<Cfg, kShared, false>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
+#pragma unroll 1
+        for (; u < ntiles; u += 2)
+            eval_pair<Cfg, kShared, true>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
+    } else {
+        // wide rows: one tile per iteration (the two-tile block would not fit the register file)
+        int u = 0;
+#pragma unroll 1
+        for (; u < nfull; ++u)
+            eval_single<Cfg, kShared, false>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
+        if (u < ntiles)
+            eval_single<Cfg, kShared, true>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
     }
 
     constexpr int NP0 = 3 + NPH;

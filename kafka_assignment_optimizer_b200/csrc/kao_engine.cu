@@ -252,7 +252,7 @@ struct Mailbox {
 struct P2P {
     int rank, world, bank;
     uint32_t idx_lo, idx_hi;                    // this rank's slice of every round
-    Mailbox *mail[kMaxPeers];                   // peer-mapped mailboxes, mail[rank] is local
+    Mailbox *const *mail;                       // [world] peer-mapped mailboxes (device array), mail[rank] is local
     unsigned long long *lkeys;                  // [rounds] this GPU's own minimum per round
     unsigned int *release;                      // CTA 0 publishes "round t is decided" here
     int *abort;                                 // set when a wait times out (a peer died): everybody leaves
@@ -502,6 +502,7 @@ struct kao_handle {
     // cross-GPU exchange (kao_p2p_*)
     Mailbox *d_mail = nullptr;              // own mailbox (plain cudaMalloc: exported through CUDA IPC)
     Mailbox *peer_mail[kMaxPeers] = {};
+    Mailbox **d_mailptrs = nullptr;         // device copy of peer_mail for the kernel
     bool peer_opened[kMaxPeers] = {};
     int p2p_rank = 0, p2p_world = 1;
     uint64_t p2p_calls = 0;
@@ -885,6 +886,8 @@ extern "C" int kao_p2p_connect(kao_handle *h, int32_t rank, int32_t world, const
         h->peer_mail[r] = static_cast<Mailbox *>(p);
         h->peer_opened[r] = true;
     }
+    if (!h->d_mailptrs) CUDA_TRY(dalloc(h, &h->d_mailptrs, sizeof(Mailbox *) * kMaxPeers));
+    CUDA_TRY(cudaMemcpy(h->d_mailptrs, h->peer_mail, sizeof(Mailbox *) * kMaxPeers, cudaMemcpyHostToDevice));
     h->p2p_rank = rank; h->p2p_world = world; h->p2p_calls = 0;
     return KAO_OK;
 }
@@ -925,7 +928,7 @@ extern "C" int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_r
         h->launches += 2;
         P2P pp{};
         pp.rank = rank; pp.world = world; pp.bank = bank; pp.idx_lo = lo; pp.idx_hi = hi;
-        for (int r = 0; r < world; ++r) pp.mail[r] = h->peer_mail[r];
+        pp.mail = h->d_mailptrs;
         pp.lkeys = h->d_lkeys; pp.release = h->d_bar + 1; pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
         CUDA_TRY(dispatch(h, LaunchPersistent{}, PersistArgs{seed, first_round + done, n, round_size,
                                                              h->d_keys + done, h->d_bar, 0, pp}));
