@@ -72,7 +72,8 @@ typedef struct kao_options {
     uint32_t rounds;          /* search rounds; candidates evaluated = rounds * round_size */
     uint32_t round_size;      /* candidates per round, 2 .. KAO_MAX_ROUND_SIZE */
     int32_t device;           /* CUDA device ordinal */
-    uint32_t flags;           /* reserved, 0 */
+    uint32_t flags;           /* bits 0-7: independent restarts (0 or 1 = one search); the best final
+                                 assignment of rounds*round_size candidates each is returned */
 } kao_options;
 
 typedef struct kao_result {
@@ -85,7 +86,7 @@ typedef struct kao_result {
     uint64_t key;             /* packed (violation, cost, index) of the last winning candidate */
     uint64_t n_candidates;    /* candidates generated and fully evaluated */
     uint32_t rounds_run;
-    uint32_t reserved;
+    uint32_t reserved;        /* restarts performed */
     double device_ms;         /* CUDA-event time of the search kernels */
     double total_ms;          /* wall time of the call incl. host<->device copies */
 } kao_result;

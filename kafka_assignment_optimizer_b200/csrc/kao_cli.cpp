@@ -258,7 +258,7 @@ int usage()
 {
     std::fprintf(stderr,
                  "usage: kao-cli --assignment FILE|- --brokers 0,1,2 --racks 0:a,1:b,2:a [--rf N]\n"
-                 "               [--rounds 256] [--round-size 32768] [--seed 24301] [--device 0] [--emit-lp] [--stats]\n");
+                 "               [--rounds 256] [--round-size 32768] [--restarts 1] [--seed 24301] [--device 0] [--emit-lp] [--stats]\n");
     return 2;
 }
 
@@ -314,6 +314,7 @@ int main(int argc, char **argv)
         opt.rounds = a.count("rounds") ? (uint32_t)std::atoi(a["rounds"].c_str()) : 256;
         opt.round_size = a.count("round-size") ? (uint32_t)std::atoi(a["round-size"].c_str()) : 32768;
         opt.device = a.count("device") ? std::atoi(a["device"].c_str()) : 0;
+        opt.flags = a.count("restarts") ? (uint32_t)std::min(255, std::max(1, std::atoi(a["restarts"].c_str()))) : 1u;
         std::vector<int32_t> reps((size_t)m.P * m.RF, -1);
         kao_result res{};
         res.replicas = reps.data();

@@ -1057,17 +1057,35 @@ extern "C" int kao_solve(const kao_problem *pb, const kao_options *opt, kao_resu
     kao_handle *h = nullptr;
     int rc = kao_create(pb, opt->device, &h);
     if (rc != KAO_OK) return rc;
+    // independent restarts (flags & 0xFF, 0 and 1 both mean a single search): each restarts from the
+    // initial base with its own seed; the best final assignment wins (violation, then objective)
+    const uint32_t restarts = (opt->flags & 0xFFu) ? (opt->flags & 0xFFu) : 1u;
     std::vector<uint64_t> keys(opt->rounds ? opt->rounds : 1, kKeyNone);
-    double dev_ms = 0;
-    rc = kao_search(h, opt->seed, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms);
-    if (rc == KAO_OK) rc = kao_get_base(h, res->replicas, &res->violation, &res->objective, &res->moves);
+    std::vector<int32_t> reps((size_t)pb->P * pb->RF);
+    double dev_ms_total = 0;
+    bool have = false;
+    for (uint32_t r = 0; r < restarts && rc == KAO_OK; ++r) {
+        double dev_ms = 0;
+        int64_t viol = 0, obj = 0;
+        int32_t moves = 0;
+        if (r) rc = kao_reset(h);
+        if (rc == KAO_OK) rc = kao_search(h, opt->seed + 0x9E3779B97F4A7C15ull * r, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms);
+        if (rc == KAO_OK) rc = kao_get_base(h, reps.data(), &viol, &obj, &moves);
+        if (rc != KAO_OK) break;
+        dev_ms_total += dev_ms;
+        if (!have || viol < res->violation || (viol == res->violation && obj > res->objective)) {
+            std::memcpy(res->replicas, reps.data(), reps.size() * 4);
+            res->violation = viol; res->objective = obj; res->moves = moves;
+            res->key = opt->rounds ? keys[opt->rounds - 1] : kKeyNone;
+            have = true;
+        }
+    }
     if (rc == KAO_OK) {
         res->feasible = res->violation == 0;
-        res->key = opt->rounds ? keys[opt->rounds - 1] : kKeyNone;
-        res->n_candidates = (uint64_t)opt->rounds * opt->round_size;
+        res->n_candidates = (uint64_t)restarts * opt->rounds * opt->round_size;
         res->rounds_run = opt->rounds;
-        res->reserved = 0;
-        res->device_ms = dev_ms;
+        res->reserved = restarts;
+        res->device_ms = dev_ms_total;
     }
     kao_destroy(h);
     res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -188,6 +188,17 @@ def test_sharded_round_equals_unsharded():
     parts.close()
 
 
+def test_restarts_keep_the_best_assignment(golden_optima):
+    """kao_options.flags: independent restarts; the result is the best of them (never worse than one)."""
+    e = golden_optima["cfg2_rm2"]
+    pb = product(m.synthetic_problem(*e["args"]))
+    one = kopt.solve(pb, seed=11, rounds=60, round_size=2048)
+    four = kopt.solve(pb, seed=11, rounds=60, round_size=2048, restarts=4)
+    assert four.n_candidates == 4 * one.n_candidates
+    assert (four.violation, -four.objective) <= (one.violation, -one.objective)
+    assert m.evaluate(m.synthetic_problem(*e["args"]), four.replicas) == (four.violation, four.objective)
+
+
 def test_abi_rejects_bad_input():
     pb = product(SHAPES["tiny"]())
     with pytest.raises(kao.KaoError):
