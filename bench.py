@@ -247,6 +247,12 @@ def main():
                     "peak_source": peak_src,
                     "note": "candidates are generated and consumed on-chip (shared memory); measured DRAM "
                             "traffic is far below the algorithmic bytes by design"}
+        # SURVEY 8(f)3, reported separately: the same search with delta evaluation (NOT the headline metric)
+        dkeys, d_ms = sess.search_delta(SEED, 30_000, ROUNDS, ROUND_SIZE)
+        dkeys, d_ms = sess.search_delta(SEED, 31_000, ROUNDS, ROUND_SIZE)
+        delta = {"value": ROUNDS * ROUND_SIZE / (d_ms * 1e-3), "unit": "candidates/s", "kernel_ms_per_launch": d_ms,
+                 "note": "same candidate stream and keys, scored from base totals + patched rows (one thread per "
+                         "candidate); not a full evaluation per candidate, so not comparable with `value`"}
         # end to end through the public C-ABI call with HOST buffers (tables up, winner down, every step)
         e2e_steps = max(3, min(args.steps, 6))
         # the step's inputs live in pinned host memory; kao_solve copies them to the device every call
@@ -286,7 +292,7 @@ def main():
                 "search_state": {"violation": int(viol), "objective": int(obj), "moves": int(moves),
                                  "exact_optimum": {"objective": 6962, "moves": 38,
                                                    "source": "tests/golden/optima.json (HiGHS)"}},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "delta_evaluation": delta, "gpu_launches": int(launches),
                 "clocks": clocks}
         print(json.dumps(line))
     sess.close()

@@ -119,6 +119,16 @@ int kao_get_base(kao_handle *h, int32_t *replicas, int64_t *violation, int64_t *
 int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
                uint32_t round_size, uint64_t *round_keys, double *device_ms);
 
+/* SURVEY.md 8(f)3 — the same search with DELTA evaluation: every candidate's key is derived from
+ * the base's totals and its <= 3 patched rows (one thread per candidate) instead of a full pass
+ * over its bit-plane.  Keys, winners and trajectory are bit-identical to kao_search; throughput
+ * is reported separately (it is not the "full evaluation per candidate" metric).  Rows of up to 64
+ * broker slots. */
+int kao_search_delta(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                     uint32_t round_size, uint64_t *round_keys, double *device_ms);
+int kao_candidate_keys_delta(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                             uint32_t idx_begin, uint32_t count, uint64_t *keys);
+
 /* keys of candidates idx_begin .. idx_begin+count-1 of `round` against the current base (host
  * buffer) — the per-candidate parity vector. */
 int kao_candidate_keys(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,

@@ -133,7 +133,9 @@ struct PatchSet {
     uint32_t ld[kMaxOps];    // its leader slot in the candidate
 };
 
-template <int W> struct Gen {
+// kThread = false: one warp generates one candidate cooperatively (patched rows go to `prow`);
+// kThread = true : every thread generates its own candidate (patched rows go to the caller's registers).
+template <int W, bool kThread = false> struct Gen {
     const uint32_t *bitsT;   // base (shared or global)
     const uint8_t *leader;
     const Consts *cs;
@@ -149,7 +151,8 @@ template <int W> struct Gen {
         for (int t = 0; t < W; ++t) row[t] = bitsT[(size_t)t * d->Ppad + p];
         ld = leader[p];
     }
-    __device__ __forceinline__ void push(PatchSet &ps, int p, const uint32_t (&row)[W], uint32_t ld) const
+    __device__ __forceinline__ void push(PatchSet &ps, int p, const uint32_t (&row)[W], uint32_t ld,
+                                         uint32_t (&rows)[kMaxOps][W]) const
     {
         int slot = ps.n;
 #pragma unroll
@@ -158,7 +161,14 @@ template <int W> struct Gen {
         // static stores keep ps in registers
 #pragma unroll
         for (int i = 0; i < kMaxOps; ++i) if (i == slot) { ps.p[i] = p; ps.ld[i] = ld; }
-        if (lane == 0) {
+        if constexpr (kThread) {
+#pragma unroll
+            for (int i = 0; i < kMaxOps; ++i)
+                if (i == slot) {
+#pragma unroll
+                    for (int t = 0; t < W; ++t) rows[i][t] = row[t];
+                }
+        } else if (lane == 0) {
 #pragma unroll
             for (int t = 0; t < W; ++t) prow[slot * W + t] = row[t];
         }
@@ -202,6 +212,21 @@ template <int W> struct Gen {
         if (src < 0 || src >= W * 32) return -1;
         const uint32_t *col = bitsT + (size_t)(src >> 5) * d->Ppad;
         const uint32_t bit = 1u << (src & 31);
+        if constexpr (kThread) {
+            int q = p0;
+            for (int k = 0; k < P; ++k) {
+                bool t = false;
+#pragma unroll
+                for (int i = 0; i < kMaxOps; ++i) t |= (ps.p[i] == q);
+                bool hit = false;
+                if (KIND == 0) hit = !t && (col[q] & bit);
+                if (KIND == 1) hit = !t && ((int)leader[q] == src);
+                if (KIND == 2) hit = !t && ((int)leader[q] != src) && (col[q] & bit);
+                if (hit) return q;
+                q = (q + 1 == P) ? 0 : q + 1;
+            }
+            return -1;
+        }
         for (int k = 0; k < P; k += 32) {
             const int off = k + lane;
             int q = p0 + off;
@@ -226,7 +251,8 @@ template <int W> struct Gen {
     }
 
     // docs/MODEL.md §5 — must stay bit-identical to the restated generator the tests check against
-    __device__ void run(uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size, PatchSet &ps) const
+    __device__ void run(uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size, PatchSet &ps,
+                        uint32_t (&rows)[kMaxOps][W]) const
     {
         ps.n = 0;
 #pragma unroll
@@ -249,7 +275,7 @@ template <int W> struct Gen {
             if (guided) { const int h0 = d->homeT[p] & 0xFF; want = (h0 == 0xFF) ? -1 : h0; }
             hi = pick_leader(row, ld, want, r[2]);
             if (hi < 0) return;
-            push(ps, p, row, ld);
+            push(ps, p, row, ld, rows);
         } else {
             const bool guided = gbit && nD > 0;
             const int p = guided ? (int)D[mulhi32(r[1], (uint32_t)nD)] : (int)mulhi32(r[1], (uint32_t)P);
@@ -278,7 +304,7 @@ template <int W> struct Gen {
             }
             hi = replace(row, ld, a, o);
             lo = a;
-            push(ps, p, row, ld);
+            push(ps, p, row, ld, rows);
         }
         if (nops == 1) return;
         philox4x32_10(idx, round, 1u, kTag, (uint32_t)seed, (uint32_t)(seed >> 32), s);
@@ -295,7 +321,7 @@ template <int W> struct Gen {
                 if (q < 0) return;
                 read_row(q, rq, lq);
                 hi = replace(rq, lq, hi, close ? olo : (int)mulhi32(rb, (uint32_t)B));
-                push(ps, q, rq, lq);
+                push(ps, q, rq, lq, rows);
             } else if (link == 1) {                            // R-pull
                 const int q = start;
                 bool t = false;
@@ -309,7 +335,7 @@ template <int W> struct Gen {
                 if (close && (int)lq < W * 32 && row_has<W>(rq, (int)lq)) src = (int)lq;
                 replace(rq, lq, src, olo);
                 lo = src;
-                push(ps, q, rq, lq);
+                push(ps, q, rq, lq, rows);
             } else if (link == 2) {                            // L-push
                 const int q = find_from<1>(ps, start, hi);
                 if (q < 0) return;
@@ -319,7 +345,7 @@ template <int W> struct Gen {
                 const int t = pick_leader(rq, lq, want, rb);
                 if (t < 0) return;
                 hi = t;
-                push(ps, q, rq, lq);
+                push(ps, q, rq, lq, rows);
             } else {                                           // L-pull
                 const int q = find_from<2>(ps, start, lo);
                 if (q < 0) return;
@@ -327,7 +353,7 @@ template <int W> struct Gen {
                 const int old = (int)lq;
                 if (pick_leader(rq, lq, lo, rb) < 0) return;
                 lo = old;
-                push(ps, q, rq, lq);
+                push(ps, q, rq, lq, rows);
             }
         }
     }
@@ -876,6 +902,155 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
     }
     viol_out = __reduce_add_sync(0xFFFFFFFFu, viol);
     obj_out = __reduce_add_sync(0xFFFFFFFFu, obj);
+}
+
+// ------------------------------------------------------------------------------------------
+// Delta evaluation (docs/MODEL.md §8): the SAME key as the full evaluator,
+// computed from the base's totals and the candidate's <= 3 patched rows.  One THREAD per candidate.
+// Reported separately from the full-evaluation throughput.
+// ------------------------------------------------------------------------------------------
+// C1 + C7 + leader validity and the objective of ONE row
+template <class Cfg, bool kShared>
+__device__ __forceinline__ void row_eval(const Params &d, const MemRef<kShared> &objT, int p,
+                                         const uint32_t (&x)[Cfg::W], uint32_t ld, int &rv, int &ro)
+{
+    constexpr int W = Cfg::W;
+    uint32_t oh[W], any = 0;
+    const uint32_t ldbit = __funnelshift_l(0u, 1u, ld);
+#pragma unroll
+    for (int t = 0; t < W; ++t) {
+        const uint32_t lm = ((int)(ld >> 5) == t) ? ldbit : 0u;
+        oh[t] = x[t] & lm;
+        any |= oh[t];
+    }
+    rv = row_rack_terms<W, Cfg::kHi1>(x, d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF) + (any ? 0 : 1);
+    ro = 0;
+    if constexpr (Cfg::kObj > 0) {
+#pragma unroll
+        for (int c = 0; c < Cfg::kObj; ++c) {
+            int cnt = 0;
+#pragma unroll
+            for (int t = 0; t < W; ++t) {
+                const uint32_t m = objT.ld32((uint32_t)((c * W + t) * d.Ppad + p) * 4u);
+                cnt += __popc((c < 2 * Cfg::kObj / 3 ? x[t] : oh[t]) & m);
+            }
+            ro += cnt * d.plane_value[c];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < d.nentries) {
+                const uint32_t e = objT.ld32((uint32_t)(k * d.Ppad + p) * 4u);
+                const uint32_t slot = e & 0xFFu;
+                const uint32_t xw = row_word<W>(x, (int)(slot >> 5));
+                const bool bit = __funnelshift_r(xw, 0u, slot) & 1u;
+                const uint32_t w = (slot == ld) ? (e >> 20) : ((e >> 8) & 0xFFFu);
+                ro += bit ? (int)w : 0;
+            }
+        if (d.dense) {
+            const uint32_t *wrow = d.dense_w + (size_t)p * d.NS;
+#pragma unroll
+            for (int t = 0; t < W; ++t) {
+                for (uint32_t m = x[t]; m; m &= m - 1) {
+                    const int s = t * 32 + __ffs(m) - 1;
+                    if (s < d.NS) {
+                        const uint32_t w = __ldg(wrow + s);
+                        ro += (s == (int)ld) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
+                    }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int band_violation(int c, uint32_t lohi)
+{
+    const int lo = (int)(lohi & 0xFFFFu), hi = (int)(lohi >> 16);
+    return max(c - hi, 0) + max(lo - c, 0);
+}
+
+// events: (slot, +-1) pairs; applies the NET change of every distinct slot once
+template <int N, class F> __device__ __forceinline__ int apply_events(const int (&slot)[N], const int (&val)[N], F cost)
+{
+    int dv = 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        bool first = slot[j] >= 0;
+        int net = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (k < j && slot[k] == slot[j]) first = false;
+            net += (slot[k] == slot[j]) ? val[k] : 0;
+        }
+        if (first && net != 0) dv += cost(slot[j], net);
+    }
+    return dv;
+}
+
+template <int W> __device__ __forceinline__ int lone_slot(const uint32_t (&m)[W])
+{
+    int s = -1;
+#pragma unroll
+    for (int t = 0; t < W; ++t) if (m[t]) s = t * 32 + __ffs(m[t]) - 1;
+    return s;
+}
+
+// cnt / lcnt: replica and (valid) leader count per slot of the BASE, rc: replica count per rack,
+// base_viol / base_obj: the base's own evaluation.  Every patched partition differs from the base
+// by at most one replica move and/or a leader change (MODEL 5: an op never revisits a partition).
+template <class Cfg>
+__device__ __forceinline__ void delta_eval(const Params &d, const uint32_t *s_bits, const uint8_t *s_leader,
+                                           const MemRef<true> &objT, const Consts *cs, const PatchSet &ps,
+                                           const uint32_t (&rows)[kMaxOps][Cfg::W], const int *cnt, const int *lcnt,
+                                           const int *rc, int base_viol, int base_obj, int &viol, int &obj)
+{
+    constexpr int W = Cfg::W;
+    viol = base_viol;
+    obj = base_obj;
+    int es[2 * kMaxOps], ev[2 * kMaxOps], ls[2 * kMaxOps], lv[2 * kMaxOps];
+#pragma unroll
+    for (int j = 0; j < 2 * kMaxOps; ++j) { es[j] = -1; ev[j] = 0; ls[j] = -1; lv[j] = 0; }
+#pragma unroll
+    for (int i = 0; i < kMaxOps; ++i) {
+        if (i < ps.n) {
+            const int p = ps.p[i];
+            uint32_t xo[W], xn[W], rem[W], add[W];
+#pragma unroll
+            for (int t = 0; t < W; ++t) {
+                xo[t] = s_bits[(size_t)t * d.Ppad + p];
+                xn[t] = rows[i][t];
+                rem[t] = xo[t] & ~xn[t];
+                add[t] = xn[t] & ~xo[t];
+            }
+            const uint32_t ldo = s_leader[p], ldn = ps.ld[i];
+            int rvo, roo, rvn, ron;
+            row_eval<Cfg, true>(d, objT, p, xo, ldo, rvo, roo);
+            row_eval<Cfg, true>(d, objT, p, xn, ldn, rvn, ron);
+            viol += rvn - rvo;
+            obj += ron - roo;
+            es[2 * i] = lone_slot<W>(rem); ev[2 * i] = -1;
+            es[2 * i + 1] = lone_slot<W>(add); ev[2 * i + 1] = 1;
+            const bool oko = ((int)ldo < W * 32) && row_has<W>(xo, (int)ldo);
+            const bool okn = ((int)ldn < W * 32) && row_has<W>(xn, (int)ldn);
+            ls[2 * i] = oko ? (int)ldo : -1; lv[2 * i] = -1;
+            ls[2 * i + 1] = okn ? (int)ldn : -1; lv[2 * i + 1] = 1;
+        }
+    }
+    viol += apply_events<2 * kMaxOps>(es, ev, [&](int s, int net) {
+        const uint32_t b = cs->bnd_rep[s];
+        return band_violation(cnt[s] + net, b) - band_violation(cnt[s], b);
+    });
+    viol += apply_events<2 * kMaxOps>(ls, lv, [&](int s, int net) {
+        const uint32_t b = cs->bnd_ldr[s];
+        return band_violation(lcnt[s] + net, b) - band_violation(lcnt[s], b);
+    });
+    int rs[2 * kMaxOps];
+#pragma unroll
+    for (int j = 0; j < 2 * kMaxOps; ++j) rs[j] = es[j] < 0 ? -1 : ((es[j] >> d.log2S) < d.R ? (es[j] >> d.log2S) : -1);
+    viol += apply_events<2 * kMaxOps>(rs, ev, [&](int r, int net) {
+        const int lo = cs->rack_lo[r], hi = cs->rack_hi[r], c0 = rc[r], c1 = rc[r] + net;
+        return (max(c1 - hi, 0) + max(lo - c1, 0)) - (max(c0 - hi, 0) + max(lo - c0, 0));
+    });
 }
 
 }  // namespace kao

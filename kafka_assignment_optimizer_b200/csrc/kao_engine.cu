@@ -48,7 +48,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // shared-memory plan of the search kernel
 // ------------------------------------------------------------------------------------------
 struct SmemPlan {
-    uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, off_lists, total;
+    uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, off_lists, off_totals, total;
 };
 static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row)
 {
@@ -63,6 +63,7 @@ static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row)
     s.off_red = o;    o += (uint32_t)warps * 8;
     s.off_bar = o;    o += 16;
     s.off_lists = o;  o += (uint32_t)Ppad * 4 + 16 + 2 * 36 * 4;   // D, DL (u16 each), counts, scan scratch
+    s.off_totals = o; o += (256 + 256 + 32 + 4) * 4;                // delta mode: cnt, lcnt, rc, base (viol, obj)
     s.total = o;
     return s;
 }
@@ -106,6 +107,7 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
     mbar_wait(s_bar, 0);
 
     Gen<W> gen;
+    uint32_t no_rows[kMaxOps][W];          // warp mode keeps patched rows in shared memory instead
     gen.bitsT = s_bits; gen.leader = s_leader; gen.cs = s_cs; gen.d = &d;
     gen.prow = s_prow + warp * kMaxOps * W; gen.lane = lane;
     gen.D = d.D; gen.DL = d.DL; gen.nD = d.nD[0]; gen.nL = d.nD[1];
@@ -123,7 +125,7 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
         ps.n = 0;
 #pragma unroll
         for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
-        if (live) gen.run(seed, round, idx, round_size, ps);
+        if (live) gen.run(seed, round, idx, round_size, ps, no_rows);
 #if KAO_LOCKSTEP
         __syncthreads();
 #else
@@ -218,11 +220,12 @@ apply_winner_kernel(Params d, uint64_t seed, uint32_t round, uint32_t round_size
         const unsigned long long k = *key;
         if (k != kKeyNone) {
             Gen<W> gen;
+            uint32_t no_rows[kMaxOps][W];
             gen.bitsT = d.bitsT; gen.leader = d.leader; gen.cs = d.consts; gen.d = &d;
             gen.prow = s_prow; gen.lane = lane;
             gen.D = d.D; gen.DL = d.DL; gen.nD = d.nD[0]; gen.nL = d.nD[1];
             PatchSet ps;
-            gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps);
+            gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps, no_rows);
             __syncwarp();
             if (lane == 0) {
 #pragma unroll
@@ -274,10 +277,11 @@ __device__ __forceinline__ bool spin_until(const unsigned int *p, unsigned int t
 // re-materialises the winner itself and patches its own shared-memory copy of the base (<= 3
 // rows) — nothing but one 8-byte key crosses the chip per round.  CTA 0 mirrors the patches into
 // the HBM base.
-template <class Cfg, int THREADS>
+template <class Cfg, int THREADS, bool kDelta>
 __global__ void __launch_bounds__(THREADS, 1)
 search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_round, uint32_t rounds,
-                         uint32_t round_size, unsigned long long *keys, unsigned int *grid_bar, P2P pp)
+                         uint32_t round_size, unsigned long long *keys, unsigned int *grid_bar, P2P pp,
+                         unsigned long long *all_keys)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *s_bits = reinterpret_cast<uint32_t *>(smem + plan.off_bits);
@@ -314,6 +318,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
 
     Gen<W> gen;
+    uint32_t no_rows[kMaxOps][W];          // warp mode keeps patched rows in shared memory instead
     gen.bitsT = s_bits; gen.leader = s_leader; gen.cs = s_cs; gen.d = &d;
     gen.prow = s_prow + warp * kMaxOps * W; gen.lane = lane;
     gen.D = s_D; gen.DL = s_DL;
@@ -326,6 +331,60 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         const uint32_t round = first_round + t;
         gen.nD = s_counts[0]; gen.nL = s_counts[1];
         unsigned long long best = kKeyNone;
+        if constexpr (kDelta) {
+            // ---- delta mode: totals of the base once per round, then one THREAD per candidate
+            int *s_cnt = reinterpret_cast<int *>(smem + plan.off_totals), *s_lcnt = s_cnt + 256, *s_rc = s_cnt + 512,
+                *s_base = s_cnt + 544;
+            for (int i = tid; i < 548; i += THREADS) s_cnt[i] = 0;
+            __syncthreads();
+            for (int p = tid; p < d.P; p += THREADS) {
+                const int ld = s_leader[p];
+                bool ok = false;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const uint32_t xw = s_bits[(size_t)w * d.Ppad + p];
+                    for (uint32_t m = xw; m; m &= m - 1) {
+                        const int sl = w * 32 + __ffs(m) - 1;
+                        atomicAdd(&s_cnt[sl], 1);
+                        atomicAdd(&s_rc[sl >> d.log2S], 1);
+                    }
+                    if ((ld >> 5) == w) ok = (xw >> (ld & 31)) & 1u;
+                }
+                if (ok) atomicAdd(&s_lcnt[ld], 1);
+            }
+            if (warp == 0) {
+                PatchSet id;
+                id.n = 0;
+#pragma unroll
+                for (int i = 0; i < kMaxOps; ++i) { id.p[i] = -1; id.ld[i] = 0xFF; }
+                int bv, bo;
+                eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, id, gen.prow, lane, bv, bo);
+                if (lane == 0) { s_base[0] = bv; s_base[1] = bo; }
+            }
+            __syncthreads();
+            Gen<W, true> tg;
+            tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
+            tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
+            const MemRef<true> m_obj(s_sw);
+            const int base_viol = s_base[0], base_obj = s_base[1];
+            const uint32_t tstride = gridDim.x * THREADS;
+            for (uint32_t idx = pp.idx_lo + blockIdx.x * THREADS + tid; idx < pp.idx_hi; idx += tstride) {
+                PatchSet ps;
+                uint32_t rows[kMaxOps][W];
+                tg.run(seed, round, idx, round_size, ps, rows);
+                int viol, obj;
+                delta_eval<Cfg>(d, s_bits, s_leader, m_obj, s_cs, ps, rows, s_cnt, s_lcnt, s_rc, base_viol, base_obj, viol, obj);
+                const unsigned long long key = pack_key(viol, obj, idx);
+                if (all_keys) all_keys[idx - pp.idx_lo] = key;
+                best = key < best ? key : best;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long w = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+                best = w < best ? w : best;
+            }
+            if (all_keys) return;                                   // key dump only: the base stays as it is
+        } else {
         for (uint32_t it = 0; it < iters; ++it) {
             const uint32_t idx = first + warp + it * stride;
             const bool live = idx < pp.idx_hi;
@@ -333,7 +392,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             ps.n = 0;
 #pragma unroll
             for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
-            if (live) gen.run(seed, round, idx, round_size, ps);
+            if (live) gen.run(seed, round, idx, round_size, ps, no_rows);
             __syncthreads();
             if (live) {
                 int viol, obj;
@@ -342,6 +401,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 best = key < best ? key : best;
             }
             __syncwarp();
+        }
         }
         if (lane == 0) s_red[warp] = best;
         __syncthreads();
@@ -394,7 +454,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             const unsigned long long k = __ldcg(keys + t);
             if (k != kKeyNone) {
                 PatchSet ps;
-                gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps);
+                gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps, no_rows);
                 __syncwarp();
                 if (lane == 0) {
 #pragma unroll
@@ -530,6 +590,7 @@ struct RoundArgs {
 struct PersistArgs {
     uint64_t seed; uint32_t first_round, rounds, round_size; unsigned long long *d_keys; unsigned int *d_bar; cudaStream_t st;
     P2P pp;
+    unsigned long long *all_keys;
 };
 
 template <class Cfg> static cudaError_t set_smem_attr(kao_handle *h, const void *kern, bool *done)
@@ -559,23 +620,27 @@ struct LaunchRound {
         return cudaGetLastError();
     }
 };
-struct LaunchPersistent {
+template <bool kDelta> struct LaunchPersistent {
     template <class Cfg> cudaError_t run(kao_handle *h, const PersistArgs &a) const
     {
-        constexpr int T = threads_for<Cfg::W>();
-        auto kern = search_persistent_kernel<Cfg, T>;
-        static bool done[64] = {};
-        cudaError_t e = set_smem_attr<Cfg>(h, reinterpret_cast<const void *>(kern), done);
-        if (e != cudaSuccess) return e;
-        Params prm = h->prm; SmemPlan plan = h->plan;
-        uint64_t seed = a.seed; uint32_t fr = a.first_round, rounds = a.rounds, rs = a.round_size;
-        unsigned long long *keys = a.d_keys; unsigned int *bar = a.d_bar;
-        P2P pp = a.pp;
-        void *args[] = {&prm, &plan, &seed, &fr, &rounds, &rs, &keys, &bar, &pp};
-        ++h->launches;
-        // cooperative launch: all CTAs are guaranteed co-resident, which the grid barrier needs
-        return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(h->grid), dim3(T), args,
-                                           h->plan.total, a.st);
+        if constexpr (kDelta && Cfg::W > 2) {
+            return cudaErrorNotSupported;                       // delta mode: rows of up to 64 slots
+        } else {
+            constexpr int T = kDelta ? 512 : threads_for<Cfg::W>();
+            auto kern = search_persistent_kernel<Cfg, T, kDelta>;
+            static bool done[64] = {};
+            cudaError_t e = set_smem_attr<Cfg>(h, reinterpret_cast<const void *>(kern), done);
+            if (e != cudaSuccess) return e;
+            Params prm = h->prm; SmemPlan plan = h->plan;
+            uint64_t seed = a.seed; uint32_t fr = a.first_round, rounds = a.rounds, rs = a.round_size;
+            unsigned long long *keys = a.d_keys, *all = a.all_keys; unsigned int *bar = a.d_bar;
+            P2P pp = a.pp;
+            void *args[] = {&prm, &plan, &seed, &fr, &rounds, &rs, &keys, &bar, &pp, &all};
+            ++h->launches;
+            // cooperative launch: all CTAs are guaranteed co-resident, which the grid barrier needs
+            return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(h->grid), dim3(T), args,
+                                               h->plan.total, a.st);
+        }
     }
 };
 
@@ -813,10 +878,11 @@ extern "C" int kao_round_apply(kao_handle *h, uint64_t seed, uint32_t round, uin
     return KAO_OK;
 }
 
-extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
-                          uint32_t round_size, uint64_t *round_keys, double *device_ms)
+static int search_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                       uint32_t round_size, uint64_t *round_keys, double *device_ms, bool delta)
 {
     if (!h) return fail(KAO_E_ARG, "null handle");
+    if (delta && h->hm.W > 2) return fail(KAO_E_ARG, "delta evaluation supports rows of up to 64 broker slots");
     if (!check_round_args(round_size)) return fail(KAO_E_ARG, "round_size must be 2..2^24");
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->keys_cap < rounds) {
@@ -837,7 +903,8 @@ extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, ui
         P2P pp{};
         pp.rank = 0; pp.world = 1; pp.idx_lo = 0; pp.idx_hi = round_size;
         pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
-        CUDA_TRY(dispatch(h, LaunchPersistent{}, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0, pp}));
+        CUDA_TRY((delta ? dispatch(h, LaunchPersistent<true>{}, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0, pp, nullptr})
+                       : dispatch(h, LaunchPersistent<false>{}, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0, pp, nullptr})));
         CUDA_TRY(launch_apply(h, seed, first_round, round_size, h->d_keys, /*regen_only=*/1, 0));
     }
     CUDA_TRY(cudaEventRecord(h->ev1, 0));
@@ -853,6 +920,43 @@ extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, ui
 }
 
 // ---- cross-GPU sharded search: the 8-byte min of every round travels through peer-mapped mailboxes
+extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                          uint32_t round_size, uint64_t *round_keys, double *device_ms)
+{
+    return search_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, false);
+}
+
+// Same search, same keys, same trajectory — but every candidate is scored by DELTA evaluation
+// (base totals + its <= 3 patched rows, one thread per candidate) instead of a full evaluation.
+extern "C" int kao_search_delta(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                                uint32_t round_size, uint64_t *round_keys, double *device_ms)
+{
+    return search_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, true);
+}
+
+extern "C" int kao_candidate_keys_delta(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                        uint32_t idx_begin, uint32_t count, uint64_t *keys)
+{
+    if (!h || !keys) return fail(KAO_E_ARG, "null argument");
+    if (!check_round_args(round_size) || idx_begin > round_size || count > round_size - idx_begin)
+        return fail(KAO_E_ARG, "bad index range");
+    if (h->hm.W > 2) return fail(KAO_E_ARG, "delta evaluation supports rows of up to 64 broker slots");
+    if (count == 0) return KAO_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long *d_all = nullptr;
+    CUDA_TRY(cudaMalloc(&d_all, (size_t)count * 8));
+    if (!h->d_bar) CUDA_TRY(dalloc(h, &h->d_bar, 16));
+    CUDA_TRY(cudaMemset(h->d_bar, 0, 16));
+    P2P pp{};
+    pp.rank = 0; pp.world = 1; pp.idx_lo = idx_begin; pp.idx_hi = idx_begin + count;
+    pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
+    cudaError_t e = dispatch(h, LaunchPersistent<true>{}, PersistArgs{seed, round, 1, round_size, h->d_key, h->d_bar, 0, pp, d_all});
+    if (e == cudaSuccess) e = cudaMemcpy(keys, d_all, (size_t)count * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_all);
+    CUDA_TRY(e);
+    return KAO_OK;
+}
+
 extern "C" int kao_p2p_export(kao_handle *h, uint8_t *handle_out)
 {
     if (!h || !handle_out) return fail(KAO_E_ARG, "null argument");
@@ -930,8 +1034,8 @@ extern "C" int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_r
         pp.rank = rank; pp.world = world; pp.bank = bank; pp.idx_lo = lo; pp.idx_hi = hi;
         pp.mail = h->d_mailptrs;
         pp.lkeys = h->d_lkeys; pp.release = h->d_bar + 1; pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
-        CUDA_TRY(dispatch(h, LaunchPersistent{}, PersistArgs{seed, first_round + done, n, round_size,
-                                                             h->d_keys + done, h->d_bar, 0, pp}));
+        CUDA_TRY(dispatch(h, LaunchPersistent<false>{}, PersistArgs{seed, first_round + done, n, round_size,
+                                                                    h->d_keys + done, h->d_bar, 0, pp, nullptr}));
         int aborted = 0;
         CUDA_TRY(cudaMemcpy(&aborted, h->d_bar + 2, 4, cudaMemcpyDeviceToHost));
         if (aborted) return fail(KAO_E_CUDA, "sharded search timed out waiting for a peer GPU");

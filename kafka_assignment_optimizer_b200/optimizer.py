@@ -147,6 +147,21 @@ class Session:
                                     C.c_uint32(round_size), C.c_void_p(keys.ctypes.data), C.byref(ms)))
         return keys[:rounds], ms.value
 
+    def search_delta(self, seed: int, first_round: int, rounds: int, round_size: int):
+        """Same search and keys as `search`, candidates scored by delta evaluation."""
+        keys = np.zeros(max(rounds, 1), np.uint64)
+        ms = C.c_double()
+        _check(self._lib.kao_search_delta(self._h, C.c_uint64(seed), C.c_uint32(first_round), C.c_uint32(rounds),
+                                          C.c_uint32(round_size), C.c_void_p(keys.ctypes.data), C.byref(ms)))
+        return keys[:rounds], ms.value
+
+    def candidate_keys_delta(self, seed: int, rnd: int, round_size: int, idx_begin: int, count: int):
+        keys = np.zeros(max(count, 1), np.uint64)
+        _check(self._lib.kao_candidate_keys_delta(self._h, C.c_uint64(seed), C.c_uint32(rnd), C.c_uint32(round_size),
+                                                  C.c_uint32(idx_begin), C.c_uint32(count),
+                                                  C.c_void_p(keys.ctypes.data)))
+        return keys[:count]
+
     def candidate_keys(self, seed: int, rnd: int, round_size: int, idx_begin: int, count: int):
         keys = np.zeros(max(count, 1), np.uint64)
         _check(self._lib.kao_candidate_keys(self._h, C.c_uint64(seed), C.c_uint32(rnd), C.c_uint32(round_size),

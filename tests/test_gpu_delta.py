@@ -1,0 +1,54 @@
+"""SURVEY.md 8(f)3 — delta evaluation: the key of every candidate, computed from the base's totals
+and the candidate's patched rows (one thread per candidate), must equal the key of the full
+evaluation bit for bit; whole searches must walk the same trajectory."""
+import numpy as np
+import pytest
+
+import kafka_assignment_optimizer_b200 as kao
+from oracle import model as m
+from problems import SHAPES
+
+pytestmark = pytest.mark.gpu
+NARROW = [n for n in sorted(SHAPES) if n not in ("w4_s16", "w8_s16")]     # rows of up to 64 slots
+
+
+@pytest.mark.parametrize("name", NARROW)
+def test_delta_keys_equal_full_keys(ref_lib, name):
+    pb = SHAPES[name]()
+    r = ref_lib.Ref(pb)
+    sess = kao.Session(kao.Problem.from_fields(pb))
+    bits, ld = r.init_base()
+    for rnd, size, lo, n in [(0, 2048, 0, 2048), (7, 4096, 4096 - 900, 900)]:
+        full = sess.candidate_keys(0xD17A, rnd, size, lo, n)
+        delta = sess.candidate_keys_delta(0xD17A, rnd, size, lo, n)
+        want = r.candidate_keys(bits, ld, 0xD17A, rnd, size, lo, n)
+        bad = np.flatnonzero(delta != full)
+        assert bad.size == 0, "idx %d: delta %s full %s" % (lo + bad[0], kao.unpack_key(delta[bad[0]]),
+                                                           kao.unpack_key(full[bad[0]]))
+        assert (delta == want).all()
+    # after some rounds the base is no longer the initial one: compare again
+    sess.search(5, 0, 6, 1024)
+    full = sess.candidate_keys(9, 3, 1024, 0, 1024)
+    assert (sess.candidate_keys_delta(9, 3, 1024, 0, 1024) == full).all()
+    sess.close()
+
+
+@pytest.mark.parametrize("name", ["cfg2_rm2", "cfg3_small", "s32", "dense_unique", "rf_up"])
+def test_delta_search_walks_the_same_trajectory(ref_lib, name):
+    pb = SHAPES[name]()
+    r = ref_lib.Ref(pb)
+    bits, ld = r.init_base()
+    _, want = r.search(bits, ld, 0x1234, 0, 12, 2000)
+    sess = kao.Session(kao.Problem.from_fields(pb))
+    got, _ = sess.search_delta(0x1234, 0, 12, 2000)
+    assert (got == want).all()
+    reps, v, o, _ = sess.get_base()
+    assert (reps == r.decode(bits, ld)).all() and (v, o) == m.evaluate(pb, reps)
+    sess.close()
+
+
+def test_delta_rejects_wide_rows():
+    sess = kao.Session(kao.Problem.from_fields(SHAPES["w8_s16"]()))
+    with pytest.raises(kao.KaoError, match="64 broker slots"):
+        sess.search_delta(1, 0, 1, 64)
+    sess.close()
