@@ -24,4 +24,26 @@ SHAPES = {
     "dense_unique": lambda: m.with_random_tiebreak(m.synthetic_problem(20, 12, 4, 3, 1), 0),
     "dense_unique2": lambda: m.with_random_tiebreak(m.synthetic_problem(12, 9, 3, 2, 1), 1),
     "tiny": lambda: make_problem(3, [2, 2], 2, seed=8),
+    # edge cases: ragged current assignment (1..4 replicas per partition, some entirely on removed
+    # brokers), RF 1, a single partition, the largest row count, every one of the 256 slots in use
+    "ragged": lambda: ragged_problem(),
+    "rf1": lambda: make_problem(40, [3, 3, 3], 1, seed=9, removed=1),
+    "one_partition": lambda: make_problem(1, [2, 2, 2], 3, seed=10),
+    "max_rows": lambda: m.synthetic_problem(8160, 16, 4, 2, remove=1),
+    "all_slots": lambda: m.synthetic_problem(64, 256, 16, 3),
 }
+
+
+def ragged_problem():
+    import numpy as np
+
+    rng = np.random.RandomState(12)
+    B0, removed = 14, 3
+    current = []
+    for p in range(60):
+        k = 1 + p % 4
+        current.append(list(map(int, rng.choice(B0, size=k, replace=False))))
+    current[5] = [12, 13]                 # every replica on a broker that leaves the cluster
+    current[6] = [11]
+    racks = {b: "az%d" % (b % 3) for b in range(B0)}
+    return m.build_problem(current, list(range(B0 - removed)), racks, 3)

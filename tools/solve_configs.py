@@ -29,6 +29,7 @@ def main():
         if len(over) > 2:
             rounds = int(over[2])
         seed = int(over[3], 0) if len(over) > 3 else 0x5EED
+        delta = len(over) > 4 and over[4] == "delta"
         pb = kao.synthetic_problem(*args)
         sess = kao.Session(pb)
         t0 = time.perf_counter()
@@ -37,7 +38,7 @@ def main():
         chunk = max(100, rounds // 20)
         dev_ms = 0.0
         while done < rounds:
-            keys, ms = sess.search(seed, done, chunk, size)
+            keys, ms = (sess.search_delta if delta else sess.search)(seed, done, chunk, size)
             dev_ms += ms
             for i, k in enumerate(keys):
                 v, o, _ = kao.unpack_key(k)
@@ -48,7 +49,7 @@ def main():
             done += chunk
         reps, viol, obj, moves = sess.get_base()
         e = opt.get(name, {})
-        print(json.dumps({"config": name, "args": args, "round_size": size, "rounds": rounds, "seed": seed,
+        print(json.dumps({"config": name, "args": args, "round_size": size, "rounds": rounds, "seed": seed, "mode": "delta" if delta else "full",
                           "candidates": rounds * size, "violation": viol, "objective": obj, "moves": moves,
                           "exact_objective": e.get("objective"), "exact_moves": e.get("moves"),
                           "first_feasible_round": first_feasible, "last_improving_round": best_round,
