@@ -73,8 +73,12 @@ typedef struct kao_options {
     uint32_t round_size;      /* candidates per round, 2 .. KAO_MAX_ROUND_SIZE */
     int32_t device;           /* CUDA device ordinal */
     uint32_t flags;           /* bits 0-7: independent restarts (0 or 1 = one search); the best final
-                                 assignment of rounds*round_size candidates each is returned */
+                                 assignment of rounds*round_size candidates each is returned.
+                                 KAO_FLAG_DELTA: score candidates by delta evaluation (same keys and
+                                 trajectory, several times more candidates per second) */
 } kao_options;
+
+#define KAO_FLAG_DELTA 0x100u
 
 typedef struct kao_result {
     int32_t *replicas;        /* [P*RF] caller-allocated; leader first, then followers by

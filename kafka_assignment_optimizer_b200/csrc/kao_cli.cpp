@@ -258,7 +258,7 @@ int usage()
 {
     std::fprintf(stderr,
                  "usage: kao-cli --assignment FILE|- --brokers 0,1,2 --racks 0:a,1:b,2:a [--rf N]\n"
-                 "               [--rounds 256] [--round-size 32768] [--restarts 1] [--seed 24301] [--device 0] [--emit-lp] [--stats]\n");
+                 "               [--rounds 256] [--round-size 32768] [--restarts 1] [--seed 24301] [--device 0] [--delta] [--emit-lp] [--stats]\n");
     return 2;
 }
 
@@ -267,11 +267,12 @@ int usage()
 int main(int argc, char **argv)
 {
     std::map<std::string, std::string> a;
-    bool emit = false, stats = false;
+    bool emit = false, stats = false, delta = false;
     for (int i = 1; i < argc; ++i) {
         std::string k = argv[i];
         if (k == "--emit-lp") { emit = true; continue; }
         if (k == "--stats") { stats = true; continue; }
+        if (k == "--delta") { delta = true; continue; }
         if (k.rfind("--", 0) != 0 || i + 1 >= argc) return usage();
         a[k.substr(2)] = argv[++i];
     }
@@ -315,6 +316,7 @@ int main(int argc, char **argv)
         opt.round_size = a.count("round-size") ? (uint32_t)std::atoi(a["round-size"].c_str()) : 32768;
         opt.device = a.count("device") ? std::atoi(a["device"].c_str()) : 0;
         opt.flags = a.count("restarts") ? (uint32_t)std::min(255, std::max(1, std::atoi(a["restarts"].c_str()))) : 1u;
+        if (delta) opt.flags |= KAO_FLAG_DELTA;
         std::vector<int32_t> reps((size_t)m.P * m.RF, -1);
         kao_result res{};
         res.replicas = reps.data();

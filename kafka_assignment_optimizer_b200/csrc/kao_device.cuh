@@ -144,6 +144,10 @@ template <int W, bool kThread = false> struct Gen {
     int lane;
     const uint16_t *D, *DL;  // displaced / leader-displaced partitions of the base (global or shared)
     int nD, nL;
+    // thread mode only: per-slot inverted lists of the base (ascending partitions), or inv_ok = false
+    bool inv_ok = false;
+    const int *hoff = nullptr, *loff = nullptr;     // [slots + 1] offsets into hold / led
+    const uint16_t *hold = nullptr, *led = nullptr; // partitions holding a replica on / led from the slot
 
     __device__ __forceinline__ void read_row(int p, uint32_t (&row)[W], uint32_t &ld) const
     {
@@ -213,6 +217,28 @@ template <int W, bool kThread = false> struct Gen {
         const uint32_t *col = bitsT + (size_t)(src >> 5) * d->Ppad;
         const uint32_t bit = 1u << (src & 31);
         if constexpr (kThread) {
+            if (inv_ok) {
+                // sorted list of the partitions that can match: lower_bound(p0), then walk cyclically
+                const uint16_t *L = (KIND == 1) ? led + loff[src] : hold + hoff[src];
+                const int n = (KIND == 1) ? loff[src + 1] - loff[src] : hoff[src + 1] - hoff[src];
+                int lo = 0, hi = n;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((int)L[mid] < p0) lo = mid + 1; else hi = mid;
+                }
+                for (int k = 0; k < n; ++k) {
+                    int j = lo + k;
+                    if (j >= n) j -= n;
+                    const int q = L[j];
+                    bool t = false;
+#pragma unroll
+                    for (int i = 0; i < kMaxOps; ++i) t |= (ps.p[i] == q);
+                    if (t) continue;
+                    if (KIND == 2 && (int)leader[q] == src) continue;
+                    return q;
+                }
+                return -1;
+            }
             int q = p0;
             for (int k = 0; k < P; ++k) {
                 bool t = false;

@@ -48,9 +48,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // shared-memory plan of the search kernel
 // ------------------------------------------------------------------------------------------
 struct SmemPlan {
-    uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, off_lists, off_totals, total;
+    uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, off_lists, off_totals, off_inv, total;
+    uint32_t cap_hold, cap_led;      // delta mode: capacity of the inverted lists (0 = not staged)
 };
-static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row)
+static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int P, int RF)
 {
     SmemPlan s;
     uint32_t o = 0;
@@ -63,7 +64,14 @@ static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row)
     s.off_red = o;    o += (uint32_t)warps * 8;
     s.off_bar = o;    o += 16;
     s.off_lists = o;  o += (uint32_t)Ppad * 4 + 16 + 2 * 36 * 4;   // D, DL (u16 each), counts, scan scratch
-    s.off_totals = o; o += (256 + 256 + 32 + 4) * 4;                // delta mode: cnt, lcnt, rc, base (viol, obj)
+    s.off_totals = o; o += (256 + 256 + 32 + 4 + 256 + 2 * 66 + 4) * 4;   // delta mode: cnt, lcnt, rc, base (viol, obj),
+                                                                           // led counts, list offsets, flag
+    s.off_inv = o;
+    s.cap_hold = s.cap_led = 0;
+    if (W <= 2) {   // inverted lists (u16 partitions) if they fit next to everything else
+        const uint32_t need = ((uint32_t)P * RF + 64 + (uint32_t)P + 8) * 2;
+        if (o + need <= 227u * 1024u) { s.cap_hold = (uint32_t)P * RF + 64; s.cap_led = (uint32_t)P; o += (need + 15u) & ~15u; }
+    }
     s.total = o;
     return s;
 }
@@ -335,7 +343,9 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             // ---- delta mode: totals of the base once per round, then one THREAD per candidate
             int *s_cnt = reinterpret_cast<int *>(smem + plan.off_totals), *s_lcnt = s_cnt + 256, *s_rc = s_cnt + 512,
                 *s_base = s_cnt + 544;
-            for (int i = tid; i < 548; i += THREADS) s_cnt[i] = 0;
+            int *s_ledn = s_cnt + 548, *s_hoff = s_cnt + 804, *s_loff = s_cnt + 870, *s_inv = s_cnt + 936;
+            uint16_t *s_hold = reinterpret_cast<uint16_t *>(smem + plan.off_inv), *s_led = s_hold + plan.cap_hold;
+            for (int i = tid; i < 804; i += THREADS) if (i < 544 || i >= 548) s_cnt[i] = 0;   // keep s_base
             __syncthreads();
             for (int p = tid; p < d.P; p += THREADS) {
                 const int ld = s_leader[p];
@@ -351,8 +361,29 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                     if ((ld >> 5) == w) ok = (xw >> (ld & 31)) & 1u;
                 }
                 if (ok) atomicAdd(&s_lcnt[ld], 1);
+                atomicAdd(&s_ledn[ld], 1);
             }
-            if (warp == 0) {
+            __syncthreads();
+            // per-slot inverted lists of the base (ascending partitions) for the per-thread generator
+            if (tid == 0) {
+                int a = 0, b = 0;
+                for (int sl = 0; sl < W * 32; ++sl) { s_hoff[sl] = a; a += s_cnt[sl]; s_loff[sl] = b; b += s_ledn[sl]; }
+                s_hoff[W * 32] = a; s_loff[W * 32] = b;
+                *s_inv = (plan.cap_hold > 0 && a <= (int)plan.cap_hold && b <= (int)plan.cap_led) ? 1 : 0;
+            }
+            __syncthreads();
+            if (*s_inv && tid < W * 32) {
+                int hpos = s_hoff[tid], lpos = s_loff[tid];
+                const uint32_t *col = s_bits + (size_t)(tid >> 5) * d.Ppad;
+                const uint32_t bit = 1u << (tid & 31);
+                for (int p = 0; p < d.P; ++p) {
+                    if (col[p] & bit) s_hold[hpos++] = (uint16_t)p;
+                    if ((int)s_leader[p] == tid) s_led[lpos++] = (uint16_t)p;
+                }
+            }
+            // the base's own evaluation: a full pass in the first round, afterwards it IS the previous
+            // winner's key (unless that key was saturated)
+            if (warp == 0 && (t == 0 || s_base[2] == 0)) {
                 PatchSet id;
                 id.n = 0;
 #pragma unroll
@@ -365,6 +396,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             Gen<W, true> tg;
             tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
             tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
+            tg.inv_ok = *s_inv != 0; tg.hoff = s_hoff; tg.loff = s_loff; tg.hold = s_hold; tg.led = s_led;
             const MemRef<true> m_obj(s_sw);
             const int base_viol = s_base[0], base_obj = s_base[1];
             const uint32_t tstride = gridDim.x * THREADS;
@@ -452,6 +484,13 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         // the winner becomes the base: every CTA patches its own shared-memory copy
         if (warp == 0) {
             const unsigned long long k = __ldcg(keys + t);
+            if (kDelta && lane == 0) {
+                int *s_base = reinterpret_cast<int *>(smem + plan.off_totals) + 544;
+                const uint32_t kv = (uint32_t)(k >> 48);
+                s_base[2] = (k != kKeyNone && kv < kViolCap) ? 1 : 0;
+                s_base[0] = (int)kv;
+                s_base[1] = (int)(kObjCap - (uint32_t)((k >> kIdxBits) & kObjCap));
+            }
             if (k != kKeyNone) {
                 PatchSet ps;
                 gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps, no_rows);
@@ -734,7 +773,7 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     const HostModel &m = h->hm;
     const int W = m.W, Ppad = m.Ppad;
     h->threads = W <= 2 ? KAO_THREADS : 256;
-    h->plan = make_plan(W, Ppad, h->threads / 32, m.nplanes > 0 ? m.nplanes * W : 4);
+    h->plan = make_plan(W, Ppad, h->threads / 32, m.nplanes > 0 ? m.nplanes * W : 4, m.P, m.RF);
     if (h->plan.total > 227u * 1024u)
         return fail(KAO_E_ARG, "problem too large for the shared-memory resident search kernel");
     h->grid = h->sms;
@@ -1173,7 +1212,9 @@ extern "C" int kao_solve(const kao_problem *pb, const kao_options *opt, kao_resu
         int64_t viol = 0, obj = 0;
         int32_t moves = 0;
         if (r) rc = kao_reset(h);
-        if (rc == KAO_OK) rc = kao_search(h, opt->seed + 0x9E3779B97F4A7C15ull * r, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms);
+        if (rc == KAO_OK)
+            rc = search_impl(h, opt->seed + 0x9E3779B97F4A7C15ull * r, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms,
+                             (opt->flags & KAO_FLAG_DELTA) != 0);
         if (rc == KAO_OK) rc = kao_get_base(h, reps.data(), &viol, &obj, &moves);
         if (rc != KAO_OK) break;
         dev_ms_total += dev_ms;

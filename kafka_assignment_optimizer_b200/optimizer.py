@@ -225,12 +225,12 @@ class Session:
 
 
 def solve(pb: Problem, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15,
-          device: int = 0, require_feasible: bool = False, restarts: int = 1) -> SolveResult:
+          device: int = 0, require_feasible: bool = False, restarts: int = 1, delta: bool = False) -> SolveResult:
     """One blocking kao_solve from host buffers (tables up, winner down)."""
     lib = load_library()
     cp = _CProblem(pb)
     reps = np.full((pb.P, pb.RF), -1, np.int32)
-    opt = _KaoOptions(seed, rounds, round_size, device, max(1, min(255, restarts)))
+    opt = _KaoOptions(seed, rounds, round_size, device, max(1, min(255, restarts)) | (0x100 if delta else 0))
     res = _KaoResult()
     res.replicas = reps.ctypes.data
     rc = _check(lib.kao_solve(cp.ref(), C.byref(opt), C.byref(res)), allow_infeasible=not require_feasible)
