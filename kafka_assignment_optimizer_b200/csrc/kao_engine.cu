@@ -69,8 +69,12 @@ static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int
     s.off_inv = o;
     s.cap_hold = s.cap_led = 0;
     if (W <= 2) {   // inverted lists (u16 partitions) if they fit next to everything else
-        const uint32_t need = ((uint32_t)P * RF + 64 + (uint32_t)P + 8) * 2;
-        if (o + need <= 227u * 1024u) { s.cap_hold = (uint32_t)P * RF + 64; s.cap_led = (uint32_t)P; o += (need + 15u) & ~15u; }
+        const uint32_t need = ((uint32_t)P * RF + 66 + (uint32_t)P + 2 + 8) * 2 + 2 * 512 * 4 + 16;   // + segment counts
+        if (o + need <= 227u * 1024u) {
+            s.cap_hold = ((uint32_t)P * RF + 64 + 1) & ~1u;     // even counts keep the int scratch behind them aligned
+            s.cap_led = ((uint32_t)P + 1) & ~1u;
+            o += (need + 15u) & ~15u;
+        }
     }
     s.total = o;
     return s;
@@ -372,13 +376,27 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 *s_inv = (plan.cap_hold > 0 && a <= (int)plan.cap_hold && b <= (int)plan.cap_led) ? 1 : 0;
             }
             __syncthreads();
-            if (*s_inv && tid < W * 32) {
-                int hpos = s_hoff[tid], lpos = s_loff[tid];
-                const uint32_t *col = s_bits + (size_t)(tid >> 5) * d.Ppad;
-                const uint32_t bit = 1u << (tid & 31);
-                for (int p = 0; p < d.P; ++p) {
+            if (*s_inv) {
+                // THREADS / slots segments of rows per slot: count, then write in place (ascending order)
+                constexpr int NSL = W * 32, NSEG = THREADS / NSL;
+                int *s_segc = reinterpret_cast<int *>(s_led + plan.cap_led + 8);       // [2][NSEG][NSL]
+                const int slot = tid % NSL, seg = tid / NSL;
+                const int chunk = (d.P + NSEG - 1) / NSEG, p_lo = seg * chunk, p_hi = min(d.P, p_lo + chunk);
+                const uint32_t *col = s_bits + (size_t)(slot >> 5) * d.Ppad;
+                const uint32_t bit = 1u << (slot & 31);
+                int hc = 0, lc = 0;
+                for (int p = p_lo; p < p_hi; ++p) {
+                    hc += (col[p] & bit) ? 1 : 0;
+                    lc += ((int)s_leader[p] == slot) ? 1 : 0;
+                }
+                s_segc[seg * NSL + slot] = hc;
+                s_segc[(NSEG + seg) * NSL + slot] = lc;
+                __syncthreads();
+                int hpos = s_hoff[slot], lpos = s_loff[slot];
+                for (int g = 0; g < seg; ++g) { hpos += s_segc[g * NSL + slot]; lpos += s_segc[(NSEG + g) * NSL + slot]; }
+                for (int p = p_lo; p < p_hi; ++p) {
                     if (col[p] & bit) s_hold[hpos++] = (uint16_t)p;
-                    if ((int)s_leader[p] == tid) s_led[lpos++] = (uint16_t)p;
+                    if ((int)s_leader[p] == slot) s_led[lpos++] = (uint16_t)p;
                 }
             }
             // the base's own evaluation: a full pass in the first round, afterwards it IS the previous
