@@ -30,3 +30,17 @@ def test_cli_solves_the_readme_example(tmp_path):
     pb = m.readme_problem()
     reps = [[int(b) for b in rows[i]] for i in range(10)]
     assert m.evaluate(pb, __import__("numpy").array(reps)) == (0, 58)
+
+
+def test_python_operator_surface_json_in_json_out():
+    """AssignmentOptimizer mirrors the reference's surface: --generate JSON + broker list + rack map
+    in, --reassignment-json-file JSON out (README.md:52-63 -> :67-78)."""
+    import kafka_assignment_optimizer_b200 as kao
+
+    racks = ",".join("%d:%s" % (b, "b" if b % 2 else "a") for b in range(20))
+    opt = kao.AssignmentOptimizer(rounds=16, round_size=2048)
+    doc, res = opt.optimize(README_CURRENT, ",".join(map(str, range(19))), racks)
+    assert res.feasible and res.objective == 58 and res.moves == 1
+    assert doc["version"] == 1 and [e["partition"] for e in doc["partitions"]] == list(range(10))
+    assert doc["partitions"][1]["replicas"][0] == 8 and 19 not in doc["partitions"][1]["replicas"]
+    assert all(e["topic"] == "x.y.z.t" for e in doc["partitions"])
