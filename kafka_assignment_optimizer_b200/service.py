@@ -1,0 +1,78 @@
+"""Minimal HTTP façade: POST /submit, JSON in, reassignment JSON out.
+
+The reference only names its hosted endpoint (`/root/reference/README.md:187-194`,
+"API endpoint: …/submit"); the request schema is not in the snapshot, so this one is ours:
+
+    POST /submit  {"assignment": {"version":1,"partitions":[...]},      README.md:52-63
+                   "brokers": "0,1,2,...",                               README.md:48
+                   "racks": "0:a,1:b,...",                               README.md:27-29
+                   "rf": 2, "rounds": 256, "round_size": 32768, "delta": false}
+    200           {"reassignment": {"version":1,"partitions":[...]},    README.md:67-78
+                   "objective": ..., "violation": ..., "moves": ..., "feasible": ...}
+
+`python -m kafka_assignment_optimizer_b200.service --port 8080` (needs a GPU: there is no CPU path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+from typing import Callable, Optional
+
+from .problem import build_problem, parse_assignment_json, parse_broker_list, parse_rack_map, reassignment_json
+
+
+def handle_submit(body: dict, solver: Optional[Callable] = None) -> dict:
+    """Pure request -> response function (the HTTP layer only moves bytes)."""
+    rows, topics = parse_assignment_json(body["assignment"])
+    brokers = body["brokers"]
+    brokers = parse_broker_list(brokers) if isinstance(brokers, str) else [int(b) for b in brokers]
+    racks = body["racks"]
+    racks = parse_rack_map(racks) if isinstance(racks, str) else {int(k): str(v) for k, v in racks.items()}
+    rf = int(body.get("rf") or max(len(r) for r in rows))
+    pb = build_problem(rows, brokers, racks, rf, topics)
+    if solver is None:
+        from .optimizer import solve as solver
+    res = solver(pb, seed=int(body.get("seed", 0x5EED)), rounds=int(body.get("rounds", 256)),
+                 round_size=int(body.get("round_size", 1 << 15)), restarts=int(body.get("restarts", 1)),
+                 delta=bool(body.get("delta", False)))
+    return {"reassignment": reassignment_json(pb, res.replicas), "objective": int(res.objective),
+            "violation": int(res.violation), "moves": int(res.moves), "feasible": bool(res.feasible)}
+
+
+class _Handler(BaseHTTPRequestHandler):
+    solver = None
+
+    def do_POST(self):  # noqa: N802
+        if self.path.rstrip("/") != "/submit":
+            self.send_error(404)
+            return
+        try:
+            body = json.loads(self.rfile.read(int(self.headers.get("Content-Length", "0"))))
+            out, code = handle_submit(body, self.solver), 200
+        except (KeyError, ValueError, TypeError) as e:
+            out, code = {"error": "bad request: %s" % e}, 400
+        except RuntimeError as e:            # KaoError: no GPU, CUDA failure
+            out, code = {"error": str(e)}, 503
+        data = json.dumps(out).encode()
+        self.send_response(code)
+        self.send_header("Content-Type", "application/json")
+        self.send_header("Content-Length", str(len(data)))
+        self.end_headers()
+        self.wfile.write(data)
+
+    def log_message(self, fmt, *args):  # quiet
+        pass
+
+
+def make_server(host: str = "127.0.0.1", port: int = 8080, solver: Optional[Callable] = None):
+    handler = type("Handler", (_Handler,), {"solver": staticmethod(solver) if solver else None})
+    return ThreadingHTTPServer((host, port), handler)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--host", default="127.0.0.1")
+    ap.add_argument("--port", type=int, default=8080)
+    a = ap.parse_args()
+    make_server(a.host, a.port).serve_forever()

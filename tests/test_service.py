@@ -1,0 +1,40 @@
+"""The /submit façade on CPU: the HTTP layer and the request->response mapping
+are exercised with a stand-in solver (the exact oracle), since solving needs a GPU."""
+import json
+import threading
+import urllib.request
+
+import numpy as np
+
+from kafka_assignment_optimizer_b200 import service
+from kafka_assignment_optimizer_b200.optimizer import SolveResult
+from oracle import model as m
+from test_host import README_CURRENT
+
+
+def oracle_solver(pb, **kw):
+    sol = m.solve_exact(m.Problem(**{f: getattr(pb, f) for f in m.Problem.__dataclass_fields__}))
+    return SolveResult(sol.replicas, sol.objective, 0, sol.moves, True, 0, 0, 0, 0.0, 0.0)
+
+
+def test_submit_round_trip_over_http():
+    srv = service.make_server(port=0, solver=oracle_solver)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    try:
+        body = {"assignment": json.loads(README_CURRENT), "brokers": ",".join(map(str, range(19))),
+                "racks": ",".join("%d:%s" % (b, "b" if b % 2 else "a") for b in range(20)), "rf": 2}
+        req = urllib.request.Request("http://127.0.0.1:%d/submit" % srv.server_address[1],
+                                     data=json.dumps(body).encode(), headers={"Content-Type": "application/json"})
+        out = json.loads(urllib.request.urlopen(req, timeout=60).read())
+        assert out["feasible"] and out["objective"] == 58 and out["moves"] == 1
+        parts = out["reassignment"]["partitions"]
+        assert parts[0] == {"topic": "x.y.z.t", "partition": 0, "replicas": [7, 18]}
+        assert parts[1]["replicas"][0] == 8 and 19 not in parts[1]["replicas"]
+        bad = urllib.request.Request("http://127.0.0.1:%d/submit" % srv.server_address[1], data=b"{}")
+        try:
+            urllib.request.urlopen(bad, timeout=10)
+            assert False
+        except urllib.error.HTTPError as e:
+            assert e.code == 400
+    finally:
+        srv.shutdown()

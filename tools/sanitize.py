@@ -16,6 +16,10 @@ for args in [(64, 16, 4, 3, 1), (300, 64, 8, 3, 2)]:
     s.candidate_keys(1, 0, 256, 0, 256)
     keys, _ = s.search(1, 0, 3, 512)
     s.profile_rounds(1, 3, 2, 512)
+    if s.stats()["words_per_row"] <= 2:
+        dk = s.candidate_keys_delta(1, 9, 256, 0, 256)
+        assert (dk == s.candidate_keys(1, 9, 256, 0, 256)).all()
+        s.search_delta(1, 5, 3, 512)
     reps, v, o, mv = s.get_base()
     vv, oo = kopt.evaluate(pb, reps)
     assert (int(vv[0]), int(oo[0])) == (v, o)
