@@ -46,10 +46,18 @@ _lib = None
 
 
 def load_library():
-    """Loads libkao.so from the package directory.  Raises KaoError if it has not been built
-    (``python -c 'import __graft_entry__ as g; g.build()'`` or ``make -C .../csrc``)."""
+    """Loads libkao.so from the package directory; if it has not been built yet (fresh checkout) it
+    is compiled once with the in-tree Makefile (nvcc, sm_100a).  Raises KaoError when neither works:
+    there is no CPU fallback."""
     global _lib
     if _lib is None:
+        if not os.path.exists(_LIB_PATH) and not os.environ.get("KAO_LIB"):
+            import subprocess
+
+            csrc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+            r = subprocess.run(["make", "-s", "-C", csrc], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode != 0:
+                raise KaoError("libkao.so is not built and building it failed (no CPU fallback):\n" + r.stdout[-2000:])
         if not os.path.exists(_LIB_PATH):
             raise KaoError("libkao.so is not built (%s); there is no CPU fallback" % _LIB_PATH)
         lib = C.CDLL(_LIB_PATH)
