@@ -83,27 +83,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_rate(seconds_target=12.0):
+def cpu_port_rate(seconds_target=10.0):
     """The oracle restatement (plain C + OpenMP, all host cores) on a bounded sample of the same
-    workload: the candidates of round 0 of the same stream, evaluated in full."""
+    workload: whole rounds of the same candidate stream, every candidate evaluated in full, until
+    about `seconds_target` seconds of CPU work have been spent."""
     from oracle import model, ref
 
     pb = model.synthetic_problem(P, B, R, RF)
     r = ref.Ref(pb)
     bits, ld = r.init_base()
     threads = ref.Ref.max_threads()
-    n = 1 << 16
-    t0 = time.perf_counter()
-    r.candidate_keys(bits, ld, SEED, 0, ROUND_SIZE, 0, n)
-    dt = time.perf_counter() - t0
-    total, spent = n, dt
-    n = int(min(ROUND_SIZE - 1, max(n, n * (seconds_target - dt) / max(dt, 1e-3))))
-    if n > 0 and dt < seconds_target:
+    n = ROUND_SIZE - 1
+    r.candidate_keys(bits, ld, SEED, 0, ROUND_SIZE, 0, 1 << 14)          # warm-up
+    total, spent, rnd = 0, 0.0, 0
+    while spent < seconds_target and rnd < 64:
         t0 = time.perf_counter()
-        r.candidate_keys(bits, ld, SEED, 0, ROUND_SIZE, 0, n)
-        dt2 = time.perf_counter() - t0
-        total, spent = n, dt2
-    return total / spent, threads, "%d candidates of round 0 (same Philox stream, full evaluation), %.1f s" % (total, spent)
+        r.candidate_keys(bits, ld, SEED, rnd, ROUND_SIZE, 0, n)
+        spent += time.perf_counter() - t0
+        total += n
+        rnd += 1
+    return total / spent, threads, "%d candidates (%d rounds of the same Philox stream, full evaluation), %.1f s" % (
+        total, rnd, spent)
 
 
 def reference_arm(args):
@@ -116,7 +116,7 @@ def reference_arm(args):
     r = ref.Ref(pb)
     bits, ld = r.init_base()
     threads = ref.Ref.max_threads()
-    sample = 1 << 19                                        # candidates per step (bounded sample)
+    sample = 1 << 20                                        # candidates per step (bounded sample, ~2 s)
     for w in range(args.warmup):
         r.candidate_keys(bits, ld, SEED, w, ROUND_SIZE, 0, 1 << 14)
     t0 = time.perf_counter()

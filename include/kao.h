@@ -161,6 +161,9 @@ int kao_p2p_export(kao_handle *h, uint8_t *handle_out /* [KAO_IPC_HANDLE_BYTES] 
 int kao_p2p_connect(kao_handle *h, int32_t rank, int32_t world, const uint8_t *handles /* [world][64] */);
 int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
                        uint32_t round_size, uint64_t *round_keys, double *device_ms);
+/* the same with delta evaluation (see kao_search_delta) */
+int kao_search_sharded_delta(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                             uint32_t round_size, uint64_t *round_keys, double *device_ms);
 
 /* introspection for benchmarks: kernel launches issued by this handle so far, words per row */
 int kao_stats(kao_handle *h, uint64_t *kernel_launches, int32_t *words_per_row,

@@ -1053,10 +1053,11 @@ extern "C" int kao_p2p_connect(kao_handle *h, int32_t rank, int32_t world, const
     return KAO_OK;
 }
 
-extern "C" int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
-                                  uint32_t round_size, uint64_t *round_keys, double *device_ms)
+static int sharded_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                        uint32_t round_size, uint64_t *round_keys, double *device_ms, bool delta)
 {
     if (!h) return fail(KAO_E_ARG, "null handle");
+    if (delta && h->hm.W > 2) return fail(KAO_E_ARG, "delta evaluation supports rows of up to 64 broker slots");
     if (!check_round_args(round_size)) return fail(KAO_E_ARG, "round_size must be 2..2^24");
     if (h->p2p_world < 2 || !h->peer_mail[h->p2p_world - 1]) return fail(KAO_E_STATE, "kao_p2p_connect first");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -1091,8 +1092,8 @@ extern "C" int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_r
         pp.rank = rank; pp.world = world; pp.bank = bank; pp.idx_lo = lo; pp.idx_hi = hi;
         pp.mail = h->d_mailptrs;
         pp.lkeys = h->d_lkeys; pp.release = h->d_bar + 1; pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
-        CUDA_TRY(dispatch(h, LaunchPersistent<false>{}, PersistArgs{seed, first_round + done, n, round_size,
-                                                                    h->d_keys + done, h->d_bar, 0, pp, nullptr}));
+        const PersistArgs pa{seed, first_round + done, n, round_size, h->d_keys + done, h->d_bar, 0, pp, nullptr};
+        CUDA_TRY(delta ? dispatch(h, LaunchPersistent<true>{}, pa) : dispatch(h, LaunchPersistent<false>{}, pa));
         int aborted = 0;
         CUDA_TRY(cudaMemcpy(&aborted, h->d_bar + 2, 4, cudaMemcpyDeviceToHost));
         if (aborted) return fail(KAO_E_CUDA, "sharded search timed out waiting for a peer GPU");
@@ -1108,6 +1109,17 @@ extern "C" int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_r
     if (round_keys && rounds)
         CUDA_TRY(cudaMemcpy(round_keys, h->d_keys, (size_t)rounds * 8, cudaMemcpyDeviceToHost));
     return KAO_OK;
+}
+
+extern "C" int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                                  uint32_t round_size, uint64_t *round_keys, double *device_ms)
+{
+    return sharded_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, false);
+}
+extern "C" int kao_search_sharded_delta(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                                        uint32_t round_size, uint64_t *round_keys, double *device_ms)
+{
+    return sharded_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, true);
 }
 
 extern "C" int kao_profile_rounds(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,

@@ -210,11 +210,12 @@ class Session:
         dist.all_gather(got, mine)
         self.p2p_connect(rank, world, [bytes(t.cpu().tolist()) for t in got])
 
-    def search_sharded(self, seed: int, first_round: int, rounds: int, round_size: int):
+    def search_sharded(self, seed: int, first_round: int, rounds: int, round_size: int, delta: bool = False):
         """Every rank calls this with identical arguments -> (per-round keys, device ms)."""
         keys = np.zeros(max(rounds, 1), np.uint64)
         ms = C.c_double()
-        _check(self._lib.kao_search_sharded(self._h, C.c_uint64(seed), C.c_uint32(first_round), C.c_uint32(rounds),
+        fn = self._lib.kao_search_sharded_delta if delta else self._lib.kao_search_sharded
+        _check(fn(self._h, C.c_uint64(seed), C.c_uint32(first_round), C.c_uint32(rounds),
                                             C.c_uint32(round_size), C.c_void_p(keys.ctypes.data), C.byref(ms)))
         return keys[:rounds], ms.value
 

@@ -29,7 +29,7 @@ def _worker(rank, world, port, q):
     sess = kao.Session(pb, device=rank)
     sess.p2p_setup_torch(torch.device("cuda", rank))
     keys_a, _ = sess.search_sharded(seed, 0, rounds, size)
-    keys_a2, _ = sess.search_sharded(seed, rounds, 5, size)          # second call: other mailbox bank
+    keys_a2, _ = sess.search_sharded(seed, rounds, 5, size, delta=True)   # second call: other mailbox bank, delta scoring
     base_a = sess.get_base()[0]
     sess.close()
     # (b) per-round kernels + NCCL min all-reduce
