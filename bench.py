@@ -83,6 +83,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1: not what we want here)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_port_rate(seconds_target=10.0):
     """The oracle restatement (plain C + OpenMP, all host cores) on a bounded sample of the same
     workload: whole rounds of the same candidate stream, every candidate evaluated in full, until
@@ -92,13 +100,13 @@ def cpu_port_rate(seconds_target=10.0):
     pb = model.synthetic_problem(P, B, R, RF)
     r = ref.Ref(pb)
     bits, ld = r.init_base()
-    threads = ref.Ref.max_threads()
+    threads = host_threads()
     n = ROUND_SIZE - 1
-    r.candidate_keys(bits, ld, SEED, 0, ROUND_SIZE, 0, 1 << 14)          # warm-up
+    r.candidate_keys(bits, ld, SEED, 0, ROUND_SIZE, 0, 1 << 14, nthreads=threads)          # warm-up
     total, spent, rnd = 0, 0.0, 0
     while spent < seconds_target and rnd < 64:
         t0 = time.perf_counter()
-        r.candidate_keys(bits, ld, SEED, rnd, ROUND_SIZE, 0, n)
+        r.candidate_keys(bits, ld, SEED, rnd, ROUND_SIZE, 0, n, nthreads=threads)
         spent += time.perf_counter() - t0
         total += n
         rnd += 1
@@ -115,13 +123,13 @@ def reference_arm(args):
     pb = model.synthetic_problem(P, B, R, RF)
     r = ref.Ref(pb)
     bits, ld = r.init_base()
-    threads = ref.Ref.max_threads()
+    threads = host_threads()
     sample = 1 << 20                                        # candidates per step (bounded sample, ~2 s)
     for w in range(args.warmup):
-        r.candidate_keys(bits, ld, SEED, w, ROUND_SIZE, 0, 1 << 14)
+        r.candidate_keys(bits, ld, SEED, w, ROUND_SIZE, 0, 1 << 14, nthreads=threads)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        r.candidate_keys(bits, ld, SEED, k, ROUND_SIZE, 0, min(sample, ROUND_SIZE - 1))
+        r.candidate_keys(bits, ld, SEED, k, ROUND_SIZE, 0, min(sample, ROUND_SIZE - 1), nthreads=threads)
     dt = time.perf_counter() - t0
     n = args.steps * min(sample, ROUND_SIZE - 1)
     val = n / dt
@@ -274,7 +282,7 @@ def main():
                "api": "kao_solve (pinned host buffers; create+upload+search+download+destroy per step), 1 GPU",
                "last_result": {"violation": int(res.violation), "objective": int(res.objective), "moves": int(res.moves)}}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:         # reported at N=1 only
             v, threads, sample = cpu_port_rate()
             cpu = {"value": v, "unit": "candidates/s", "cores": threads, "kind": "port", "sample": sample,
                    "note": "lp_solve (the reference's solver) is not installed here and cannot be timed; "
