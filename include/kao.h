@@ -75,10 +75,12 @@ typedef struct kao_options {
     uint32_t flags;           /* bits 0-7: independent restarts (0 or 1 = one search); the best final
                                  assignment of rounds*round_size candidates each is returned.
                                  KAO_FLAG_DELTA: score candidates by delta evaluation (same keys and
-                                 trajectory, several times more candidates per second) */
+                                 trajectory, several times more candidates per second).
+                                 KAO_FLAG_PATIENCE(n): early stop; rounds_run / n_candidates report what ran */
 } kao_options;
 
 #define KAO_FLAG_DELTA 0x100u
+#define KAO_FLAG_PATIENCE(n) ((uint32_t)(n) << 16)  /* stop a search after n (<= 65535) rounds without a better key */
 
 typedef struct kao_result {
     int32_t *replicas;        /* [P*RF] caller-allocated; leader first, then followers by
@@ -89,7 +91,7 @@ typedef struct kao_result {
     int32_t feasible;
     uint64_t key;             /* packed (violation, cost, index) of the last winning candidate */
     uint64_t n_candidates;    /* candidates generated and fully evaluated */
-    uint32_t rounds_run;
+    uint32_t rounds_run;      /* rounds actually run, summed over restarts */
     uint32_t reserved;        /* restarts performed */
     double device_ms;         /* CUDA-event time of the search kernels */
     double total_ms;          /* wall time of the call incl. host<->device copies */
@@ -132,6 +134,12 @@ int kao_search_delta(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_
                      uint32_t round_size, uint64_t *round_keys, double *device_ms);
 int kao_candidate_keys_delta(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
                              uint32_t idx_begin, uint32_t count, uint64_t *keys);
+
+/* early stop for every later search on this handle: leave after `n` rounds without a better
+ * (violation, objective); 0 = run all rounds.  The decision depends only on the round keys, so all
+ * ranks of a sharded search stop together.  kao_last_rounds: rounds the last search actually ran. */
+int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
+int kao_last_rounds(kao_handle *h, uint32_t *rounds_run);
 
 /* keys of candidates idx_begin .. idx_begin+count-1 of `round` against the current base (host
  * buffer) — the per-candidate parity vector. */

@@ -258,7 +258,7 @@ int usage()
 {
     std::fprintf(stderr,
                  "usage: kao-cli --assignment FILE|- --brokers 0,1,2 --racks 0:a,1:b,2:a [--rf N]\n"
-                 "               [--rounds 256] [--round-size 32768] [--restarts 1] [--seed 24301] [--device 0] [--delta] [--emit-lp] [--stats]\n");
+                 "               [--rounds 256] [--round-size 32768] [--restarts 1] [--seed 24301] [--device 0] [--delta] [--patience N] [--emit-lp] [--stats]\n");
     return 2;
 }
 
@@ -317,6 +317,7 @@ int main(int argc, char **argv)
         opt.device = a.count("device") ? std::atoi(a["device"].c_str()) : 0;
         opt.flags = a.count("restarts") ? (uint32_t)std::min(255, std::max(1, std::atoi(a["restarts"].c_str()))) : 1u;
         if (delta) opt.flags |= KAO_FLAG_DELTA;
+        if (a.count("patience")) opt.flags |= KAO_FLAG_PATIENCE(std::min(65535, std::max(0, std::atoi(a["patience"].c_str()))));
         std::vector<int32_t> reps((size_t)m.P * m.RF, -1);
         kao_result res{};
         res.replicas = reps.data();

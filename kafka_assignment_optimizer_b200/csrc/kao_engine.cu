@@ -271,6 +271,8 @@ struct P2P {
     unsigned long long *lkeys;                  // [rounds] this GPU's own minimum per round
     unsigned int *release;                      // CTA 0 publishes "round t is decided" here
     int *abort;                                 // set when a wait times out (a peer died): everybody leaves
+    uint32_t patience;                          // > 0: stop after this many rounds without a better key
+    unsigned int *rounds_run;                   // CTA 0 reports the number of rounds actually run
 };
 
 __device__ __forceinline__ bool spin_until(const unsigned int *p, unsigned int target, int *abort_flag)
@@ -339,6 +341,10 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     const uint32_t first = pp.idx_lo + blockIdx.x * kWarps;
     const uint32_t iters = first < pp.idx_hi ? (pp.idx_hi - first + stride - 1) / stride : 0;
     if (tid == 0) s_abort = 0;
+    int &s_stop = *reinterpret_cast<int *>(smem + plan.off_bar + 12);
+    if (tid == 0) s_stop = 0;
+    unsigned long long best_seen = kKeyNone;       // warp 0 / lane 0 only: best (violation, cost) so far
+    uint32_t stall = 0;
     for (uint32_t t = 0; t < rounds; ++t) {
         const uint32_t round = first_round + t;
         gen.nD = s_counts[0]; gen.nL = s_counts[1];
@@ -502,6 +508,13 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         // the winner becomes the base: every CTA patches its own shared-memory copy
         if (warp == 0) {
             const unsigned long long k = __ldcg(keys + t);
+            if (lane == 0) {
+                // early stop (same decision in every CTA and on every rank: it only depends on the keys)
+                const unsigned long long vc = k >> kIdxBits;
+                if (vc < best_seen) { best_seen = vc; stall = 0; } else ++stall;
+                if (pp.patience && stall >= pp.patience) s_stop = 1;
+                if (blockIdx.x == 0 && pp.rounds_run) *pp.rounds_run = t + 1;
+            }
             if (kDelta && lane == 0) {
                 int *s_base = reinterpret_cast<int *>(smem + plan.off_totals) + 544;
                 const uint32_t kv = (uint32_t)(k >> 48);
@@ -531,6 +544,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         }
         __syncthreads();
         rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
+        if (s_stop) break;
     }
 }
 
@@ -623,6 +637,7 @@ struct kao_handle {
     bool peer_opened[kMaxPeers] = {};
     int p2p_rank = 0, p2p_world = 1;
     uint64_t p2p_calls = 0;
+    uint32_t patience = 0, last_rounds = 0;
     unsigned long long *d_lkeys = nullptr; size_t lkeys_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
@@ -960,6 +975,7 @@ static int search_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint3
         P2P pp{};
         pp.rank = 0; pp.world = 1; pp.idx_lo = 0; pp.idx_hi = round_size;
         pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
+        pp.patience = h->patience; pp.rounds_run = h->d_bar + 3;
         CUDA_TRY((delta ? dispatch(h, LaunchPersistent<true>{}, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0, pp, nullptr})
                        : dispatch(h, LaunchPersistent<false>{}, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0, pp, nullptr})));
         CUDA_TRY(launch_apply(h, seed, first_round, round_size, h->d_keys, /*regen_only=*/1, 0));
@@ -971,12 +987,31 @@ static int search_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint3
         CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         *device_ms = ms;
     }
+    h->last_rounds = 0;
+    if (rounds) {
+        unsigned int st[4] = {0, 0, 0, 0};
+        CUDA_TRY(cudaMemcpy(st, h->d_bar, 16, cudaMemcpyDeviceToHost));
+        if (st[2]) return fail(KAO_E_CUDA, "search kernel timed out at a grid barrier");
+        h->last_rounds = st[3];
+    }
     if (round_keys && rounds)
         CUDA_TRY(cudaMemcpy(round_keys, h->d_keys, (size_t)rounds * 8, cudaMemcpyDeviceToHost));
     return KAO_OK;
 }
 
-// ---- cross-GPU sharded search: the 8-byte min of every round travels through peer-mapped mailboxes
+extern "C" int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    h->patience = rounds_without_improvement;
+    return KAO_OK;
+}
+extern "C" int kao_last_rounds(kao_handle *h, uint32_t *rounds_run)
+{
+    if (!h || !rounds_run) return fail(KAO_E_ARG, "null argument");
+    *rounds_run = h->last_rounds;
+    return KAO_OK;
+}
+
 extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
                           uint32_t round_size, uint64_t *round_keys, double *device_ms)
 {
@@ -1014,6 +1049,7 @@ extern "C" int kao_candidate_keys_delta(kao_handle *h, uint64_t seed, uint32_t r
     return KAO_OK;
 }
 
+// ---- cross-GPU sharded search: the 8-byte min of every round travels through peer-mapped mailboxes
 extern "C" int kao_p2p_export(kao_handle *h, uint8_t *handle_out)
 {
     if (!h || !handle_out) return fail(KAO_E_ARG, "null argument");
@@ -1092,11 +1128,14 @@ static int sharded_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint
         pp.rank = rank; pp.world = world; pp.bank = bank; pp.idx_lo = lo; pp.idx_hi = hi;
         pp.mail = h->d_mailptrs;
         pp.lkeys = h->d_lkeys; pp.release = h->d_bar + 1; pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
+        pp.patience = h->patience; pp.rounds_run = h->d_bar + 3;
         const PersistArgs pa{seed, first_round + done, n, round_size, h->d_keys + done, h->d_bar, 0, pp, nullptr};
         CUDA_TRY(delta ? dispatch(h, LaunchPersistent<true>{}, pa) : dispatch(h, LaunchPersistent<false>{}, pa));
-        int aborted = 0;
-        CUDA_TRY(cudaMemcpy(&aborted, h->d_bar + 2, 4, cudaMemcpyDeviceToHost));
-        if (aborted) return fail(KAO_E_CUDA, "sharded search timed out waiting for a peer GPU");
+        unsigned int st[4] = {0, 0, 0, 0};
+        CUDA_TRY(cudaMemcpy(st, h->d_bar, 16, cudaMemcpyDeviceToHost));
+        if (st[2]) return fail(KAO_E_CUDA, "sharded search timed out waiting for a peer GPU");
+        h->last_rounds = done + st[3];
+        if (st[3] < n) break;                                   // early stop (every rank stops at the same round)
     }
     if (rounds) CUDA_TRY(launch_apply(h, seed, first_round, round_size, h->d_keys, /*regen_only=*/1, 0));
     CUDA_TRY(cudaEventRecord(h->ev1, 0));
@@ -1233,6 +1272,8 @@ extern "C" int kao_solve(const kao_problem *pb, const kao_options *opt, kao_resu
     // independent restarts (flags & 0xFF, 0 and 1 both mean a single search): each restarts from the
     // initial base with its own seed; the best final assignment wins (violation, then objective)
     const uint32_t restarts = (opt->flags & 0xFFu) ? (opt->flags & 0xFFu) : 1u;
+    h->patience = opt->flags >> 16;                             // KAO_FLAG_PATIENCE(n)
+    uint32_t rounds_run = 0;
     std::vector<uint64_t> keys(opt->rounds ? opt->rounds : 1, kKeyNone);
     std::vector<int32_t> reps((size_t)pb->P * pb->RF);
     double dev_ms_total = 0;
@@ -1248,17 +1289,18 @@ extern "C" int kao_solve(const kao_problem *pb, const kao_options *opt, kao_resu
         if (rc == KAO_OK) rc = kao_get_base(h, reps.data(), &viol, &obj, &moves);
         if (rc != KAO_OK) break;
         dev_ms_total += dev_ms;
+        rounds_run += h->last_rounds;
         if (!have || viol < res->violation || (viol == res->violation && obj > res->objective)) {
             std::memcpy(res->replicas, reps.data(), reps.size() * 4);
             res->violation = viol; res->objective = obj; res->moves = moves;
-            res->key = opt->rounds ? keys[opt->rounds - 1] : kKeyNone;
+            res->key = h->last_rounds ? keys[h->last_rounds - 1] : kKeyNone;
             have = true;
         }
     }
     if (rc == KAO_OK) {
         res->feasible = res->violation == 0;
-        res->n_candidates = (uint64_t)restarts * opt->rounds * opt->round_size;
-        res->rounds_run = opt->rounds;
+        res->n_candidates = (uint64_t)rounds_run * opt->round_size;
+        res->rounds_run = rounds_run;
         res->reserved = restarts;
         res->device_ms = dev_ms_total;
     }

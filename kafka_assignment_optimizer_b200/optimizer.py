@@ -132,6 +132,14 @@ class Session:
         except Exception:
             pass
 
+    def set_patience(self, rounds_without_improvement: int):
+        _check(self._lib.kao_set_patience(self._h, C.c_uint32(rounds_without_improvement)))
+
+    def last_rounds(self) -> int:
+        n = C.c_uint32()
+        _check(self._lib.kao_last_rounds(self._h, C.byref(n)))
+        return n.value
+
     def reset(self):
         _check(self._lib.kao_reset(self._h))
 
@@ -234,12 +242,13 @@ class Session:
 
 
 def solve(pb: Problem, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15,
-          device: int = 0, require_feasible: bool = False, restarts: int = 1, delta: bool = False) -> SolveResult:
+          device: int = 0, require_feasible: bool = False, restarts: int = 1, delta: bool = False,
+          patience: int = 0) -> SolveResult:
     """One blocking kao_solve from host buffers (tables up, winner down)."""
     lib = load_library()
     cp = _CProblem(pb)
     reps = np.full((pb.P, pb.RF), -1, np.int32)
-    opt = _KaoOptions(seed, rounds, round_size, device, max(1, min(255, restarts)) | (0x100 if delta else 0))
+    opt = _KaoOptions(seed, rounds, round_size, device, max(1, min(255, restarts)) | (0x100 if delta else 0) | (max(0, min(65535, patience)) << 16))
     res = _KaoResult()
     res.replicas = reps.ctypes.data
     rc = _check(lib.kao_solve(cp.ref(), C.byref(opt), C.byref(res)), allow_infeasible=not require_feasible)

@@ -35,7 +35,7 @@ def handle_submit(body: dict, solver: Optional[Callable] = None) -> dict:
         from .optimizer import solve as solver
     res = solver(pb, seed=int(body.get("seed", 0x5EED)), rounds=int(body.get("rounds", 256)),
                  round_size=int(body.get("round_size", 1 << 15)), restarts=int(body.get("restarts", 1)),
-                 delta=bool(body.get("delta", False)))
+                 delta=bool(body.get("delta", False)), patience=int(body.get("patience", 0)))
     return {"reassignment": reassignment_json(pb, res.replicas), "objective": int(res.objective),
             "violation": int(res.violation), "moves": int(res.moves), "feasible": bool(res.feasible)}
 

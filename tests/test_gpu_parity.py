@@ -199,6 +199,25 @@ def test_restarts_keep_the_best_assignment(golden_optima):
     assert m.evaluate(m.synthetic_problem(*e["args"]), four.replicas) == (four.violation, four.objective)
 
 
+def test_patience_stops_early_with_the_same_answer(golden_optima):
+    """Early stop: the trajectory up to the stop equals the full one, and the answer on config 3 is
+    still the exact optimum, found in a fraction of the rounds."""
+    e = golden_optima["cfg3"]
+    pb = product(m.synthetic_problem(*e["args"]))
+    sess = kao.Session(pb)
+    full, _ = sess.search(0x5EED, 0, 400, 1 << 14)
+    sess.reset()
+    sess.set_patience(60)
+    part, _ = sess.search(0x5EED, 0, 400, 1 << 14)
+    n = sess.last_rounds()
+    assert 60 < n < 400 and (part[:n] == full[:n]).all() and (part[n:] == kopt.KEY_NONE).all()
+    assert kao.unpack_key(part[n - 1])[:2] == (0, e["objective"])
+    assert sess.get_base()[2] == e["objective"]
+    sess.close()
+    res = kopt.solve(pb, seed=0x5EED, rounds=400, round_size=1 << 14, patience=60)
+    assert res.objective == e["objective"] and res.rounds == n and res.n_candidates == n << 14
+
+
 def test_abi_rejects_bad_input():
     pb = product(SHAPES["tiny"]())
     with pytest.raises(kao.KaoError):
