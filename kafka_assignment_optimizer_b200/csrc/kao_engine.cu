@@ -646,7 +646,10 @@ struct kao_handle {
 #ifndef KAO_THREADS
 #define KAO_THREADS 768
 #endif
-template <int W> static constexpr int threads_for() { return W <= 2 ? KAO_THREADS : 256; }
+#ifndef KAO_THREADS_WIDE
+#define KAO_THREADS_WIDE 256
+#endif
+template <int W> static constexpr int threads_for() { return W <= 2 ? KAO_THREADS : KAO_THREADS_WIDE; }
 
 template <class T> static cudaError_t dalloc(kao_handle *h, T **p, size_t bytes)
 {
@@ -805,7 +808,7 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     }
     const HostModel &m = h->hm;
     const int W = m.W, Ppad = m.Ppad;
-    h->threads = W <= 2 ? KAO_THREADS : 256;
+    h->threads = W <= 2 ? KAO_THREADS : KAO_THREADS_WIDE;
     h->plan = make_plan(W, Ppad, h->threads / 32, m.nplanes > 0 ? m.nplanes * W : 4, m.P, m.RF);
     if (h->plan.total > 227u * 1024u)
         return fail(KAO_E_ARG, "problem too large for the shared-memory resident search kernel");

@@ -23,6 +23,8 @@ SHAPES = {
     # weights scaled + seeded random per-cell preference
     "dense_unique": lambda: m.with_random_tiebreak(m.synthetic_problem(20, 12, 4, 3, 1), 0),
     "dense_unique2": lambda: m.with_random_tiebreak(m.synthetic_problem(12, 9, 3, 2, 1), 1),
+    "dense_unique3": lambda: m.with_random_tiebreak(m.synthetic_problem(12, 9, 3, 2, 1), 0),
+    "dense_unique4": lambda: m.with_random_tiebreak(m.synthetic_problem(20, 12, 4, 3, 1), 2),
     "tiny": lambda: make_problem(3, [2, 2], 2, seed=8),
     # edge cases: ragged current assignment (1..4 replicas per partition, some entirely on removed
     # brokers), RF 1, a single partition, the largest row count, every one of the 256 slots in use

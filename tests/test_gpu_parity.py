@@ -118,7 +118,7 @@ def test_readme_vector_through_the_abi():
     assert doc["partitions"][1]["replicas"][0] == 8 and doc["partitions"][0]["replicas"] == [7, 18]
 
 
-@pytest.mark.parametrize("name", ["dense_unique", "dense_unique2", "readme_tb"])
+@pytest.mark.parametrize("name", ["dense_unique", "dense_unique2", "dense_unique3", "dense_unique4", "readme_tb"])
 def test_unique_optimum_bit_exact_winner(name):
     """T2: on instances whose optimum is unique the winner equals the exact solver's, bit for bit."""
     pb = SHAPES[name]()
