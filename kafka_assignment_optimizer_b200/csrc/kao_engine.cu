@@ -61,7 +61,7 @@ static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int
     s.off_consts = o; o += (uint32_t)sizeof(Consts);
     s.off_prow = o;   o += (uint32_t)warps * kMaxOps * W * 4;
     o = (o + 15u) & ~15u;
-    s.off_red = o;    o += (uint32_t)warps * 8;
+    s.off_red = o;    o += (uint32_t)(warps + 4) * 8;      // + early-stop state behind the per-warp minima
     s.off_bar = o;    o += 16;
     s.off_lists = o;  o += (uint32_t)Ppad * 4 + 16 + 2 * 36 * 4;   // D, DL (u16 each), counts, scan scratch
     s.off_totals = o; o += (256 + 256 + 32 + 4 + 256 + 2 * 66 + 4) * 4;   // delta mode: cnt, lcnt, rc, base (viol, obj),
@@ -341,10 +341,9 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     const uint32_t first = pp.idx_lo + blockIdx.x * kWarps;
     const uint32_t iters = first < pp.idx_hi ? (pp.idx_hi - first + stride - 1) / stride : 0;
     if (tid == 0) s_abort = 0;
-    int &s_stop = *reinterpret_cast<int *>(smem + plan.off_bar + 12);
-    if (tid == 0) s_stop = 0;
-    unsigned long long best_seen = kKeyNone;       // warp 0 / lane 0 only: best (violation, cost) so far
-    uint32_t stall = 0;
+    // early-stop state lives behind the per-warp minima (s_red is live anyway; a separate pointer would
+    // cost a register in the hot loop): [kWarps] stop flag, [kWarps+1] best (violation, cost), [kWarps+2] stall
+    if (tid == 0) { s_red[kWarps] = 0; s_red[kWarps + 1] = kKeyNone; s_red[kWarps + 2] = 0; }
     for (uint32_t t = 0; t < rounds; ++t) {
         const uint32_t round = first_round + t;
         gen.nD = s_counts[0]; gen.nL = s_counts[1];
@@ -508,13 +507,15 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         // the winner becomes the base: every CTA patches its own shared-memory copy
         if (warp == 0) {
             const unsigned long long k = __ldcg(keys + t);
+#if !defined(KAO_NO_PATIENCE)
             if (lane == 0) {
                 // early stop (same decision in every CTA and on every rank: it only depends on the keys)
                 const unsigned long long vc = k >> kIdxBits;
-                if (vc < best_seen) { best_seen = vc; stall = 0; } else ++stall;
-                if (pp.patience && stall >= pp.patience) s_stop = 1;
+                if (vc < s_red[kWarps + 1]) { s_red[kWarps + 1] = vc; s_red[kWarps + 2] = 0; } else ++s_red[kWarps + 2];
+                if (pp.patience && s_red[kWarps + 2] >= pp.patience) s_red[kWarps] = 1;
                 if (blockIdx.x == 0 && pp.rounds_run) *pp.rounds_run = t + 1;
             }
+#endif
             if (kDelta && lane == 0) {
                 int *s_base = reinterpret_cast<int *>(smem + plan.off_totals) + 544;
                 const uint32_t kv = (uint32_t)(k >> 48);
@@ -544,7 +545,9 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         }
         __syncthreads();
         rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
-        if (s_stop) break;
+#if !defined(KAO_NO_PATIENCE)
+        if (s_red[kWarps]) break;
+#endif
     }
 }
 
