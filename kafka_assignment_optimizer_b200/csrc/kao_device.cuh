@@ -508,11 +508,15 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int i)
 //   general bounds: SWAR field counts and saturating field-wise subtraction.
 // The slot layout makes a rack an aligned field of S = 8 / 16 slots or 1..8 whole words.
 // ------------------------------------------------------------------------------------------
-template <int W, bool kHi1>
-__device__ __forceinline__ int row_rack_terms(const uint32_t (&x)[W], int log2S, int R, int lo, int hi, int RF)
+// kRack: 0 = general bounds, field width read at run time; 3 / 4 / 5 = the kHi1 form with 8-slot,
+// 16-slot or whole-word rack fields fixed at compile time (no per-row dispatch on the layout).
+template <int W, int kRack>
+__device__ __forceinline__ int row_rack_terms(const uint32_t (&x)[W], int log2S_rt, int R, int lo, int hi, int RF)
 {
+    constexpr bool kHi1 = kRack != 0;
+    const int log2S = (kRack == 3 || kRack == 4) ? kRack : log2S_rt;
     int n = 0, pen = 0;
-    if (log2S == 3) {
+    if (kRack != 5 && log2S == 3) {
 #pragma unroll
         for (int t = 0; t < W; ++t) {
             const int pc = __popc(x[t]);
@@ -534,7 +538,7 @@ __device__ __forceinline__ int row_rack_terms(const uint32_t (&x)[W], int log2S,
                 }
             }
         }
-    } else if (log2S == 4) {
+    } else if (kRack != 5 && log2S == 4) {
 #pragma unroll
         for (int t = 0; t < W; ++t) {
             const int pc = __popc(x[t]);
@@ -558,7 +562,8 @@ __device__ __forceinline__ int row_rack_terms(const uint32_t (&x)[W], int log2S,
             }
         }
     } else {
-        const int wpr = 1 << (log2S - 5);
+        const int lw = (log2S_rt > 5 ? log2S_rt : 5) - 5;     // log2(words per rack); this branch is dead for kRack 3 / 4
+        const int wpr = 1 << lw;
         int c = 0;
 #pragma unroll
         for (int t = 0; t < W; ++t) {
@@ -566,7 +571,7 @@ __device__ __forceinline__ int row_rack_terms(const uint32_t (&x)[W], int log2S,
             n += pc;
             c += pc;
             if (((t + 1) & (wpr - 1)) == 0) {
-                if ((t >> (log2S - 5)) < R) pen += max(c - hi, 0) + max(lo - c, 0);
+                if ((t >> lw) < R) pen += max(c - hi, 0) + max(lo - c, 0);
                 c = 0;
             }
         }
@@ -596,7 +601,7 @@ __device__ __forceinline__ void load_planes(uint32_t (&pl)[kPlanes], const ColCo
 template <int NI, int NP0>
 __device__ __forceinline__ int column_violation(uint32_t (&pl)[NI][kPlanes], int lane, int nA,
                                                 const uint32_t *bndA, const uint32_t *bndB,
-                                                bool racks, int log2S, int R, const Consts *cs)
+                                                bool racks, int lead_mode, int log2S, int R, const Consts *cs)
 {
     static_assert(NP0 + 5 <= kPlanes, "plane budget");
     int item = 0;
@@ -656,6 +661,10 @@ __device__ __forceinline__ int column_violation(uint32_t (&pl)[NI][kPlanes], int
         viol += max((int)c - hi, 0) + max(lo - (int)c, 0);
         csum += (int)c;
     }
+    // C2/C5: a partition whose leader slot is one of its replicas shows up exactly once in the
+    // leader columns, so (#partitions - sum of leader counts) is the number of invalid leaders; the
+    // caller adds P once.  lead_mode 1: items >= nA are leader words, 2: all items are.
+    if (lead_mode == 2 || (lead_mode == 1 && second)) viol -= csum;
     if (racks) {
         // C6: replica columns summed per rack; leader items and padding racks form ignored groups
         const int rk = (word * 32 + t0) >> log2S;
@@ -677,22 +686,33 @@ constexpr int kObjEntries = 0;   // kObj > 0: that many weighted mask planes (3 
                                  // the first 2*kObj/3 apply to the row, the last kObj/3 to the leader one-hot
 constexpr int kMaxWPlanes = 6;
 
-template <int W_, int NPH_, bool kHi1_, int kObj_> struct EvalCfg {
-    static constexpr int W = W_, NPH = NPH_, kObj = kObj_;
-    static constexpr bool kHi1 = kHi1_;
+template <int W_, int NPH_, int kRack_, int kObj_> struct EvalCfg {
+    static constexpr int W = W_, NPH = NPH_, kObj = kObj_, kRack = kRack_;
 };
+// The search kernels keep a leader one-hot plane [W][Ppad] right behind the shared-memory bit-plane
+// for narrow rows scored with mask planes (the leader bytes are then not read by the evaluator).
+template <class Cfg> __host__ __device__ constexpr bool has_oh_plane() { return Cfg::W <= 2 && Cfg::kObj > 0; }
+
 
 // Loads one 128-row tile of the candidate: 4 consecutive rows per lane (128-bit shared-memory
 // loads, conflict-free), with the candidate's row patches substituted (rare, warp-uniform test).
-template <int W, bool kShared>
+// kOh: the base's leader one-hot plane (row & 1 << leader, kept next to the bit-plane by the search
+// kernels) is loaded instead of the leader bytes; a patched row's one-hot is rebuilt here.
+template <int W, bool kShared, bool kOh>
 __device__ __forceinline__ void load_tile(const MemRef<kShared> &bitsT, const MemRef<kShared> &leader, int Ppad,
                                           const PatchSet &ps, const uint32_t *prow, int lane, int u,
-                                          uint4 (&xv)[W], uint32_t &ld4)
+                                          uint4 (&xv)[W], uint4 (&ohv)[W], uint32_t &ld4)
 {
     const int r0 = u * kTileRows + lane * kRowsPerLane;
 #pragma unroll
     for (int t = 0; t < W; ++t) xv[t] = bitsT.ld128((uint32_t)(t * Ppad + r0) * 4u);
-    ld4 = leader.ld32((uint32_t)r0);
+    if constexpr (kOh) {
+#pragma unroll
+        for (int t = 0; t < W; ++t) ohv[t] = bitsT.ld128((uint32_t)((W + t) * Ppad + r0) * 4u);
+        ld4 = 0;
+    } else {
+        ld4 = leader.ld32((uint32_t)r0);
+    }
     if (((ps.p[0] >> 7) == u) | ((ps.p[1] >> 7) == u) | ((ps.p[2] >> 7) == u)) {
 #pragma unroll
         for (int i = 0; i < kMaxOps; ++i) {
@@ -704,8 +724,13 @@ __device__ __forceinline__ void load_tile(const MemRef<kShared> &bitsT, const Me
                     const uint32_t v = prow[i * W + t];
                     if (rr == 0) xv[t].x = v; else if (rr == 1) xv[t].y = v;
                     else if (rr == 2) xv[t].z = v; else xv[t].w = v;
+                    if constexpr (kOh) {
+                        const uint32_t o = ((int)(ps.ld[i] >> 5) == t) ? (v & (1u << (ps.ld[i] & 31u))) : 0u;
+                        if (rr == 0) ohv[t].x = o; else if (rr == 1) ohv[t].y = o;
+                        else if (rr == 2) ohv[t].z = o; else ohv[t].w = o;
+                    }
                 }
-                ld4 = (ld4 & ~(0xFFu << (8 * rr))) | (ps.ld[i] << (8 * rr));
+                if constexpr (!kOh) ld4 = (ld4 & ~(0xFFu << (8 * rr))) | (ps.ld[i] << (8 * rr));
             }
         }
     }
@@ -715,10 +740,10 @@ __device__ __forceinline__ void load_tile(const MemRef<kShared> &bitsT, const Me
 //   part A  per row: C1 / C7 terms, leader validity (C2/C5), leader-bonus planes; per tile: the
 //           carry-save column counters of replicas (C3, C6) and leaders (C4)
 //   part B  per row: the follower-weight part of the objective
-template <class Cfg, bool kShared, bool kCheckValid>
+template <class Cfg, bool kShared, bool kCheckValid, bool kOh>
 __device__ __forceinline__ void tile_pass_a(const Params &d, const MemRef<kShared> &objT,
                                             int lane, int u, int &viol, int &obj,
-                                            const uint4 (&xv)[Cfg::W], uint32_t ld4,
+                                            const uint4 (&xv)[Cfg::W], const uint4 (&ohv)[Cfg::W], uint32_t ld4,
                                             uint32_t (&x)[kRowsPerLane][Cfg::W], uint32_t (&oh)[kRowsPerLane][Cfg::W])
 {
     constexpr int W = Cfg::W;
@@ -727,25 +752,26 @@ __device__ __forceinline__ void tile_pass_a(const Params &d, const MemRef<kShare
     for (int i = 0; i < kRowsPerLane; ++i) {
 #pragma unroll
         for (int t = 0; t < W; ++t) x[i][t] = comp(xv[t], i);
-        const uint32_t ld = (ld4 >> (8 * i)) & 0xFFu;
-        // leader one-hot restricted to the row: C2/C5 hold by construction of the encoding
-        uint32_t any = 0;
-        if constexpr (W == 2) {
+        const uint32_t ld = __byte_perm(ld4, 0u, 0x4440u + i);   // byte i of the four leader slots
+        // leader one-hot restricted to the row (empty when the leader slot is not a replica: that
+        // partition is then missing from the leader columns, which is how C2/C5 are charged)
+        if constexpr (kOh) {
+#pragma unroll
+            for (int t = 0; t < W; ++t) oh[i][t] = comp(ohv[t], i);
+        } else if constexpr (W == 2) {
             unsigned long long ob;                               // 1 << ld; PTX shl clamps: ld >= 64 gives 0
             asm("shl.b64 %0, %1, %2;" : "=l"(ob) : "l"(1ull), "r"(ld));
             oh[i][0] = x[i][0] & (uint32_t)ob;
             oh[i][1] = x[i][1] & (uint32_t)(ob >> 32);
-            any = oh[i][0] | oh[i][1];
         } else {
             const uint32_t ldbit = __funnelshift_l(0u, 1u, ld);  // 1 << (ld & 31)
 #pragma unroll
             for (int t = 0; t < W; ++t) {
                 const uint32_t lm = ((int)(ld >> 5) == t) ? ldbit : 0u;  // mask first: no indexed row access
                 oh[i][t] = x[i][t] & lm;
-                any |= oh[i][t];
             }
         }
-        int rv = row_rack_terms<W, Cfg::kHi1>(x[i], d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF) + (any ? 0 : 1);
+        int rv = row_rack_terms<W, Cfg::kRack>(x[i], d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF);
         if constexpr (kCheckValid) rv = ((r0 + i) < d.P) ? rv : 0;
         viol += rv;
     }
@@ -829,7 +855,7 @@ __device__ __forceinline__ void tile_pass_b(const Params &d, const MemRef<kShare
 
 // Two tiles (8 rows per lane) = one carry-save block.  Ppad is a multiple of 256, so the second
 // tile of the last pair exists in memory even when it holds no real row.
-template <class Cfg, bool kShared, bool kChk>
+template <class Cfg, bool kShared, bool kChk, bool kOh>
 __device__ __forceinline__ void eval_pair(const Params &d, const MemRef<kShared> &m_bits,
                                           const MemRef<kShared> &m_leader, const MemRef<kShared> &m_obj,
                                           const PatchSet &ps, const uint32_t *prow, int lane, int u,
@@ -838,19 +864,19 @@ __device__ __forceinline__ void eval_pair(const Params &d, const MemRef<kShared>
 {
     constexpr int W = Cfg::W;
     {
-        uint4 xv[W];
+        uint4 xv[W], ohv[W];
         uint32_t ld4, x[kRowsPerLane][W], oh[kRowsPerLane][W];
-        load_tile<W, kShared>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ld4);
-        tile_pass_a<Cfg, kShared, kChk>(d, m_obj, lane, u, viol, obj, xv, ld4, x, oh);
+        load_tile<W, kShared, kOh>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ohv, ld4);
+        tile_pass_a<Cfg, kShared, kChk, kOh>(d, m_obj, lane, u, viol, obj, xv, ohv, ld4, x, oh);
         tile_pass_b<Cfg, kShared, kChk>(d, m_obj, lane, u, obj, xv, ld4);
         rc.template push_half<false>(x);
         lc.template push_half<false>(oh);
     }
     {
-        uint4 xv[W];
+        uint4 xv[W], ohv[W];
         uint32_t ld4, x[kRowsPerLane][W], oh[kRowsPerLane][W];
-        load_tile<W, kShared>(m_bits, m_leader, d.Ppad, ps, prow, lane, u + 1, xv, ld4);
-        tile_pass_a<Cfg, kShared, kChk>(d, m_obj, lane, u + 1, viol, obj, xv, ld4, x, oh);
+        load_tile<W, kShared, kOh>(m_bits, m_leader, d.Ppad, ps, prow, lane, u + 1, xv, ohv, ld4);
+        tile_pass_a<Cfg, kShared, kChk, kOh>(d, m_obj, lane, u + 1, viol, obj, xv, ohv, ld4, x, oh);
         tile_pass_b<Cfg, kShared, kChk>(d, m_obj, lane, u + 1, obj, xv, ld4);
         rc.template push_half<true>(x);
         lc.template push_half<true>(oh);
@@ -865,10 +891,10 @@ __device__ __forceinline__ void eval_single(const Params &d, const MemRef<kShare
                                             int &viol, int &obj)
 {
     constexpr int W = Cfg::W;
-    uint4 xv[W];
+    uint4 xv[W], ohv[W];
     uint32_t ld4, x[kRowsPerLane][W], oh[kRowsPerLane][W];
-    load_tile<W, kShared>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ld4);
-    tile_pass_a<Cfg, kShared, kChk>(d, m_obj, lane, u, viol, obj, xv, ld4, x, oh);
+    load_tile<W, kShared, false>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ohv, ld4);
+    tile_pass_a<Cfg, kShared, kChk, false>(d, m_obj, lane, u, viol, obj, xv, ohv, ld4, x, oh);
     tile_pass_b<Cfg, kShared, kChk>(d, m_obj, lane, u, obj, xv, ld4);
     rc.push4(x[0], x[1], x[2], x[3]);
     lc.push4(oh[0], oh[1], oh[2], oh[3]);
@@ -882,6 +908,7 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
                                const uint32_t *prow, int lane, int &viol_out, int &obj_out)
 {
     constexpr int W = Cfg::W, NPH = Cfg::NPH;
+    constexpr bool kOh = kShared && has_oh_plane<Cfg>();
     const MemRef<kShared> m_bits(bitsT), m_leader(leader), m_obj(objT);
     int viol = 0, obj = 0;
     const int ntiles = (d.P + kTileRows - 1) / kTileRows;
@@ -893,10 +920,10 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
         int u = 0;
 #pragma unroll 1
         for (; u + 2 <= nfull; u += 2)
-            eval_pair<Cfg, kShared, false>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
+            eval_pair<Cfg, kShared, false, kOh>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
 #pragma unroll 1
         for (; u < ntiles; u += 2)
-            eval_pair<Cfg, kShared, true>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
+            eval_pair<Cfg, kShared, true, kOh>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
     } else {
         // wide rows: one tile per iteration (the two-tile block would not fit the register file)
         int u = 0;
@@ -916,17 +943,17 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
             load_planes<W, NPH>(pl[t], rc, t);
             load_planes<W, NPH>(pl[W + t], lc, t);
         }
-        viol += column_violation<2 * W, NP0>(pl, lane, W, cs->bnd_rep, cs->bnd_ldr, true, d.log2S, d.R, cs);
+        viol += column_violation<2 * W, NP0>(pl, lane, W, cs->bnd_rep, cs->bnd_ldr, true, 1, d.log2S, d.R, cs);
     } else {
         uint32_t pl[W][kPlanes];
 #pragma unroll
         for (int t = 0; t < W; ++t) load_planes<W, NPH>(pl[t], rc, t);
-        viol += column_violation<W, NP0>(pl, lane, W, cs->bnd_rep, cs->bnd_rep, true, d.log2S, d.R, cs);
+        viol += column_violation<W, NP0>(pl, lane, W, cs->bnd_rep, cs->bnd_rep, true, 0, d.log2S, d.R, cs);
 #pragma unroll
         for (int t = 0; t < W; ++t) load_planes<W, NPH>(pl[t], lc, t);
-        viol += column_violation<W, NP0>(pl, lane, W, cs->bnd_ldr, cs->bnd_ldr, false, d.log2S, d.R, cs);
+        viol += column_violation<W, NP0>(pl, lane, W, cs->bnd_ldr, cs->bnd_ldr, false, 2, d.log2S, d.R, cs);
     }
-    viol_out = __reduce_add_sync(0xFFFFFFFFu, viol);
+    viol_out = __reduce_add_sync(0xFFFFFFFFu, viol) + d.P;          // + P: see column_violation (C2/C5)
     obj_out = __reduce_add_sync(0xFFFFFFFFu, obj);
 }
 
@@ -949,7 +976,7 @@ __device__ __forceinline__ void row_eval(const Params &d, const MemRef<kShared> 
         oh[t] = x[t] & lm;
         any |= oh[t];
     }
-    rv = row_rack_terms<W, Cfg::kHi1>(x, d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF) + (any ? 0 : 1);
+    rv = row_rack_terms<W, Cfg::kRack>(x, d.log2S, d.R, d.ppr_lo, d.ppr_hi, d.RF) + (any ? 0 : 1);
     ro = 0;
     if constexpr (Cfg::kObj > 0) {
 #pragma unroll

@@ -51,11 +51,12 @@ struct SmemPlan {
     uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, off_lists, off_totals, off_inv, total;
     uint32_t cap_hold, cap_led;      // delta mode: capacity of the inverted lists (0 = not staged)
 };
-static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int P, int RF)
+static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int P, int RF, bool oh_plane)
 {
     SmemPlan s;
     uint32_t o = 0;
     s.off_bits = o;   o += (uint32_t)W * Ppad * 4;
+    if (oh_plane) o += (uint32_t)W * Ppad * 4;            // leader one-hot plane, directly behind the bit-plane
     s.off_sw = o;     o += (uint32_t)obj_words_per_row * Ppad * 4;
     s.off_leader = o; o += (uint32_t)Ppad;
     s.off_consts = o; o += (uint32_t)sizeof(Consts);
@@ -78,6 +79,23 @@ static SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int
     }
     s.total = o;
     return s;
+}
+
+// Leader one-hot plane of the shared-memory base (kao_device.cuh, has_oh_plane): row & (1 << leader),
+// empty when the leader slot is not one of the row's replicas.  Stored right behind the bit-plane.
+template <int W> __device__ __forceinline__ uint32_t oh_word(uint32_t x, uint32_t ld, int w)
+{
+    return ((int)(ld >> 5) == w) ? (x & (1u << (ld & 31u))) : 0u;
+}
+template <int W, int THREADS>
+__device__ __forceinline__ void build_oh_plane(uint32_t *s_bits, const uint8_t *s_leader, int Ppad)
+{
+    for (int p = threadIdx.x; p < Ppad; p += THREADS) {
+        const uint32_t ld = s_leader[p];
+#pragma unroll
+        for (int w = 0; w < W; ++w) s_bits[(size_t)(W + w) * Ppad + p] = oh_word<W>(s_bits[(size_t)w * Ppad + p], ld, w);
+    }
+    __syncthreads();
 }
 
 // One search round (or a slice of it): every warp walks candidate indices idx_lo + gw, + stride ...,
@@ -117,6 +135,7 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
         bulk_g2s(s_cs, d.consts, (uint32_t)sizeof(Consts), s_bar);
     }
     mbar_wait(s_bar, 0);
+    if constexpr (has_oh_plane<Cfg>()) build_oh_plane<W, THREADS>(s_bits, s_leader, d.Ppad);
 
     Gen<W> gen;
     uint32_t no_rows[kMaxOps][W];          // warp mode keeps patched rows in shared memory instead
@@ -329,6 +348,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         bulk_g2s(s_cs, d.consts, (uint32_t)sizeof(Consts), s_bar);
     }
     mbar_wait(s_bar, 0);
+    if constexpr (has_oh_plane<Cfg>()) build_oh_plane<W, THREADS>(s_bits, s_leader, d.Ppad);
     rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
 
     Gen<W> gen;
@@ -534,6 +554,8 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                             for (int w = 0; w < W; ++w) {
                                 const uint32_t v = gen.prow[i * W + w];
                                 s_bits[(size_t)w * d.Ppad + ps.p[i]] = v;
+                                if constexpr (has_oh_plane<Cfg>())
+                                    s_bits[(size_t)(W + w) * d.Ppad + ps.p[i]] = oh_word<W>(v, ps.ld[i], w);
                                 if (blockIdx.x == 0) d.bitsT[(size_t)w * d.Ppad + ps.p[i]] = v;
                             }
                             s_leader[ps.p[i]] = (uint8_t)ps.ld[i];
@@ -571,7 +593,7 @@ eval_batch_kernel(Params d, const uint32_t *cand_bits, const uint8_t *cand_leade
 #pragma unroll
     for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
     int viol, obj;
-    eval_candidate<EvalCfg<W, NPH, false, kObjEntries>, false>(d, cand_bits + (size_t)w * W * d.Ppad,
+    eval_candidate<EvalCfg<W, NPH, 0, kObjEntries>, false>(d, cand_bits + (size_t)w * W * d.Ppad,
                                                                cand_leader + (size_t)w * d.Ppad, d.swT, d.consts, ps,
                                                                nullptr, lane, viol, obj);
     if (lane == 0) { viol_out[w] = viol; obj_out[w] = obj; }
@@ -722,19 +744,25 @@ template <bool kDelta> struct LaunchPersistent {
     }
 };
 
+template <int W, int NPH, int kRack, class F, class A>
+static cudaError_t dispatch_obj(kao_handle *h, const F &f, const A &a)
+{
+    const int planes = h->prm.nplanes;
+    if constexpr (W <= 2) {
+        if (planes == 3) return f.template run<EvalCfg<W, NPH, kRack, 3>>(h, a);
+        if (planes == 6) return f.template run<EvalCfg<W, NPH, kRack, 6>>(h, a);
+    }
+    return f.template run<EvalCfg<W, NPH, kRack, kObjEntries>>(h, a);
+}
+// Rack form of the evaluator (kao_device.cuh, row_rack_terms): "at most one replica per rack" with
+// the field width fixed at compile time (8 / 16 slots / whole words), or general bounds.
 template <int W, int NPH, class F, class A>
 static cudaError_t dispatch_w(kao_handle *h, const F &f, const A &a)
 {
-    const int planes = h->prm.nplanes;
-    const bool hi1 = h->hm.hi1;
-    if constexpr (W <= 2) {
-        if (planes == 3 && hi1) return f.template run<EvalCfg<W, NPH, true, 3>>(h, a);
-        if (planes == 3) return f.template run<EvalCfg<W, NPH, false, 3>>(h, a);
-        if (planes == 6 && hi1) return f.template run<EvalCfg<W, NPH, true, 6>>(h, a);
-        if (planes == 6) return f.template run<EvalCfg<W, NPH, false, 6>>(h, a);
-    }
-    if (hi1) return f.template run<EvalCfg<W, NPH, true, kObjEntries>>(h, a);
-    return f.template run<EvalCfg<W, NPH, false, kObjEntries>>(h, a);
+    if (!h->hm.hi1) return dispatch_obj<W, NPH, 0>(h, f, a);
+    if (h->hm.log2S == 3) return dispatch_obj<W, NPH, 3>(h, f, a);
+    if (h->hm.log2S == 4) return dispatch_obj<W, NPH, 4>(h, f, a);
+    return dispatch_obj<W, NPH, 5>(h, f, a);
 }
 template <class F, class A> static cudaError_t dispatch(kao_handle *h, const F &f, const A &a)
 {
@@ -812,7 +840,12 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     const HostModel &m = h->hm;
     const int W = m.W, Ppad = m.Ppad;
     h->threads = W <= 2 ? KAO_THREADS : KAO_THREADS_WIDE;
-    h->plan = make_plan(W, Ppad, h->threads / 32, m.nplanes > 0 ? m.nplanes * W : 4, m.P, m.RF);
+    h->plan = make_plan(W, Ppad, h->threads / 32, m.nplanes > 0 ? m.nplanes * W : 4, m.P, m.RF, m.nplanes > 0);
+    if (h->plan.total > 227u * 1024u && m.nplanes > 0) {
+        // mask planes + one-hot plane do not fit next to the base: score with packed entries / the dense table
+        h->hm.nplanes = 0;
+        h->plan = make_plan(W, Ppad, h->threads / 32, 4, m.P, m.RF, false);
+    }
     if (h->plan.total > 227u * 1024u)
         return fail(KAO_E_ARG, "problem too large for the shared-memory resident search kernel");
     h->grid = h->sms;

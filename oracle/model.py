@@ -218,12 +218,12 @@ def evaluate(pb: Problem, replicas: np.ndarray):
         row = [int(b) for b in replicas[p] if b >= 0]
         uniq = set(row)
         viol += abs(len(uniq) - pb.RF)  # C1 (+C5: duplicates collapse)
-        if not row:
-            viol += 1  # C2: no leader
-            continue
-        ld = row[0]
-        lcnt[ld] += 1
-        obj += int(pb.wL[p, ld])
+        ld = row[0] if row else -1
+        if ld < 0:
+            viol += 1  # C2: no leader (C7's lower bound still applies to the empty row)
+        else:
+            lcnt[ld] += 1
+            obj += int(pb.wL[p, ld])
         pr = np.zeros(R, dtype=np.int64)
         for b in uniq:
             cnt[b] += 1

@@ -226,3 +226,34 @@ def test_abi_rejects_bad_input():
     bad.RF = bad.B                                             # RF must be < B
     with pytest.raises(kao.KaoError):
         kao.Session(bad)
+
+
+@pytest.mark.parametrize("name", ["cfg2_rm2", "s32", "w4_s16", "ragged", "rf_up"])
+def test_candidate_keys_from_an_arbitrary_malformed_base(ref_lib, name):
+    """kao_set_base with a damaged assignment (short rows, an empty row, duplicated brokers, rows
+    violating every constraint): generator and evaluator still agree with the restatement, in full
+    and (narrow rows) in delta evaluation."""
+    pb = SHAPES[name]()
+    r = ref_lib.Ref(pb)
+    rng = np.random.RandomState(21)
+    reps = np.stack([rng.choice(pb.B, size=pb.RF, replace=False) for _ in range(pb.P)]).astype(np.int32)
+    reps[0, :] = -1                                            # no replica at all: leader 0xFF
+    if pb.P > 3:
+        reps[1, -1] = -1                                       # short row
+        reps[2, -1] = reps[2, 0]                               # duplicate collapses
+        reps[3, :] = reps[3, 0]
+    bits, ld = r.encode(reps)
+    sess = kao.Session(product(pb))
+    sess.set_base(reps)
+    base, v, o, _ = sess.get_base()
+    assert (v, o) == r.evaluate(bits, ld) == m.evaluate(pb, r.decode(bits, ld))
+    want = r.candidate_keys(bits, ld, 0xBAD, 4, 2048, 0, 2048)
+    got = sess.candidate_keys(0xBAD, 4, 2048, 0, 2048)
+    bad = np.flatnonzero(want != got)
+    assert bad.size == 0, "idx %d: want %s got %s" % (bad[0], kao.unpack_key(want[bad[0]]), kao.unpack_key(got[bad[0]]))
+    if sess.stats()["words_per_row"] <= 2:
+        assert (sess.candidate_keys_delta(0xBAD, 4, 2048, 0, 2048) == want).all()
+    _, traj = r.search(bits, ld, 0xBAD, 0, 10, 1024)
+    keys, _ = sess.search(0xBAD, 0, 10, 1024)
+    assert (keys == traj).all()
+    sess.close()
