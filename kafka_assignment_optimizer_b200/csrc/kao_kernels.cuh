@@ -1,0 +1,558 @@
+// kao_kernels.cuh — the search kernels (one search round; all rounds in one persistent cooperative
+// launch, full or delta evaluation) and what they share with the host side: the shared-memory plan
+// and the cross-GPU mailbox.  Included by kao_engine.cu (host side, C ABI; the kernels are only
+// DECLARED there through explicit instantiation declarations) and by kao_inst.cu, which is compiled
+// once per (row width, counter depth, evaluation mode) and holds the explicit instantiations — the
+// translation units build in parallel and every one of them is compiled deterministically.
+#pragma once
+#include "kao_device.cuh"
+
+#include <cstdint>
+
+using namespace kao;
+
+#ifndef KAO_THREADS
+#define KAO_THREADS 768
+#endif
+#ifndef KAO_THREADS_WIDE
+#define KAO_THREADS_WIDE 256
+#endif
+#define KAO_THREADS_DELTA 512
+template <int W> constexpr int threads_for() { return W <= 2 ? KAO_THREADS : KAO_THREADS_WIDE; }
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA bulk copy (SASS: SYNCS / UBLKCP)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory plan of the search kernel
+// ------------------------------------------------------------------------------------------
+struct SmemPlan {
+    uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, off_lists, off_totals, off_inv, total;
+    uint32_t cap_hold, cap_led;      // delta mode: capacity of the inverted lists (0 = not staged)
+};
+inline SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int P, int RF, bool oh_plane)
+{
+    SmemPlan s;
+    uint32_t o = 0;
+    s.off_bits = o;   o += (uint32_t)W * Ppad * 4;
+    if (oh_plane) o += (uint32_t)W * Ppad * 4;            // leader one-hot plane, directly behind the bit-plane
+    s.off_sw = o;     o += (uint32_t)obj_words_per_row * Ppad * 4;
+    s.off_leader = o; o += (uint32_t)Ppad;
+    s.off_consts = o; o += (uint32_t)sizeof(Consts);
+    s.off_prow = o;   o += (uint32_t)warps * kMaxOps * W * 4;
+    o = (o + 15u) & ~15u;
+    s.off_red = o;    o += (uint32_t)(warps + 4) * 8;      // + early-stop state behind the per-warp minima
+    s.off_bar = o;    o += 16;
+    s.off_lists = o;  o += (uint32_t)Ppad * 4 + 16 + 2 * 36 * 4;   // D, DL (u16 each), counts, scan scratch
+    s.off_totals = o; o += (256 + 256 + 32 + 4 + 256 + 2 * 66 + 4) * 4;   // delta mode: cnt, lcnt, rc, base (viol, obj),
+                                                                           // led counts, list offsets, flag
+    s.off_inv = o;
+    s.cap_hold = s.cap_led = 0;
+    if (W <= 2) {   // inverted lists (u16 partitions) if they fit next to everything else
+        const uint32_t need = ((uint32_t)P * RF + 66 + (uint32_t)P + 2 + 8) * 2 + 2 * 512 * 4 + 16;   // + segment counts
+        if (o + need <= 227u * 1024u) {
+            s.cap_hold = ((uint32_t)P * RF + 64 + 1) & ~1u;     // even counts keep the int scratch behind them aligned
+            s.cap_led = ((uint32_t)P + 1) & ~1u;
+            o += (need + 15u) & ~15u;
+        }
+    }
+    s.total = o;
+    return s;
+}
+
+// Leader one-hot plane of the shared-memory base (kao_device.cuh, has_oh_plane): row & (1 << leader),
+// empty when the leader slot is not one of the row's replicas.  Stored right behind the bit-plane.
+template <int W> __device__ __forceinline__ uint32_t oh_word(uint32_t x, uint32_t ld, int w)
+{
+    return ((int)(ld >> 5) == w) ? (x & (1u << (ld & 31u))) : 0u;
+}
+template <int W, int THREADS>
+__device__ __forceinline__ void build_oh_plane(uint32_t *s_bits, const uint8_t *s_leader, int Ppad)
+{
+    for (int p = threadIdx.x; p < Ppad; p += THREADS) {
+        const uint32_t ld = s_leader[p];
+#pragma unroll
+        for (int w = 0; w < W; ++w) s_bits[(size_t)(W + w) * Ppad + p] = oh_word<W>(s_bits[(size_t)w * Ppad + p], ld, w);
+    }
+    __syncthreads();
+}
+
+// One search round (or a slice of it): every warp walks candidate indices idx_lo + gw, + stride ...,
+// generates the candidate from the shared-memory base, evaluates it in full and keeps the minimum
+// packed key; the block minimum goes to *out_key with one atomicMin.  all_keys (optional)
+// receives every candidate's key (parity tests).
+template <class Cfg, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint32_t round_size,
+                    uint32_t idx_lo, uint32_t idx_hi, unsigned long long *out_key,
+                    unsigned long long *all_keys)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(smem + plan.off_bits);
+    uint32_t *s_sw = reinterpret_cast<uint32_t *>(smem + plan.off_sw);
+    uint8_t *s_leader = smem + plan.off_leader;
+    Consts *s_cs = reinterpret_cast<Consts *>(smem + plan.off_consts);
+    uint32_t *s_prow = reinterpret_cast<uint32_t *>(smem + plan.off_prow);
+    unsigned long long *s_red = reinterpret_cast<unsigned long long *>(smem + plan.off_red);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + plan.off_bar);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = THREADS / 32;
+    constexpr int W = Cfg::W;
+    const uint32_t *g_obj = Cfg::kObj > 0 ? d.planesT : d.swT;
+    const uint32_t obj_words = Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries;
+
+    // stage base + tables: HBM/L2 -> shared memory with TMA bulk copies, one mbarrier
+    if (tid == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t nb = (uint32_t)W * d.Ppad * 4, ns = obj_words * d.Ppad * 4, nl = (uint32_t)d.Ppad;
+        mbar_expect_tx(s_bar, nb + ns + nl + (uint32_t)sizeof(Consts));
+        bulk_g2s(s_bits, d.bitsT, nb, s_bar);
+        if (ns) bulk_g2s(s_sw, g_obj, ns, s_bar);
+        bulk_g2s(s_leader, d.leader, nl, s_bar);
+        bulk_g2s(s_cs, d.consts, (uint32_t)sizeof(Consts), s_bar);
+    }
+    mbar_wait(s_bar, 0);
+    if constexpr (has_oh_plane<Cfg>()) build_oh_plane<W, THREADS>(s_bits, s_leader, d.Ppad);
+
+    Gen<W> gen;
+    uint32_t no_rows[kMaxOps][W];          // warp mode keeps patched rows in shared memory instead
+    gen.bitsT = s_bits; gen.leader = s_leader; gen.cs = s_cs; gen.d = &d;
+    gen.prow = s_prow + warp * kMaxOps * W; gen.lane = lane;
+    gen.D = d.D; gen.DL = d.DL; gen.nD = d.nD[0]; gen.nL = d.nD[1];
+
+    unsigned long long best = kKeyNone;
+    const uint32_t stride = gridDim.x * kWarps;
+    // every warp of the block runs the same number of iterations and meets at a barrier before each
+    // evaluation: the warps of a scheduler then walk the same code together (instruction cache)
+    const uint32_t first = idx_lo + blockIdx.x * kWarps;
+    const uint32_t iters = first < idx_hi ? (idx_hi - first + stride - 1) / stride : 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t idx = first + warp + it * stride;
+        const bool live = idx < idx_hi;
+        PatchSet ps;
+        ps.n = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
+        if (live) gen.run(seed, round, idx, round_size, ps, no_rows);
+#if KAO_LOCKSTEP
+        __syncthreads();
+#else
+        __syncwarp();
+#endif
+        if (live) {
+            int viol, obj;
+            eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
+            const unsigned long long key = live ? pack_key(viol, obj, idx) : kKeyNone;
+            if (all_keys && lane == 0) all_keys[idx - idx_lo] = key;
+            best = key < best ? key : best;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) s_red[warp] = best;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = lane < kWarps ? s_red[lane] : kKeyNone;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long w = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            v = w < v ? w : v;
+        }
+        if (lane == 0 && v != kKeyNone) atomicMin(out_key, v);
+    }
+}
+
+// Rebuilds the displaced lists of a base with the whole block (ballot compaction, ascending
+// order).  cnt: 2 x 36 ints of shared scratch.  counts[0] = |D|, counts[1] = |DL|.
+template <int THREADS>
+__device__ __forceinline__ void rebuild_lists(const uint32_t *bitsT, const uint8_t *leader, const uint32_t *homeT,
+                                              int P, int Ppad, uint16_t *D, uint16_t *DL, int *counts, int *cnt)
+{
+    constexpr int kWarps = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *cD = cnt, *cL = cnt + 36;
+    int baseD = 0, baseL = 0;
+    for (int p0 = 0; p0 < P; p0 += THREADS) {
+        const int p = p0 + tid;
+        bool miss = false, ldis = false;
+        if (p < P) {
+            const uint32_t h4 = homeT[p];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int hs = (h4 >> (8 * i)) & 0xFF;
+                if (hs != 0xFF) {
+                    const bool has = (bitsT[(size_t)(hs >> 5) * Ppad + p] >> (hs & 31)) & 1u;
+                    miss |= !has;
+                    if (i == 0) ldis = has && ((int)leader[p] != hs);
+                }
+            }
+        }
+        const uint32_t mD = __ballot_sync(0xFFFFFFFFu, miss);
+        const uint32_t mL = __ballot_sync(0xFFFFFFFFu, ldis);
+        if (lane == 0) { cD[warp] = __popc(mD); cL[warp] = __popc(mL); }
+        __syncthreads();
+        if (warp == 0) {
+            int c = lane < kWarps ? cD[lane] : 0, incl = c, cl = lane < kWarps ? cL[lane] : 0, incl2 = cl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                const int v2 = __shfl_up_sync(0xFFFFFFFFu, incl2, o);
+                if (lane >= o) { incl += v; incl2 += v2; }
+            }
+            cD[lane] = incl - c;
+            cL[lane] = incl2 - cl;
+            if (lane == 31) { cD[32] = incl; cL[32] = incl2; }
+        }
+        __syncthreads();
+        const uint32_t below = (1u << lane) - 1u;
+        if (miss) D[baseD + cD[warp] + __popc(mD & below)] = (uint16_t)p;
+        if (ldis) DL[baseL + cL[warp] + __popc(mL & below)] = (uint16_t)p;
+        baseD += cD[32];
+        baseL += cL[32];
+        __syncthreads();
+    }
+    if (tid == 0) { counts[0] = baseD; counts[1] = baseL; }
+    __syncthreads();
+}
+
+// Cross-GPU exchange state of the persistent kernel (docs/MODEL.md §7): every rank owns a mailbox
+// in its HBM that all peers map through CUDA IPC; per round the ranks min-reduce their 8-byte keys
+// into every mailbox with NVLink atomics and count arrivals — no host, no NCCL in the loop.
+constexpr int kMaxPeers = 8;
+constexpr uint32_t kMailRounds = 8192;          // rounds per launch when sharded
+struct Mailbox {
+    unsigned long long keys[2][kMailRounds];    // [bank][round]  min of the ranks' keys
+    unsigned int arrive[2][kMailRounds];        // [bank][round]  ranks that have contributed
+};
+struct P2P {
+    int rank, world, bank;
+    uint32_t idx_lo, idx_hi;                    // this rank's slice of every round
+    Mailbox *const *mail;                       // [world] peer-mapped mailboxes (device array), mail[rank] is local
+    unsigned long long *lkeys;                  // [rounds] this GPU's own minimum per round
+    unsigned int *release;                      // CTA 0 publishes "round t is decided" here
+    int *abort;                                 // set when a wait times out (a peer died): everybody leaves
+    uint32_t patience;                          // > 0: stop after this many rounds without a better key
+    unsigned int *rounds_run;                   // CTA 0 reports the number of rounds actually run
+};
+
+__device__ __forceinline__ bool spin_until(const unsigned int *p, unsigned int target, int *abort_flag)
+{
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile unsigned int *>(p) < target) {
+        if (*reinterpret_cast<volatile int *>(abort_flag)) return false;
+        if (clock64() - t0 > 6000000000ll) { atomicExch(abort_flag, 1); return false; }   // ~3 s
+    }
+    return true;
+}
+
+// All rounds of a search in ONE launch (cooperative: one CTA per SM, all co-resident).  The base
+// and the tables stay in shared memory for the whole search; per round every CTA evaluates its
+// share of the candidates, min-reduces into keys[t], meets the other CTAs at a grid barrier, then
+// re-materialises the winner itself and patches its own shared-memory copy of the base (<= 3
+// rows) — nothing but one 8-byte key crosses the chip per round.  CTA 0 mirrors the patches into
+// the HBM base.
+template <class Cfg, int THREADS, bool kDelta>
+__global__ void __launch_bounds__(THREADS, 1)
+search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                         uint32_t round_size, unsigned long long *keys, unsigned int *grid_bar, P2P pp,
+                         unsigned long long *all_keys)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(smem + plan.off_bits);
+    uint32_t *s_sw = reinterpret_cast<uint32_t *>(smem + plan.off_sw);
+    uint8_t *s_leader = smem + plan.off_leader;
+    Consts *s_cs = reinterpret_cast<Consts *>(smem + plan.off_consts);
+    uint32_t *s_prow = reinterpret_cast<uint32_t *>(smem + plan.off_prow);
+    unsigned long long *s_red = reinterpret_cast<unsigned long long *>(smem + plan.off_red);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + plan.off_bar);
+    int &s_abort = *reinterpret_cast<int *>(smem + plan.off_bar + 8);   // no static shared memory: the
+                                                                        // dynamic limit is the full 227 KB
+    uint16_t *s_D = reinterpret_cast<uint16_t *>(smem + plan.off_lists);
+    uint16_t *s_DL = s_D + d.Ppad;
+    int *s_counts = reinterpret_cast<int *>(smem + plan.off_lists + (size_t)d.Ppad * 4);
+    int *s_scan = s_counts + 4;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = THREADS / 32;
+    constexpr int W = Cfg::W;
+    const uint32_t *g_obj = Cfg::kObj > 0 ? d.planesT : d.swT;
+    const uint32_t obj_words = Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries;
+
+    if (tid == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t nb = (uint32_t)W * d.Ppad * 4, ns = obj_words * d.Ppad * 4, nl = (uint32_t)d.Ppad;
+        mbar_expect_tx(s_bar, nb + ns + nl + (uint32_t)sizeof(Consts));
+        bulk_g2s(s_bits, d.bitsT, nb, s_bar);
+        if (ns) bulk_g2s(s_sw, g_obj, ns, s_bar);
+        bulk_g2s(s_leader, d.leader, nl, s_bar);
+        bulk_g2s(s_cs, d.consts, (uint32_t)sizeof(Consts), s_bar);
+    }
+    mbar_wait(s_bar, 0);
+    if constexpr (has_oh_plane<Cfg>()) build_oh_plane<W, THREADS>(s_bits, s_leader, d.Ppad);
+    rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
+
+    Gen<W> gen;
+    uint32_t no_rows[kMaxOps][W];          // warp mode keeps patched rows in shared memory instead
+    gen.bitsT = s_bits; gen.leader = s_leader; gen.cs = s_cs; gen.d = &d;
+    gen.prow = s_prow + warp * kMaxOps * W; gen.lane = lane;
+    gen.D = s_D; gen.DL = s_DL;
+
+    const uint32_t stride = gridDim.x * kWarps;
+    const uint32_t first = pp.idx_lo + blockIdx.x * kWarps;
+    const uint32_t iters = first < pp.idx_hi ? (pp.idx_hi - first + stride - 1) / stride : 0;
+    if (tid == 0) s_abort = 0;
+    // early-stop state lives behind the per-warp minima (s_red is live anyway; a separate pointer would
+    // cost a register in the hot loop): [kWarps] stop flag, [kWarps+1] best (violation, cost), [kWarps+2] stall
+    if (tid == 0) { s_red[kWarps] = 0; s_red[kWarps + 1] = kKeyNone; s_red[kWarps + 2] = 0; }
+    for (uint32_t t = 0; t < rounds; ++t) {
+        const uint32_t round = first_round + t;
+        gen.nD = s_counts[0]; gen.nL = s_counts[1];
+        unsigned long long best = kKeyNone;
+        if constexpr (kDelta) {
+            // ---- delta mode: totals of the base once per round, then one THREAD per candidate
+            int *s_cnt = reinterpret_cast<int *>(smem + plan.off_totals), *s_lcnt = s_cnt + 256, *s_rc = s_cnt + 512,
+                *s_base = s_cnt + 544;
+            int *s_ledn = s_cnt + 548, *s_hoff = s_cnt + 804, *s_loff = s_cnt + 870, *s_inv = s_cnt + 936;
+            uint16_t *s_hold = reinterpret_cast<uint16_t *>(smem + plan.off_inv), *s_led = s_hold + plan.cap_hold;
+            for (int i = tid; i < 804; i += THREADS) if (i < 544 || i >= 548) s_cnt[i] = 0;   // keep s_base
+            __syncthreads();
+            for (int p = tid; p < d.P; p += THREADS) {
+                const int ld = s_leader[p];
+                bool ok = false;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const uint32_t xw = s_bits[(size_t)w * d.Ppad + p];
+                    for (uint32_t m = xw; m; m &= m - 1) {
+                        const int sl = w * 32 + __ffs(m) - 1;
+                        atomicAdd(&s_cnt[sl], 1);
+                        atomicAdd(&s_rc[sl >> d.log2S], 1);
+                    }
+                    if ((ld >> 5) == w) ok = (xw >> (ld & 31)) & 1u;
+                }
+                if (ok) atomicAdd(&s_lcnt[ld], 1);
+                atomicAdd(&s_ledn[ld], 1);
+            }
+            __syncthreads();
+            // per-slot inverted lists of the base (ascending partitions) for the per-thread generator
+            if (tid == 0) {
+                int a = 0, b = 0;
+                for (int sl = 0; sl < W * 32; ++sl) { s_hoff[sl] = a; a += s_cnt[sl]; s_loff[sl] = b; b += s_ledn[sl]; }
+                s_hoff[W * 32] = a; s_loff[W * 32] = b;
+                *s_inv = (plan.cap_hold > 0 && a <= (int)plan.cap_hold && b <= (int)plan.cap_led) ? 1 : 0;
+            }
+            __syncthreads();
+            if (*s_inv) {
+                // THREADS / slots segments of rows per slot: count, then write in place (ascending order)
+                constexpr int NSL = W * 32, NSEG = THREADS / NSL;
+                int *s_segc = reinterpret_cast<int *>(s_led + plan.cap_led + 8);       // [2][NSEG][NSL]
+                const int slot = tid % NSL, seg = tid / NSL;
+                const int chunk = (d.P + NSEG - 1) / NSEG, p_lo = seg * chunk, p_hi = min(d.P, p_lo + chunk);
+                const uint32_t *col = s_bits + (size_t)(slot >> 5) * d.Ppad;
+                const uint32_t bit = 1u << (slot & 31);
+                int hc = 0, lc = 0;
+                for (int p = p_lo; p < p_hi; ++p) {
+                    hc += (col[p] & bit) ? 1 : 0;
+                    lc += ((int)s_leader[p] == slot) ? 1 : 0;
+                }
+                s_segc[seg * NSL + slot] = hc;
+                s_segc[(NSEG + seg) * NSL + slot] = lc;
+                __syncthreads();
+                int hpos = s_hoff[slot], lpos = s_loff[slot];
+                for (int g = 0; g < seg; ++g) { hpos += s_segc[g * NSL + slot]; lpos += s_segc[(NSEG + g) * NSL + slot]; }
+                for (int p = p_lo; p < p_hi; ++p) {
+                    if (col[p] & bit) s_hold[hpos++] = (uint16_t)p;
+                    if ((int)s_leader[p] == slot) s_led[lpos++] = (uint16_t)p;
+                }
+            }
+            // the base's own evaluation: a full pass in the first round, afterwards it IS the previous
+            // winner's key (unless that key was saturated)
+            if (warp == 0 && (t == 0 || s_base[2] == 0)) {
+                PatchSet id;
+                id.n = 0;
+#pragma unroll
+                for (int i = 0; i < kMaxOps; ++i) { id.p[i] = -1; id.ld[i] = 0xFF; }
+                int bv, bo;
+                eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, id, gen.prow, lane, bv, bo);
+                if (lane == 0) { s_base[0] = bv; s_base[1] = bo; }
+            }
+            __syncthreads();
+            Gen<W, true> tg;
+            tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
+            tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
+            tg.inv_ok = *s_inv != 0; tg.hoff = s_hoff; tg.loff = s_loff; tg.hold = s_hold; tg.led = s_led;
+            const MemRef<true> m_obj(s_sw);
+            const int base_viol = s_base[0], base_obj = s_base[1];
+            const uint32_t tstride = gridDim.x * THREADS;
+            for (uint32_t idx = pp.idx_lo + blockIdx.x * THREADS + tid; idx < pp.idx_hi; idx += tstride) {
+                PatchSet ps;
+                uint32_t rows[kMaxOps][W];
+                tg.run(seed, round, idx, round_size, ps, rows);
+                int viol, obj;
+                delta_eval<Cfg>(d, s_bits, s_leader, m_obj, s_cs, ps, rows, s_cnt, s_lcnt, s_rc, base_viol, base_obj, viol, obj);
+                const unsigned long long key = pack_key(viol, obj, idx);
+                if (all_keys) all_keys[idx - pp.idx_lo] = key;
+                best = key < best ? key : best;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long w = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+                best = w < best ? w : best;
+            }
+            if (all_keys) return;                                   // key dump only: the base stays as it is
+        } else {
+        for (uint32_t it = 0; it < iters; ++it) {
+            const uint32_t idx = first + warp + it * stride;
+            const bool live = idx < pp.idx_hi;
+            PatchSet ps;
+            ps.n = 0;
+#pragma unroll
+            for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
+            if (live) gen.run(seed, round, idx, round_size, ps, no_rows);
+            __syncthreads();
+            if (live) {
+                int viol, obj;
+                eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
+                const unsigned long long key = pack_key(viol, obj, idx);
+                best = key < best ? key : best;
+            }
+            __syncwarp();
+        }
+        }
+        if (lane == 0) s_red[warp] = best;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long v = lane < kWarps ? s_red[lane] : kKeyNone;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long w = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                v = w < v ? w : v;
+            }
+            if (lane == 0) {
+                if (pp.world == 1) {
+                    if (v != kKeyNone) atomicMin(keys + t, v);
+                    // grid barrier: every CTA's contribution to keys[t] is visible before anyone reads it
+                    __threadfence();
+                    atomicAdd(grid_bar, 1u);
+                    if (!spin_until(grid_bar, (t + 1) * gridDim.x, pp.abort)) s_abort = 1;
+                    __threadfence();
+                } else {
+                    // 1. this GPU's minimum
+                    if (v != kKeyNone) atomicMin(pp.lkeys + t, v);
+                    __threadfence();
+                    atomicAdd(grid_bar, 1u);
+                    if (blockIdx.x == 0) {
+                        // 2. CTA 0 trades it with every peer over NVLink: min into each mailbox, then arrive
+                        bool ok = spin_until(grid_bar, (t + 1) * gridDim.x, pp.abort);
+                        if (ok) {
+                            __threadfence();
+                            const unsigned long long mine = __ldcg(pp.lkeys + t);
+                            for (int r = 0; r < pp.world; ++r) atomicMin_system(&pp.mail[r]->keys[pp.bank][t], mine);
+                            __threadfence_system();
+                            for (int r = 0; r < pp.world; ++r) atomicAdd_system(&pp.mail[r]->arrive[pp.bank][t], 1u);
+                            ok = spin_until(&pp.mail[pp.rank]->arrive[pp.bank][t], (unsigned int)pp.world, pp.abort);
+                        }
+                        if (ok) {
+                            __threadfence_system();
+                            keys[t] = *reinterpret_cast<volatile unsigned long long *>(&pp.mail[pp.rank]->keys[pp.bank][t]);
+                            __threadfence();
+                            atomicExch(pp.release, t + 1);            // 3. local CTAs may read keys[t]
+                        } else s_abort = 1;
+                    } else if (!spin_until(pp.release, t + 1, pp.abort)) s_abort = 1;
+                    __threadfence();
+                }
+            }
+        }
+        __syncthreads();
+        if (s_abort) return;                                        // a peer vanished: leave, the host reports it
+        // the winner becomes the base: every CTA patches its own shared-memory copy
+        if (warp == 0) {
+            const unsigned long long k = __ldcg(keys + t);
+#if !defined(KAO_NO_PATIENCE)
+            if (lane == 0) {
+                // early stop (same decision in every CTA and on every rank: it only depends on the keys)
+                const unsigned long long vc = k >> kIdxBits;
+                if (vc < s_red[kWarps + 1]) { s_red[kWarps + 1] = vc; s_red[kWarps + 2] = 0; } else ++s_red[kWarps + 2];
+                if (pp.patience && s_red[kWarps + 2] >= pp.patience) s_red[kWarps] = 1;
+                if (blockIdx.x == 0 && pp.rounds_run) *pp.rounds_run = t + 1;
+            }
+#endif
+            if (kDelta && lane == 0) {
+                int *s_base = reinterpret_cast<int *>(smem + plan.off_totals) + 544;
+                const uint32_t kv = (uint32_t)(k >> 48);
+                s_base[2] = (k != kKeyNone && kv < kViolCap) ? 1 : 0;
+                s_base[0] = (int)kv;
+                s_base[1] = (int)(kObjCap - (uint32_t)((k >> kIdxBits) & kObjCap));
+            }
+            if (k != kKeyNone) {
+                PatchSet ps;
+                gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps, no_rows);
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < kMaxOps; ++i) {
+                        if (i < ps.n) {
+                            for (int w = 0; w < W; ++w) {
+                                const uint32_t v = gen.prow[i * W + w];
+                                s_bits[(size_t)w * d.Ppad + ps.p[i]] = v;
+                                if constexpr (has_oh_plane<Cfg>())
+                                    s_bits[(size_t)(W + w) * d.Ppad + ps.p[i]] = oh_word<W>(v, ps.ld[i], w);
+                                if (blockIdx.x == 0) d.bitsT[(size_t)w * d.Ppad + ps.p[i]] = v;
+                            }
+                            s_leader[ps.p[i]] = (uint8_t)ps.ld[i];
+                            if (blockIdx.x == 0) d.leader[ps.p[i]] = (uint8_t)ps.ld[i];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
+#if !defined(KAO_NO_PATIENCE)
+        if (s_red[kWarps]) break;
+#endif
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// instantiation lists.  X(W, NPH, kRack, kObj) for every evaluator configuration of a row width /
+// counter depth: rack forms {general, 8-slot, 16-slot, whole-word} x objective encodings {packed
+// entries / dense, 3 mask planes, 6 mask planes} (mask planes: rows of up to 64 slots only).
+// ------------------------------------------------------------------------------------------
+#define KAO_FOR_RACKS(X, W, NPH, O) X(W, NPH, 0, O) X(W, NPH, 3, O) X(W, NPH, 4, O) X(W, NPH, 5, O)
+#define KAO_FOR_CFGS_NARROW(X, W, NPH) KAO_FOR_RACKS(X, W, NPH, 0) KAO_FOR_RACKS(X, W, NPH, 3) KAO_FOR_RACKS(X, W, NPH, 6)
+#define KAO_FOR_CFGS_WIDE(X, W, NPH) KAO_FOR_RACKS(X, W, NPH, 0)
+
+#define KAO_ROUND_KERNEL(W, NPH, R, O)                                                                      \
+    search_round_kernel<EvalCfg<W, NPH, R, O>, threads_for<W>()>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
+                                                                   uint32_t, uint32_t, unsigned long long *,      \
+                                                                   unsigned long long *)
+#define KAO_PERSISTENT_KERNEL(W, NPH, R, O, T, DELTA)                                                       \
+    search_persistent_kernel<EvalCfg<W, NPH, R, O>, T, DELTA>(Params, SmemPlan, uint64_t, uint32_t, uint32_t,      \
+                                                             uint32_t, unsigned long long *, unsigned int *, P2P, \
+                                                             unsigned long long *)

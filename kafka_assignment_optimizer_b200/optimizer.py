@@ -55,7 +55,7 @@ def load_library():
             import subprocess
 
             csrc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-            r = subprocess.run(["make", "-s", "-C", csrc], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            r = subprocess.run(["make", "-s", "-j", str(os.cpu_count() or 4), "-C", csrc], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             if r.returncode != 0:
                 raise KaoError("libkao.so is not built and building it failed (no CPU fallback):\n" + r.stdout[-2000:])
         if not os.path.exists(_LIB_PATH):
