@@ -249,7 +249,7 @@ def main():
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "search_persistent_kernel<EvalCfg<W=2,NPH=3,hi1,planes=3>,768>",
+                    "traffic": traffic, "kernel": "search_persistent_kernel<EvalCfg<W=2,NPH=3,rack=8-slot hi1,planes=3>,768>",
                     "algorithmic_bytes_per_candidate": ALGO_BYTES, "candidates_per_launch": ROUND_SIZE * ROUNDS,
                     "kernel_ms_per_launch": s_ms,
                     "per_round_kernels_ms": {"search_round_kernel": pr_ms / 8, "apply_winner_kernel": ap_ms / 8},
