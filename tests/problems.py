@@ -33,6 +33,9 @@ SHAPES = {
     "one_partition": lambda: make_problem(1, [2, 2, 2], 3, seed=10),
     "max_rows": lambda: m.synthetic_problem(8160, 16, 4, 2, remove=1),
     "all_slots": lambda: m.synthetic_problem(64, 256, 16, 3),
+    # two-word rows too many for mask planes + one-hot plane in shared memory: the engine falls back
+    # to packed weight entries (same keys)
+    "w2_rows6000": lambda: m.synthetic_problem(6000, 64, 8, 3, remove=1),
 }
 
 
