@@ -466,6 +466,16 @@ __device__ __forceinline__ uint32_t bytecounts(uint32_t x)
 
 // Base address of a table, resolved once per candidate: a 32-bit shared-memory address for the
 // search kernel (no generic->shared conversion per load), a global pointer for explicit populations.
+#if defined(KAO_HOST_EMU)
+// tests/emu compiles these device functions for the host (a warp = 32 lock-stepped fibers): there
+// "shared memory" is plain memory and the PTX loads below become ordinary loads.
+template <bool kShared> struct MemRef {
+    const char *ga;
+    explicit MemRef(const void *p) : ga(static_cast<const char *>(p)) {}
+    uint4 ld128(uint32_t byte_off) const { return *reinterpret_cast<const uint4 *>(ga + byte_off); }
+    uint32_t ld32(uint32_t byte_off) const { return *reinterpret_cast<const uint32_t *>(ga + byte_off); }
+};
+#else
 template <bool kShared> struct MemRef {
     uint32_t sa;
     const char *ga;
@@ -495,6 +505,7 @@ template <bool kShared> struct MemRef {
         }
     }
 };
+#endif
 
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int i)
 {
@@ -760,7 +771,11 @@ __device__ __forceinline__ void tile_pass_a(const Params &d, const MemRef<kShare
             for (int t = 0; t < W; ++t) oh[i][t] = comp(ohv[t], i);
         } else if constexpr (W == 2) {
             unsigned long long ob;                               // 1 << ld; PTX shl clamps: ld >= 64 gives 0
+#if defined(KAO_HOST_EMU)
+            ob = ld >= 64u ? 0ull : 1ull << ld;
+#else
             asm("shl.b64 %0, %1, %2;" : "=l"(ob) : "l"(1ull), "r"(ld));
+#endif
             oh[i][0] = x[i][0] & (uint32_t)ob;
             oh[i][1] = x[i][1] & (uint32_t)(ob >> 32);
         } else {

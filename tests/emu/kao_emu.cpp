@@ -1,0 +1,334 @@
+// kao_emu.cpp — TEST INFRASTRUCTURE.  The engine's own device code (csrc/kao_device.cuh: candidate
+// generator, full evaluator, delta evaluator) compiled for the host on top of warp_emu.hpp, with the
+// engine's own host model (csrc/kao_host.hpp) and shared-memory plan (csrc/kao_plan.hpp) deciding
+// layout and evaluator configuration exactly as kao_create / dispatch do.  tests/test_device_emulation.py
+// checks it against the committed golden streams and the oracle restatement, so the arithmetic of the
+// CUDA path is exercised by the CPU suite as well; the kernels themselves (staging, grid barrier,
+// cross-GPU exchange) are only tested on the GPU.  Never linked into libkao.so.
+#define KAO_HOST_EMU 1
+#include "warp_emu.hpp"
+
+#include "../../kafka_assignment_optimizer_b200/csrc/kao_device.cuh"
+#include "../../kafka_assignment_optimizer_b200/csrc/kao_plan.hpp"
+#include "../../kafka_assignment_optimizer_b200/csrc/kao_host.hpp"
+
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace kao;
+
+namespace {
+
+struct Emu {
+    HostModel hm;
+    Params prm{};
+    Consts cs{};
+    bool oh = false;                     // leader one-hot plane kept behind the bit-plane (has_oh_plane)
+    int nph = 3, rack = 0, obj = 0;      // evaluator configuration (EvalCfg<W, NPH, kRack, kObj>)
+    std::vector<uint32_t> bits;          // [W or 2W][Ppad]
+    std::vector<uint8_t> leader;         // [Ppad]
+    std::vector<uint16_t> D, DL;
+    int nD = 0, nL = 0;
+    std::vector<uint32_t> prow;          // [kMaxOps * W]
+    std::string err;
+};
+
+uint32_t oh_word(uint32_t x, uint32_t ld, int w) { return ((int)(ld >> 5) == w) ? (x & (1u << (ld & 31u))) : 0u; }
+
+// rebuild_lists of kao_kernels.cuh: ascending partitions that miss a home slot (D) / hold home slot
+// 0 without being led from it (DL)
+void rebuild_lists(Emu &e)
+{
+    const HostModel &m = e.hm;
+    e.nD = e.nL = 0;
+    for (int p = 0; p < m.P; ++p) {
+        const uint32_t h4 = m.homeT[p];
+        bool miss = false, ldis = false;
+        for (int i = 0; i < 4; ++i) {
+            const int hs = (h4 >> (8 * i)) & 0xFF;
+            if (hs == 0xFF) continue;
+            const bool has = (e.bits[(size_t)(hs >> 5) * m.Ppad + p] >> (hs & 31)) & 1u;
+            miss |= !has;
+            if (i == 0) ldis = has && ((int)e.leader[p] != hs);
+        }
+        if (miss) e.D[e.nD++] = (uint16_t)p;
+        if (ldis) e.DL[e.nL++] = (uint16_t)p;
+    }
+}
+
+void set_base(Emu &e, const std::vector<uint32_t> &bitsT, const std::vector<uint8_t> &leader)
+{
+    const HostModel &m = e.hm;
+    e.bits.assign((size_t)(e.oh ? 2 : 1) * m.W * m.Ppad, 0);
+    std::copy(bitsT.begin(), bitsT.end(), e.bits.begin());
+    e.leader = leader;
+    if (e.oh)
+        for (int p = 0; p < m.Ppad; ++p)
+            for (int w = 0; w < m.W; ++w)
+                e.bits[(size_t)(m.W + w) * m.Ppad + p] = oh_word(e.bits[(size_t)w * m.Ppad + p], e.leader[p], w);
+    e.prm.bitsT = e.bits.data();
+    e.prm.leader = e.leader.data();
+    rebuild_lists(e);
+}
+
+template <class Cfg> struct Run {
+    static constexpr int W = Cfg::W;
+    static Gen<W> make_gen(Emu &e, int lane)
+    {
+        Gen<W> g;
+        g.bitsT = e.bits.data(); g.leader = e.leader.data(); g.cs = &e.cs; g.d = &e.prm;
+        g.prow = e.prow.data(); g.lane = lane;
+        g.D = e.D.data(); g.DL = e.DL.data(); g.nD = e.nD; g.nL = e.nL;
+        return g;
+    }
+    // generate + evaluate in full, as one warp of the search kernels does
+    static unsigned long long key(Emu &e, uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size)
+    {
+        unsigned long long out = 0;
+        const uint32_t *objT = Cfg::kObj > 0 ? e.prm.planesT : e.prm.swT;
+        emu::run_warp([&](int lane) {
+            Gen<W> g = make_gen(e, lane);
+            uint32_t no_rows[kMaxOps][W];
+            PatchSet ps;
+            g.run(seed, round, idx, round_size, ps, no_rows);
+            __syncwarp();                                     // __syncthreads() of the kernels
+            int viol, obj;
+            eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
+            if (lane == 0) out = pack_key(viol, obj, idx);
+        });
+        return out;
+    }
+    // the winner becomes the base (search_persistent_kernel, after the grid barrier)
+    static void apply(Emu &e, uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size)
+    {
+        PatchSet win;
+        emu::run_warp([&](int lane) {
+            Gen<W> g = make_gen(e, lane);
+            uint32_t no_rows[kMaxOps][W];
+            PatchSet ps;
+            g.run(seed, round, idx, round_size, ps, no_rows);
+            if (lane == 0) win = ps;
+        });
+        const int Ppad = e.hm.Ppad;
+        for (int i = 0; i < win.n; ++i) {
+            for (int w = 0; w < W; ++w) {
+                const uint32_t v = e.prow[i * W + w];
+                e.bits[(size_t)w * Ppad + win.p[i]] = v;
+                if (e.oh) e.bits[(size_t)(W + w) * Ppad + win.p[i]] = oh_word(v, win.ld[i], w);
+            }
+            e.leader[win.p[i]] = (uint8_t)win.ld[i];
+        }
+        rebuild_lists(e);
+    }
+    // delta mode (search_persistent_kernel<..., kDelta>): per-thread generator + delta evaluator on
+    // the base's totals; no inverted lists here (the generator's linear-scan form)
+    static unsigned long long key_delta(Emu &e, uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size,
+                                        const int *cnt, const int *lcnt, const int *rc, int base_viol, int base_obj)
+    {
+        if constexpr (W <= 2) {
+            Gen<W, true> tg;
+            tg.bitsT = e.bits.data(); tg.leader = e.leader.data(); tg.cs = &e.cs; tg.d = &e.prm; tg.prow = nullptr; tg.lane = 0;
+            tg.D = e.D.data(); tg.DL = e.DL.data(); tg.nD = e.nD; tg.nL = e.nL;
+            const uint32_t *objT = Cfg::kObj > 0 ? e.prm.planesT : e.prm.swT;
+            const MemRef<true> m_obj(objT);
+            PatchSet ps;
+            uint32_t rows[kMaxOps][W];
+            tg.run(seed, round, idx, round_size, ps, rows);
+            int viol, obj;
+            delta_eval<Cfg>(e.prm, e.bits.data(), e.leader.data(), m_obj, &e.cs, ps, rows, cnt, lcnt, rc, base_viol, base_obj, viol, obj);
+            return pack_key(viol, obj, idx);
+        } else {
+            (void)e; (void)seed; (void)round; (void)idx; (void)round_size; (void)cnt; (void)lcnt; (void)rc; (void)base_viol; (void)base_obj;
+            return kKeyNone;
+        }
+    }
+};
+
+// explicit candidate from HBM-style buffers (eval_batch_kernel): general rack form, packed entries
+template <int W> void eval_explicit(Emu &e, const uint32_t *cb, const uint8_t *cl, long long &viol, long long &obj)
+{
+    int v = 0, o = 0;
+    emu::run_warp([&](int lane) {
+        PatchSet ps;
+        ps.n = 0;
+        for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
+        int lv, lo;
+        eval_candidate<EvalCfg<W, 5, 0, kObjEntries>, false>(e.prm, cb, cl, e.prm.swT, &e.cs, ps, nullptr, lane, lv, lo);
+        if (lane == 0) { v = lv; o = lo; }
+    });
+    viol = v; obj = o;
+}
+
+// kao_engine.cu: dispatch / dispatch_w / dispatch_obj
+template <class F> auto dispatch(Emu &e, F f)
+{
+#define KAO_EMU_CASE(W_, NPH_, R_, O_) \
+    if (e.hm.W == W_ && e.nph == NPH_ && e.rack == R_ && e.obj == O_) return f(Run<EvalCfg<W_, NPH_, R_, O_>>{});
+#define KAO_EMU_RACKS(W_, NPH_, O_) KAO_EMU_CASE(W_, NPH_, 0, O_) KAO_EMU_CASE(W_, NPH_, 3, O_) KAO_EMU_CASE(W_, NPH_, 4, O_) KAO_EMU_CASE(W_, NPH_, 5, O_)
+#define KAO_EMU_NARROW(W_, NPH_) KAO_EMU_RACKS(W_, NPH_, 0) KAO_EMU_RACKS(W_, NPH_, 3) KAO_EMU_RACKS(W_, NPH_, 6)
+    KAO_EMU_NARROW(1, 3) KAO_EMU_NARROW(1, 5) KAO_EMU_NARROW(2, 3) KAO_EMU_NARROW(2, 5)
+    KAO_EMU_RACKS(4, 3, 0) KAO_EMU_RACKS(4, 5, 0) KAO_EMU_RACKS(8, 3, 0) KAO_EMU_RACKS(8, 5, 0)
+    fprintf(stderr, "kao_emu: no evaluator configuration W=%d NPH=%d rack=%d obj=%d\n", e.hm.W, e.nph, e.rack, e.obj);
+    abort();
+    return f(Run<EvalCfg<1, 3, 0, 0>>{});
+}
+
+thread_local std::string g_err;
+
+}  // namespace
+
+extern "C" {
+
+const char *kao_emu_last_error(void) { return g_err.c_str(); }
+
+void *kao_emu_create(const kao_problem *pb)
+{
+    auto e = std::make_unique<Emu>();
+    if (!build_host_model(*pb, e->hm, g_err)) return nullptr;
+    HostModel &m = e->hm;
+    // kao_create: do mask planes + one-hot plane fit next to the base, else packed entries
+    const int threads = m.W <= 2 ? 768 : 256;
+    SmemPlan plan = make_plan(m.W, m.Ppad, threads / 32, m.nplanes > 0 ? m.nplanes * m.W : 4, m.P, m.RF, m.nplanes > 0);
+    if (plan.total > 227u * 1024u && m.nplanes > 0) {
+        m.nplanes = 0;
+        plan = make_plan(m.W, m.Ppad, threads / 32, 4, m.P, m.RF, false);
+    }
+    if (plan.total > 227u * 1024u) { g_err = "problem too large for the shared-memory resident search kernel"; return nullptr; }
+    e->nph = (m.Ppad / 32 <= 63) ? 3 : 5;
+    e->rack = !m.hi1 ? 0 : (m.log2S == 3 ? 3 : (m.log2S == 4 ? 4 : 5));
+    e->obj = (m.W <= 2 && (m.nplanes == 3 || m.nplanes == 6)) ? m.nplanes : 0;
+    e->oh = m.W <= 2 && e->obj > 0;
+    fill_consts(m, e->cs);
+    Params &p = e->prm;
+    p.P = m.P; p.Ppad = m.Ppad; p.B = m.B; p.R = m.R; p.RF = m.RF; p.NS = m.NS; p.log2S = m.log2S;
+    p.ppr_lo = m.ppr_lo; p.ppr_hi = m.ppr_hi; p.dense = m.dense ? 1 : 0;
+    p.nentries = m.nentries; p.nplanes = m.nplanes; p.plane_on_leader = m.plane_on_leader;
+    for (int c = 0; c < 6; ++c) p.plane_value[c] = m.plane_value[c];
+    p.swT = m.swT.data();
+    p.planesT = m.nplanes > 0 ? m.planesT.data() : nullptr;
+    p.dense_w = m.dense ? m.dense_w.data() : nullptr;
+    p.homeT = m.homeT.data();
+    p.consts = &e->cs;
+    e->D.assign(m.Ppad, 0);
+    e->DL.assign(m.Ppad, 0);
+    e->prow.assign((size_t)kMaxOps * m.W, 0);
+    std::vector<uint32_t> bitsT;
+    std::vector<uint8_t> leader;
+    initial_base(m, bitsT, leader);
+    set_base(*e, bitsT, leader);
+    return e.release();
+}
+
+void kao_emu_destroy(void *h) { delete static_cast<Emu *>(h); }
+
+// 4 ints: words per row, counter planes above the fours (NPH), rack form, objective planes
+void kao_emu_config(void *h, int32_t *out)
+{
+    Emu &e = *static_cast<Emu *>(h);
+    out[0] = e.hm.W; out[1] = e.nph; out[2] = e.rack; out[3] = e.obj;
+}
+
+void kao_emu_set_base(void *h, const int32_t *replicas)
+{
+    Emu &e = *static_cast<Emu *>(h);
+    std::vector<uint32_t> bitsT;
+    std::vector<uint8_t> leader;
+    encode_replicas(e.hm, replicas, bitsT, leader);
+    set_base(e, bitsT, leader);
+}
+
+// replica lists of the base and its evaluation as the identity candidate of the search evaluator
+void kao_emu_get_base(void *h, int32_t *replicas, int64_t *violation, int64_t *objective, int32_t *moves)
+{
+    Emu &e = *static_cast<Emu *>(h);
+    std::vector<uint32_t> bitsT(e.bits.begin(), e.bits.begin() + (size_t)e.hm.W * e.hm.Ppad);
+    decode_replicas(e.hm, bitsT, e.leader, replicas);
+    if (moves) *moves = count_moves(e.hm, replicas);
+    // idx + 1 == round_size is the identity candidate (docs/MODEL.md §5)
+    const unsigned long long k = dispatch(e, [&](auto r) { return decltype(r)::key(e, 0, 0, 1, 2); });
+    if (violation) *violation = (int64_t)(k >> 48);
+    if (objective) *objective = (int64_t)(kObjCap - (uint32_t)((k >> kIdxBits) & kObjCap));
+}
+
+void kao_emu_candidate_keys(void *h, uint64_t seed, uint32_t round, uint32_t round_size, uint32_t idx_begin,
+                            uint32_t count, uint64_t *keys)
+{
+    Emu &e = *static_cast<Emu *>(h);
+    dispatch(e, [&](auto r) {
+        for (uint32_t i = 0; i < count; ++i) keys[i] = decltype(r)::key(e, seed, round, idx_begin + i, round_size);
+        return 0;
+    });
+}
+
+// whole rounds: argmin of the keys, the winner becomes the base (kao_search, one GPU, no early stop)
+void kao_emu_search(void *h, uint64_t seed, uint32_t first_round, uint32_t rounds, uint32_t round_size, uint64_t *round_keys)
+{
+    Emu &e = *static_cast<Emu *>(h);
+    dispatch(e, [&](auto r) {
+        for (uint32_t t = 0; t < rounds; ++t) {
+            unsigned long long best = kKeyNone;
+            for (uint32_t idx = 0; idx < round_size; ++idx) best = std::min(best, decltype(r)::key(e, seed, first_round + t, idx, round_size));
+            if (round_keys) round_keys[t] = best;
+            if (best != kKeyNone) decltype(r)::apply(e, seed, first_round + t, (uint32_t)(best & kIdxMask), round_size);
+        }
+        return 0;
+    });
+}
+
+// delta mode keys (rows of up to 64 slots): totals of the base as the kernel builds them per round
+int kao_emu_candidate_keys_delta(void *h, uint64_t seed, uint32_t round, uint32_t round_size, uint32_t idx_begin,
+                                 uint32_t count, uint64_t *keys)
+{
+    Emu &e = *static_cast<Emu *>(h);
+    const HostModel &m = e.hm;
+    if (m.W > 2) { g_err = "delta evaluation: rows of up to 64 slots"; return -1; }
+    std::vector<int> cnt(256, 0), lcnt(256, 0), rc(32 + 4, 0);
+    for (int p = 0; p < m.P; ++p) {
+        const int ld = e.leader[p];
+        bool ok = false;
+        for (int w = 0; w < m.W; ++w) {
+            const uint32_t xw = e.bits[(size_t)w * m.Ppad + p];
+            for (uint32_t b = xw; b; b &= b - 1) {
+                const int sl = w * 32 + __ffs(b) - 1;
+                ++cnt[sl];
+                ++rc[sl >> m.log2S];
+            }
+            if ((ld >> 5) == w) ok = (xw >> (ld & 31)) & 1u;
+        }
+        if (ok) ++lcnt[ld];
+    }
+    int64_t bv, bo;
+    std::vector<int32_t> reps((size_t)m.P * m.RF);
+    kao_emu_get_base(h, reps.data(), &bv, &bo, nullptr);
+    dispatch(e, [&](auto r) {
+        for (uint32_t i = 0; i < count; ++i)
+            keys[i] = decltype(r)::key_delta(e, seed, round, idx_begin + i, round_size, cnt.data(), lcnt.data(), rc.data(), (int)bv, (int)bo);
+        return 0;
+    });
+    return 0;
+}
+
+// explicit candidates (kao_eval / eval_batch_kernel): replicas [n][P*RF]
+void kao_emu_eval(void *h, const int32_t *replicas, int32_t n, int64_t *violation, int64_t *objective)
+{
+    Emu &e = *static_cast<Emu *>(h);
+    const HostModel &m = e.hm;
+    for (int i = 0; i < n; ++i) {
+        std::vector<uint32_t> cb;
+        std::vector<uint8_t> cl;
+        encode_replicas(m, replicas + (size_t)i * m.P * m.RF, cb, cl);
+        long long v = 0, o = 0;
+        switch (m.W) {
+        case 1: eval_explicit<1>(e, cb.data(), cl.data(), v, o); break;
+        case 2: eval_explicit<2>(e, cb.data(), cl.data(), v, o); break;
+        case 4: eval_explicit<4>(e, cb.data(), cl.data(), v, o); break;
+        default: eval_explicit<8>(e, cb.data(), cl.data(), v, o); break;
+        }
+        violation[i] = v;
+        objective[i] = o;
+    }
+}
+
+}  // extern "C"
