@@ -699,6 +699,7 @@ constexpr int kMaxWPlanes = 6;
 
 template <int W_, int NPH_, int kRack_, int kObj_> struct EvalCfg {
     static constexpr int W = W_, NPH = NPH_, kObj = kObj_, kRack = kRack_;
+    static constexpr bool kTrans = false;      // true: column-major evaluator, kao_device_t.cuh
 };
 // The search kernels keep a leader one-hot plane [W][Ppad] right behind the shared-memory bit-plane
 // for narrow rows scored with mask planes (the leader bytes are then not read by the evaluator).

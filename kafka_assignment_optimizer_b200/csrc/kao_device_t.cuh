@@ -1,0 +1,256 @@
+// kao_device_t.cuh — column-major ("transposed") full evaluator of one candidate by one warp.
+//
+// Same result as eval_candidate (kao_device.cuh, docs/MODEL.md §3) for the layout class of the
+// headline configuration: rows of up to 64 slots, 8-slot rack fields, "at most one replica of a
+// partition per rack" (C7 bounds 0..1), three weighted mask planes.  The base is ALSO kept transposed
+// in shared memory: for every slot s a bitmap over the partitions (32 per word).  Five planes:
+//   q = 0  replicas            T0[s] bit p  <=>  partition p has a replica on slot s
+//   q = 1  leader one-hot      T1[s] bit p  <=>  ... and is led from s
+//   q = 2,3,4  objective masks Mc[s] bit p  <=>  row-major mask plane c of partition p has bit s
+// The evaluation walks this matrix twice, each time with all data of a constraint inside one lane:
+//   rows     (C1, C7)  a lane owns 32 PARTITIONS (one word of every slot): a carry-save counter
+//            network over the slot words gives the bit-sliced replica count n_p of its partitions and
+//            the bit-sliced count z_p of non-empty rack fields; rows with n = z = RF cost nothing more
+//            (no POPC per row), the others are charged |n - RF| + (n - z) one by one;
+//   columns  (C2-C6, objective)  a lane owns one SLOT per row word: replica and leader totals of its
+//            columns are plain popcount sums — no bit-sliced counters, no cross-lane reduce-scatter —
+//            and the objective is popc(column & mask column).
+// The candidate's <= 3 patched rows are substituted while loading (columns) / skipped and scored
+// from the patch itself (rows), so every row of the candidate is evaluated, none is taken from a
+// previous evaluation.  Model: /root/reference/README.md:144-185.
+#pragma once
+#include "kao_device.cuh"
+
+namespace kao {
+
+template <int W_> struct EvalCfgT {
+    static constexpr int W = W_, NPH = 3, kRack = 3, kObj = 3;
+    static constexpr bool kTrans = true;
+};
+constexpr int kTPlanes = 5;
+
+// physical word of (plane q, slot s, partition word w).  Rows are rotated by 4 * (s & 7) words so
+// that the 128-bit column loads of a quarter warp (8 consecutive slots) hit 8 different bank groups;
+// the 32-bit row loads of a warp (32 consecutive words of one slot) stay conflict-free.
+__host__ __device__ __forceinline__ int t_word(int q, int s, int w, int nW, int NSL)
+{
+    int t = w + (nW >= 32 ? 4 * (s & 7) : 0);
+    t -= (t >= nW) ? nW : 0;
+    return (q * NSL + s) * nW + t;
+}
+
+// ------------------------------------------------------------------------------------------
+// rows: C1 + C7 of every partition that is not patched, bit-sliced over 32 partitions per lane
+// ------------------------------------------------------------------------------------------
+template <int W, bool kShared>
+__device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, int nW, int P, int RF, int lane, const PatchSet &ps)
+{
+    constexpr int NB = 4 * W;                       // 8-slot blocks = rack fields
+    int viol = 0;
+    const uint32_t rf0 = (RF & 1) ? ~0u : 0u, rf1 = (RF & 2) ? ~0u : 0u, rf2 = (RF & 4) ? ~0u : 0u, rf3 = (RF & 8) ? ~0u : 0u;
+#pragma unroll 1
+    for (int w = lane; w < nW; w += 32) {
+        const int left = P - 32 * w;                // partitions of this word that exist
+        uint32_t valid = left >= 32 ? ~0u : (left <= 0 ? 0u : ((1u << left) - 1u));
+#pragma unroll
+        for (int i = 0; i < kMaxOps; ++i)           // unused patches hold -1: (-1 >> 5) never equals w
+            valid &= ((ps.p[i] >> 5) == w) ? ~(1u << (ps.p[i] & 31)) : ~0u;
+        int tk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int t = w + (nW >= 32 ? 4 * k : 0);
+            t -= (t >= nW) ? nW : 0;
+            tk[k] = t;
+        }
+        uint32_t ones = 0, twos = 0, fours = 0;     // n_p, weights 1 2 4
+        uint32_t e1 = 0, e2 = 0, e4 = 0, e8 = 0;    // n_p, weights 8 16 32 64
+        uint32_t z1 = 0, z2 = 0, z4 = 0, z8 = 0;    // non-empty fields of p, 0..8
+#pragma unroll
+        for (int b = 0; b < NB; b += 2) {
+            uint32_t o8[2], ne[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t x[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = T.ld32((uint32_t)(((b + h) * 8 + k) * nW + tk[k]) * 4u);
+                uint32_t a2, b2, qa, qb;
+                csa(a2, ones, ones, x[0], x[1]);
+                csa(b2, ones, ones, x[2], x[3]);
+                csa(qa, twos, twos, a2, b2);
+                csa(a2, ones, ones, x[4], x[5]);
+                csa(b2, ones, ones, x[6], x[7]);
+                csa(qb, twos, twos, a2, b2);
+                csa(o8[h], fours, fours, qa, qb);
+                ne[h] = (x[0] | x[1] | x[2]) | (x[3] | x[4] | x[5]) | (x[6] | x[7]);
+            }
+            uint32_t c16, c;
+            csa(c16, e1, e1, o8[0], o8[1]);
+            c = e2 & c16; e2 ^= c16;
+            c16 = e4 & c; e4 ^= c;
+            e8 ^= c16;
+            uint32_t y2;
+            csa(y2, z1, z1, ne[0], ne[1]);
+            c = z2 & y2; z2 ^= y2;
+            y2 = z4 & c; z4 ^= c;
+            z8 ^= y2;
+        }
+        // partitions whose replica count or non-empty field count is not RF (RF <= 8)
+        uint32_t bad = (ones ^ rf0) | (twos ^ rf1) | (fours ^ rf2) | (e1 ^ rf3) | e2 | e4 | e8;
+        bad |= (z1 ^ rf0) | (z2 ^ rf1) | (z4 ^ rf2) | (z8 ^ rf3);
+        bad &= valid;
+        for (uint32_t m = bad; m; m &= m - 1) {
+            const int s = __ffs(m) - 1;
+            const int n = (int)(((ones >> s) & 1u) | (((twos >> s) & 1u) << 1) | (((fours >> s) & 1u) << 2) |
+                                (((e1 >> s) & 1u) << 3) | (((e2 >> s) & 1u) << 4) | (((e4 >> s) & 1u) << 5) |
+                                (((e8 >> s) & 1u) << 6));
+            const int z = (int)(((z1 >> s) & 1u) | (((z2 >> s) & 1u) << 1) | (((z4 >> s) & 1u) << 2) | (((z8 >> s) & 1u) << 3));
+            viol += abs(n - RF) + (n - z);
+        }
+    }
+    return viol;
+}
+
+// C1 + C7 of one row held row-major (a patched row of the candidate): same terms as row_rack_terms<W, 3>
+template <int W> __device__ __forceinline__ int row_terms_hi1_s8(const uint32_t (&x)[W], int RF)
+{
+    int n = 0, nz = 0;
+#pragma unroll
+    for (int t = 0; t < W; ++t) {
+        n += __popc(x[t]);
+        nz += __popc((((x[t] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x[t]) & 0x80808080u);
+    }
+    return abs(n - RF) + (n - nz);
+}
+
+__device__ __forceinline__ void set_comp(uint4 &v, int k, uint32_t clear, uint32_t set)
+{
+    if (k == 0) v.x = (v.x & ~clear) | set;
+    else if (k == 1) v.y = (v.y & ~clear) | set;
+    else if (k == 2) v.z = (v.z & ~clear) | set;
+    else v.w = (v.w & ~clear) | set;
+}
+
+// ------------------------------------------------------------------------------------------
+// the whole candidate.  T: the five transposed planes; prow: this warp's patched rows [kMaxOps * W]
+// ------------------------------------------------------------------------------------------
+template <int W, bool kShared>
+__device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW, const Consts *cs, const PatchSet &ps,
+                                 const uint32_t *prow, int lane, int &viol_out, int &obj_out)
+{
+    constexpr int NSL = 32 * W;
+    const MemRef<kShared> T(Tp);
+    // ---- rows: unpatched partitions from the transposed bit-plane, patched ones from the patch
+    int viol = rows_vertical<W, kShared>(T, nW, d.P, d.RF, lane, ps);
+    if (lane < kMaxOps) {
+        const int i = lane;
+        const int pp = i == 0 ? ps.p[0] : (i == 1 ? ps.p[1] : ps.p[2]);
+        if (pp >= 0) {
+            uint32_t x[W];
+#pragma unroll
+            for (int t = 0; t < W; ++t) x[t] = prow[i * W + t];
+            viol += row_terms_hi1_s8<W>(x, d.RF);
+        }
+    }
+    // ---- columns: this lane owns slot `lane` of every row word
+    int cnt[W], lcnt[W], o0 = 0, o1 = 0, o2 = 0;
+#pragma unroll
+    for (int t = 0; t < W; ++t) cnt[t] = lcnt[t] = 0;
+    const int rot = nW >= 32 ? 4 * (lane & 7) : 0;
+    const int nch = nW >> 2;
+#pragma unroll 1
+    for (int j = 0; j < nch; ++j) {
+        int tw = 4 * j + rot;
+        tw -= (tw >= nW) ? nW : 0;
+        uint4 col[W], oh[W], m0[W], m1[W], m2[W];
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const int s = lane + 32 * t;
+            col[t] = T.ld128((uint32_t)((0 * NSL + s) * nW + tw) * 4u);
+            oh[t] = T.ld128((uint32_t)((1 * NSL + s) * nW + tw) * 4u);
+            m0[t] = T.ld128((uint32_t)((2 * NSL + s) * nW + tw) * 4u);
+            m1[t] = T.ld128((uint32_t)((3 * NSL + s) * nW + tw) * 4u);
+            m2[t] = T.ld128((uint32_t)((4 * NSL + s) * nW + tw) * 4u);
+        }
+        // the candidate's patched rows replace their partition's bit in this lane's columns
+        if (((ps.p[0] >> 7) == j) | ((ps.p[1] >> 7) == j) | ((ps.p[2] >> 7) == j)) {
+#pragma unroll
+            for (int i = 0; i < kMaxOps; ++i) {
+                const int pp = ps.p[i];
+                if ((pp >> 7) == j) {
+                    const int k = (pp >> 5) & 3;
+                    const uint32_t bit = 1u << (pp & 31);
+#pragma unroll
+                    for (int t = 0; t < W; ++t) {
+                        const bool has = (prow[i * W + t] >> lane) & 1u;
+                        const bool led = has && ((int)ps.ld[i] == lane + 32 * t);
+                        set_comp(col[t], k, bit, has ? bit : 0u);
+                        set_comp(oh[t], k, bit, led ? bit : 0u);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t hit = 0;                       // leader bonus: the one-hot columns of a lane are disjoint
+#pragma unroll
+            for (int t = 0; t < W; ++t) {
+                const uint32_t c = comp(col[t], i), o = comp(oh[t], i);
+                cnt[t] += __popc(c);
+                lcnt[t] += __popc(o);
+                o0 += __popc(c & comp(m0[t], i));
+                o1 += __popc(c & comp(m1[t], i));
+                hit |= o & comp(m2[t], i);
+            }
+            o2 += __popc(hit);
+        }
+    }
+    // ---- C3 / C4 on this lane's columns, C2/C5 as P - sum of valid leaders, C6 per 8-lane rack group
+#pragma unroll
+    for (int t = 0; t < W; ++t) {
+        const int s = lane + 32 * t;
+        viol += band_violation(cnt[t], cs->bnd_rep[s]) + band_violation(lcnt[t], cs->bnd_ldr[s]) - lcnt[t];
+        const int tot = __reduce_add_sync(0xFFu << (lane & 24), cnt[t]);
+        const int rk = s >> 3;
+        if ((lane & 7) == 0 && rk < d.R) viol += max(tot - cs->rack_hi[rk], 0) + max(cs->rack_lo[rk] - tot, 0);
+    }
+    const int obj = o0 * d.plane_value[0] + o1 * d.plane_value[1] + o2 * d.plane_value[2];
+    viol_out = __reduce_add_sync(0xFFFFFFFFu, viol) + d.P;
+    obj_out = __reduce_add_sync(0xFFFFFFFFu, obj);
+}
+
+// ------------------------------------------------------------------------------------------
+// keeping the transposed planes in step with the row-major base (search kernels; tests/emu)
+// ------------------------------------------------------------------------------------------
+// one word (32 partitions) of plane q, slot s, gathered from the row-major tables
+template <int W>
+__device__ __forceinline__ uint32_t t_gather(int q, int s, int w, const uint32_t *bitsT, const uint8_t *leader,
+                                             const uint32_t *planesT, int Ppad)
+{
+    uint32_t out = 0;
+    const int sw = s >> 5, sb = s & 31;
+    for (int b = 0; b < 32; ++b) {
+        const int p = 32 * w + b;
+        uint32_t bit;
+        if (q == 0) bit = (bitsT[(size_t)sw * Ppad + p] >> sb) & 1u;
+        else if (q == 1) bit = ((bitsT[(size_t)sw * Ppad + p] >> sb) & 1u) & ((int)leader[p] == s ? 1u : 0u);
+        else bit = (planesT[((size_t)(q - 2) * W + sw) * Ppad + p] >> sb) & 1u;
+        out |= bit << b;
+    }
+    return out;
+}
+// row p of the base changes from (oldrow, oldld) to (newrow, newld): planes 0 and 1 follow
+template <int W>
+__device__ __forceinline__ void t_patch_row(uint32_t *T, int nW, int p, const uint32_t (&oldrow)[W], uint32_t oldld,
+                                            const uint32_t (&newrow)[W], uint32_t newld)
+{
+    constexpr int NSL = 32 * W;
+    const int w = p >> 5;
+    const uint32_t bit = 1u << (p & 31);
+#pragma unroll
+    for (int t = 0; t < W; ++t)
+        for (uint32_t m = oldrow[t] ^ newrow[t]; m; m &= m - 1) T[t_word(0, 32 * t + __ffs(m) - 1, w, nW, NSL)] ^= bit;
+    if ((int)oldld < NSL && row_has<W>(oldrow, (int)oldld)) T[t_word(1, (int)oldld, w, nW, NSL)] &= ~bit;
+    if ((int)newld < NSL && row_has<W>(newrow, (int)newld)) T[t_word(1, (int)newld, w, nW, NSL)] |= bit;
+}
+
+}  // namespace kao

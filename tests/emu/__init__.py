@@ -45,6 +45,10 @@ class EmuSession:
         lib().kao_emu_config(self._h, out)
         return dict(W=out[0], NPH=out[1], rack=out[2], obj=out[3])
 
+    def set_evaluator(self, mode):
+        """1: column-major evaluator (csrc/kao_device_t.cuh); False is returned for unsupported layouts."""
+        return lib().kao_emu_set_evaluator(self._h, C.c_int32(mode)) == 0
+
     def set_base(self, replicas):
         reps = np.ascontiguousarray(replicas, dtype=np.int32)
         lib().kao_emu_set_base(self._h, C.c_void_p(reps.ctypes.data))

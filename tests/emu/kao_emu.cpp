@@ -9,6 +9,7 @@
 #include "warp_emu.hpp"
 
 #include "../../kafka_assignment_optimizer_b200/csrc/kao_device.cuh"
+#include "../../kafka_assignment_optimizer_b200/csrc/kao_device_t.cuh"
 #include "../../kafka_assignment_optimizer_b200/csrc/kao_plan.hpp"
 #include "../../kafka_assignment_optimizer_b200/csrc/kao_host.hpp"
 
@@ -32,8 +33,22 @@ struct Emu {
     std::vector<uint16_t> D, DL;
     int nD = 0, nL = 0;
     std::vector<uint32_t> prow;          // [kMaxOps * W]
+    // column-major evaluator (kao_device_t.cuh): supported shape, in use, the five transposed planes
+    bool trans_ok = false, trans = false;
+    int nW = 0;
+    std::vector<uint32_t> T;
     std::string err;
 };
+
+template <int W> void build_T(Emu &e)
+{
+    const HostModel &m = e.hm;
+    e.T.assign((size_t)kTPlanes * 32 * W * e.nW, 0);
+    for (int q = 0; q < kTPlanes; ++q)
+        for (int s = 0; s < 32 * W; ++s)
+            for (int w = 0; w < e.nW; ++w)
+                e.T[t_word(q, s, w, e.nW, 32 * W)] = t_gather<W>(q, s, w, e.bits.data(), e.leader.data(), m.planesT.data(), m.Ppad);
+}
 
 uint32_t oh_word(uint32_t x, uint32_t ld, int w) { return ((int)(ld >> 5) == w) ? (x & (1u << (ld & 31u))) : 0u; }
 
@@ -71,6 +86,7 @@ void set_base(Emu &e, const std::vector<uint32_t> &bitsT, const std::vector<uint
     e.prm.bitsT = e.bits.data();
     e.prm.leader = e.leader.data();
     rebuild_lists(e);
+    if (e.trans_ok) { if (m.W == 1) build_T<1>(e); else build_T<2>(e); }
 }
 
 template <class Cfg> struct Run {
@@ -95,7 +111,12 @@ template <class Cfg> struct Run {
             g.run(seed, round, idx, round_size, ps, no_rows);
             __syncwarp();                                     // __syncthreads() of the kernels
             int viol, obj;
-            eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
+            if constexpr (W <= 2) {
+                if (e.trans) eval_candidate_t<W, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
+                else eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
+            } else {
+                eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
+            }
             if (lane == 0) out = pack_key(viol, obj, idx);
         });
         return out;
@@ -113,6 +134,13 @@ template <class Cfg> struct Run {
         });
         const int Ppad = e.hm.Ppad;
         for (int i = 0; i < win.n; ++i) {
+            if constexpr (W <= 2) {
+                if (e.trans_ok) {                   // as the kernel does: transposed planes first, from the old row
+                    uint32_t oldrow[W], newrow[W];
+                    for (int w = 0; w < W; ++w) { oldrow[w] = e.bits[(size_t)w * Ppad + win.p[i]]; newrow[w] = e.prow[i * W + w]; }
+                    t_patch_row<W>(e.T.data(), e.nW, win.p[i], oldrow, e.leader[win.p[i]], newrow, win.ld[i]);
+                }
+            }
             for (int w = 0; w < W; ++w) {
                 const uint32_t v = e.prow[i * W + w];
                 e.bits[(size_t)w * Ppad + win.p[i]] = v;
@@ -200,6 +228,10 @@ void *kao_emu_create(const kao_problem *pb)
     e->rack = !m.hi1 ? 0 : (m.log2S == 3 ? 3 : (m.log2S == 4 ? 4 : 5));
     e->obj = (m.W <= 2 && (m.nplanes == 3 || m.nplanes == 6)) ? m.nplanes : 0;
     e->oh = m.W <= 2 && e->obj > 0;
+    // kao_set_evaluator: the column-major evaluator covers 8-slot rack fields with C7 = "at most one
+    // replica per rack" and three mask planes
+    e->trans_ok = m.W <= 2 && m.hi1 && m.log2S == 3 && m.nplanes == 3;
+    e->nW = m.Ppad / 32;
     fill_consts(m, e->cs);
     Params &p = e->prm;
     p.P = m.P; p.Ppad = m.Ppad; p.B = m.B; p.R = m.R; p.RF = m.RF; p.NS = m.NS; p.log2S = m.log2S;
@@ -219,6 +251,14 @@ void *kao_emu_create(const kao_problem *pb)
     initial_base(m, bitsT, leader);
     set_base(*e, bitsT, leader);
     return e.release();
+}
+
+int kao_emu_set_evaluator(void *h, int32_t mode)
+{
+    Emu &e = *static_cast<Emu *>(h);
+    if (mode != 0 && !e.trans_ok) { g_err = "column-major evaluator: unsupported layout"; return -1; }
+    e.trans = mode != 0;
+    return 0;
 }
 
 void kao_emu_destroy(void *h) { delete static_cast<Emu *>(h); }
