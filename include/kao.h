@@ -80,6 +80,8 @@ typedef struct kao_options {
 } kao_options;
 
 #define KAO_FLAG_DELTA 0x100u
+#define KAO_FLAG_COLUMN_MAJOR 0x200u  /* full evaluation by the column-major evaluator where the layout allows it
+                                         (see kao_set_evaluator); same keys, same result, a performance choice */
 #define KAO_FLAG_PATIENCE(n) ((uint32_t)(n) << 16)  /* stop a search after n (<= 65535) rounds without a better key */
 
 typedef struct kao_result {
@@ -139,6 +141,17 @@ int kao_candidate_keys_delta(kao_handle *h, uint64_t seed, uint32_t round, uint3
  * (violation, objective); 0 = run all rounds.  The decision depends only on the round keys, so all
  * ranks of a sharded search stop together.  kao_last_rounds: rounds the last search actually ran. */
 int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
+
+/* Full-evaluation kernel used by kao_search / kao_search_sharded / kao_candidate_keys of this session.
+ * Both evaluate every row and column of every candidate (C1..C7 + objective, README.md:144-185) and
+ * return bit-identical keys; they differ in how the base is laid out in shared memory:
+ *   KAO_EVAL_ROW_MAJOR     rows of the (partition x broker) bit-plane, column totals by bit-sliced counters (default)
+ *   KAO_EVAL_COLUMN_MAJOR  also one bitmap over the partitions per broker slot; needs rows of up to 64
+ *                          slots, racks of up to 8 brokers, C7 = at most one replica per rack, three
+ *                          objective mask planes; KAO_E_ARG otherwise */
+#define KAO_EVAL_ROW_MAJOR 0
+#define KAO_EVAL_COLUMN_MAJOR 1
+int kao_set_evaluator(kao_handle *h, int32_t evaluator);
 int kao_last_rounds(kao_handle *h, uint32_t *rounds_run);
 
 /* keys of candidates idx_begin .. idx_begin+count-1 of `round` against the current base (host

@@ -703,7 +703,7 @@ template <int W_, int NPH_, int kRack_, int kObj_> struct EvalCfg {
 };
 // The search kernels keep a leader one-hot plane [W][Ppad] right behind the shared-memory bit-plane
 // for narrow rows scored with mask planes (the leader bytes are then not read by the evaluator).
-template <class Cfg> __host__ __device__ constexpr bool has_oh_plane() { return Cfg::W <= 2 && Cfg::kObj > 0; }
+template <class Cfg> __host__ __device__ constexpr bool has_oh_plane() { return Cfg::W <= 2 && Cfg::kObj > 0 && !Cfg::kTrans; }
 
 
 // Loads one 128-row tile of the candidate: 4 consecutive rows per lane (128-bit shared-memory

@@ -27,6 +27,8 @@ KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 4, 3) KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 4, 5)
 KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 8, 3) KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 8, 5)
 KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 1, 3) KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 1, 5)
 KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 2, 3) KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 2, 5)
+extern template __global__ void KAO_PERSISTENT_KERNEL_T(1);     // column-major evaluator, kao_device_t.cuh
+extern template __global__ void KAO_PERSISTENT_KERNEL_T(2);
 
 
 // Winner of a round becomes the base: re-materialise its patches from (seed, round, index), write
@@ -141,6 +143,10 @@ struct kao_handle {
     Params prm{};
     SmemPlan plan{};
     int threads = 0, grid = 0;
+    // column-major full evaluator (kao_set_evaluator): layout supported, selected, its shared-memory plan
+    bool trans_ok = false;
+    int evaluator = KAO_EVAL_ROW_MAJOR;
+    SmemPlan plan_t{};
     // device buffers
     uint32_t *d_bits = nullptr; uint8_t *d_leader = nullptr; uint32_t *d_sw = nullptr;
     uint32_t *d_dense = nullptr; uint32_t *d_planes = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
@@ -217,7 +223,7 @@ template <bool kDelta> struct LaunchPersistent {
             static bool done[64] = {};
             cudaError_t e = set_smem_attr<Cfg>(h, reinterpret_cast<const void *>(kern), done);
             if (e != cudaSuccess) return e;
-            Params prm = h->prm; SmemPlan plan = h->plan;
+            Params prm = h->prm; SmemPlan plan = Cfg::kTrans ? h->plan_t : h->plan;
             uint64_t seed = a.seed; uint32_t fr = a.first_round, rounds = a.rounds, rs = a.round_size;
             unsigned long long *keys = a.d_keys, *all = a.all_keys; unsigned int *bar = a.d_bar;
             P2P pp = a.pp;
@@ -225,7 +231,7 @@ template <bool kDelta> struct LaunchPersistent {
             ++h->launches;
             // cooperative launch: all CTAs are guaranteed co-resident, which the grid barrier needs
             return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(h->grid), dim3(T), args,
-                                               h->plan.total, a.st);
+                                               plan.total, a.st);
         }
     }
 };
@@ -259,6 +265,15 @@ template <class F, class A> static cudaError_t dispatch(kao_handle *h, const F &
     case 4: return small ? dispatch_w<4, 3>(h, f, a) : dispatch_w<4, 5>(h, f, a);
     default: return small ? dispatch_w<8, 3>(h, f, a) : dispatch_w<8, 5>(h, f, a);
     }
+}
+// all rounds of a search in one cooperative launch, with the evaluator the session selected
+static cudaError_t launch_persistent(kao_handle *h, const PersistArgs &pa, bool delta)
+{
+    if (delta) return dispatch(h, LaunchPersistent<true>{}, pa);
+    if (h->evaluator == KAO_EVAL_COLUMN_MAJOR)
+        return h->hm.W == 1 ? LaunchPersistent<false>{}.template run<EvalCfgT<1>>(h, pa)
+                            : LaunchPersistent<false>{}.template run<EvalCfgT<2>>(h, pa);
+    return dispatch(h, LaunchPersistent<false>{}, pa);
 }
 static cudaError_t launch_round(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
                                 uint32_t lo, uint32_t hi, unsigned long long *d_key,
@@ -334,6 +349,10 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     }
     if (h->plan.total > 227u * 1024u)
         return fail(KAO_E_ARG, "problem too large for the shared-memory resident search kernel");
+    // column-major evaluator: 8-slot rack fields, C7 = "at most one replica per rack", three mask planes;
+    // its five transposed planes (5 * W words per partition) take the place of the objective table
+    h->plan_t = make_plan(W, Ppad, h->threads / 32, kTPlanes * W, m.P, m.RF, false);
+    h->trans_ok = W <= 2 && m.hi1 && m.log2S == 3 && h->hm.nplanes == 3 && h->plan_t.total <= 227u * 1024u;
     h->grid = h->sms;
     CUDA_TRY(dalloc(h, &h->d_bits, (size_t)W * Ppad * 4));
     CUDA_TRY(dalloc(h, &h->d_leader, (size_t)Ppad));
@@ -501,8 +520,7 @@ static int search_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint3
         pp.rank = 0; pp.world = 1; pp.idx_lo = 0; pp.idx_hi = round_size;
         pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
         pp.patience = h->patience; pp.rounds_run = h->d_bar + 3;
-        CUDA_TRY((delta ? dispatch(h, LaunchPersistent<true>{}, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0, pp, nullptr})
-                       : dispatch(h, LaunchPersistent<false>{}, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0, pp, nullptr})));
+        CUDA_TRY(launch_persistent(h, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0, pp, nullptr}, delta));
         CUDA_TRY(launch_apply(h, seed, first_round, round_size, h->d_keys, /*regen_only=*/1, 0));
     }
     CUDA_TRY(cudaEventRecord(h->ev1, 0));
@@ -521,6 +539,17 @@ static int search_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint3
     }
     if (round_keys && rounds)
         CUDA_TRY(cudaMemcpy(round_keys, h->d_keys, (size_t)rounds * 8, cudaMemcpyDeviceToHost));
+    return KAO_OK;
+}
+
+extern "C" int kao_set_evaluator(kao_handle *h, int32_t evaluator)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    if (evaluator != KAO_EVAL_ROW_MAJOR && evaluator != KAO_EVAL_COLUMN_MAJOR) return fail(KAO_E_ARG, "unknown evaluator");
+    if (evaluator == KAO_EVAL_COLUMN_MAJOR && !h->trans_ok)
+        return fail(KAO_E_ARG, "column-major evaluator: needs rows of up to 64 slots, racks of up to 8 brokers, at most one "
+                               "replica per rack (C7 0..1), three objective mask planes, and its planes in shared memory");
+    h->evaluator = evaluator;
     return KAO_OK;
 }
 
@@ -655,7 +684,7 @@ static int sharded_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint
         pp.lkeys = h->d_lkeys; pp.release = h->d_bar + 1; pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
         pp.patience = h->patience; pp.rounds_run = h->d_bar + 3;
         const PersistArgs pa{seed, first_round + done, n, round_size, h->d_keys + done, h->d_bar, 0, pp, nullptr};
-        CUDA_TRY(delta ? dispatch(h, LaunchPersistent<true>{}, pa) : dispatch(h, LaunchPersistent<false>{}, pa));
+        CUDA_TRY(launch_persistent(h, pa, delta));
         unsigned int st[4] = {0, 0, 0, 0};
         CUDA_TRY(cudaMemcpy(st, h->d_bar, 16, cudaMemcpyDeviceToHost));
         if (st[2]) return fail(KAO_E_CUDA, "sharded search timed out waiting for a peer GPU");
@@ -731,7 +760,18 @@ extern "C" int kao_candidate_keys(kao_handle *h, uint64_t seed, uint32_t round, 
     unsigned long long *d_all = nullptr;
     CUDA_TRY(cudaMalloc(&d_all, (size_t)count * 8));
     { const unsigned long long none = kKeyNone; CUDA_TRY(cudaMemcpy(h->d_key, &none, 8, cudaMemcpyHostToDevice)); }
-    cudaError_t e = launch_round(h, seed, round, round_size, idx_begin, idx_begin + count, h->d_key, d_all, 0);
+    cudaError_t e;
+    if (h->evaluator == KAO_EVAL_COLUMN_MAJOR) {
+        // the column-major evaluator lives in the persistent kernel only: one round, key dump, base untouched
+        e = h->d_bar ? cudaSuccess : dalloc(h, &h->d_bar, 16);
+        if (e == cudaSuccess) e = cudaMemset(h->d_bar, 0, 16);
+        P2P pp{};
+        pp.rank = 0; pp.world = 1; pp.idx_lo = idx_begin; pp.idx_hi = idx_begin + count;
+        pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
+        if (e == cudaSuccess) e = launch_persistent(h, PersistArgs{seed, round, 1, round_size, h->d_key, h->d_bar, 0, pp, d_all}, false);
+    } else {
+        e = launch_round(h, seed, round, round_size, idx_begin, idx_begin + count, h->d_key, d_all, 0);
+    }
     if (e == cudaSuccess) e = cudaMemcpy(keys, d_all, (size_t)count * 8, cudaMemcpyDeviceToHost);
     cudaFree(d_all);
     CUDA_TRY(e);
@@ -798,6 +838,8 @@ extern "C" int kao_solve(const kao_problem *pb, const kao_options *opt, kao_resu
     // initial base with its own seed; the best final assignment wins (violation, then objective)
     const uint32_t restarts = (opt->flags & 0xFFu) ? (opt->flags & 0xFFu) : 1u;
     h->patience = opt->flags >> 16;                             // KAO_FLAG_PATIENCE(n)
+    // a performance hint, not a different result: layouts the column-major evaluator does not cover keep the row-major one
+    if ((opt->flags & KAO_FLAG_COLUMN_MAJOR) && h->trans_ok) h->evaluator = KAO_EVAL_COLUMN_MAJOR;
     uint32_t rounds_run = 0;
     std::vector<uint64_t> keys(opt->rounds ? opt->rounds : 1, kKeyNone);
     std::vector<int32_t> reps((size_t)pb->P * pb->RF);

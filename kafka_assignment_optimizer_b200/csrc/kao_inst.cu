@@ -1,5 +1,6 @@
 // kao_inst.cu — explicit instantiations of the search kernels (kao_kernels.cuh) for ONE row width
-// (KAO_INST_W words), counter depth (KAO_INST_NPH high planes) and evaluation mode (KAO_INST_DELTA).
+// (KAO_INST_W words), counter depth (KAO_INST_NPH high planes) and evaluation mode (KAO_INST_DELTA;
+// KAO_INST_TRANS: the column-major evaluator).
 // The Makefile compiles this file once per combination; the objects build in parallel.
 #include "kao_kernels.cuh"
 
@@ -12,7 +13,10 @@
     template __global__ void KAO_PERSISTENT_KERNEL(W, NPH, R, O, threads_for<W>(), false);
 #define KAO_INST_DELTA_K(W, NPH, R, O) template __global__ void KAO_PERSISTENT_KERNEL(W, NPH, R, O, KAO_THREADS_DELTA, true);
 
-#if KAO_INST_DELTA
+#if defined(KAO_INST_TRANS) && KAO_INST_TRANS
+// column-major evaluator (kao_device_t.cuh): rows of up to 64 slots
+template __global__ void KAO_PERSISTENT_KERNEL_T(KAO_INST_W);
+#elif KAO_INST_DELTA
 #if KAO_INST_W > 2
 #error "delta evaluation: rows of up to 64 slots"
 #endif

@@ -6,6 +6,7 @@
 // translation units build in parallel and every one of them is compiled deterministically.
 #pragma once
 #include "kao_device.cuh"
+#include "kao_device_t.cuh"
 #include "kao_plan.hpp"
 
 #include <cstdint>
@@ -61,6 +62,22 @@ __device__ __forceinline__ void build_oh_plane(uint32_t *s_bits, const uint8_t *
         const uint32_t ld = s_leader[p];
 #pragma unroll
         for (int w = 0; w < W; ++w) s_bits[(size_t)(W + w) * Ppad + p] = oh_word<W>(s_bits[(size_t)w * Ppad + p], ld, w);
+    }
+    __syncthreads();
+}
+
+// Column-major evaluator (kao_device_t.cuh): the five transposed planes are gathered once per launch
+// from the staged row-major base and the row-major mask planes in HBM (L2); they take the place of
+// the objective table in the shared-memory plan (5 * W words per partition at off_sw).
+template <int W, int THREADS>
+__device__ __forceinline__ void build_t_planes(uint32_t *T, const uint32_t *s_bits, const uint8_t *s_leader,
+                                               const uint32_t *g_planes, int Ppad)
+{
+    constexpr int NSL = 32 * W;
+    const int nW = Ppad >> 5, total = kTPlanes * NSL * nW;
+    for (int o = threadIdx.x; o < total; o += THREADS) {
+        const int w = o % nW, s = (o / nW) % NSL, q = o / (nW * NSL);
+        T[t_word(q, s, w, nW, NSL)] = t_gather<W>(q, s, w, s_bits, s_leader, g_planes, Ppad);
     }
     __syncthreads();
 }
@@ -265,7 +282,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     constexpr int kWarps = THREADS / 32;
     constexpr int W = Cfg::W;
     const uint32_t *g_obj = Cfg::kObj > 0 ? d.planesT : d.swT;
-    const uint32_t obj_words = Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries;
+    const uint32_t obj_words = Cfg::kTrans ? 0u : (Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries);
 
     if (tid == 0) mbar_init(s_bar, 1);
     __syncthreads();
@@ -279,6 +296,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     }
     mbar_wait(s_bar, 0);
     if constexpr (has_oh_plane<Cfg>()) build_oh_plane<W, THREADS>(s_bits, s_leader, d.Ppad);
+    if constexpr (Cfg::kTrans) build_t_planes<W, THREADS>(s_sw, s_bits, s_leader, d.planesT, d.Ppad);
     rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
 
     Gen<W> gen;
@@ -401,11 +419,21 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             __syncthreads();
             if (live) {
                 int viol, obj;
-                eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
+                if constexpr (Cfg::kTrans) {
+                    eval_candidate_t<W, true>(d, s_sw, d.Ppad >> 5, s_cs, ps, gen.prow, lane, viol, obj);
+                } else {
+                    eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
+                }
                 const unsigned long long key = pack_key(viol, obj, idx);
+                if constexpr (Cfg::kTrans) {
+                    if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = key;
+                }
                 best = key < best ? key : best;
             }
             __syncwarp();
+        }
+        if constexpr (Cfg::kTrans) {
+            if (all_keys) return;                                   // key dump only: the base stays as it is
         }
         }
         if (lane == 0) s_red[warp] = best;
@@ -481,6 +509,15 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 #pragma unroll
                     for (int i = 0; i < kMaxOps; ++i) {
                         if (i < ps.n) {
+                            if constexpr (Cfg::kTrans) {            // transposed planes first: they need the old row
+                                uint32_t oldrow[W], newrow[W];
+#pragma unroll
+                                for (int w = 0; w < W; ++w) {
+                                    oldrow[w] = s_bits[(size_t)w * d.Ppad + ps.p[i]];
+                                    newrow[w] = gen.prow[i * W + w];
+                                }
+                                t_patch_row<W>(s_sw, d.Ppad >> 5, ps.p[i], oldrow, s_leader[ps.p[i]], newrow, ps.ld[i]);
+                            }
                             for (int w = 0; w < W; ++w) {
                                 const uint32_t v = gen.prow[i * W + w];
                                 s_bits[(size_t)w * d.Ppad + ps.p[i]] = v;
@@ -516,6 +553,10 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     search_round_kernel<EvalCfg<W, NPH, R, O>, threads_for<W>()>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
                                                                    uint32_t, uint32_t, unsigned long long *,      \
                                                                    unsigned long long *)
+#define KAO_PERSISTENT_KERNEL_T(W)                                                                          \
+    search_persistent_kernel<EvalCfgT<W>, threads_for<W>(), false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
+                                                                  uint32_t, unsigned long long *, unsigned int *, P2P, \
+                                                                  unsigned long long *)
 #define KAO_PERSISTENT_KERNEL(W, NPH, R, O, T, DELTA)                                                       \
     search_persistent_kernel<EvalCfg<W, NPH, R, O>, T, DELTA>(Params, SmemPlan, uint64_t, uint32_t, uint32_t,      \
                                                              uint32_t, unsigned long long *, unsigned int *, P2P, \

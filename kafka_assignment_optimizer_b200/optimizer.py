@@ -132,6 +132,18 @@ class Session:
         except Exception:
             pass
 
+    def set_evaluator(self, column_major: bool) -> bool:
+        """Selects the full-evaluation kernel of this session (kao_set_evaluator): row-major (default) or
+        column-major.  Same keys either way.  Returns False when the layout is not covered by the
+        column-major evaluator (the session then stays as it was)."""
+        rc = self._lib.kao_set_evaluator(self._h, C.c_int32(1 if column_major else 0))
+        if rc == KAO_OK:
+            return True
+        if column_major and rc == -1:           # KAO_E_ARG: unsupported layout
+            return False
+        _check(rc)
+        return False
+
     def set_patience(self, rounds_without_improvement: int):
         _check(self._lib.kao_set_patience(self._h, C.c_uint32(rounds_without_improvement)))
 
@@ -243,12 +255,12 @@ class Session:
 
 def solve(pb: Problem, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15,
           device: int = 0, require_feasible: bool = False, restarts: int = 1, delta: bool = False,
-          patience: int = 0) -> SolveResult:
+          patience: int = 0, column_major: bool = False) -> SolveResult:
     """One blocking kao_solve from host buffers (tables up, winner down)."""
     lib = load_library()
     cp = _CProblem(pb)
     reps = np.full((pb.P, pb.RF), -1, np.int32)
-    opt = _KaoOptions(seed, rounds, round_size, device, max(1, min(255, restarts)) | (0x100 if delta else 0) | (max(0, min(65535, patience)) << 16))
+    opt = _KaoOptions(seed, rounds, round_size, device, max(1, min(255, restarts)) | (0x100 if delta else 0) | (0x200 if column_major else 0) | (max(0, min(65535, patience)) << 16))
     res = _KaoResult()
     res.replicas = reps.ctypes.data
     rc = _check(lib.kao_solve(cp.ref(), C.byref(opt), C.byref(res)), allow_infeasible=not require_feasible)

@@ -1,0 +1,109 @@
+"""GPU parity of the column-major full evaluator (kao_set_evaluator / KAO_FLAG_COLUMN_MAJOR,
+csrc/kao_device_t.cuh): same keys, trajectories and winners as the row-major evaluator, the
+restatement and the golden streams.  The file sorts last on purpose: this evaluator was added after
+the round's GPU budget was spent, so it has only been checked in the host emulation
+(tests/test_device_emulation.py) before this run."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import kafka_assignment_optimizer_b200 as kao
+from kafka_assignment_optimizer_b200 import optimizer as kopt
+from oracle import model as m
+from problems import SHAPES
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+SUPPORTED = ["cfg2", "cfg2_rm2", "cfg3_small", "rf1", "rf_down", "max_rows"]
+
+
+def product(pb):
+    return kao.Problem.from_fields(pb)
+
+
+@pytest.fixture(scope="module")
+def golden_streams():
+    with open(os.path.join(GOLDEN, "streams.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", SUPPORTED)
+def test_golden_streams_column_major(golden_streams, name):
+    g = golden_streams[name]
+    sess = kao.Session(product(SHAPES[name]()))
+    assert sess.set_evaluator(True)
+    assert [int(k) for k in sess.candidate_keys(0xC0FFEE, 2, 1024, 0, 192)] == g["keys_round2"]
+    assert int(sess.candidate_keys(0xC0FFEE, 2, 1024, 1023, 1)[0]) == g["identity_key"]
+    keys, _ = sess.search(0xC0FFEE, 0, 8, 512)
+    assert [int(k) for k in keys] == g["trajectory"]
+    assert sess.get_base()[0].tolist() == g["final_base"]
+    sess.close()
+
+
+@pytest.mark.parametrize("name", ["cfg2_rm2", "cfg3_small", "rf_down"])
+def test_keys_and_trajectory_vs_restatement_column_major(ref_lib, name):
+    pb = SHAPES[name]()
+    r = ref_lib.Ref(pb)
+    bits, ld = r.init_base()
+    sess = kao.Session(product(pb))
+    assert sess.set_evaluator(True)
+    for rnd, size, lo, n in [(0, 1024, 0, 1024), (5, 4096, 4096 - 700, 700), (9, 2, 0, 2)]:
+        want = r.candidate_keys(bits, ld, 0xC0FFEE, rnd, size, lo, n)
+        got = sess.candidate_keys(0xC0FFEE, rnd, size, lo, n)
+        assert (want == got).all()
+    _, want = r.search(bits, ld, 0xABCDEF12345, 3, 12, 1500)
+    got, _ = sess.search(0xABCDEF12345, 3, 12, 1500)
+    assert (want == got).all()
+    reps, v, o, moves = sess.get_base()
+    assert (reps == r.decode(bits, ld)).all()
+    assert (v, o) == m.evaluate(pb, reps) and moves == m.replica_moves(pb, reps)
+    sess.close()
+
+
+def test_malformed_base_column_major(ref_lib):
+    """Short rows, duplicate brokers, random placement: every violation term is non-zero."""
+    pb = SHAPES["cfg3_small"]()
+    r = ref_lib.Ref(pb)
+    sess = kao.Session(product(pb))
+    assert sess.set_evaluator(True)
+    rng = np.random.RandomState(3)
+    for it in range(3):
+        reps = np.stack([rng.choice(pb.B, size=pb.RF, replace=False) for _ in range(pb.P)]).astype(np.int32)
+        if it == 1:
+            for _ in range(5):
+                reps[rng.randint(pb.P), -1] = -1
+        if it == 2:
+            for _ in range(5):
+                p = rng.randint(pb.P)
+                reps[p, 1] = reps[p, 0]
+        sess.set_base(reps)
+        bits, ld = r.encode(reps)
+        want = r.candidate_keys(bits, ld, 11 + it, it, 2048, 0, 2048)
+        assert (want == sess.candidate_keys(11 + it, it, 2048, 0, 2048)).all()
+    sess.close()
+
+
+def test_config3_same_winner_both_evaluators():
+    """Headline shape: the two full evaluators walk the same trajectory and reach the same assignment."""
+    pb = m.synthetic_problem(1000, 64, 8, 3)
+    a = kao.Session(product(pb))
+    b = kao.Session(product(pb))
+    assert b.set_evaluator(True)
+    ka, _ = a.search(0x5EED, 0, 6, 65536)
+    kb, _ = b.search(0x5EED, 0, 6, 65536)
+    assert (ka == kb).all()
+    assert (a.get_base()[0] == b.get_base()[0]).all() and a.get_base()[1:3] == b.get_base()[1:3]
+    a.close()
+    b.close()
+    r1 = kopt.solve(product(pb), seed=3, rounds=6, round_size=8192)
+    r2 = kopt.solve(product(pb), seed=3, rounds=6, round_size=8192, column_major=True)
+    assert (r1.replicas == r2.replicas).all() and (r1.violation, r1.objective, r1.key) == (r2.violation, r2.objective, r2.key)
+
+
+def test_unsupported_layouts_are_refused():
+    for name in ["readme", "w8_s16", "dense_small"]:
+        sess = kao.Session(product(SHAPES[name]()))
+        assert not sess.set_evaluator(True)
+        sess.close()
