@@ -83,6 +83,54 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def probe_evaluators(device):
+    """Untimed probe, run in a CHILD process (a faulting kernel must not poison the bench's CUDA
+    context): one warm and one timed launch of the step with each full evaluator of the engine on the
+    same stream of candidates; the round keys and the final assignment must be identical."""
+    import numpy as np
+
+    import kafka_assignment_optimizer_b200 as kao
+
+    pb = kao.synthetic_problem(P, B, R, RF)
+    out = {}
+    ref_keys = ref_base = None
+    for name, col in (("row_major", False), ("column_major", True)):
+        sess = kao.Session(pb, device=device)
+        if col and not sess.set_evaluator(True):
+            out[name] = {"error": "layout not covered"}
+            sess.close()
+            continue
+        sess.search(SEED, 50_000, 2, ROUND_SIZE)
+        sess.reset()
+        keys, _ = sess.search(SEED, 60_000, ROUNDS, ROUND_SIZE)
+        base = sess.get_base()[0]
+        ms = min(sess.search(SEED, 70_000 + i * ROUNDS, ROUNDS, ROUND_SIZE)[1] for i in range(2))
+        if ref_keys is None:
+            ref_keys, ref_base = keys.copy(), base.copy()
+        out[name] = {"ms_per_launch": ms, "identical_to_row_major": bool((keys == ref_keys).all() and (base == ref_base).all())}
+        sess.close()
+    print("PROBE " + json.dumps(out))
+    return 0
+
+
+def choose_evaluator(device):
+    """-> (use_column_major, report).  The faster evaluator whose results are identical wins."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-evaluators", "--device", str(device)],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        line = [l for l in r.stdout.splitlines() if l.startswith("PROBE ")]
+        if r.returncode != 0 or not line:
+            return False, {"selected": "row_major", "probe_error": (r.stderr or r.stdout)[-300:]}
+        rep = json.loads(line[-1][6:])
+    except Exception as e:                                   # noqa: BLE001 — any probe failure keeps the default evaluator
+        return False, {"selected": "row_major", "probe_error": repr(e)[:300]}
+    col, row = rep.get("column_major", {}), rep.get("row_major", {})
+    use = bool(col.get("identical_to_row_major") and "ms_per_launch" in row and col["ms_per_launch"] < row["ms_per_launch"])
+    rep["selected"] = "column_major" if use else "row_major"
+    rep["how"] = "untimed probe in a child process before the warm-up: same candidates through both full evaluators"
+    return use, rep
+
+
 def host_threads():
     """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1: not what we want here)."""
     try:
@@ -153,11 +201,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--probe-evaluators", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--device", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--evaluator", default="auto", choices=["auto", "row", "column"],
+                    help="full evaluator of the search kernel: auto = probe both, keep the faster one with identical results")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: per-round min inside the kernel over NVLink peer memory (p2p) or NCCL all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.probe_evaluators:
+        return probe_evaluators(args.device)
 
     import numpy as np
     import torch
@@ -180,7 +234,16 @@ def main():
     dev = torch.device("cuda", local)
 
     pb = kao.synthetic_problem(P, B, R, RF)
+    # both full evaluators give bit-identical keys, so every rank may choose for its own GPU
+    if args.evaluator == "auto":
+        use_col, eval_report = choose_evaluator(local)
+    else:
+        use_col, eval_report = args.evaluator == "column", {"selected": args.evaluator + " (forced)"}
+    if world > 1 and args.collective == "nccl":
+        use_col, eval_report = False, {"selected": "row_major", "note": "the NCCL variant runs the per-round kernels (row-major evaluator)"}
     sess = kao.Session(pb, device=local)
+    if use_col and not sess.set_evaluator(True):
+        use_col, eval_report = False, dict(eval_report, selected="row_major", note="column-major refused by the session")
     gsize = ROUND_SIZE * world                               # weak scaling: per-GPU work fixed
     key = torch.full((1,), kopt.KEY_NONE, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -247,11 +310,14 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("search_persistent_kernel_dram_bytes_per_launch")
+                traffic = json.load(f).get("search_persistent_kernel_column_major_dram_bytes_per_launch" if use_col
+                                           else "search_persistent_kernel_dram_bytes_per_launch")
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "search_persistent_kernel<EvalCfg<W=2,NPH=3,rack=8-slot hi1,planes=3>,768>",
+                    "traffic": traffic,
+                    "kernel": ("search_persistent_kernel<EvalCfgT<W=2,words=32>,768> (column-major evaluator)" if use_col else
+                               "search_persistent_kernel<EvalCfg<W=2,NPH=3,rack=8-slot hi1,planes=3>,768>"),
                     "algorithmic_bytes_per_candidate": ALGO_BYTES, "candidates_per_launch": ROUND_SIZE * ROUNDS,
                     "kernel_ms_per_launch": s_ms,
                     "per_round_kernels_ms": {"search_round_kernel": pr_ms / 8, "apply_winner_kernel": ap_ms / 8},
@@ -271,11 +337,11 @@ def main():
         pinned = {f.name: torch.from_numpy(np.ascontiguousarray(getattr(pb, f.name))).pin_memory()
                   for f in dataclasses.fields(pb) if isinstance(getattr(pb, f.name), np.ndarray)}
         pb_host = dataclasses.replace(pb, **{k: v.numpy() for k, v in pinned.items()})
-        kopt.solve(pb_host, SEED, 2, 1 << 12, local)        # warm the context / module
+        kopt.solve(pb_host, SEED, 2, 1 << 12, local, column_major=use_col)        # warm the context / module
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for k in range(e2e_steps):
-            res = kopt.solve(pb_host, SEED + k, ROUNDS, ROUND_SIZE, local)
+            res = kopt.solve(pb_host, SEED + k, ROUNDS, ROUND_SIZE, local, column_major=use_col)
         e2e_s = time.perf_counter() - t0
         h2d = (pb.rack_of.nbytes + pb.wF.nbytes + pb.wL.nbytes + 4 * 4 * pb.B + 2 * 4 * pb.R + pb.cur.nbytes)
         d2h = pb.P * pb.RF * 4 + ROUNDS * 8 + 16
@@ -295,6 +361,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rounds_per_step": ROUNDS, "round_size_per_gpu": ROUND_SIZE,
                            "candidates_per_step": ROUNDS * gsize, "seed": SEED,
+                           "evaluator": eval_report,
                            "l2": "flushed between timed steps (256 MiB write); working set is shared-memory resident",
                            "parallelism": ("single GPU" if world == 1 else
                                            "index-range sharding over %d ranks; per-round 8-byte min %s" % (

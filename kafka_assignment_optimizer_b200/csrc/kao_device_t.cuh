@@ -23,8 +23,10 @@
 
 namespace kao {
 
-template <int W_> struct EvalCfgT {
-    static constexpr int W = W_, NPH = 3, kRack = 3, kObj = 3;
+// kNW: partition words per slot fixed at compile time (32 = 1024 padded partitions, the headline
+// shape: every shared-memory offset of the evaluator is then an immediate), 0 = read at run time.
+template <int W_, int kNW_ = 0> struct EvalCfgT {
+    static constexpr int W = W_, NPH = 3, kRack = 3, kObj = 3, kNW = kNW_;
     static constexpr bool kTrans = true;
 };
 constexpr int kTPlanes = 5;
@@ -42,9 +44,10 @@ __host__ __device__ __forceinline__ int t_word(int q, int s, int w, int nW, int 
 // ------------------------------------------------------------------------------------------
 // rows: C1 + C7 of every partition that is not patched, bit-sliced over 32 partitions per lane
 // ------------------------------------------------------------------------------------------
-template <int W, bool kShared>
-__device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, int nW, int P, int RF, int lane, const PatchSet &ps)
+template <int W, bool kShared, int kNW>
+__device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, int nW_rt, int P, int RF, int lane, const PatchSet &ps)
 {
+    const int nW = kNW ? kNW : nW_rt;
     constexpr int NB = 4 * W;                       // 8-slot blocks = rack fields
     int viol = 0;
     const uint32_t rf0 = (RF & 1) ? ~0u : 0u, rf1 = (RF & 2) ? ~0u : 0u, rf2 = (RF & 4) ? ~0u : 0u, rf3 = (RF & 8) ? ~0u : 0u;
@@ -133,14 +136,15 @@ __device__ __forceinline__ void set_comp(uint4 &v, int k, uint32_t clear, uint32
 // ------------------------------------------------------------------------------------------
 // the whole candidate.  T: the five transposed planes; prow: this warp's patched rows [kMaxOps * W]
 // ------------------------------------------------------------------------------------------
-template <int W, bool kShared>
-__device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW, const Consts *cs, const PatchSet &ps,
+template <int W, bool kShared, int kNW = 0>
+__device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt, const Consts *cs, const PatchSet &ps,
                                  const uint32_t *prow, int lane, int &viol_out, int &obj_out)
 {
     constexpr int NSL = 32 * W;
+    const int nW = kNW ? kNW : nW_rt;
     const MemRef<kShared> T(Tp);
     // ---- rows: unpatched partitions from the transposed bit-plane, patched ones from the patch
-    int viol = rows_vertical<W, kShared>(T, nW, d.P, d.RF, lane, ps);
+    int viol = rows_vertical<W, kShared, kNW>(T, nW, d.P, d.RF, lane, ps);
     if (lane < kMaxOps) {
         const int i = lane;
         const int pp = i == 0 ? ps.p[0] : (i == 1 ? ps.p[1] : ps.p[2]);

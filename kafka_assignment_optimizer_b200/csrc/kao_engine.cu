@@ -27,8 +27,10 @@ KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 4, 3) KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 4, 5)
 KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 8, 3) KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 8, 5)
 KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 1, 3) KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 1, 5)
 KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 2, 3) KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 2, 5)
-extern template __global__ void KAO_PERSISTENT_KERNEL_T(1);     // column-major evaluator, kao_device_t.cuh
-extern template __global__ void KAO_PERSISTENT_KERNEL_T(2);
+extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 0);  // column-major evaluator, kao_device_t.cuh
+extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 0);
+extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 32);
+extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 32);
 
 
 // Winner of a round becomes the base: re-materialise its patches from (seed, round, index), write
@@ -270,9 +272,13 @@ template <class F, class A> static cudaError_t dispatch(kao_handle *h, const F &
 static cudaError_t launch_persistent(kao_handle *h, const PersistArgs &pa, bool delta)
 {
     if (delta) return dispatch(h, LaunchPersistent<true>{}, pa);
-    if (h->evaluator == KAO_EVAL_COLUMN_MAJOR)
+    if (h->evaluator == KAO_EVAL_COLUMN_MAJOR) {
+        if (h->hm.Ppad == 1024)                                 // 32 partition words per slot: compile-time offsets
+            return h->hm.W == 1 ? LaunchPersistent<false>{}.template run<EvalCfgT<1, 32>>(h, pa)
+                                : LaunchPersistent<false>{}.template run<EvalCfgT<2, 32>>(h, pa);
         return h->hm.W == 1 ? LaunchPersistent<false>{}.template run<EvalCfgT<1>>(h, pa)
                             : LaunchPersistent<false>{}.template run<EvalCfgT<2>>(h, pa);
+    }
     return dispatch(h, LaunchPersistent<false>{}, pa);
 }
 static cudaError_t launch_round(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,

@@ -15,7 +15,8 @@
 
 #if defined(KAO_INST_TRANS) && KAO_INST_TRANS
 // column-major evaluator (kao_device_t.cuh): rows of up to 64 slots
-template __global__ void KAO_PERSISTENT_KERNEL_T(KAO_INST_W);
+template __global__ void KAO_PERSISTENT_KERNEL_T(KAO_INST_W, 0);
+template __global__ void KAO_PERSISTENT_KERNEL_T(KAO_INST_W, 32);
 #elif KAO_INST_DELTA
 #if KAO_INST_W > 2
 #error "delta evaluation: rows of up to 64 slots"

@@ -420,7 +420,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             if (live) {
                 int viol, obj;
                 if constexpr (Cfg::kTrans) {
-                    eval_candidate_t<W, true>(d, s_sw, d.Ppad >> 5, s_cs, ps, gen.prow, lane, viol, obj);
+                    eval_candidate_t<W, true, Cfg::kNW>(d, s_sw, d.Ppad >> 5, s_cs, ps, gen.prow, lane, viol, obj);
                 } else {
                     eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
                 }
@@ -553,8 +553,8 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     search_round_kernel<EvalCfg<W, NPH, R, O>, threads_for<W>()>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
                                                                    uint32_t, uint32_t, unsigned long long *,      \
                                                                    unsigned long long *)
-#define KAO_PERSISTENT_KERNEL_T(W)                                                                          \
-    search_persistent_kernel<EvalCfgT<W>, threads_for<W>(), false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
+#define KAO_PERSISTENT_KERNEL_T(W, NW)                                                                      \
+    search_persistent_kernel<EvalCfgT<W, NW>, threads_for<W>(), false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
                                                                   uint32_t, unsigned long long *, unsigned int *, P2P, \
                                                                   unsigned long long *)
 #define KAO_PERSISTENT_KERNEL(W, NPH, R, O, T, DELTA)                                                       \

@@ -34,7 +34,7 @@ struct Emu {
     int nD = 0, nL = 0;
     std::vector<uint32_t> prow;          // [kMaxOps * W]
     // column-major evaluator (kao_device_t.cuh): supported shape, in use, the five transposed planes
-    bool trans_ok = false, trans = false;
+    bool trans_ok = false, trans = false, trans_generic = false;   // generic: run-time word count even for 32 words
     int nW = 0;
     std::vector<uint32_t> T;
     std::string err;
@@ -112,7 +112,8 @@ template <class Cfg> struct Run {
             __syncwarp();                                     // __syncthreads() of the kernels
             int viol, obj;
             if constexpr (W <= 2) {
-                if (e.trans) eval_candidate_t<W, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
+                if (e.trans && e.nW == 32 && !e.trans_generic) eval_candidate_t<W, true, 32>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
+                else if (e.trans) eval_candidate_t<W, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
                 else eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
             } else {
                 eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
@@ -258,6 +259,7 @@ int kao_emu_set_evaluator(void *h, int32_t mode)
     Emu &e = *static_cast<Emu *>(h);
     if (mode != 0 && !e.trans_ok) { g_err = "column-major evaluator: unsupported layout"; return -1; }
     e.trans = mode != 0;
+    e.trans_generic = mode == 2;
     return 0;
 }
 

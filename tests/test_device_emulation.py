@@ -168,6 +168,20 @@ def test_column_major_evaluator_on_arbitrary_bases(emu, ref_lib, name):
     sess.close()
 
 
+def test_column_major_run_time_and_fixed_word_count_agree(emu):
+    """1024 padded partitions: the engine picks the specialisation with 32 words per slot fixed at
+    compile time; the run-time-sized form must give the same keys."""
+    pb = COLUMN_MAJOR["cfg3"]()
+    sess = emu.EmuSession(product(pb))
+    assert sess.set_evaluator(1)
+    fixed = sess.candidate_keys(0x5EED, 3, 4096, 100, 96)
+    assert sess.set_evaluator(2)
+    assert (fixed == sess.candidate_keys(0x5EED, 3, 4096, 100, 96)).all()
+    assert sess.set_evaluator(0)
+    assert (fixed == sess.candidate_keys(0x5EED, 3, 4096, 100, 96)).all()
+    sess.close()
+
+
 def test_column_major_evaluator_refuses_other_layouts(emu):
     for name in ["readme", "s32", "w8_s16", "dense_small", "rf_up"]:
         sess = emu.EmuSession(product(SHAPES[name]()))
