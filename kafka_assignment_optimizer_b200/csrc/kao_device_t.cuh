@@ -156,9 +156,9 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
         }
     }
     // ---- columns: this lane owns slot `lane` of every row word
-    int cnt[W], lcnt[W], o0 = 0, o1 = 0, o2 = 0;
+    int cnt[W], lcnt[W], cnt2[W], lcnt2[W], o0 = 0, o1 = 0, o2 = 0, o2b = 0;
 #pragma unroll
-    for (int t = 0; t < W; ++t) cnt[t] = lcnt[t] = 0;
+    for (int t = 0; t < W; ++t) cnt[t] = lcnt[t] = cnt2[t] = lcnt2[t] = 0;
     const int rot = nW >= 32 ? 4 * (lane & 7) : 0;
     const int nch = nW >> 2;
 #pragma unroll 1
@@ -193,21 +193,40 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
                 }
             }
         }
+        // The XU pipe (POPC) is the scarce one here: the four words of a chunk that feed the same total
+        // go through one carry-save adder first, a + b + c = 2 * maj + xor, so 3 popcounts replace 4
+        // (totals of a column, valid leaders of a column, leader bonus); the doubled parts are summed
+        // apart and weighted once per candidate.
+        uint32_t hit[4];                            // leader bonus: the one-hot columns of a lane are disjoint
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint32_t hit = 0;                       // leader bonus: the one-hot columns of a lane are disjoint
+        for (int i = 0; i < 4; ++i) hit[i] = 0;
 #pragma unroll
-            for (int t = 0; t < W; ++t) {
-                const uint32_t c = comp(col[t], i), o = comp(oh[t], i);
-                cnt[t] += __popc(c);
-                lcnt[t] += __popc(o);
+        for (int t = 0; t < W; ++t) {
+            uint32_t h, l;
+            csa(h, l, col[t].x, col[t].y, col[t].z);
+            cnt[t] += __popc(l) + __popc(col[t].w);
+            cnt2[t] += __popc(h);
+            csa(h, l, oh[t].x, oh[t].y, oh[t].z);
+            lcnt[t] += __popc(l) + __popc(oh[t].w);
+            lcnt2[t] += __popc(h);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t c = comp(col[t], i);
                 o0 += __popc(c & comp(m0[t], i));
                 o1 += __popc(c & comp(m1[t], i));
-                hit |= o & comp(m2[t], i);
+                hit[i] |= comp(oh[t], i) & comp(m2[t], i);
             }
-            o2 += __popc(hit);
+        }
+        {
+            uint32_t h, l;
+            csa(h, l, hit[0], hit[1], hit[2]);
+            o2 += __popc(l) + __popc(hit[3]);
+            o2b += __popc(h);
         }
     }
+#pragma unroll
+    for (int t = 0; t < W; ++t) { cnt[t] += 2 * cnt2[t]; lcnt[t] += 2 * lcnt2[t]; }
+    o2 += 2 * o2b;
     // ---- C3 / C4 on this lane's columns, C2/C5 as P - sum of valid leaders, C6 per 8-lane rack group
 #pragma unroll
     for (int t = 0; t < W; ++t) {
