@@ -83,52 +83,73 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+SCHEDULES = [(sy, c, t, u) for sy in (0, 1, 2) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 0)]
+DEFAULT_SCHEDULE = (0, 1, 768, 1)
+
+
 def probe_evaluators(device):
     """Untimed probe, run in a CHILD process (a faulting kernel must not poison the bench's CUDA
-    context): one warm and one timed launch of the step with each full evaluator of the engine on the
-    same stream of candidates; the round keys and the final assignment must be identical."""
-    import numpy as np
-
+    context): one warm, one recorded and two timed launches of the step with each full evaluator of
+    the engine — row-major, column-major, and the schedules of the column-major one — on the same
+    stream of candidates; the round keys and the final assignment must be identical to the row-major
+    evaluator's.  One line per variant, flushed as it completes."""
     import kafka_assignment_optimizer_b200 as kao
 
     pb = kao.synthetic_problem(P, B, R, RF)
-    out = {}
-    ref_keys = ref_base = None
-    for name, col in (("row_major", False), ("column_major", True)):
+    ref = {}
+
+    def run(name, col, sched):
         sess = kao.Session(pb, device=device)
-        if col and not sess.set_evaluator(True):
-            out[name] = {"error": "layout not covered"}
+        try:
+            if col and not sess.set_evaluator(True):
+                return {"name": name, "error": "layout not covered"}
+            if sched is not None and not sess.set_schedule(*sched):
+                return {"name": name, "error": "schedule not built"}
+            sess.search(SEED, 50_000, 2, ROUND_SIZE)
+            sess.reset()
+            keys, _ = sess.search(SEED, 60_000, ROUNDS, ROUND_SIZE)
+            base = sess.get_base()[0]
+            ms = min(sess.search(SEED, 70_000 + i * ROUNDS, ROUNDS, ROUND_SIZE)[1] for i in range(2))
+            if not ref:
+                ref["keys"], ref["base"] = keys.copy(), base.copy()
+            same = bool((keys == ref["keys"]).all() and (base == ref["base"]).all())
+            return {"name": name, "column_major": col, "schedule": sched, "ms_per_launch": ms, "identical_to_row_major": same}
+        finally:
             sess.close()
-            continue
-        sess.search(SEED, 50_000, 2, ROUND_SIZE)
-        sess.reset()
-        keys, _ = sess.search(SEED, 60_000, ROUNDS, ROUND_SIZE)
-        base = sess.get_base()[0]
-        ms = min(sess.search(SEED, 70_000 + i * ROUNDS, ROUNDS, ROUND_SIZE)[1] for i in range(2))
-        if ref_keys is None:
-            ref_keys, ref_base = keys.copy(), base.copy()
-        out[name] = {"ms_per_launch": ms, "identical_to_row_major": bool((keys == ref_keys).all() and (base == ref_base).all())}
-        sess.close()
-    print("PROBE " + json.dumps(out))
+
+    print("PROBE " + json.dumps(run("row_major", False, None)), flush=True)
+    print("PROBE " + json.dumps(run("column_major", True, None)), flush=True)
+    for sched in SCHEDULES:
+        if sched != DEFAULT_SCHEDULE:
+            print("PROBE " + json.dumps(run("column_major sync=%d compress=%d threads=%d unroll=%d" % sched, True, sched)), flush=True)
     return 0
 
 
 def choose_evaluator(device):
-    """-> (use_column_major, report).  The faster evaluator whose results are identical wins."""
+    """-> (use_column_major, schedule or None, report).  The fastest variant whose results are
+    identical to the row-major evaluator's wins; whatever the child managed to report before a failure counts."""
+    rows, err = [], None
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-evaluators", "--device", str(device)],
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
-        line = [l for l in r.stdout.splitlines() if l.startswith("PROBE ")]
-        if r.returncode != 0 or not line:
-            return False, {"selected": "row_major", "probe_error": (r.stderr or r.stdout)[-300:]}
-        rep = json.loads(line[-1][6:])
-    except Exception as e:                                   # noqa: BLE001 — any probe failure keeps the default evaluator
-        return False, {"selected": "row_major", "probe_error": repr(e)[:300]}
-    col, row = rep.get("column_major", {}), rep.get("row_major", {})
-    use = bool(col.get("identical_to_row_major") and "ms_per_launch" in row and col["ms_per_launch"] < row["ms_per_launch"])
-    rep["selected"] = "column_major" if use else "row_major"
-    rep["how"] = "untimed probe in a child process before the warm-up: same candidates through both full evaluators"
-    return use, rep
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=420)
+        rows = [json.loads(l[6:]) for l in r.stdout.splitlines() if l.startswith("PROBE ")]
+        if r.returncode != 0:
+            err = (r.stderr or r.stdout)[-300:]
+    except Exception as e:                                   # noqa: BLE001 — any probe failure keeps what is known to work
+        err = repr(e)[:300]
+    ok = [x for x in rows if x.get("identical_to_row_major") and "ms_per_launch" in x]
+    report = {"how": "untimed probe in a child process before the warm-up: the same candidates through every "
+                     "full-evaluation variant; identical round keys and final assignment required",
+              "variants": [{k: v for k, v in x.items() if k != "column_major"} for x in rows]}
+    if err:
+        report["probe_error"] = err
+    if not ok or not any(x["name"] == "row_major" for x in ok):
+        report["selected"] = "row_major"
+        return False, None, report
+    best = min(ok, key=lambda x: x["ms_per_launch"])
+    report["selected"] = best["name"]
+    sched = tuple(best["schedule"]) if best.get("schedule") else None
+    return bool(best["column_major"]), sched, report
 
 
 def host_threads():
@@ -235,15 +256,21 @@ def main():
 
     pb = kao.synthetic_problem(P, B, R, RF)
     # both full evaluators give bit-identical keys, so every rank may choose for its own GPU
+    sched = None
     if args.evaluator == "auto":
-        use_col, eval_report = choose_evaluator(local)
+        use_col, sched, eval_report = choose_evaluator(local)
     else:
         use_col, eval_report = args.evaluator == "column", {"selected": args.evaluator + " (forced)"}
     if world > 1 and args.collective == "nccl":
-        use_col, eval_report = False, {"selected": "row_major", "note": "the NCCL variant runs the per-round kernels (row-major evaluator)"}
+        use_col, sched, eval_report = False, None, {"selected": "row_major", "note": "the NCCL variant runs the per-round kernels (row-major evaluator)"}
     sess = kao.Session(pb, device=local)
     if use_col and not sess.set_evaluator(True):
-        use_col, eval_report = False, dict(eval_report, selected="row_major", note="column-major refused by the session")
+        use_col, sched, eval_report = False, None, dict(eval_report, selected="row_major", note="column-major refused by the session")
+    if use_col and sched is not None:
+        if sess.set_schedule(*sched):
+            os.environ["KAO_SCHEDULE"] = "%d,%d,%d,%d" % sched      # kao_solve (the e2e leg) creates its own sessions
+        else:
+            sched = None
     gsize = ROUND_SIZE * world                               # weak scaling: per-GPU work fixed
     key = torch.full((1,), kopt.KEY_NONE, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -316,7 +343,8 @@ def main():
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic,
-                    "kernel": ("search_persistent_kernel<EvalCfgT<W=2,words=32>,768> (column-major evaluator)" if use_col else
+                    "kernel": ("search_persistent_kernel<EvalCfgT<W=2,words=32,sync=%d,compress=%d,threads=%d,unroll=%d>> (column-major evaluator)"
+                               % (sched or DEFAULT_SCHEDULE) if use_col else
                                "search_persistent_kernel<EvalCfg<W=2,NPH=3,rack=8-slot hi1,planes=3>,768>"),
                     "algorithmic_bytes_per_candidate": ALGO_BYTES, "candidates_per_launch": ROUND_SIZE * ROUNDS,
                     "kernel_ms_per_launch": s_ms,

@@ -152,6 +152,14 @@ int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
 #define KAO_EVAL_ROW_MAJOR 0
 #define KAO_EVAL_COLUMN_MAJOR 1
 int kao_set_evaluator(kao_handle *h, int32_t evaluator);
+/* Schedule of the column-major evaluator: the same arithmetic, laid out differently in time.  sync: how
+ * the warps of a CTA meet before an evaluation (0 block barrier, 1 warp only, 2 one barrier per warp
+ * scheduler); compress: carry-save compression of three popcount streams (1) or plain popcounts (0);
+ * (threads per CTA, unroll of the column loop): (768,1), (512,1) or (512,2).  Default (0, 1, 768, 1).
+ * Results never depend on it; bench.py measures the variants on the GPU it runs on and keeps the
+ * fastest.  Built for two-word rows with 769..1024 partitions; KAO_E_ARG otherwise.  The environment
+ * variable KAO_SCHEDULE="sync,compress,threads,unroll" sets it for every session (and kao_solve). */
+int kao_set_schedule(kao_handle *h, int32_t sync, int32_t compress, int32_t threads, int32_t unroll);
 int kao_last_rounds(kao_handle *h, uint32_t *rounds_run);
 
 /* keys of candidates idx_begin .. idx_begin+count-1 of `round` against the current base (host

@@ -25,8 +25,15 @@ namespace kao {
 
 // kNW: partition words per slot fixed at compile time (32 = 1024 padded partitions, the headline
 // shape: every shared-memory offset of the evaluator is then an immediate), 0 = read at run time.
-template <int W_, int kNW_ = 0> struct EvalCfgT {
+// The other parameters are SCHEDULES of the same arithmetic (kao_set_schedule; results identical):
+//   kSync      how the warps of a CTA meet before an evaluation: 0 block barrier (all warps walk the
+//              evaluator together: instruction cache), 1 warp only, 2 one named barrier per scheduler
+//   kCompress  1: carry-save compression of the column / leader / bonus popcount streams
+//   kThreads   threads per CTA (0 = threads_for<W>()); fewer threads = more registers per thread
+//   kUnroll    unroll factor of the column chunk loop
+template <int W_, int kNW_ = 0, int kSync_ = 0, int kCompress_ = 1, int kThreads_ = 0, int kUnroll_ = 1> struct EvalCfgT {
     static constexpr int W = W_, NPH = 3, kRack = 3, kObj = 3, kNW = kNW_;
+    static constexpr int kSync = kSync_, kCompress = kCompress_, kThreads = kThreads_, kUnroll = kUnroll_;
     static constexpr bool kTrans = true;
 };
 constexpr int kTPlanes = 5;
@@ -136,10 +143,11 @@ __device__ __forceinline__ void set_comp(uint4 &v, int k, uint32_t clear, uint32
 // ------------------------------------------------------------------------------------------
 // the whole candidate.  T: the five transposed planes; prow: this warp's patched rows [kMaxOps * W]
 // ------------------------------------------------------------------------------------------
-template <int W, bool kShared, int kNW = 0>
+template <class Cfg, bool kShared>
 __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt, const Consts *cs, const PatchSet &ps,
                                  const uint32_t *prow, int lane, int &viol_out, int &obj_out)
 {
+    constexpr int W = Cfg::W, kNW = Cfg::kNW;
     constexpr int NSL = 32 * W;
     const int nW = kNW ? kNW : nW_rt;
     const MemRef<kShared> T(Tp);
@@ -161,7 +169,7 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
     for (int t = 0; t < W; ++t) cnt[t] = lcnt[t] = cnt2[t] = lcnt2[t] = 0;
     const int rot = nW >= 32 ? 4 * (lane & 7) : 0;
     const int nch = nW >> 2;
-#pragma unroll 1
+#pragma unroll (Cfg::kUnroll)
     for (int j = 0; j < nch; ++j) {
         int tw = 4 * j + rot;
         tw -= (tw >= nW) ? nW : 0;
@@ -202,26 +210,34 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
         for (int i = 0; i < 4; ++i) hit[i] = 0;
 #pragma unroll
         for (int t = 0; t < W; ++t) {
-            uint32_t h, l;
-            csa(h, l, col[t].x, col[t].y, col[t].z);
-            cnt[t] += __popc(l) + __popc(col[t].w);
-            cnt2[t] += __popc(h);
-            csa(h, l, oh[t].x, oh[t].y, oh[t].z);
-            lcnt[t] += __popc(l) + __popc(oh[t].w);
-            lcnt2[t] += __popc(h);
+            if constexpr (Cfg::kCompress) {
+                uint32_t h, l;
+                csa(h, l, col[t].x, col[t].y, col[t].z);
+                cnt[t] += __popc(l) + __popc(col[t].w);
+                cnt2[t] += __popc(h);
+                csa(h, l, oh[t].x, oh[t].y, oh[t].z);
+                lcnt[t] += __popc(l) + __popc(oh[t].w);
+                lcnt2[t] += __popc(h);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const uint32_t c = comp(col[t], i);
+                if constexpr (!Cfg::kCompress) {
+                    cnt[t] += __popc(c);
+                    lcnt[t] += __popc(comp(oh[t], i));
+                }
                 o0 += __popc(c & comp(m0[t], i));
                 o1 += __popc(c & comp(m1[t], i));
                 hit[i] |= comp(oh[t], i) & comp(m2[t], i);
             }
         }
-        {
+        if constexpr (Cfg::kCompress) {
             uint32_t h, l;
             csa(h, l, hit[0], hit[1], hit[2]);
             o2 += __popc(l) + __popc(hit[3]);
             o2b += __popc(h);
+        } else {
+            o2 += __popc(hit[0]) + __popc(hit[1]) + __popc(hit[2]) + __popc(hit[3]);
         }
     }
 #pragma unroll

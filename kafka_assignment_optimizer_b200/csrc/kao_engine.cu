@@ -11,6 +11,8 @@
 #include <map>
 #include <mutex>
 #include <cstdio>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -31,6 +33,8 @@ extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 0);  // column-major 
 extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 0);
 extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 32);
 extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 32);
+#define KAO_DECL_TUNE(S, C, T, U) extern template __global__ void KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U);
+KAO_FOR_TUNE_SYNC(KAO_DECL_TUNE, 0) KAO_FOR_TUNE_SYNC(KAO_DECL_TUNE, 1) KAO_FOR_TUNE_SYNC(KAO_DECL_TUNE, 2)
 
 
 // Winner of a round becomes the base: re-materialise its patches from (seed, round, index), write
@@ -101,6 +105,7 @@ eval_batch_kernel(Params d, const uint32_t *cand_bits, const uint8_t *cand_leade
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+static bool schedule_exists(int sync, int compress, int threads, int unroll);
 #define CUDA_TRY(expr)                                                                       \
     do {                                                                                     \
         cudaError_t e_ = (expr);                                                             \
@@ -149,6 +154,9 @@ struct kao_handle {
     bool trans_ok = false;
     int evaluator = KAO_EVAL_ROW_MAJOR;
     SmemPlan plan_t{};
+    // schedule of the column-major evaluator (kao_set_schedule): barrier form, popcount compression,
+    // threads per CTA, unroll of the column loop.  Same results; (0, 1, 768, 1) is the default.
+    int sch_sync = 0, sch_compress = 1, sch_threads = KAO_THREADS, sch_unroll = 1;
     // device buffers
     uint32_t *d_bits = nullptr; uint8_t *d_leader = nullptr; uint32_t *d_sw = nullptr;
     uint32_t *d_dense = nullptr; uint32_t *d_planes = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
@@ -220,12 +228,14 @@ template <bool kDelta> struct LaunchPersistent {
         if constexpr (kDelta && Cfg::W > 2) {
             return cudaErrorNotSupported;                       // delta mode: rows of up to 64 slots
         } else {
-            constexpr int T = kDelta ? KAO_THREADS_DELTA : threads_for<Cfg::W>();
+            constexpr int T = kDelta ? KAO_THREADS_DELTA : cfg_threads<Cfg>();
             auto kern = search_persistent_kernel<Cfg, T, kDelta>;
             static bool done[64] = {};
             cudaError_t e = set_smem_attr<Cfg>(h, reinterpret_cast<const void *>(kern), done);
             if (e != cudaSuccess) return e;
-            Params prm = h->prm; SmemPlan plan = Cfg::kTrans ? h->plan_t : h->plan;
+            Params prm = h->prm;
+            // the column-major plan depends on the warps per CTA of the schedule (per-warp scratch)
+            SmemPlan plan = Cfg::kTrans ? make_plan(Cfg::W, h->hm.Ppad, T / 32, kTPlanes * Cfg::W, h->hm.P, h->hm.RF, false) : h->plan;
             uint64_t seed = a.seed; uint32_t fr = a.first_round, rounds = a.rounds, rs = a.round_size;
             unsigned long long *keys = a.d_keys, *all = a.all_keys; unsigned int *bar = a.d_bar;
             P2P pp = a.pp;
@@ -273,6 +283,14 @@ static cudaError_t launch_persistent(kao_handle *h, const PersistArgs &pa, bool 
 {
     if (delta) return dispatch(h, LaunchPersistent<true>{}, pa);
     if (h->evaluator == KAO_EVAL_COLUMN_MAJOR) {
+        if (h->hm.Ppad == 1024 && h->hm.W == 2 &&
+            !(h->sch_sync == 0 && h->sch_compress == 1 && h->sch_threads == KAO_THREADS && h->sch_unroll == 1)) {
+#define KAO_RUN_TUNE(S, C, T, U)                                                                       \
+    if (h->sch_sync == S && h->sch_compress == C && h->sch_threads == T && h->sch_unroll == U)           \
+        return LaunchPersistent<false>{}.template run<KAO_TUNE_CFG(S, C, T, U)>(h, pa);
+            KAO_FOR_TUNE_SYNC(KAO_RUN_TUNE, 0) KAO_FOR_TUNE_SYNC(KAO_RUN_TUNE, 1) KAO_FOR_TUNE_SYNC(KAO_RUN_TUNE, 2)
+#undef KAO_RUN_TUNE
+        }
         if (h->hm.Ppad == 1024)                                 // 32 partition words per slot: compile-time offsets
             return h->hm.W == 1 ? LaunchPersistent<false>{}.template run<EvalCfgT<1, 32>>(h, pa)
                                 : LaunchPersistent<false>{}.template run<EvalCfgT<2, 32>>(h, pa);
@@ -359,6 +377,12 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     // its five transposed planes (5 * W words per partition) take the place of the objective table
     h->plan_t = make_plan(W, Ppad, h->threads / 32, kTPlanes * W, m.P, m.RF, false);
     h->trans_ok = W <= 2 && m.hi1 && m.log2S == 3 && h->hm.nplanes == 3 && h->plan_t.total <= 227u * 1024u;
+    if (const char *env = std::getenv("KAO_SCHEDULE")) {      // "sync,compress,threads,unroll": tuning only, ignored if not built
+        int a = 0, b = 1, c = KAO_THREADS, u = 1;
+        if (std::sscanf(env, "%d,%d,%d,%d", &a, &b, &c, &u) == 4 && schedule_exists(a, b, c, u) && h->trans_ok && W == 2 && Ppad == 1024) {
+            h->sch_sync = a; h->sch_compress = b; h->sch_threads = c; h->sch_unroll = u;
+        }
+    }
     h->grid = h->sms;
     CUDA_TRY(dalloc(h, &h->d_bits, (size_t)W * Ppad * 4));
     CUDA_TRY(dalloc(h, &h->d_leader, (size_t)Ppad));
@@ -556,6 +580,25 @@ extern "C" int kao_set_evaluator(kao_handle *h, int32_t evaluator)
         return fail(KAO_E_ARG, "column-major evaluator: needs rows of up to 64 slots, racks of up to 8 brokers, at most one "
                                "replica per rack (C7 0..1), three objective mask planes, and its planes in shared memory");
     h->evaluator = evaluator;
+    return KAO_OK;
+}
+
+static bool schedule_exists(int sync, int compress, int threads, int unroll)
+{
+#define KAO_HAS_TUNE(S, C, T, U) if (sync == S && compress == C && threads == T && unroll == U) return true;
+    KAO_FOR_TUNE_SYNC(KAO_HAS_TUNE, 0) KAO_FOR_TUNE_SYNC(KAO_HAS_TUNE, 1) KAO_FOR_TUNE_SYNC(KAO_HAS_TUNE, 2)
+#undef KAO_HAS_TUNE
+    return false;
+}
+
+extern "C" int kao_set_schedule(kao_handle *h, int32_t sync, int32_t compress, int32_t threads, int32_t unroll)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    if (!schedule_exists(sync, compress, threads, unroll))
+        return fail(KAO_E_ARG, "no such schedule: sync 0..2, compress 0..1, (threads, unroll) one of (768,1) (512,1) (512,2)");
+    if (!(h->trans_ok && h->hm.W == 2 && h->hm.Ppad == 1024) && !(sync == 0 && compress == 1 && threads == KAO_THREADS && unroll == 1))
+        return fail(KAO_E_ARG, "schedules other than the default are built for two-word rows with 769..1024 partitions");
+    h->sch_sync = sync; h->sch_compress = compress; h->sch_threads = threads; h->sch_unroll = unroll;
     return KAO_OK;
 }
 

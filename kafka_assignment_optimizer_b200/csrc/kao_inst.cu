@@ -13,7 +13,11 @@
     template __global__ void KAO_PERSISTENT_KERNEL(W, NPH, R, O, threads_for<W>(), false);
 #define KAO_INST_DELTA_K(W, NPH, R, O) template __global__ void KAO_PERSISTENT_KERNEL(W, NPH, R, O, KAO_THREADS_DELTA, true);
 
-#if defined(KAO_INST_TRANS) && KAO_INST_TRANS
+#if defined(KAO_INST_TUNE) && KAO_INST_TUNE >= 0
+// schedules of the column-major evaluator (kao_set_schedule), one object per barrier form
+#define KAO_INST_TUNE_K(S, C, T, U) template __global__ void KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U);
+KAO_FOR_TUNE_SYNC(KAO_INST_TUNE_K, KAO_INST_TUNE)
+#elif defined(KAO_INST_TRANS) && KAO_INST_TRANS
 // column-major evaluator (kao_device_t.cuh): rows of up to 64 slots
 template __global__ void KAO_PERSISTENT_KERNEL_T(KAO_INST_W, 0);
 template __global__ void KAO_PERSISTENT_KERNEL_T(KAO_INST_W, 32);

@@ -21,6 +21,12 @@ using namespace kao;
 #endif
 #define KAO_THREADS_DELTA 512
 template <int W> constexpr int threads_for() { return W <= 2 ? KAO_THREADS : KAO_THREADS_WIDE; }
+// threads per CTA of the full-evaluation kernels of a configuration (column-major schedules may choose)
+template <class Cfg> constexpr int cfg_threads()
+{
+    if constexpr (Cfg::kTrans) return Cfg::kThreads ? Cfg::kThreads : threads_for<Cfg::W>();
+    else return threads_for<Cfg::W>();
+}
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + TMA bulk copy (SASS: SYNCS / UBLKCP)
@@ -416,11 +422,19 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 #pragma unroll
             for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
             if (live) gen.run(seed, round, idx, round_size, ps, no_rows);
-            __syncthreads();
+            if constexpr (Cfg::kTrans) {
+                // schedules of the column-major evaluator: who meets before an evaluation (the patched
+                // rows were written by lane 0 of this warp, so a warp-level sync is enough for correctness)
+                if constexpr (Cfg::kSync == 0) __syncthreads();
+                else if constexpr (Cfg::kSync == 1) __syncwarp();
+                else asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(THREADS / 4) : "memory");
+            } else {
+                __syncthreads();
+            }
             if (live) {
                 int viol, obj;
                 if constexpr (Cfg::kTrans) {
-                    eval_candidate_t<W, true, Cfg::kNW>(d, s_sw, d.Ppad >> 5, s_cs, ps, gen.prow, lane, viol, obj);
+                    eval_candidate_t<Cfg, true>(d, s_sw, d.Ppad >> 5, s_cs, ps, gen.prow, lane, viol, obj);
                 } else {
                     eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
                 }
@@ -557,6 +571,14 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     search_persistent_kernel<EvalCfgT<W, NW>, threads_for<W>(), false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
                                                                   uint32_t, unsigned long long *, unsigned int *, P2P, \
                                                                   unsigned long long *)
+// schedules of the column-major evaluator for the headline layout (two-word rows, 32 partition words):
+// X(sync, compress, threads, unroll); (0, 1, 768, 1) is the default above
+#define KAO_TUNE_CFG(S, C, T, U) EvalCfgT<2, 32, S, C, T, U>
+#define KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U)                                                              \
+    search_persistent_kernel<KAO_TUNE_CFG(S, C, T, U), T, false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
+                                                                 uint32_t, unsigned long long *, unsigned int *, P2P, \
+                                                                 unsigned long long *)
+#define KAO_FOR_TUNE_SYNC(X, S) X(S, 1, 768, 1) X(S, 0, 768, 1) X(S, 1, 512, 1) X(S, 0, 512, 1) X(S, 1, 512, 2) X(S, 0, 512, 2)
 #define KAO_PERSISTENT_KERNEL(W, NPH, R, O, T, DELTA)                                                       \
     search_persistent_kernel<EvalCfg<W, NPH, R, O>, T, DELTA>(Params, SmemPlan, uint64_t, uint32_t, uint32_t,      \
                                                              uint32_t, unsigned long long *, unsigned int *, P2P, \

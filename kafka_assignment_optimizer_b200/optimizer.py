@@ -144,6 +144,15 @@ class Session:
         _check(rc)
         return False
 
+    def set_schedule(self, sync: int, compress: int, threads: int, unroll: int) -> bool:
+        """Schedule of the column-major evaluator (kao_set_schedule): results never depend on it.
+        False when that variant is not built for this layout."""
+        rc = self._lib.kao_set_schedule(self._h, C.c_int32(sync), C.c_int32(compress), C.c_int32(threads), C.c_int32(unroll))
+        if rc == -1:
+            return False
+        _check(rc)
+        return True
+
     def set_patience(self, rounds_without_improvement: int):
         _check(self._lib.kao_set_patience(self._h, C.c_uint32(rounds_without_improvement)))
 

@@ -46,8 +46,9 @@ class EmuSession:
         return dict(W=out[0], NPH=out[1], rack=out[2], obj=out[3])
 
     def set_evaluator(self, mode):
-        """1: column-major evaluator (csrc/kao_device_t.cuh), 2: its run-time-sized form even where the
-        engine would pick the 32-word specialisation; False is returned for unsupported layouts."""
+        """0: row-major evaluator; 1: column-major evaluator (csrc/kao_device_t.cuh) as the engine picks it;
+        2: its run-time-sized form even where the 32-word specialisation applies; 3: plain popcounts
+        (kCompress = 0); 4: unrolled column loop.  False is returned for unsupported layouts."""
         return lib().kao_emu_set_evaluator(self._h, C.c_int32(mode)) == 0
 
     def set_base(self, replicas):

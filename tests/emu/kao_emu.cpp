@@ -34,7 +34,8 @@ struct Emu {
     int nD = 0, nL = 0;
     std::vector<uint32_t> prow;          // [kMaxOps * W]
     // column-major evaluator (kao_device_t.cuh): supported shape, in use, the five transposed planes
-    bool trans_ok = false, trans = false, trans_generic = false;   // generic: run-time word count even for 32 words
+    bool trans_ok = false;
+    int trans = 0;                       // 0 row-major evaluator, 1..4 forms of the column-major one
     int nW = 0;
     std::vector<uint32_t> T;
     std::string err;
@@ -112,8 +113,14 @@ template <class Cfg> struct Run {
             __syncwarp();                                     // __syncthreads() of the kernels
             int viol, obj;
             if constexpr (W <= 2) {
-                if (e.trans && e.nW == 32 && !e.trans_generic) eval_candidate_t<W, true, 32>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
-                else if (e.trans) eval_candidate_t<W, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
+                // forms of the column-major evaluator: 1 as the engine picks it (32-word specialisation where it
+                // applies, compressed popcounts), 2 run-time word count, 3 plain popcounts, 4 unrolled column loop
+                const bool fixed = e.nW == 32;
+                if (e.trans == 1 && fixed) eval_candidate_t<EvalCfgT<W, 32>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
+                else if (e.trans == 1 || e.trans == 2) eval_candidate_t<EvalCfgT<W, 0>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
+                else if (e.trans == 3 && fixed) eval_candidate_t<EvalCfgT<W, 32, 0, 0>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
+                else if (e.trans == 3) eval_candidate_t<EvalCfgT<W, 0, 0, 0>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
+                else if (e.trans == 4) eval_candidate_t<EvalCfgT<W, 0, 0, 1, 512, 2>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
                 else eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
             } else {
                 eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
@@ -258,8 +265,8 @@ int kao_emu_set_evaluator(void *h, int32_t mode)
 {
     Emu &e = *static_cast<Emu *>(h);
     if (mode != 0 && !e.trans_ok) { g_err = "column-major evaluator: unsupported layout"; return -1; }
-    e.trans = mode != 0;
-    e.trans_generic = mode == 2;
+    if (mode < 0 || mode > 4) { g_err = "unknown evaluator form"; return -1; }
+    e.trans = mode;
     return 0;
 }
 

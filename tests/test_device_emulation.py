@@ -168,17 +168,35 @@ def test_column_major_evaluator_on_arbitrary_bases(emu, ref_lib, name):
     sess.close()
 
 
-def test_column_major_run_time_and_fixed_word_count_agree(emu):
+def test_column_major_forms_agree(emu):
     """1024 padded partitions: the engine picks the specialisation with 32 words per slot fixed at
-    compile time; the run-time-sized form must give the same keys."""
+    compile time; the run-time-sized form and the other schedules' arithmetic must give the same keys."""
     pb = COLUMN_MAJOR["cfg3"]()
     sess = emu.EmuSession(product(pb))
     assert sess.set_evaluator(1)
     fixed = sess.candidate_keys(0x5EED, 3, 4096, 100, 96)
-    assert sess.set_evaluator(2)
-    assert (fixed == sess.candidate_keys(0x5EED, 3, 4096, 100, 96)).all()
+    for form in (2, 3, 4):               # run-time word count, plain popcounts, unrolled column loop
+        assert sess.set_evaluator(form)
+        assert (fixed == sess.candidate_keys(0x5EED, 3, 4096, 100, 96)).all()
     assert sess.set_evaluator(0)
     assert (fixed == sess.candidate_keys(0x5EED, 3, 4096, 100, 96)).all()
+    sess.close()
+
+
+def test_column_major_plain_popcounts_on_a_malformed_base(emu, ref_lib):
+    pb = COLUMN_MAJOR["rf4_w2"]()
+    r = ref_lib.Ref(pb)
+    rng = np.random.RandomState(9)
+    reps = np.stack([rng.choice(pb.B, size=pb.RF, replace=False) for _ in range(pb.P)]).astype(np.int32)
+    reps[7, -1] = -1
+    reps[11, 1] = reps[11, 0]
+    bits, ld = r.encode(reps)
+    want = r.candidate_keys(bits, ld, 21, 2, 256, 0, 48)
+    sess = emu.EmuSession(product(pb))
+    for form in (1, 3, 4):
+        assert sess.set_evaluator(form)
+        sess.set_base(reps)
+        assert (want == sess.candidate_keys(21, 2, 256, 0, 48)).all()
     sess.close()
 
 

@@ -30,7 +30,7 @@ def test_abi_exports_every_declared_symbol(lib):
     names = set(re.findall(r"\b(kao_[a-z0-9_]+)\s*\(", hdr))
     assert {"kao_solve", "kao_eval", "kao_create", "kao_search", "kao_round_launch", "kao_round_apply",
             "kao_candidate_keys", "kao_profile_rounds", "kao_p2p_export", "kao_p2p_connect",
-            "kao_search_sharded", "kao_search_sharded_delta", "kao_search_delta", "kao_set_patience", "kao_set_evaluator", "kao_last_rounds", "kao_candidate_keys_delta", "kao_version", "kao_last_error"} <= names
+            "kao_search_sharded", "kao_search_sharded_delta", "kao_search_delta", "kao_set_patience", "kao_set_evaluator", "kao_set_schedule", "kao_last_rounds", "kao_candidate_keys_delta", "kao_version", "kao_last_error"} <= names
     for n in sorted(names):
         assert hasattr(lib, n), n
     assert lib.kao_version() == 0x00010000
