@@ -97,8 +97,18 @@ def probe_evaluators(device):
 
     pb = kao.synthetic_problem(P, B, R, RF)
     ref = {}
+    progress = [time.monotonic()]
+
+    def watchdog():                                          # a variant that hangs ends the probe, not the bench
+        while True:
+            time.sleep(1.0)
+            if time.monotonic() - progress[0] > 25.0:
+                os._exit(3)
+
+    threading.Thread(target=watchdog, daemon=True).start()
 
     def run(name, col, sched):
+        progress[0] = time.monotonic()
         sess = kao.Session(pb, device=device)
         try:
             if col and not sess.set_evaluator(True):
@@ -131,12 +141,19 @@ def choose_evaluator(device):
     rows, err = [], None
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-evaluators", "--device", str(device)],
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=420)
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
         rows = [json.loads(l[6:]) for l in r.stdout.splitlines() if l.startswith("PROBE ")]
         if r.returncode != 0:
             err = (r.stderr or r.stdout)[-300:]
     except Exception as e:                                   # noqa: BLE001 — any probe failure keeps what is known to work
         err = repr(e)[:300]
+        out = getattr(e, "stdout", None) or ""               # TimeoutExpired carries what the child printed so far
+        if isinstance(out, bytes):
+            out = out.decode(errors="replace")
+        try:
+            rows = [json.loads(l[6:]) for l in out.splitlines() if l.startswith("PROBE ")]
+        except ValueError:
+            rows = []
     ok = [x for x in rows if x.get("identical_to_row_major") and "ms_per_launch" in x]
     report = {"how": "untimed probe in a child process before the warm-up: the same candidates through every "
                      "full-evaluation variant; identical round keys and final assignment required",
