@@ -1,0 +1,62 @@
+"""bench.py picks the full-evaluation variant to time from an untimed probe run in a child process.
+The selection logic is host code: checked here with canned child output (no GPU)."""
+import json
+import subprocess
+import types
+
+import bench
+
+
+def _fake(lines, rc=0, stderr=""):
+    def run(*a, **k):
+        return types.SimpleNamespace(stdout="".join("PROBE " + json.dumps(l) + "\n" for l in lines) + "noise\n", stderr=stderr, returncode=rc)
+    return run
+
+
+ROW = {"name": "row_major", "column_major": False, "schedule": None, "ms_per_launch": 31.8, "identical_to_row_major": True}
+COL = {"name": "column_major", "column_major": True, "schedule": None, "ms_per_launch": 29.5, "identical_to_row_major": True}
+FAST = {"name": "column_major sync=1 compress=0 threads=512 unroll=2", "column_major": True, "schedule": [1, 0, 512, 2],
+        "ms_per_launch": 25.0, "identical_to_row_major": True}
+WRONG = {"name": "column_major sync=2 compress=1 threads=768 unroll=1", "column_major": True, "schedule": [2, 1, 768, 1],
+         "ms_per_launch": 10.0, "identical_to_row_major": False}
+
+
+def test_fastest_identical_variant_wins(monkeypatch):
+    monkeypatch.setattr(subprocess, "run", _fake([ROW, COL, FAST, WRONG]))
+    use_col, sched, rep = bench.choose_evaluator(0)
+    assert use_col and sched == (1, 0, 512, 2) and rep["selected"] == FAST["name"] and len(rep["variants"]) == 4
+
+
+def test_default_column_major_has_no_schedule(monkeypatch):
+    monkeypatch.setattr(subprocess, "run", _fake([ROW, COL, WRONG]))
+    assert bench.choose_evaluator(0)[:2] == (True, None)
+
+
+def test_row_major_stays_when_it_is_fastest_or_the_others_differ(monkeypatch):
+    monkeypatch.setattr(subprocess, "run", _fake([dict(ROW, ms_per_launch=20.0), COL, WRONG]))
+    assert bench.choose_evaluator(0)[:2] == (False, None)
+    monkeypatch.setattr(subprocess, "run", _fake([ROW, dict(COL, identical_to_row_major=False), {"name": "x", "error": "schedule not built"}]))
+    assert bench.choose_evaluator(0)[:2] == (False, None)
+
+
+def test_partial_output_of_a_crashed_or_hung_child_counts(monkeypatch):
+    monkeypatch.setattr(subprocess, "run", _fake([ROW, COL], rc=3, stderr="watchdog"))
+    use_col, sched, rep = bench.choose_evaluator(0)
+    assert (use_col, sched) == (True, None) and "probe_error" in rep
+
+    def hang(*a, **k):
+        raise subprocess.TimeoutExpired(cmd="probe", timeout=1, output=("PROBE " + json.dumps(ROW) + "\nPROBE " + json.dumps(FAST) + "\n").encode())
+    monkeypatch.setattr(subprocess, "run", hang)
+    assert bench.choose_evaluator(0)[:2] == (True, (1, 0, 512, 2))
+
+    def boom(*a, **k):
+        raise OSError("no python")
+    monkeypatch.setattr(subprocess, "run", boom)
+    assert bench.choose_evaluator(0)[:2] == (False, None)
+    monkeypatch.setattr(subprocess, "run", _fake([COL, FAST]))            # no row-major reference: nothing to compare with
+    assert bench.choose_evaluator(0)[:2] == (False, None)
+
+
+def test_schedule_list_matches_the_engine():
+    assert len(bench.SCHEDULES) == 18 and bench.DEFAULT_SCHEDULE in bench.SCHEDULES
+    assert {(t, u) for _, _, t, u in bench.SCHEDULES} == {(768, 1), (512, 1), (512, 2)}
