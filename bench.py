@@ -83,7 +83,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-SCHEDULES = [(sy, c, t, u) for sy in (0, 1, 2) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 0)]
+SCHEDULES = [(sy, c, t, u) for sy in (0, 1, 2, 3) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 0, 2)]
 DEFAULT_SCHEDULE = (0, 1, 768, 1)
 
 

@@ -154,7 +154,8 @@ int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
 int kao_set_evaluator(kao_handle *h, int32_t evaluator);
 /* Schedule of the column-major evaluator: the same arithmetic, laid out differently in time.  sync: how
  * the warps of a CTA meet before an evaluation (0 block barrier, 1 warp only, 2 one barrier per warp
- * scheduler); compress: carry-save compression of three popcount streams (1) or plain popcounts (0);
+ * scheduler, 3 two half-CTA groups); compress: carry-save compression of popcount streams (0 none, 1
+ * three streams, 2 five);
  * (threads per CTA, unroll of the column loop): (768,1), (512,1) or (512,2).  Default (0, 1, 768, 1).
  * Results never depend on it; bench.py measures the variants on the GPU it runs on and keeps the
  * fastest.  Built for two-word rows with 769..1024 partitions; KAO_E_ARG otherwise.  The environment

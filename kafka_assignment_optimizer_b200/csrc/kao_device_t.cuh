@@ -27,8 +27,11 @@ namespace kao {
 // shape: every shared-memory offset of the evaluator is then an immediate), 0 = read at run time.
 // The other parameters are SCHEDULES of the same arithmetic (kao_set_schedule; results identical):
 //   kSync      how the warps of a CTA meet before an evaluation: 0 block barrier (all warps walk the
-//              evaluator together: instruction cache), 1 warp only, 2 one named barrier per scheduler
-//   kCompress  1: carry-save compression of the column / leader / bonus popcount streams
+//              evaluator together: instruction cache), 1 warp only, 2 one named barrier per scheduler,
+//              3 two groups that each hold half of every scheduler's warps (one group can generate
+//              while the other evaluates)
+//   kCompress  carry-save compression of popcount streams: 0 none, 1 column / leader / bonus totals,
+//              2 also the two objective streams (pooled over the lane's slots)
 //   kThreads   threads per CTA (0 = threads_for<W>()); fewer threads = more registers per thread
 //   kUnroll    unroll factor of the column chunk loop
 template <int W_, int kNW_ = 0, int kSync_ = 0, int kCompress_ = 1, int kThreads_ = 0, int kUnroll_ = 1> struct EvalCfgT {
@@ -164,7 +167,7 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
         }
     }
     // ---- columns: this lane owns slot `lane` of every row word
-    int cnt[W], lcnt[W], cnt2[W], lcnt2[W], o0 = 0, o1 = 0, o2 = 0, o2b = 0;
+    int cnt[W], lcnt[W], cnt2[W], lcnt2[W], o0 = 0, o1 = 0, o2 = 0, o2b = 0, o0b = 0, o1b = 0;
 #pragma unroll
     for (int t = 0; t < W; ++t) cnt[t] = lcnt[t] = cnt2[t] = lcnt2[t] = 0;
     const int rot = nW >= 32 ? 4 * (lane & 7) : 0;
@@ -206,11 +209,12 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
         // (totals of a column, valid leaders of a column, leader bonus); the doubled parts are summed
         // apart and weighted once per candidate.
         uint32_t hit[4];                            // leader bonus: the one-hot columns of a lane are disjoint
+        uint32_t y0[4 * W], y1[4 * W];              // objective streams (kCompress 2)
 #pragma unroll
         for (int i = 0; i < 4; ++i) hit[i] = 0;
 #pragma unroll
         for (int t = 0; t < W; ++t) {
-            if constexpr (Cfg::kCompress) {
+            if constexpr (Cfg::kCompress >= 1) {
                 uint32_t h, l;
                 csa(h, l, col[t].x, col[t].y, col[t].z);
                 cnt[t] += __popc(l) + __popc(col[t].w);
@@ -222,16 +226,36 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const uint32_t c = comp(col[t], i);
-                if constexpr (!Cfg::kCompress) {
+                if constexpr (Cfg::kCompress == 0) {
                     cnt[t] += __popc(c);
                     lcnt[t] += __popc(comp(oh[t], i));
                 }
-                o0 += __popc(c & comp(m0[t], i));
-                o1 += __popc(c & comp(m1[t], i));
+                if constexpr (Cfg::kCompress >= 2) {
+                    y0[4 * t + i] = c & comp(m0[t], i);
+                    y1[4 * t + i] = c & comp(m1[t], i);
+                } else {
+                    o0 += __popc(c & comp(m0[t], i));
+                    o1 += __popc(c & comp(m1[t], i));
+                }
                 hit[i] |= comp(oh[t], i) & comp(m2[t], i);
             }
         }
-        if constexpr (Cfg::kCompress) {
+        if constexpr (Cfg::kCompress >= 2) {
+            // 4 * W words per stream: every full group of three goes through one carry-save adder
+#pragma unroll
+            for (int g = 0; g + 3 <= 4 * W; g += 3) {
+                uint32_t h, l;
+                csa(h, l, y0[g], y0[g + 1], y0[g + 2]);
+                o0 += __popc(l);
+                o0b += __popc(h);
+                csa(h, l, y1[g], y1[g + 1], y1[g + 2]);
+                o1 += __popc(l);
+                o1b += __popc(h);
+            }
+#pragma unroll
+            for (int g = (4 * W) / 3 * 3; g < 4 * W; ++g) { o0 += __popc(y0[g]); o1 += __popc(y1[g]); }
+        }
+        if constexpr (Cfg::kCompress >= 1) {
             uint32_t h, l;
             csa(h, l, hit[0], hit[1], hit[2]);
             o2 += __popc(l) + __popc(hit[3]);
@@ -243,6 +267,8 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
 #pragma unroll
     for (int t = 0; t < W; ++t) { cnt[t] += 2 * cnt2[t]; lcnt[t] += 2 * lcnt2[t]; }
     o2 += 2 * o2b;
+    o0 += 2 * o0b;
+    o1 += 2 * o1b;
     // ---- C3 / C4 on this lane's columns, C2/C5 as P - sum of valid leaders, C6 per 8-lane rack group
 #pragma unroll
     for (int t = 0; t < W; ++t) {

@@ -34,7 +34,7 @@ extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 0);
 extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 32);
 extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 32);
 #define KAO_DECL_TUNE(S, C, T, U) extern template __global__ void KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U);
-KAO_FOR_TUNE_SYNC(KAO_DECL_TUNE, 0) KAO_FOR_TUNE_SYNC(KAO_DECL_TUNE, 1) KAO_FOR_TUNE_SYNC(KAO_DECL_TUNE, 2)
+KAO_FOR_TUNE_ALL(KAO_DECL_TUNE)
 
 
 // Winner of a round becomes the base: re-materialise its patches from (seed, round, index), write
@@ -288,7 +288,7 @@ static cudaError_t launch_persistent(kao_handle *h, const PersistArgs &pa, bool 
 #define KAO_RUN_TUNE(S, C, T, U)                                                                       \
     if (h->sch_sync == S && h->sch_compress == C && h->sch_threads == T && h->sch_unroll == U)           \
         return LaunchPersistent<false>{}.template run<KAO_TUNE_CFG(S, C, T, U)>(h, pa);
-            KAO_FOR_TUNE_SYNC(KAO_RUN_TUNE, 0) KAO_FOR_TUNE_SYNC(KAO_RUN_TUNE, 1) KAO_FOR_TUNE_SYNC(KAO_RUN_TUNE, 2)
+            KAO_FOR_TUNE_ALL(KAO_RUN_TUNE)
 #undef KAO_RUN_TUNE
         }
         if (h->hm.Ppad == 1024)                                 // 32 partition words per slot: compile-time offsets
@@ -586,7 +586,7 @@ extern "C" int kao_set_evaluator(kao_handle *h, int32_t evaluator)
 static bool schedule_exists(int sync, int compress, int threads, int unroll)
 {
 #define KAO_HAS_TUNE(S, C, T, U) if (sync == S && compress == C && threads == T && unroll == U) return true;
-    KAO_FOR_TUNE_SYNC(KAO_HAS_TUNE, 0) KAO_FOR_TUNE_SYNC(KAO_HAS_TUNE, 1) KAO_FOR_TUNE_SYNC(KAO_HAS_TUNE, 2)
+    KAO_FOR_TUNE_ALL(KAO_HAS_TUNE)
 #undef KAO_HAS_TUNE
     return false;
 }
@@ -595,7 +595,7 @@ extern "C" int kao_set_schedule(kao_handle *h, int32_t sync, int32_t compress, i
 {
     if (!h) return fail(KAO_E_ARG, "null handle");
     if (!schedule_exists(sync, compress, threads, unroll))
-        return fail(KAO_E_ARG, "no such schedule: sync 0..2, compress 0..1, (threads, unroll) one of (768,1) (512,1) (512,2)");
+        return fail(KAO_E_ARG, "no such schedule: sync 0..3, compress 0..2, (threads, unroll) one of (768,1) (512,1) (512,2)");
     if (!(h->trans_ok && h->hm.W == 2 && h->hm.Ppad == 1024) && !(sync == 0 && compress == 1 && threads == KAO_THREADS && unroll == 1))
         return fail(KAO_E_ARG, "schedules other than the default are built for two-word rows with 769..1024 partitions");
     h->sch_sync = sync; h->sch_compress = compress; h->sch_threads = threads; h->sch_unroll = unroll;

@@ -427,7 +427,8 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 // rows were written by lane 0 of this warp, so a warp-level sync is enough for correctness)
                 if constexpr (Cfg::kSync == 0) __syncthreads();
                 else if constexpr (Cfg::kSync == 1) __syncwarp();
-                else asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(THREADS / 4) : "memory");
+                else if constexpr (Cfg::kSync == 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(THREADS / 4) : "memory");
+                else asm volatile("bar.sync %0, %1;" ::"r"(1 + ((warp >> 2) & 1)), "r"(THREADS / 2) : "memory");
             } else {
                 __syncthreads();
             }
@@ -578,7 +579,9 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     search_persistent_kernel<KAO_TUNE_CFG(S, C, T, U), T, false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
                                                                  uint32_t, unsigned long long *, unsigned int *, P2P, \
                                                                  unsigned long long *)
-#define KAO_FOR_TUNE_SYNC(X, S) X(S, 1, 768, 1) X(S, 0, 768, 1) X(S, 1, 512, 1) X(S, 0, 512, 1) X(S, 1, 512, 2) X(S, 0, 512, 2)
+#define KAO_FOR_TUNE_TU(X, S, T, U) X(S, 1, T, U) X(S, 0, T, U) X(S, 2, T, U)
+#define KAO_FOR_TUNE_SYNC(X, S) KAO_FOR_TUNE_TU(X, S, 768, 1) KAO_FOR_TUNE_TU(X, S, 512, 1) KAO_FOR_TUNE_TU(X, S, 512, 2)
+#define KAO_FOR_TUNE_ALL(X) KAO_FOR_TUNE_SYNC(X, 0) KAO_FOR_TUNE_SYNC(X, 1) KAO_FOR_TUNE_SYNC(X, 2) KAO_FOR_TUNE_SYNC(X, 3)
 #define KAO_PERSISTENT_KERNEL(W, NPH, R, O, T, DELTA)                                                       \
     search_persistent_kernel<EvalCfg<W, NPH, R, O>, T, DELTA>(Params, SmemPlan, uint64_t, uint32_t, uint32_t,      \
                                                              uint32_t, unsigned long long *, unsigned int *, P2P, \

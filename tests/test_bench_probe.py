@@ -58,5 +58,5 @@ def test_partial_output_of_a_crashed_or_hung_child_counts(monkeypatch):
 
 
 def test_schedule_list_matches_the_engine():
-    assert len(bench.SCHEDULES) == 18 and bench.DEFAULT_SCHEDULE in bench.SCHEDULES
+    assert len(bench.SCHEDULES) == 36 and bench.DEFAULT_SCHEDULE in bench.SCHEDULES
     assert {(t, u) for _, _, t, u in bench.SCHEDULES} == {(768, 1), (512, 1), (512, 2)}

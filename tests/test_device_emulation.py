@@ -175,7 +175,7 @@ def test_column_major_forms_agree(emu):
     sess = emu.EmuSession(product(pb))
     assert sess.set_evaluator(1)
     fixed = sess.candidate_keys(0x5EED, 3, 4096, 100, 96)
-    for form in (2, 3, 4):               # run-time word count, plain popcounts, unrolled column loop
+    for form in (2, 3, 4, 5):            # run-time word count, plain popcounts, unrolled column loop, five compressed streams
         assert sess.set_evaluator(form)
         assert (fixed == sess.candidate_keys(0x5EED, 3, 4096, 100, 96)).all()
     assert sess.set_evaluator(0)
@@ -183,8 +183,9 @@ def test_column_major_forms_agree(emu):
     sess.close()
 
 
-def test_column_major_plain_popcounts_on_a_malformed_base(emu, ref_lib):
-    pb = COLUMN_MAJOR["rf4_w2"]()
+@pytest.mark.parametrize("name", ["rf4_w2", "cfg2_rm2"])          # two-word and one-word rows
+def test_column_major_forms_on_a_malformed_base(emu, ref_lib, name):
+    pb = COLUMN_MAJOR[name]()
     r = ref_lib.Ref(pb)
     rng = np.random.RandomState(9)
     reps = np.stack([rng.choice(pb.B, size=pb.RF, replace=False) for _ in range(pb.P)]).astype(np.int32)
@@ -193,7 +194,7 @@ def test_column_major_plain_popcounts_on_a_malformed_base(emu, ref_lib):
     bits, ld = r.encode(reps)
     want = r.candidate_keys(bits, ld, 21, 2, 256, 0, 48)
     sess = emu.EmuSession(product(pb))
-    for form in (1, 3, 4):
+    for form in (1, 3, 4, 5):
         assert sess.set_evaluator(form)
         sess.set_base(reps)
         assert (want == sess.candidate_keys(21, 2, 256, 0, 48)).all()

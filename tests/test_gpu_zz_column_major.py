@@ -117,9 +117,9 @@ def test_every_schedule_gives_the_same_keys():
     want_traj, _ = base.search(0x5EED, 0, 4, 16384)
     want_base = base.get_base()[0]
     base.close()
-    for sync in (0, 1, 2):
+    for sync in (0, 1, 2, 3):
         for threads, unroll in ((768, 1), (512, 1), (512, 2)):
-            for compress in (1, 0):
+            for compress in (1, 0, 2):
                 sess = kao.Session(product(pb))
                 assert sess.set_evaluator(True) and sess.set_schedule(sync, compress, threads, unroll)
                 assert (want_keys == sess.candidate_keys(0x5EED, 1, 8192, 0, 8192)).all(), (sync, compress, threads, unroll)
