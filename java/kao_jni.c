@@ -33,7 +33,8 @@ JNIEXPORT jint JNICALL Java_ch_sqooba_kao_KaoNative_solve(
     pb.rack_lo = (const int32_t *)bd + 4 * B; pb.rack_hi = (const int32_t *)bd + 4 * B + R;
     pb.ppr_lo = bd[4 * B + 2 * R];            pb.ppr_hi = bd[4 * B + 2 * R + 1];
     pb.cur = (const int32_t *)cu;
-    kao_options opt = {(uint64_t)seed, (uint32_t)rounds, (uint32_t)roundSize, device, 0};
+    /* KAO_FLAG_COLUMN_MAJOR is a hint: layouts the column-major evaluator does not cover keep the default one */
+    kao_options opt = {(uint64_t)seed, (uint32_t)rounds, (uint32_t)roundSize, device, KAO_FLAG_COLUMN_MAJOR};
     kao_result res;
     res.replicas = (int32_t *)out;
     const int rc = kao_solve(&pb, &opt, &res);

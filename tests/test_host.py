@@ -83,3 +83,15 @@ def test_json_codec_readme_shapes():
     doc = kprob.reassignment_json(pb, np.array([[7, 18], [8, 1]] + [[0, 1]] * 8))
     assert doc["version"] == 1 and doc["partitions"][1] == {"topic": "x.y.z.t", "partition": 1, "replicas": [8, 1]}
     json.dumps(doc)
+
+
+def test_jni_shim_type_checks_against_the_abi():
+    """java/kao_jni.c cannot be built here (no JDK): type-check it against include/kao.h with a stub
+    <jni.h> that declares the JNI entries it uses with the specification's signatures."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(root, "tests", "jni_stub"), "-I", os.path.join(root, "include"),
+                        os.path.join(root, "java", "kao_jni.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
