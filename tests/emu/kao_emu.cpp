@@ -240,7 +240,8 @@ void *kao_emu_create(const kao_problem *pb)
     e->oh = m.W <= 2 && e->obj > 0;
     // kao_set_evaluator: the column-major evaluator covers 8-slot rack fields with C7 = "at most one
     // replica per rack" and three mask planes
-    e->trans_ok = m.W <= 2 && m.hi1 && m.log2S == 3 && m.nplanes == 3;
+    e->trans_ok = m.W <= 2 && m.hi1 && m.log2S == 3 && m.nplanes == 3 &&
+                  make_plan(m.W, m.Ppad, threads / 32, kTPlanes * m.W, m.P, m.RF, false).total <= 227u * 1024u;
     e->nW = m.Ppad / 32;
     fill_consts(m, e->cs);
     Params &p = e->prm;

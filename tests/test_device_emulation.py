@@ -115,7 +115,9 @@ def test_explicit_evaluation_matches_exact_model(emu, name):
 # ---- column-major full evaluator (csrc/kao_device_t.cuh) --------------------------------------
 COLUMN_MAJOR = {
     "cfg2": SHAPES["cfg2"], "cfg2_rm2": SHAPES["cfg2_rm2"], "cfg3_small": SHAPES["cfg3_small"],
-    "rf1": SHAPES["rf1"], "rf_down": SHAPES["rf_down"], "max_rows": SHAPES["max_rows"],
+    "rf1": SHAPES["rf1"], "rf_down": SHAPES["rf_down"],
+    "w1_6000": lambda: m.synthetic_problem(6000, 32, 4, 3, remove=1),      # 188 partition words: six per lane, rotated rows wrap
+    "w2_4000": lambda: m.synthetic_problem(4000, 64, 8, 3),                # the largest two-word shape whose planes fit
     "rf4_w2": lambda: m.synthetic_problem(300, 40, 5, 4, remove=3),
     "r8_b61": lambda: m.synthetic_problem(96, 61, 8, 3),                   # unequal racks, padding slots
     "p1100": lambda: m.synthetic_problem(1100, 64, 8, 3, remove=2),        # 40 partition words: two per lane
@@ -123,7 +125,7 @@ COLUMN_MAJOR = {
 }
 
 
-@pytest.mark.parametrize("name", ["cfg2", "cfg2_rm2", "cfg3_small", "rf1", "rf_down", "max_rows"])
+@pytest.mark.parametrize("name", ["cfg2", "cfg2_rm2", "cfg3_small", "rf1", "rf_down"])
 def test_column_major_evaluator_reproduces_golden_streams(emu, golden_streams, name):
     g = golden_streams[name]
     sess = emu.EmuSession(product(SHAPES[name]()))
@@ -202,7 +204,8 @@ def test_column_major_forms_on_a_malformed_base(emu, ref_lib, name):
 
 
 def test_column_major_evaluator_refuses_other_layouts(emu):
-    for name in ["readme", "s32", "w8_s16", "dense_small", "rf_up"]:
+    # general rack bounds, whole-word racks, wide rows, dense weights, C7 lower bound, planes too large for shared memory
+    for name in ["readme", "s32", "w8_s16", "dense_small", "rf_up", "max_rows"]:
         sess = emu.EmuSession(product(SHAPES[name]()))
         assert not sess.set_evaluator(1)
         sess.close()

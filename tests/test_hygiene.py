@@ -27,3 +27,21 @@ def test_bench_uses_the_oracle_only_in_its_cpu_legs():
         fn = src.rfind("\ndef ", 0, mt.start())
         name = re.match(r"\ndef (\w+)", src[fn:]).group(1)
         assert name in ("cpu_port_rate", "reference_arm"), name
+
+
+def test_host_emulation_stays_out_of_the_product():
+    """tests/emu compiles the device headers for the host (KAO_HOST_EMU) as a checker; the product's
+    build never defines that macro and libkao.so carries none of the emulation's symbols."""
+    import subprocess
+
+    mk = open(os.path.join(PKG, "csrc", "Makefile")).read()
+    assert "KAO_HOST_EMU" not in mk and "tests/" not in mk and "emu" not in mk
+    for base, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".hpp")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert "kao_emu" not in text and "warp_emu" not in text, f
+    so = os.path.join(PKG, "libkao.so")
+    if os.path.exists(so):
+        syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+        assert "kao_emu" not in syms and "kao_solve" in syms
