@@ -209,3 +209,23 @@ def test_column_major_evaluator_refuses_other_layouts(emu):
         sess = emu.EmuSession(product(SHAPES[name]()))
         assert not sess.set_evaluator(1)
         sess.close()
+
+
+@pytest.mark.parametrize("form", [1, 2, 5])
+def test_column_major_long_stream_on_the_headline_shape(emu, ref_lib, form):
+    """Config 3 (1000 x 64 x 8, RF 3): 12,000 candidates of four rounds against the restatement, with
+    the base moved by winners in between (1-, 2- and 3-row patches in every chunk of the column walk)."""
+    pb = COLUMN_MAJOR["cfg3"]()
+    r = ref_lib.Ref(pb)
+    bits, ld = r.init_base()
+    sess = emu.EmuSession(product(pb))
+    assert sess.set_evaluator(form)
+    for rnd in range(4):
+        want = r.candidate_keys(bits, ld, 0xFACE, rnd, 3000, 0, 3000)
+        got = sess.candidate_keys(0xFACE, rnd, 3000, 0, 3000)
+        bad = np.flatnonzero(want != got)
+        assert bad.size == 0, (rnd, int(bad[0]), kao.unpack_key(want[bad[0]]), kao.unpack_key(got[bad[0]]))
+        _, wk = r.search(bits, ld, 0xFACE, rnd, 1, 3000)
+        assert (wk == sess.search(0xFACE, rnd, 1, 3000)).all()
+    assert (sess.get_base()[0] == r.decode(bits, ld)).all()
+    sess.close()
