@@ -34,9 +34,11 @@ namespace kao {
 //              2 also the two objective streams (pooled over the lane's slots)
 //   kThreads   threads per CTA (0 = threads_for<W>()); fewer threads = more registers per thread
 //   kUnroll    unroll factor of the column chunk loop
-template <int W_, int kNW_ = 0, int kSync_ = 0, int kCompress_ = 1, int kThreads_ = 0, int kUnroll_ = 1> struct EvalCfgT {
+//   kRoll      1: the row pass loops over pairs of rack fields instead of being unrolled (a quarter of
+//              the code: matters when the warps of a scheduler are not in step and share the instruction cache)
+template <int W_, int kNW_ = 0, int kSync_ = 0, int kCompress_ = 1, int kThreads_ = 0, int kUnroll_ = 1, int kRoll_ = 0> struct EvalCfgT {
     static constexpr int W = W_, NPH = 3, kRack = 3, kObj = 3, kNW = kNW_;
-    static constexpr int kSync = kSync_, kCompress = kCompress_, kThreads = kThreads_, kUnroll = kUnroll_;
+    static constexpr int kSync = kSync_, kCompress = kCompress_, kThreads = kThreads_, kUnroll = kUnroll_, kRoll = kRoll_;
     static constexpr bool kTrans = true;
 };
 constexpr int kTPlanes = 5;
@@ -54,7 +56,7 @@ __host__ __device__ __forceinline__ int t_word(int q, int s, int w, int nW, int 
 // ------------------------------------------------------------------------------------------
 // rows: C1 + C7 of every partition that is not patched, bit-sliced over 32 partitions per lane
 // ------------------------------------------------------------------------------------------
-template <int W, bool kShared, int kNW>
+template <int W, bool kShared, int kNW, int kRoll>
 __device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, int nW_rt, int P, int RF, int lane, const PatchSet &ps)
 {
     const int nW = kNW ? kNW : nW_rt;
@@ -78,7 +80,7 @@ __device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, int nW_rt
         uint32_t ones = 0, twos = 0, fours = 0;     // n_p, weights 1 2 4
         uint32_t e1 = 0, e2 = 0, e4 = 0, e8 = 0;    // n_p, weights 8 16 32 64
         uint32_t z1 = 0, z2 = 0, z4 = 0, z8 = 0;    // non-empty fields of p, 0..8
-#pragma unroll
+#pragma unroll (kRoll ? 1 : NB / 2)
         for (int b = 0; b < NB; b += 2) {
             uint32_t o8[2], ne[2];
 #pragma unroll
@@ -155,7 +157,7 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
     const int nW = kNW ? kNW : nW_rt;
     const MemRef<kShared> T(Tp);
     // ---- rows: unpatched partitions from the transposed bit-plane, patched ones from the patch
-    int viol = rows_vertical<W, kShared, kNW>(T, nW, d.P, d.RF, lane, ps);
+    int viol = rows_vertical<W, kShared, kNW, Cfg::kRoll>(T, nW, d.P, d.RF, lane, ps);
     if (lane < kMaxOps) {
         const int i = lane;
         const int pp = i == 0 ? ps.p[0] : (i == 1 ? ps.p[1] : ps.p[2]);

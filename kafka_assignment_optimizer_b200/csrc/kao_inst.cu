@@ -15,8 +15,16 @@
 
 #if defined(KAO_INST_TUNE) && KAO_INST_TUNE >= 0
 // schedules of the column-major evaluator (kao_set_schedule), one object per barrier form
-#define KAO_INST_TUNE_K(S, C, T, U) template __global__ void KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U);
-KAO_FOR_TUNE_SYNC(KAO_INST_TUNE_K, KAO_INST_TUNE)
+#define KAO_INST_TUNE_K(S, C, T, U, RL) template __global__ void KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U, RL);
+#if KAO_INST_TUNE == 0
+KAO_FOR_TUNE_SYNC_0(KAO_INST_TUNE_K)
+#elif KAO_INST_TUNE == 1
+KAO_FOR_TUNE_SYNC_1(KAO_INST_TUNE_K)
+#elif KAO_INST_TUNE == 2
+KAO_FOR_TUNE_SYNC_2(KAO_INST_TUNE_K)
+#else
+KAO_FOR_TUNE_SYNC_3(KAO_INST_TUNE_K)
+#endif
 #elif defined(KAO_INST_TRANS) && KAO_INST_TRANS
 // column-major evaluator (kao_device_t.cuh): rows of up to 64 slots
 template __global__ void KAO_PERSISTENT_KERNEL_T(KAO_INST_W, 0);

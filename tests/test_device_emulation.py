@@ -177,7 +177,7 @@ def test_column_major_forms_agree(emu):
     sess = emu.EmuSession(product(pb))
     assert sess.set_evaluator(1)
     fixed = sess.candidate_keys(0x5EED, 3, 4096, 100, 96)
-    for form in (2, 3, 4, 5):            # run-time word count, plain popcounts, unrolled column loop, five compressed streams
+    for form in (2, 3, 4, 5, 6):         # run-time word count, plain popcounts, unrolled column loop, five compressed streams, rolled row pass
         assert sess.set_evaluator(form)
         assert (fixed == sess.candidate_keys(0x5EED, 3, 4096, 100, 96)).all()
     assert sess.set_evaluator(0)
@@ -196,7 +196,7 @@ def test_column_major_forms_on_a_malformed_base(emu, ref_lib, name):
     bits, ld = r.encode(reps)
     want = r.candidate_keys(bits, ld, 21, 2, 256, 0, 48)
     sess = emu.EmuSession(product(pb))
-    for form in (1, 3, 4, 5):
+    for form in (1, 3, 4, 5, 6):
         assert sess.set_evaluator(form)
         sess.set_base(reps)
         assert (want == sess.candidate_keys(21, 2, 256, 0, 48)).all()

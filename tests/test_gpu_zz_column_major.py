@@ -135,16 +135,16 @@ def test_every_schedule_gives_the_same_keys():
     want_traj, _ = base.search(0x5EED, 0, 4, 16384)
     want_base = base.get_base()[0]
     base.close()
-    for sync in (0, 1, 2, 3):
-        for threads, unroll in ((768, 1), (512, 1), (512, 2)):
-            for compress in (1, 0, 2):
-                sess = kao.Session(product(pb))
-                assert sess.set_evaluator(True) and sess.set_schedule(sync, compress, threads, unroll)
-                assert (want_keys == sess.candidate_keys(0x5EED, 1, 8192, 0, 8192)).all(), (sync, compress, threads, unroll)
-                got, _ = sess.search(0x5EED, 0, 4, 16384)
-                assert (want_traj == got).all() and (want_base == sess.get_base()[0]).all(), (sync, compress, threads, unroll)
-                sess.close()
+    import bench
+
+    for sched in bench.SCHEDULES:                       # (sync, compress, threads, unroll, roll)
+        sess = kao.Session(product(pb))
+        assert sess.set_evaluator(True) and sess.set_schedule(*sched), sched
+        assert (want_keys == sess.candidate_keys(0x5EED, 1, 8192, 0, 8192)).all(), sched
+        got, _ = sess.search(0x5EED, 0, 4, 16384)
+        assert (want_traj == got).all() and (want_base == sess.get_base()[0]).all(), sched
+        sess.close()
     small = kao.Session(product(SHAPES["cfg2"]()))
-    assert small.set_evaluator(True) and not small.set_schedule(1, 1, 512, 2)      # built for the headline layout only
-    assert small.set_schedule(0, 1, 768, 1)
+    assert small.set_evaluator(True) and not small.set_schedule(1, 1, 512, 2, 0)   # built for the headline layout only
+    assert small.set_schedule(0, 1, 768, 1, 0) and not small.set_schedule(0, 1, 768, 1, 1)
     small.close()
