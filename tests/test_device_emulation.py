@@ -229,3 +229,47 @@ def test_column_major_long_stream_on_the_headline_shape(emu, ref_lib, form):
         assert (wk == sess.search(0xFACE, rnd, 1, 3000)).all()
     assert (sess.get_base()[0] == r.decode(bits, ld)).all()
     sess.close()
+
+
+def test_column_major_vs_row_major_on_random_topologies(emu):
+    """Seeded fuzz: 2..8 racks of 3..8 brokers, RF 1..4, 1..4 current replicas, 5..700 partitions, 0..2
+    brokers removed.  Wherever the column-major evaluator accepts the layout, three of its forms give
+    the row-major evaluator's keys, from the initial base and from a damaged one, and the base it
+    reaches evaluates like the exact model."""
+    from conftest import make_problem
+
+    rng = np.random.RandomState(123)
+    tested = 0
+    for trial in range(40):
+        R = int(rng.randint(2, 9))
+        sizes = [int(rng.randint(3, 9)) for _ in range(R)]
+        RF = int(rng.randint(1, min(R, 4) + 1))
+        RFcur = int(rng.randint(1, 5))
+        P = int(rng.choice([5, 31, 32, 33, 64, 100, 129, 257, 700]))
+        removed = int(rng.randint(0, 3))
+        try:
+            pb = make_problem(P, sizes, RF, RFcur=RFcur, seed=trial, removed=removed)
+            sess = emu.EmuSession(product(pb))
+        except Exception:            # noqa: BLE001 — topologies the model builder or the engine rejects are not the subject
+            continue
+        if not sess.set_evaluator(1):
+            sess.close()
+            continue
+        tested += 1
+        for it in range(2):
+            if it == 1:
+                reps = np.stack([rng.choice(pb.B, size=pb.RF, replace=False) for _ in range(pb.P)]).astype(np.int32)
+                reps[rng.randint(pb.P), -1] = -1
+                sess.set_base(reps)
+            keys = {}
+            for form in (0, 1, 5, 6):
+                assert sess.set_evaluator(form)
+                keys[form] = sess.candidate_keys(77 + trial, it, 300, 0, 300)
+            for form in (1, 5, 6):
+                assert (keys[0] == keys[form]).all(), (trial, sizes, RF, RFcur, P, form)
+            assert sess.set_evaluator(1)
+            sess.search(5 + trial, 0, 2, 128)
+            reps, v, o, _ = sess.get_base()
+            assert (v, o) == m.evaluate(pb, reps), trial
+        sess.close()
+    assert tested >= 20
