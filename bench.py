@@ -83,10 +83,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# (sync, compress, threads, unroll, roll) — the variants csrc/kao_kernels.cuh builds (KAO_FOR_TUNE_ALL)
-SCHEDULES = ([(sy, c, t, u, 0) for sy in (0, 1, 2, 3) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 0, 2)] +
-             [(sy, c, t, u, 1) for sy in (1, 3) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 2)])
-DEFAULT_SCHEDULE = (0, 1, 768, 1, 0)
+# (sync, compress, threads, unroll, roll, fuse) — the variants csrc/kao_kernels.cuh builds (KAO_FOR_TUNE_ALL)
+SCHEDULES = ([(sy, c, t, u, 0, 0) for sy in (0, 1, 2, 3) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 0, 2)] +
+             [(sy, c, t, u, 1, 0) for sy in (1, 3) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 2)] +
+             [(sy, c, t, 1, 0, 1) for sy in (0, 1, 2, 3) for t in (512, 768) for c in (1, 2)])
+DEFAULT_SCHEDULE = (0, 1, 768, 1, 0, 0)
 
 
 def probe_evaluators(device):
@@ -133,7 +134,7 @@ def probe_evaluators(device):
     print("PROBE " + json.dumps(run("column_major", True, None)), flush=True)
     for sched in SCHEDULES:
         if sched != DEFAULT_SCHEDULE:
-            print("PROBE " + json.dumps(run("column_major sync=%d compress=%d threads=%d unroll=%d roll=%d" % sched, True, sched)), flush=True)
+            print("PROBE " + json.dumps(run("column_major sync=%d compress=%d threads=%d unroll=%d roll=%d fuse=%d" % sched, True, sched)), flush=True)
     return 0
 
 
@@ -287,7 +288,7 @@ def main():
         use_col, sched, eval_report = False, None, dict(eval_report, selected="row_major", note="column-major refused by the session")
     if use_col and sched is not None:
         if sess.set_schedule(*sched):
-            os.environ["KAO_SCHEDULE"] = "%d,%d,%d,%d,%d" % sched   # kao_solve (the e2e leg) creates its own sessions
+            os.environ["KAO_SCHEDULE"] = "%d,%d,%d,%d,%d,%d" % sched   # kao_solve (the e2e leg) creates its own sessions
         else:
             sched = None
     gsize = ROUND_SIZE * world                               # weak scaling: per-GPU work fixed
@@ -362,7 +363,7 @@ def main():
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic,
-                    "kernel": ("search_persistent_kernel<EvalCfgT<W=2,words=32,sync=%d,compress=%d,threads=%d,unroll=%d,roll=%d>> (column-major evaluator)"
+                    "kernel": ("search_persistent_kernel<EvalCfgT<W=2,words=32,sync=%d,compress=%d,threads=%d,unroll=%d,roll=%d,fuse=%d>> (column-major evaluator)"
                                % (sched or DEFAULT_SCHEDULE) if use_col else
                                "search_persistent_kernel<EvalCfg<W=2,NPH=3,rack=8-slot hi1,planes=3>,768>"),
                     "algorithmic_bytes_per_candidate": ALGO_BYTES, "candidates_per_launch": ROUND_SIZE * ROUNDS,

@@ -157,11 +157,14 @@ int kao_set_evaluator(kao_handle *h, int32_t evaluator);
  * scheduler, 3 two half-CTA groups); compress: carry-save compression of popcount streams (0 none, 1
  * three streams, 2 five);
  * (threads per CTA, unroll of the column loop): (768,1), (512,1) or (512,2); roll: 1 = the row pass as
- * a loop instead of unrolled (built for sync 1 / 3 with compress 1 / 2).  Default (0, 1, 768, 1, 0).
+ * a loop instead of unrolled (built for sync 1 / 3 with compress 1 / 2); fuse: 1 = the row network is
+ * folded into the column loop, one rack field per chunk (compress 1 / 2, unroll 1, roll 0).  Default
+ * (0, 1, 768, 1, 0, 0).
  * Results never depend on it; bench.py measures the variants on the GPU it runs on and keeps the
  * fastest.  Built for two-word rows with 769..1024 partitions; KAO_E_ARG otherwise.  The environment
- * variable KAO_SCHEDULE="sync,compress,threads,unroll,roll" sets it for every session (and kao_solve). */
-int kao_set_schedule(kao_handle *h, int32_t sync, int32_t compress, int32_t threads, int32_t unroll, int32_t roll);
+ * variable KAO_SCHEDULE="sync,compress,threads,unroll,roll,fuse" sets it for every session (and kao_solve). */
+int kao_set_schedule(kao_handle *h, int32_t sync, int32_t compress, int32_t threads, int32_t unroll, int32_t roll,
+                     int32_t fuse);
 int kao_last_rounds(kao_handle *h, uint32_t *rounds_run);
 
 /* keys of candidates idx_begin .. idx_begin+count-1 of `round` against the current base (host

@@ -36,9 +36,14 @@ namespace kao {
 //   kUnroll    unroll factor of the column chunk loop
 //   kRoll      1: the row pass loops over pairs of rack fields instead of being unrolled (a quarter of
 //              the code: matters when the warps of a scheduler are not in step and share the instruction cache)
-template <int W_, int kNW_ = 0, int kSync_ = 0, int kCompress_ = 1, int kThreads_ = 0, int kUnroll_ = 1, int kRoll_ = 0> struct EvalCfgT {
+//   kFuse      1 (two-word rows, 32 partition words): the row network is not a pass of its own — column
+//              chunk j also folds rack field j into it, so that the ALU work of the rows and the
+//              popcounts of the columns overlap inside one warp even when all warps are in step
+template <int W_, int kNW_ = 0, int kSync_ = 0, int kCompress_ = 1, int kThreads_ = 0, int kUnroll_ = 1, int kRoll_ = 0, int kFuse_ = 0>
+struct EvalCfgT {
     static constexpr int W = W_, NPH = 3, kRack = 3, kObj = 3, kNW = kNW_;
-    static constexpr int kSync = kSync_, kCompress = kCompress_, kThreads = kThreads_, kUnroll = kUnroll_, kRoll = kRoll_;
+    static constexpr int kSync = kSync_, kCompress = kCompress_, kThreads = kThreads_, kUnroll = kUnroll_, kRoll = kRoll_, kFuse = kFuse_;
+    static_assert(!kFuse_ || (W_ == 2 && kNW_ == 32), "fused passes: one rack field per column chunk");
     static constexpr bool kTrans = true;
 };
 constexpr int kTPlanes = 5;
@@ -145,6 +150,48 @@ __device__ __forceinline__ void set_comp(uint4 &v, int k, uint32_t clear, uint32
     else v.w = (v.w & ~clear) | set;
 }
 
+// Row network held across the column loop (kFuse): the planes of rows_vertical, one rack field at a time.
+struct RowNet {
+    uint32_t ones = 0, twos = 0, fours = 0, e1 = 0, e2 = 0, e4 = 0, e8 = 0, z1 = 0, z2 = 0, z4 = 0, z8 = 0;
+    __device__ __forceinline__ void fold(const uint32_t (&x)[8])
+    {
+        uint32_t a2, b2, qa, qb, o8;
+        csa(a2, ones, ones, x[0], x[1]);
+        csa(b2, ones, ones, x[2], x[3]);
+        csa(qa, twos, twos, a2, b2);
+        csa(a2, ones, ones, x[4], x[5]);
+        csa(b2, ones, ones, x[6], x[7]);
+        csa(qb, twos, twos, a2, b2);
+        csa(o8, fours, fours, qa, qb);
+        const uint32_t ne = (x[0] | x[1] | x[2]) | (x[3] | x[4] | x[5]) | (x[6] | x[7]);
+        uint32_t c = e1 & o8; e1 ^= o8;             // + o8 at weight 8
+        uint32_t c2 = e2 & c; e2 ^= c;
+        c = e4 & c2; e4 ^= c2;
+        e8 ^= c;
+        c = z1 & ne; z1 ^= ne;                      // + 1 non-empty field
+        c2 = z2 & c; z2 ^= c;
+        c = z4 & c2; z4 ^= c2;
+        z8 ^= c;
+    }
+    __device__ __forceinline__ int charge(uint32_t valid, int RF) const
+    {
+        const uint32_t rf0 = (RF & 1) ? ~0u : 0u, rf1 = (RF & 2) ? ~0u : 0u, rf2 = (RF & 4) ? ~0u : 0u, rf3 = (RF & 8) ? ~0u : 0u;
+        uint32_t bad = (ones ^ rf0) | (twos ^ rf1) | (fours ^ rf2) | (e1 ^ rf3) | e2 | e4 | e8;
+        bad |= (z1 ^ rf0) | (z2 ^ rf1) | (z4 ^ rf2) | (z8 ^ rf3);
+        bad &= valid;
+        int viol = 0;
+        for (uint32_t m = bad; m; m &= m - 1) {
+            const int s = __ffs(m) - 1;
+            const int n = (int)(((ones >> s) & 1u) | (((twos >> s) & 1u) << 1) | (((fours >> s) & 1u) << 2) |
+                                (((e1 >> s) & 1u) << 3) | (((e2 >> s) & 1u) << 4) | (((e4 >> s) & 1u) << 5) |
+                                (((e8 >> s) & 1u) << 6));
+            const int z = (int)(((z1 >> s) & 1u) | (((z2 >> s) & 1u) << 1) | (((z4 >> s) & 1u) << 2) | (((z8 >> s) & 1u) << 3));
+            viol += abs(n - RF) + (n - z);
+        }
+        return viol;
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // the whole candidate.  T: the five transposed planes; prow: this warp's patched rows [kMaxOps * W]
 // ------------------------------------------------------------------------------------------
@@ -157,7 +204,20 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
     const int nW = kNW ? kNW : nW_rt;
     const MemRef<kShared> T(Tp);
     // ---- rows: unpatched partitions from the transposed bit-plane, patched ones from the patch
-    int viol = rows_vertical<W, kShared, kNW, Cfg::kRoll>(T, nW, d.P, d.RF, lane, ps);
+    int viol = 0;
+    RowNet net;                                     // kFuse: filled inside the column loop
+    uint32_t net_valid = 0;
+    int net_tk[8];
+    if constexpr (Cfg::kFuse) {
+        const int left = d.P - 32 * lane;           // 32 partition words: word `lane` is this lane's
+        net_valid = left >= 32 ? ~0u : (left <= 0 ? 0u : ((1u << left) - 1u));
+#pragma unroll
+        for (int i = 0; i < kMaxOps; ++i) net_valid &= ((ps.p[i] >> 5) == lane) ? ~(1u << (ps.p[i] & 31)) : ~0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) net_tk[k] = ((lane + 4 * k) & 31) * 4;
+    } else {
+        viol = rows_vertical<W, kShared, kNW, Cfg::kRoll>(T, nW, d.P, d.RF, lane, ps);
+    }
     if (lane < kMaxOps) {
         const int i = lane;
         const int pp = i == 0 ? ps.p[0] : (i == 1 ? ps.p[1] : ps.p[2]);
@@ -187,6 +247,12 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
             m0[t] = T.ld128((uint32_t)((2 * NSL + s) * nW + tw) * 4u);
             m1[t] = T.ld128((uint32_t)((3 * NSL + s) * nW + tw) * 4u);
             m2[t] = T.ld128((uint32_t)((4 * NSL + s) * nW + tw) * 4u);
+        }
+        if constexpr (Cfg::kFuse) {                 // rack field j of the row network (8 slots x this lane's word)
+            uint32_t x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = T.ld32((uint32_t)((j * 8 + k) * (nW * 4) + net_tk[k]));
+            net.fold(x);
         }
         // the candidate's patched rows replace their partition's bit in this lane's columns
         if (((ps.p[0] >> 7) == j) | ((ps.p[1] >> 7) == j) | ((ps.p[2] >> 7) == j)) {
@@ -266,6 +332,7 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
             o2 += __popc(hit[0]) + __popc(hit[1]) + __popc(hit[2]) + __popc(hit[3]);
         }
     }
+    if constexpr (Cfg::kFuse) viol += net.charge(net_valid, d.RF);
 #pragma unroll
     for (int t = 0; t < W; ++t) { cnt[t] += 2 * cnt2[t]; lcnt[t] += 2 * lcnt2[t]; }
     o2 += 2 * o2b;

@@ -33,7 +33,7 @@ extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 0);  // column-major 
 extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 0);
 extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 32);
 extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 32);
-#define KAO_DECL_TUNE(S, C, T, U, RL) extern template __global__ void KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U, RL);
+#define KAO_DECL_TUNE(S, C, T, U, RL, F) extern template __global__ void KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U, RL, F);
 KAO_FOR_TUNE_ALL(KAO_DECL_TUNE)
 
 
@@ -105,7 +105,7 @@ eval_batch_kernel(Params d, const uint32_t *cand_bits, const uint8_t *cand_leade
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
-static bool schedule_exists(int sync, int compress, int threads, int unroll, int roll);
+static bool schedule_exists(int sync, int compress, int threads, int unroll, int roll, int fuse);
 #define CUDA_TRY(expr)                                                                       \
     do {                                                                                     \
         cudaError_t e_ = (expr);                                                             \
@@ -156,7 +156,7 @@ struct kao_handle {
     SmemPlan plan_t{};
     // schedule of the column-major evaluator (kao_set_schedule): barrier form, popcount compression,
     // threads per CTA, unroll of the column loop.  Same results; (0, 1, 768, 1) is the default.
-    int sch_sync = 0, sch_compress = 1, sch_threads = KAO_THREADS, sch_unroll = 1, sch_roll = 0;
+    int sch_sync = 0, sch_compress = 1, sch_threads = KAO_THREADS, sch_unroll = 1, sch_roll = 0, sch_fuse = 0;
     // device buffers
     uint32_t *d_bits = nullptr; uint8_t *d_leader = nullptr; uint32_t *d_sw = nullptr;
     uint32_t *d_dense = nullptr; uint32_t *d_planes = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
@@ -284,10 +284,10 @@ static cudaError_t launch_persistent(kao_handle *h, const PersistArgs &pa, bool 
     if (delta) return dispatch(h, LaunchPersistent<true>{}, pa);
     if (h->evaluator == KAO_EVAL_COLUMN_MAJOR) {
         if (h->hm.Ppad == 1024 && h->hm.W == 2 &&
-            !(h->sch_sync == 0 && h->sch_compress == 1 && h->sch_threads == KAO_THREADS && h->sch_unroll == 1 && h->sch_roll == 0)) {
-#define KAO_RUN_TUNE(S, C, T, U, RL)                                                                             \
-    if (h->sch_sync == S && h->sch_compress == C && h->sch_threads == T && h->sch_unroll == U && h->sch_roll == RL) \
-        return LaunchPersistent<false>{}.template run<KAO_TUNE_CFG(S, C, T, U, RL)>(h, pa);
+            !(h->sch_sync == 0 && h->sch_compress == 1 && h->sch_threads == KAO_THREADS && h->sch_unroll == 1 && h->sch_roll == 0 && h->sch_fuse == 0)) {
+#define KAO_RUN_TUNE(S, C, T, U, RL, F)                                                                          \
+    if (h->sch_sync == S && h->sch_compress == C && h->sch_threads == T && h->sch_unroll == U && h->sch_roll == RL && h->sch_fuse == F) \
+        return LaunchPersistent<false>{}.template run<KAO_TUNE_CFG(S, C, T, U, RL, F)>(h, pa);
             KAO_FOR_TUNE_ALL(KAO_RUN_TUNE)
 #undef KAO_RUN_TUNE
         }
@@ -377,10 +377,11 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     // its five transposed planes (5 * W words per partition) take the place of the objective table
     h->plan_t = make_plan(W, Ppad, h->threads / 32, kTPlanes * W, m.P, m.RF, false);
     h->trans_ok = W <= 2 && m.hi1 && m.log2S == 3 && h->hm.nplanes == 3 && h->plan_t.total <= 227u * 1024u;
-    if (const char *env = std::getenv("KAO_SCHEDULE")) {      // "sync,compress,threads,unroll,roll": tuning only, ignored if not built
-        int a = 0, b = 1, c = KAO_THREADS, u = 1, rl = 0;
-        if (std::sscanf(env, "%d,%d,%d,%d,%d", &a, &b, &c, &u, &rl) == 5 && schedule_exists(a, b, c, u, rl) && h->trans_ok && W == 2 && Ppad == 1024) {
-            h->sch_sync = a; h->sch_compress = b; h->sch_threads = c; h->sch_unroll = u; h->sch_roll = rl;
+    if (const char *env = std::getenv("KAO_SCHEDULE")) {      // "sync,compress,threads,unroll,roll,fuse": tuning only, ignored if not built
+        int a = 0, b = 1, c = KAO_THREADS, u = 1, rl = 0, fu = 0;
+        if (std::sscanf(env, "%d,%d,%d,%d,%d,%d", &a, &b, &c, &u, &rl, &fu) == 6 && schedule_exists(a, b, c, u, rl, fu) && h->trans_ok &&
+            W == 2 && Ppad == 1024) {
+            h->sch_sync = a; h->sch_compress = b; h->sch_threads = c; h->sch_unroll = u; h->sch_roll = rl; h->sch_fuse = fu;
         }
     }
     h->grid = h->sms;
@@ -583,24 +584,26 @@ extern "C" int kao_set_evaluator(kao_handle *h, int32_t evaluator)
     return KAO_OK;
 }
 
-static bool schedule_exists(int sync, int compress, int threads, int unroll, int roll)
+static bool schedule_exists(int sync, int compress, int threads, int unroll, int roll, int fuse)
 {
-#define KAO_HAS_TUNE(S, C, T, U, RL) if (sync == S && compress == C && threads == T && unroll == U && roll == RL) return true;
+#define KAO_HAS_TUNE(S, C, T, U, RL, F) if (sync == S && compress == C && threads == T && unroll == U && roll == RL && fuse == F) return true;
     KAO_FOR_TUNE_ALL(KAO_HAS_TUNE)
 #undef KAO_HAS_TUNE
     return false;
 }
 
-extern "C" int kao_set_schedule(kao_handle *h, int32_t sync, int32_t compress, int32_t threads, int32_t unroll, int32_t roll)
+extern "C" int kao_set_schedule(kao_handle *h, int32_t sync, int32_t compress, int32_t threads, int32_t unroll, int32_t roll,
+                                int32_t fuse)
 {
     if (!h) return fail(KAO_E_ARG, "null handle");
-    if (!schedule_exists(sync, compress, threads, unroll, roll))
-        return fail(KAO_E_ARG, "no such schedule: sync 0..3, compress 0..2, (threads, unroll) one of (768,1) (512,1) (512,2), "
-                               "roll 0, or 1 with sync 1 / 3 and compress 1 / 2");
+    if (!schedule_exists(sync, compress, threads, unroll, roll, fuse))
+        return fail(KAO_E_ARG, "no such schedule: sync 0..3, compress 0..2, (threads, unroll) one of (768,1) (512,1) (512,2); "
+                               "roll 1 only with sync 1 / 3 and compress 1 / 2; fuse 1 only with compress 1 / 2, unroll 1, roll 0");
     if (!(h->trans_ok && h->hm.W == 2 && h->hm.Ppad == 1024) &&
-        !(sync == 0 && compress == 1 && threads == KAO_THREADS && unroll == 1 && roll == 0))
+        !(sync == 0 && compress == 1 && threads == KAO_THREADS && unroll == 1 && roll == 0 && fuse == 0))
         return fail(KAO_E_ARG, "schedules other than the default are built for two-word rows with 769..1024 partitions");
     h->sch_sync = sync; h->sch_compress = compress; h->sch_threads = threads; h->sch_unroll = unroll; h->sch_roll = roll;
+    h->sch_fuse = fuse;
     return KAO_OK;
 }
 

@@ -15,7 +15,7 @@
 
 #if defined(KAO_INST_TUNE) && KAO_INST_TUNE >= 0
 // schedules of the column-major evaluator (kao_set_schedule), one object per barrier form
-#define KAO_INST_TUNE_K(S, C, T, U, RL) template __global__ void KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U, RL);
+#define KAO_INST_TUNE_K(S, C, T, U, RL, F) template __global__ void KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U, RL, F);
 #if KAO_INST_TUNE == 0
 KAO_FOR_TUNE_SYNC_0(KAO_INST_TUNE_K)
 #elif KAO_INST_TUNE == 1

@@ -573,20 +573,23 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                                                                   uint32_t, unsigned long long *, unsigned int *, P2P, \
                                                                   unsigned long long *)
 // schedules of the column-major evaluator for the headline layout (two-word rows, 32 partition words):
-// X(sync, compress, threads, unroll, roll); (0, 1, 768, 1, 0) is the default above
-#define KAO_TUNE_CFG(S, C, T, U, RL) EvalCfgT<2, 32, S, C, T, U, RL>
-#define KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U, RL)                                                          \
-    search_persistent_kernel<KAO_TUNE_CFG(S, C, T, U, RL), T, false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
-                                                                     uint32_t, unsigned long long *, unsigned int *, P2P, \
-                                                                     unsigned long long *)
-#define KAO_FOR_TUNE_TU(X, S, T, U) X(S, 1, T, U, 0) X(S, 0, T, U, 0) X(S, 2, T, U, 0)
-#define KAO_FOR_TUNE_TU_ROLLED(X, S, T, U) X(S, 1, T, U, 1) X(S, 2, T, U, 1)
-#define KAO_FOR_TUNE_SYNC_0(X) KAO_FOR_TUNE_TU(X, 0, 768, 1) KAO_FOR_TUNE_TU(X, 0, 512, 1) KAO_FOR_TUNE_TU(X, 0, 512, 2)
-#define KAO_FOR_TUNE_SYNC_2(X) KAO_FOR_TUNE_TU(X, 2, 768, 1) KAO_FOR_TUNE_TU(X, 2, 512, 1) KAO_FOR_TUNE_TU(X, 2, 512, 2)
+// X(sync, compress, threads, unroll, roll, fuse); (0, 1, 768, 1, 0, 0) is the default above
+#define KAO_TUNE_CFG(S, C, T, U, RL, F) EvalCfgT<2, 32, S, C, T, U, RL, F>
+#define KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U, RL, F)                                                       \
+    search_persistent_kernel<KAO_TUNE_CFG(S, C, T, U, RL, F), T, false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
+                                                                        uint32_t, unsigned long long *, unsigned int *, P2P, \
+                                                                        unsigned long long *)
+#define KAO_FOR_TUNE_TU(X, S, T, U) X(S, 1, T, U, 0, 0) X(S, 0, T, U, 0, 0) X(S, 2, T, U, 0, 0)
+#define KAO_FOR_TUNE_TU_ROLLED(X, S, T, U) X(S, 1, T, U, 1, 0) X(S, 2, T, U, 1, 0)
+// row network fused into the column loop (needs the registers of 512 threads per CTA; 768 is built too)
+#define KAO_FOR_TUNE_FUSED(X, S) X(S, 1, 512, 1, 0, 1) X(S, 2, 512, 1, 0, 1) X(S, 1, 768, 1, 0, 1) X(S, 2, 768, 1, 0, 1)
+#define KAO_FOR_TUNE_PLAIN(X, S) KAO_FOR_TUNE_TU(X, S, 768, 1) KAO_FOR_TUNE_TU(X, S, 512, 1) KAO_FOR_TUNE_TU(X, S, 512, 2) KAO_FOR_TUNE_FUSED(X, S)
 // warps not in step (warp-only sync, half-CTA groups): also with the rolled row pass
-#define KAO_FOR_TUNE_LOOSE(X, S) KAO_FOR_TUNE_TU(X, S, 768, 1) KAO_FOR_TUNE_TU(X, S, 512, 1) KAO_FOR_TUNE_TU(X, S, 512, 2) \
+#define KAO_FOR_TUNE_LOOSE(X, S) KAO_FOR_TUNE_PLAIN(X, S) \
     KAO_FOR_TUNE_TU_ROLLED(X, S, 768, 1) KAO_FOR_TUNE_TU_ROLLED(X, S, 512, 1) KAO_FOR_TUNE_TU_ROLLED(X, S, 512, 2)
+#define KAO_FOR_TUNE_SYNC_0(X) KAO_FOR_TUNE_PLAIN(X, 0)
 #define KAO_FOR_TUNE_SYNC_1(X) KAO_FOR_TUNE_LOOSE(X, 1)
+#define KAO_FOR_TUNE_SYNC_2(X) KAO_FOR_TUNE_PLAIN(X, 2)
 #define KAO_FOR_TUNE_SYNC_3(X) KAO_FOR_TUNE_LOOSE(X, 3)
 #define KAO_FOR_TUNE_ALL(X) KAO_FOR_TUNE_SYNC_0(X) KAO_FOR_TUNE_SYNC_1(X) KAO_FOR_TUNE_SYNC_2(X) KAO_FOR_TUNE_SYNC_3(X)
 #define KAO_PERSISTENT_KERNEL(W, NPH, R, O, T, DELTA)                                                       \

@@ -144,11 +144,11 @@ class Session:
         _check(rc)
         return False
 
-    def set_schedule(self, sync: int, compress: int, threads: int, unroll: int, roll: int = 0) -> bool:
+    def set_schedule(self, sync: int, compress: int, threads: int, unroll: int, roll: int = 0, fuse: int = 0) -> bool:
         """Schedule of the column-major evaluator (kao_set_schedule): results never depend on it.
         False when that variant is not built for this layout."""
         rc = self._lib.kao_set_schedule(self._h, C.c_int32(sync), C.c_int32(compress), C.c_int32(threads), C.c_int32(unroll),
-                                        C.c_int32(roll))
+                                        C.c_int32(roll), C.c_int32(fuse))
         if rc == -1:
             return False
         _check(rc)

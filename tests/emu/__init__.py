@@ -48,7 +48,8 @@ class EmuSession:
     def set_evaluator(self, mode):
         """0: row-major evaluator; 1: column-major evaluator (csrc/kao_device_t.cuh) as the engine picks it;
         2: its run-time-sized form even where the 32-word specialisation applies; 3: plain popcounts
-        (kCompress = 0); 4: unrolled column loop; 5: five compressed popcount streams (kCompress = 2); 6: row pass as a loop (kRoll = 1).  False is returned for unsupported layouts."""
+        (kCompress = 0); 4: unrolled column loop; 5: five compressed popcount streams (kCompress = 2); 6: row pass as a loop (kRoll = 1); 7: row network fused into the column loop (kFuse = 1; two-word
+        rows with 32 partition words only).  False is returned for unsupported layouts."""
         return lib().kao_emu_set_evaluator(self._h, C.c_int32(mode)) == 0
 
     def set_base(self, replicas):

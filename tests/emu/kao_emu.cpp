@@ -114,7 +114,7 @@ template <class Cfg> struct Run {
             int viol, obj;
             if constexpr (W <= 2) {
                 // forms of the column-major evaluator: 1 as the engine picks it (32-word specialisation where it
-                // applies, compressed popcounts), 2 run-time word count, 3 plain popcounts, 4 unrolled column loop, 5 five compressed streams, 6 rolled row pass
+                // applies, compressed popcounts), 2 run-time word count, 3 plain popcounts, 4 unrolled column loop, 5 five compressed streams, 6 rolled row pass, 7 fused passes
                 const bool fixed = e.nW == 32;
                 if (e.trans == 1 && fixed) eval_candidate_t<EvalCfgT<W, 32>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
                 else if (e.trans == 1 || e.trans == 2) eval_candidate_t<EvalCfgT<W, 0>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
@@ -124,6 +124,9 @@ template <class Cfg> struct Run {
                 else if (e.trans == 5 && fixed) eval_candidate_t<EvalCfgT<W, 32, 0, 2>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
                 else if (e.trans == 5) eval_candidate_t<EvalCfgT<W, 0, 0, 2>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
                 else if (e.trans == 6) eval_candidate_t<EvalCfgT<W, 0, 1, 1, 0, 1, 1>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
+                else if (e.trans == 7) {
+                    if constexpr (W == 2) eval_candidate_t<EvalCfgT<2, 32, 0, 2, 512, 1, 0, 1>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
+                }
                 else eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
             } else {
                 eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
@@ -269,7 +272,8 @@ int kao_emu_set_evaluator(void *h, int32_t mode)
 {
     Emu &e = *static_cast<Emu *>(h);
     if (mode != 0 && !e.trans_ok) { g_err = "column-major evaluator: unsupported layout"; return -1; }
-    if (mode < 0 || mode > 6) { g_err = "unknown evaluator form"; return -1; }
+    if (mode < 0 || mode > 7) { g_err = "unknown evaluator form"; return -1; }
+    if (mode == 7 && !(e.hm.W == 2 && e.nW == 32)) { g_err = "fused passes: two-word rows, 32 partition words"; return -1; }
     e.trans = mode;
     return 0;
 }

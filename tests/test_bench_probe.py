@@ -15,16 +15,16 @@ def _fake(lines, rc=0, stderr=""):
 
 ROW = {"name": "row_major", "column_major": False, "schedule": None, "ms_per_launch": 31.8, "identical_to_row_major": True}
 COL = {"name": "column_major", "column_major": True, "schedule": None, "ms_per_launch": 29.5, "identical_to_row_major": True}
-FAST = {"name": "column_major sync=1 compress=0 threads=512 unroll=2 roll=0", "column_major": True, "schedule": [1, 0, 512, 2, 0],
+FAST = {"name": "column_major sync=1 compress=0 threads=512 unroll=2 roll=0 fuse=0", "column_major": True, "schedule": [1, 0, 512, 2, 0, 0],
         "ms_per_launch": 25.0, "identical_to_row_major": True}
-WRONG = {"name": "column_major sync=2 compress=1 threads=768 unroll=1 roll=0", "column_major": True, "schedule": [2, 1, 768, 1, 0],
+WRONG = {"name": "column_major sync=2 compress=1 threads=768 unroll=1 roll=0 fuse=0", "column_major": True, "schedule": [2, 1, 768, 1, 0, 0],
          "ms_per_launch": 10.0, "identical_to_row_major": False}
 
 
 def test_fastest_identical_variant_wins(monkeypatch):
     monkeypatch.setattr(subprocess, "run", _fake([ROW, COL, FAST, WRONG]))
     use_col, sched, rep = bench.choose_evaluator(0)
-    assert use_col and sched == (1, 0, 512, 2, 0) and rep["selected"] == FAST["name"] and len(rep["variants"]) == 4
+    assert use_col and sched == (1, 0, 512, 2, 0, 0) and rep["selected"] == FAST["name"] and len(rep["variants"]) == 4
 
 
 def test_default_column_major_has_no_schedule(monkeypatch):
@@ -47,7 +47,7 @@ def test_partial_output_of_a_crashed_or_hung_child_counts(monkeypatch):
     def hang(*a, **k):
         raise subprocess.TimeoutExpired(cmd="probe", timeout=1, output=("PROBE " + json.dumps(ROW) + "\nPROBE " + json.dumps(FAST) + "\n").encode())
     monkeypatch.setattr(subprocess, "run", hang)
-    assert bench.choose_evaluator(0)[:2] == (True, (1, 0, 512, 2, 0))
+    assert bench.choose_evaluator(0)[:2] == (True, (1, 0, 512, 2, 0, 0))
 
     def boom(*a, **k):
         raise OSError("no python")
@@ -58,11 +58,12 @@ def test_partial_output_of_a_crashed_or_hung_child_counts(monkeypatch):
 
 
 def test_schedule_list_matches_the_engine():
-    assert len(bench.SCHEDULES) == 48 and len(set(bench.SCHEDULES)) == 48 and bench.DEFAULT_SCHEDULE in bench.SCHEDULES
-    assert {(t, u) for _, _, t, u, _ in bench.SCHEDULES} == {(768, 1), (512, 1), (512, 2)}
+    assert len(bench.SCHEDULES) == 64 and len(set(bench.SCHEDULES)) == 64 and bench.DEFAULT_SCHEDULE in bench.SCHEDULES
+    assert {(t, u) for _, _, t, u, _, _ in bench.SCHEDULES} == {(768, 1), (512, 1), (512, 2)}
     # the list must be the one the engine builds (KAO_FOR_TUNE_ALL in csrc/kao_kernels.cuh)
     import os
     import re
     src = open(os.path.join(os.path.dirname(os.path.abspath(bench.__file__)), "kafka_assignment_optimizer_b200", "csrc", "kao_kernels.cuh")).read()
-    assert "X(S, 1, T, U, 0) X(S, 0, T, U, 0) X(S, 2, T, U, 0)" in src and "X(S, 1, T, U, 1) X(S, 2, T, U, 1)" in src
+    assert "X(S, 1, T, U, 0, 0) X(S, 0, T, U, 0, 0) X(S, 2, T, U, 0, 0)" in src and "X(S, 1, T, U, 1, 0) X(S, 2, T, U, 1, 0)" in src
+    assert "X(S, 1, 512, 1, 0, 1) X(S, 2, 512, 1, 0, 1) X(S, 1, 768, 1, 0, 1) X(S, 2, 768, 1, 0, 1)" in src
     assert re.search(r"KAO_FOR_TUNE_SYNC_1\(X\) KAO_FOR_TUNE_LOOSE\(X, 1\)", src) and re.search(r"KAO_FOR_TUNE_SYNC_3\(X\) KAO_FOR_TUNE_LOOSE\(X, 3\)", src)

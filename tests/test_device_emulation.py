@@ -177,7 +177,7 @@ def test_column_major_forms_agree(emu):
     sess = emu.EmuSession(product(pb))
     assert sess.set_evaluator(1)
     fixed = sess.candidate_keys(0x5EED, 3, 4096, 100, 96)
-    for form in (2, 3, 4, 5, 6):         # run-time word count, plain popcounts, unrolled column loop, five compressed streams, rolled row pass
+    for form in (2, 3, 4, 5, 6, 7):      # run-time word count, plain popcounts, unrolled column loop, five compressed streams, rolled row pass, fused passes
         assert sess.set_evaluator(form)
         assert (fixed == sess.candidate_keys(0x5EED, 3, 4096, 100, 96)).all()
     assert sess.set_evaluator(0)
@@ -211,7 +211,7 @@ def test_column_major_evaluator_refuses_other_layouts(emu):
         sess.close()
 
 
-@pytest.mark.parametrize("form", [1, 2, 5])
+@pytest.mark.parametrize("form", [1, 2, 5, 7])
 def test_column_major_long_stream_on_the_headline_shape(emu, ref_lib, form):
     """Config 3 (1000 x 64 x 8, RF 3): 12,000 candidates of four rounds against the restatement, with
     the base moved by winners in between (1-, 2- and 3-row patches in every chunk of the column walk)."""

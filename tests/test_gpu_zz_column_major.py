@@ -137,7 +137,7 @@ def test_every_schedule_gives_the_same_keys():
     base.close()
     import bench
 
-    for sched in bench.SCHEDULES:                       # (sync, compress, threads, unroll, roll)
+    for sched in bench.SCHEDULES:                       # (sync, compress, threads, unroll, roll, fuse)
         sess = kao.Session(product(pb))
         assert sess.set_evaluator(True) and sess.set_schedule(*sched), sched
         assert (want_keys == sess.candidate_keys(0x5EED, 1, 8192, 0, 8192)).all(), sched
@@ -145,6 +145,6 @@ def test_every_schedule_gives_the_same_keys():
         assert (want_traj == got).all() and (want_base == sess.get_base()[0]).all(), sched
         sess.close()
     small = kao.Session(product(SHAPES["cfg2"]()))
-    assert small.set_evaluator(True) and not small.set_schedule(1, 1, 512, 2, 0)   # built for the headline layout only
-    assert small.set_schedule(0, 1, 768, 1, 0) and not small.set_schedule(0, 1, 768, 1, 1)
+    assert small.set_evaluator(True) and not small.set_schedule(1, 1, 512, 2, 0, 0)   # built for the headline layout only
+    assert small.set_schedule(0, 1, 768, 1, 0, 0) and not small.set_schedule(0, 1, 768, 1, 1, 0)
     small.close()
