@@ -83,93 +83,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# (sync, compress, threads, unroll, roll, fuse) — the variants csrc/kao_kernels.cuh builds (KAO_FOR_TUNE_ALL)
-SCHEDULES = ([(sy, c, t, u, 0, 0) for sy in (0, 1, 2, 3) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 0, 2)] +
-             [(sy, c, t, u, 1, 0) for sy in (1, 3) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 2)] +
-             [(sy, c, t, 1, 0, 1) for sy in (0, 1, 2, 3) for t in (512, 768) for c in (1, 2)])
-DEFAULT_SCHEDULE = (0, 1, 768, 1, 0, 0)
-
-
 def probe_evaluators(device):
-    """Untimed probe, run in a CHILD process (a faulting kernel must not poison the bench's CUDA
-    context): one warm, one recorded and two timed launches of the step with each full evaluator of
-    the engine — row-major, column-major, and the schedules of the column-major one — on the same
-    stream of candidates; the round keys and the final assignment must be identical to the row-major
-    evaluator's.  One line per variant, flushed as it completes."""
+    """`bench.py --probe-evaluators`: the engine's tuning probe (kafka_assignment_optimizer_b200/tuning.py)
+    on the bench workload, in this process — one PROBE line per full-evaluation variant."""
     import kafka_assignment_optimizer_b200 as kao
+    from kafka_assignment_optimizer_b200 import tuning
 
-    pb = kao.synthetic_problem(P, B, R, RF)
-    ref = {}
-    progress = [time.monotonic()]
-
-    def watchdog():                                          # a variant that hangs ends the probe, not the bench
-        while True:
-            time.sleep(1.0)
-            if time.monotonic() - progress[0] > 25.0:
-                os._exit(3)
-
-    threading.Thread(target=watchdog, daemon=True).start()
-
-    def run(name, col, sched):
-        progress[0] = time.monotonic()
-        sess = kao.Session(pb, device=device)
-        try:
-            if col and not sess.set_evaluator(True):
-                return {"name": name, "error": "layout not covered"}
-            if sched is not None and not sess.set_schedule(*sched):
-                return {"name": name, "error": "schedule not built"}
-            sess.search(SEED, 50_000, 2, ROUND_SIZE)
-            sess.reset()
-            keys, _ = sess.search(SEED, 60_000, ROUNDS, ROUND_SIZE)
-            base = sess.get_base()[0]
-            ms = min(sess.search(SEED, 70_000 + i * ROUNDS, ROUNDS, ROUND_SIZE)[1] for i in range(2))
-            if not ref:
-                ref["keys"], ref["base"] = keys.copy(), base.copy()
-            same = bool((keys == ref["keys"]).all() and (base == ref["base"]).all())
-            return {"name": name, "column_major": col, "schedule": sched, "ms_per_launch": ms, "identical_to_row_major": same}
-        finally:
-            sess.close()
-
-    print("PROBE " + json.dumps(run("row_major", False, None)), flush=True)
-    print("PROBE " + json.dumps(run("column_major", True, None)), flush=True)
-    for sched in SCHEDULES:
-        if sched != DEFAULT_SCHEDULE:
-            print("PROBE " + json.dumps(run("column_major sync=%d compress=%d threads=%d unroll=%d roll=%d fuse=%d" % sched, True, sched)), flush=True)
-    return 0
-
-
-def choose_evaluator(device):
-    """-> (use_column_major, schedule or None, report).  The fastest variant whose results are
-    identical to the row-major evaluator's wins; whatever the child managed to report before a failure counts."""
-    rows, err = [], None
-    try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-evaluators", "--device", str(device)],
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
-        rows = [json.loads(l[6:]) for l in r.stdout.splitlines() if l.startswith("PROBE ")]
-        if r.returncode != 0:
-            err = (r.stderr or r.stdout)[-300:]
-    except Exception as e:                                   # noqa: BLE001 — any probe failure keeps what is known to work
-        err = repr(e)[:300]
-        out = getattr(e, "stdout", None) or ""               # TimeoutExpired carries what the child printed so far
-        if isinstance(out, bytes):
-            out = out.decode(errors="replace")
-        try:
-            rows = [json.loads(l[6:]) for l in out.splitlines() if l.startswith("PROBE ")]
-        except ValueError:
-            rows = []
-    ok = [x for x in rows if x.get("identical_to_row_major") and "ms_per_launch" in x]
-    report = {"how": "untimed probe in a child process before the warm-up: the same candidates through every "
-                     "full-evaluation variant; identical round keys and final assignment required",
-              "variants": [{k: v for k, v in x.items() if k != "column_major"} for x in rows]}
-    if err:
-        report["probe_error"] = err
-    if not ok or not any(x["name"] == "row_major" for x in ok):
-        report["selected"] = "row_major"
-        return False, None, report
-    best = min(ok, key=lambda x: x["ms_per_launch"])
-    report["selected"] = best["name"]
-    sched = tuple(best["schedule"]) if best.get("schedule") else None
-    return bool(best["column_major"]), sched, report
+    return tuning.probe(kao.synthetic_problem(P, B, R, RF), device, ROUNDS, ROUND_SIZE, SEED)
 
 
 def host_threads():
@@ -275,22 +195,21 @@ def main():
     dev = torch.device("cuda", local)
 
     pb = kao.synthetic_problem(P, B, R, RF)
-    # both full evaluators give bit-identical keys, so every rank may choose for its own GPU
+    # Both full evaluators (and the schedules of the column-major one) give bit-identical keys, so every
+    # rank may choose for its own GPU: the engine's tuning probe runs the bench workload through every
+    # variant in a child process, untimed, before the warm-up (kafka_assignment_optimizer_b200/tuning.py).
+    from kafka_assignment_optimizer_b200 import tuning
+
     sched = None
     if args.evaluator == "auto":
-        use_col, sched, eval_report = choose_evaluator(local)
+        use_col, sched, eval_report = tuning.tune(pb, device=local, rounds=ROUNDS, round_size=ROUND_SIZE, seed=SEED)
     else:
         use_col, eval_report = args.evaluator == "column", {"selected": args.evaluator + " (forced)"}
     if world > 1 and args.collective == "nccl":
         use_col, sched, eval_report = False, None, {"selected": "row_major", "note": "the NCCL variant runs the per-round kernels (row-major evaluator)"}
     sess = kao.Session(pb, device=local)
-    if use_col and not sess.set_evaluator(True):
+    if use_col and not tuning.apply(sess, use_col, sched):
         use_col, sched, eval_report = False, None, dict(eval_report, selected="row_major", note="column-major refused by the session")
-    if use_col and sched is not None:
-        if sess.set_schedule(*sched):
-            os.environ["KAO_SCHEDULE"] = "%d,%d,%d,%d,%d,%d" % sched   # kao_solve (the e2e leg) creates its own sessions
-        else:
-            sched = None
     gsize = ROUND_SIZE * world                               # weak scaling: per-GPU work fixed
     key = torch.full((1,), kopt.KEY_NONE, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -364,7 +283,7 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic,
                     "kernel": ("search_persistent_kernel<EvalCfgT<W=2,words=32,sync=%d,compress=%d,threads=%d,unroll=%d,roll=%d,fuse=%d>> (column-major evaluator)"
-                               % (sched or DEFAULT_SCHEDULE) if use_col else
+                               % (sched or tuning.DEFAULT_SCHEDULE) if use_col else
                                "search_persistent_kernel<EvalCfg<W=2,NPH=3,rack=8-slot hi1,planes=3>,768>"),
                     "algorithmic_bytes_per_candidate": ALGO_BYTES, "candidates_per_launch": ROUND_SIZE * ROUNDS,
                     "kernel_ms_per_launch": s_ms,

@@ -135,9 +135,9 @@ def test_every_schedule_gives_the_same_keys():
     want_traj, _ = base.search(0x5EED, 0, 4, 16384)
     want_base = base.get_base()[0]
     base.close()
-    import bench
+    from kafka_assignment_optimizer_b200 import tuning
 
-    for sched in bench.SCHEDULES:                       # (sync, compress, threads, unroll, roll, fuse)
+    for sched in tuning.SCHEDULES:                       # (sync, compress, threads, unroll, roll, fuse)
         sess = kao.Session(product(pb))
         assert sess.set_evaluator(True) and sess.set_schedule(*sched), sched
         assert (want_keys == sess.candidate_keys(0x5EED, 1, 8192, 0, 8192)).all(), sched

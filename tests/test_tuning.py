@@ -1,10 +1,22 @@
-"""bench.py picks the full-evaluation variant to time from an untimed probe run in a child process.
-The selection logic is host code: checked here with canned child output (no GPU)."""
+"""The engine's tuning probe (kafka_assignment_optimizer_b200/tuning.py; bench.py times the variant it
+picks) runs every full-evaluation variant in a child process.  The selection logic is host code:
+checked here with canned child output (no GPU)."""
 import json
 import subprocess
 import types
 
-import bench
+import kafka_assignment_optimizer_b200 as kao
+from kafka_assignment_optimizer_b200 import tuning
+
+PB = kao.synthetic_problem(16, 8, 2, 2)
+
+
+class bench:                                    # the selection used to live in bench.py: same call shape
+    SCHEDULES, DEFAULT_SCHEDULE = tuning.SCHEDULES, tuning.DEFAULT_SCHEDULE
+
+    @staticmethod
+    def choose_evaluator(device):
+        return tuning.tune(PB, device=device, rounds=2, round_size=64)
 
 
 def _fake(lines, rc=0, stderr=""):
@@ -63,7 +75,39 @@ def test_schedule_list_matches_the_engine():
     # the list must be the one the engine builds (KAO_FOR_TUNE_ALL in csrc/kao_kernels.cuh)
     import os
     import re
-    src = open(os.path.join(os.path.dirname(os.path.abspath(bench.__file__)), "kafka_assignment_optimizer_b200", "csrc", "kao_kernels.cuh")).read()
+    src = open(os.path.join(os.path.dirname(os.path.abspath(tuning.__file__)), "csrc", "kao_kernels.cuh")).read()
     assert "X(S, 1, T, U, 0, 0) X(S, 0, T, U, 0, 0) X(S, 2, T, U, 0, 0)" in src and "X(S, 1, T, U, 1, 0) X(S, 2, T, U, 1, 0)" in src
     assert "X(S, 1, 512, 1, 0, 1) X(S, 2, 512, 1, 0, 1) X(S, 1, 768, 1, 0, 1) X(S, 2, 768, 1, 0, 1)" in src
     assert re.search(r"KAO_FOR_TUNE_SYNC_1\(X\) KAO_FOR_TUNE_LOOSE\(X, 1\)", src) and re.search(r"KAO_FOR_TUNE_SYNC_3\(X\) KAO_FOR_TUNE_LOOSE\(X, 3\)", src)
+
+
+def test_probe_child_without_a_gpu_fails_loudly_and_tune_keeps_the_default():
+    """No monkeypatching: the real child process starts, finds no CUDA device, and tune() falls back."""
+    use_col, sched, rep = tuning.tune(PB, device=0, rounds=1, round_size=16, timeout=120)
+    assert (use_col, sched) == (False, None) and rep["selected"] == "row_major"
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:            # noqa: BLE001
+        has_gpu = False
+    if not has_gpu:
+        assert "no CUDA device" in rep.get("probe_error", "")
+
+
+def test_apply_sets_the_environment_for_kao_solve(monkeypatch):
+    calls = []
+
+    class FakeSession:
+        def set_evaluator(self, on):
+            calls.append(("eval", on))
+            return True
+
+        def set_schedule(self, *s):
+            calls.append(("sched", s))
+            return True
+
+    monkeypatch.delenv("KAO_SCHEDULE", raising=False)
+    import os
+    assert tuning.apply(FakeSession(), True, (1, 2, 512, 1, 0, 1)) and os.environ["KAO_SCHEDULE"] == "1,2,512,1,0,1"
+    assert not tuning.apply(FakeSession(), False, None)
+    monkeypatch.delenv("KAO_SCHEDULE", raising=False)
