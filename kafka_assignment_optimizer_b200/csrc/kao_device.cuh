@@ -106,8 +106,11 @@ template <int W> __device__ __forceinline__ int row_count(const uint32_t (&w)[W]
     for (int t = 0; t < W; ++t) n += __popc(w[t]);
     return n;
 }
-// k-th (0-based) set bit in ascending slot order, -1 if fewer
-template <int W> __device__ __forceinline__ int row_kth(const uint32_t (&w)[W], int k)
+// k-th (0-based) set bit in ascending slot order, -1 if fewer.  kSmall: the bit-clearing loop stays a
+// loop.  (Left alone the compiler unrolls it sixteen-fold at every call site: 2,900 of the 8,500
+// instructions of a search kernel for a loop that runs 0..7 times.  The column-major kernels use the
+// small form; the row-major kernels keep the code that was measured.)
+template <int W, bool kSmall = false> __device__ __forceinline__ int row_kth(const uint32_t (&w)[W], int k)
 {
     int res = -1;
 #pragma unroll
@@ -115,7 +118,12 @@ template <int W> __device__ __forceinline__ int row_kth(const uint32_t (&w)[W], 
         const int c = __popc(w[t]);
         if (res < 0 && k < c) {
             uint32_t m = w[t];
-            for (int i = 0; i < k; ++i) m &= m - 1;
+            if constexpr (kSmall) {
+#pragma unroll 1
+                for (int i = 0; i < k; ++i) m &= m - 1;
+            } else {
+                for (int i = 0; i < k; ++i) m &= m - 1;
+            }
             res = t * 32 + __ffs(m) - 1;
         }
         k -= c;
@@ -135,7 +143,8 @@ struct PatchSet {
 
 // kThread = false: one warp generates one candidate cooperatively (patched rows go to `prow`);
 // kThread = true : every thread generates its own candidate (patched rows go to the caller's registers).
-template <int W, bool kThread = false> struct Gen {
+// kSmall: compact code (row_kth), same candidates.
+template <int W, bool kThread = false, bool kSmall = false> struct Gen {
     const uint32_t *bitsT;   // base (shared or global)
     const uint8_t *leader;
     const Consts *cs;
@@ -204,7 +213,7 @@ template <int W, bool kThread = false> struct Gen {
         const int cnt = row_count<W>(m);
         if (cnt < 1) return -1;
         if (want >= 0 && want < W * 32 && want != (int)ld && row_has<W>(row, want)) { ld = (uint32_t)want; return want; }
-        ld = (uint32_t)row_kth<W>(m, (int)mulhi32(rnd, (uint32_t)cnt));
+        ld = (uint32_t)row_kth<W, kSmall>(m, (int)mulhi32(rnd, (uint32_t)cnt));
         return (int)ld;
     }
     // first partition q >= p0 (cyclic), not yet patched, for which pred(q) holds; kind 0: holds a
@@ -308,7 +317,7 @@ template <int W, bool kThread = false> struct Gen {
             read_row(p, row, ld);
             const int n = row_count<W>(row);
             if (n == 0) return;
-            int a = row_kth<W>(row, (int)mulhi32(r[2], (uint32_t)n));
+            int a = row_kth<W, kSmall>(row, (int)mulhi32(r[2], (uint32_t)n));
             int o = (int)mulhi32(r[3], (uint32_t)B);
             if (guided) {
                 const uint32_t h4 = d->homeT[p];
@@ -324,8 +333,8 @@ template <int W, bool kThread = false> struct Gen {
                 for (int t = 0; t < W; ++t) { miss[t] = home[t] & ~row[t]; nonhome[t] = row[t] & ~home[t]; }
                 const int nm = row_count<W>(miss), nn = row_count<W>(nonhome);
                 if (nm > 0) {
-                    o = cs->order_of_slot[row_kth<W>(miss, (int)mulhi32(r[3], (uint32_t)nm))];
-                    if (nn > 0) a = row_kth<W>(nonhome, (int)mulhi32(r[2], (uint32_t)nn));
+                    o = cs->order_of_slot[row_kth<W, kSmall>(miss, (int)mulhi32(r[3], (uint32_t)nm))];
+                    if (nn > 0) a = row_kth<W, kSmall>(nonhome, (int)mulhi32(r[2], (uint32_t)nn));
                 }
             }
             hi = replace(row, ld, a, o);
@@ -357,7 +366,7 @@ template <int W, bool kThread = false> struct Gen {
                 read_row(q, rq, lq);
                 const int nq = row_count<W>(rq);
                 if (nq == 0) return;
-                int src = row_kth<W>(rq, (int)mulhi32(rb, (uint32_t)nq));
+                int src = row_kth<W, kSmall>(rq, (int)mulhi32(rb, (uint32_t)nq));
                 if (close && (int)lq < W * 32 && row_has<W>(rq, (int)lq)) src = (int)lq;
                 replace(rq, lq, src, olo);
                 lo = src;

@@ -305,7 +305,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     if constexpr (Cfg::kTrans) build_t_planes<W, THREADS>(s_sw, s_bits, s_leader, d.planesT, d.Ppad);
     rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
 
-    Gen<W> gen;
+    Gen<W, false, Cfg::kTrans> gen;        // column-major kernels: compact generator code (same candidates)
     uint32_t no_rows[kMaxOps][W];          // warp mode keeps patched rows in shared memory instead
     gen.bitsT = s_bits; gen.leader = s_leader; gen.cs = s_cs; gen.d = &d;
     gen.prow = s_prow + warp * kMaxOps * W; gen.lane = lane;

@@ -92,9 +92,9 @@ void set_base(Emu &e, const std::vector<uint32_t> &bitsT, const std::vector<uint
 
 template <class Cfg> struct Run {
     static constexpr int W = Cfg::W;
-    static Gen<W> make_gen(Emu &e, int lane)
+    template <bool kSmall> static Gen<W, false, kSmall> make_gen(Emu &e, int lane)
     {
-        Gen<W> g;
+        Gen<W, false, kSmall> g;
         g.bitsT = e.bits.data(); g.leader = e.leader.data(); g.cs = &e.cs; g.d = &e.prm;
         g.prow = e.prow.data(); g.lane = lane;
         g.D = e.D.data(); g.DL = e.DL.data(); g.nD = e.nD; g.nL = e.nL;
@@ -106,10 +106,10 @@ template <class Cfg> struct Run {
         unsigned long long out = 0;
         const uint32_t *objT = Cfg::kObj > 0 ? e.prm.planesT : e.prm.swT;
         emu::run_warp([&](int lane) {
-            Gen<W> g = make_gen(e, lane);
             uint32_t no_rows[kMaxOps][W];
             PatchSet ps;
-            g.run(seed, round, idx, round_size, ps, no_rows);
+            if (e.trans) make_gen<true>(e, lane).run(seed, round, idx, round_size, ps, no_rows);   // as the column-major kernels
+            else make_gen<false>(e, lane).run(seed, round, idx, round_size, ps, no_rows);
             __syncwarp();                                     // __syncthreads() of the kernels
             int viol, obj;
             if constexpr (W <= 2) {
@@ -140,10 +140,10 @@ template <class Cfg> struct Run {
     {
         PatchSet win;
         emu::run_warp([&](int lane) {
-            Gen<W> g = make_gen(e, lane);
             uint32_t no_rows[kMaxOps][W];
             PatchSet ps;
-            g.run(seed, round, idx, round_size, ps, no_rows);
+            if (e.trans) make_gen<true>(e, lane).run(seed, round, idx, round_size, ps, no_rows);
+            else make_gen<false>(e, lane).run(seed, round, idx, round_size, ps, no_rows);
             if (lane == 0) win = ps;
         });
         const int Ppad = e.hm.Ppad;
