@@ -154,7 +154,7 @@ int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
 int kao_set_evaluator(kao_handle *h, int32_t evaluator);
 /* Schedule of the column-major evaluator: the same arithmetic, laid out differently in time.  sync: how
  * the warps of a CTA meet before an evaluation (0 block barrier, 1 warp only, 2 one barrier per warp
- * scheduler, 3 two half-CTA groups); compress: carry-save compression of popcount streams (0 none, 1
+ * scheduler, 3 two half-CTA groups, 4 the same groups started in anti-phase); compress: carry-save compression of popcount streams (0 none, 1
  * three streams, 2 five);
  * (threads per CTA, unroll of the column loop): (768,1), (512,1) or (512,2); roll: 1 = the row pass as
  * a loop instead of unrolled (built for sync 1 / 3 with compress 1 / 2); fuse: 1 = the row network is

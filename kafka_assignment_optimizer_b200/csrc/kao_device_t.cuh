@@ -29,7 +29,7 @@ namespace kao {
 //   kSync      how the warps of a CTA meet before an evaluation: 0 block barrier (all warps walk the
 //              evaluator together: instruction cache), 1 warp only, 2 one named barrier per scheduler,
 //              3 two groups that each hold half of every scheduler's warps (one group can generate
-//              while the other evaluates)
+//              while the other evaluates), 4 the same two groups started in anti-phase
 //   kCompress  carry-save compression of popcount streams: 0 none, 1 column / leader / bonus totals,
 //              2 also the two objective streams (pooled over the lane's slots)
 //   kThreads   threads per CTA (0 = threads_for<W>()); fewer threads = more registers per thread

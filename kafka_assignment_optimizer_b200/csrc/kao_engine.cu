@@ -597,7 +597,7 @@ extern "C" int kao_set_schedule(kao_handle *h, int32_t sync, int32_t compress, i
 {
     if (!h) return fail(KAO_E_ARG, "null handle");
     if (!schedule_exists(sync, compress, threads, unroll, roll, fuse))
-        return fail(KAO_E_ARG, "no such schedule: sync 0..3, compress 0..2, (threads, unroll) one of (768,1) (512,1) (512,2); "
+        return fail(KAO_E_ARG, "no such schedule: sync 0..4, compress 0..2, (threads, unroll) one of (768,1) (512,1) (512,2); "
                                "roll 1 only with sync 1 / 3 and compress 1 / 2; fuse 1 only with compress 1 / 2, unroll 1, roll 0");
     if (!(h->trans_ok && h->hm.W == 2 && h->hm.Ppad == 1024) &&
         !(sync == 0 && compress == 1 && threads == KAO_THREADS && unroll == 1 && roll == 0 && fuse == 0))

@@ -22,8 +22,10 @@ KAO_FOR_TUNE_SYNC_0(KAO_INST_TUNE_K)
 KAO_FOR_TUNE_SYNC_1(KAO_INST_TUNE_K)
 #elif KAO_INST_TUNE == 2
 KAO_FOR_TUNE_SYNC_2(KAO_INST_TUNE_K)
-#else
+#elif KAO_INST_TUNE == 3
 KAO_FOR_TUNE_SYNC_3(KAO_INST_TUNE_K)
+#else
+KAO_FOR_TUNE_SYNC_4(KAO_INST_TUNE_K)
 #endif
 #elif defined(KAO_INST_TRANS) && KAO_INST_TRANS
 // column-major evaluator (kao_device_t.cuh): rows of up to 64 slots

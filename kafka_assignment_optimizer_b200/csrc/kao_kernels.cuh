@@ -414,6 +414,17 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             }
             if (all_keys) return;                                   // key dump only: the base stays as it is
         } else {
+        if constexpr (Cfg::kTrans) {
+            if constexpr (Cfg::kSync == 4) {
+                // two half-CTA groups in ANTI-phase: the second group starts each round about half an
+                // interval late, so that on every scheduler three warps generate (latency-bound) while
+                // the other three evaluate (pipe-bound); the groups keep their own barriers after that
+                if ((warp >> 2) & 1) {
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < 6000) {}
+                }
+            }
+        }
         for (uint32_t it = 0; it < iters; ++it) {
             const uint32_t idx = first + warp + it * stride;
             const bool live = idx < pp.idx_hi;
@@ -428,7 +439,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 if constexpr (Cfg::kSync == 0) __syncthreads();
                 else if constexpr (Cfg::kSync == 1) __syncwarp();
                 else if constexpr (Cfg::kSync == 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(THREADS / 4) : "memory");
-                else asm volatile("bar.sync %0, %1;" ::"r"(1 + ((warp >> 2) & 1)), "r"(THREADS / 2) : "memory");
+                else asm volatile("bar.sync %0, %1;" ::"r"(1 + ((warp >> 2) & 1)), "r"(THREADS / 2) : "memory");   // 3, 4
             } else {
                 __syncthreads();
             }
@@ -591,7 +602,8 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 #define KAO_FOR_TUNE_SYNC_1(X) KAO_FOR_TUNE_LOOSE(X, 1)
 #define KAO_FOR_TUNE_SYNC_2(X) KAO_FOR_TUNE_PLAIN(X, 2)
 #define KAO_FOR_TUNE_SYNC_3(X) KAO_FOR_TUNE_LOOSE(X, 3)
-#define KAO_FOR_TUNE_ALL(X) KAO_FOR_TUNE_SYNC_0(X) KAO_FOR_TUNE_SYNC_1(X) KAO_FOR_TUNE_SYNC_2(X) KAO_FOR_TUNE_SYNC_3(X)
+#define KAO_FOR_TUNE_SYNC_4(X) KAO_FOR_TUNE_PLAIN(X, 4)
+#define KAO_FOR_TUNE_ALL(X) KAO_FOR_TUNE_SYNC_0(X) KAO_FOR_TUNE_SYNC_1(X) KAO_FOR_TUNE_SYNC_2(X) KAO_FOR_TUNE_SYNC_3(X) KAO_FOR_TUNE_SYNC_4(X)
 #define KAO_PERSISTENT_KERNEL(W, NPH, R, O, T, DELTA)                                                       \
     search_persistent_kernel<EvalCfg<W, NPH, R, O>, T, DELTA>(Params, SmemPlan, uint64_t, uint32_t, uint32_t,      \
                                                              uint32_t, unsigned long long *, unsigned int *, P2P, \

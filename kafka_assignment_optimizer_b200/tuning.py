@@ -22,9 +22,9 @@ import threading
 import time
 
 # (sync, compress, threads, unroll, roll, fuse) — the variants csrc/kao_kernels.cuh builds (KAO_FOR_TUNE_ALL)
-SCHEDULES = ([(sy, c, t, u, 0, 0) for sy in (0, 1, 2, 3) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 0, 2)] +
+SCHEDULES = ([(sy, c, t, u, 0, 0) for sy in (0, 1, 2, 3, 4) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 0, 2)] +
              [(sy, c, t, u, 1, 0) for sy in (1, 3) for (t, u) in ((768, 1), (512, 1), (512, 2)) for c in (1, 2)] +
-             [(sy, c, t, 1, 0, 1) for sy in (0, 1, 2, 3) for t in (512, 768) for c in (1, 2)])
+             [(sy, c, t, 1, 0, 1) for sy in (0, 1, 2, 3, 4) for t in (512, 768) for c in (1, 2)])
 DEFAULT_SCHEDULE = (0, 1, 768, 1, 0, 0)
 SCHEDULE_FIELDS = ("sync", "compress", "threads", "unroll", "roll", "fuse")
 

@@ -70,7 +70,7 @@ def test_partial_output_of_a_crashed_or_hung_child_counts(monkeypatch):
 
 
 def test_schedule_list_matches_the_engine():
-    assert len(bench.SCHEDULES) == 64 and len(set(bench.SCHEDULES)) == 64 and bench.DEFAULT_SCHEDULE in bench.SCHEDULES
+    assert len(bench.SCHEDULES) == 77 and len(set(bench.SCHEDULES)) == 77 and bench.DEFAULT_SCHEDULE in bench.SCHEDULES
     assert {(t, u) for _, _, t, u, _, _ in bench.SCHEDULES} == {(768, 1), (512, 1), (512, 2)}
     # the list must be the one the engine builds (KAO_FOR_TUNE_ALL in csrc/kao_kernels.cuh)
     import os
@@ -78,6 +78,7 @@ def test_schedule_list_matches_the_engine():
     src = open(os.path.join(os.path.dirname(os.path.abspath(tuning.__file__)), "csrc", "kao_kernels.cuh")).read()
     assert "X(S, 1, T, U, 0, 0) X(S, 0, T, U, 0, 0) X(S, 2, T, U, 0, 0)" in src and "X(S, 1, T, U, 1, 0) X(S, 2, T, U, 1, 0)" in src
     assert "X(S, 1, 512, 1, 0, 1) X(S, 2, 512, 1, 0, 1) X(S, 1, 768, 1, 0, 1) X(S, 2, 768, 1, 0, 1)" in src
+    assert "KAO_FOR_TUNE_SYNC_4(X) KAO_FOR_TUNE_PLAIN(X, 4)" in src and "KAO_FOR_TUNE_SYNC_0(X) KAO_FOR_TUNE_PLAIN(X, 0)" in src
     assert re.search(r"KAO_FOR_TUNE_SYNC_1\(X\) KAO_FOR_TUNE_LOOSE\(X, 1\)", src) and re.search(r"KAO_FOR_TUNE_SYNC_3\(X\) KAO_FOR_TUNE_LOOSE\(X, 3\)", src)
 
 
