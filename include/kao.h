@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KAO_VERSION 0x00010000 /* major.minor.patch = 0.1.0 */
+#define KAO_VERSION 0x00020000 /* major.minor.patch = 0.2.0 (kao_options / kao_result grew, per-problem key layout) */
 
 /* return codes */
 #define KAO_OK 0
@@ -41,6 +41,8 @@ extern "C" {
 #define KAO_MAX_RACKS 32
 #define KAO_MAX_RF 8
 #define KAO_MAX_ROUND_SIZE (1u << 24)
+#define KAO_MAX_ROUNDS (1u << 20)  /* rounds of one search call (one cooperative launch per 8192 when sharded) */
+#define KAO_MAX_GPUS 8
 
 /*
  * The model, README.md:139-185.  x[b,p] / l[b,p] are the reference's binaries t1b{b}p{p} /
@@ -69,19 +71,25 @@ typedef struct kao_problem {
 
 typedef struct kao_options {
     uint64_t seed;            /* Philox key of the candidate stream */
-    uint32_t rounds;          /* search rounds; candidates evaluated = rounds * round_size */
-    uint32_t round_size;      /* candidates per round, 2 .. KAO_MAX_ROUND_SIZE */
-    int32_t device;           /* CUDA device ordinal */
+    uint32_t rounds;          /* search rounds (<= KAO_MAX_ROUNDS); candidates evaluated = rounds * round_size */
+    uint32_t round_size;      /* candidates per round over ALL GPUs of the call, 2 .. KAO_MAX_ROUND_SIZE */
+    int32_t device;           /* CUDA device ordinal (the first one when n_gpus > 1 and device_mask == 0) */
     uint32_t flags;           /* bits 0-7: independent restarts (0 or 1 = one search); the best final
                                  assignment of rounds*round_size candidates each is returned.
                                  KAO_FLAG_DELTA: score candidates by delta evaluation (same keys and
                                  trajectory, several times more candidates per second).
                                  KAO_FLAG_PATIENCE(n): early stop; rounds_run / n_candidates report what ran */
+    int32_t n_gpus;           /* 0 or 1: one GPU.  N (<= KAO_MAX_GPUS): every round's index range is sharded over N
+                                 GPUs of this process (devices device .. device+N-1, or those of device_mask), one
+                                 host thread each; the per-round minimum travels through peer-mapped mailboxes inside
+                                 the kernels (NVLink).  The result does not depend on N: same round_size, same
+                                 trajectory, same assignment. */
+    uint32_t device_mask;     /* != 0: bit i selects CUDA device i; n_gpus must then be 0 or its popcount */
 } kao_options;
 
 #define KAO_FLAG_DELTA 0x100u
-#define KAO_FLAG_COLUMN_MAJOR 0x200u  /* full evaluation by the column-major evaluator where the layout allows it
-                                         (see kao_set_evaluator); same keys, same result, a performance choice */
+#define KAO_FLAG_ROW_MAJOR 0x200u     /* full evaluation by the row-major evaluator even where the (default, faster)
+                                         column-major one applies (see kao_set_evaluator); same keys, same result */
 #define KAO_FLAG_PATIENCE(n) ((uint32_t)(n) << 16)  /* stop a search after n (<= 65535) rounds without a better key */
 
 typedef struct kao_result {
@@ -94,9 +102,17 @@ typedef struct kao_result {
     uint64_t key;             /* packed (violation, cost, index) of the last winning candidate */
     uint64_t n_candidates;    /* candidates generated and fully evaluated */
     uint32_t rounds_run;      /* rounds actually run, summed over restarts */
-    uint32_t reserved;        /* restarts performed */
-    double device_ms;         /* CUDA-event time of the search kernels */
+    uint32_t restarts;        /* restarts performed */
+    double device_ms;         /* CUDA-event time of the search kernels (max over the GPUs) */
     double total_ms;          /* wall time of the call incl. host<->device copies */
+    int64_t objective_bound;  /* an upper bound on the objective of ANY feasible assignment (per partition: the
+                                 best leader + best RF-1 followers, C3..C7 ignored); lp_solve's optimum
+                                 (README.md:135-136) lies between `objective` and this */
+    int32_t optimal;          /* 1: feasible and objective == objective_bound, i.e. PROVEN optimal; 0: not proven
+                                 (the search is a heuristic: it never claims more than the bound shows) */
+    int32_t key_obj_bits;     /* width of the cost field of `key` (KAO_KEY_* macros) */
+    int32_t n_gpus;           /* GPUs that took part */
+    int32_t reserved;
 } kao_result;
 
 int kao_version(void);
@@ -145,26 +161,24 @@ int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
 /* Full-evaluation kernel used by kao_search / kao_search_sharded / kao_candidate_keys of this session.
  * Both evaluate every row and column of every candidate (C1..C7 + objective, README.md:144-185) and
  * return bit-identical keys; they differ in how the base is laid out in shared memory:
- *   KAO_EVAL_ROW_MAJOR     rows of the (partition x broker) bit-plane, column totals by bit-sliced counters (default)
  *   KAO_EVAL_COLUMN_MAJOR  also one bitmap over the partitions per broker slot; needs rows of up to 64
  *                          slots, racks of up to 8 brokers, C7 = at most one replica per rack, three
- *                          objective mask planes; KAO_E_ARG otherwise */
+ *                          objective mask planes, and its planes in shared memory (about P <= 2800);
+ *                          the DEFAULT wherever it applies; KAO_E_ARG when requested elsewhere
+ *   KAO_EVAL_ROW_MAJOR     rows of the (partition x broker) bit-plane, column totals by bit-sliced
+ *                          counters; every layout */
 #define KAO_EVAL_ROW_MAJOR 0
 #define KAO_EVAL_COLUMN_MAJOR 1
 int kao_set_evaluator(kao_handle *h, int32_t evaluator);
 /* Schedule of the column-major evaluator: the same arithmetic, laid out differently in time.  sync: how
- * the warps of a CTA meet before an evaluation (0 block barrier, 1 warp only, 2 one barrier per warp
- * scheduler, 3 two half-CTA groups, 4 the same groups started in anti-phase); compress: carry-save compression of popcount streams (0 none, 1
- * three streams, 2 five);
- * (threads per CTA, unroll of the column loop): (768,1), (512,1) or (512,2); roll: 1 = the row pass as
- * a loop instead of unrolled (built for sync 1 / 3 with compress 1 / 2); fuse: 1 = the row network is
- * folded into the column loop, one rack field per chunk (compress 1 / 2, unroll 1, roll 0).  Default
- * (0, 1, 768, 1, 0, 0).
- * Results never depend on it; bench.py measures the variants on the GPU it runs on and keeps the
- * fastest.  Built for two-word rows with 769..1024 partitions; KAO_E_ARG otherwise.  The environment
- * variable KAO_SCHEDULE="sync,compress,threads,unroll,roll,fuse" sets it for every session (and kao_solve). */
-int kao_set_schedule(kao_handle *h, int32_t sync, int32_t compress, int32_t threads, int32_t unroll, int32_t roll,
-                     int32_t fuse);
+ * the warps of a CTA meet before an evaluation (0 block barrier, 1 warp only); pop: one hex digit per
+ * popcount stream (column totals, leader totals, two follower-weight sums, leader bonus; lowest digit
+ * first): 0 a POPC per word, 1 three per four words, 2 two, 3 one (carry-save adders do the rest);
+ * threads per CTA: 768 or 512.  Only the combinations built into the library are accepted
+ * (KAO_E_ARG otherwise); the default is the fastest one measured on a B200 (profiles/).  Results never
+ * depend on it.  The environment variable KAO_SCHEDULE="sync,pop(hex),threads" sets it for every
+ * session (and kao_solve); KAO_EVALUATOR=row forces the row-major evaluator. */
+int kao_set_schedule(kao_handle *h, int32_t sync, int32_t pop, int32_t threads);
 int kao_last_rounds(kao_handle *h, uint32_t *rounds_run);
 
 /* keys of candidates idx_begin .. idx_begin+count-1 of `round` against the current base (host
@@ -183,9 +197,10 @@ int kao_round_launch(kao_handle *h, uint64_t seed, uint32_t round, uint32_t roun
 int kao_round_apply(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
                     const uint64_t *d_key, void *stream);
 
-/* sharded search with the reduction INSIDE the kernel: every rank owns a mailbox in its HBM that
- * the peers map through CUDA IPC; per round the ranks min-reduce their 8-byte keys into every
- * mailbox with NVLink atomics (no host, no NCCL in the loop).  Setup, once per session:
+/* sharded search with the reduction INSIDE the kernel, one PROCESS per GPU (kao_solve with n_gpus > 1 does
+ * the same inside one process): every rank owns a mailbox in its HBM that the peers map through CUDA IPC;
+ * per round every rank stores its 8-byte key into its slot of every mailbox over NVLink and takes the
+ * minimum of the slots of its own (no host, no NCCL in the loop).  Setup, once per session:
  *   kao_p2p_export   -> 64 opaque bytes; all-gather them across the ranks (any transport);
  *   kao_p2p_connect  <- the world's handles in rank order.
  * kao_search_sharded must then be called by every rank with identical arguments; each evaluates
@@ -207,12 +222,17 @@ int kao_stats(kao_handle *h, uint64_t *kernel_launches, int32_t *words_per_row,
 int kao_profile_rounds(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
                        uint32_t round_size, double *search_ms, double *apply_ms);
 
-/* key layout: violation(15 bits, saturating; bit 63 is always 0 so keys order the same as signed
- * int64) | (0xFFFFFF - objective)(24) | index(24).  KAO_KEY_NONE = "no candidate evaluated". */
+/* key layout, smaller is better: violation | (objmax - objective) | index(24).  The cost field is `ob`
+ * bits wide, ob = bit length of P * RF * (largest weight) = kao_key_obj_bits(problem) (also reported in
+ * kao_result.key_obj_bits), objmax = 2^ob - 1; the violation field takes the remaining 63 - 24 - ob bits
+ * (15..38, at most 31 used) and saturates; bit 63 is always 0, so keys order the same as signed int64.
+ * KAO_KEY_NONE = "no candidate evaluated". */
 #define KAO_KEY_NONE 0x7FFFFFFFFFFFFFFFull
-#define KAO_KEY_VIOLATION(k) ((uint32_t)((k) >> 48))
-#define KAO_KEY_OBJECTIVE(k) (0xFFFFFFu - (uint32_t)(((k) >> 24) & 0xFFFFFFu))
+#define KAO_KEY_VIOLATION(k, ob) ((uint32_t)((k) >> (24 + (ob))))
+#define KAO_KEY_OBJECTIVE(k, ob) (((1u << (ob)) - 1u) - ((uint32_t)((k) >> 24) & ((1u << (ob)) - 1u)))
 #define KAO_KEY_INDEX(k) ((uint32_t)((k) & 0xFFFFFFu))
+/* width of the cost field of this problem's keys; < 0 on a bad problem */
+int kao_key_obj_bits(const kao_problem *pb);
 
 #ifdef __cplusplus
 }

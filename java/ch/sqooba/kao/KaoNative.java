@@ -23,12 +23,16 @@ public final class KaoNative {
      *                (each [R]), ppr_lo, ppr_hi — C3, C4, C6, C7 right-hand sides (README.md:158-180)
      * @param cur     [P*RFcur] current assignment, leader first, -1 = absent (README.md:52-63)
      * @param replicasOut [P*RF] result, leader first (README.md:67-78, :88)
-     * @param statsOut [4] objective, violation, replica moves, candidates evaluated
+     * @param nGpus   1, or N: every round is sharded over N GPUs of this process (device .. device+N-1)
+     * @param flags   kao_options.flags: restarts | KAO_FLAG_DELTA (0x100) | KAO_FLAG_PATIENCE(n) (n << 16)
+     * @param statsOut [8] objective, violation, replica moves, candidates evaluated, objective upper
+     *                bound, proven optimal (0/1), rounds run, GPUs used
      * @return 0 ok, 1 no feasible assignment found; throws KaoException on argument/CUDA errors
      */
     public static native int solve(int P, int B, int R, int RF, int RFcur, byte[] rackOf, short[] wF,
                                    short[] wL, int[] bounds, int[] cur, long seed, int rounds,
-                                   int roundSize, int device, int[] replicasOut, long[] statsOut);
+                                   int roundSize, int device, int nGpus, int flags, int[] replicasOut,
+                                   long[] statsOut);
 
     public static final class KaoException extends RuntimeException {
         public final int code;

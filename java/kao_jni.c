@@ -13,7 +13,7 @@ JNIEXPORT jint JNICALL Java_ch_sqooba_kao_KaoNative_version(JNIEnv *env, jclass 
 JNIEXPORT jint JNICALL Java_ch_sqooba_kao_KaoNative_solve(
     JNIEnv *env, jclass cls, jint P, jint B, jint R, jint RF, jint RFcur, jbyteArray rackOf,
     jshortArray wF, jshortArray wL, jintArray bounds, jintArray cur, jlong seed, jint rounds,
-    jint roundSize, jint device, jintArray replicasOut, jlongArray statsOut)
+    jint roundSize, jint device, jint nGpus, jint flags, jintArray replicasOut, jlongArray statsOut)
 {
     (void)cls;
     jbyte *rk = (*env)->GetByteArrayElements(env, rackOf, NULL);
@@ -33,8 +33,8 @@ JNIEXPORT jint JNICALL Java_ch_sqooba_kao_KaoNative_solve(
     pb.rack_lo = (const int32_t *)bd + 4 * B; pb.rack_hi = (const int32_t *)bd + 4 * B + R;
     pb.ppr_lo = bd[4 * B + 2 * R];            pb.ppr_hi = bd[4 * B + 2 * R + 1];
     pb.cur = (const int32_t *)cu;
-    /* KAO_FLAG_COLUMN_MAJOR is a hint: layouts the column-major evaluator does not cover keep the default one */
-    kao_options opt = {(uint64_t)seed, (uint32_t)rounds, (uint32_t)roundSize, device, KAO_FLAG_COLUMN_MAJOR};
+    /* nGpus > 1: the rounds are sharded over that many GPUs of this process (include/kao.h, kao_options) */
+    kao_options opt = {(uint64_t)seed, (uint32_t)rounds, (uint32_t)roundSize, device, (uint32_t)flags, nGpus, 0u};
     kao_result res;
     res.replicas = (int32_t *)out;
     const int rc = kao_solve(&pb, &opt, &res);
@@ -52,7 +52,8 @@ JNIEXPORT jint JNICALL Java_ch_sqooba_kao_KaoNative_solve(
         (*env)->Throw(env, (jthrowable)(*env)->NewObject(env, ex, ctor, rc, msg));
         return rc;
     }
-    jlong st[4] = {res.objective, res.violation, res.moves, (jlong)res.n_candidates};
-    (*env)->SetLongArrayRegion(env, statsOut, 0, 4, st);
+    jlong st[8] = {res.objective, res.violation, res.moves, (jlong)res.n_candidates,
+                   res.objective_bound, res.optimal, res.rounds_run, res.n_gpus};
+    (*env)->SetLongArrayRegion(env, statsOut, 0, 8, st);
     return rc;
 }

@@ -258,7 +258,7 @@ int usage()
 {
     std::fprintf(stderr,
                  "usage: kao-cli --assignment FILE|- --brokers 0,1,2 --racks 0:a,1:b,2:a [--rf N]\n"
-                 "               [--rounds 256] [--round-size 32768] [--restarts 1] [--seed 24301] [--device 0] [--delta] [--column-major] [--patience N] [--emit-lp] [--stats]\n");
+                 "               [--rounds 256] [--round-size 32768] [--restarts 1] [--seed 24301] [--device 0] [--delta] [--row-major] [--gpus N] [--patience N] [--emit-lp] [--stats]\n");
     return 2;
 }
 
@@ -267,13 +267,14 @@ int usage()
 int main(int argc, char **argv)
 {
     std::map<std::string, std::string> a;
-    bool emit = false, stats = false, delta = false, colmajor = false;
+    bool emit = false, stats = false, delta = false, rowmajor = false;
     for (int i = 1; i < argc; ++i) {
         std::string k = argv[i];
         if (k == "--emit-lp") { emit = true; continue; }
         if (k == "--stats") { stats = true; continue; }
         if (k == "--delta") { delta = true; continue; }
-        if (k == "--column-major") { colmajor = true; continue; }
+        if (k == "--row-major") { rowmajor = true; continue; }
+        if (k == "--column-major") continue;                  // accepted for old scripts: it is the default now
         if (k.rfind("--", 0) != 0 || i + 1 >= argc) return usage();
         a[k.substr(2)] = argv[++i];
     }
@@ -316,9 +317,10 @@ int main(int argc, char **argv)
         opt.rounds = a.count("rounds") ? (uint32_t)std::atoi(a["rounds"].c_str()) : 256;
         opt.round_size = a.count("round-size") ? (uint32_t)std::atoi(a["round-size"].c_str()) : 32768;
         opt.device = a.count("device") ? std::atoi(a["device"].c_str()) : 0;
+        opt.n_gpus = a.count("gpus") ? std::atoi(a["gpus"].c_str()) : 1;     // rounds sharded over N GPUs, same result
         opt.flags = a.count("restarts") ? (uint32_t)std::min(255, std::max(1, std::atoi(a["restarts"].c_str()))) : 1u;
         if (delta) opt.flags |= KAO_FLAG_DELTA;
-        if (colmajor) opt.flags |= KAO_FLAG_COLUMN_MAJOR;     // a hint: other layouts keep the row-major evaluator
+        if (rowmajor) opt.flags |= KAO_FLAG_ROW_MAJOR;        // measurements: the other full evaluator, same result
         if (a.count("patience")) opt.flags |= KAO_FLAG_PATIENCE(std::min(65535, std::max(0, std::atoi(a["patience"].c_str()))));
         std::vector<int32_t> reps((size_t)m.P * m.RF, -1);
         kao_result res{};
@@ -342,9 +344,11 @@ int main(int argc, char **argv)
         }
         std::cout << "]}\n";
         if (stats)
-            std::fprintf(stderr, "kao-cli: objective %lld, violation %lld, replica moves %d, %llu candidates, %.2f ms on device, %.2f ms total\n",
-                         (long long)res.objective, (long long)res.violation, res.moves,
-                         (unsigned long long)res.n_candidates, res.device_ms, res.total_ms);
+            std::fprintf(stderr, "kao-cli: objective %lld (upper bound %lld%s), violation %lld, replica moves %d, %llu candidates, "
+                                 "%d GPU(s), %.2f ms on device, %.2f ms total\n",
+                         (long long)res.objective, (long long)res.objective_bound, res.optimal ? ": proven optimal" : "",
+                         (long long)res.violation, res.moves, (unsigned long long)res.n_candidates, res.n_gpus, res.device_ms,
+                         res.total_ms);
         return rc == KAO_INFEASIBLE ? 3 : 0;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "kao-cli: %s\n", e.what());

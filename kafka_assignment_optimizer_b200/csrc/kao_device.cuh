@@ -21,8 +21,7 @@ namespace kao {
 constexpr int kMaxOps = 3;
 constexpr uint32_t kIdxBits = 24;
 constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1;
-constexpr uint32_t kObjCap = 0xFFFFFFu;
-constexpr uint32_t kViolCap = 0x7FFFu;      // keys < 2^63: same order as signed int64 (NCCL min)
+constexpr int kKeyBits = 63;                // keys < 2^63: same order as signed int64 (NCCL min)
 constexpr unsigned long long kKeyNone = 0x7FFFFFFFFFFFFFFFull;
 constexpr uint32_t kTag = 0x4B414F21u;
 constexpr int kRowsPerLane = 4;            // rows handled per lane per 128-row tile
@@ -44,6 +43,7 @@ struct Params {
     int ppr_lo, ppr_hi;
     int dense;                   // 1: weights come from dense_w (general tables in HBM)
     int nentries;                // packed weight entries per partition in use (0..4)
+    int key_obj_bits;            // width of the cost field of a packed key (docs/MODEL.md 3: per problem)
     int nplanes;                 // weighted mask planes in use (0 = objective uses entries / dense)
     int plane_on_leader;         // bit c set: plane c applies to the leader one-hot, else to the row
     int plane_value[6];          // weight of each plane
@@ -62,11 +62,27 @@ struct Params {
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t pack_key(int viol, int obj, uint32_t idx)
+// Packed key, smaller is better: violation | (objmax - objective) | index.  The cost field is as wide as
+// the problem's largest possible objective needs (obj_bits = bit length of P * RF * max weight, fixed
+// per problem by the host); the violation field takes what is left of 63 bits (15..38) and saturates.
+__host__ __device__ __forceinline__ uint64_t key_viol_cap(int obj_bits)
 {
-    const uint32_t v = viol > (int)kViolCap ? kViolCap : (uint32_t)viol;
-    const uint32_t c = (uint32_t)obj > kObjCap ? 0u : kObjCap - (uint32_t)obj;
-    return ((uint64_t)v << 48) | ((uint64_t)c << kIdxBits) | (uint64_t)(idx & kIdxMask);
+    const int vbits = kKeyBits - (int)kIdxBits - obj_bits;
+    return vbits >= 31 ? 0x7FFFFFFFull : ((1ull << vbits) - 1ull);
+}
+__host__ __device__ __forceinline__ uint64_t pack_key(int viol, int obj, uint32_t idx, int obj_bits)
+{
+    const uint64_t vcap = key_viol_cap(obj_bits);
+    const uint32_t omax = (1u << obj_bits) - 1u;
+    const uint64_t v = (uint64_t)(uint32_t)(viol < 0 ? 0 : viol) > vcap ? vcap : (uint64_t)(uint32_t)(viol < 0 ? 0 : viol);
+    const uint32_t c = (uint32_t)obj > omax ? 0u : omax - (uint32_t)obj;
+    return (v << (kIdxBits + obj_bits)) | ((uint64_t)c << kIdxBits) | (uint64_t)(idx & kIdxMask);
+}
+__host__ __device__ __forceinline__ uint32_t key_violation(uint64_t k, int obj_bits) { return (uint32_t)(k >> (kIdxBits + obj_bits)); }
+__host__ __device__ __forceinline__ uint32_t key_objective(uint64_t k, int obj_bits)
+{
+    const uint32_t omax = (1u << obj_bits) - 1u;
+    return omax - ((uint32_t)(k >> kIdxBits) & omax);
 }
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -6,15 +6,19 @@
 // in shared memory: for every slot s a bitmap over the partitions (32 per word).  Five planes:
 //   q = 0  replicas            T0[s] bit p  <=>  partition p has a replica on slot s
 //   q = 1  leader one-hot      T1[s] bit p  <=>  ... and is led from s
-//   q = 2,3,4  objective masks Mc[s] bit p  <=>  row-major mask plane c of partition p has bit s
+//   q = 2,3  follower weight   A0 = T0 & M0, A1 = T0 & M1   (Mc: objective mask plane c, transposed)
+//   q = 4  leader bonus        A2 = T1 & M2
+// (the objective planes are stored already masked, so the evaluation spends no AND on them; a patched
+// row gets its mask bits from the row-major mask planes kept next to the transposed ones).
 // The evaluation walks this matrix twice, each time with all data of a constraint inside one lane:
-//   rows     (C1, C7)  a lane owns 32 PARTITIONS (one word of every slot): a carry-save counter
-//            network over the slot words gives the bit-sliced replica count n_p of its partitions and
-//            the bit-sliced count z_p of non-empty rack fields; rows with n = z = RF cost nothing more
-//            (no POPC per row), the others are charged |n - RF| + (n - z) one by one;
+//   rows     (C1, C7)  a lane owns 32 PARTITIONS (one word of every slot).  Per 8-slot rack field two
+//            words are formed, `any` (the field holds a replica) and `dup` (it holds two or more); a
+//            partition is fine when no field is doubled and exactly RF fields are in use, which is one
+//            bit-sliced sum of the `any` words against RF — no POPC per row.  Partitions that fail are
+//            charged |n - RF| + (n - z) from their row-major row, one by one (rare);
 //   columns  (C2-C6, objective)  a lane owns one SLOT per row word: replica and leader totals of its
-//            columns are plain popcount sums — no bit-sliced counters, no cross-lane reduce-scatter —
-//            and the objective is popc(column & mask column).
+//            columns and the three objective sums are popcount sums over the partition words — no
+//            bit-sliced column counters, no cross-lane reduce-scatter.
 // The candidate's <= 3 patched rows are substituted while loading (columns) / skipped and scored
 // from the patch itself (rows), so every row of the candidate is evaluated, none is taken from a
 // previous evaluation.  Model: /root/reference/README.md:144-185.
@@ -27,26 +31,20 @@ namespace kao {
 // shape: every shared-memory offset of the evaluator is then an immediate), 0 = read at run time.
 // The other parameters are SCHEDULES of the same arithmetic (kao_set_schedule; results identical):
 //   kSync      how the warps of a CTA meet before an evaluation: 0 block barrier (all warps walk the
-//              evaluator together: instruction cache), 1 warp only, 2 one named barrier per scheduler,
-//              3 two groups that each hold half of every scheduler's warps (one group can generate
-//              while the other evaluates), 4 the same two groups started in anti-phase
-//   kCompress  carry-save compression of popcount streams: 0 none, 1 column / leader / bonus totals,
-//              2 also the two objective streams (pooled over the lane's slots)
+//              evaluator together), 1 warp only (one warp's generator overlaps another's evaluation)
+//   kPop       how the five popcount streams (column totals, leader totals, the two follower-weight
+//              sums, the leader bonus) trade POPC (XU pipe, 8 cycles a warp) for carry-save LOP3 (ALU
+//              pipe, 2 cycles): one hex digit per stream, 0 = a POPC per word, 1 = three per four words,
+//              2 = two, 3 = one (Harley-Seal accumulators carried across the whole column)
 //   kThreads   threads per CTA (0 = threads_for<W>()); fewer threads = more registers per thread
-//   kUnroll    unroll factor of the column chunk loop
-//   kRoll      1: the row pass loops over pairs of rack fields instead of being unrolled (a quarter of
-//              the code: matters when the warps of a scheduler are not in step and share the instruction cache)
-//   kFuse      1 (two-word rows, 32 partition words): the row network is not a pass of its own — column
-//              chunk j also folds rack field j into it, so that the ALU work of the rows and the
-//              popcounts of the columns overlap inside one warp even when all warps are in step
-template <int W_, int kNW_ = 0, int kSync_ = 0, int kCompress_ = 1, int kThreads_ = 0, int kUnroll_ = 1, int kRoll_ = 0, int kFuse_ = 0>
+template <int W_, int kNW_ = 0, int kSync_ = 1, int kPop_ = 0x11111, int kThreads_ = 0>
 struct EvalCfgT {
-    static constexpr int W = W_, NPH = 3, kRack = 3, kObj = 3, kNW = kNW_;
-    static constexpr int kSync = kSync_, kCompress = kCompress_, kThreads = kThreads_, kUnroll = kUnroll_, kRoll = kRoll_, kFuse = kFuse_;
-    static_assert(!kFuse_ || (W_ == 2 && kNW_ == 32), "fused passes: one rack field per column chunk");
+    static constexpr int W = W_, NPH = 5, kRack = 3, kObj = 3, kNW = kNW_;
+    static constexpr int kSync = kSync_, kPop = kPop_, kThreads = kThreads_;
     static constexpr bool kTrans = true;
 };
 constexpr int kTPlanes = 5;
+constexpr int kTMaskPlanes = 3;      // row-major objective mask planes kept behind the transposed planes
 
 // physical word of (plane q, slot s, partition word w).  Rows are rotated by 4 * (s & 7) words so
 // that the 128-bit column loads of a quarter warp (8 consecutive slots) hit 8 different bank groups;
@@ -58,11 +56,27 @@ __host__ __device__ __forceinline__ int t_word(int q, int s, int w, int nW, int 
     return (q * NSL + s) * nW + t;
 }
 
+// C1 + C7 of one row held row-major (a patched row of the candidate, or a row the vertical pass
+// flagged): same terms as row_rack_terms<W, 3>
+template <int W> __device__ __forceinline__ int row_terms_hi1_s8(const uint32_t (&x)[W], int RF)
+{
+    int n = 0, nz = 0;
+#pragma unroll
+    for (int t = 0; t < W; ++t) {
+        n += __popc(x[t]);
+        nz += __popc((((x[t] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x[t]) & 0x80808080u);
+    }
+    return abs(n - RF) + (n - nz);
+}
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | ((a | b) & c); }
+
 // ------------------------------------------------------------------------------------------
-// rows: C1 + C7 of every partition that is not patched, bit-sliced over 32 partitions per lane
+// rows: C1 + C7 of every partition that is not patched, 32 partitions per lane
 // ------------------------------------------------------------------------------------------
-template <int W, bool kShared, int kNW, int kRoll>
-__device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, int nW_rt, int P, int RF, int lane, const PatchSet &ps)
+template <int W, bool kShared, int kNW>
+__device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, const MemRef<kShared> &bitsT, int nW_rt, int Ppad, int P, int RF,
+                                             int lane, const PatchSet &ps)
 {
     const int nW = kNW ? kNW : nW_rt;
     constexpr int NB = 4 * W;                       // 8-slot blocks = rack fields
@@ -82,64 +96,50 @@ __device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, int nW_rt
             t -= (t >= nW) ? nW : 0;
             tk[k] = t;
         }
-        uint32_t ones = 0, twos = 0, fours = 0;     // n_p, weights 1 2 4
-        uint32_t e1 = 0, e2 = 0, e4 = 0, e8 = 0;    // n_p, weights 8 16 32 64
-        uint32_t z1 = 0, z2 = 0, z4 = 0, z8 = 0;    // non-empty fields of p, 0..8
-#pragma unroll (kRoll ? 1 : NB / 2)
-        for (int b = 0; b < NB; b += 2) {
-            uint32_t o8[2], ne[2];
+        uint32_t any[NB], dup = 0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t x[8];
+        for (int b = 0; b < NB; ++b) {
+            uint32_t x[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) x[k] = T.ld32((uint32_t)(((b + h) * 8 + k) * nW + tk[k]) * 4u);
-                uint32_t a2, b2, qa, qb;
-                csa(a2, ones, ones, x[0], x[1]);
-                csa(b2, ones, ones, x[2], x[3]);
-                csa(qa, twos, twos, a2, b2);
-                csa(a2, ones, ones, x[4], x[5]);
-                csa(b2, ones, ones, x[6], x[7]);
-                csa(qb, twos, twos, a2, b2);
-                csa(o8[h], fours, fours, qa, qb);
-                ne[h] = (x[0] | x[1] | x[2]) | (x[3] | x[4] | x[5]) | (x[6] | x[7]);
-            }
-            uint32_t c16, c;
-            csa(c16, e1, e1, o8[0], o8[1]);
-            c = e2 & c16; e2 ^= c16;
-            c16 = e4 & c; e4 ^= c;
-            e8 ^= c16;
-            uint32_t y2;
-            csa(y2, z1, z1, ne[0], ne[1]);
-            c = z2 & y2; z2 ^= y2;
-            y2 = z4 & c; z4 ^= c;
-            z8 ^= y2;
+            for (int k = 0; k < 8; ++k) x[k] = T.ld32((uint32_t)((b * 8 + k) * nW + tk[k]) * 4u);
+            const uint32_t a1 = x[0] | x[1] | x[2], a2 = x[3] | x[4] | x[5], a3 = x[6] | x[7];
+            dup |= maj3(x[0], x[1], x[2]) | maj3(x[3], x[4], x[5]);
+            dup |= (x[6] & x[7]) | maj3(a1, a2, a3);
+            any[b] = a1 | a2 | a3;
         }
-        // partitions whose replica count or non-empty field count is not RF (RF <= 8)
-        uint32_t bad = (ones ^ rf0) | (twos ^ rf1) | (fours ^ rf2) | (e1 ^ rf3) | e2 | e4 | e8;
-        bad |= (z1 ^ rf0) | (z2 ^ rf1) | (z4 ^ rf2) | (z8 ^ rf3);
+        // z = number of rack fields in use, bit-sliced (0..8); without a doubled field z is also the replica count
+        uint32_t z1, z2, z4 = 0, z8 = 0;
+        if constexpr (NB == 4) {
+            uint32_t c1, s1;
+            csa(c1, s1, any[0], any[1], any[2]);
+            z1 = s1 ^ any[3];
+            const uint32_t c2 = s1 & any[3];
+            z2 = c1 ^ c2;
+            z4 = c1 & c2;
+        } else {
+            uint32_t c1, s1, c2, s2, c3, s3, e1, t1;
+            csa(c1, s1, any[0], any[1], any[2]);
+            csa(c2, s2, any[3], any[4], any[5]);
+            csa(c3, s3, s1, s2, any[6]);
+            z1 = s3 ^ any[7];
+            const uint32_t c4 = s3 & any[7];
+            csa(e1, t1, c1, c2, c3);
+            z2 = t1 ^ c4;
+            const uint32_t e2 = t1 & c4;
+            z4 = e1 ^ e2;
+            z8 = e1 & e2;
+        }
+        uint32_t bad = dup | (z1 ^ rf0) | (z2 ^ rf1) | (z4 ^ rf2) | (z8 ^ rf3);
         bad &= valid;
-        for (uint32_t m = bad; m; m &= m - 1) {
-            const int s = __ffs(m) - 1;
-            const int n = (int)(((ones >> s) & 1u) | (((twos >> s) & 1u) << 1) | (((fours >> s) & 1u) << 2) |
-                                (((e1 >> s) & 1u) << 3) | (((e2 >> s) & 1u) << 4) | (((e4 >> s) & 1u) << 5) |
-                                (((e8 >> s) & 1u) << 6));
-            const int z = (int)(((z1 >> s) & 1u) | (((z2 >> s) & 1u) << 1) | (((z4 >> s) & 1u) << 2) | (((z8 >> s) & 1u) << 3));
-            viol += abs(n - RF) + (n - z);
+        for (uint32_t m = bad; m; m &= m - 1) {     // rare: the exact terms of that row, from the row-major base
+            const int p = 32 * w + __ffs(m) - 1;
+            uint32_t x[W];
+#pragma unroll
+            for (int t = 0; t < W; ++t) x[t] = bitsT.ld32((uint32_t)(t * Ppad + p) * 4u);
+            viol += row_terms_hi1_s8<W>(x, RF);
         }
     }
     return viol;
-}
-
-// C1 + C7 of one row held row-major (a patched row of the candidate): same terms as row_rack_terms<W, 3>
-template <int W> __device__ __forceinline__ int row_terms_hi1_s8(const uint32_t (&x)[W], int RF)
-{
-    int n = 0, nz = 0;
-#pragma unroll
-    for (int t = 0; t < W; ++t) {
-        n += __popc(x[t]);
-        nz += __popc((((x[t] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x[t]) & 0x80808080u);
-    }
-    return abs(n - RF) + (n - nz);
 }
 
 __device__ __forceinline__ void set_comp(uint4 &v, int k, uint32_t clear, uint32_t set)
@@ -150,74 +150,59 @@ __device__ __forceinline__ void set_comp(uint4 &v, int k, uint32_t clear, uint32
     else v.w = (v.w & ~clear) | set;
 }
 
-// Row network held across the column loop (kFuse): the planes of rows_vertical, one rack field at a time.
-struct RowNet {
-    uint32_t ones = 0, twos = 0, fours = 0, e1 = 0, e2 = 0, e4 = 0, e8 = 0, z1 = 0, z2 = 0, z4 = 0, z8 = 0;
-    __device__ __forceinline__ void fold(const uint32_t (&x)[8])
+// One popcount stream of the column pass: words arrive four at a time (one 128-bit load), the total is
+// read once per candidate.  kLvl picks how many of the four popcounts are replaced by carry-save adders:
+//   0  popc(a) + popc(b) + popc(c) + popc(d)                                            4 POPC
+//   1  a + b + c = 2 maj + xor                                                          3 POPC, 2 LOP3
+//   2  a running `ones` word absorbs the words two at a time, the carries are counted   2 POPC, 4 LOP3
+//   3  Harley-Seal: running `ones` and `twos`, only the weight-4 carry is counted       1 POPC, 6 LOP3
+template <int kLvl> struct PopStream {
+    uint32_t ones = 0, twos = 0;
+    int n1 = 0, n2 = 0, n4 = 0;
+    __device__ __forceinline__ void add4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
     {
-        uint32_t a2, b2, qa, qb, o8;
-        csa(a2, ones, ones, x[0], x[1]);
-        csa(b2, ones, ones, x[2], x[3]);
-        csa(qa, twos, twos, a2, b2);
-        csa(a2, ones, ones, x[4], x[5]);
-        csa(b2, ones, ones, x[6], x[7]);
-        csa(qb, twos, twos, a2, b2);
-        csa(o8, fours, fours, qa, qb);
-        const uint32_t ne = (x[0] | x[1] | x[2]) | (x[3] | x[4] | x[5]) | (x[6] | x[7]);
-        uint32_t c = e1 & o8; e1 ^= o8;             // + o8 at weight 8
-        uint32_t c2 = e2 & c; e2 ^= c;
-        c = e4 & c2; e4 ^= c2;
-        e8 ^= c;
-        c = z1 & ne; z1 ^= ne;                      // + 1 non-empty field
-        c2 = z2 & c; z2 ^= c;
-        c = z4 & c2; z4 ^= c2;
-        z8 ^= c;
-    }
-    __device__ __forceinline__ int charge(uint32_t valid, int RF) const
-    {
-        const uint32_t rf0 = (RF & 1) ? ~0u : 0u, rf1 = (RF & 2) ? ~0u : 0u, rf2 = (RF & 4) ? ~0u : 0u, rf3 = (RF & 8) ? ~0u : 0u;
-        uint32_t bad = (ones ^ rf0) | (twos ^ rf1) | (fours ^ rf2) | (e1 ^ rf3) | e2 | e4 | e8;
-        bad |= (z1 ^ rf0) | (z2 ^ rf1) | (z4 ^ rf2) | (z8 ^ rf3);
-        bad &= valid;
-        int viol = 0;
-        for (uint32_t m = bad; m; m &= m - 1) {
-            const int s = __ffs(m) - 1;
-            const int n = (int)(((ones >> s) & 1u) | (((twos >> s) & 1u) << 1) | (((fours >> s) & 1u) << 2) |
-                                (((e1 >> s) & 1u) << 3) | (((e2 >> s) & 1u) << 4) | (((e4 >> s) & 1u) << 5) |
-                                (((e8 >> s) & 1u) << 6));
-            const int z = (int)(((z1 >> s) & 1u) | (((z2 >> s) & 1u) << 1) | (((z4 >> s) & 1u) << 2) | (((z8 >> s) & 1u) << 3));
-            viol += abs(n - RF) + (n - z);
+        if constexpr (kLvl == 0) {
+            n1 += __popc(a) + __popc(b) + __popc(c) + __popc(d);
+        } else if constexpr (kLvl == 1) {
+            uint32_t h, l;
+            csa(h, l, a, b, c);
+            n1 += __popc(l) + __popc(d);
+            n2 += __popc(h);
+        } else if constexpr (kLvl == 2) {
+            uint32_t c1, c2;
+            csa(c1, ones, ones, a, b);
+            csa(c2, ones, ones, c, d);
+            n2 += __popc(c1) + __popc(c2);
+        } else {
+            uint32_t c1, c2, f;
+            csa(c1, ones, ones, a, b);
+            csa(c2, ones, ones, c, d);
+            csa(f, twos, twos, c1, c2);
+            n4 += __popc(f);
         }
-        return viol;
+    }
+    __device__ __forceinline__ int total() const
+    {
+        if constexpr (kLvl <= 1) return n1 + 2 * n2;
+        else if constexpr (kLvl == 2) return __popc(ones) + 2 * n2;
+        else return __popc(ones) + 2 * __popc(twos) + 4 * n4;
     }
 };
 
 // ------------------------------------------------------------------------------------------
-// the whole candidate.  T: the five transposed planes; prow: this warp's patched rows [kMaxOps * W]
+// the whole candidate.  T: the five transposed planes; bits / masks: the row-major base and the
+// row-major objective mask planes [3][W][Ppad]; prow: this warp's patched rows [kMaxOps * W]
 // ------------------------------------------------------------------------------------------
 template <class Cfg, bool kShared>
-__device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt, const Consts *cs, const PatchSet &ps,
-                                 const uint32_t *prow, int lane, int &viol_out, int &obj_out)
+__device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt, const uint32_t *bitsT, const uint32_t *masksT,
+                                 const Consts *cs, const PatchSet &ps, const uint32_t *prow, int lane, int &viol_out, int &obj_out)
 {
     constexpr int W = Cfg::W, kNW = Cfg::kNW;
     constexpr int NSL = 32 * W;
     const int nW = kNW ? kNW : nW_rt;
-    const MemRef<kShared> T(Tp);
+    const MemRef<kShared> T(Tp), B(bitsT);
     // ---- rows: unpatched partitions from the transposed bit-plane, patched ones from the patch
-    int viol = 0;
-    RowNet net;                                     // kFuse: filled inside the column loop
-    uint32_t net_valid = 0;
-    int net_tk[8];
-    if constexpr (Cfg::kFuse) {
-        const int left = d.P - 32 * lane;           // 32 partition words: word `lane` is this lane's
-        net_valid = left >= 32 ? ~0u : (left <= 0 ? 0u : ((1u << left) - 1u));
-#pragma unroll
-        for (int i = 0; i < kMaxOps; ++i) net_valid &= ((ps.p[i] >> 5) == lane) ? ~(1u << (ps.p[i] & 31)) : ~0u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) net_tk[k] = ((lane + 4 * k) & 31) * 4;
-    } else {
-        viol = rows_vertical<W, kShared, kNW, Cfg::kRoll>(T, nW, d.P, d.RF, lane, ps);
-    }
+    int viol = rows_vertical<W, kShared, kNW>(T, B, nW, d.Ppad, d.P, d.RF, lane, ps);
     if (lane < kMaxOps) {
         const int i = lane;
         const int pp = i == 0 ? ps.p[0] : (i == 1 ? ps.p[1] : ps.p[2]);
@@ -229,31 +214,27 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
         }
     }
     // ---- columns: this lane owns slot `lane` of every row word
-    int cnt[W], lcnt[W], cnt2[W], lcnt2[W], o0 = 0, o1 = 0, o2 = 0, o2b = 0, o0b = 0, o1b = 0;
-#pragma unroll
-    for (int t = 0; t < W; ++t) cnt[t] = lcnt[t] = cnt2[t] = lcnt2[t] = 0;
-    const int rot = nW >= 32 ? 4 * (lane & 7) : 0;
+    PopStream<(Cfg::kPop >> 0) & 15> cnt[W];
+    PopStream<(Cfg::kPop >> 4) & 15> lcnt[W];
+    PopStream<(Cfg::kPop >> 8) & 15> o0;
+    PopStream<(Cfg::kPop >> 12) & 15> o1;
+    PopStream<(Cfg::kPop >> 16) & 15> o2;
     const int nch = nW >> 2;
-#pragma unroll (Cfg::kUnroll)
+    int tw = nW >= 32 ? 4 * (lane & 7) : 0;        // physical word of logical word 0 (see t_word)
+#pragma unroll 1
     for (int j = 0; j < nch; ++j) {
-        int tw = 4 * j + rot;
-        tw -= (tw >= nW) ? nW : 0;
-        uint4 col[W], oh[W], m0[W], m1[W], m2[W];
+        uint4 col[W], oh[W], a0[W], a1[W], a2[W];
 #pragma unroll
         for (int t = 0; t < W; ++t) {
             const int s = lane + 32 * t;
             col[t] = T.ld128((uint32_t)((0 * NSL + s) * nW + tw) * 4u);
             oh[t] = T.ld128((uint32_t)((1 * NSL + s) * nW + tw) * 4u);
-            m0[t] = T.ld128((uint32_t)((2 * NSL + s) * nW + tw) * 4u);
-            m1[t] = T.ld128((uint32_t)((3 * NSL + s) * nW + tw) * 4u);
-            m2[t] = T.ld128((uint32_t)((4 * NSL + s) * nW + tw) * 4u);
+            a0[t] = T.ld128((uint32_t)((2 * NSL + s) * nW + tw) * 4u);
+            a1[t] = T.ld128((uint32_t)((3 * NSL + s) * nW + tw) * 4u);
+            a2[t] = T.ld128((uint32_t)((4 * NSL + s) * nW + tw) * 4u);
         }
-        if constexpr (Cfg::kFuse) {                 // rack field j of the row network (8 slots x this lane's word)
-            uint32_t x[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = T.ld32((uint32_t)((j * 8 + k) * (nW * 4) + net_tk[k]));
-            net.fold(x);
-        }
+        tw += 4;
+        tw -= (tw >= nW) ? nW : 0;
         // the candidate's patched rows replace their partition's bit in this lane's columns
         if (((ps.p[0] >> 7) == j) | ((ps.p[1] >> 7) == j) | ((ps.p[2] >> 7) == j)) {
 #pragma unroll
@@ -266,88 +247,43 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
                     for (int t = 0; t < W; ++t) {
                         const bool has = (prow[i * W + t] >> lane) & 1u;
                         const bool led = has && ((int)ps.ld[i] == lane + 32 * t);
+                        const bool m0 = (masksT[(size_t)(0 * W + t) * d.Ppad + pp] >> lane) & 1u;
+                        const bool m1 = (masksT[(size_t)(1 * W + t) * d.Ppad + pp] >> lane) & 1u;
+                        const bool m2 = (masksT[(size_t)(2 * W + t) * d.Ppad + pp] >> lane) & 1u;
                         set_comp(col[t], k, bit, has ? bit : 0u);
                         set_comp(oh[t], k, bit, led ? bit : 0u);
+                        set_comp(a0[t], k, bit, (has && m0) ? bit : 0u);
+                        set_comp(a1[t], k, bit, (has && m1) ? bit : 0u);
+                        set_comp(a2[t], k, bit, (led && m2) ? bit : 0u);
                     }
                 }
             }
         }
-        // The XU pipe (POPC) is the scarce one here: the four words of a chunk that feed the same total
-        // go through one carry-save adder first, a + b + c = 2 * maj + xor, so 3 popcounts replace 4
-        // (totals of a column, valid leaders of a column, leader bonus); the doubled parts are summed
-        // apart and weighted once per candidate.
         uint32_t hit[4];                            // leader bonus: the one-hot columns of a lane are disjoint
-        uint32_t y0[4 * W], y1[4 * W];              // objective streams (kCompress 2)
 #pragma unroll
         for (int i = 0; i < 4; ++i) hit[i] = 0;
 #pragma unroll
         for (int t = 0; t < W; ++t) {
-            if constexpr (Cfg::kCompress >= 1) {
-                uint32_t h, l;
-                csa(h, l, col[t].x, col[t].y, col[t].z);
-                cnt[t] += __popc(l) + __popc(col[t].w);
-                cnt2[t] += __popc(h);
-                csa(h, l, oh[t].x, oh[t].y, oh[t].z);
-                lcnt[t] += __popc(l) + __popc(oh[t].w);
-                lcnt2[t] += __popc(h);
-            }
+            cnt[t].add4(col[t].x, col[t].y, col[t].z, col[t].w);
+            lcnt[t].add4(oh[t].x, oh[t].y, oh[t].z, oh[t].w);
+            o0.add4(a0[t].x, a0[t].y, a0[t].z, a0[t].w);
+            o1.add4(a1[t].x, a1[t].y, a1[t].z, a1[t].w);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t c = comp(col[t], i);
-                if constexpr (Cfg::kCompress == 0) {
-                    cnt[t] += __popc(c);
-                    lcnt[t] += __popc(comp(oh[t], i));
-                }
-                if constexpr (Cfg::kCompress >= 2) {
-                    y0[4 * t + i] = c & comp(m0[t], i);
-                    y1[4 * t + i] = c & comp(m1[t], i);
-                } else {
-                    o0 += __popc(c & comp(m0[t], i));
-                    o1 += __popc(c & comp(m1[t], i));
-                }
-                hit[i] |= comp(oh[t], i) & comp(m2[t], i);
-            }
+            for (int i = 0; i < 4; ++i) hit[i] |= comp(a2[t], i);
         }
-        if constexpr (Cfg::kCompress >= 2) {
-            // 4 * W words per stream: every full group of three goes through one carry-save adder
-#pragma unroll
-            for (int g = 0; g + 3 <= 4 * W; g += 3) {
-                uint32_t h, l;
-                csa(h, l, y0[g], y0[g + 1], y0[g + 2]);
-                o0 += __popc(l);
-                o0b += __popc(h);
-                csa(h, l, y1[g], y1[g + 1], y1[g + 2]);
-                o1 += __popc(l);
-                o1b += __popc(h);
-            }
-#pragma unroll
-            for (int g = (4 * W) / 3 * 3; g < 4 * W; ++g) { o0 += __popc(y0[g]); o1 += __popc(y1[g]); }
-        }
-        if constexpr (Cfg::kCompress >= 1) {
-            uint32_t h, l;
-            csa(h, l, hit[0], hit[1], hit[2]);
-            o2 += __popc(l) + __popc(hit[3]);
-            o2b += __popc(h);
-        } else {
-            o2 += __popc(hit[0]) + __popc(hit[1]) + __popc(hit[2]) + __popc(hit[3]);
-        }
+        o2.add4(hit[0], hit[1], hit[2], hit[3]);
     }
-    if constexpr (Cfg::kFuse) viol += net.charge(net_valid, d.RF);
-#pragma unroll
-    for (int t = 0; t < W; ++t) { cnt[t] += 2 * cnt2[t]; lcnt[t] += 2 * lcnt2[t]; }
-    o2 += 2 * o2b;
-    o0 += 2 * o0b;
-    o1 += 2 * o1b;
     // ---- C3 / C4 on this lane's columns, C2/C5 as P - sum of valid leaders, C6 per 8-lane rack group
 #pragma unroll
     for (int t = 0; t < W; ++t) {
         const int s = lane + 32 * t;
-        viol += band_violation(cnt[t], cs->bnd_rep[s]) + band_violation(lcnt[t], cs->bnd_ldr[s]) - lcnt[t];
-        const int tot = __reduce_add_sync(0xFFu << (lane & 24), cnt[t]);
+        const int c = cnt[t].total(), l = lcnt[t].total();
+        viol += band_violation(c, cs->bnd_rep[s]) + band_violation(l, cs->bnd_ldr[s]) - l;
+        const int tot = __reduce_add_sync(0xFFu << (lane & 24), c);
         const int rk = s >> 3;
         if ((lane & 7) == 0 && rk < d.R) viol += max(tot - cs->rack_hi[rk], 0) + max(cs->rack_lo[rk] - tot, 0);
     }
-    const int obj = o0 * d.plane_value[0] + o1 * d.plane_value[1] + o2 * d.plane_value[2];
+    const int obj = o0.total() * d.plane_value[0] + o1.total() * d.plane_value[1] + o2.total() * d.plane_value[2];
     viol_out = __reduce_add_sync(0xFFFFFFFFu, viol) + d.P;
     obj_out = __reduce_add_sync(0xFFFFFFFFu, obj);
 }
@@ -364,27 +300,38 @@ __device__ __forceinline__ uint32_t t_gather(int q, int s, int w, const uint32_t
     const int sw = s >> 5, sb = s & 31;
     for (int b = 0; b < 32; ++b) {
         const int p = 32 * w + b;
+        const uint32_t has = (bitsT[(size_t)sw * Ppad + p] >> sb) & 1u;
+        const uint32_t led = has & ((int)leader[p] == s ? 1u : 0u);
         uint32_t bit;
-        if (q == 0) bit = (bitsT[(size_t)sw * Ppad + p] >> sb) & 1u;
-        else if (q == 1) bit = ((bitsT[(size_t)sw * Ppad + p] >> sb) & 1u) & ((int)leader[p] == s ? 1u : 0u);
-        else bit = (planesT[((size_t)(q - 2) * W + sw) * Ppad + p] >> sb) & 1u;
+        if (q == 0) bit = has;
+        else if (q == 1) bit = led;
+        else bit = (q == 4 ? led : has) & ((planesT[((size_t)(q - 2) * W + sw) * Ppad + p] >> sb) & 1u);
         out |= bit << b;
     }
     return out;
 }
-// row p of the base changes from (oldrow, oldld) to (newrow, newld): planes 0 and 1 follow
+// Row p of the base becomes (newrow, newld): every lane rewrites bit p of its own slots' words in all
+// five planes (the whole warp calls this; the row-major base itself is patched by the caller).
 template <int W>
-__device__ __forceinline__ void t_patch_row(uint32_t *T, int nW, int p, const uint32_t (&oldrow)[W], uint32_t oldld,
-                                            const uint32_t (&newrow)[W], uint32_t newld)
+__device__ __forceinline__ void t_patch_row(uint32_t *T, int nW, int Ppad, int p, const uint32_t (&newrow)[W], uint32_t newld,
+                                            const uint32_t *masksT, int lane)
 {
     constexpr int NSL = 32 * W;
     const int w = p >> 5;
     const uint32_t bit = 1u << (p & 31);
 #pragma unroll
-    for (int t = 0; t < W; ++t)
-        for (uint32_t m = oldrow[t] ^ newrow[t]; m; m &= m - 1) T[t_word(0, 32 * t + __ffs(m) - 1, w, nW, NSL)] ^= bit;
-    if ((int)oldld < NSL && row_has<W>(oldrow, (int)oldld)) T[t_word(1, (int)oldld, w, nW, NSL)] &= ~bit;
-    if ((int)newld < NSL && row_has<W>(newrow, (int)newld)) T[t_word(1, (int)newld, w, nW, NSL)] |= bit;
+    for (int t = 0; t < W; ++t) {
+        const int s = lane + 32 * t;
+        const bool has = (newrow[t] >> lane) & 1u;
+        const bool led = has && ((int)newld == s);
+#pragma unroll
+        for (int q = 0; q < kTPlanes; ++q) {
+            bool on = q == 0 ? has : led;
+            if (q >= 2) on = (q == 4 ? led : has) && ((masksT[(size_t)((q - 2) * W + t) * Ppad + p] >> lane) & 1u);
+            uint32_t &word = T[t_word(q, s, w, nW, NSL)];
+            word = on ? (word | bit) : (word & ~bit);
+        }
+    }
 }
 
 }  // namespace kao

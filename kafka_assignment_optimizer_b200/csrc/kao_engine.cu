@@ -11,10 +11,10 @@
 #include <map>
 #include <mutex>
 #include <cstdio>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 // The search kernels are instantiated in kao_inst.cu (one object per row width / counter depth /
@@ -23,18 +23,16 @@
     extern template __global__ void KAO_ROUND_KERNEL(W, NPH, R, O);            \
     extern template __global__ void KAO_PERSISTENT_KERNEL(W, NPH, R, O, threads_for<W>(), false);
 #define KAO_DECL_DELTA(W, NPH, R, O) extern template __global__ void KAO_PERSISTENT_KERNEL(W, NPH, R, O, KAO_THREADS_DELTA, true);
-KAO_FOR_CFGS_NARROW(KAO_DECL_FULL, 1, 3) KAO_FOR_CFGS_NARROW(KAO_DECL_FULL, 1, 5)
-KAO_FOR_CFGS_NARROW(KAO_DECL_FULL, 2, 3) KAO_FOR_CFGS_NARROW(KAO_DECL_FULL, 2, 5)
-KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 4, 3) KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 4, 5)
-KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 8, 3) KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 8, 5)
-KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 1, 3) KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 1, 5)
-KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 2, 3) KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 2, 5)
-extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 0);  // column-major evaluator, kao_device_t.cuh
-extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 0);
-extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 32);
-extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 32);
-#define KAO_DECL_TUNE(S, C, T, U, RL, F) extern template __global__ void KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U, RL, F);
-KAO_FOR_TUNE_ALL(KAO_DECL_TUNE)
+KAO_FOR_CFGS_NARROW(KAO_DECL_FULL, 1, 5) KAO_FOR_CFGS_NARROW(KAO_DECL_FULL, 2, 5)
+KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 4, 5) KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 8, 5)
+KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 1, 5) KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 2, 5)
+// column-major evaluator (kao_device_t.cuh), every built schedule
+#define KAO_DECL_T(S, POP, T)                                                  \
+    extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 0, S, POP, T);  \
+    extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 32, S, POP, T); \
+    extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 0, S, POP, T);  \
+    extern template __global__ void KAO_PERSISTENT_KERNEL_T(2, 32, S, POP, T);
+KAO_FOR_SCHEDULES(KAO_DECL_T)
 
 
 // Winner of a round becomes the base: re-materialise its patches from (seed, round, index), write
@@ -105,13 +103,28 @@ eval_batch_kernel(Params d, const uint32_t *cand_bits, const uint8_t *cand_leade
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
-static bool schedule_exists(int sync, int compress, int threads, int unroll, int roll, int fuse);
+static bool schedule_exists(int sync, int pop, int threads);
 #define CUDA_TRY(expr)                                                                       \
     do {                                                                                     \
         cudaError_t e_ = (expr);                                                             \
         if (e_ != cudaSuccess)                                                               \
             return fail(KAO_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
     } while (0)
+
+// Nothing may cross the C ABI but a return code (include/kao.h: "never throw"): every extern "C" body
+// runs inside this guard.
+template <class F> static int guarded(F &&f) noexcept
+{
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return fail(KAO_E_ARG, "out of host memory (argument too large?)");
+    } catch (const std::exception &e) {
+        return fail(KAO_E_CUDA, std::string("internal error: ") + e.what());
+    } catch (...) {
+        return fail(KAO_E_CUDA, "internal error");
+    }
+}
 
 // Device buffers are recycled across handles: kao_solve creates and destroys a session per call,
 // and cudaMalloc / cudaFree (which synchronises the device) would dominate short solves.
@@ -140,7 +153,28 @@ struct DevPool {
     }
 };
 DevPool g_pool;
+
+// a temporary device buffer that is freed on every path out of the scope that owns it
+template <class T> struct DevTmp {
+    T *p = nullptr;
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, count * sizeof(T)); }
+    ~DevTmp() { if (p) cudaFree(p); }
+};
+
+// every wait inside a kernel (grid barrier, peer GPUs) gives up after this much wall time and the call
+// returns KAO_E_CUDA instead of hanging the GPU; KAO_WAIT_TIMEOUT_MS overrides the 20 s default
+unsigned long long wait_budget_ns()
+{
+    static const unsigned long long ns = [] {
+        double ms = 20000.0;
+        if (const char *e = std::getenv("KAO_WAIT_TIMEOUT_MS")) { const double v = std::atof(e); if (v >= 1.0) ms = v; }
+        return (unsigned long long)(ms * 1e6);
+    }();
+    return ns;
+}
 }  // namespace
+
+constexpr size_t kBarBytes = 32;   // d_bar: [0] grid barrier, [1] release, [2] abort, [3] rounds run, [4..7] early-stop carry (2 x u64)
 
 struct kao_handle {
     std::vector<std::pair<void *, size_t>> owned;   // device buffers to hand back to the pool
@@ -150,25 +184,26 @@ struct kao_handle {
     Params prm{};
     SmemPlan plan{};
     int threads = 0, grid = 0;
-    // column-major full evaluator (kao_set_evaluator): layout supported, selected, its shared-memory plan
+    // column-major full evaluator (kao_set_evaluator): layout supported, selected (the default wherever it
+    // applies), its shared-memory plan
     bool trans_ok = false;
     int evaluator = KAO_EVAL_ROW_MAJOR;
     SmemPlan plan_t{};
-    // schedule of the column-major evaluator (kao_set_schedule): barrier form, popcount compression,
-    // threads per CTA, unroll of the column loop.  Same results; (0, 1, 768, 1) is the default.
-    int sch_sync = 0, sch_compress = 1, sch_threads = KAO_THREADS, sch_unroll = 1, sch_roll = 0, sch_fuse = 0;
+    // schedule of the column-major evaluator (kao_set_schedule): barrier form, popcount compression per
+    // stream, threads per CTA.  Same results whatever the schedule.
+    int sch_sync = KAO_SCHEDULE_DEFAULT_SYNC, sch_pop = KAO_SCHEDULE_DEFAULT_POP, sch_threads = KAO_THREADS;
     // device buffers
     uint32_t *d_bits = nullptr; uint8_t *d_leader = nullptr; uint32_t *d_sw = nullptr;
     uint32_t *d_dense = nullptr; uint32_t *d_planes = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
     Consts *d_consts = nullptr; unsigned long long *d_key = nullptr; unsigned long long *d_keys = nullptr;
     size_t keys_cap = 0;
     long long *d_vo = nullptr;
-    unsigned int *d_bar = nullptr;          // [0] grid barrier, [1] release, [2] abort flag
-    // cross-GPU exchange (kao_p2p_*)
-    Mailbox *d_mail = nullptr;              // own mailbox (plain cudaMalloc: exported through CUDA IPC)
+    unsigned int *d_bar = nullptr;          // kBarBytes, see above
+    // cross-GPU exchange (kao_p2p_*, kao_solve with n_gpus > 1)
+    Mailbox *d_mail = nullptr;              // own mailbox (plain cudaMalloc: exported through CUDA IPC / used by peers directly)
     Mailbox *peer_mail[kMaxPeers] = {};
     Mailbox **d_mailptrs = nullptr;         // device copy of peer_mail for the kernel
-    bool peer_opened[kMaxPeers] = {};
+    bool peer_opened[kMaxPeers] = {};       // mapped with cudaIpcOpenMemHandle (to be closed)
     int p2p_rank = 0, p2p_world = 1;
     uint64_t p2p_calls = 0;
     uint32_t patience = 0, last_rounds = 0;
@@ -235,7 +270,7 @@ template <bool kDelta> struct LaunchPersistent {
             if (e != cudaSuccess) return e;
             Params prm = h->prm;
             // the column-major plan depends on the warps per CTA of the schedule (per-warp scratch)
-            SmemPlan plan = Cfg::kTrans ? make_plan(Cfg::W, h->hm.Ppad, T / 32, kTPlanes * Cfg::W, h->hm.P, h->hm.RF, false) : h->plan;
+            SmemPlan plan = Cfg::kTrans ? make_plan(Cfg::W, h->hm.Ppad, T / 32, (kTPlanes + kTMaskPlanes) * Cfg::W, h->hm.P, h->hm.RF, false) : h->plan;
             uint64_t seed = a.seed; uint32_t fr = a.first_round, rounds = a.rounds, rs = a.round_size;
             unsigned long long *keys = a.d_keys, *all = a.all_keys; unsigned int *bar = a.d_bar;
             P2P pp = a.pp;
@@ -251,10 +286,8 @@ template <bool kDelta> struct LaunchPersistent {
 template <int W, int NPH, int kRack, class F, class A>
 static cudaError_t dispatch_obj(kao_handle *h, const F &f, const A &a)
 {
-    const int planes = h->prm.nplanes;
     if constexpr (W <= 2) {
-        if (planes == 3) return f.template run<EvalCfg<W, NPH, kRack, 3>>(h, a);
-        if (planes == 6) return f.template run<EvalCfg<W, NPH, kRack, 6>>(h, a);
+        if (h->prm.nplanes == 3) return f.template run<EvalCfg<W, NPH, kRack, 3>>(h, a);
     }
     return f.template run<EvalCfg<W, NPH, kRack, kObjEntries>>(h, a);
 }
@@ -270,12 +303,11 @@ static cudaError_t dispatch_w(kao_handle *h, const F &f, const A &a)
 }
 template <class F, class A> static cudaError_t dispatch(kao_handle *h, const F &f, const A &a)
 {
-    const bool small = h->hm.Ppad / 32 <= 63;             // per-lane column counts fit 6 planes
-    switch (h->hm.W) {
-    case 1: return small ? dispatch_w<1, 3>(h, f, a) : dispatch_w<1, 5>(h, f, a);
-    case 2: return small ? dispatch_w<2, 3>(h, f, a) : dispatch_w<2, 5>(h, f, a);
-    case 4: return small ? dispatch_w<4, 3>(h, f, a) : dispatch_w<4, 5>(h, f, a);
-    default: return small ? dispatch_w<8, 3>(h, f, a) : dispatch_w<8, 5>(h, f, a);
+    switch (h->hm.W) {                                    // one counter depth: per-lane column counts up to 255
+    case 1: return dispatch_w<1, 5>(h, f, a);
+    case 2: return dispatch_w<2, 5>(h, f, a);
+    case 4: return dispatch_w<4, 5>(h, f, a);
+    default: return dispatch_w<8, 5>(h, f, a);
     }
 }
 // all rounds of a search in one cooperative launch, with the evaluator the session selected
@@ -283,19 +315,17 @@ static cudaError_t launch_persistent(kao_handle *h, const PersistArgs &pa, bool 
 {
     if (delta) return dispatch(h, LaunchPersistent<true>{}, pa);
     if (h->evaluator == KAO_EVAL_COLUMN_MAJOR) {
-        if (h->hm.Ppad == 1024 && h->hm.W == 2 &&
-            !(h->sch_sync == 0 && h->sch_compress == 1 && h->sch_threads == KAO_THREADS && h->sch_unroll == 1 && h->sch_roll == 0 && h->sch_fuse == 0)) {
-#define KAO_RUN_TUNE(S, C, T, U, RL, F)                                                                          \
-    if (h->sch_sync == S && h->sch_compress == C && h->sch_threads == T && h->sch_unroll == U && h->sch_roll == RL && h->sch_fuse == F) \
-        return LaunchPersistent<false>{}.template run<KAO_TUNE_CFG(S, C, T, U, RL, F)>(h, pa);
-            KAO_FOR_TUNE_ALL(KAO_RUN_TUNE)
-#undef KAO_RUN_TUNE
-        }
-        if (h->hm.Ppad == 1024)                                 // 32 partition words per slot: compile-time offsets
-            return h->hm.W == 1 ? LaunchPersistent<false>{}.template run<EvalCfgT<1, 32>>(h, pa)
-                                : LaunchPersistent<false>{}.template run<EvalCfgT<2, 32>>(h, pa);
-        return h->hm.W == 1 ? LaunchPersistent<false>{}.template run<EvalCfgT<1>>(h, pa)
-                            : LaunchPersistent<false>{}.template run<EvalCfgT<2>>(h, pa);
+        const bool nw32 = h->hm.Ppad == 1024;                   // 32 partition words per slot: compile-time offsets
+#define KAO_RUN_T(S, POP, T)                                                                                   \
+    if (h->sch_sync == S && h->sch_pop == POP && h->sch_threads == T) {                                        \
+        if (h->hm.W == 1) return nw32 ? LaunchPersistent<false>{}.template run<EvalCfgT<1, 32, S, POP, T>>(h, pa) \
+                                      : LaunchPersistent<false>{}.template run<EvalCfgT<1, 0, S, POP, T>>(h, pa); \
+        return nw32 ? LaunchPersistent<false>{}.template run<EvalCfgT<2, 32, S, POP, T>>(h, pa)                 \
+                    : LaunchPersistent<false>{}.template run<EvalCfgT<2, 0, S, POP, T>>(h, pa);                 \
+    }
+        KAO_FOR_SCHEDULES(KAO_RUN_T)
+#undef KAO_RUN_T
+        return cudaErrorInvalidValue;                           // kao_set_schedule only accepts built schedules
     }
     return dispatch(h, LaunchPersistent<false>{}, pa);
 }
@@ -327,10 +357,7 @@ static int upload_base(kao_handle *h, const std::vector<uint32_t> &bitsT, const 
     return KAO_OK;
 }
 
-extern "C" int kao_version(void) { return KAO_VERSION; }
-extern "C" const char *kao_last_error(void) { return g_err.c_str(); }
-
-extern "C" int kao_destroy(kao_handle *h)
+static int destroy_impl(kao_handle *h)
 {
     if (!h) return KAO_OK;
     cudaSetDevice(h->device);
@@ -345,7 +372,15 @@ extern "C" int kao_destroy(kao_handle *h)
     return KAO_OK;
 }
 
-extern "C" int kao_reset(kao_handle *h);
+static int reset_impl(kao_handle *h)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<uint32_t> bitsT; std::vector<uint8_t> leader;
+    initial_base(h->hm, bitsT, leader);
+    return upload_base(h, bitsT, leader);
+}
+
 static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
 {
     std::string why;
@@ -374,14 +409,17 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     if (h->plan.total > 227u * 1024u)
         return fail(KAO_E_ARG, "problem too large for the shared-memory resident search kernel");
     // column-major evaluator: 8-slot rack fields, C7 = "at most one replica per rack", three mask planes;
-    // its five transposed planes (5 * W words per partition) take the place of the objective table
-    h->plan_t = make_plan(W, Ppad, h->threads / 32, kTPlanes * W, m.P, m.RF, false);
+    // its five transposed planes and the row-major mask planes ((5 + 3) * W words per partition) take
+    // the place of the objective table.  It is the default full evaluator wherever it applies.
+    h->plan_t = make_plan(W, Ppad, KAO_THREADS / 32, (kTPlanes + kTMaskPlanes) * W, m.P, m.RF, false);
     h->trans_ok = W <= 2 && m.hi1 && m.log2S == 3 && h->hm.nplanes == 3 && h->plan_t.total <= 227u * 1024u;
-    if (const char *env = std::getenv("KAO_SCHEDULE")) {      // "sync,compress,threads,unroll,roll,fuse": tuning only, ignored if not built
-        int a = 0, b = 1, c = KAO_THREADS, u = 1, rl = 0, fu = 0;
-        if (std::sscanf(env, "%d,%d,%d,%d,%d,%d", &a, &b, &c, &u, &rl, &fu) == 6 && schedule_exists(a, b, c, u, rl, fu) && h->trans_ok &&
-            W == 2 && Ppad == 1024) {
-            h->sch_sync = a; h->sch_compress = b; h->sch_threads = c; h->sch_unroll = u; h->sch_roll = rl; h->sch_fuse = fu;
+    if (h->trans_ok) h->evaluator = KAO_EVAL_COLUMN_MAJOR;
+    if (const char *env = std::getenv("KAO_EVALUATOR"))       // "row" forces the row-major evaluator (measurements)
+        if (std::strcmp(env, "row") == 0) h->evaluator = KAO_EVAL_ROW_MAJOR;
+    if (const char *env = std::getenv("KAO_SCHEDULE")) {      // "sync,pop(hex),threads": measurements only, ignored if not built
+        int a = 0, c = 0; unsigned b = 0;
+        if (std::sscanf(env, "%d,%x,%d", &a, &b, &c) == 3 && schedule_exists(a, (int)b, c)) {
+            h->sch_sync = a; h->sch_pop = (int)b; h->sch_threads = c;
         }
     }
     h->grid = h->sms;
@@ -394,6 +432,7 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     CUDA_TRY(dalloc(h, &h->d_nD, 16));
     CUDA_TRY(dalloc(h, &h->d_consts, sizeof(Consts)));
     CUDA_TRY(dalloc(h, &h->d_key, 16));
+    CUDA_TRY(dalloc(h, &h->d_bar, kBarBytes));
     CUDA_TRY(cudaMemset(h->d_nD, 0, 16));
     { const unsigned long long none[2] = {kKeyNone, kKeyNone}; CUDA_TRY(cudaMemcpy(h->d_key, none, 16, cudaMemcpyHostToDevice)); }
     if (m.dense) {
@@ -414,15 +453,16 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     Params &p = h->prm;
     p.P = m.P; p.Ppad = Ppad; p.B = m.B; p.R = m.R; p.RF = m.RF; p.NS = m.NS; p.log2S = m.log2S;
     p.ppr_lo = m.ppr_lo; p.ppr_hi = m.ppr_hi; p.dense = m.dense ? 1 : 0;
+    p.key_obj_bits = m.key_obj_bits;
     p.nentries = m.nentries; p.nplanes = m.nplanes; p.plane_on_leader = m.plane_on_leader;
     for (int c = 0; c < 6; ++c) p.plane_value[c] = m.plane_value[c];
     p.planesT = h->d_planes;
     p.bitsT = h->d_bits; p.leader = h->d_leader; p.swT = h->d_sw; p.dense_w = h->d_dense;
     p.homeT = h->d_home; p.D = h->d_D; p.DL = h->d_DL; p.nD = h->d_nD; p.consts = h->d_consts;
-    return kao_reset(h);
+    return reset_impl(h);
 }
 
-extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **out)
+static int create_handle(const kao_problem *pb, int32_t device, kao_handle **out)
 {
     if (!pb || !out) return fail(KAO_E_ARG, "null argument");
     *out = nullptr;
@@ -430,7 +470,7 @@ extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **ou
     const int rc = create_impl(pb, device, h);
     if (rc != KAO_OK) {
         const std::string keep = g_err;
-        kao_destroy(h);
+        destroy_impl(h);
         g_err = keep;
         return rc;
     }
@@ -438,16 +478,7 @@ extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **ou
     return KAO_OK;
 }
 
-extern "C" int kao_reset(kao_handle *h)
-{
-    if (!h) return fail(KAO_E_ARG, "null handle");
-    CUDA_TRY(cudaSetDevice(h->device));
-    std::vector<uint32_t> bitsT; std::vector<uint8_t> leader;
-    initial_base(h->hm, bitsT, leader);
-    return upload_base(h, bitsT, leader);
-}
-
-extern "C" int kao_set_base(kao_handle *h, const int32_t *replicas)
+static int set_base_impl(kao_handle *h, const int32_t *replicas)
 {
     if (!h || !replicas) return fail(KAO_E_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -471,8 +502,7 @@ static int eval_on_device(kao_handle *h, const uint32_t *d_bits, const uint8_t *
     return KAO_OK;
 }
 
-extern "C" int kao_get_base(kao_handle *h, int32_t *replicas, int64_t *violation, int64_t *objective,
-                            int32_t *moves)
+static int get_base_impl(kao_handle *h, int32_t *replicas, int64_t *violation, int64_t *objective, int32_t *moves)
 {
     if (!h) return fail(KAO_E_ARG, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -497,32 +527,32 @@ extern "C" int kao_get_base(kao_handle *h, int32_t *replicas, int64_t *violation
     return KAO_OK;
 }
 
-static bool check_round_args(uint32_t round_size)
-{
-    return round_size >= 2 && round_size <= KAO_MAX_ROUND_SIZE;
-}
+static bool check_round_args(uint32_t round_size) { return round_size >= 2 && round_size <= KAO_MAX_ROUND_SIZE; }
 
-extern "C" int kao_round_launch(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
-                                uint32_t idx_lo, uint32_t idx_hi, uint64_t *d_key, void *stream)
+static int reserve_keys(kao_handle *h, uint32_t rounds)
 {
-    if (!h || !d_key) return fail(KAO_E_ARG, "null argument");
-    if (!check_round_args(round_size) || idx_lo > idx_hi || idx_hi > round_size)
-        return fail(KAO_E_ARG, "bad round_size / index range");
-    CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(launch_round(h, seed, round, round_size, idx_lo, idx_hi,
-                          reinterpret_cast<unsigned long long *>(d_key), nullptr, (cudaStream_t)stream));
+    if (h->keys_cap < rounds || !h->d_keys) {
+        h->d_keys = nullptr;                   // the old buffer stays owned by the handle until destroy
+        CUDA_TRY(dalloc(h, &h->d_keys, (size_t)(rounds > 0 ? rounds : 1) * 8));
+        h->keys_cap = rounds;
+    }
+    if (rounds) {
+        fill_u64_kernel<<<64, 256>>>(h->d_keys, kKeyNone, (size_t)rounds);
+        CUDA_TRY(cudaGetLastError());
+    }
     return KAO_OK;
 }
 
-extern "C" int kao_round_apply(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
-                               const uint64_t *d_key, void *stream)
+static P2P solo_p2p(kao_handle *h, uint32_t idx_lo, uint32_t idx_hi)
 {
-    if (!h || !d_key) return fail(KAO_E_ARG, "null argument");
-    if (!check_round_args(round_size)) return fail(KAO_E_ARG, "bad round_size");
-    CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(launch_apply(h, seed, round, round_size, reinterpret_cast<const unsigned long long *>(d_key), 0,
-                          (cudaStream_t)stream));
-    return KAO_OK;
+    P2P pp{};
+    pp.rank = 0; pp.world = 1; pp.idx_lo = idx_lo; pp.idx_hi = idx_hi;
+    pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
+    pp.patience = h->patience; pp.rounds_run = h->d_bar + 3;
+    pp.best_in = kKeyNone; pp.stall_in = 0;
+    pp.carry = reinterpret_cast<unsigned long long *>(h->d_bar + 4);
+    pp.timeout_ns = wait_budget_ns();
+    return pp;
 }
 
 static int search_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
@@ -531,27 +561,18 @@ static int search_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint3
     if (!h) return fail(KAO_E_ARG, "null handle");
     if (delta && h->hm.W > 2) return fail(KAO_E_ARG, "delta evaluation supports rows of up to 64 broker slots");
     if (!check_round_args(round_size)) return fail(KAO_E_ARG, "round_size must be 2..2^24");
+    if (rounds > KAO_MAX_ROUNDS) return fail(KAO_E_ARG, "rounds must not exceed KAO_MAX_ROUNDS (2^20) per call");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (h->keys_cap < rounds) {
-        h->d_keys = nullptr;                   // the old buffer stays owned by the handle until destroy
-        CUDA_TRY(dalloc(h, &h->d_keys, (size_t)(rounds > 0 ? rounds : 1) * 8));
-        h->keys_cap = rounds;
-    }
-    if (rounds) {
-        std::vector<unsigned long long> none(rounds, kKeyNone);
-        CUDA_TRY(cudaMemcpy(h->d_keys, none.data(), (size_t)rounds * 8, cudaMemcpyHostToDevice));
-    }
-    if (!h->d_bar) CUDA_TRY(dalloc(h, &h->d_bar, 16));
-    CUDA_TRY(cudaMemsetAsync(h->d_bar, 0, 16, 0));
+    h->last_rounds = 0;
+    int rc = reserve_keys(h, rounds);
+    if (rc != KAO_OK) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_bar, 0, kBarBytes, 0));
     CUDA_TRY(cudaEventRecord(h->ev0, 0));
     if (rounds) {
         // all rounds in one cooperative launch; the HBM base is kept current by CTA 0, the displaced
         // lists in HBM are rebuilt once at the end for the per-round entry points
-        P2P pp{};
-        pp.rank = 0; pp.world = 1; pp.idx_lo = 0; pp.idx_hi = round_size;
-        pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
-        pp.patience = h->patience; pp.rounds_run = h->d_bar + 3;
-        CUDA_TRY(launch_persistent(h, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0, pp, nullptr}, delta));
+        CUDA_TRY(launch_persistent(h, PersistArgs{seed, first_round, rounds, round_size, h->d_keys, h->d_bar, 0,
+                                                  solo_p2p(h, 0, round_size), nullptr}, delta));
         CUDA_TRY(launch_apply(h, seed, first_round, round_size, h->d_keys, /*regen_only=*/1, 0));
     }
     CUDA_TRY(cudaEventRecord(h->ev1, 0));
@@ -561,7 +582,6 @@ static int search_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint3
         CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         *device_ms = ms;
     }
-    h->last_rounds = 0;
     if (rounds) {
         unsigned int st[4] = {0, 0, 0, 0};
         CUDA_TRY(cudaMemcpy(st, h->d_bar, 16, cudaMemcpyDeviceToHost));
@@ -573,110 +593,70 @@ static int search_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint3
     return KAO_OK;
 }
 
-extern "C" int kao_set_evaluator(kao_handle *h, int32_t evaluator)
+static bool schedule_exists(int sync, int pop, int threads)
 {
-    if (!h) return fail(KAO_E_ARG, "null handle");
-    if (evaluator != KAO_EVAL_ROW_MAJOR && evaluator != KAO_EVAL_COLUMN_MAJOR) return fail(KAO_E_ARG, "unknown evaluator");
-    if (evaluator == KAO_EVAL_COLUMN_MAJOR && !h->trans_ok)
-        return fail(KAO_E_ARG, "column-major evaluator: needs rows of up to 64 slots, racks of up to 8 brokers, at most one "
-                               "replica per rack (C7 0..1), three objective mask planes, and its planes in shared memory");
-    h->evaluator = evaluator;
-    return KAO_OK;
-}
-
-static bool schedule_exists(int sync, int compress, int threads, int unroll, int roll, int fuse)
-{
-#define KAO_HAS_TUNE(S, C, T, U, RL, F) if (sync == S && compress == C && threads == T && unroll == U && roll == RL && fuse == F) return true;
-    KAO_FOR_TUNE_ALL(KAO_HAS_TUNE)
-#undef KAO_HAS_TUNE
+#define KAO_HAS_T(S, POP, T) if (sync == S && pop == POP && threads == T) return true;
+    KAO_FOR_SCHEDULES(KAO_HAS_T)
+#undef KAO_HAS_T
     return false;
 }
 
-extern "C" int kao_set_schedule(kao_handle *h, int32_t sync, int32_t compress, int32_t threads, int32_t unroll, int32_t roll,
-                                int32_t fuse)
-{
-    if (!h) return fail(KAO_E_ARG, "null handle");
-    if (!schedule_exists(sync, compress, threads, unroll, roll, fuse))
-        return fail(KAO_E_ARG, "no such schedule: sync 0..4, compress 0..2, (threads, unroll) one of (768,1) (512,1) (512,2); "
-                               "roll 1 only with sync 1 / 3 and compress 1 / 2; fuse 1 only with compress 1 / 2, unroll 1, roll 0");
-    if (!(h->trans_ok && h->hm.W == 2 && h->hm.Ppad == 1024) &&
-        !(sync == 0 && compress == 1 && threads == KAO_THREADS && unroll == 1 && roll == 0 && fuse == 0))
-        return fail(KAO_E_ARG, "schedules other than the default are built for two-word rows with 769..1024 partitions");
-    h->sch_sync = sync; h->sch_compress = compress; h->sch_threads = threads; h->sch_unroll = unroll; h->sch_roll = roll;
-    h->sch_fuse = fuse;
-    return KAO_OK;
-}
-
-extern "C" int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement)
-{
-    if (!h) return fail(KAO_E_ARG, "null handle");
-    h->patience = rounds_without_improvement;
-    return KAO_OK;
-}
-extern "C" int kao_last_rounds(kao_handle *h, uint32_t *rounds_run)
-{
-    if (!h || !rounds_run) return fail(KAO_E_ARG, "null argument");
-    *rounds_run = h->last_rounds;
-    return KAO_OK;
-}
-
-extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
-                          uint32_t round_size, uint64_t *round_keys, double *device_ms)
-{
-    return search_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, false);
-}
-
-// Same search, same keys, same trajectory — but every candidate is scored by DELTA evaluation
-// (base totals + its <= 3 patched rows, one thread per candidate) instead of a full evaluation.
-extern "C" int kao_search_delta(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
-                                uint32_t round_size, uint64_t *round_keys, double *device_ms)
-{
-    return search_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, true);
-}
-
-extern "C" int kao_candidate_keys_delta(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
-                                        uint32_t idx_begin, uint32_t count, uint64_t *keys)
+static int candidate_keys_impl(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                               uint32_t idx_begin, uint32_t count, uint64_t *keys, bool delta)
 {
     if (!h || !keys) return fail(KAO_E_ARG, "null argument");
     if (!check_round_args(round_size) || idx_begin > round_size || count > round_size - idx_begin)
         return fail(KAO_E_ARG, "bad index range");
-    if (h->hm.W > 2) return fail(KAO_E_ARG, "delta evaluation supports rows of up to 64 broker slots");
+    if (delta && h->hm.W > 2) return fail(KAO_E_ARG, "delta evaluation supports rows of up to 64 broker slots");
     if (count == 0) return KAO_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    unsigned long long *d_all = nullptr;
-    CUDA_TRY(cudaMalloc(&d_all, (size_t)count * 8));
-    if (!h->d_bar) CUDA_TRY(dalloc(h, &h->d_bar, 16));
-    CUDA_TRY(cudaMemset(h->d_bar, 0, 16));
-    P2P pp{};
-    pp.rank = 0; pp.world = 1; pp.idx_lo = idx_begin; pp.idx_hi = idx_begin + count;
-    pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
-    cudaError_t e = dispatch(h, LaunchPersistent<true>{}, PersistArgs{seed, round, 1, round_size, h->d_key, h->d_bar, 0, pp, d_all});
-    if (e == cudaSuccess) e = cudaMemcpy(keys, d_all, (size_t)count * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_all);
-    CUDA_TRY(e);
+    DevTmp<unsigned long long> all;
+    CUDA_TRY(all.alloc(count));
+    { const unsigned long long none = kKeyNone; CUDA_TRY(cudaMemcpy(h->d_key, &none, 8, cudaMemcpyHostToDevice)); }
+    if (delta || h->evaluator == KAO_EVAL_COLUMN_MAJOR) {
+        // these evaluators live in the persistent kernel only: one round, key dump, base untouched
+        CUDA_TRY(cudaMemset(h->d_bar, 0, kBarBytes));
+        P2P pp = solo_p2p(h, idx_begin, idx_begin + count);
+        pp.patience = 0;
+        CUDA_TRY(launch_persistent(h, PersistArgs{seed, round, 1, round_size, h->d_key, h->d_bar, 0, pp, all.p}, delta));
+    } else {
+        CUDA_TRY(launch_round(h, seed, round, round_size, idx_begin, idx_begin + count, h->d_key, all.p, 0));
+    }
+    CUDA_TRY(cudaMemcpy(keys, all.p, (size_t)count * 8, cudaMemcpyDeviceToHost));
     return KAO_OK;
 }
 
-// ---- cross-GPU sharded search: the 8-byte min of every round travels through peer-mapped mailboxes
-extern "C" int kao_p2p_export(kao_handle *h, uint8_t *handle_out)
+// ---- cross-GPU sharded search: the 8-byte minimum of every round travels through peer-writable mailboxes
+static int ensure_mailbox(kao_handle *h)
+{
+    if (h->d_mail) return KAO_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMalloc(&h->d_mail, sizeof(Mailbox)));
+    CUDA_TRY(cudaMemset(h->d_mail, 0xFF, sizeof(Mailbox)));        // kMailEmpty everywhere
+    CUDA_TRY(cudaDeviceSynchronize());
+    return KAO_OK;
+}
+static int publish_mailboxes(kao_handle *h, int rank, int world)
+{
+    if (!h->d_mailptrs) CUDA_TRY(dalloc(h, &h->d_mailptrs, sizeof(Mailbox *) * kMaxPeers));
+    CUDA_TRY(cudaMemcpy(h->d_mailptrs, h->peer_mail, sizeof(Mailbox *) * kMaxPeers, cudaMemcpyHostToDevice));
+    h->p2p_rank = rank; h->p2p_world = world; h->p2p_calls = 0;
+    return KAO_OK;
+}
+
+static int p2p_export_impl(kao_handle *h, uint8_t *handle_out)
 {
     if (!h || !handle_out) return fail(KAO_E_ARG, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == KAO_IPC_HANDLE_BYTES, "ipc handle size");
-    CUDA_TRY(cudaSetDevice(h->device));
-    if (!h->d_mail) {
-        CUDA_TRY(cudaMalloc(&h->d_mail, sizeof(Mailbox)));
-        fill_u64_kernel<<<64, 256>>>(&h->d_mail->keys[0][0], kKeyNone, 2 * (size_t)kMailRounds);
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemset(&h->d_mail->arrive[0][0], 0, sizeof(h->d_mail->arrive)));
-        CUDA_TRY(cudaDeviceSynchronize());
-    }
+    const int rc = ensure_mailbox(h);
+    if (rc != KAO_OK) return rc;
     cudaIpcMemHandle_t ipc;
     CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->d_mail));
     std::memcpy(handle_out, &ipc, sizeof ipc);
     return KAO_OK;
 }
 
-extern "C" int kao_p2p_connect(kao_handle *h, int32_t rank, int32_t world, const uint8_t *handles)
+static int p2p_connect_impl(kao_handle *h, int32_t rank, int32_t world, const uint8_t *handles)
 {
     if (!h || !handles) return fail(KAO_E_ARG, "null argument");
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(KAO_E_ARG, "bad rank / world");
@@ -691,10 +671,7 @@ extern "C" int kao_p2p_connect(kao_handle *h, int32_t rank, int32_t world, const
         h->peer_mail[r] = static_cast<Mailbox *>(p);
         h->peer_opened[r] = true;
     }
-    if (!h->d_mailptrs) CUDA_TRY(dalloc(h, &h->d_mailptrs, sizeof(Mailbox *) * kMaxPeers));
-    CUDA_TRY(cudaMemcpy(h->d_mailptrs, h->peer_mail, sizeof(Mailbox *) * kMaxPeers, cudaMemcpyHostToDevice));
-    h->p2p_rank = rank; h->p2p_world = world; h->p2p_calls = 0;
-    return KAO_OK;
+    return publish_mailboxes(h, rank, world);
 }
 
 static int sharded_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
@@ -703,23 +680,23 @@ static int sharded_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint
     if (!h) return fail(KAO_E_ARG, "null handle");
     if (delta && h->hm.W > 2) return fail(KAO_E_ARG, "delta evaluation supports rows of up to 64 broker slots");
     if (!check_round_args(round_size)) return fail(KAO_E_ARG, "round_size must be 2..2^24");
+    if (rounds > KAO_MAX_ROUNDS) return fail(KAO_E_ARG, "rounds must not exceed KAO_MAX_ROUNDS (2^20) per call");
     if (h->p2p_world < 2 || !h->peer_mail[h->p2p_world - 1]) return fail(KAO_E_STATE, "kao_p2p_connect first");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (h->keys_cap < rounds) {
-        h->d_keys = nullptr;
-        CUDA_TRY(dalloc(h, &h->d_keys, (size_t)(rounds > 0 ? rounds : 1) * 8));
-        h->keys_cap = rounds;
-    }
+    h->last_rounds = 0;
+    int rc = reserve_keys(h, rounds);
+    if (rc != KAO_OK) return rc;
     if (h->lkeys_cap < kMailRounds) {
         CUDA_TRY(dalloc(h, &h->d_lkeys, (size_t)kMailRounds * 8));
         h->lkeys_cap = kMailRounds;
     }
-    if (!h->d_bar) CUDA_TRY(dalloc(h, &h->d_bar, 16));
     const int world = h->p2p_world, rank = h->p2p_rank;
     // contiguous slice of every round for this rank (same split on every rank)
     const uint32_t base = round_size / world, extra = round_size % world;
     const uint32_t lo = rank * base + ((uint32_t)rank < extra ? rank : extra);
     const uint32_t hi = lo + base + ((uint32_t)rank < extra ? 1 : 0);
+    unsigned long long best = kKeyNone;                             // early-stop state, carried from launch to launch
+    uint32_t stall = 0;
     CUDA_TRY(cudaEventRecord(h->ev0, 0));
     for (uint32_t done = 0; done < rounds; done += kMailRounds) {
         const uint32_t n = rounds - done < kMailRounds ? rounds - done : kMailRounds;
@@ -727,22 +704,23 @@ static int sharded_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint
         ++h->p2p_calls;
         // the OTHER bank is reset now: no peer can reach the next launch before this rank has taken
         // part in every round of this one (docs/MODEL.md §7), so the reset cannot race with a writer
-        fill_u64_kernel<<<32, 256>>>(&h->d_mail->keys[bank ^ 1][0], kKeyNone, (size_t)kMailRounds);
-        CUDA_TRY(cudaMemsetAsync(&h->d_mail->arrive[bank ^ 1][0], 0, sizeof(unsigned int) * kMailRounds, 0));
+        CUDA_TRY(cudaMemsetAsync(&h->d_mail->slot[bank ^ 1][0][0], 0xFF, sizeof(h->d_mail->slot[0]), 0));
         fill_u64_kernel<<<32, 256>>>(h->d_lkeys, kKeyNone, (size_t)n);
-        CUDA_TRY(cudaMemsetAsync(h->d_bar, 0, 16, 0));
-        h->launches += 2;
-        P2P pp{};
-        pp.rank = rank; pp.world = world; pp.bank = bank; pp.idx_lo = lo; pp.idx_hi = hi;
+        CUDA_TRY(cudaMemsetAsync(h->d_bar, 0, kBarBytes, 0));
+        h->launches += 1;
+        P2P pp = solo_p2p(h, lo, hi);
+        pp.rank = rank; pp.world = world; pp.bank = bank;
         pp.mail = h->d_mailptrs;
-        pp.lkeys = h->d_lkeys; pp.release = h->d_bar + 1; pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
-        pp.patience = h->patience; pp.rounds_run = h->d_bar + 3;
+        pp.lkeys = h->d_lkeys; pp.release = h->d_bar + 1;
+        pp.best_in = best; pp.stall_in = stall;
         const PersistArgs pa{seed, first_round + done, n, round_size, h->d_keys + done, h->d_bar, 0, pp, nullptr};
         CUDA_TRY(launch_persistent(h, pa, delta));
-        unsigned int st[4] = {0, 0, 0, 0};
-        CUDA_TRY(cudaMemcpy(st, h->d_bar, 16, cudaMemcpyDeviceToHost));
+        unsigned int st[8] = {};
+        CUDA_TRY(cudaMemcpy(st, h->d_bar, kBarBytes, cudaMemcpyDeviceToHost));
         if (st[2]) return fail(KAO_E_CUDA, "sharded search timed out waiting for a peer GPU");
         h->last_rounds = done + st[3];
+        std::memcpy(&best, st + 4, 8);
+        { unsigned long long s64; std::memcpy(&s64, st + 6, 8); stall = (uint32_t)s64; }
         if (st[3] < n) break;                                   // early stop (every rank stops at the same round)
     }
     if (rounds) CUDA_TRY(launch_apply(h, seed, first_round, round_size, h->d_keys, /*regen_only=*/1, 0));
@@ -758,80 +736,338 @@ static int sharded_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint
     return KAO_OK;
 }
 
-extern "C" int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
-                                  uint32_t round_size, uint64_t *round_keys, double *device_ms)
+static int profile_rounds_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                               uint32_t round_size, double *search_ms, double *apply_ms)
 {
-    return sharded_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, false);
-}
-extern "C" int kao_search_sharded_delta(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
-                                        uint32_t round_size, uint64_t *round_keys, double *device_ms)
-{
-    return sharded_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, true);
-}
-
-extern "C" int kao_profile_rounds(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
-                                  uint32_t round_size, double *search_ms, double *apply_ms)
-{
-    if (!h || !rounds) return fail(KAO_E_ARG, "bad argument");
+    if (!h || !rounds || rounds > 4096) return fail(KAO_E_ARG, "bad argument (1..4096 rounds)");
     if (!check_round_args(round_size)) return fail(KAO_E_ARG, "bad round_size");
     CUDA_TRY(cudaSetDevice(h->device));
-    std::vector<cudaEvent_t> ev(3 * (size_t)rounds);
-    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
-    unsigned long long *d_k = nullptr;
-    CUDA_TRY(cudaMalloc(&d_k, (size_t)rounds * 8));
-    std::vector<unsigned long long> none(rounds, kKeyNone);
-    CUDA_TRY(cudaMemcpy(d_k, none.data(), (size_t)rounds * 8, cudaMemcpyHostToDevice));
+    struct Events {
+        std::vector<cudaEvent_t> ev;
+        ~Events() { for (auto &e : ev) if (e) cudaEventDestroy(e); }
+    } evs;
+    evs.ev.assign(3 * (size_t)rounds, nullptr);
+    for (auto &e : evs.ev) CUDA_TRY(cudaEventCreate(&e));
+    DevTmp<unsigned long long> k;
+    CUDA_TRY(k.alloc(rounds));
+    fill_u64_kernel<<<32, 256>>>(k.p, kKeyNone, (size_t)rounds);
     for (uint32_t t = 0; t < rounds; ++t) {
-        CUDA_TRY(cudaEventRecord(ev[3 * t], 0));
-        CUDA_TRY(launch_round(h, seed, first_round + t, round_size, 0, round_size, d_k + t, nullptr, 0));
-        CUDA_TRY(cudaEventRecord(ev[3 * t + 1], 0));
-        CUDA_TRY(launch_apply(h, seed, first_round + t, round_size, d_k + t, 0, 0));
-        CUDA_TRY(cudaEventRecord(ev[3 * t + 2], 0));
+        CUDA_TRY(cudaEventRecord(evs.ev[3 * t], 0));
+        CUDA_TRY(launch_round(h, seed, first_round + t, round_size, 0, round_size, k.p + t, nullptr, 0));
+        CUDA_TRY(cudaEventRecord(evs.ev[3 * t + 1], 0));
+        CUDA_TRY(launch_apply(h, seed, first_round + t, round_size, k.p + t, 0, 0));
+        CUDA_TRY(cudaEventRecord(evs.ev[3 * t + 2], 0));
     }
     CUDA_TRY(cudaDeviceSynchronize());
     double s_ms = 0, a_ms = 0;
     for (uint32_t t = 0; t < rounds; ++t) {
         float a = 0, b = 0;
-        CUDA_TRY(cudaEventElapsedTime(&a, ev[3 * t], ev[3 * t + 1]));
-        CUDA_TRY(cudaEventElapsedTime(&b, ev[3 * t + 1], ev[3 * t + 2]));
+        CUDA_TRY(cudaEventElapsedTime(&a, evs.ev[3 * t], evs.ev[3 * t + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&b, evs.ev[3 * t + 1], evs.ev[3 * t + 2]));
         s_ms += a; a_ms += b;
     }
-    for (auto &e : ev) cudaEventDestroy(e);
-    cudaFree(d_k);
     if (search_ms) *search_ms = s_ms;
     if (apply_ms) *apply_ms = a_ms;
     return KAO_OK;
 }
 
-extern "C" int kao_candidate_keys(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
-                                  uint32_t idx_begin, uint32_t count, uint64_t *keys)
+static int eval_impl(const kao_problem *pb, int32_t device, const int32_t *replicas, int32_t n,
+                     int64_t *violation, int64_t *objective)
 {
-    if (!h || !keys) return fail(KAO_E_ARG, "null argument");
-    if (!check_round_args(round_size) || idx_begin > round_size || count > round_size - idx_begin)
-        return fail(KAO_E_ARG, "bad index range");
-    if (count == 0) return KAO_OK;
-    CUDA_TRY(cudaSetDevice(h->device));
-    unsigned long long *d_all = nullptr;
-    CUDA_TRY(cudaMalloc(&d_all, (size_t)count * 8));
-    { const unsigned long long none = kKeyNone; CUDA_TRY(cudaMemcpy(h->d_key, &none, 8, cudaMemcpyHostToDevice)); }
-    cudaError_t e;
-    if (h->evaluator == KAO_EVAL_COLUMN_MAJOR) {
-        // the column-major evaluator lives in the persistent kernel only: one round, key dump, base untouched
-        e = h->d_bar ? cudaSuccess : dalloc(h, &h->d_bar, 16);
-        if (e == cudaSuccess) e = cudaMemset(h->d_bar, 0, 16);
-        P2P pp{};
-        pp.rank = 0; pp.world = 1; pp.idx_lo = idx_begin; pp.idx_hi = idx_begin + count;
-        pp.abort = reinterpret_cast<int *>(h->d_bar + 2);
-        if (e == cudaSuccess) e = launch_persistent(h, PersistArgs{seed, round, 1, round_size, h->d_key, h->d_bar, 0, pp, d_all}, false);
-    } else {
-        e = launch_round(h, seed, round, round_size, idx_begin, idx_begin + count, h->d_key, d_all, 0);
+    if (!pb || !replicas || n < 0 || !violation || !objective) return fail(KAO_E_ARG, "bad argument");
+    kao_handle *h = nullptr;
+    int rc = create_handle(pb, device, &h);
+    if (rc != KAO_OK) return rc;
+    struct Closer { kao_handle *h; ~Closer() { const std::string keep = g_err; destroy_impl(h); g_err = keep; } } closer{h};
+    const HostModel &m = h->hm;
+    const size_t nb = (size_t)m.W * m.Ppad, nl = (size_t)m.Ppad;
+    if (n == 0) return KAO_OK;
+    std::vector<uint32_t> bits(nb * n), one;
+    std::vector<uint8_t> lead(nl * n), onel;
+    for (int i = 0; i < n; ++i) {
+        encode_replicas(m, replicas + (size_t)i * m.P * m.RF, one, onel);
+        std::memcpy(bits.data() + nb * i, one.data(), nb * 4);
+        std::memcpy(lead.data() + nl * i, onel.data(), nl);
     }
-    if (e == cudaSuccess) e = cudaMemcpy(keys, d_all, (size_t)count * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_all);
-    CUDA_TRY(e);
+    DevTmp<uint32_t> d_b; DevTmp<uint8_t> d_l; DevTmp<long long> d_v;
+    CUDA_TRY(d_b.alloc(bits.size()));
+    CUDA_TRY(d_l.alloc(lead.size()));
+    CUDA_TRY(d_v.alloc((size_t)n * 2));
+    CUDA_TRY(cudaMemcpy(d_b.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_l.p, lead.data(), lead.size(), cudaMemcpyHostToDevice));
+    rc = eval_on_device(h, d_b.p, d_l.p, n, d_v.p, d_v.p + n);
+    if (rc != KAO_OK) return rc;
+    static_assert(sizeof(long long) == sizeof(int64_t), "abi");
+    CUDA_TRY(cudaMemcpy(violation, d_v.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(objective, d_v.p + n, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return KAO_OK;
 }
 
+// ---- kao_solve: one GPU, or the rounds sharded over several GPUs of this process
+static int pick_devices(const kao_options *opt, std::vector<int> &devs)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(KAO_E_CUDA, "no CUDA device: libkao has no CPU path");
+    devs.clear();
+    if (opt->device_mask) {
+        for (int i = 0; i < 32; ++i)
+            if (opt->device_mask >> i & 1u) devs.push_back(i);
+        if (opt->n_gpus > 1 && opt->n_gpus != (int)devs.size()) return fail(KAO_E_ARG, "n_gpus does not match device_mask");
+    } else {
+        const int n = opt->n_gpus > 1 ? opt->n_gpus : 1;
+        for (int i = 0; i < n; ++i) devs.push_back(opt->device + i);
+    }
+    if (devs.empty() || (int)devs.size() > KAO_MAX_GPUS) return fail(KAO_E_ARG, "1..KAO_MAX_GPUS devices");
+    for (int d : devs)
+        if (d < 0 || d >= ndev) return fail(KAO_E_ARG, "bad device ordinal (n_gpus / device_mask exceed the visible devices)");
+    return KAO_OK;
+}
+
+// handles of one multi-GPU solve; destroyed on every path
+struct Gang {
+    std::vector<kao_handle *> h;
+    ~Gang() { const std::string keep = g_err; for (auto *x : h) destroy_impl(x); g_err = keep; }
+};
+
+static int connect_gang(Gang &g)
+{
+    const int world = (int)g.h.size();
+    for (int i = 0; i < world; ++i) {
+        CUDA_TRY(cudaSetDevice(g.h[i]->device));
+        for (int j = 0; j < world; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, g.h[i]->device, g.h[j]->device));
+            if (!can) return fail(KAO_E_CUDA, "the selected GPUs cannot access each other's memory (no peer access)");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(g.h[j]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(KAO_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        }
+        const int rc = ensure_mailbox(g.h[i]);
+        if (rc != KAO_OK) return rc;
+    }
+    for (int i = 0; i < world; ++i) {
+        CUDA_TRY(cudaSetDevice(g.h[i]->device));
+        for (int j = 0; j < world; ++j) g.h[i]->peer_mail[j] = g.h[j]->d_mail;      // unified addressing: a peer's pointer is valid here
+        const int rc = publish_mailboxes(g.h[i], i, world);
+        if (rc != KAO_OK) return rc;
+    }
+    return KAO_OK;
+}
+
+static int solve_impl(const kao_problem *pb, const kao_options *opt, kao_result *res)
+{
+    if (!pb || !opt || !res || !res->replicas) return fail(KAO_E_ARG, "null argument");
+    if (opt->rounds > KAO_MAX_ROUNDS) return fail(KAO_E_ARG, "rounds must not exceed KAO_MAX_ROUNDS (2^20)");
+    if (!check_round_args(opt->round_size)) return fail(KAO_E_ARG, "round_size must be 2..2^24");
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<int> devs;
+    int rc = pick_devices(opt, devs);
+    if (rc != KAO_OK) return rc;
+    const int world = (int)devs.size();
+    Gang g;
+    for (int d : devs) {
+        kao_handle *h = nullptr;
+        rc = create_handle(pb, d, &h);
+        if (rc != KAO_OK) return rc;
+        g.h.push_back(h);
+    }
+    if (world > 1 && (rc = connect_gang(g)) != KAO_OK) return rc;
+    // independent restarts (flags & 0xFF, 0 and 1 both mean a single search): each restarts from the
+    // initial base with its own seed; the best final assignment wins (violation, then objective)
+    const uint32_t restarts = (opt->flags & 0xFFu) ? (opt->flags & 0xFFu) : 1u;
+    const bool delta = (opt->flags & KAO_FLAG_DELTA) != 0;
+    for (auto *h : g.h) {
+        h->patience = opt->flags >> 16;                         // KAO_FLAG_PATIENCE(n)
+        // the column-major evaluator is the default where the layout allows it; the flag selects the other full evaluator (same keys)
+        if (opt->flags & KAO_FLAG_ROW_MAJOR) h->evaluator = KAO_EVAL_ROW_MAJOR;
+    }
+    kao_handle *h0 = g.h[0];
+    uint32_t rounds_run = 0;
+    std::vector<uint64_t> keys(opt->rounds ? opt->rounds : 1, kKeyNone);
+    std::vector<int32_t> reps((size_t)pb->P * pb->RF);
+    double dev_ms_total = 0;
+    bool have = false;
+    for (uint32_t r = 0; r < restarts; ++r) {
+        const uint64_t seed = opt->seed + 0x9E3779B97F4A7C15ull * r;
+        double dev_ms = 0;
+        if (world == 1) {
+            if (r && (rc = reset_impl(h0)) != KAO_OK) return rc;
+            rc = search_impl(h0, seed, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms, delta);
+            if (rc != KAO_OK) return rc;
+        } else {
+            // one host thread per GPU; each runs its slice of every round, the kernels trade the per-round minimum
+            std::vector<int> rcs(world, KAO_OK);
+            std::vector<std::string> errs(world);
+            std::vector<double> ms(world, 0.0);
+            std::vector<std::thread> th;
+            for (int i = 0; i < world; ++i)
+                th.emplace_back([&, i] {
+                    rcs[i] = guarded([&] {
+                        int c = r ? reset_impl(g.h[i]) : KAO_OK;
+                        if (c == KAO_OK) c = sharded_impl(g.h[i], seed, 0, opt->rounds, opt->round_size, i == 0 ? keys.data() : nullptr, &ms[i], delta);
+                        return c;
+                    });
+                    if (rcs[i] != KAO_OK) errs[i] = g_err;      // g_err is thread-local
+                });
+            for (auto &t : th) t.join();
+            for (int i = 0; i < world; ++i) {
+                if (rcs[i] != KAO_OK) return fail(rcs[i], "GPU " + std::to_string(devs[i]) + ": " + errs[i]);
+                dev_ms = ms[i] > dev_ms ? ms[i] : dev_ms;
+            }
+        }
+        int64_t viol = 0, obj = 0;
+        int32_t moves = 0;
+        rc = get_base_impl(h0, reps.data(), &viol, &obj, &moves);
+        if (rc != KAO_OK) return rc;
+        dev_ms_total += dev_ms;
+        rounds_run += h0->last_rounds;
+        if (!have || viol < res->violation || (viol == res->violation && obj > res->objective)) {
+            std::memcpy(res->replicas, reps.data(), reps.size() * 4);
+            res->violation = viol; res->objective = obj; res->moves = moves;
+            res->key = h0->last_rounds ? keys[h0->last_rounds - 1] : kKeyNone;
+            have = true;
+        }
+    }
+    res->feasible = res->violation == 0;
+    res->n_candidates = (uint64_t)rounds_run * opt->round_size;
+    res->rounds_run = rounds_run;
+    res->restarts = restarts;
+    res->device_ms = dev_ms_total;
+    res->objective_bound = objective_upper_bound(h0->hm, *pb);
+    res->optimal = res->feasible && res->objective == res->objective_bound;
+    res->key_obj_bits = h0->hm.key_obj_bits;
+    res->n_gpus = world;
+    res->reserved = 0;
+    res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (!res->feasible) { g_err = "no candidate satisfying C1..C7 was found"; return KAO_INFEASIBLE; }
+    return KAO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the C ABI (include/kao.h): thin, guarded entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int kao_version(void) { return KAO_VERSION; }
+extern "C" const char *kao_last_error(void) { return g_err.c_str(); }
+extern "C" int kao_key_obj_bits(const kao_problem *pb)
+{
+    return guarded([&] {
+        if (!pb) return fail(KAO_E_ARG, "null argument");
+        HostModel m;
+        std::string why;
+        if (!build_host_model(*pb, m, why)) return fail(KAO_E_ARG, why);
+        return m.key_obj_bits;
+    });
+}
+extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **out) { return guarded([&] { return create_handle(pb, device, out); }); }
+extern "C" int kao_destroy(kao_handle *h) { return guarded([&] { return destroy_impl(h); }); }
+extern "C" int kao_reset(kao_handle *h) { return guarded([&] { return reset_impl(h); }); }
+extern "C" int kao_set_base(kao_handle *h, const int32_t *replicas) { return guarded([&] { return set_base_impl(h, replicas); }); }
+extern "C" int kao_get_base(kao_handle *h, int32_t *replicas, int64_t *violation, int64_t *objective, int32_t *moves)
+{
+    return guarded([&] { return get_base_impl(h, replicas, violation, objective, moves); });
+}
+extern "C" int kao_round_launch(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                uint32_t idx_lo, uint32_t idx_hi, uint64_t *d_key, void *stream)
+{
+    return guarded([&] {
+        if (!h || !d_key) return fail(KAO_E_ARG, "null argument");
+        if (!check_round_args(round_size) || idx_lo > idx_hi || idx_hi > round_size)
+            return fail(KAO_E_ARG, "bad round_size / index range");
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(launch_round(h, seed, round, round_size, idx_lo, idx_hi,
+                              reinterpret_cast<unsigned long long *>(d_key), nullptr, (cudaStream_t)stream));
+        return KAO_OK;
+    });
+}
+extern "C" int kao_round_apply(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                               const uint64_t *d_key, void *stream)
+{
+    return guarded([&] {
+        if (!h || !d_key) return fail(KAO_E_ARG, "null argument");
+        if (!check_round_args(round_size)) return fail(KAO_E_ARG, "bad round_size");
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(launch_apply(h, seed, round, round_size, reinterpret_cast<const unsigned long long *>(d_key), 0,
+                              (cudaStream_t)stream));
+        return KAO_OK;
+    });
+}
+extern "C" int kao_set_evaluator(kao_handle *h, int32_t evaluator)
+{
+    return guarded([&] {
+        if (!h) return fail(KAO_E_ARG, "null handle");
+        if (evaluator != KAO_EVAL_ROW_MAJOR && evaluator != KAO_EVAL_COLUMN_MAJOR) return fail(KAO_E_ARG, "unknown evaluator");
+        if (evaluator == KAO_EVAL_COLUMN_MAJOR && !h->trans_ok)
+            return fail(KAO_E_ARG, "column-major evaluator: needs rows of up to 64 slots, racks of up to 8 brokers, at most one "
+                                   "replica per rack (C7 0..1), three objective mask planes, and its planes in shared memory");
+        h->evaluator = evaluator;
+        return KAO_OK;
+    });
+}
+extern "C" int kao_set_schedule(kao_handle *h, int32_t sync, int32_t pop, int32_t threads)
+{
+    return guarded([&] {
+        if (!h) return fail(KAO_E_ARG, "null handle");
+        if (!schedule_exists(sync, pop, threads)) return fail(KAO_E_ARG, "no such schedule (kao.h, kao_set_schedule)");
+        h->sch_sync = sync; h->sch_pop = pop; h->sch_threads = threads;
+        return KAO_OK;
+    });
+}
+extern "C" int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    h->patience = rounds_without_improvement;
+    return KAO_OK;
+}
+extern "C" int kao_last_rounds(kao_handle *h, uint32_t *rounds_run)
+{
+    if (!h || !rounds_run) return fail(KAO_E_ARG, "null argument");
+    *rounds_run = h->last_rounds;
+    return KAO_OK;
+}
+extern "C" int kao_search(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                          uint32_t round_size, uint64_t *round_keys, double *device_ms)
+{
+    return guarded([&] { return search_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, false); });
+}
+// Same search, same keys, same trajectory — but every candidate is scored by DELTA evaluation
+// (base totals + its <= 3 patched rows, one thread per candidate) instead of a full evaluation.
+extern "C" int kao_search_delta(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                                uint32_t round_size, uint64_t *round_keys, double *device_ms)
+{
+    return guarded([&] { return search_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, true); });
+}
+extern "C" int kao_candidate_keys(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                  uint32_t idx_begin, uint32_t count, uint64_t *keys)
+{
+    return guarded([&] { return candidate_keys_impl(h, seed, round, round_size, idx_begin, count, keys, false); });
+}
+extern "C" int kao_candidate_keys_delta(kao_handle *h, uint64_t seed, uint32_t round, uint32_t round_size,
+                                        uint32_t idx_begin, uint32_t count, uint64_t *keys)
+{
+    return guarded([&] { return candidate_keys_impl(h, seed, round, round_size, idx_begin, count, keys, true); });
+}
+extern "C" int kao_p2p_export(kao_handle *h, uint8_t *handle_out) { return guarded([&] { return p2p_export_impl(h, handle_out); }); }
+extern "C" int kao_p2p_connect(kao_handle *h, int32_t rank, int32_t world, const uint8_t *handles)
+{
+    return guarded([&] { return p2p_connect_impl(h, rank, world, handles); });
+}
+extern "C" int kao_search_sharded(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                                  uint32_t round_size, uint64_t *round_keys, double *device_ms)
+{
+    return guarded([&] { return sharded_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, false); });
+}
+extern "C" int kao_search_sharded_delta(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                                        uint32_t round_size, uint64_t *round_keys, double *device_ms)
+{
+    return guarded([&] { return sharded_impl(h, seed, first_round, rounds, round_size, round_keys, device_ms, true); });
+}
+extern "C" int kao_profile_rounds(kao_handle *h, uint64_t seed, uint32_t first_round, uint32_t rounds,
+                                  uint32_t round_size, double *search_ms, double *apply_ms)
+{
+    return guarded([&] { return profile_rounds_impl(h, seed, first_round, rounds, round_size, search_ms, apply_ms); });
+}
 extern "C" int kao_stats(kao_handle *h, uint64_t *kernel_launches, int32_t *words_per_row,
                          int32_t *slots, int32_t *dense_weights)
 {
@@ -842,92 +1078,12 @@ extern "C" int kao_stats(kao_handle *h, uint64_t *kernel_launches, int32_t *word
     if (dense_weights) *dense_weights = h->hm.dense ? 1 : 0;
     return KAO_OK;
 }
-
 extern "C" int kao_eval(const kao_problem *pb, int32_t device, const int32_t *replicas, int32_t n,
                         int64_t *violation, int64_t *objective)
 {
-    if (!pb || !replicas || n < 0 || !violation || !objective) return fail(KAO_E_ARG, "bad argument");
-    kao_handle *h = nullptr;
-    int rc = kao_create(pb, device, &h);
-    if (rc != KAO_OK) return rc;
-    const HostModel &m = h->hm;
-    const size_t nb = (size_t)m.W * m.Ppad, nl = (size_t)m.Ppad;
-    std::vector<uint32_t> bits(nb * n), one;
-    std::vector<uint8_t> lead(nl * n), onel;
-    for (int i = 0; i < n; ++i) {
-        encode_replicas(m, replicas + (size_t)i * m.P * m.RF, one, onel);
-        std::memcpy(bits.data() + nb * i, one.data(), nb * 4);
-        std::memcpy(lead.data() + nl * i, onel.data(), nl);
-    }
-    uint32_t *d_b = nullptr; uint8_t *d_l = nullptr; long long *d_v = nullptr;
-    cudaError_t e = cudaSuccess;
-    if (n > 0) {
-        if ((e = cudaMalloc(&d_b, bits.size() * 4)) == cudaSuccess &&
-            (e = cudaMalloc(&d_l, lead.size())) == cudaSuccess &&
-            (e = cudaMalloc(&d_v, (size_t)n * 16)) == cudaSuccess &&
-            (e = cudaMemcpy(d_b, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice)) == cudaSuccess &&
-            (e = cudaMemcpy(d_l, lead.data(), lead.size(), cudaMemcpyHostToDevice)) == cudaSuccess) {
-            rc = eval_on_device(h, d_b, d_l, n, d_v, d_v + n);
-            if (rc == KAO_OK) {
-                static_assert(sizeof(long long) == sizeof(int64_t), "abi");
-                e = cudaMemcpy(violation, d_v, (size_t)n * 8, cudaMemcpyDeviceToHost);
-                if (e == cudaSuccess) e = cudaMemcpy(objective, d_v + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
-            }
-        }
-        cudaFree(d_b); cudaFree(d_l); cudaFree(d_v);
-    }
-    kao_destroy(h);
-    if (e != cudaSuccess) return fail(KAO_E_CUDA, cudaGetErrorString(e));
-    return rc;
+    return guarded([&] { return eval_impl(pb, device, replicas, n, violation, objective); });
 }
-
 extern "C" int kao_solve(const kao_problem *pb, const kao_options *opt, kao_result *res)
 {
-    if (!pb || !opt || !res || !res->replicas) return fail(KAO_E_ARG, "null argument");
-    const auto t0 = std::chrono::steady_clock::now();
-    kao_handle *h = nullptr;
-    int rc = kao_create(pb, opt->device, &h);
-    if (rc != KAO_OK) return rc;
-    // independent restarts (flags & 0xFF, 0 and 1 both mean a single search): each restarts from the
-    // initial base with its own seed; the best final assignment wins (violation, then objective)
-    const uint32_t restarts = (opt->flags & 0xFFu) ? (opt->flags & 0xFFu) : 1u;
-    h->patience = opt->flags >> 16;                             // KAO_FLAG_PATIENCE(n)
-    // a performance hint, not a different result: layouts the column-major evaluator does not cover keep the row-major one
-    if ((opt->flags & KAO_FLAG_COLUMN_MAJOR) && h->trans_ok) h->evaluator = KAO_EVAL_COLUMN_MAJOR;
-    uint32_t rounds_run = 0;
-    std::vector<uint64_t> keys(opt->rounds ? opt->rounds : 1, kKeyNone);
-    std::vector<int32_t> reps((size_t)pb->P * pb->RF);
-    double dev_ms_total = 0;
-    bool have = false;
-    for (uint32_t r = 0; r < restarts && rc == KAO_OK; ++r) {
-        double dev_ms = 0;
-        int64_t viol = 0, obj = 0;
-        int32_t moves = 0;
-        if (r) rc = kao_reset(h);
-        if (rc == KAO_OK)
-            rc = search_impl(h, opt->seed + 0x9E3779B97F4A7C15ull * r, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms,
-                             (opt->flags & KAO_FLAG_DELTA) != 0);
-        if (rc == KAO_OK) rc = kao_get_base(h, reps.data(), &viol, &obj, &moves);
-        if (rc != KAO_OK) break;
-        dev_ms_total += dev_ms;
-        rounds_run += h->last_rounds;
-        if (!have || viol < res->violation || (viol == res->violation && obj > res->objective)) {
-            std::memcpy(res->replicas, reps.data(), reps.size() * 4);
-            res->violation = viol; res->objective = obj; res->moves = moves;
-            res->key = h->last_rounds ? keys[h->last_rounds - 1] : kKeyNone;
-            have = true;
-        }
-    }
-    if (rc == KAO_OK) {
-        res->feasible = res->violation == 0;
-        res->n_candidates = (uint64_t)rounds_run * opt->round_size;
-        res->rounds_run = rounds_run;
-        res->reserved = restarts;
-        res->device_ms = dev_ms_total;
-    }
-    kao_destroy(h);
-    res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (rc != KAO_OK) return rc;
-    if (!res->feasible) { g_err = "no candidate satisfying C1..C7 was found"; return KAO_INFEASIBLE; }
-    return KAO_OK;
+    return guarded([&] { return solve_impl(pb, opt, res); });
 }

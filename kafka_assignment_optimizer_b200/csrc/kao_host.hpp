@@ -29,6 +29,7 @@ struct HostModel {
     int plane_value[6] = {0, 0, 0, 0, 0, 0};
     std::vector<uint32_t> planesT;            // [nplanes][W][Ppad]
     bool hi1 = false;                         // C7 is exactly "at most one replica per rack"
+    int key_obj_bits = 24;                    // width of the cost field of a packed key (docs/MODEL.md 3)
     std::vector<uint32_t> dense_w;            // [P][NS] when dense
     std::vector<uint32_t> homeT;              // [Ppad]
 };
@@ -109,6 +110,10 @@ inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &w
     }
     for (size_t i = 0; i < (size_t)pb.P * pb.B; ++i) maxw = std::max<uint32_t>(maxw, std::max(pb.wF[i], pb.wL[i]));
     if ((uint64_t)pb.P * pb.RF * maxw > 0xFFFFFFull) return bad("objective range exceeds 24 bits");
+    // cost field of the packed key: just wide enough for the largest objective the model can reach, so
+    // that the violation field gets the rest of the 63 bits (15 bits saturate at P = 8000)
+    m.key_obj_bits = 1;
+    while (((uint64_t)pb.P * pb.RF * maxw) >> m.key_obj_bits) ++m.key_obj_bits;
     m.dense = !sparse_ok;
     m.swT.assign((size_t)4 * m.Ppad, 0);
     if (m.dense) {
@@ -132,8 +137,8 @@ inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &w
             for (int p = 0; p < pb.P; ++p)
                 if (m.swT[(size_t)k * m.Ppad + p]) m.nentries = k + 1;
     // mask planes: one per distinct follower weight (applied to the row) and one per distinct
-    // leader bonus wL - wF (applied to the leader one-hot); needs wL >= wF everywhere and at most
-    // six distinct values in total, and only pays off for narrow rows
+    // leader bonus wL - wF (applied to the leader one-hot); needs wL >= wF everywhere, at most two
+    // follower weights and one bonus value, and only pays off for narrow rows
     {
         std::vector<uint32_t> vf, vd;
         bool ok = (m.W <= 2);
@@ -144,11 +149,12 @@ inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &w
             if (l - f && std::find(vd.begin(), vd.end(), l - f) == vd.end()) vd.push_back(l - f);
             if (vf.size() + vd.size() > 6) ok = false;
         }
-        // kernels exist for 3 planes (2 row planes + 1 leader plane) and 6 (4 + 2); empty planes pad
-        if (ok && vf.size() + vd.size() > 0 && vf.size() <= 4 && vd.size() <= 2) {
+        // kernels exist for 3 planes (2 row planes + 1 leader plane); empty planes pad; other weight
+        // tables are scored from packed entries / the dense table
+        if (ok && vf.size() + vd.size() > 0 && vf.size() <= 2 && vd.size() <= 1) {
             std::sort(vf.begin(), vf.end());
             std::sort(vd.begin(), vd.end());
-            m.nplanes = (vf.size() <= 2 && vd.size() <= 1) ? 3 : 6;
+            m.nplanes = 3;
             const int nrow = 2 * m.nplanes / 3;
             m.planesT.assign((size_t)m.nplanes * m.W * m.Ppad, 0);
             for (int c = 0; c < m.nplanes; ++c) {
@@ -276,6 +282,37 @@ inline int count_moves(const HostModel &m, const int32_t *replicas)
             moves += had ? 0 : 1;
         }
     return moves;
+}
+
+// An upper bound on the objective of every feasible assignment: per partition the best choice of a
+// leader plus RF - 1 followers on distinct brokers, with the balance and rack constraints C3..C7
+// dropped.  A search result that reaches it is proven optimal (kao_result.optimal); otherwise the
+// optimum lp_solve would return (README.md:135-136) lies between the two.
+inline int64_t objective_upper_bound(const HostModel &m, const kao_problem &pb)
+{
+    int64_t total = 0;
+    const int nf = m.RF - 1;
+    std::vector<std::pair<uint32_t, int>> top;           // the RF largest follower weights of the row
+    for (int p = 0; p < m.P; ++p) {
+        const uint16_t *wF = pb.wF + (size_t)p * m.B, *wL = pb.wL + (size_t)p * m.B;
+        top.clear();
+        for (int b = 0; b < m.B; ++b) {
+            top.emplace_back(wF[b], b);
+            std::sort(top.begin(), top.end(), [](const auto &x, const auto &y) { return x.first > y.first; });
+            if ((int)top.size() > m.RF) top.pop_back();
+        }
+        int64_t sum_nf = 0, sum_rf = 0;                  // sums of the nf / nf + 1 largest follower weights
+        for (int i = 0; i < (int)top.size(); ++i) { if (i < nf) sum_nf += top[i].first; sum_rf += top[i].first; }
+        int64_t best = 0;
+        for (int b = 0; b < m.B; ++b) {
+            bool in_top = false;
+            for (int i = 0; i < nf && i < (int)top.size(); ++i) in_top |= top[i].second == b;
+            const int64_t followers = in_top ? sum_rf - wF[b] : sum_nf;     // the leader's broker cannot follow too
+            best = std::max(best, (int64_t)wL[b] + followers);
+        }
+        total += best;
+    }
+    return total;
 }
 
 inline void fill_consts(const HostModel &m, Consts &cs)

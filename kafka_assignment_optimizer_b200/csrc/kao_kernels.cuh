@@ -73,8 +73,9 @@ __device__ __forceinline__ void build_oh_plane(uint32_t *s_bits, const uint8_t *
 }
 
 // Column-major evaluator (kao_device_t.cuh): the five transposed planes are gathered once per launch
-// from the staged row-major base and the row-major mask planes in HBM (L2); they take the place of
-// the objective table in the shared-memory plan (5 * W words per partition at off_sw).
+// from the staged row-major base and the row-major objective mask planes; both take the place of the
+// objective table in the shared-memory plan ((5 + 3) * W words per partition at off_sw: the transposed
+// planes, then the row-major mask planes a patched row takes its mask bits from).
 template <int W, int THREADS>
 __device__ __forceinline__ void build_t_planes(uint32_t *T, const uint32_t *s_bits, const uint8_t *s_leader,
                                                const uint32_t *g_planes, int Ppad)
@@ -155,7 +156,7 @@ search_round_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t round, uint
         if (live) {
             int viol, obj;
             eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
-            const unsigned long long key = live ? pack_key(viol, obj, idx) : kKeyNone;
+            const unsigned long long key = live ? pack_key(viol, obj, idx, d.key_obj_bits) : kKeyNone;
             if (all_keys && lane == 0) all_keys[idx - idx_lo] = key;
             best = key < best ? key : best;
         }
@@ -227,14 +228,17 @@ __device__ __forceinline__ void rebuild_lists(const uint32_t *bitsT, const uint8
     __syncthreads();
 }
 
-// Cross-GPU exchange state of the persistent kernel (docs/MODEL.md §7): every rank owns a mailbox
-// in its HBM that all peers map through CUDA IPC; per round the ranks min-reduce their 8-byte keys
-// into every mailbox with NVLink atomics and count arrivals — no host, no NCCL in the loop.
+// Cross-GPU exchange state of the persistent kernel (docs/MODEL.md §7): every rank owns a mailbox in
+// its HBM that all peers can write (mapped through CUDA IPC between processes, or directly with peer
+// access inside one process).  Per round every rank stores its 8-byte key into ITS slot of every
+// mailbox (one NVLink store per peer, all in flight together) and polls its own mailbox until the
+// slots of all ranks are filled — the key is its own flag, no counter, no fence between the two; the
+// minimum of the slots is the round's winner on every rank.  No host, no NCCL in the loop.
 constexpr int kMaxPeers = 8;
 constexpr uint32_t kMailRounds = 8192;          // rounds per launch when sharded
+constexpr unsigned long long kMailEmpty = ~0ull;   // no key has bit 63 set
 struct Mailbox {
-    unsigned long long keys[2][kMailRounds];    // [bank][round]  min of the ranks' keys
-    unsigned int arrive[2][kMailRounds];        // [bank][round]  ranks that have contributed
+    unsigned long long slot[2][kMailRounds][kMaxPeers];   // [bank][round][rank]
 };
 struct P2P {
     int rank, world, bank;
@@ -245,14 +249,40 @@ struct P2P {
     int *abort;                                 // set when a wait times out (a peer died): everybody leaves
     uint32_t patience;                          // > 0: stop after this many rounds without a better key
     unsigned int *rounds_run;                   // CTA 0 reports the number of rounds actually run
+    // early-stop state carried from one launch of a long search to the next (the host passes the values the
+    // previous launch left in `carry`): best (violation, cost) so far, rounds since it improved
+    unsigned long long best_in;
+    uint32_t stall_in;
+    unsigned long long *carry;                  // [2] CTA 0 leaves (best, stall) here
+    unsigned long long timeout_ns;              // budget of every wait (grid barrier, peers)
 };
 
-__device__ __forceinline__ bool spin_until(const unsigned int *p, unsigned int target, int *abort_flag)
+__device__ __forceinline__ unsigned long long global_ns()
 {
-    const long long t0 = clock64();
+#if defined(KAO_HOST_EMU)
+    return 0;
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
+// waits in wall time (the SM clock would make the budget depend on the clock frequency)
+__device__ __forceinline__ bool spin_until(const unsigned int *p, unsigned int target, int *abort_flag, unsigned long long budget_ns)
+{
+    const unsigned long long t0 = global_ns();
     while (*reinterpret_cast<const volatile unsigned int *>(p) < target) {
         if (*reinterpret_cast<volatile int *>(abort_flag)) return false;
-        if (clock64() - t0 > 6000000000ll) { atomicExch(abort_flag, 1); return false; }   // ~3 s
+        if (global_ns() - t0 > budget_ns) { atomicExch(abort_flag, 1); return false; }
+    }
+    return true;
+}
+__device__ __forceinline__ bool spin_filled(const unsigned long long *p, unsigned long long &v, int *abort_flag, unsigned long long budget_ns)
+{
+    const unsigned long long t0 = global_ns();
+    while ((v = *reinterpret_cast<const volatile unsigned long long *>(p)) == kMailEmpty) {
+        if (*reinterpret_cast<volatile int *>(abort_flag)) return false;
+        if (global_ns() - t0 > budget_ns) { atomicExch(abort_flag, 1); return false; }
     }
     return true;
 }
@@ -288,7 +318,9 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     constexpr int kWarps = THREADS / 32;
     constexpr int W = Cfg::W;
     const uint32_t *g_obj = Cfg::kObj > 0 ? d.planesT : d.swT;
-    const uint32_t obj_words = Cfg::kTrans ? 0u : (Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries);
+    const uint32_t obj_words = Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries;
+    // column-major evaluator: the row-major mask planes sit behind the five transposed planes
+    uint32_t *s_obj = Cfg::kTrans ? s_sw + (size_t)kTPlanes * W * d.Ppad : s_sw;
 
     if (tid == 0) mbar_init(s_bar, 1);
     __syncthreads();
@@ -296,13 +328,13 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         const uint32_t nb = (uint32_t)W * d.Ppad * 4, ns = obj_words * d.Ppad * 4, nl = (uint32_t)d.Ppad;
         mbar_expect_tx(s_bar, nb + ns + nl + (uint32_t)sizeof(Consts));
         bulk_g2s(s_bits, d.bitsT, nb, s_bar);
-        if (ns) bulk_g2s(s_sw, g_obj, ns, s_bar);
+        if (ns) bulk_g2s(s_obj, g_obj, ns, s_bar);
         bulk_g2s(s_leader, d.leader, nl, s_bar);
         bulk_g2s(s_cs, d.consts, (uint32_t)sizeof(Consts), s_bar);
     }
     mbar_wait(s_bar, 0);
     if constexpr (has_oh_plane<Cfg>()) build_oh_plane<W, THREADS>(s_bits, s_leader, d.Ppad);
-    if constexpr (Cfg::kTrans) build_t_planes<W, THREADS>(s_sw, s_bits, s_leader, d.planesT, d.Ppad);
+    if constexpr (Cfg::kTrans) build_t_planes<W, THREADS>(s_sw, s_bits, s_leader, s_obj, d.Ppad);
     rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
 
     Gen<W, false, Cfg::kTrans> gen;        // column-major kernels: compact generator code (same candidates)
@@ -317,7 +349,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     if (tid == 0) s_abort = 0;
     // early-stop state lives behind the per-warp minima (s_red is live anyway; a separate pointer would
     // cost a register in the hot loop): [kWarps] stop flag, [kWarps+1] best (violation, cost), [kWarps+2] stall
-    if (tid == 0) { s_red[kWarps] = 0; s_red[kWarps + 1] = kKeyNone; s_red[kWarps + 2] = 0; }
+    if (tid == 0) { s_red[kWarps] = 0; s_red[kWarps + 1] = pp.best_in; s_red[kWarps + 2] = pp.stall_in; }
     for (uint32_t t = 0; t < rounds; ++t) {
         const uint32_t round = first_round + t;
         gen.nD = s_counts[0]; gen.nL = s_counts[1];
@@ -403,7 +435,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 tg.run(seed, round, idx, round_size, ps, rows);
                 int viol, obj;
                 delta_eval<Cfg>(d, s_bits, s_leader, m_obj, s_cs, ps, rows, s_cnt, s_lcnt, s_rc, base_viol, base_obj, viol, obj);
-                const unsigned long long key = pack_key(viol, obj, idx);
+                const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
                 if (all_keys) all_keys[idx - pp.idx_lo] = key;
                 best = key < best ? key : best;
             }
@@ -414,17 +446,6 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             }
             if (all_keys) return;                                   // key dump only: the base stays as it is
         } else {
-        if constexpr (Cfg::kTrans) {
-            if constexpr (Cfg::kSync == 4) {
-                // two half-CTA groups in ANTI-phase: the second group starts each round about half an
-                // interval late, so that on every scheduler three warps generate (latency-bound) while
-                // the other three evaluate (pipe-bound); the groups keep their own barriers after that
-                if ((warp >> 2) & 1) {
-                    const long long t0 = clock64();
-                    while (clock64() - t0 < 6000) {}
-                }
-            }
-        }
         for (uint32_t it = 0; it < iters; ++it) {
             const uint32_t idx = first + warp + it * stride;
             const bool live = idx < pp.idx_hi;
@@ -437,20 +458,18 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 // schedules of the column-major evaluator: who meets before an evaluation (the patched
                 // rows were written by lane 0 of this warp, so a warp-level sync is enough for correctness)
                 if constexpr (Cfg::kSync == 0) __syncthreads();
-                else if constexpr (Cfg::kSync == 1) __syncwarp();
-                else if constexpr (Cfg::kSync == 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(THREADS / 4) : "memory");
-                else asm volatile("bar.sync %0, %1;" ::"r"(1 + ((warp >> 2) & 1)), "r"(THREADS / 2) : "memory");   // 3, 4
+                else __syncwarp();
             } else {
                 __syncthreads();
             }
             if (live) {
                 int viol, obj;
                 if constexpr (Cfg::kTrans) {
-                    eval_candidate_t<Cfg, true>(d, s_sw, d.Ppad >> 5, s_cs, ps, gen.prow, lane, viol, obj);
+                    eval_candidate_t<Cfg, true>(d, s_sw, d.Ppad >> 5, s_bits, s_obj, s_cs, ps, gen.prow, lane, viol, obj);
                 } else {
                     eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
                 }
-                const unsigned long long key = pack_key(viol, obj, idx);
+                const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
                 if constexpr (Cfg::kTrans) {
                     if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = key;
                 }
@@ -471,37 +490,52 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 const unsigned long long w = __shfl_xor_sync(0xFFFFFFFFu, v, o);
                 v = w < v ? w : v;
             }
-            if (lane == 0) {
-                if (pp.world == 1) {
+            if (pp.world == 1) {
+                if (lane == 0) {
                     if (v != kKeyNone) atomicMin(keys + t, v);
                     // grid barrier: every CTA's contribution to keys[t] is visible before anyone reads it
                     __threadfence();
                     atomicAdd(grid_bar, 1u);
-                    if (!spin_until(grid_bar, (t + 1) * gridDim.x, pp.abort)) s_abort = 1;
+                    if (!spin_until(grid_bar, (t + 1) * gridDim.x, pp.abort, pp.timeout_ns)) s_abort = 1;
                     __threadfence();
-                } else {
-                    // 1. this GPU's minimum
+                }
+            } else {
+                // 1. this GPU's minimum
+                if (lane == 0) {
                     if (v != kKeyNone) atomicMin(pp.lkeys + t, v);
                     __threadfence();
                     atomicAdd(grid_bar, 1u);
-                    if (blockIdx.x == 0) {
-                        // 2. CTA 0 trades it with every peer over NVLink: min into each mailbox, then arrive
-                        bool ok = spin_until(grid_bar, (t + 1) * gridDim.x, pp.abort);
-                        if (ok) {
-                            __threadfence();
-                            const unsigned long long mine = __ldcg(pp.lkeys + t);
-                            for (int r = 0; r < pp.world; ++r) atomicMin_system(&pp.mail[r]->keys[pp.bank][t], mine);
-                            __threadfence_system();
-                            for (int r = 0; r < pp.world; ++r) atomicAdd_system(&pp.mail[r]->arrive[pp.bank][t], 1u);
-                            ok = spin_until(&pp.mail[pp.rank]->arrive[pp.bank][t], (unsigned int)pp.world, pp.abort);
+                }
+                if (blockIdx.x == 0) {
+                    // 2. CTA 0 trades it with every peer over NVLink: lane r stores this rank's key into its slot
+                    //    of rank r's mailbox (all stores in flight together), then polls slot r of the own mailbox
+                    bool ok = true;
+                    if (lane == 0) ok = spin_until(grid_bar, (t + 1) * gridDim.x, pp.abort, pp.timeout_ns);
+                    ok = __shfl_sync(0xFFFFFFFFu, ok ? 1 : 0, 0) != 0;
+                    unsigned long long got = kKeyNone;
+                    if (ok) {
+                        __threadfence();
+                        const unsigned long long mine = __ldcg(pp.lkeys + t);
+                        if (lane < pp.world) {
+                            *reinterpret_cast<volatile unsigned long long *>(&pp.mail[lane]->slot[pp.bank][t][pp.rank]) = mine;
+                            ok = spin_filled(&pp.mail[pp.rank]->slot[pp.bank][t][lane], got, pp.abort, pp.timeout_ns);
                         }
-                        if (ok) {
-                            __threadfence_system();
-                            keys[t] = *reinterpret_cast<volatile unsigned long long *>(&pp.mail[pp.rank]->keys[pp.bank][t]);
+                        ok = __all_sync(0xFFFFFFFFu, ok);
+                    }
+                    if (ok) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const unsigned long long w = __shfl_xor_sync(0xFFFFFFFFu, got, o);
+                            got = w < got ? w : got;
+                        }
+                        if (lane == 0) {
+                            keys[t] = got;
                             __threadfence();
                             atomicExch(pp.release, t + 1);            // 3. local CTAs may read keys[t]
-                        } else s_abort = 1;
-                    } else if (!spin_until(pp.release, t + 1, pp.abort)) s_abort = 1;
+                        }
+                    } else if (lane == 0) s_abort = 1;
+                } else if (lane == 0) {
+                    if (!spin_until(pp.release, t + 1, pp.abort, pp.timeout_ns)) s_abort = 1;
                     __threadfence();
                 }
             }
@@ -518,32 +552,35 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 if (vc < s_red[kWarps + 1]) { s_red[kWarps + 1] = vc; s_red[kWarps + 2] = 0; } else ++s_red[kWarps + 2];
                 if (pp.patience && s_red[kWarps + 2] >= pp.patience) s_red[kWarps] = 1;
                 if (blockIdx.x == 0 && pp.rounds_run) *pp.rounds_run = t + 1;
+                if (blockIdx.x == 0 && pp.carry) { pp.carry[0] = s_red[kWarps + 1]; pp.carry[1] = s_red[kWarps + 2]; }
             }
 #endif
             if (kDelta && lane == 0) {
                 int *s_base = reinterpret_cast<int *>(smem + plan.off_totals) + 544;
-                const uint32_t kv = (uint32_t)(k >> 48);
-                s_base[2] = (k != kKeyNone && kv < kViolCap) ? 1 : 0;
+                const uint32_t kv = key_violation(k, d.key_obj_bits);
+                s_base[2] = (k != kKeyNone && (uint64_t)kv < key_viol_cap(d.key_obj_bits)) ? 1 : 0;
                 s_base[0] = (int)kv;
-                s_base[1] = (int)(kObjCap - (uint32_t)((k >> kIdxBits) & kObjCap));
+                s_base[1] = (int)key_objective(k, d.key_obj_bits);
             }
             if (k != kKeyNone) {
                 PatchSet ps;
                 gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps, no_rows);
                 __syncwarp();
+                if constexpr (Cfg::kTrans) {                        // every lane rewrites its own slots' words
+#pragma unroll
+                    for (int i = 0; i < kMaxOps; ++i) {
+                        if (i < ps.n) {
+                            uint32_t newrow[W];
+#pragma unroll
+                            for (int w = 0; w < W; ++w) newrow[w] = gen.prow[i * W + w];
+                            t_patch_row<W>(s_sw, d.Ppad >> 5, d.Ppad, ps.p[i], newrow, ps.ld[i], s_obj, lane);
+                        }
+                    }
+                }
                 if (lane == 0) {
 #pragma unroll
                     for (int i = 0; i < kMaxOps; ++i) {
                         if (i < ps.n) {
-                            if constexpr (Cfg::kTrans) {            // transposed planes first: they need the old row
-                                uint32_t oldrow[W], newrow[W];
-#pragma unroll
-                                for (int w = 0; w < W; ++w) {
-                                    oldrow[w] = s_bits[(size_t)w * d.Ppad + ps.p[i]];
-                                    newrow[w] = gen.prow[i * W + w];
-                                }
-                                t_patch_row<W>(s_sw, d.Ppad >> 5, ps.p[i], oldrow, s_leader[ps.p[i]], newrow, ps.ld[i]);
-                            }
                             for (int w = 0; w < W; ++w) {
                                 const uint32_t v = gen.prow[i * W + w];
                                 s_bits[(size_t)w * d.Ppad + ps.p[i]] = v;
@@ -567,43 +604,29 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 }
 
 // ------------------------------------------------------------------------------------------
-// instantiation lists.  X(W, NPH, kRack, kObj) for every evaluator configuration of a row width /
-// counter depth: rack forms {general, 8-slot, 16-slot, whole-word} x objective encodings {packed
-// entries / dense, 3 mask planes, 6 mask planes} (mask planes: rows of up to 64 slots only).
+// instantiation lists.  X(W, NPH, kRack, kObj) for every evaluator configuration of a row width:
+// rack forms {general, 8-slot, 16-slot, whole-word} x objective encodings {packed entries / dense,
+// 3 mask planes} (mask planes: rows of up to 64 slots only).  One counter depth (NPH = 5: per-lane
+// column counts up to 255, i.e. every P the engine accepts).
 // ------------------------------------------------------------------------------------------
 #define KAO_FOR_RACKS(X, W, NPH, O) X(W, NPH, 0, O) X(W, NPH, 3, O) X(W, NPH, 4, O) X(W, NPH, 5, O)
-#define KAO_FOR_CFGS_NARROW(X, W, NPH) KAO_FOR_RACKS(X, W, NPH, 0) KAO_FOR_RACKS(X, W, NPH, 3) KAO_FOR_RACKS(X, W, NPH, 6)
+#define KAO_FOR_CFGS_NARROW(X, W, NPH) KAO_FOR_RACKS(X, W, NPH, 0) KAO_FOR_RACKS(X, W, NPH, 3)
 #define KAO_FOR_CFGS_WIDE(X, W, NPH) KAO_FOR_RACKS(X, W, NPH, 0)
 
 #define KAO_ROUND_KERNEL(W, NPH, R, O)                                                                      \
     search_round_kernel<EvalCfg<W, NPH, R, O>, threads_for<W>()>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
                                                                    uint32_t, uint32_t, unsigned long long *,      \
                                                                    unsigned long long *)
-#define KAO_PERSISTENT_KERNEL_T(W, NW)                                                                      \
-    search_persistent_kernel<EvalCfgT<W, NW>, threads_for<W>(), false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
-                                                                  uint32_t, unsigned long long *, unsigned int *, P2P, \
-                                                                  unsigned long long *)
-// schedules of the column-major evaluator for the headline layout (two-word rows, 32 partition words):
-// X(sync, compress, threads, unroll, roll, fuse); (0, 1, 768, 1, 0, 0) is the default above
-#define KAO_TUNE_CFG(S, C, T, U, RL, F) EvalCfgT<2, 32, S, C, T, U, RL, F>
-#define KAO_PERSISTENT_KERNEL_TUNE(S, C, T, U, RL, F)                                                       \
-    search_persistent_kernel<KAO_TUNE_CFG(S, C, T, U, RL, F), T, false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
-                                                                        uint32_t, unsigned long long *, unsigned int *, P2P, \
-                                                                        unsigned long long *)
-#define KAO_FOR_TUNE_TU(X, S, T, U) X(S, 1, T, U, 0, 0) X(S, 0, T, U, 0, 0) X(S, 2, T, U, 0, 0)
-#define KAO_FOR_TUNE_TU_ROLLED(X, S, T, U) X(S, 1, T, U, 1, 0) X(S, 2, T, U, 1, 0)
-// row network fused into the column loop (needs the registers of 512 threads per CTA; 768 is built too)
-#define KAO_FOR_TUNE_FUSED(X, S) X(S, 1, 512, 1, 0, 1) X(S, 2, 512, 1, 0, 1) X(S, 1, 768, 1, 0, 1) X(S, 2, 768, 1, 0, 1)
-#define KAO_FOR_TUNE_PLAIN(X, S) KAO_FOR_TUNE_TU(X, S, 768, 1) KAO_FOR_TUNE_TU(X, S, 512, 1) KAO_FOR_TUNE_TU(X, S, 512, 2) KAO_FOR_TUNE_FUSED(X, S)
-// warps not in step (warp-only sync, half-CTA groups): also with the rolled row pass
-#define KAO_FOR_TUNE_LOOSE(X, S) KAO_FOR_TUNE_PLAIN(X, S) \
-    KAO_FOR_TUNE_TU_ROLLED(X, S, 768, 1) KAO_FOR_TUNE_TU_ROLLED(X, S, 512, 1) KAO_FOR_TUNE_TU_ROLLED(X, S, 512, 2)
-#define KAO_FOR_TUNE_SYNC_0(X) KAO_FOR_TUNE_PLAIN(X, 0)
-#define KAO_FOR_TUNE_SYNC_1(X) KAO_FOR_TUNE_LOOSE(X, 1)
-#define KAO_FOR_TUNE_SYNC_2(X) KAO_FOR_TUNE_PLAIN(X, 2)
-#define KAO_FOR_TUNE_SYNC_3(X) KAO_FOR_TUNE_LOOSE(X, 3)
-#define KAO_FOR_TUNE_SYNC_4(X) KAO_FOR_TUNE_PLAIN(X, 4)
-#define KAO_FOR_TUNE_ALL(X) KAO_FOR_TUNE_SYNC_0(X) KAO_FOR_TUNE_SYNC_1(X) KAO_FOR_TUNE_SYNC_2(X) KAO_FOR_TUNE_SYNC_3(X) KAO_FOR_TUNE_SYNC_4(X)
+// Column-major kernels: X(sync, pop, threads) for every built schedule (kao_set_schedule); each is
+// instantiated for W = 1, 2 and for 32 partition words (compile-time offsets) / any word count.
+#define KAO_FOR_SCHEDULES(X) \
+    X(1, 0x11111, 768) X(0, 0x11111, 768) X(1, 0x11122, 768) X(1, 0x11133, 768) X(1, 0x22233, 768) X(1, 0x11133, 512)
+#define KAO_SCHEDULE_DEFAULT_SYNC 1
+#define KAO_SCHEDULE_DEFAULT_POP 0x11111
+#define KAO_PERSISTENT_KERNEL_T(W, NW, S, POP, T)                                                            \
+    search_persistent_kernel<EvalCfgT<W, NW, S, POP, T>, T, false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
+                                                                    uint32_t, unsigned long long *, unsigned int *, P2P, \
+                                                                    unsigned long long *)
 #define KAO_PERSISTENT_KERNEL(W, NPH, R, O, T, DELTA)                                                       \
     search_persistent_kernel<EvalCfg<W, NPH, R, O>, T, DELTA>(Params, SmemPlan, uint64_t, uint32_t, uint32_t,      \
                                                              uint32_t, unsigned long long *, unsigned int *, P2P, \

@@ -32,14 +32,15 @@ class _KaoProblem(C.Structure):
 
 class _KaoOptions(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("rounds", C.c_uint32), ("round_size", C.c_uint32),
-                ("device", C.c_int32), ("flags", C.c_uint32)]
+                ("device", C.c_int32), ("flags", C.c_uint32), ("n_gpus", C.c_int32), ("device_mask", C.c_uint32)]
 
 
 class _KaoResult(C.Structure):
     _fields_ = [("replicas", C.c_void_p), ("objective", C.c_int64), ("violation", C.c_int64),
                 ("moves", C.c_int32), ("feasible", C.c_int32), ("key", C.c_uint64),
-                ("n_candidates", C.c_uint64), ("rounds_run", C.c_uint32), ("reserved", C.c_uint32),
-                ("device_ms", C.c_double), ("total_ms", C.c_double)]
+                ("n_candidates", C.c_uint64), ("rounds_run", C.c_uint32), ("restarts", C.c_uint32),
+                ("device_ms", C.c_double), ("total_ms", C.c_double), ("objective_bound", C.c_int64),
+                ("optimal", C.c_int32), ("key_obj_bits", C.c_int32), ("n_gpus", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -73,10 +74,19 @@ def _check(rc, allow_infeasible=False):
     raise KaoError("libkao error %d: %s" % (rc, load_library().kao_last_error().decode()))
 
 
-def unpack_key(key: int):
-    """packed key -> (violation, objective, index)  (include/kao.h KAO_KEY_*)."""
-    key = int(key)
-    return key >> 48, 0xFFFFFF - ((key >> 24) & 0xFFFFFF), key & 0xFFFFFF
+def unpack_key(key: int, obj_bits: int):
+    """packed key -> (violation, objective, index)  (include/kao.h KAO_KEY_*); obj_bits = key_obj_bits(problem)
+    = Session.key_obj_bits = SolveResult.key_obj_bits: the width of the cost field of that problem's keys."""
+    key, omax = int(key), (1 << obj_bits) - 1
+    return key >> (24 + obj_bits), omax - ((key >> 24) & omax), key & 0xFFFFFF
+
+
+def key_obj_bits(pb: Problem) -> int:
+    """Width of the cost field of this problem's packed keys (kao_key_obj_bits; needs no GPU)."""
+    rc = load_library().kao_key_obj_bits(_CProblem(pb).ref())
+    if rc < 0:
+        _check(rc)
+    return rc
 
 
 class _CProblem:
@@ -109,6 +119,10 @@ class SolveResult:
     rounds: int
     device_ms: float
     total_ms: float
+    objective_bound: int = 0  # upper bound on any feasible assignment's objective (kao_result.objective_bound)
+    optimal: bool = False     # proven optimal: feasible and objective == objective_bound
+    key_obj_bits: int = 24    # cost-field width of `key` (unpack_key)
+    n_gpus: int = 1
 
 
 class Session:
@@ -120,6 +134,10 @@ class Session:
         self._h = C.c_void_p()
         self._lib = load_library()
         _check(self._lib.kao_create(self._cp.ref(), C.c_int32(device), C.byref(self._h)))
+        self.key_obj_bits = self._lib.kao_key_obj_bits(self._cp.ref())
+
+    def unpack_key(self, key):
+        return unpack_key(key, self.key_obj_bits)
 
     def close(self):
         if self._h:
@@ -133,9 +151,9 @@ class Session:
             pass
 
     def set_evaluator(self, column_major: bool) -> bool:
-        """Selects the full-evaluation kernel of this session (kao_set_evaluator): row-major (default) or
-        column-major.  Same keys either way.  Returns False when the layout is not covered by the
-        column-major evaluator (the session then stays as it was)."""
+        """Selects the full-evaluation kernel of this session (kao_set_evaluator): column-major (the default
+        where the layout allows it) or row-major.  Same keys either way.  Returns False when the layout is
+        not covered by the column-major evaluator (the session then stays as it was)."""
         rc = self._lib.kao_set_evaluator(self._h, C.c_int32(1 if column_major else 0))
         if rc == KAO_OK:
             return True
@@ -144,11 +162,10 @@ class Session:
         _check(rc)
         return False
 
-    def set_schedule(self, sync: int, compress: int, threads: int, unroll: int, roll: int = 0, fuse: int = 0) -> bool:
+    def set_schedule(self, sync: int, pop: int, threads: int) -> bool:
         """Schedule of the column-major evaluator (kao_set_schedule): results never depend on it.
-        False when that variant is not built for this layout."""
-        rc = self._lib.kao_set_schedule(self._h, C.c_int32(sync), C.c_int32(compress), C.c_int32(threads), C.c_int32(unroll),
-                                        C.c_int32(roll), C.c_int32(fuse))
+        False when that variant is not built."""
+        rc = self._lib.kao_set_schedule(self._h, C.c_int32(sync), C.c_int32(pop), C.c_int32(threads))
         if rc == -1:
             return False
         _check(rc)
@@ -265,17 +282,21 @@ class Session:
 
 def solve(pb: Problem, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15,
           device: int = 0, require_feasible: bool = False, restarts: int = 1, delta: bool = False,
-          patience: int = 0, column_major: bool = False) -> SolveResult:
-    """One blocking kao_solve from host buffers (tables up, winner down)."""
+          patience: int = 0, row_major: bool = False, n_gpus: int = 1, device_mask: int = 0) -> SolveResult:
+    """One blocking kao_solve from host buffers (tables up, winner down).  n_gpus > 1: every round is sharded
+    over that many GPUs of this process (devices device .. device+n_gpus-1, or those of device_mask); the
+    result is the same as on one GPU with the same round_size."""
     lib = load_library()
     cp = _CProblem(pb)
     reps = np.full((pb.P, pb.RF), -1, np.int32)
-    opt = _KaoOptions(seed, rounds, round_size, device, max(1, min(255, restarts)) | (0x100 if delta else 0) | (0x200 if column_major else 0) | (max(0, min(65535, patience)) << 16))
+    flags = max(1, min(255, restarts)) | (0x100 if delta else 0) | (0x200 if row_major else 0) | (max(0, min(65535, patience)) << 16)
+    opt = _KaoOptions(seed & (2 ** 64 - 1), rounds, round_size, device, flags, n_gpus, device_mask)
     res = _KaoResult()
     res.replicas = reps.ctypes.data
     rc = _check(lib.kao_solve(cp.ref(), C.byref(opt), C.byref(res)), allow_infeasible=not require_feasible)
     return SolveResult(reps, res.objective, res.violation, res.moves, rc == KAO_OK, res.key,
-                       res.n_candidates, res.rounds_run, res.device_ms, res.total_ms)
+                       res.n_candidates, res.rounds_run, res.device_ms, res.total_ms, res.objective_bound,
+                       bool(res.optimal), res.key_obj_bits, res.n_gpus)
 
 
 def evaluate(pb: Problem, replicas, device: int = 0):

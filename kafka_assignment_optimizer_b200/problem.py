@@ -72,7 +72,7 @@ def default_bounds(P: int, B: int, R: int, RF: int, rack_of: np.ndarray):
 
 def build_problem(current: Sequence[Sequence[int]], broker_ids: Iterable[int],
                   rack_by_broker: Dict[int, str], rf: int, topics: Optional[list] = None) -> Problem:
-    ids = sorted(int(b) for b in broker_ids)
+    ids = sorted({int(b) for b in broker_ids})          # a repeated id is one broker (as kao-cli's build_model)
     dense = {b: i for i, b in enumerate(ids)}
     racks = sorted({str(rack_by_broker[b]) for b in ids})
     ridx = {r: i for i, r in enumerate(racks)}

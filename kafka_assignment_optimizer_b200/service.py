@@ -22,6 +22,18 @@ from typing import Callable, Optional
 from .problem import build_problem, parse_assignment_json, parse_broker_list, parse_rack_map, reassignment_json
 
 
+MAX_ROUNDS = 1 << 20            # KAO_MAX_ROUNDS
+MAX_ROUND_SIZE = 1 << 24        # KAO_MAX_ROUND_SIZE
+MAX_CANDIDATES = 1 << 36        # per request: minutes of one GPU, not days
+
+
+def _bounded(body: dict, name: str, default: int, lo: int, hi: int) -> int:
+    v = int(body.get(name, default))
+    if not lo <= v <= hi:
+        raise ValueError("%s must be %d..%d" % (name, lo, hi))
+    return v
+
+
 def handle_submit(body: dict, solver: Optional[Callable] = None) -> dict:
     """Pure request -> response function (the HTTP layer only moves bytes)."""
     rows, topics = parse_assignment_json(body["assignment"])
@@ -33,9 +45,15 @@ def handle_submit(body: dict, solver: Optional[Callable] = None) -> dict:
     pb = build_problem(rows, brokers, racks, rf, topics)
     if solver is None:
         from .optimizer import solve as solver
-    res = solver(pb, seed=int(body.get("seed", 0x5EED)), rounds=int(body.get("rounds", 256)),
-                 round_size=int(body.get("round_size", 1 << 15)), restarts=int(body.get("restarts", 1)),
-                 delta=bool(body.get("delta", False)), patience=int(body.get("patience", 0)))
+    # a request cannot ask for an unbounded search: the limits of include/kao.h, checked here as well
+    rounds = _bounded(body, "rounds", 256, 0, MAX_ROUNDS)
+    round_size = _bounded(body, "round_size", 1 << 15, 2, MAX_ROUND_SIZE)
+    restarts = _bounded(body, "restarts", 1, 1, 255)
+    patience = _bounded(body, "patience", 0, 0, 65535)
+    if rounds * round_size * restarts > MAX_CANDIDATES:
+        raise ValueError("rounds * round_size * restarts exceeds %d candidates per request" % MAX_CANDIDATES)
+    res = solver(pb, seed=int(body.get("seed", 0x5EED)) & (2**64 - 1), rounds=rounds, round_size=round_size,
+                 restarts=restarts, delta=bool(body.get("delta", False)), patience=patience)
     return {"reassignment": reassignment_json(pb, res.replicas), "objective": int(res.objective),
             "violation": int(res.violation), "moves": int(res.moves), "feasible": bool(res.feasible)}
 

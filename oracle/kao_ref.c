@@ -41,8 +41,7 @@ typedef struct {
     const int32_t *cur;              /* [P*RFcur] dense broker index, -1 = absent */
 } ref_problem;
 
-#define OBJ_CAP 0xFFFFFFu
-#define VIOL_CAP 0x7FFFu        /* keys stay below 2^63: they order the same as signed int64 */
+#define KEY_BITS 63             /* keys stay below 2^63: they order the same as signed int64 */
 #define IDX_BITS 24
 #define KEY_NONE 0x7FFFFFFFFFFFFFFFull
 
@@ -170,11 +169,30 @@ void kao_ref_eval(const ref_problem *pb, const uint32_t *bits, const uint8_t *le
     *viol_out = viol; *obj_out = obj;
 }
 
-uint64_t kao_ref_pack(int64_t viol, int64_t obj, uint32_t idx)
+/* Packed key (docs/MODEL.md 3): violation | (objmax - objective) | index, smaller is better.  The
+ * cost field is obj_bits wide = the bit length of the largest objective the model can reach
+ * (P * RF * largest weight); the violation field takes the remaining 63 - 24 - obj_bits bits
+ * (at most 31) and saturates. */
+int kao_ref_obj_bits(const ref_problem *pb)
 {
-    uint64_t v = viol > VIOL_CAP ? VIOL_CAP : (uint64_t)viol;
-    uint64_t c = obj > OBJ_CAP ? 0 : (uint64_t)(OBJ_CAP - obj);
-    return (v << 48) | (c << IDX_BITS) | (idx & ((1u << IDX_BITS) - 1));
+    uint64_t maxw = 0, top;
+    int bits = 1;
+    for (size_t i = 0; i < (size_t)pb->P * pb->B; ++i) {
+        if (pb->wF[i] > maxw) maxw = pb->wF[i];
+        if (pb->wL[i] > maxw) maxw = pb->wL[i];
+    }
+    top = (uint64_t)pb->P * pb->RF * maxw;
+    while (top >> bits) ++bits;
+    return bits;
+}
+uint64_t kao_ref_pack(int64_t viol, int64_t obj, uint32_t idx, int obj_bits)
+{
+    const int vbits = KEY_BITS - IDX_BITS - obj_bits;
+    const uint64_t vcap = vbits >= 31 ? 0x7FFFFFFFull : ((1ull << vbits) - 1);
+    const uint64_t omax = (1ull << obj_bits) - 1;
+    uint64_t v = viol < 0 ? 0 : ((uint64_t)viol > vcap ? vcap : (uint64_t)viol);
+    uint64_t c = (obj < 0 || (uint64_t)obj > omax) ? 0 : omax - (uint64_t)obj;
+    return (v << (IDX_BITS + obj_bits)) | (c << IDX_BITS) | (idx & ((1u << IDX_BITS) - 1));
 }
 
 /* ---------------------------------------------------------------- replica lists <-> bit-plane */
@@ -522,6 +540,7 @@ void kao_ref_candidate_keys(const ref_problem *pb, const uint32_t *bits, const u
     ref_layout L; kao_ref_layout(pb, &L);
     const size_t nb = (size_t)pb->P * L.W;
     ref_aux ax;
+    const int obj_bits = kao_ref_obj_bits(pb);
     aux_alloc(pb, L.W, &ax);
     analyse(pb, &L, bits, leader, &ax);
 #ifdef _OPENMP
@@ -541,7 +560,7 @@ void kao_ref_candidate_keys(const ref_problem *pb, const uint32_t *bits, const u
             memcpy(sb, bits, nb * 4); memcpy(sl, leader, (size_t)pb->P);
             apply_patches(L.W, &ps, sb, sl);
             kao_ref_eval(pb, sb, sl, &v, &o);
-            keys[i] = kao_ref_pack(v, o, idx);
+            keys[i] = kao_ref_pack(v, o, idx, obj_bits);
         }
         free(sb); free(sl);
     }

@@ -37,7 +37,7 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
         _lib.kao_ref_pack.restype = C.c_uint64
-        _lib.kao_ref_pack.argtypes = [C.c_int64, C.c_int64, C.c_uint32]
+        _lib.kao_ref_pack.argtypes = [C.c_int64, C.c_int64, C.c_uint32, C.c_int]
         _lib.kao_ref_search.restype = C.c_uint64
     return _lib
 
@@ -65,6 +65,7 @@ class Ref:
         self.W = lib().kao_ref_words(C.byref(self.c))
         if self.W < 1:
             raise ValueError("unsupported topology (more than 256 rack-aligned broker slots)")
+        self.obj_bits = int(lib().kao_ref_obj_bits(C.byref(self.c)))     # cost-field width of this problem's keys
 
     def _p(self):
         return C.byref(self.c)
@@ -135,6 +136,14 @@ class Ref:
         return lib().kao_ref_max_threads()
 
 
-def unpack_key(key):
-    key = int(key)
-    return key >> 48, 0xFFFFFF - ((key >> 24) & 0xFFFFFF), key & 0xFFFFFF
+    def unpack_key(self, key):
+        return unpack_key(key, self.obj_bits)
+
+    def pack_key(self, viol, obj, idx):
+        return int(lib().kao_ref_pack(int(viol), int(obj), int(idx), self.obj_bits))
+
+
+def unpack_key(key, obj_bits):
+    """packed key -> (violation, objective, index); obj_bits = Ref.obj_bits (docs/MODEL.md 3)."""
+    key, omax = int(key), (1 << obj_bits) - 1
+    return key >> (24 + obj_bits), omax - ((key >> 24) & omax), key & 0xFFFFFF

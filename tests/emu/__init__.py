@@ -47,9 +47,9 @@ class EmuSession:
 
     def set_evaluator(self, mode):
         """0: row-major evaluator; 1: column-major evaluator (csrc/kao_device_t.cuh) as the engine picks it;
-        2: its run-time-sized form even where the 32-word specialisation applies; 3: plain popcounts
-        (kCompress = 0); 4: unrolled column loop; 5: five compressed popcount streams (kCompress = 2); 6: row pass as a loop (kRoll = 1); 7: row network fused into the column loop (kFuse = 1; two-word
-        rows with 32 partition words only).  False is returned for unsupported layouts."""
+        2: its run-time-sized form even where the 32-word specialisation applies; 3: a POPC per word
+        (kPop = 0x00000); 4: kPop = 0x11122; 5: kPop = 0x11133 (Harley-Seal on the column / leader totals);
+        6: kPop = 0x22233.  False is returned for unsupported layouts."""
         return lib().kao_emu_set_evaluator(self._h, C.c_int32(mode)) == 0
 
     def set_base(self, replicas):

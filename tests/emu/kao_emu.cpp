@@ -35,7 +35,7 @@ struct Emu {
     std::vector<uint32_t> prow;          // [kMaxOps * W]
     // column-major evaluator (kao_device_t.cuh): supported shape, in use, the five transposed planes
     bool trans_ok = false;
-    int trans = 0;                       // 0 row-major evaluator, 1..4 forms of the column-major one
+    int trans = 0;                       // 0 row-major evaluator, 1.. forms (schedules) of the column-major one
     int nW = 0;
     std::vector<uint32_t> T;
     std::string err;
@@ -114,24 +114,26 @@ template <class Cfg> struct Run {
             int viol, obj;
             if constexpr (W <= 2) {
                 // forms of the column-major evaluator: 1 as the engine picks it (32-word specialisation where it
-                // applies, compressed popcounts), 2 run-time word count, 3 plain popcounts, 4 unrolled column loop, 5 five compressed streams, 6 rolled row pass, 7 fused passes
+                // applies, default popcount streams), 2 run-time word count, 3 a POPC per word, 4 two POPC per four
+                // words on the totals, 5 Harley-Seal on the totals, 6 carry-save on every stream
                 const bool fixed = e.nW == 32;
-                if (e.trans == 1 && fixed) eval_candidate_t<EvalCfgT<W, 32>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
-                else if (e.trans == 1 || e.trans == 2) eval_candidate_t<EvalCfgT<W, 0>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
-                else if (e.trans == 3 && fixed) eval_candidate_t<EvalCfgT<W, 32, 0, 0>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
-                else if (e.trans == 3) eval_candidate_t<EvalCfgT<W, 0, 0, 0>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
-                else if (e.trans == 4) eval_candidate_t<EvalCfgT<W, 0, 0, 1, 512, 2>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
-                else if (e.trans == 5 && fixed) eval_candidate_t<EvalCfgT<W, 32, 0, 2>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
-                else if (e.trans == 5) eval_candidate_t<EvalCfgT<W, 0, 0, 2>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
-                else if (e.trans == 6) eval_candidate_t<EvalCfgT<W, 0, 1, 1, 0, 1, 1>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
-                else if (e.trans == 7) {
-                    if constexpr (W == 2) eval_candidate_t<EvalCfgT<2, 32, 0, 2, 512, 1, 0, 1>, true>(e.prm, e.T.data(), e.nW, &e.cs, ps, e.prow.data(), lane, viol, obj);
-                }
+#define KAO_EMU_T(NW_, POP_) eval_candidate_t<EvalCfgT<W, NW_, 1, POP_>, true>(e.prm, e.T.data(), e.nW, e.bits.data(), e.prm.planesT, &e.cs, ps, e.prow.data(), lane, viol, obj)
+                if (e.trans == 1 && fixed) KAO_EMU_T(32, 0x11111);
+                else if (e.trans == 1 || e.trans == 2) KAO_EMU_T(0, 0x11111);
+                else if (e.trans == 3 && fixed) KAO_EMU_T(32, 0x00000);
+                else if (e.trans == 3) KAO_EMU_T(0, 0x00000);
+                else if (e.trans == 4 && fixed) KAO_EMU_T(32, 0x11122);
+                else if (e.trans == 4) KAO_EMU_T(0, 0x11122);
+                else if (e.trans == 5 && fixed) KAO_EMU_T(32, 0x11133);
+                else if (e.trans == 5) KAO_EMU_T(0, 0x11133);
+                else if (e.trans == 6 && fixed) KAO_EMU_T(32, 0x22233);
+                else if (e.trans == 6) KAO_EMU_T(0, 0x22233);
+#undef KAO_EMU_T
                 else eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
             } else {
                 eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
             }
-            if (lane == 0) out = pack_key(viol, obj, idx);
+            if (lane == 0) out = pack_key(viol, obj, idx, e.prm.key_obj_bits);
         });
         return out;
     }
@@ -149,10 +151,11 @@ template <class Cfg> struct Run {
         const int Ppad = e.hm.Ppad;
         for (int i = 0; i < win.n; ++i) {
             if constexpr (W <= 2) {
-                if (e.trans_ok) {                   // as the kernel does: transposed planes first, from the old row
-                    uint32_t oldrow[W], newrow[W];
-                    for (int w = 0; w < W; ++w) { oldrow[w] = e.bits[(size_t)w * Ppad + win.p[i]]; newrow[w] = e.prow[i * W + w]; }
-                    t_patch_row<W>(e.T.data(), e.nW, win.p[i], oldrow, e.leader[win.p[i]], newrow, win.ld[i]);
+                if (e.trans_ok) {                   // as the kernel does: every lane rewrites its own slots' words
+                    uint32_t newrow[W];
+                    for (int w = 0; w < W; ++w) newrow[w] = e.prow[i * W + w];
+                    for (int lane = 0; lane < 32; ++lane)
+                        t_patch_row<W>(e.T.data(), e.nW, Ppad, win.p[i], newrow, win.ld[i], e.prm.planesT, lane);
                 }
             }
             for (int w = 0; w < W; ++w) {
@@ -180,7 +183,7 @@ template <class Cfg> struct Run {
             tg.run(seed, round, idx, round_size, ps, rows);
             int viol, obj;
             delta_eval<Cfg>(e.prm, e.bits.data(), e.leader.data(), m_obj, &e.cs, ps, rows, cnt, lcnt, rc, base_viol, base_obj, viol, obj);
-            return pack_key(viol, obj, idx);
+            return pack_key(viol, obj, idx, e.prm.key_obj_bits);
         } else {
             (void)e; (void)seed; (void)round; (void)idx; (void)round_size; (void)cnt; (void)lcnt; (void)rc; (void)base_viol; (void)base_obj;
             return kKeyNone;
@@ -209,12 +212,11 @@ template <class F> auto dispatch(Emu &e, F f)
 #define KAO_EMU_CASE(W_, NPH_, R_, O_) \
     if (e.hm.W == W_ && e.nph == NPH_ && e.rack == R_ && e.obj == O_) return f(Run<EvalCfg<W_, NPH_, R_, O_>>{});
 #define KAO_EMU_RACKS(W_, NPH_, O_) KAO_EMU_CASE(W_, NPH_, 0, O_) KAO_EMU_CASE(W_, NPH_, 3, O_) KAO_EMU_CASE(W_, NPH_, 4, O_) KAO_EMU_CASE(W_, NPH_, 5, O_)
-#define KAO_EMU_NARROW(W_, NPH_) KAO_EMU_RACKS(W_, NPH_, 0) KAO_EMU_RACKS(W_, NPH_, 3) KAO_EMU_RACKS(W_, NPH_, 6)
-    KAO_EMU_NARROW(1, 3) KAO_EMU_NARROW(1, 5) KAO_EMU_NARROW(2, 3) KAO_EMU_NARROW(2, 5)
-    KAO_EMU_RACKS(4, 3, 0) KAO_EMU_RACKS(4, 5, 0) KAO_EMU_RACKS(8, 3, 0) KAO_EMU_RACKS(8, 5, 0)
+#define KAO_EMU_NARROW(W_, NPH_) KAO_EMU_RACKS(W_, NPH_, 0) KAO_EMU_RACKS(W_, NPH_, 3)
+    KAO_EMU_NARROW(1, 5) KAO_EMU_NARROW(2, 5) KAO_EMU_RACKS(4, 5, 0) KAO_EMU_RACKS(8, 5, 0)
     fprintf(stderr, "kao_emu: no evaluator configuration W=%d NPH=%d rack=%d obj=%d\n", e.hm.W, e.nph, e.rack, e.obj);
     abort();
-    return f(Run<EvalCfg<1, 3, 0, 0>>{});
+    return f(Run<EvalCfg<1, 5, 0, 0>>{});
 }
 
 thread_local std::string g_err;
@@ -238,18 +240,19 @@ void *kao_emu_create(const kao_problem *pb)
         plan = make_plan(m.W, m.Ppad, threads / 32, 4, m.P, m.RF, false);
     }
     if (plan.total > 227u * 1024u) { g_err = "problem too large for the shared-memory resident search kernel"; return nullptr; }
-    e->nph = (m.Ppad / 32 <= 63) ? 3 : 5;
+    e->nph = 5;                                       // one counter depth (kao_engine.cu: dispatch)
     e->rack = !m.hi1 ? 0 : (m.log2S == 3 ? 3 : (m.log2S == 4 ? 4 : 5));
-    e->obj = (m.W <= 2 && (m.nplanes == 3 || m.nplanes == 6)) ? m.nplanes : 0;
+    e->obj = (m.W <= 2 && m.nplanes == 3) ? 3 : 0;
     e->oh = m.W <= 2 && e->obj > 0;
     // kao_set_evaluator: the column-major evaluator covers 8-slot rack fields with C7 = "at most one
     // replica per rack" and three mask planes
     e->trans_ok = m.W <= 2 && m.hi1 && m.log2S == 3 && m.nplanes == 3 &&
-                  make_plan(m.W, m.Ppad, threads / 32, kTPlanes * m.W, m.P, m.RF, false).total <= 227u * 1024u;
+                  make_plan(m.W, m.Ppad, threads / 32, (kTPlanes + kTMaskPlanes) * m.W, m.P, m.RF, false).total <= 227u * 1024u;
     e->nW = m.Ppad / 32;
     fill_consts(m, e->cs);
     Params &p = e->prm;
     p.P = m.P; p.Ppad = m.Ppad; p.B = m.B; p.R = m.R; p.RF = m.RF; p.NS = m.NS; p.log2S = m.log2S;
+    p.key_obj_bits = m.key_obj_bits;
     p.ppr_lo = m.ppr_lo; p.ppr_hi = m.ppr_hi; p.dense = m.dense ? 1 : 0;
     p.nentries = m.nentries; p.nplanes = m.nplanes; p.plane_on_leader = m.plane_on_leader;
     for (int c = 0; c < 6; ++c) p.plane_value[c] = m.plane_value[c];
@@ -272,8 +275,7 @@ int kao_emu_set_evaluator(void *h, int32_t mode)
 {
     Emu &e = *static_cast<Emu *>(h);
     if (mode != 0 && !e.trans_ok) { g_err = "column-major evaluator: unsupported layout"; return -1; }
-    if (mode < 0 || mode > 7) { g_err = "unknown evaluator form"; return -1; }
-    if (mode == 7 && !(e.hm.W == 2 && e.nW == 32)) { g_err = "fused passes: two-word rows, 32 partition words"; return -1; }
+    if (mode < 0 || mode > 6) { g_err = "unknown evaluator form"; return -1; }
     e.trans = mode;
     return 0;
 }
@@ -305,8 +307,8 @@ void kao_emu_get_base(void *h, int32_t *replicas, int64_t *violation, int64_t *o
     if (moves) *moves = count_moves(e.hm, replicas);
     // idx + 1 == round_size is the identity candidate (docs/MODEL.md §5)
     const unsigned long long k = dispatch(e, [&](auto r) { return decltype(r)::key(e, 0, 0, 1, 2); });
-    if (violation) *violation = (int64_t)(k >> 48);
-    if (objective) *objective = (int64_t)(kObjCap - (uint32_t)((k >> kIdxBits) & kObjCap));
+    if (violation) *violation = (int64_t)key_violation(k, e.prm.key_obj_bits);
+    if (objective) *objective = (int64_t)key_objective(k, e.prm.key_obj_bits);
 }
 
 void kao_emu_candidate_keys(void *h, uint64_t seed, uint32_t round, uint32_t round_size, uint32_t idx_begin,

@@ -37,7 +37,8 @@ def optima():
 
 
 def streams():
-    """keys of the first 192 candidates + identity of round 2, and an 8-round trajectory, per shape"""
+    """keys of the first 192 candidates + identity of round 2, and an 8-round trajectory, per shape
+    (packed with the per-problem key layout of docs/MODEL.md 3: obj_bits is stored next to them)"""
     out = {}
     for name in sorted(SHAPES):
         pb = SHAPES[name]()
@@ -49,7 +50,7 @@ def streams():
         last = r.candidate_keys(bits, ld, 0xC0FFEE, 2, 1024, 1023, 1)
         b2, l2 = bits.copy(), ld.copy()
         _, traj = r.search(b2, l2, 0xC0FFEE, 0, 8, 512)
-        out[name] = {"W": r.W, "init_base": base.tolist(), "init_eval": [v, o],
+        out[name] = {"W": r.W, "obj_bits": r.obj_bits, "init_base": base.tolist(), "init_eval": [v, o],
                      "keys_round2": [int(k) for k in keys], "identity_key": int(last[0]),
                      "trajectory": [int(k) for k in traj], "final_base": r.decode(b2, l2).tolist()}
     return out

@@ -116,8 +116,8 @@ def test_explicit_evaluation_matches_exact_model(emu, name):
 COLUMN_MAJOR = {
     "cfg2": SHAPES["cfg2"], "cfg2_rm2": SHAPES["cfg2_rm2"], "cfg3_small": SHAPES["cfg3_small"],
     "rf1": SHAPES["rf1"], "rf_down": SHAPES["rf_down"],
-    "w1_6000": lambda: m.synthetic_problem(6000, 32, 4, 3, remove=1),      # 188 partition words: six per lane, rotated rows wrap
-    "w2_4000": lambda: m.synthetic_problem(4000, 64, 8, 3),                # the largest two-word shape whose planes fit
+    "w1_5300": lambda: m.synthetic_problem(5300, 32, 4, 3, remove=1),      # 168 partition words: six per lane, rotated rows wrap
+    "w2_2800": lambda: m.synthetic_problem(2800, 64, 8, 3),                # the largest two-word shape whose planes fit
     "rf4_w2": lambda: m.synthetic_problem(300, 40, 5, 4, remove=3),
     "r8_b61": lambda: m.synthetic_problem(96, 61, 8, 3),                   # unequal racks, padding slots
     "p1100": lambda: m.synthetic_problem(1100, 64, 8, 3, remove=2),        # 40 partition words: two per lane
@@ -177,7 +177,7 @@ def test_column_major_forms_agree(emu):
     sess = emu.EmuSession(product(pb))
     assert sess.set_evaluator(1)
     fixed = sess.candidate_keys(0x5EED, 3, 4096, 100, 96)
-    for form in (2, 3, 4, 5, 6, 7):      # run-time word count, plain popcounts, unrolled column loop, five compressed streams, rolled row pass, fused passes
+    for form in (2, 3, 4, 5, 6):         # run-time word count, a POPC per word, deeper carry-save on the totals / on every stream
         assert sess.set_evaluator(form)
         assert (fixed == sess.candidate_keys(0x5EED, 3, 4096, 100, 96)).all()
     assert sess.set_evaluator(0)
@@ -211,7 +211,7 @@ def test_column_major_evaluator_refuses_other_layouts(emu):
         sess.close()
 
 
-@pytest.mark.parametrize("form", [1, 2, 5, 7])
+@pytest.mark.parametrize("form", [1, 2, 5, 6])
 def test_column_major_long_stream_on_the_headline_shape(emu, ref_lib, form):
     """Config 3 (1000 x 64 x 8, RF 3): 12,000 candidates of four rounds against the restatement, with
     the base moved by winners in between (1-, 2- and 3-row patches in every chunk of the column walk)."""
@@ -224,7 +224,7 @@ def test_column_major_long_stream_on_the_headline_shape(emu, ref_lib, form):
         want = r.candidate_keys(bits, ld, 0xFACE, rnd, 3000, 0, 3000)
         got = sess.candidate_keys(0xFACE, rnd, 3000, 0, 3000)
         bad = np.flatnonzero(want != got)
-        assert bad.size == 0, (rnd, int(bad[0]), kao.unpack_key(want[bad[0]]), kao.unpack_key(got[bad[0]]))
+        assert bad.size == 0, (rnd, int(bad[0]), r.unpack_key(want[bad[0]]), r.unpack_key(got[bad[0]]))
         _, wk = r.search(bits, ld, 0xFACE, rnd, 1, 3000)
         assert (wk == sess.search(0xFACE, rnd, 1, 3000)).all()
     assert (sess.get_base()[0] == r.decode(bits, ld)).all()

@@ -23,8 +23,8 @@ def test_delta_keys_equal_full_keys(ref_lib, name):
         delta = sess.candidate_keys_delta(0xD17A, rnd, size, lo, n)
         want = r.candidate_keys(bits, ld, 0xD17A, rnd, size, lo, n)
         bad = np.flatnonzero(delta != full)
-        assert bad.size == 0, "idx %d: delta %s full %s" % (lo + bad[0], kao.unpack_key(delta[bad[0]]),
-                                                           kao.unpack_key(full[bad[0]]))
+        assert bad.size == 0, "idx %d: delta %s full %s" % (lo + bad[0], sess.unpack_key(delta[bad[0]]),
+                                                           sess.unpack_key(full[bad[0]]))
         assert (delta == want).all()
     # after some rounds the base is no longer the initial one: compare again
     sess.search(5, 0, 6, 1024)

@@ -48,7 +48,7 @@ def test_candidate_keys_bit_exact_vs_restatement(ref_lib, name):
         got = sess.candidate_keys(0xC0FFEE, rnd, size, lo, n)
         bad = np.flatnonzero(want != got)
         assert bad.size == 0, "first mismatch idx %d: want %s got %s (%d bad)" % (
-            lo + bad[0], kao.unpack_key(want[bad[0]]), kao.unpack_key(got[bad[0]]), bad.size)
+            lo + bad[0], sess.unpack_key(want[bad[0]]), sess.unpack_key(got[bad[0]]), bad.size)
     sess.close()
 
 
@@ -146,7 +146,7 @@ def test_full_size_properties_config3(golden_optima):
     pb = m.synthetic_problem(*e["args"])
     sess = kao.Session(product(pb))
     keys, ms = sess.search(0x5EED, 0, 150, 1 << 15)
-    ks = [kao.unpack_key(k)[:2] for k in keys]
+    ks = [sess.unpack_key(k)[:2] for k in keys]
     assert all((a[0], -a[1]) >= (b[0], -b[1]) for a, b in zip(ks, ks[1:]))
     reps, v, o, moves = sess.get_base()
     assert (v, o) == ks[-1] == m.evaluate(pb, reps)
@@ -155,7 +155,7 @@ def test_full_size_properties_config3(golden_optima):
     assert moves == m.replica_moves(pb, reps)
     # identity candidate of any later round reproduces the base's own evaluation
     ident = sess.candidate_keys(77, 1000, 4096, 4095, 1)[0]
-    assert kao.unpack_key(ident) == (v, o, 4095)
+    assert sess.unpack_key(ident) == (v, o, 4095)
     # determinism: same seed, fresh session -> identical trajectory
     sess2 = kao.Session(product(pb))
     keys2, _ = sess2.search(0x5EED, 0, 150, 1 << 15)
@@ -211,7 +211,7 @@ def test_patience_stops_early_with_the_same_answer(golden_optima):
     part, _ = sess.search(0x5EED, 0, 400, 1 << 14)
     n = sess.last_rounds()
     assert 60 < n < 400 and (part[:n] == full[:n]).all() and (part[n:] == kopt.KEY_NONE).all()
-    assert kao.unpack_key(part[n - 1])[:2] == (0, e["objective"])
+    assert sess.unpack_key(part[n - 1])[:2] == (0, e["objective"])
     assert sess.get_base()[2] == e["objective"]
     sess.close()
     res = kopt.solve(pb, seed=0x5EED, rounds=400, round_size=1 << 14, patience=60)
@@ -250,7 +250,7 @@ def test_candidate_keys_from_an_arbitrary_malformed_base(ref_lib, name):
     want = r.candidate_keys(bits, ld, 0xBAD, 4, 2048, 0, 2048)
     got = sess.candidate_keys(0xBAD, 4, 2048, 0, 2048)
     bad = np.flatnonzero(want != got)
-    assert bad.size == 0, "idx %d: want %s got %s" % (bad[0], kao.unpack_key(want[bad[0]]), kao.unpack_key(got[bad[0]]))
+    assert bad.size == 0, "idx %d: want %s got %s" % (bad[0], sess.unpack_key(want[bad[0]]), sess.unpack_key(got[bad[0]]))
     if sess.stats()["words_per_row"] <= 2:
         assert (sess.candidate_keys_delta(0xBAD, 4, 2048, 0, 2048) == want).all()
     _, traj = r.search(bits, ld, 0xBAD, 0, 10, 1024)

@@ -30,17 +30,34 @@ def test_abi_exports_every_declared_symbol(lib):
     names = set(re.findall(r"\b(kao_[a-z0-9_]+)\s*\(", hdr))
     assert {"kao_solve", "kao_eval", "kao_create", "kao_search", "kao_round_launch", "kao_round_apply",
             "kao_candidate_keys", "kao_profile_rounds", "kao_p2p_export", "kao_p2p_connect",
-            "kao_search_sharded", "kao_search_sharded_delta", "kao_search_delta", "kao_set_patience", "kao_set_evaluator", "kao_set_schedule", "kao_last_rounds", "kao_candidate_keys_delta", "kao_version", "kao_last_error"} <= names
+            "kao_search_sharded", "kao_search_sharded_delta", "kao_search_delta", "kao_set_patience", "kao_set_evaluator", "kao_set_schedule", "kao_last_rounds", "kao_candidate_keys_delta", "kao_key_obj_bits", "kao_version", "kao_last_error"} <= names
     for n in sorted(names):
         assert hasattr(lib, n), n
-    assert lib.kao_version() == 0x00010000
+    assert lib.kao_version() == 0x00020000
 
 
-def test_struct_layout_matches_header():
-    # sizes the C compiler gives the structs of include/kao.h (x86-64 SysV)
-    assert ctypes.sizeof(kopt._KaoProblem) == 5 * 4 + 4 + 9 * 8 + 2 * 4 + 8
-    assert ctypes.sizeof(kopt._KaoOptions) == 24
-    assert ctypes.sizeof(kopt._KaoResult) == 72
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors of kao_problem / kao_options / kao_result have the size and field offsets the C
+    compiler gives the structs of include/kao.h (asked of gcc, not hard-coded)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mirrors = {"kao_problem": kopt._KaoProblem, "kao_options": kopt._KaoOptions, "kao_result": kopt._KaoResult}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "kao.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)])
+    want = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in mirrors.items():
+        assert ctypes.sizeof(cls) == int(want[cname]), cname
+        for fname, _ in cls._fields_:
+            assert getattr(cls, fname).offset == int(want["%s.%s" % (cname, fname)]), (cname, fname)
 
 
 def test_no_gpu_means_loud_failure(lib):

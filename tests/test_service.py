@@ -38,3 +38,28 @@ def test_submit_round_trip_over_http():
             assert e.code == 400
     finally:
         srv.shutdown()
+
+
+def test_submit_refuses_unbounded_requests():
+    """`rounds` / `round_size` / `restarts` of a request are checked before they reach the C ABI
+    (a negative value would wrap to 4 billion rounds through c_uint32)."""
+    import pytest
+
+    base = {"assignment": json.loads(README_CURRENT), "brokers": ",".join(map(str, range(19))),
+            "racks": ",".join("%d:%s" % (b, "b" if b % 2 else "a") for b in range(20)), "rf": 2}
+    for bad in ({"rounds": -1}, {"rounds": 1 << 21}, {"round_size": 1}, {"round_size": 1 << 25}, {"restarts": 0},
+                {"restarts": 256}, {"patience": 1 << 16}, {"rounds": 1 << 20, "round_size": 1 << 20}):
+        with pytest.raises(ValueError):
+            service.handle_submit(dict(base, **bad), solver=oracle_solver)
+    assert service.handle_submit(dict(base, rounds=0), solver=oracle_solver)["feasible"]
+
+
+def test_duplicate_broker_ids_are_one_broker():
+    """a repeated id in the broker list must not create a phantom broker (kao-cli dedupes too)."""
+    from kafka_assignment_optimizer_b200.problem import build_problem
+
+    racks = {b: ("b" if b % 2 else "a") for b in range(4)}
+    cur = [[0, 1], [2, 3]]
+    a = build_problem(cur, [0, 1, 2, 3], racks, 2)
+    b = build_problem(cur, [0, 1, 1, 2, 3, 3], racks, 2)
+    assert a.B == b.B == 4 and (a.rep_hi == b.rep_hi).all() and (a.cur == b.cur).all()

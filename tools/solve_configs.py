@@ -41,7 +41,7 @@ def main():
             keys, ms = (sess.search_delta if delta else sess.search)(seed, done, chunk, size)
             dev_ms += ms
             for i, k in enumerate(keys):
-                v, o, _ = kao.unpack_key(k)
+                v, o, _ = sess.unpack_key(k)
                 if v == 0 and first_feasible is None:
                     first_feasible = done + i
                 if last is None or (v, -o) < last:
