@@ -163,7 +163,8 @@ int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
  * return bit-identical keys; they differ in how the base is laid out in shared memory:
  *   KAO_EVAL_COLUMN_MAJOR  also one bitmap over the partitions per broker slot; needs rows of up to 64
  *                          slots, racks of up to 8 brokers, C7 = at most one replica per rack, three
- *                          objective mask planes, and its planes in shared memory (about P <= 2800);
+ *                          objective mask planes, and its planes in shared memory (P <= 2048 for two-word rows,
+ *                          P <= 3840 for one-word rows);
  *                          the DEFAULT wherever it applies; KAO_E_ARG when requested elsewhere
  *   KAO_EVAL_ROW_MAJOR     rows of the (partition x broker) bit-plane, column totals by bit-sliced
  *                          counters; every layout */
@@ -179,6 +180,8 @@ int kao_set_evaluator(kao_handle *h, int32_t evaluator);
  * depend on it.  The environment variable KAO_SCHEDULE="sync,pop(hex),threads" sets it for every
  * session (and kao_solve); KAO_EVALUATOR=row forces the row-major evaluator. */
 int kao_set_schedule(kao_handle *h, int32_t sync, int32_t pop, int32_t threads);
+/* what kao_search of this session runs right now: evaluator (KAO_EVAL_*) and the schedule of the column-major one */
+int kao_get_evaluator(kao_handle *h, int32_t *evaluator, int32_t *sync, int32_t *pop, int32_t *threads);
 int kao_last_rounds(kao_handle *h, uint32_t *rounds_run);
 
 /* keys of candidates idx_begin .. idx_begin+count-1 of `round` against the current base (host

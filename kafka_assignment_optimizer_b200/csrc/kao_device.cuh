@@ -413,6 +413,29 @@ template <int W, bool kThread = false, bool kSmall = false> struct Gen {
 // ------------------------------------------------------------------------------------------
 // full evaluation of one candidate by one warp (docs/MODEL.md §3)
 // ------------------------------------------------------------------------------------------
+// One three-input logic instruction (LOP3.LUT): the truth table is the byte kLut with a = 0xF0, b = 0xCC,
+// c = 0xAA (e.g. majority 0xE8, a ^ b ^ c 0x96, a | b | c 0xFE, (a & b) | c 0xEA).  Spelled out because the
+// compiler does not always fuse a three-input expression into one instruction.
+template <int kLut> __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(KAO_HOST_EMU)
+    uint32_t r = 0;
+    if (kLut & 0x80) r |= a & b & c;
+    if (kLut & 0x40) r |= a & b & ~c;
+    if (kLut & 0x20) r |= a & ~b & c;
+    if (kLut & 0x10) r |= a & ~b & ~c;
+    if (kLut & 0x08) r |= ~a & b & c;
+    if (kLut & 0x04) r |= ~a & b & ~c;
+    if (kLut & 0x02) r |= ~a & ~b & c;
+    if (kLut & 0x01) r |= ~a & ~b & ~c;
+    return r;
+#else
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(kLut));
+    return r;
+#endif
+}
+
 // Carry-save adder: (h, l) = a + b + c  bitwise; two LOP3.
 __device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32_t b, uint32_t c)
 {
@@ -777,8 +800,8 @@ __device__ __forceinline__ void load_tile(const MemRef<kShared> &bitsT, const Me
 //   part A  per row: C1 / C7 terms, leader validity (C2/C5), leader-bonus planes; per tile: the
 //           carry-save column counters of replicas (C3, C6) and leaders (C4)
 //   part B  per row: the follower-weight part of the objective
-template <class Cfg, bool kShared, bool kCheckValid, bool kOh>
-__device__ __forceinline__ void tile_pass_a(const Params &d, const MemRef<kShared> &objT,
+template <class Cfg, bool kShared, bool kCheckValid, bool kOh, bool kObjShared = kShared>
+__device__ __forceinline__ void tile_pass_a(const Params &d, const MemRef<kObjShared> &objT,
                                             int lane, int u, int &viol, int &obj,
                                             const uint4 (&xv)[Cfg::W], const uint4 (&ohv)[Cfg::W], uint32_t ld4,
                                             uint32_t (&x)[kRowsPerLane][Cfg::W], uint32_t (&oh)[kRowsPerLane][Cfg::W])
@@ -835,8 +858,8 @@ __device__ __forceinline__ void tile_pass_a(const Params &d, const MemRef<kShare
         }
     }
 }
-template <class Cfg, bool kShared, bool kCheckValid>
-__device__ __forceinline__ void tile_pass_b(const Params &d, const MemRef<kShared> &objT,
+template <class Cfg, bool kShared, bool kCheckValid, bool kObjShared = kShared>
+__device__ __forceinline__ void tile_pass_b(const Params &d, const MemRef<kObjShared> &objT,
                                             int lane, int u, int &obj,
                                             const uint4 (&xv)[Cfg::W], uint32_t ld4)
 {
@@ -896,9 +919,9 @@ __device__ __forceinline__ void tile_pass_b(const Params &d, const MemRef<kShare
 
 // Two tiles (8 rows per lane) = one carry-save block.  Ppad is a multiple of 256, so the second
 // tile of the last pair exists in memory even when it holds no real row.
-template <class Cfg, bool kShared, bool kChk, bool kOh>
+template <class Cfg, bool kShared, bool kChk, bool kOh, bool kObjShared = kShared>
 __device__ __forceinline__ void eval_pair(const Params &d, const MemRef<kShared> &m_bits,
-                                          const MemRef<kShared> &m_leader, const MemRef<kShared> &m_obj,
+                                          const MemRef<kShared> &m_leader, const MemRef<kObjShared> &m_obj,
                                           const PatchSet &ps, const uint32_t *prow, int lane, int u,
                                           ColCounter<Cfg::W, Cfg::NPH> &rc, ColCounter<Cfg::W, Cfg::NPH> &lc,
                                           int &viol, int &obj)
@@ -908,8 +931,8 @@ __device__ __forceinline__ void eval_pair(const Params &d, const MemRef<kShared>
         uint4 xv[W], ohv[W];
         uint32_t ld4, x[kRowsPerLane][W], oh[kRowsPerLane][W];
         load_tile<W, kShared, kOh>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ohv, ld4);
-        tile_pass_a<Cfg, kShared, kChk, kOh>(d, m_obj, lane, u, viol, obj, xv, ohv, ld4, x, oh);
-        tile_pass_b<Cfg, kShared, kChk>(d, m_obj, lane, u, obj, xv, ld4);
+        tile_pass_a<Cfg, kShared, kChk, kOh, kObjShared>(d, m_obj, lane, u, viol, obj, xv, ohv, ld4, x, oh);
+        tile_pass_b<Cfg, kShared, kChk, kObjShared>(d, m_obj, lane, u, obj, xv, ld4);
         rc.template push_half<false>(x);
         lc.template push_half<false>(oh);
     }
@@ -917,16 +940,16 @@ __device__ __forceinline__ void eval_pair(const Params &d, const MemRef<kShared>
         uint4 xv[W], ohv[W];
         uint32_t ld4, x[kRowsPerLane][W], oh[kRowsPerLane][W];
         load_tile<W, kShared, kOh>(m_bits, m_leader, d.Ppad, ps, prow, lane, u + 1, xv, ohv, ld4);
-        tile_pass_a<Cfg, kShared, kChk, kOh>(d, m_obj, lane, u + 1, viol, obj, xv, ohv, ld4, x, oh);
-        tile_pass_b<Cfg, kShared, kChk>(d, m_obj, lane, u + 1, obj, xv, ld4);
+        tile_pass_a<Cfg, kShared, kChk, kOh, kObjShared>(d, m_obj, lane, u + 1, viol, obj, xv, ohv, ld4, x, oh);
+        tile_pass_b<Cfg, kShared, kChk, kObjShared>(d, m_obj, lane, u + 1, obj, xv, ld4);
         rc.template push_half<true>(x);
         lc.template push_half<true>(oh);
     }
 }
 
-template <class Cfg, bool kShared, bool kChk>
+template <class Cfg, bool kShared, bool kChk, bool kObjShared = kShared>
 __device__ __forceinline__ void eval_single(const Params &d, const MemRef<kShared> &m_bits,
-                                            const MemRef<kShared> &m_leader, const MemRef<kShared> &m_obj,
+                                            const MemRef<kShared> &m_leader, const MemRef<kObjShared> &m_obj,
                                             const PatchSet &ps, const uint32_t *prow, int lane, int u,
                                             ColCounter<Cfg::W, Cfg::NPH> &rc, ColCounter<Cfg::W, Cfg::NPH> &lc,
                                             int &viol, int &obj)
@@ -935,22 +958,24 @@ __device__ __forceinline__ void eval_single(const Params &d, const MemRef<kShare
     uint4 xv[W], ohv[W];
     uint32_t ld4, x[kRowsPerLane][W], oh[kRowsPerLane][W];
     load_tile<W, kShared, false>(m_bits, m_leader, d.Ppad, ps, prow, lane, u, xv, ohv, ld4);
-    tile_pass_a<Cfg, kShared, kChk, false>(d, m_obj, lane, u, viol, obj, xv, ohv, ld4, x, oh);
-    tile_pass_b<Cfg, kShared, kChk>(d, m_obj, lane, u, obj, xv, ld4);
+    tile_pass_a<Cfg, kShared, kChk, false, kObjShared>(d, m_obj, lane, u, viol, obj, xv, ohv, ld4, x, oh);
+    tile_pass_b<Cfg, kShared, kChk, kObjShared>(d, m_obj, lane, u, obj, xv, ld4);
     rc.push4(x[0], x[1], x[2], x[3]);
     lc.push4(oh[0], oh[1], oh[2], oh[3]);
 }
 
-// Evaluates candidate = base + patches.  kShared: base/weights are in shared memory.
+// Evaluates candidate = base + patches.  kShared: the base is in shared memory; kObjShared: the objective
+// table is (wide-row delta kernels keep it in HBM / L2: it is only read for the base's own evaluation).
 // Outputs (same value in every lane): total violation amount and objective.
-template <class Cfg, bool kShared>
+template <class Cfg, bool kShared, bool kObjShared = kShared>
 __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uint8_t *leader,
                                const uint32_t *objT, const Consts *cs, const PatchSet &ps,
                                const uint32_t *prow, int lane, int &viol_out, int &obj_out)
 {
     constexpr int W = Cfg::W, NPH = Cfg::NPH;
     constexpr bool kOh = kShared && has_oh_plane<Cfg>();
-    const MemRef<kShared> m_bits(bitsT), m_leader(leader), m_obj(objT);
+    const MemRef<kShared> m_bits(bitsT), m_leader(leader);
+    const MemRef<kObjShared> m_obj(objT);
     int viol = 0, obj = 0;
     const int ntiles = (d.P + kTileRows - 1) / kTileRows;
     const int nfull = d.P / kTileRows;                   // tiles made of real rows only
@@ -961,18 +986,18 @@ __device__ void eval_candidate(const Params &d, const uint32_t *bitsT, const uin
         int u = 0;
 #pragma unroll 1
         for (; u + 2 <= nfull; u += 2)
-            eval_pair<Cfg, kShared, false, kOh>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
+            eval_pair<Cfg, kShared, false, kOh, kObjShared>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
 #pragma unroll 1
         for (; u < ntiles; u += 2)
-            eval_pair<Cfg, kShared, true, kOh>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
+            eval_pair<Cfg, kShared, true, kOh, kObjShared>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
     } else {
         // wide rows: one tile per iteration (the two-tile block would not fit the register file)
         int u = 0;
 #pragma unroll 1
         for (; u < nfull; ++u)
-            eval_single<Cfg, kShared, false>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
+            eval_single<Cfg, kShared, false, kObjShared>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
         if (u < ntiles)
-            eval_single<Cfg, kShared, true>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
+            eval_single<Cfg, kShared, true, kObjShared>(d, m_bits, m_leader, m_obj, ps, prow, lane, u, rc, lc, viol, obj);
     }
 
     constexpr int NP0 = 3 + NPH;
@@ -1092,9 +1117,9 @@ template <int W> __device__ __forceinline__ int lone_slot(const uint32_t (&m)[W]
 // cnt / lcnt: replica and (valid) leader count per slot of the BASE, rc: replica count per rack,
 // base_viol / base_obj: the base's own evaluation.  Every patched partition differs from the base
 // by at most one replica move and/or a leader change (MODEL 5: an op never revisits a partition).
-template <class Cfg>
+template <class Cfg, bool kObjShared = true>
 __device__ __forceinline__ void delta_eval(const Params &d, const uint32_t *s_bits, const uint8_t *s_leader,
-                                           const MemRef<true> &objT, const Consts *cs, const PatchSet &ps,
+                                           const MemRef<kObjShared> &objT, const Consts *cs, const PatchSet &ps,
                                            const uint32_t (&rows)[kMaxOps][Cfg::W], const int *cnt, const int *lcnt,
                                            const int *rc, int base_viol, int base_obj, int &viol, int &obj)
 {
@@ -1118,8 +1143,8 @@ __device__ __forceinline__ void delta_eval(const Params &d, const uint32_t *s_bi
             }
             const uint32_t ldo = s_leader[p], ldn = ps.ld[i];
             int rvo, roo, rvn, ron;
-            row_eval<Cfg, true>(d, objT, p, xo, ldo, rvo, roo);
-            row_eval<Cfg, true>(d, objT, p, xn, ldn, rvn, ron);
+            row_eval<Cfg, kObjShared>(d, objT, p, xo, ldo, rvo, roo);
+            row_eval<Cfg, kObjShared>(d, objT, p, xn, ldn, rvn, ron);
             viol += rvn - rvo;
             obj += ron - roo;
             es[2 * i] = lone_slot<W>(rem); ev[2 * i] = -1;

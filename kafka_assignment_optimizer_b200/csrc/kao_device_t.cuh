@@ -69,8 +69,9 @@ template <int W> __device__ __forceinline__ int row_terms_hi1_s8(const uint32_t 
     return abs(n - RF) + (n - nz);
 }
 
-__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | ((a | b) & c); }
-
+#if defined(KAO_HOST_EMU)
+inline long long emu_rows_charged_one_by_one = 0;
+#endif
 // ------------------------------------------------------------------------------------------
 // rows: C1 + C7 of every partition that is not patched, 32 partitions per lane
 // ------------------------------------------------------------------------------------------
@@ -102,10 +103,12 @@ __device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, const Mem
             uint32_t x[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) x[k] = T.ld32((uint32_t)((b * 8 + k) * nW + tk[k]) * 4u);
-            const uint32_t a1 = x[0] | x[1] | x[2], a2 = x[3] | x[4] | x[5], a3 = x[6] | x[7];
-            dup |= maj3(x[0], x[1], x[2]) | maj3(x[3], x[4], x[5]);
-            dup |= (x[6] & x[7]) | maj3(a1, a2, a3);
-            any[b] = a1 | a2 | a3;
+            // 10 LOP3 per field: any = OR of the 8 words; dup = two of them share a bit (inside a triple, the
+            // pair, or across the three groups)
+            const uint32_t a1 = lop3<0xFE>(x[0], x[1], x[2]), a2 = lop3<0xFE>(x[3], x[4], x[5]), a3 = x[6] | x[7];
+            dup = lop3<0xFE>(dup, lop3<0xE8>(x[0], x[1], x[2]), lop3<0xE8>(x[3], x[4], x[5]));
+            dup = lop3<0xEA>(x[6], x[7], dup) | lop3<0xE8>(a1, a2, a3);
+            any[b] = lop3<0xFE>(a1, a2, a3);
         }
         // z = number of rack fields in use, bit-sliced (0..8); without a doubled field z is also the replica count
         uint32_t z1, z2, z4 = 0, z8 = 0;
@@ -132,6 +135,9 @@ __device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, const Mem
         uint32_t bad = dup | (z1 ^ rf0) | (z2 ^ rf1) | (z4 ^ rf2) | (z8 ^ rf3);
         bad &= valid;
         for (uint32_t m = bad; m; m &= m - 1) {     // rare: the exact terms of that row, from the row-major base
+#if defined(KAO_HOST_EMU)
+            ++emu_rows_charged_one_by_one;          // tests/emu: a well-formed row must never come here
+#endif
             const int p = 32 * w + __ffs(m) - 1;
             uint32_t x[W];
 #pragma unroll

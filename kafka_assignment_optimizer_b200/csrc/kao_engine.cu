@@ -26,6 +26,7 @@
 KAO_FOR_CFGS_NARROW(KAO_DECL_FULL, 1, 5) KAO_FOR_CFGS_NARROW(KAO_DECL_FULL, 2, 5)
 KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 4, 5) KAO_FOR_CFGS_WIDE(KAO_DECL_FULL, 8, 5)
 KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 1, 5) KAO_FOR_CFGS_NARROW(KAO_DECL_DELTA, 2, 5)
+KAO_FOR_CFGS_WIDE(KAO_DECL_DELTA, 4, 5) KAO_FOR_CFGS_WIDE(KAO_DECL_DELTA, 8, 5)
 // column-major evaluator (kao_device_t.cuh), every built schedule
 #define KAO_DECL_T(S, POP, T)                                                  \
     extern template __global__ void KAO_PERSISTENT_KERNEL_T(1, 0, S, POP, T);  \
@@ -191,7 +192,7 @@ struct kao_handle {
     SmemPlan plan_t{};
     // schedule of the column-major evaluator (kao_set_schedule): barrier form, popcount compression per
     // stream, threads per CTA.  Same results whatever the schedule.
-    int sch_sync = KAO_SCHEDULE_DEFAULT_SYNC, sch_pop = KAO_SCHEDULE_DEFAULT_POP, sch_threads = KAO_THREADS;
+    int sch_sync = KAO_SCHEDULE_DEFAULT_SYNC, sch_pop = KAO_SCHEDULE_DEFAULT_POP, sch_threads = KAO_SCHEDULE_DEFAULT_THREADS;
     // device buffers
     uint32_t *d_bits = nullptr; uint8_t *d_leader = nullptr; uint32_t *d_sw = nullptr;
     uint32_t *d_dense = nullptr; uint32_t *d_planes = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
@@ -260,9 +261,7 @@ struct LaunchRound {
 template <bool kDelta> struct LaunchPersistent {
     template <class Cfg> cudaError_t run(kao_handle *h, const PersistArgs &a) const
     {
-        if constexpr (kDelta && Cfg::W > 2) {
-            return cudaErrorNotSupported;                       // delta mode: rows of up to 64 slots
-        } else {
+        {
             constexpr int T = kDelta ? KAO_THREADS_DELTA : cfg_threads<Cfg>();
             auto kern = search_persistent_kernel<Cfg, T, kDelta>;
             static bool done[64] = {};
@@ -270,7 +269,9 @@ template <bool kDelta> struct LaunchPersistent {
             if (e != cudaSuccess) return e;
             Params prm = h->prm;
             // the column-major plan depends on the warps per CTA of the schedule (per-warp scratch)
-            SmemPlan plan = Cfg::kTrans ? make_plan(Cfg::W, h->hm.Ppad, T / 32, (kTPlanes + kTMaskPlanes) * Cfg::W, h->hm.P, h->hm.RF, false) : h->plan;
+            SmemPlan plan = Cfg::kTrans ? make_plan_t(Cfg::W, h->hm.Ppad, T, h->hm.P, h->hm.RF)
+                            : (kDelta && Cfg::W > 2) ? make_plan_delta_wide(Cfg::W, h->hm.Ppad, T, h->hm.P, h->hm.RF) : h->plan;
+            if (plan.total > 227u * 1024u) return cudaErrorInvalidConfiguration;
             uint64_t seed = a.seed; uint32_t fr = a.first_round, rounds = a.rounds, rs = a.round_size;
             unsigned long long *keys = a.d_keys, *all = a.all_keys; unsigned int *bar = a.d_bar;
             P2P pp = a.pp;
@@ -411,8 +412,9 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     // column-major evaluator: 8-slot rack fields, C7 = "at most one replica per rack", three mask planes;
     // its five transposed planes and the row-major mask planes ((5 + 3) * W words per partition) take
     // the place of the objective table.  It is the default full evaluator wherever it applies.
-    h->plan_t = make_plan(W, Ppad, KAO_THREADS / 32, (kTPlanes + kTMaskPlanes) * W, m.P, m.RF, false);
-    h->trans_ok = W <= 2 && m.hi1 && m.log2S == 3 && h->hm.nplanes == 3 && h->plan_t.total <= 227u * 1024u;
+    h->plan_t = make_plan_t(W, Ppad, KAO_THREADS, m.P, m.RF);
+    h->trans_ok = W <= 2 && m.hi1 && m.log2S == 3 && h->hm.nplanes == 3 &&
+                  column_major_fits(W, Ppad, KAO_THREADS, m.P, m.RF);     // incl. the inverted lists of its per-thread generator
     if (h->trans_ok) h->evaluator = KAO_EVAL_COLUMN_MAJOR;
     if (const char *env = std::getenv("KAO_EVALUATOR"))       // "row" forces the row-major evaluator (measurements)
         if (std::strcmp(env, "row") == 0) h->evaluator = KAO_EVAL_ROW_MAJOR;
@@ -528,6 +530,12 @@ static int get_base_impl(kao_handle *h, int32_t *replicas, int64_t *violation, i
 }
 
 static bool check_round_args(uint32_t round_size) { return round_size >= 2 && round_size <= KAO_MAX_ROUND_SIZE; }
+// delta evaluation keeps the base and the per-round tables in shared memory (rows wider than 64 slots: without the objective table)
+static bool delta_fits(const kao_handle *h)
+{
+    if (h->hm.W <= 2) return true;                              // the session's own plan (validated at kao_create)
+    return make_plan_delta_wide(h->hm.W, h->hm.Ppad, KAO_THREADS_DELTA, h->hm.P, h->hm.RF).total <= 227u * 1024u;
+}
 
 static int reserve_keys(kao_handle *h, uint32_t rounds)
 {
@@ -559,7 +567,7 @@ static int search_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint3
                        uint32_t round_size, uint64_t *round_keys, double *device_ms, bool delta)
 {
     if (!h) return fail(KAO_E_ARG, "null handle");
-    if (delta && h->hm.W > 2) return fail(KAO_E_ARG, "delta evaluation supports rows of up to 64 broker slots");
+    if (delta && !delta_fits(h)) return fail(KAO_E_ARG, "delta evaluation: the base and its per-round tables do not fit in shared memory");
     if (!check_round_args(round_size)) return fail(KAO_E_ARG, "round_size must be 2..2^24");
     if (rounds > KAO_MAX_ROUNDS) return fail(KAO_E_ARG, "rounds must not exceed KAO_MAX_ROUNDS (2^20) per call");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -607,7 +615,7 @@ static int candidate_keys_impl(kao_handle *h, uint64_t seed, uint32_t round, uin
     if (!h || !keys) return fail(KAO_E_ARG, "null argument");
     if (!check_round_args(round_size) || idx_begin > round_size || count > round_size - idx_begin)
         return fail(KAO_E_ARG, "bad index range");
-    if (delta && h->hm.W > 2) return fail(KAO_E_ARG, "delta evaluation supports rows of up to 64 broker slots");
+    if (delta && !delta_fits(h)) return fail(KAO_E_ARG, "delta evaluation: the base and its per-round tables do not fit in shared memory");
     if (count == 0) return KAO_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     DevTmp<unsigned long long> all;
@@ -678,7 +686,7 @@ static int sharded_impl(kao_handle *h, uint64_t seed, uint32_t first_round, uint
                         uint32_t round_size, uint64_t *round_keys, double *device_ms, bool delta)
 {
     if (!h) return fail(KAO_E_ARG, "null handle");
-    if (delta && h->hm.W > 2) return fail(KAO_E_ARG, "delta evaluation supports rows of up to 64 broker slots");
+    if (delta && !delta_fits(h)) return fail(KAO_E_ARG, "delta evaluation: the base and its per-round tables do not fit in shared memory");
     if (!check_round_args(round_size)) return fail(KAO_E_ARG, "round_size must be 2..2^24");
     if (rounds > KAO_MAX_ROUNDS) return fail(KAO_E_ARG, "rounds must not exceed KAO_MAX_ROUNDS (2^20) per call");
     if (h->p2p_world < 2 || !h->peer_mail[h->p2p_world - 1]) return fail(KAO_E_STATE, "kao_p2p_connect first");
@@ -1013,6 +1021,15 @@ extern "C" int kao_set_schedule(kao_handle *h, int32_t sync, int32_t pop, int32_
         h->sch_sync = sync; h->sch_pop = pop; h->sch_threads = threads;
         return KAO_OK;
     });
+}
+extern "C" int kao_get_evaluator(kao_handle *h, int32_t *evaluator, int32_t *sync, int32_t *pop, int32_t *threads)
+{
+    if (!h) return fail(KAO_E_ARG, "null handle");
+    if (evaluator) *evaluator = h->evaluator;
+    if (sync) *sync = h->sch_sync;
+    if (pop) *pop = h->sch_pop;
+    if (threads) *threads = h->sch_threads;
+    return KAO_OK;
 }
 extern "C" int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement)
 {

@@ -22,10 +22,11 @@
     template __global__ void KAO_PERSISTENT_KERNEL_T(KAO_INST_W, 32, S, POP, T);
 KAO_FOR_SCHEDULES(KAO_INST_T)
 #elif KAO_INST_MODE == 1
-#if KAO_INST_W > 2
-#error "delta evaluation: rows of up to 64 slots"
-#endif
+#if KAO_INST_W <= 2
 KAO_FOR_CFGS_NARROW(KAO_INST_DELTA_K, KAO_INST_W, 5)
+#else
+KAO_FOR_CFGS_WIDE(KAO_INST_DELTA_K, KAO_INST_W, 5)
+#endif
 #elif KAO_INST_W <= 2
 KAO_FOR_CFGS_NARROW(KAO_INST_FULL, KAO_INST_W, 5)
 #else

@@ -287,6 +287,93 @@ __device__ __forceinline__ bool spin_filled(const unsigned long long *p, unsigne
     return true;
 }
 
+// Per-round tables of the base for the per-THREAD generator (and the delta evaluator): replica / valid-leader
+// counts per slot, replicas per rack, and per-slot inverted lists (ascending partitions that hold a replica
+// on / are led from the slot) so that a thread finds "the first holder of slot s from partition q on" by a
+// binary search instead of a scan.  All in shared memory at plan.off_totals / plan.off_inv; rebuilt by the
+// whole CTA whenever the base has changed.
+struct RoundTables {
+    int *cnt, *lcnt, *rc, *base, *ledn, *hoff, *loff, *inv;
+    uint16_t *hold, *led;
+};
+__device__ __forceinline__ RoundTables round_tables(uint8_t *smem, const SmemPlan &plan)
+{
+    RoundTables r;
+    r.cnt = reinterpret_cast<int *>(smem + plan.off_totals);
+    r.lcnt = r.cnt + 256; r.rc = r.cnt + 512; r.base = r.cnt + 544;
+    r.ledn = r.cnt + 548; r.hoff = r.cnt + 804; r.loff = r.cnt + 1062; r.inv = r.cnt + 1320;
+    r.hold = reinterpret_cast<uint16_t *>(smem + plan.off_inv);
+    r.led = r.hold + plan.cap_hold;
+    return r;
+}
+template <int W, int THREADS>
+__device__ __forceinline__ void build_round_tables(const RoundTables &rt, const SmemPlan &plan, const Params &d,
+                                                   const uint32_t *s_bits, const uint8_t *s_leader)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 804; i += THREADS) if (i < 544 || i >= 548) rt.cnt[i] = 0;   // keep rt.base
+    __syncthreads();
+    for (int p = tid; p < d.P; p += THREADS) {
+        const int ld = s_leader[p];
+        bool ok = false;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const uint32_t xw = s_bits[(size_t)w * d.Ppad + p];
+            for (uint32_t m = xw; m; m &= m - 1) {
+                const int sl = w * 32 + __ffs(m) - 1;
+                atomicAdd(&rt.cnt[sl], 1);
+                atomicAdd(&rt.rc[sl >> d.log2S], 1);
+            }
+            if ((ld >> 5) == w) ok = (xw >> (ld & 31)) & 1u;
+        }
+        if (ok) atomicAdd(&rt.lcnt[ld], 1);
+        atomicAdd(&rt.ledn[ld], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int a = 0, b = 0;
+        for (int sl = 0; sl < W * 32; ++sl) { rt.hoff[sl] = a; a += rt.cnt[sl]; rt.loff[sl] = b; b += rt.ledn[sl]; }
+        rt.hoff[W * 32] = a; rt.loff[W * 32] = b;
+        *rt.inv = (plan.cap_hold > 0 && a <= (int)plan.cap_hold && b <= (int)plan.cap_led) ? 1 : 0;
+    }
+    __syncthreads();
+    if (*rt.inv) {
+        // THREADS / slots segments of rows per slot: count, then write in place (ascending order)
+        constexpr int NSL = W * 32, NSEG = THREADS / NSL;
+        static_assert(THREADS % NSL == 0, "one thread per (segment, slot)");
+        int *s_segc = reinterpret_cast<int *>(rt.led + plan.cap_led + 8);       // [2][NSEG][NSL]
+        const int slot = tid % NSL, seg = tid / NSL;
+        const int chunk = (d.P + NSEG - 1) / NSEG, p_lo = seg * chunk, p_hi = min(d.P, p_lo + chunk);
+        const uint32_t *col = s_bits + (size_t)(slot >> 5) * d.Ppad;
+        const uint32_t bit = 1u << (slot & 31);
+        int hc = 0, lc = 0;
+        for (int p = p_lo; p < p_hi; ++p) {
+            hc += (col[p] & bit) ? 1 : 0;
+            lc += ((int)s_leader[p] == slot) ? 1 : 0;
+        }
+        s_segc[seg * NSL + slot] = hc;
+        s_segc[(NSEG + seg) * NSL + slot] = lc;
+        __syncthreads();
+        int hpos = rt.hoff[slot], lpos = rt.loff[slot];
+        for (int g = 0; g < seg; ++g) { hpos += s_segc[g * NSL + slot]; lpos += s_segc[(NSEG + g) * NSL + slot]; }
+        for (int p = p_lo; p < p_hi; ++p) {
+            if (col[p] & bit) rt.hold[hpos++] = (uint16_t)p;
+            if ((int)s_leader[p] == slot) rt.led[lpos++] = (uint16_t)p;
+        }
+    }
+    __syncthreads();
+}
+template <int W>
+__device__ __forceinline__ void bind_tables(Gen<W, true> &tg, const RoundTables &rt)
+{
+    tg.inv_ok = *rt.inv != 0; tg.hoff = rt.hoff; tg.loff = rt.loff; tg.hold = rt.hold; tg.led = rt.led;
+}
+
+// Column-major kernels: the 32 lanes of a warp generate 32 candidates at once (one each, per-thread
+// generator) and park them in the warp's scratch; the warp then evaluates them one after the other.
+// Scratch per candidate: 3 partitions, (leader slots | count << 24), 3 x W row words (16-byte aligned).
+template <int W> __host__ __device__ constexpr int batch_stride() { return batch_stride_words(W); }
+
 // All rounds of a search in ONE launch (cooperative: one CTA per SM, all co-resident).  The base
 // and the tables stay in shared memory for the whole search; per round every CTA evaluates its
 // share of the candidates, min-reduces into keys[t], meets the other CTAs at a grid barrier, then
@@ -318,7 +405,8 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     constexpr int kWarps = THREADS / 32;
     constexpr int W = Cfg::W;
     const uint32_t *g_obj = Cfg::kObj > 0 ? d.planesT : d.swT;
-    const uint32_t obj_words = Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries;
+    constexpr bool kObjShared = !(kDelta && W > 2);    // wide-row delta kernels read the objective table from HBM / L2
+    const uint32_t obj_words = !kObjShared ? 0u : (Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries);
     // column-major evaluator: the row-major mask planes sit behind the five transposed planes
     uint32_t *s_obj = Cfg::kTrans ? s_sw + (size_t)kTPlanes * W * d.Ppad : s_sw;
 
@@ -340,7 +428,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     Gen<W, false, Cfg::kTrans> gen;        // column-major kernels: compact generator code (same candidates)
     uint32_t no_rows[kMaxOps][W];          // warp mode keeps patched rows in shared memory instead
     gen.bitsT = s_bits; gen.leader = s_leader; gen.cs = s_cs; gen.d = &d;
-    gen.prow = s_prow + warp * kMaxOps * W; gen.lane = lane;
+    gen.prow = s_prow + (size_t)warp * (Cfg::kTrans ? 32 * batch_stride<W>() : kMaxOps * W); gen.lane = lane;
     gen.D = s_D; gen.DL = s_DL;
 
     const uint32_t stride = gridDim.x * kWarps;
@@ -356,60 +444,9 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         unsigned long long best = kKeyNone;
         if constexpr (kDelta) {
             // ---- delta mode: totals of the base once per round, then one THREAD per candidate
-            int *s_cnt = reinterpret_cast<int *>(smem + plan.off_totals), *s_lcnt = s_cnt + 256, *s_rc = s_cnt + 512,
-                *s_base = s_cnt + 544;
-            int *s_ledn = s_cnt + 548, *s_hoff = s_cnt + 804, *s_loff = s_cnt + 870, *s_inv = s_cnt + 936;
-            uint16_t *s_hold = reinterpret_cast<uint16_t *>(smem + plan.off_inv), *s_led = s_hold + plan.cap_hold;
-            for (int i = tid; i < 804; i += THREADS) if (i < 544 || i >= 548) s_cnt[i] = 0;   // keep s_base
-            __syncthreads();
-            for (int p = tid; p < d.P; p += THREADS) {
-                const int ld = s_leader[p];
-                bool ok = false;
-#pragma unroll
-                for (int w = 0; w < W; ++w) {
-                    const uint32_t xw = s_bits[(size_t)w * d.Ppad + p];
-                    for (uint32_t m = xw; m; m &= m - 1) {
-                        const int sl = w * 32 + __ffs(m) - 1;
-                        atomicAdd(&s_cnt[sl], 1);
-                        atomicAdd(&s_rc[sl >> d.log2S], 1);
-                    }
-                    if ((ld >> 5) == w) ok = (xw >> (ld & 31)) & 1u;
-                }
-                if (ok) atomicAdd(&s_lcnt[ld], 1);
-                atomicAdd(&s_ledn[ld], 1);
-            }
-            __syncthreads();
-            // per-slot inverted lists of the base (ascending partitions) for the per-thread generator
-            if (tid == 0) {
-                int a = 0, b = 0;
-                for (int sl = 0; sl < W * 32; ++sl) { s_hoff[sl] = a; a += s_cnt[sl]; s_loff[sl] = b; b += s_ledn[sl]; }
-                s_hoff[W * 32] = a; s_loff[W * 32] = b;
-                *s_inv = (plan.cap_hold > 0 && a <= (int)plan.cap_hold && b <= (int)plan.cap_led) ? 1 : 0;
-            }
-            __syncthreads();
-            if (*s_inv) {
-                // THREADS / slots segments of rows per slot: count, then write in place (ascending order)
-                constexpr int NSL = W * 32, NSEG = THREADS / NSL;
-                int *s_segc = reinterpret_cast<int *>(s_led + plan.cap_led + 8);       // [2][NSEG][NSL]
-                const int slot = tid % NSL, seg = tid / NSL;
-                const int chunk = (d.P + NSEG - 1) / NSEG, p_lo = seg * chunk, p_hi = min(d.P, p_lo + chunk);
-                const uint32_t *col = s_bits + (size_t)(slot >> 5) * d.Ppad;
-                const uint32_t bit = 1u << (slot & 31);
-                int hc = 0, lc = 0;
-                for (int p = p_lo; p < p_hi; ++p) {
-                    hc += (col[p] & bit) ? 1 : 0;
-                    lc += ((int)s_leader[p] == slot) ? 1 : 0;
-                }
-                s_segc[seg * NSL + slot] = hc;
-                s_segc[(NSEG + seg) * NSL + slot] = lc;
-                __syncthreads();
-                int hpos = s_hoff[slot], lpos = s_loff[slot];
-                for (int g = 0; g < seg; ++g) { hpos += s_segc[g * NSL + slot]; lpos += s_segc[(NSEG + g) * NSL + slot]; }
-                for (int p = p_lo; p < p_hi; ++p) {
-                    if (col[p] & bit) s_hold[hpos++] = (uint16_t)p;
-                    if ((int)s_leader[p] == slot) s_led[lpos++] = (uint16_t)p;
-                }
-            }
+            const RoundTables rt = round_tables(smem, plan);
+            int *s_cnt = rt.cnt, *s_lcnt = rt.lcnt, *s_rc = rt.rc, *s_base = rt.base;
+            build_round_tables<W, THREADS>(rt, plan, d, s_bits, s_leader);
             // the base's own evaluation: a full pass in the first round, afterwards it IS the previous
             // winner's key (unless that key was saturated)
             if (warp == 0 && (t == 0 || s_base[2] == 0)) {
@@ -418,15 +455,15 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 #pragma unroll
                 for (int i = 0; i < kMaxOps; ++i) { id.p[i] = -1; id.ld[i] = 0xFF; }
                 int bv, bo;
-                eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, id, gen.prow, lane, bv, bo);
+                eval_candidate<Cfg, true, kObjShared>(d, s_bits, s_leader, kObjShared ? s_sw : g_obj, s_cs, id, gen.prow, lane, bv, bo);
                 if (lane == 0) { s_base[0] = bv; s_base[1] = bo; }
             }
             __syncthreads();
             Gen<W, true> tg;
             tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
             tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
-            tg.inv_ok = *s_inv != 0; tg.hoff = s_hoff; tg.loff = s_loff; tg.hold = s_hold; tg.led = s_led;
-            const MemRef<true> m_obj(s_sw);
+            bind_tables<W>(tg, rt);
+            const MemRef<kObjShared> m_obj(kObjShared ? s_sw : g_obj);
             const int base_viol = s_base[0], base_obj = s_base[1];
             const uint32_t tstride = gridDim.x * THREADS;
             for (uint32_t idx = pp.idx_lo + blockIdx.x * THREADS + tid; idx < pp.idx_hi; idx += tstride) {
@@ -434,7 +471,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 uint32_t rows[kMaxOps][W];
                 tg.run(seed, round, idx, round_size, ps, rows);
                 int viol, obj;
-                delta_eval<Cfg>(d, s_bits, s_leader, m_obj, s_cs, ps, rows, s_cnt, s_lcnt, s_rc, base_viol, base_obj, viol, obj);
+                delta_eval<Cfg, kObjShared>(d, s_bits, s_leader, m_obj, s_cs, ps, rows, s_cnt, s_lcnt, s_rc, base_viol, base_obj, viol, obj);
                 const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
                 if (all_keys) all_keys[idx - pp.idx_lo] = key;
                 best = key < best ? key : best;
@@ -445,6 +482,60 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 best = w < best ? w : best;
             }
             if (all_keys) return;                                   // key dump only: the base stays as it is
+        } else if constexpr (Cfg::kTrans) {
+            // ---- column-major evaluator: candidates are generated 32 at a time, one per LANE (per-thread
+            // generator over the round's inverted lists), then evaluated in full one after the other by the warp
+            const RoundTables rt = round_tables(smem, plan);
+            build_round_tables<W, THREADS>(rt, plan, d, s_bits, s_leader);
+            Gen<W, true> tg;
+            tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
+            tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
+            bind_tables<W>(tg, rt);
+            constexpr int BS = batch_stride<W>();
+            uint32_t *batch = s_prow + (size_t)warp * 32 * BS;
+            for (uint32_t it0 = 0; it0 < iters; it0 += 32) {
+                {
+                    const uint32_t idx = first + warp + (it0 + lane) * stride;
+                    PatchSet ps;
+                    uint32_t rows[kMaxOps][W];
+                    ps.n = 0;
+#pragma unroll
+                    for (int i = 0; i < kMaxOps; ++i) {
+                        ps.p[i] = -1; ps.ld[i] = 0xFF;
+#pragma unroll
+                        for (int w = 0; w < W; ++w) rows[i][w] = 0;
+                    }
+                    if (it0 + lane < iters && idx < pp.idx_hi) tg.run(seed, round, idx, round_size, ps, rows);
+                    uint32_t *mine = batch + lane * BS;
+                    mine[0] = (uint32_t)ps.p[0]; mine[1] = (uint32_t)ps.p[1]; mine[2] = (uint32_t)ps.p[2];
+                    mine[3] = (ps.ld[0] & 0xFFu) | ((ps.ld[1] & 0xFFu) << 8) | ((ps.ld[2] & 0xFFu) << 16) | ((uint32_t)ps.n << 24);
+#pragma unroll
+                    for (int i = 0; i < kMaxOps; ++i)
+#pragma unroll
+                        for (int w = 0; w < W; ++w) mine[4 + i * W + w] = rows[i][w];
+                }
+                __syncwarp();
+                const uint32_t nb = iters - it0 < 32u ? iters - it0 : 32u;
+                for (uint32_t j = 0; j < nb; ++j) {
+                    const uint32_t idx = first + warp + (it0 + j) * stride;
+                    if constexpr (Cfg::kSync == 0) __syncthreads();          // all warps walk the evaluator together
+                    if (idx < pp.idx_hi) {
+                        const uint32_t *slot = batch + j * BS;
+                        const uint4 hdr = *reinterpret_cast<const uint4 *>(slot);
+                        PatchSet ps;
+                        ps.p[0] = (int)hdr.x; ps.p[1] = (int)hdr.y; ps.p[2] = (int)hdr.z;
+                        ps.ld[0] = hdr.w & 0xFFu; ps.ld[1] = (hdr.w >> 8) & 0xFFu; ps.ld[2] = (hdr.w >> 16) & 0xFFu;
+                        ps.n = (int)(hdr.w >> 24);
+                        int viol, obj;
+                        eval_candidate_t<Cfg, true>(d, s_sw, d.Ppad >> 5, s_bits, s_obj, s_cs, ps, slot + 4, lane, viol, obj);
+                        const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
+                        if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = key;
+                        best = key < best ? key : best;
+                    }
+                }
+                __syncwarp();                                               // the batch is consumed before it is refilled
+            }
+            if (all_keys) return;                                           // key dump only: the base stays as it is
         } else {
         for (uint32_t it = 0; it < iters; ++it) {
             const uint32_t idx = first + warp + it * stride;
@@ -454,31 +545,14 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 #pragma unroll
             for (int i = 0; i < kMaxOps; ++i) { ps.p[i] = -1; ps.ld[i] = 0xFF; }
             if (live) gen.run(seed, round, idx, round_size, ps, no_rows);
-            if constexpr (Cfg::kTrans) {
-                // schedules of the column-major evaluator: who meets before an evaluation (the patched
-                // rows were written by lane 0 of this warp, so a warp-level sync is enough for correctness)
-                if constexpr (Cfg::kSync == 0) __syncthreads();
-                else __syncwarp();
-            } else {
-                __syncthreads();
-            }
+            __syncthreads();
             if (live) {
                 int viol, obj;
-                if constexpr (Cfg::kTrans) {
-                    eval_candidate_t<Cfg, true>(d, s_sw, d.Ppad >> 5, s_bits, s_obj, s_cs, ps, gen.prow, lane, viol, obj);
-                } else {
-                    eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
-                }
+                eval_candidate<Cfg, true>(d, s_bits, s_leader, s_sw, s_cs, ps, gen.prow, lane, viol, obj);
                 const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
-                if constexpr (Cfg::kTrans) {
-                    if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = key;
-                }
                 best = key < best ? key : best;
             }
             __syncwarp();
-        }
-        if constexpr (Cfg::kTrans) {
-            if (all_keys) return;                                   // key dump only: the base stays as it is
         }
         }
         if (lane == 0) s_red[warp] = best;
@@ -564,7 +638,27 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             }
             if (k != kKeyNone) {
                 PatchSet ps;
-                gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps, no_rows);
+                if constexpr (Cfg::kTrans) {
+                    // every lane re-materialises the same winner with the per-thread generator; lane 0 parks its rows
+                    Gen<W, true> tg;
+                    tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
+                    tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
+                    bind_tables<W>(tg, round_tables(smem, plan));
+                    uint32_t rows[kMaxOps][W];
+#pragma unroll
+                    for (int i = 0; i < kMaxOps; ++i)
+#pragma unroll
+                        for (int w = 0; w < W; ++w) rows[i][w] = 0;
+                    tg.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps, rows);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < kMaxOps; ++i)
+#pragma unroll
+                            for (int w = 0; w < W; ++w) gen.prow[i * W + w] = rows[i][w];
+                    }
+                } else {
+                    gen.run(seed, round, (uint32_t)(k & kIdxMask), round_size, ps, no_rows);
+                }
                 __syncwarp();
                 if constexpr (Cfg::kTrans) {                        // every lane rewrites its own slots' words
 #pragma unroll
@@ -620,9 +714,10 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 // Column-major kernels: X(sync, pop, threads) for every built schedule (kao_set_schedule); each is
 // instantiated for W = 1, 2 and for 32 partition words (compile-time offsets) / any word count.
 #define KAO_FOR_SCHEDULES(X) \
-    X(1, 0x11111, 768) X(0, 0x11111, 768) X(1, 0x11122, 768) X(1, 0x11133, 768) X(1, 0x22233, 768) X(1, 0x11133, 512)
+    X(1, 0x11133, 512) X(1, 0x11111, 512) X(1, 0x11122, 512) X(1, 0x22233, 512) X(1, 0x11123, 512) X(1, 0x33333, 512) X(1, 0x11133, 640) X(1, 0x11111, 640) X(1, 0x11133, 768) X(1, 0x11111, 768) X(0, 0x11133, 512) X(0, 0x11133, 768)
 #define KAO_SCHEDULE_DEFAULT_SYNC 1
-#define KAO_SCHEDULE_DEFAULT_POP 0x11111
+#define KAO_SCHEDULE_DEFAULT_POP 0x11133
+#define KAO_SCHEDULE_DEFAULT_THREADS 512
 #define KAO_PERSISTENT_KERNEL_T(W, NW, S, POP, T)                                                            \
     search_persistent_kernel<EvalCfgT<W, NW, S, POP, T>, T, false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
                                                                     uint32_t, unsigned long long *, unsigned int *, P2P, \

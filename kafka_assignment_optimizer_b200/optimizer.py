@@ -276,8 +276,11 @@ class Session:
     def stats(self):
         n, w, s, dn = C.c_uint64(), C.c_int32(), C.c_int32(), C.c_int32()
         _check(self._lib.kao_stats(self._h, C.byref(n), C.byref(w), C.byref(s), C.byref(dn)))
+        ev, sy, pop, th = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _check(self._lib.kao_get_evaluator(self._h, C.byref(ev), C.byref(sy), C.byref(pop), C.byref(th)))
         return {"kernel_launches": n.value, "words_per_row": w.value, "slots": s.value,
-                "dense_weights": bool(dn.value)}
+                "dense_weights": bool(dn.value), "column_major": ev.value == 1,
+                "schedule": (sy.value, pop.value, th.value)}
 
 
 def solve(pb: Problem, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15,

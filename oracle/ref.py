@@ -22,10 +22,43 @@ class RefProblem(C.Structure):
                 ("ppr_lo", C.c_int32), ("ppr_hi", C.c_int32), ("cur", C.c_void_p)]
 
 
+CFLAGS = "-O3 -march=native -fopenmp -fPIC -Wall -Wextra -std=c11"      # the stated CPU baseline is not a strawman build
+
+
+def _host_stamp() -> str:
+    """-march=native code is only valid on the CPU it was built on: the library is rebuilt when the host's
+    instruction-set flags (or the build flags) differ from the ones it was built with."""
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for l in f:
+                if l.startswith("flags"):
+                    flags = " ".join(sorted(l.split(":", 1)[1].split()))
+                    break
+    except OSError:
+        pass
+    import hashlib
+
+    return hashlib.sha256((CFLAGS + "|" + flags).encode()).hexdigest()
+
+
+def build_flags() -> str:
+    return "gcc " + CFLAGS
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "kao_ref.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
+    stamp_path = _SO + ".stamp"
+    stamp = _host_stamp()
+    try:
+        with open(stamp_path) as f:
+            same_host = f.read().strip() == stamp
+    except OSError:
+        same_host = False
+    if force or not same_host or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "CFLAGS=" + CFLAGS])
+        with open(stamp_path, "w") as f:
+            f.write(stamp)
     return _SO
 
 

@@ -20,6 +20,7 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.kao_emu_create.restype = C.c_void_p
         _lib.kao_emu_last_error.restype = C.c_char_p
+        _lib.kao_emu_rows_charged_one_by_one.restype = C.c_longlong
     return _lib
 
 
@@ -84,3 +85,8 @@ class EmuSession:
         lib().kao_emu_eval(self._h, C.c_void_p(reps.ctypes.data), C.c_int32(n), C.c_void_p(v.ctypes.data),
                            C.c_void_p(o.ctypes.data))
         return v, o
+
+
+def rows_charged_one_by_one():
+    """Rows the column-major evaluator sent through its exact one-by-one path since the last call."""
+    return int(lib().kao_emu_rows_charged_one_by_one())

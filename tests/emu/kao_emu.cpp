@@ -172,22 +172,17 @@ template <class Cfg> struct Run {
     static unsigned long long key_delta(Emu &e, uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size,
                                         const int *cnt, const int *lcnt, const int *rc, int base_viol, int base_obj)
     {
-        if constexpr (W <= 2) {
-            Gen<W, true> tg;
-            tg.bitsT = e.bits.data(); tg.leader = e.leader.data(); tg.cs = &e.cs; tg.d = &e.prm; tg.prow = nullptr; tg.lane = 0;
-            tg.D = e.D.data(); tg.DL = e.DL.data(); tg.nD = e.nD; tg.nL = e.nL;
-            const uint32_t *objT = Cfg::kObj > 0 ? e.prm.planesT : e.prm.swT;
-            const MemRef<true> m_obj(objT);
-            PatchSet ps;
-            uint32_t rows[kMaxOps][W];
-            tg.run(seed, round, idx, round_size, ps, rows);
-            int viol, obj;
-            delta_eval<Cfg>(e.prm, e.bits.data(), e.leader.data(), m_obj, &e.cs, ps, rows, cnt, lcnt, rc, base_viol, base_obj, viol, obj);
-            return pack_key(viol, obj, idx, e.prm.key_obj_bits);
-        } else {
-            (void)e; (void)seed; (void)round; (void)idx; (void)round_size; (void)cnt; (void)lcnt; (void)rc; (void)base_viol; (void)base_obj;
-            return kKeyNone;
-        }
+        Gen<W, true> tg;
+        tg.bitsT = e.bits.data(); tg.leader = e.leader.data(); tg.cs = &e.cs; tg.d = &e.prm; tg.prow = nullptr; tg.lane = 0;
+        tg.D = e.D.data(); tg.DL = e.DL.data(); tg.nD = e.nD; tg.nL = e.nL;
+        const uint32_t *objT = Cfg::kObj > 0 ? e.prm.planesT : e.prm.swT;
+        const MemRef<true> m_obj(objT);
+        PatchSet ps;
+        uint32_t rows[kMaxOps][W];
+        tg.run(seed, round, idx, round_size, ps, rows);
+        int viol, obj;
+        delta_eval<Cfg>(e.prm, e.bits.data(), e.leader.data(), m_obj, &e.cs, ps, rows, cnt, lcnt, rc, base_viol, base_obj, viol, obj);
+        return pack_key(viol, obj, idx, e.prm.key_obj_bits);
     }
 };
 
@@ -246,8 +241,7 @@ void *kao_emu_create(const kao_problem *pb)
     e->oh = m.W <= 2 && e->obj > 0;
     // kao_set_evaluator: the column-major evaluator covers 8-slot rack fields with C7 = "at most one
     // replica per rack" and three mask planes
-    e->trans_ok = m.W <= 2 && m.hi1 && m.log2S == 3 && m.nplanes == 3 &&
-                  make_plan(m.W, m.Ppad, threads / 32, (kTPlanes + kTMaskPlanes) * m.W, m.P, m.RF, false).total <= 227u * 1024u;
+    e->trans_ok = m.W <= 2 && m.hi1 && m.log2S == 3 && m.nplanes == 3 && column_major_fits(m.W, m.Ppad, threads, m.P, m.RF);
     e->nW = m.Ppad / 32;
     fill_consts(m, e->cs);
     Params &p = e->prm;
@@ -281,6 +275,14 @@ int kao_emu_set_evaluator(void *h, int32_t mode)
 }
 
 void kao_emu_destroy(void *h) { delete static_cast<Emu *>(h); }
+
+// rows the column-major evaluator charged one by one (its slow, exact path) since the last call
+long long kao_emu_rows_charged_one_by_one(void)
+{
+    const long long n = emu_rows_charged_one_by_one;
+    emu_rows_charged_one_by_one = 0;
+    return n;
+}
 
 // 4 ints: words per row, counter planes above the fours (NPH), rack form, objective planes
 void kao_emu_config(void *h, int32_t *out)
@@ -342,7 +344,6 @@ int kao_emu_candidate_keys_delta(void *h, uint64_t seed, uint32_t round, uint32_
 {
     Emu &e = *static_cast<Emu *>(h);
     const HostModel &m = e.hm;
-    if (m.W > 2) { g_err = "delta evaluation: rows of up to 64 slots"; return -1; }
     std::vector<int> cnt(256, 0), lcnt(256, 0), rc(32 + 4, 0);
     for (int p = 0; p < m.P; ++p) {
         const int ld = e.leader[p];

@@ -78,7 +78,7 @@ def test_device_code_vs_restatement(emu, ref_lib, name):
     sess.close()
 
 
-@pytest.mark.parametrize("name", ["readme", "cfg2_rm2", "cfg3_small", "s32", "rf_up", "dense_small", "rf1", "ragged"])
+@pytest.mark.parametrize("name", ["readme", "cfg2_rm2", "cfg3_small", "s32", "rf_up", "dense_small", "rf1", "ragged", "w4_s16", "w8_s16"])
 def test_delta_evaluator_gives_the_full_evaluators_keys(emu, name):
     """docs/MODEL.md §8: the per-thread generator + delta evaluator return the key of the full evaluation."""
     sess = emu.EmuSession(product(SHAPES[name]()))
@@ -116,8 +116,8 @@ def test_explicit_evaluation_matches_exact_model(emu, name):
 COLUMN_MAJOR = {
     "cfg2": SHAPES["cfg2"], "cfg2_rm2": SHAPES["cfg2_rm2"], "cfg3_small": SHAPES["cfg3_small"],
     "rf1": SHAPES["rf1"], "rf_down": SHAPES["rf_down"],
-    "w1_5300": lambda: m.synthetic_problem(5300, 32, 4, 3, remove=1),      # 168 partition words: six per lane, rotated rows wrap
-    "w2_2800": lambda: m.synthetic_problem(2800, 64, 8, 3),                # the largest two-word shape whose planes fit
+    "w1_3800": lambda: m.synthetic_problem(3800, 32, 4, 3, remove=1),      # 120 partition words: four per lane, rotated rows wrap
+    "w2_2000": lambda: m.synthetic_problem(2000, 64, 8, 3),                # about the largest two-word shape whose planes fit
     "rf4_w2": lambda: m.synthetic_problem(300, 40, 5, 4, remove=3),
     "r8_b61": lambda: m.synthetic_problem(96, 61, 8, 3),                   # unequal racks, padding slots
     "p1100": lambda: m.synthetic_problem(1100, 64, 8, 3, remove=2),        # 40 partition words: two per lane
@@ -167,6 +167,26 @@ def test_column_major_evaluator_on_arbitrary_bases(emu, ref_lib, name):
         bits, ld = r.encode(reps)
         want = r.candidate_keys(bits, ld, 11 + it, it, 256, 0, n)
         assert (want == sess.candidate_keys(11 + it, it, 256, 0, n)).all()
+    sess.close()
+
+
+def test_row_pass_takes_its_exact_path_for_broken_rows_only(emu):
+    """The row pass of the column-major evaluator flags a partition (and scores it one by one from its
+    row-major row) only when a rack field holds two replicas or the number of racks in use is not RF.  On a
+    base whose rows are all well formed that path must never run — results would still be right if it did
+    (the one-by-one terms are exact), only slow; a wrong truth table in the flag logic went unnoticed that way."""
+    pb = COLUMN_MAJOR["cfg3"]()
+    sess = emu.EmuSession(product(pb))
+    assert sess.set_evaluator(1)
+    emu.rows_charged_one_by_one()
+    sess.candidate_keys(0x5EED, 0, 4096, 0, 64)
+    assert emu.rows_charged_one_by_one() == 0
+    reps = sess.get_base()[0].copy()
+    reps[17, 2] = -1                                # a short row: n = 2
+    reps[40, 1] = (reps[40, 0] + 8) % 64            # two replicas in one rack (brokers b and b + 8 share rack b mod 8)
+    sess.set_base(reps)
+    sess.candidate_keys(0x5EED, 0, 4096, 4095, 1)   # the identity candidate: nothing patched
+    assert emu.rows_charged_one_by_one() == 2
     sess.close()
 
 

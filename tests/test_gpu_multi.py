@@ -74,3 +74,35 @@ def test_sharded_search_matches_single_gpu():
         assert keys_a == [int(k) for k in want], "peer-mailbox path, rank %d" % rank
         assert keys_b == [int(k) for k in want], "NCCL path, rank %d" % rank
         assert base_a == want_base and base_b == want_base
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_kao_solve_gives_the_same_answer_on_any_number_of_gpus():
+    """multi-GPU behind the C ABI.  kao_options.n_gpus shards every round over the GPUs of ONE
+    process (a host thread per GPU, peer-memory mailboxes, no torch, no IPC); for the same global round_size
+    1 / 2 / 4 / 8 GPUs return the identical assignment, key, objective and number of rounds."""
+    sys.path.insert(0, ROOT)
+    import kafka_assignment_optimizer_b200 as kao
+    from kafka_assignment_optimizer_b200 import optimizer as kopt
+
+    ndev = torch.cuda.device_count()
+    for pb, kw in [(kao.synthetic_problem(1000, 64, 8, 3), dict(rounds=24, round_size=30011)),
+                   (kao.synthetic_problem(256, 32, 4, 3, remove=2), dict(rounds=40, round_size=4099, delta=True)),
+                   (kao.synthetic_problem(1000, 64, 8, 3), dict(rounds=300, round_size=1 << 13, patience=25)),
+                   (kao.synthetic_problem(600, 96, 6, 3), dict(rounds=6, round_size=2048))]:     # W = 4: row-major kernels
+        one = kopt.solve(pb, seed=77, n_gpus=1, **kw)
+        for n in [g for g in (2, 4, 8) if g <= ndev]:
+            many = kopt.solve(pb, seed=77, n_gpus=n, **kw)
+            assert many.n_gpus == n and one.n_gpus == 1
+            assert (many.replicas == one.replicas).all(), n
+            assert (many.violation, many.objective, many.moves, many.key, many.rounds) == (
+                one.violation, one.objective, one.moves, one.key, one.rounds), n
+    # explicit device list, restarts
+    pb = kao.synthetic_problem(256, 32, 4, 3, remove=2)
+    a = kopt.solve(pb, seed=5, rounds=30, round_size=4096, restarts=3)
+    b = kopt.solve(pb, seed=5, rounds=30, round_size=4096, restarts=3, n_gpus=0, device_mask=0b11)
+    assert b.n_gpus == 2 and (a.replicas == b.replicas).all() and a.key == b.key
+    with pytest.raises(kao.KaoError):
+        kopt.solve(pb, rounds=1, round_size=64, n_gpus=ndev + 1)            # more GPUs than the box has
+    with pytest.raises(kao.KaoError):
+        kopt.solve(pb, rounds=1, round_size=64, n_gpus=3, device_mask=0b11)  # n_gpus contradicts the mask

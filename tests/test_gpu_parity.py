@@ -232,7 +232,7 @@ def test_abi_rejects_bad_input():
 def test_candidate_keys_from_an_arbitrary_malformed_base(ref_lib, name):
     """kao_set_base with a damaged assignment (short rows, an empty row, duplicated brokers, rows
     violating every constraint): generator and evaluator still agree with the restatement, in full
-    and (narrow rows) in delta evaluation."""
+    and in delta evaluation."""
     pb = SHAPES[name]()
     r = ref_lib.Ref(pb)
     rng = np.random.RandomState(21)
@@ -251,8 +251,7 @@ def test_candidate_keys_from_an_arbitrary_malformed_base(ref_lib, name):
     got = sess.candidate_keys(0xBAD, 4, 2048, 0, 2048)
     bad = np.flatnonzero(want != got)
     assert bad.size == 0, "idx %d: want %s got %s" % (bad[0], sess.unpack_key(want[bad[0]]), sess.unpack_key(got[bad[0]]))
-    if sess.stats()["words_per_row"] <= 2:
-        assert (sess.candidate_keys_delta(0xBAD, 4, 2048, 0, 2048) == want).all()
+    assert (sess.candidate_keys_delta(0xBAD, 4, 2048, 0, 2048) == want).all()
     _, traj = r.search(bits, ld, 0xBAD, 0, 10, 1024)
     keys, _ = sess.search(0xBAD, 0, 10, 1024)
     assert (keys == traj).all()

@@ -30,7 +30,7 @@ def test_abi_exports_every_declared_symbol(lib):
     names = set(re.findall(r"\b(kao_[a-z0-9_]+)\s*\(", hdr))
     assert {"kao_solve", "kao_eval", "kao_create", "kao_search", "kao_round_launch", "kao_round_apply",
             "kao_candidate_keys", "kao_profile_rounds", "kao_p2p_export", "kao_p2p_connect",
-            "kao_search_sharded", "kao_search_sharded_delta", "kao_search_delta", "kao_set_patience", "kao_set_evaluator", "kao_set_schedule", "kao_last_rounds", "kao_candidate_keys_delta", "kao_key_obj_bits", "kao_version", "kao_last_error"} <= names
+            "kao_search_sharded", "kao_search_sharded_delta", "kao_search_delta", "kao_set_patience", "kao_set_evaluator", "kao_get_evaluator", "kao_set_schedule", "kao_last_rounds", "kao_candidate_keys_delta", "kao_key_obj_bits", "kao_version", "kao_last_error"} <= names
     for n in sorted(names):
         assert hasattr(lib, n), n
     assert lib.kao_version() == 0x00020000
@@ -112,3 +112,15 @@ def test_jni_shim_type_checks_against_the_abi():
                         "-I", os.path.join(root, "tests", "jni_stub"), "-I", os.path.join(root, "include"),
                         os.path.join(root, "java", "kao_jni.c")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_rounds_are_bounded_before_anything_is_allocated(lib):
+    """ADVICE r1: `rounds` sized host vectors unchecked (std::bad_alloc across extern "C"; -1 wraps to 4 billion
+    through c_uint32).  KAO_MAX_ROUNDS is checked first, and every entry point runs inside a catch-all guard."""
+    pb = kao.synthetic_problem(16, 8, 2, 2)
+    for rounds in ((1 << 20) + 1, -1):
+        with pytest.raises(kao.KaoError, match="KAO_MAX_ROUNDS"):
+            kopt.solve(pb, rounds=rounds, round_size=16)
+    with pytest.raises(kao.KaoError, match="round_size"):
+        kopt.solve(pb, rounds=1, round_size=1 << 25)
+    assert kopt.key_obj_bits(pb) == (16 * 2 * 4).bit_length()       # needs no GPU
