@@ -225,7 +225,10 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
     PopStream<(Cfg::kPop >> 8) & 15> o0;
     PopStream<(Cfg::kPop >> 12) & 15> o1;
     PopStream<(Cfg::kPop >> 16) & 15> o2;
-    const int nch = nW >> 2;
+    const int nch = nW >> 2;                        // <= 30 chunks of 128 partitions (P <= 3840)
+    uint32_t patched_chunks = 0;                    // bit j: a patched partition lies in chunk j
+#pragma unroll
+    for (int i = 0; i < kMaxOps; ++i) patched_chunks |= ps.p[i] >= 0 ? 1u << (ps.p[i] >> 7) : 0u;
     int tw = nW >= 32 ? 4 * (lane & 7) : 0;        // physical word of logical word 0 (see t_word)
 #pragma unroll 1
     for (int j = 0; j < nch; ++j) {
@@ -242,7 +245,7 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
         tw += 4;
         tw -= (tw >= nW) ? nW : 0;
         // the candidate's patched rows replace their partition's bit in this lane's columns
-        if (((ps.p[0] >> 7) == j) | ((ps.p[1] >> 7) == j) | ((ps.p[2] >> 7) == j)) {
+        if ((patched_chunks >> j) & 1u) {
 #pragma unroll
             for (int i = 0; i < kMaxOps; ++i) {
                 const int pp = ps.p[i];
@@ -280,14 +283,26 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
         o2.add4(hit[0], hit[1], hit[2], hit[3]);
     }
     // ---- C3 / C4 on this lane's columns, C2/C5 as P - sum of valid leaders, C6 per 8-lane rack group
+    // (rack totals: the W column totals of a lane travel packed in one word through three butterfly steps
+    // inside the 8-lane group — a partial-mask warp reduction would run once per group, one after the other)
+    static_assert(W <= 2, "two 16-bit totals per word");
+    uint32_t packed = 0;
 #pragma unroll
     for (int t = 0; t < W; ++t) {
         const int s = lane + 32 * t;
         const int c = cnt[t].total(), l = lcnt[t].total();
+        packed |= (uint32_t)c << (16 * t);                      // c <= P < 8192: the sum of 8 lanes stays below 2^16
         viol += band_violation(c, cs->bnd_rep[s]) + band_violation(l, cs->bnd_ldr[s]) - l;
-        const int tot = __reduce_add_sync(0xFFu << (lane & 24), c);
-        const int rk = s >> 3;
-        if ((lane & 7) == 0 && rk < d.R) viol += max(tot - cs->rack_hi[rk], 0) + max(cs->rack_lo[rk] - tot, 0);
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
+    if ((lane & 7) == 0) {
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const int rk = (lane + 32 * t) >> 3;
+            const int tot = (int)((packed >> (16 * t)) & 0xFFFFu);
+            if (rk < d.R) viol += max(tot - cs->rack_hi[rk], 0) + max(cs->rack_lo[rk] - tot, 0);
+        }
     }
     const int obj = o0.total() * d.plane_value[0] + o1.total() * d.plane_value[1] + o2.total() * d.plane_value[2];
     viol_out = __reduce_add_sync(0xFFFFFFFFu, viol) + d.P;

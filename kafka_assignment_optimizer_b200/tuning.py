@@ -12,8 +12,7 @@ from __future__ import annotations
 import json
 
 # (sync, pop, threads) — the variants csrc/kao_kernels.cuh builds (KAO_FOR_SCHEDULES); the first is the default
-SCHEDULES = [(1, 0x11133, 512), (1, 0x11111, 512), (1, 0x11122, 512), (1, 0x22233, 512), (1, 0x11123, 512), (1, 0x33333, 512),
-             (1, 0x11133, 640), (1, 0x11111, 640), (1, 0x11133, 768), (1, 0x11111, 768), (0, 0x11133, 512), (0, 0x11133, 768)]
+SCHEDULES = [(1, 0x22222, 640), (1, 0x22233, 640), (1, 0x11133, 640), (1, 0x22222, 512), (0, 0x22222, 640), (1, 0x11111, 768)]
 DEFAULT_SCHEDULE = SCHEDULES[0]
 SCHEDULE_FIELDS = ("sync", "pop", "threads")
 

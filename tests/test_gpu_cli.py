@@ -26,7 +26,7 @@ def test_cli_solves_the_readme_example(tmp_path):
     want = {0: [7, 18], 2: [9, 10], 3: [0, 11], 4: [1, 12], 5: [2, 13], 6: [3, 14], 7: [4, 15], 8: [5, 16], 9: [6, 17]}
     assert all(rows[k] == v for k, v in want.items())           # "All the other moves are not required"
     assert rows[1][0] == 8 and rows[1][1] % 2 == 1 and rows[1][1] != 19   # leader kept, follower in the other AZ
-    assert "objective 58, violation 0, replica moves 1" in p.stderr
+    assert "objective 58 (upper bound 58: proven optimal), violation 0, replica moves 1" in p.stderr
     pb = m.readme_problem()
     reps = [[int(b) for b in rows[i]] for i in range(10)]
     assert m.evaluate(pb, __import__("numpy").array(reps)) == (0, 58)

@@ -12,10 +12,11 @@ def test_schedule_list_matches_the_kernel_header():
     built = [(int(a), int(b, 16), int(c)) for a, b, c in re.findall(r"X\((\d+), (0x[0-9a-fA-F]+), (\d+)\)", body)]
     assert built == tuning.SCHEDULES and len(set(built)) == len(built) <= 6
     default = (int(re.search(r"#define KAO_SCHEDULE_DEFAULT_SYNC (\d+)", src).group(1)),
-               int(re.search(r"#define KAO_SCHEDULE_DEFAULT_POP (0x[0-9a-fA-F]+)", src).group(1), 16), 768)
+               int(re.search(r"#define KAO_SCHEDULE_DEFAULT_POP (0x[0-9a-fA-F]+)", src).group(1), 16),
+               int(re.search(r"#define KAO_SCHEDULE_DEFAULT_THREADS (\d+)", src).group(1)))
     assert default == tuning.DEFAULT_SCHEDULE == built[0]
     for sync, pop, threads in built:
-        assert sync in (0, 1) and threads in (512, 768)
+        assert sync in (0, 1) and threads in (512, 640, 768)
         assert all(0 <= (pop >> (4 * i)) & 15 <= 3 for i in range(5)) and pop >> 20 == 0
 
 
