@@ -90,6 +90,8 @@ typedef struct kao_options {
 #define KAO_FLAG_DELTA 0x100u
 #define KAO_FLAG_ROW_MAJOR 0x200u     /* full evaluation by the row-major evaluator even where the (default, faster)
                                          column-major one applies (see kao_set_evaluator); same keys, same result */
+#define KAO_FLAG_BOUND 0x400u         /* kao_result.objective_bound from the flow relaxations of kao_objective_bound (host work
+                                         after the search, milliseconds at config 3) instead of the per-partition bound */
 #define KAO_FLAG_PATIENCE(n) ((uint32_t)(n) << 16)  /* stop a search after n (<= 65535) rounds without a better key */
 
 typedef struct kao_result {
@@ -105,9 +107,10 @@ typedef struct kao_result {
     uint32_t restarts;        /* restarts performed */
     double device_ms;         /* CUDA-event time of the search kernels (max over the GPUs) */
     double total_ms;          /* wall time of the call incl. host<->device copies */
-    int64_t objective_bound;  /* an upper bound on the objective of ANY feasible assignment (per partition: the
-                                 best leader + best RF-1 followers, C3..C7 ignored); lp_solve's optimum
-                                 (README.md:135-136) lies between `objective` and this */
+    int64_t objective_bound;  /* an upper bound on the objective of ANY feasible assignment: per partition the best
+                                 leader + best RF-1 followers (C3..C7 ignored), or with KAO_FLAG_BOUND the much
+                                 tighter flow bound of kao_objective_bound; lp_solve's optimum (README.md:135-136)
+                                 lies between `objective` and this */
     int32_t optimal;          /* 1: feasible and objective == objective_bound, i.e. PROVEN optimal; 0: not proven
                                  (the search is a heuristic: it never claims more than the bound shows) */
     int32_t key_obj_bits;     /* width of the cost field of `key` (KAO_KEY_* macros) */
@@ -121,6 +124,14 @@ const char *kao_last_error(void);
 /* One blocking solve from host buffers: tables -> device, `rounds` search rounds, winner -> host.
  * Replaces "emit LP + run lp_solve + parse variables" (README.md:135-136, :139-185). */
 int kao_solve(const kao_problem *pb, const kao_options *opt, kao_result *res);
+
+/* An upper bound on the objective of every feasible assignment of `pb` — what tells a caller how far a search
+ * result can be from the optimum lp_solve would return (README.md:135-136).  Host-side, needs no GPU.
+ * replicas == NULL: per partition the best leader + best RF-1 followers, constraints C3..C7 ignored.
+ * replicas = a FEASIBLE assignment ([P*RF], leader first): Y* + L*, the optima of two network-flow relaxations
+ * (placement under C1/C3/C6/C7, leadership under C2/C4; only their coupling is dropped), found by cancelling
+ * negative cycles from that assignment; never above the first bound.  objective == bound proves optimality. */
+int kao_objective_bound(const kao_problem *pb, const int32_t *replicas, int64_t *bound);
 
 /* Evaluate n explicit assignments (each [P*RF] replica lists, leader first, -1 padded) on the
  * GPU with the same evaluator the search uses: C1..C7 violation amount and objective. */

@@ -8,7 +8,7 @@ solve with a GPU candidate search behind the C ABI of ``include/kao.h`` (``libka
 There is no CPU fallback: importing works without a GPU, solving raises ``KaoError``.
 """
 from .problem import Problem, build_problem, default_bounds, default_weights, synthetic_problem  # noqa: F401
-from .optimizer import AssignmentOptimizer, KaoError, Session, SolveResult, key_obj_bits, unpack_key  # noqa: F401
+from .optimizer import AssignmentOptimizer, KaoError, Session, SolveResult, key_obj_bits, objective_bound, unpack_key  # noqa: F401
 
 __all__ = ["Problem", "build_problem", "default_bounds", "default_weights", "synthetic_problem",
-           "AssignmentOptimizer", "KaoError", "Session", "SolveResult", "key_obj_bits", "unpack_key"]
+           "AssignmentOptimizer", "KaoError", "Session", "SolveResult", "key_obj_bits", "objective_bound", "unpack_key"]

@@ -5,9 +5,11 @@
 // There is no CPU fallback: every entry point fails with KAO_E_CUDA when no device is usable.
 #include "kao_kernels.cuh"
 #include "kao_host.hpp"
+#include "kao_bound.hpp"
 #include "../../include/kao.h"
 
 #include <chrono>
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <cstdio>
@@ -205,6 +207,7 @@ struct kao_handle {
     Mailbox *peer_mail[kMaxPeers] = {};
     Mailbox **d_mailptrs = nullptr;         // device copy of peer_mail for the kernel
     bool peer_opened[kMaxPeers] = {};       // mapped with cudaIpcOpenMemHandle (to be closed)
+    bool mail_pooled = false;               // d_mail came from the buffer pool (kao_solve's gang), not from cudaMalloc
     int p2p_rank = 0, p2p_world = 1;
     uint64_t p2p_calls = 0;
     uint32_t patience = 0, last_rounds = 0;
@@ -366,7 +369,7 @@ static int destroy_impl(kao_handle *h)
     for (auto &b : h->owned) g_pool.put(h->device, b.first, b.second);
     for (int r = 0; r < kMaxPeers; ++r)
         if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
-    if (h->d_mail) cudaFree(h->d_mail);
+    if (h->d_mail && !h->mail_pooled) cudaFree(h->d_mail);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -832,35 +835,124 @@ static int pick_devices(const kao_options *opt, std::vector<int> &devs)
     return KAO_OK;
 }
 
-// handles of one multi-GPU solve; destroyed on every path
-struct Gang {
-    std::vector<kao_handle *> h;
-    ~Gang() { const std::string keep = g_err; for (auto *x : h) destroy_impl(x); g_err = keep; }
+// ---- several GPUs of this process: one host thread per GPU does everything for its device (create, connect,
+// search, destroy), so that the per-call set-up cost does not grow with the number of GPUs
+namespace {
+struct Rendezvous {                                   // a reusable barrier that also spreads "somebody failed"
+    std::mutex mu;
+    std::condition_variable cv;
+    int n, waiting = 0, generation = 0;
+    bool failed = false;
+    explicit Rendezvous(int parties) : n(parties) {}
+    bool arrive(bool ok)                              // -> false once any party has arrived with ok == false
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        failed |= !ok;
+        const int gen = generation;
+        if (++waiting == n) { waiting = 0; ++generation; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != generation; });
+        return !failed;
+    }
+};
+std::mutex g_peer_mu;
+bool g_peer_enabled[64][64] = {};
+}  // namespace
+
+static int enable_peers(int dev, const std::vector<int> &devs)
+{
+    CUDA_TRY(cudaSetDevice(dev));
+    for (int other : devs) {
+        if (other == dev) continue;
+        {
+            std::lock_guard<std::mutex> g(g_peer_mu);
+            if (g_peer_enabled[dev & 63][other & 63]) continue;
+        }
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, dev, other));
+        if (!can) return fail(KAO_E_CUDA, "the selected GPUs cannot access each other's memory (no peer access)");
+        const cudaError_t e = cudaDeviceEnablePeerAccess(other, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return fail(KAO_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        std::lock_guard<std::mutex> g(g_peer_mu);
+        g_peer_enabled[dev & 63][other & 63] = true;
+    }
+    return KAO_OK;
+}
+
+struct GangResult {                                   // what rank 0 reports per restart
+    int64_t viol = 0, obj = 0;
+    int32_t moves = 0;
+    uint32_t rounds = 0;
+    double dev_ms = 0;
 };
 
-static int connect_gang(Gang &g)
+static int solve_gang(const kao_problem *pb, const kao_options *opt, kao_result *res, const std::vector<int> &devs,
+                      uint32_t restarts, bool delta, std::vector<uint64_t> &keys, std::vector<int32_t> &reps,
+                      uint32_t &rounds_run, double &dev_ms_total, HostModel &hm_out)
 {
-    const int world = (int)g.h.size();
-    for (int i = 0; i < world; ++i) {
-        CUDA_TRY(cudaSetDevice(g.h[i]->device));
-        for (int j = 0; j < world; ++j) {
-            if (i == j) continue;
-            int can = 0;
-            CUDA_TRY(cudaDeviceCanAccessPeer(&can, g.h[i]->device, g.h[j]->device));
-            if (!can) return fail(KAO_E_CUDA, "the selected GPUs cannot access each other's memory (no peer access)");
-            const cudaError_t e = cudaDeviceEnablePeerAccess(g.h[j]->device, 0);
-            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-            else if (e != cudaSuccess) return fail(KAO_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    const int world = (int)devs.size();
+    std::vector<kao_handle *> hs(world, nullptr);
+    std::vector<int> rcs(world, KAO_OK);
+    std::vector<std::string> errs(world);
+    std::vector<double> ms(world, 0.0);
+    Rendezvous meet(world);
+    bool have = false;
+    auto worker = [&](int i) {
+        auto step = [&](int rc) {                     // record the first failure of this rank, then meet the others
+            if (rc != KAO_OK && rcs[i] == KAO_OK) { rcs[i] = rc; errs[i] = g_err; }
+            return meet.arrive(rc == KAO_OK);
+        };
+        kao_handle *h = nullptr;
+        bool ok = step(guarded([&] { return create_handle(pb, devs[i], &h); }));
+        hs[i] = h;
+        if (ok) ok = step(guarded([&] {
+            int rc = enable_peers(devs[i], devs);
+            if (rc != KAO_OK) return rc;
+            CUDA_TRY(dalloc(h, &h->d_mail, sizeof(Mailbox)));          // recycled: no cudaMalloc / cudaFree per solve
+            h->mail_pooled = true;
+            CUDA_TRY(cudaMemsetAsync(h->d_mail, 0xFF, sizeof(Mailbox), 0));   // kMailEmpty everywhere, before any peer can write
+            CUDA_TRY(cudaStreamSynchronize(0));
+            h->patience = opt->flags >> 16;                         // KAO_FLAG_PATIENCE(n)
+            if (opt->flags & KAO_FLAG_ROW_MAJOR) h->evaluator = KAO_EVAL_ROW_MAJOR;
+            return KAO_OK;
+        }));
+        if (ok) ok = step(guarded([&] {
+            for (int j = 0; j < world; ++j) h->peer_mail[j] = hs[j]->d_mail;    // unified addressing: a peer's pointer is valid here
+            return publish_mailboxes(h, i, world);
+        }));
+        for (uint32_t r = 0; ok && r < restarts; ++r) {
+            const uint64_t seed = opt->seed + 0x9E3779B97F4A7C15ull * r;
+            ok = step(guarded([&] {
+                int rc = r ? reset_impl(h) : KAO_OK;
+                if (rc == KAO_OK) rc = sharded_impl(h, seed, 0, opt->rounds, opt->round_size, i == 0 ? keys.data() : nullptr, &ms[i], delta);
+                return rc;
+            }));
+            if (ok && i == 0) {                       // all ranks hold the same base: rank 0 reports it
+                GangResult g;
+                int rc = guarded([&] { return get_base_impl(h, reps.data(), &g.viol, &g.obj, &g.moves); });
+                if (rc == KAO_OK) {
+                    for (int j = 0; j < world; ++j) g.dev_ms = ms[j] > g.dev_ms ? ms[j] : g.dev_ms;
+                    dev_ms_total += g.dev_ms;
+                    rounds_run += h->last_rounds;
+                    if (!have || g.viol < res->violation || (g.viol == res->violation && g.obj > res->objective)) {
+                        std::memcpy(res->replicas, reps.data(), reps.size() * 4);
+                        res->violation = g.viol; res->objective = g.obj; res->moves = g.moves;
+                        res->key = h->last_rounds ? keys[h->last_rounds - 1] : kKeyNone;
+                        have = true;
+                    }
+                } else { rcs[0] = rc; errs[0] = g_err; }
+            }
+            if (ok) ok = meet.arrive(i != 0 || rcs[0] == KAO_OK);   // nobody resets the base while rank 0 reads it
         }
-        const int rc = ensure_mailbox(g.h[i]);
-        if (rc != KAO_OK) return rc;
-    }
-    for (int i = 0; i < world; ++i) {
-        CUDA_TRY(cudaSetDevice(g.h[i]->device));
-        for (int j = 0; j < world; ++j) g.h[i]->peer_mail[j] = g.h[j]->d_mail;      // unified addressing: a peer's pointer is valid here
-        const int rc = publish_mailboxes(g.h[i], i, world);
-        if (rc != KAO_OK) return rc;
-    }
+        if (i == 0 && h) hm_out = h->hm;
+        if (h) { const std::string keep = g_err; destroy_impl(h); g_err = keep; }
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < world; ++i) th.emplace_back(worker, i);
+    worker(0);
+    for (auto &t : th) t.join();
+    for (int i = 0; i < world; ++i)
+        if (rcs[i] != KAO_OK) return fail(rcs[i], "GPU " + std::to_string(devs[i]) + ": " + errs[i]);
     return KAO_OK;
 }
 
@@ -874,78 +966,57 @@ static int solve_impl(const kao_problem *pb, const kao_options *opt, kao_result 
     int rc = pick_devices(opt, devs);
     if (rc != KAO_OK) return rc;
     const int world = (int)devs.size();
-    Gang g;
-    for (int d : devs) {
-        kao_handle *h = nullptr;
-        rc = create_handle(pb, d, &h);
-        if (rc != KAO_OK) return rc;
-        g.h.push_back(h);
-    }
-    if (world > 1 && (rc = connect_gang(g)) != KAO_OK) return rc;
     // independent restarts (flags & 0xFF, 0 and 1 both mean a single search): each restarts from the
     // initial base with its own seed; the best final assignment wins (violation, then objective)
     const uint32_t restarts = (opt->flags & 0xFFu) ? (opt->flags & 0xFFu) : 1u;
     const bool delta = (opt->flags & KAO_FLAG_DELTA) != 0;
-    for (auto *h : g.h) {
-        h->patience = opt->flags >> 16;                         // KAO_FLAG_PATIENCE(n)
-        // the column-major evaluator is the default where the layout allows it; the flag selects the other full evaluator (same keys)
-        if (opt->flags & KAO_FLAG_ROW_MAJOR) h->evaluator = KAO_EVAL_ROW_MAJOR;
-    }
-    kao_handle *h0 = g.h[0];
     uint32_t rounds_run = 0;
     std::vector<uint64_t> keys(opt->rounds ? opt->rounds : 1, kKeyNone);
     std::vector<int32_t> reps((size_t)pb->P * pb->RF);
     double dev_ms_total = 0;
-    bool have = false;
-    for (uint32_t r = 0; r < restarts; ++r) {
-        const uint64_t seed = opt->seed + 0x9E3779B97F4A7C15ull * r;
-        double dev_ms = 0;
-        if (world == 1) {
+    HostModel hm;
+    if (world == 1) {
+        kao_handle *h0 = nullptr;
+        rc = create_handle(pb, devs[0], &h0);
+        if (rc != KAO_OK) return rc;
+        struct Closer { kao_handle *h; ~Closer() { const std::string keep = g_err; destroy_impl(h); g_err = keep; } } closer{h0};
+        h0->patience = opt->flags >> 16;                         // KAO_FLAG_PATIENCE(n)
+        // the column-major evaluator is the default where the layout allows it; the flag selects the other full evaluator (same keys)
+        if (opt->flags & KAO_FLAG_ROW_MAJOR) h0->evaluator = KAO_EVAL_ROW_MAJOR;
+        bool have = false;
+        for (uint32_t r = 0; r < restarts; ++r) {
+            double dev_ms = 0;
             if (r && (rc = reset_impl(h0)) != KAO_OK) return rc;
-            rc = search_impl(h0, seed, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms, delta);
+            rc = search_impl(h0, opt->seed + 0x9E3779B97F4A7C15ull * r, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms, delta);
             if (rc != KAO_OK) return rc;
-        } else {
-            // one host thread per GPU; each runs its slice of every round, the kernels trade the per-round minimum
-            std::vector<int> rcs(world, KAO_OK);
-            std::vector<std::string> errs(world);
-            std::vector<double> ms(world, 0.0);
-            std::vector<std::thread> th;
-            for (int i = 0; i < world; ++i)
-                th.emplace_back([&, i] {
-                    rcs[i] = guarded([&] {
-                        int c = r ? reset_impl(g.h[i]) : KAO_OK;
-                        if (c == KAO_OK) c = sharded_impl(g.h[i], seed, 0, opt->rounds, opt->round_size, i == 0 ? keys.data() : nullptr, &ms[i], delta);
-                        return c;
-                    });
-                    if (rcs[i] != KAO_OK) errs[i] = g_err;      // g_err is thread-local
-                });
-            for (auto &t : th) t.join();
-            for (int i = 0; i < world; ++i) {
-                if (rcs[i] != KAO_OK) return fail(rcs[i], "GPU " + std::to_string(devs[i]) + ": " + errs[i]);
-                dev_ms = ms[i] > dev_ms ? ms[i] : dev_ms;
+            int64_t viol = 0, obj = 0;
+            int32_t moves = 0;
+            rc = get_base_impl(h0, reps.data(), &viol, &obj, &moves);
+            if (rc != KAO_OK) return rc;
+            dev_ms_total += dev_ms;
+            rounds_run += h0->last_rounds;
+            if (!have || viol < res->violation || (viol == res->violation && obj > res->objective)) {
+                std::memcpy(res->replicas, reps.data(), reps.size() * 4);
+                res->violation = viol; res->objective = obj; res->moves = moves;
+                res->key = h0->last_rounds ? keys[h0->last_rounds - 1] : kKeyNone;
+                have = true;
             }
         }
-        int64_t viol = 0, obj = 0;
-        int32_t moves = 0;
-        rc = get_base_impl(h0, reps.data(), &viol, &obj, &moves);
+        hm = h0->hm;
+    } else {
+        rc = solve_gang(pb, opt, res, devs, restarts, delta, keys, reps, rounds_run, dev_ms_total, hm);
         if (rc != KAO_OK) return rc;
-        dev_ms_total += dev_ms;
-        rounds_run += h0->last_rounds;
-        if (!have || viol < res->violation || (viol == res->violation && obj > res->objective)) {
-            std::memcpy(res->replicas, reps.data(), reps.size() * 4);
-            res->violation = viol; res->objective = obj; res->moves = moves;
-            res->key = h0->last_rounds ? keys[h0->last_rounds - 1] : kKeyNone;
-            have = true;
-        }
     }
     res->feasible = res->violation == 0;
     res->n_candidates = (uint64_t)rounds_run * opt->round_size;
     res->rounds_run = rounds_run;
     res->restarts = restarts;
     res->device_ms = dev_ms_total;
-    res->objective_bound = objective_upper_bound(h0->hm, *pb);
+    res->objective_bound = objective_upper_bound(hm, *pb);
+    if ((opt->flags & KAO_FLAG_BOUND) && res->feasible)
+        res->objective_bound = objective_flow_bound(hm, *pb, res->replicas, res->objective_bound);
     res->optimal = res->feasible && res->objective == res->objective_bound;
-    res->key_obj_bits = h0->hm.key_obj_bits;
+    res->key_obj_bits = hm.key_obj_bits;
     res->n_gpus = world;
     res->reserved = 0;
     res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -966,6 +1037,18 @@ extern "C" int kao_key_obj_bits(const kao_problem *pb)
         std::string why;
         if (!build_host_model(*pb, m, why)) return fail(KAO_E_ARG, why);
         return m.key_obj_bits;
+    });
+}
+extern "C" int kao_objective_bound(const kao_problem *pb, const int32_t *replicas, int64_t *bound)
+{
+    return guarded([&] {
+        if (!pb || !bound) return fail(KAO_E_ARG, "null argument");
+        HostModel m;
+        std::string why;
+        if (!build_host_model(*pb, m, why)) return fail(KAO_E_ARG, why);
+        *bound = objective_upper_bound(m, *pb);
+        if (replicas) *bound = objective_flow_bound(m, *pb, replicas, *bound);
+        return KAO_OK;
     });
 }
 extern "C" int kao_create(const kao_problem *pb, int32_t device, kao_handle **out) { return guarded([&] { return create_handle(pb, device, out); }); }

@@ -89,6 +89,15 @@ def key_obj_bits(pb: Problem) -> int:
     return rc
 
 
+def objective_bound(pb: Problem, replicas=None) -> int:
+    """Upper bound on the objective of every feasible assignment (kao_objective_bound; needs no GPU): the cheap
+    per-partition bound, or — given a feasible assignment [P, RF], leader first — the flow bound Y* + L*."""
+    out = C.c_int64()
+    r = None if replicas is None else np.ascontiguousarray(replicas, dtype=np.int32)
+    _check(load_library().kao_objective_bound(_CProblem(pb).ref(), None if r is None else C.c_void_p(r.ctypes.data), C.byref(out)))
+    return out.value
+
+
 class _CProblem:
     """Keeps contiguous numpy buffers alive next to the C struct that points into them."""
 
@@ -285,14 +294,16 @@ class Session:
 
 def solve(pb: Problem, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15,
           device: int = 0, require_feasible: bool = False, restarts: int = 1, delta: bool = False,
-          patience: int = 0, row_major: bool = False, n_gpus: int = 1, device_mask: int = 0) -> SolveResult:
+          patience: int = 0, row_major: bool = False, n_gpus: int = 1, device_mask: int = 0,
+          tight_bound: bool = False) -> SolveResult:
     """One blocking kao_solve from host buffers (tables up, winner down).  n_gpus > 1: every round is sharded
     over that many GPUs of this process (devices device .. device+n_gpus-1, or those of device_mask); the
     result is the same as on one GPU with the same round_size."""
     lib = load_library()
     cp = _CProblem(pb)
     reps = np.full((pb.P, pb.RF), -1, np.int32)
-    flags = max(1, min(255, restarts)) | (0x100 if delta else 0) | (0x200 if row_major else 0) | (max(0, min(65535, patience)) << 16)
+    flags = (max(1, min(255, restarts)) | (0x100 if delta else 0) | (0x200 if row_major else 0) | (0x400 if tight_bound else 0) |
+             (max(0, min(65535, patience)) << 16))
     opt = _KaoOptions(seed & (2 ** 64 - 1), rounds, round_size, device, flags, n_gpus, device_mask)
     res = _KaoResult()
     res.replicas = reps.ctypes.data
