@@ -26,7 +26,8 @@ def test_bench_uses_the_oracle_only_in_its_cpu_legs():
     for mt in re.finditer(r"from oracle import", src):
         fn = src.rfind("\ndef ", 0, mt.start())
         name = re.match(r"\ndef (\w+)", src[fn:]).group(1)
-        assert name in ("cpu_port_rate", "reference_arm"), name
+        # the CPU legs: the port's rate, the reference arm, and the exact (HiGHS) solve timed beside them
+        assert name in ("cpu_port_rate", "reference_arm", "exact_solve"), name
 
 
 def test_host_emulation_stays_out_of_the_product():
