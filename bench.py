@@ -161,7 +161,7 @@ def cpu_port_rate(cfg, seconds_target=10.0):
         total += n
         rnd += 1
     return total / spent, threads, "%d candidates (%d rounds of the same Philox stream, full evaluation), %.1f s" % (
-        total, rnd, spent), r.max_threads()
+        total, rnd, spent), r.max_threads(), ref.build_flags()
 
 
 def exact_solve(cfg, limit_s):
@@ -489,11 +489,9 @@ def main():
             solo.close()
         cpu = None
         if not args.no_cpu_baseline and world == 1:         # reported at N=1 only
-            from oracle import ref
-
-            v, threads, sample, omp = cpu_port_rate(args.config)
+            v, threads, sample, omp, port_build = cpu_port_rate(args.config)
             cpu = {"value": v, "unit": "candidates/s", "cores": threads, "kind": "port", "sample": sample,
-                   "omp_max_threads": omp, "build": ref.build_flags(), "host": host_cpu_info(),
+                   "omp_max_threads": omp, "build": port_build, "host": host_cpu_info(),
                    "note": "lp_solve (the reference's solver) is not installed here and cannot be timed; "
                            "this is the plain-C/OpenMP restatement of the same path"}
             if not args.no_extras and args.config in ("2", "3", "4"):
