@@ -53,6 +53,11 @@ struct Params {
     const uint32_t *planesT;     // weighted mask planes [nplanes][W][Ppad], or nullptr
     const uint32_t *dense_w;     // [P][NS] wF | wL << 16, or nullptr
     const uint32_t *homeT;       // [Ppad] 4 x u8 home slots (0xFF = none)
+    // term planes of the sparse objective (column-major evaluator, kao_device_t.cuh; host: kao_host.hpp)
+    int nz;                      // planes in use (0..8)
+    int z_on_leader;             // bit j set: plane j counts leaderships (bonus wL - wF), else replicas (wF)
+    int z_value[8];              // value of a term of plane j
+    const uint8_t *zslot;        // [Ppad][8] slot of partition p's term in plane j, 0xFF = none
     uint16_t *D;                 // displaced partitions of the base, ascending
     uint16_t *DL;                // leader-displaced partitions of the base, ascending
     int *nD;                     // [0] = |D|, [1] = |DL|

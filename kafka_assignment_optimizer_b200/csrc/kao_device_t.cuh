@@ -2,26 +2,31 @@
 //
 // Same result as eval_candidate (kao_device.cuh, docs/MODEL.md §3) for the layout class of the
 // headline configuration: rows of up to 64 slots, 8-slot rack fields, "at most one replica of a
-// partition per rack" (C7 bounds 0..1), three weighted mask planes.  The base is ALSO kept transposed
-// in shared memory: for every slot s a bitmap over the partitions (32 per word).  Five planes:
+// partition per rack" (C7 bounds 0..1), an objective whose non-zero terms fit 8 term planes.
+// The base is ALSO kept transposed in shared memory: for every slot s a bitmap over the partitions
+// (32 per word), two planes:
 //   q = 0  replicas            T0[s] bit p  <=>  partition p has a replica on slot s
 //   q = 1  leader one-hot      T1[s] bit p  <=>  ... and is led from s
-//   q = 2,3  follower weight   A0 = T0 & M0, A1 = T0 & M1   (Mc: objective mask plane c, transposed)
-//   q = 4  leader bonus        A2 = T1 & M2
-// (the objective planes are stored already masked, so the evaluation spends no AND on them; a patched
-// row gets its mask bits from the row-major mask planes kept next to the transposed ones).
-// The evaluation walks this matrix twice, each time with all data of a constraint inside one lane:
-//   rows     (C1, C7)  a lane owns 32 PARTITIONS (one word of every slot).  Per 8-slot rack field two
-//            words are formed, `any` (the field holds a replica) and `dup` (it holds two or more); a
-//            partition is fine when no field is doubled and exactly RF fields are in use, which is one
-//            bit-sliced sum of the `any` words against RF — no POPC per row.  Partitions that fail are
-//            charged |n - RF| + (n - z) from their row-major row, one by one (rare);
-//   columns  (C2-C6, objective)  a lane owns one SLOT per row word: replica and leader totals of its
-//            columns and the three objective sums are popcount sums over the partition words — no
-//            bit-sliced column counters, no cross-lane reduce-scatter.
-// The candidate's <= 3 patched rows are substituted while loading (columns) / skipped and scored
-// from the patch itself (rows), so every row of the candidate is evaluated, none is taken from a
-// previous evaluation.  Model: /root/reference/README.md:144-185.
+// and the objective as the reference writes it — a sum over the variables with a non-zero weight
+// (README.md:145-146: `max: 1 t1b12p5 + 4 t1b19p6_l + ...`, only existing placements appear) — as up to
+// eight TERM PLANES over the partitions (host: kao_host.hpp): all terms of plane j have the value
+// z_value[j] and one kind (replica on / leadership of the term's slot), a partition has at most one term
+// per plane, and
+//   Z[j] bit p  <=>  term j of partition p holds in the base   =>   objective = sum_j z_value[j] * popc(Z[j]).
+// The evaluation walks the matrix twice, each time with all data of a constraint inside one lane:
+//   rows     (C1, C7, objective)  a lane owns 32 PARTITIONS (one word of every slot and of every term
+//            plane).  Per 8-slot rack field two words are formed, `any` (the field holds a replica) and
+//            `dup` (it holds two or more); a partition is fine when no field is doubled and exactly RF
+//            fields are in use, which is one bit-sliced sum of the `any` words against RF — no POPC per
+//            row.  Partitions that fail are charged |n - RF| + (n - z) from their row-major row, one by one
+//            (rare).  The objective is one POPC per term plane;
+//   columns  (C2-C6)  a lane owns one SLOT per row word: replica and leader totals of its columns are
+//            popcount sums over the partition words — no bit-sliced column counters, no cross-lane
+//            reduce-scatter.
+// The candidate's <= 3 patched rows are substituted while loading (columns) / masked out of the base and
+// scored from the patch itself (rows: C1 / C7 terms and objective terms of a patched row are computed from
+// the row when the candidate is generated, patch_terms), so every row of the candidate is evaluated, none
+// is taken from a previous evaluation.  Model: /root/reference/README.md:144-185.
 #pragma once
 #include "kao_device.cuh"
 
@@ -32,19 +37,19 @@ namespace kao {
 // The other parameters are SCHEDULES of the same arithmetic (kao_set_schedule; results identical):
 //   kSync      how the warps of a CTA meet before an evaluation: 0 block barrier (all warps walk the
 //              evaluator together), 1 warp only (one warp's generator overlaps another's evaluation)
-//   kPop       how the five popcount streams (column totals, leader totals, the two follower-weight
-//              sums, the leader bonus) trade POPC (XU pipe, 8 cycles a warp) for carry-save LOP3 (ALU
-//              pipe, 2 cycles): one hex digit per stream, 0 = a POPC per word, 1 = three per four words,
-//              2 = two, 3 = one (Harley-Seal accumulators carried across the whole column)
+//   kPop       how the two popcount streams (column totals, leader totals) trade POPC (XU pipe, 8 cycles
+//              a warp) for carry-save LOP3 (ALU pipe, 2 cycles): one hex digit per stream, 0 = a POPC per
+//              word, 1 = three per four words, 2 = two, 3 = one (Harley-Seal accumulators carried across
+//              the whole column)
 //   kThreads   threads per CTA (0 = threads_for<W>()); fewer threads = more registers per thread
-template <int W_, int kNW_ = 0, int kSync_ = 1, int kPop_ = 0x11111, int kThreads_ = 0>
+template <int W_, int kNW_ = 0, int kSync_ = 1, int kPop_ = 0x22, int kThreads_ = 0>
 struct EvalCfgT {
     static constexpr int W = W_, NPH = 5, kRack = 3, kObj = 3, kNW = kNW_;
     static constexpr int kSync = kSync_, kPop = kPop_, kThreads = kThreads_;
     static constexpr bool kTrans = true;
 };
-constexpr int kTPlanes = 5;
-constexpr int kTMaskPlanes = 3;      // row-major objective mask planes kept behind the transposed planes
+constexpr int kTPlanes = 2;
+constexpr int kZPlanes = 8;          // term planes of the objective: [kZPlanes][nW] words behind the transposed planes
 
 // physical word of (plane q, slot s, partition word w).  Rows are rotated by 4 * (s & 7) words so
 // that the 128-bit column loads of a quarter warp (8 consecutive slots) hit 8 different bank groups;
@@ -76,9 +81,10 @@ inline long long emu_rows_charged_one_by_one = 0;
 // rows: C1 + C7 of every partition that is not patched, 32 partitions per lane
 // ------------------------------------------------------------------------------------------
 template <int W, bool kShared, int kNW>
-__device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, const MemRef<kShared> &bitsT, int nW_rt, int Ppad, int P, int RF,
-                                             int lane, const PatchSet &ps)
+__device__ __forceinline__ int rows_vertical(const Params &d, const MemRef<kShared> &T, const MemRef<kShared> &Z, const MemRef<kShared> &bitsT,
+                                             int nW_rt, int lane, const PatchSet &ps, int &obj)
 {
+    const int Ppad = d.Ppad, P = d.P, RF = d.RF;
     const int nW = kNW ? kNW : nW_rt;
     constexpr int NB = 4 * W;                       // 8-slot blocks = rack fields
     int viol = 0;
@@ -90,6 +96,13 @@ __device__ __forceinline__ int rows_vertical(const MemRef<kShared> &T, const Mem
 #pragma unroll
         for (int i = 0; i < kMaxOps; ++i)           // unused patches hold -1: (-1 >> 5) never equals w
             valid &= ((ps.p[i] >> 5) == w) ? ~(1u << (ps.p[i] & 31)) : ~0u;
+        // objective: the terms that hold, one POPC per term plane (planes nz.. are empty and weigh nothing)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) obj += __popc(Z.ld32((uint32_t)(j * nW + w) * 4u) & valid) * d.z_value[j];
+        if (d.nz > 4) {
+#pragma unroll
+            for (int j = 4; j < kZPlanes; ++j) obj += __popc(Z.ld32((uint32_t)(j * nW + w) * 4u) & valid) * d.z_value[j];
+        }
         int tk[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -196,51 +209,63 @@ template <int kLvl> struct PopStream {
 };
 
 // ------------------------------------------------------------------------------------------
-// the whole candidate.  T: the five transposed planes; bits / masks: the row-major base and the
-// row-major objective mask planes [3][W][Ppad]; prow: this warp's patched rows [kMaxOps * W]
+// C1 / C7 terms and objective terms of the candidate's patched rows, from the rows themselves (one thread:
+// the per-thread generator of the search kernels calls this for its own candidate)
+// ------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void patch_terms(const Params &d, const PatchSet &ps, const uint32_t (&rows)[kMaxOps][W], int &pviol, int &pobj)
+{
+    pviol = 0;
+    pobj = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxOps; ++i) {
+        if (ps.p[i] < 0) continue;
+        pviol += row_terms_hi1_s8<W>(rows[i], d.RF);
+        const uint32_t *zs = reinterpret_cast<const uint32_t *>(d.zslot + (size_t)ps.p[i] * kZPlanes);
+        const uint32_t z03 = zs[0], z47 = d.nz > 4 ? zs[1] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < kZPlanes; ++j) {
+            const int slot = (int)(((j < 4 ? z03 : z47) >> (8 * (j & 3))) & 0xFFu);      // 0xFF (no term) is never a slot of the row
+            const bool has = row_has<W>(rows[i], slot);
+            const bool on = ((d.z_on_leader >> j) & 1) ? (has && (int)ps.ld[i] == slot) : has;
+            pobj += on ? d.z_value[j] : 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the whole candidate.  T: the two transposed planes; Z: the term planes [kZPlanes][nW]; bits: the row-major
+// base; prow: this candidate's patched rows [kMaxOps * W]; pviol / pobj: patch_terms of those rows
 // ------------------------------------------------------------------------------------------
 template <class Cfg, bool kShared>
-__device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt, const uint32_t *bitsT, const uint32_t *masksT,
-                                 const Consts *cs, const PatchSet &ps, const uint32_t *prow, int lane, int &viol_out, int &obj_out)
+__device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt, const uint32_t *bitsT, const uint32_t *Zp,
+                                 const Consts *cs, const PatchSet &ps, const uint32_t *prow, int pviol, int pobj, int lane,
+                                 int &viol_out, int &obj_out)
 {
     constexpr int W = Cfg::W, kNW = Cfg::kNW;
     constexpr int NSL = 32 * W;
     const int nW = kNW ? kNW : nW_rt;
-    const MemRef<kShared> T(Tp), B(bitsT);
-    // ---- rows: unpatched partitions from the transposed bit-plane, patched ones from the patch
-    int viol = rows_vertical<W, kShared, kNW>(T, B, nW, d.Ppad, d.P, d.RF, lane, ps);
-    if (lane < kMaxOps) {
-        const int i = lane;
-        const int pp = i == 0 ? ps.p[0] : (i == 1 ? ps.p[1] : ps.p[2]);
-        if (pp >= 0) {
-            uint32_t x[W];
-#pragma unroll
-            for (int t = 0; t < W; ++t) x[t] = prow[i * W + t];
-            viol += row_terms_hi1_s8<W>(x, d.RF);
-        }
-    }
+    const MemRef<kShared> T(Tp), B(bitsT), Z(Zp);
+    // ---- rows: unpatched partitions from the transposed bit-plane and the term planes, patched ones from the patch
+    int obj = 0;
+    int viol = rows_vertical<W, kShared, kNW>(d, T, Z, B, nW, lane, ps, obj);
+    if (lane == 0) { viol += pviol; obj += pobj; }
     // ---- columns: this lane owns slot `lane` of every row word
     PopStream<(Cfg::kPop >> 0) & 15> cnt[W];
     PopStream<(Cfg::kPop >> 4) & 15> lcnt[W];
-    PopStream<(Cfg::kPop >> 8) & 15> o0;
-    PopStream<(Cfg::kPop >> 12) & 15> o1;
-    PopStream<(Cfg::kPop >> 16) & 15> o2;
-    const int nch = nW >> 2;                        // <= 30 chunks of 128 partitions (P <= 3840)
+    const int nch = nW >> 2;                        // <= 32 chunks of 128 partitions (P <= 4096)
     uint32_t patched_chunks = 0;                    // bit j: a patched partition lies in chunk j
 #pragma unroll
     for (int i = 0; i < kMaxOps; ++i) patched_chunks |= ps.p[i] >= 0 ? 1u << (ps.p[i] >> 7) : 0u;
     int tw = nW >= 32 ? 4 * (lane & 7) : 0;        // physical word of logical word 0 (see t_word)
 #pragma unroll 1
     for (int j = 0; j < nch; ++j) {
-        uint4 col[W], oh[W], a0[W], a1[W], a2[W];
+        uint4 col[W], oh[W];
 #pragma unroll
         for (int t = 0; t < W; ++t) {
             const int s = lane + 32 * t;
             col[t] = T.ld128((uint32_t)((0 * NSL + s) * nW + tw) * 4u);
             oh[t] = T.ld128((uint32_t)((1 * NSL + s) * nW + tw) * 4u);
-            a0[t] = T.ld128((uint32_t)((2 * NSL + s) * nW + tw) * 4u);
-            a1[t] = T.ld128((uint32_t)((3 * NSL + s) * nW + tw) * 4u);
-            a2[t] = T.ld128((uint32_t)((4 * NSL + s) * nW + tw) * 4u);
         }
         tw += 4;
         tw -= (tw >= nW) ? nW : 0;
@@ -256,31 +281,17 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
                     for (int t = 0; t < W; ++t) {
                         const bool has = (prow[i * W + t] >> lane) & 1u;
                         const bool led = has && ((int)ps.ld[i] == lane + 32 * t);
-                        const bool m0 = (masksT[(size_t)(0 * W + t) * d.Ppad + pp] >> lane) & 1u;
-                        const bool m1 = (masksT[(size_t)(1 * W + t) * d.Ppad + pp] >> lane) & 1u;
-                        const bool m2 = (masksT[(size_t)(2 * W + t) * d.Ppad + pp] >> lane) & 1u;
                         set_comp(col[t], k, bit, has ? bit : 0u);
                         set_comp(oh[t], k, bit, led ? bit : 0u);
-                        set_comp(a0[t], k, bit, (has && m0) ? bit : 0u);
-                        set_comp(a1[t], k, bit, (has && m1) ? bit : 0u);
-                        set_comp(a2[t], k, bit, (led && m2) ? bit : 0u);
                     }
                 }
             }
         }
-        uint32_t hit[4];                            // leader bonus: the one-hot columns of a lane are disjoint
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hit[i] = 0;
 #pragma unroll
         for (int t = 0; t < W; ++t) {
             cnt[t].add4(col[t].x, col[t].y, col[t].z, col[t].w);
             lcnt[t].add4(oh[t].x, oh[t].y, oh[t].z, oh[t].w);
-            o0.add4(a0[t].x, a0[t].y, a0[t].z, a0[t].w);
-            o1.add4(a1[t].x, a1[t].y, a1[t].z, a1[t].w);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) hit[i] |= comp(a2[t], i);
         }
-        o2.add4(hit[0], hit[1], hit[2], hit[3]);
     }
     // ---- C3 / C4 on this lane's columns, C2/C5 as P - sum of valid leaders, C6 per 8-lane rack group
     // (rack totals: the W column totals of a lane travel packed in one word through three butterfly steps
@@ -304,7 +315,6 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
             if (rk < d.R) viol += max(tot - cs->rack_hi[rk], 0) + max(cs->rack_lo[rk] - tot, 0);
         }
     }
-    const int obj = o0.total() * d.plane_value[0] + o1.total() * d.plane_value[1] + o2.total() * d.plane_value[2];
     viol_out = __reduce_add_sync(0xFFFFFFFFu, viol) + d.P;
     obj_out = __reduce_add_sync(0xFFFFFFFFu, obj);
 }
@@ -314,8 +324,7 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
 // ------------------------------------------------------------------------------------------
 // one word (32 partitions) of plane q, slot s, gathered from the row-major tables
 template <int W>
-__device__ __forceinline__ uint32_t t_gather(int q, int s, int w, const uint32_t *bitsT, const uint8_t *leader,
-                                             const uint32_t *planesT, int Ppad)
+__device__ __forceinline__ uint32_t t_gather(int q, int s, int w, const uint32_t *bitsT, const uint8_t *leader, int Ppad)
 {
     uint32_t out = 0;
     const int sw = s >> 5, sb = s & 31;
@@ -323,19 +332,39 @@ __device__ __forceinline__ uint32_t t_gather(int q, int s, int w, const uint32_t
         const int p = 32 * w + b;
         const uint32_t has = (bitsT[(size_t)sw * Ppad + p] >> sb) & 1u;
         const uint32_t led = has & ((int)leader[p] == s ? 1u : 0u);
-        uint32_t bit;
-        if (q == 0) bit = has;
-        else if (q == 1) bit = led;
-        else bit = (q == 4 ? led : has) & ((planesT[((size_t)(q - 2) * W + sw) * Ppad + p] >> sb) & 1u);
-        out |= bit << b;
+        out |= (q == 0 ? has : led) << b;
     }
     return out;
 }
-// Row p of the base becomes (newrow, newld): every lane rewrites bit p of its own slots' words in all
-// five planes (the whole warp calls this; the row-major base itself is patched by the caller).
+// does term j of partition p hold for the row (row, ld)
 template <int W>
-__device__ __forceinline__ void t_patch_row(uint32_t *T, int nW, int Ppad, int p, const uint32_t (&newrow)[W], uint32_t newld,
-                                            const uint32_t *masksT, int lane)
+__device__ __forceinline__ bool z_term_holds(const Params &d, int j, int p, const uint32_t (&row)[W], uint32_t ld)
+{
+    const int slot = d.zslot[(size_t)p * kZPlanes + j];
+    const bool has = row_has<W>(row, slot);                     // 0xFF (no term) is never a slot of the row
+    return ((d.z_on_leader >> j) & 1) ? (has && (int)ld == slot) : has;
+}
+// one word (32 partitions) of term plane j
+template <int W>
+__device__ __forceinline__ uint32_t z_gather(const Params &d, int j, int w, const uint32_t *bitsT, const uint8_t *leader)
+{
+    uint32_t out = 0;
+    for (int b = 0; b < 32; ++b) {
+        const int p = 32 * w + b;
+        if (p >= d.P) break;
+        uint32_t row[W];
+#pragma unroll
+        for (int t = 0; t < W; ++t) row[t] = bitsT[(size_t)t * d.Ppad + p];
+        out |= (z_term_holds<W>(d, j, p, row, leader[p]) ? 1u : 0u) << b;
+    }
+    return out;
+}
+// Row p of the base becomes (newrow, newld): every lane rewrites bit p of its own slots' words in both
+// transposed planes, lanes 0..7 bit p of one term plane each (the whole warp calls this; the row-major base
+// itself is patched by the caller).
+template <int W>
+__device__ __forceinline__ void t_patch_row(const Params &d, uint32_t *T, uint32_t *Z, int nW, int p, const uint32_t (&newrow)[W],
+                                            uint32_t newld, int lane)
 {
     constexpr int NSL = 32 * W;
     const int w = p >> 5;
@@ -347,11 +376,14 @@ __device__ __forceinline__ void t_patch_row(uint32_t *T, int nW, int Ppad, int p
         const bool led = has && ((int)newld == s);
 #pragma unroll
         for (int q = 0; q < kTPlanes; ++q) {
-            bool on = q == 0 ? has : led;
-            if (q >= 2) on = (q == 4 ? led : has) && ((masksT[(size_t)((q - 2) * W + t) * Ppad + p] >> lane) & 1u);
+            const bool on = q == 0 ? has : led;
             uint32_t &word = T[t_word(q, s, w, nW, NSL)];
             word = on ? (word | bit) : (word & ~bit);
         }
+    }
+    if (lane < kZPlanes) {
+        uint32_t &word = Z[lane * nW + w];
+        word = z_term_holds<W>(d, lane, p, newrow, newld) ? (word | bit) : (word & ~bit);
     }
 }
 

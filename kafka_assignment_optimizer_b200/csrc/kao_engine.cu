@@ -197,7 +197,7 @@ struct kao_handle {
     int sch_sync = KAO_SCHEDULE_DEFAULT_SYNC, sch_pop = KAO_SCHEDULE_DEFAULT_POP, sch_threads = KAO_SCHEDULE_DEFAULT_THREADS;
     // device buffers
     uint32_t *d_bits = nullptr; uint8_t *d_leader = nullptr; uint32_t *d_sw = nullptr;
-    uint32_t *d_dense = nullptr; uint32_t *d_planes = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
+    uint32_t *d_dense = nullptr; uint32_t *d_planes = nullptr; uint8_t *d_zslot = nullptr; uint32_t *d_home = nullptr; uint16_t *d_D = nullptr; uint16_t *d_DL = nullptr; int *d_nD = nullptr;
     Consts *d_consts = nullptr; unsigned long long *d_key = nullptr; unsigned long long *d_keys = nullptr;
     size_t keys_cap = 0;
     long long *d_vo = nullptr;
@@ -412,12 +412,12 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     }
     if (h->plan.total > 227u * 1024u)
         return fail(KAO_E_ARG, "problem too large for the shared-memory resident search kernel");
-    // column-major evaluator: 8-slot rack fields, C7 = "at most one replica per rack", three mask planes;
-    // its five transposed planes and the row-major mask planes ((5 + 3) * W words per partition) take
-    // the place of the objective table.  It is the default full evaluator wherever it applies.
+    // column-major evaluator: 8-slot rack fields, C7 = "at most one replica per rack", an objective that fits
+    // eight term planes (kao_host.hpp); its two transposed planes (2 * W words per partition) and the term planes
+    // take the place of the objective table.  It is the default full evaluator wherever it applies.
     h->plan_t = make_plan_t(W, Ppad, KAO_THREADS, m.P, m.RF);
-    h->trans_ok = W <= 2 && m.hi1 && m.log2S == 3 && h->hm.nplanes == 3 &&
-                  column_major_fits(W, Ppad, KAO_THREADS, m.P, m.RF);     // incl. the inverted lists of its per-thread generator
+    h->trans_ok = W <= 2 && m.hi1 && m.log2S == 3 && m.z_ok &&
+                  column_major_fits(W, Ppad, 1024, m.P, m.RF);     // incl. the inverted lists of its per-thread generator
     if (h->trans_ok) h->evaluator = KAO_EVAL_COLUMN_MAJOR;
     if (const char *env = std::getenv("KAO_EVALUATOR"))       // "row" forces the row-major evaluator (measurements)
         if (std::strcmp(env, "row") == 0) h->evaluator = KAO_EVAL_ROW_MAJOR;
@@ -450,6 +450,10 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
         CUDA_TRY(cudaMemcpy(h->d_planes, m.planesT.data(), m.planesT.size() * 4, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemcpy(h->d_home, m.homeT.data(), m.homeT.size() * 4, cudaMemcpyHostToDevice));
+    if (m.z_ok) {
+        CUDA_TRY(dalloc(h, &h->d_zslot, m.zslot.size()));
+        CUDA_TRY(cudaMemcpy(h->d_zslot, m.zslot.data(), m.zslot.size(), cudaMemcpyHostToDevice));
+    }
     Consts cs;
     fill_consts(m, cs);
     CUDA_TRY(cudaMemcpy(h->d_consts, &cs, sizeof cs, cudaMemcpyHostToDevice));
@@ -462,6 +466,8 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     p.nentries = m.nentries; p.nplanes = m.nplanes; p.plane_on_leader = m.plane_on_leader;
     for (int c = 0; c < 6; ++c) p.plane_value[c] = m.plane_value[c];
     p.planesT = h->d_planes;
+    p.nz = m.z_ok ? m.nz : 0; p.z_on_leader = m.z_on_leader; p.zslot = h->d_zslot;
+    for (int j = 0; j < 8; ++j) p.z_value[j] = m.z_value[j];
     p.bitsT = h->d_bits; p.leader = h->d_leader; p.swT = h->d_sw; p.dense_w = h->d_dense;
     p.homeT = h->d_home; p.D = h->d_D; p.DL = h->d_DL; p.nD = h->d_nD; p.consts = h->d_consts;
     return reset_impl(h);

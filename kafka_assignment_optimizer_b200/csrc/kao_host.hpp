@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace kao {
@@ -28,6 +29,14 @@ struct HostModel {
     int nplanes = 0, plane_on_leader = 0;
     int plane_value[6] = {0, 0, 0, 0, 0, 0};
     std::vector<uint32_t> planesT;            // [nplanes][W][Ppad]
+    // sparse objective of the column-major evaluator (docs/MODEL.md §3.3): the non-zero terms of the objective
+    // row (README.md:145-146 lists exactly these) grouped into nz <= 8 TERM PLANES — all terms of a plane share
+    // one value and one kind (follower weight on the replica bit / leader bonus wL - wF on the leader bit) and a
+    // partition has at most one term per plane: objective = sum_j z_value[j] * |{p : term j of p holds}|
+    bool z_ok = false;                        // the term planes below describe the whole objective
+    int nz = 0, z_on_leader = 0;
+    int z_value[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<uint8_t> zslot;               // [Ppad][8] slot of partition p's term in plane j, 0xFF = none
     bool hi1 = false;                         // C7 is exactly "at most one replica per rack"
     int key_obj_bits = 24;                    // width of the cost field of a packed key (docs/MODEL.md 3)
     std::vector<uint32_t> dense_w;            // [P][NS] when dense
@@ -172,6 +181,62 @@ inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &w
                             m.planesT[((size_t)c * m.W + (s >> 5)) * m.Ppad + p] |= 1u << (s & 31);
                         }
                     }
+            }
+        }
+    }
+    // term planes: classes (kind, value) in ascending order, followers first; a class takes as many planes as
+    // its largest number of terms in one partition (terms of a partition in ascending slot order)
+    {
+        struct Term { int kind; uint32_t val; int slot; };
+        std::vector<std::pair<int, uint32_t>> classes;
+        std::vector<std::vector<Term>> terms(pb.P);
+        bool ok = true;
+        for (int p = 0; p < pb.P && ok; ++p)
+            for (int b = 0; b < pb.B; ++b) {
+                const uint32_t f = pb.wF[(size_t)p * pb.B + b], l = pb.wL[(size_t)p * pb.B + b];
+                if (l < f) { ok = false; break; }
+                if (f) terms[p].push_back({0, f, m.slot_of_broker[b]});
+                if (l - f) terms[p].push_back({1, l - f, m.slot_of_broker[b]});
+                if (terms[p].size() > 16) { ok = false; break; }
+            }
+        if (ok) {
+            for (int p = 0; p < pb.P; ++p)
+                for (const Term &t : terms[p]) {
+                    const std::pair<int, uint32_t> c(t.kind, t.val);
+                    if (std::find(classes.begin(), classes.end(), c) == classes.end()) classes.push_back(c);
+                    if (classes.size() > 8) ok = false;
+                }
+        }
+        if (ok) {
+            std::sort(classes.begin(), classes.end());
+            std::vector<int> mult(classes.size(), 0), first(classes.size(), 0);
+            for (int p = 0; p < pb.P; ++p) {
+                std::vector<int> n(classes.size(), 0);
+                for (const Term &t : terms[p]) {
+                    const size_t c = std::find(classes.begin(), classes.end(), std::pair<int, uint32_t>(t.kind, t.val)) - classes.begin();
+                    mult[c] = std::max(mult[c], ++n[c]);
+                }
+            }
+            int J = 0;
+            for (size_t c = 0; c < classes.size(); ++c) { first[c] = J; J += mult[c]; }
+            if (J <= 8) {
+                m.z_ok = true;
+                m.nz = J;
+                m.zslot.assign((size_t)m.Ppad * 8, 0xFF);
+                for (size_t c = 0; c < classes.size(); ++c)
+                    for (int k = 0; k < mult[c]; ++k) {
+                        m.z_value[first[c] + k] = (int)classes[c].second;
+                        if (classes[c].first) m.z_on_leader |= 1 << (first[c] + k);
+                    }
+                for (int p = 0; p < pb.P; ++p) {
+                    std::vector<Term> ts = terms[p];
+                    std::sort(ts.begin(), ts.end(), [](const Term &a, const Term &b) { return a.slot < b.slot; });
+                    std::vector<int> n(classes.size(), 0);
+                    for (const Term &t : ts) {
+                        const size_t c = std::find(classes.begin(), classes.end(), std::pair<int, uint32_t>(t.kind, t.val)) - classes.begin();
+                        m.zslot[(size_t)p * 8 + first[c] + n[c]++] = (uint8_t)t.slot;
+                    }
+                }
             }
         }
     }

@@ -72,20 +72,19 @@ __device__ __forceinline__ void build_oh_plane(uint32_t *s_bits, const uint8_t *
     __syncthreads();
 }
 
-// Column-major evaluator (kao_device_t.cuh): the five transposed planes are gathered once per launch
-// from the staged row-major base and the row-major objective mask planes; both take the place of the
-// objective table in the shared-memory plan ((5 + 3) * W words per partition at off_sw: the transposed
-// planes, then the row-major mask planes a patched row takes its mask bits from).
+// Column-major evaluator (kao_device_t.cuh): the two transposed planes and the term planes of the objective
+// are gathered once per launch from the staged row-major base (2 * W words per partition at off_sw, the term
+// planes at off_z).
 template <int W, int THREADS>
-__device__ __forceinline__ void build_t_planes(uint32_t *T, const uint32_t *s_bits, const uint8_t *s_leader,
-                                               const uint32_t *g_planes, int Ppad)
+__device__ __forceinline__ void build_t_planes(const Params &d, uint32_t *T, uint32_t *Z, const uint32_t *s_bits, const uint8_t *s_leader)
 {
     constexpr int NSL = 32 * W;
-    const int nW = Ppad >> 5, total = kTPlanes * NSL * nW;
+    const int nW = d.Ppad >> 5, total = kTPlanes * NSL * nW;
     for (int o = threadIdx.x; o < total; o += THREADS) {
         const int w = o % nW, s = (o / nW) % NSL, q = o / (nW * NSL);
-        T[t_word(q, s, w, nW, NSL)] = t_gather<W>(q, s, w, s_bits, s_leader, g_planes, Ppad);
+        T[t_word(q, s, w, nW, NSL)] = t_gather<W>(q, s, w, s_bits, s_leader, d.Ppad);
     }
+    for (int o = threadIdx.x; o < kZPlanes * nW; o += THREADS) Z[o] = z_gather<W>(d, o / nW, o % nW, s_bits, s_leader);
     __syncthreads();
 }
 
@@ -406,9 +405,9 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     constexpr int W = Cfg::W;
     const uint32_t *g_obj = Cfg::kObj > 0 ? d.planesT : d.swT;
     constexpr bool kObjShared = !(kDelta && W > 2);    // wide-row delta kernels read the objective table from HBM / L2
-    const uint32_t obj_words = !kObjShared ? 0u : (Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries);
-    // column-major evaluator: the row-major mask planes sit behind the five transposed planes
-    uint32_t *s_obj = Cfg::kTrans ? s_sw + (size_t)kTPlanes * W * d.Ppad : s_sw;
+    // (the column-major evaluator stages no objective table: it keeps term planes, built below)
+    const uint32_t obj_words = (!kObjShared || Cfg::kTrans) ? 0u : (Cfg::kObj > 0 ? (uint32_t)Cfg::kObj * W : (uint32_t)d.nentries);
+    uint32_t *s_z = reinterpret_cast<uint32_t *>(smem + plan.off_z);
 
     if (tid == 0) mbar_init(s_bar, 1);
     __syncthreads();
@@ -416,13 +415,13 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         const uint32_t nb = (uint32_t)W * d.Ppad * 4, ns = obj_words * d.Ppad * 4, nl = (uint32_t)d.Ppad;
         mbar_expect_tx(s_bar, nb + ns + nl + (uint32_t)sizeof(Consts));
         bulk_g2s(s_bits, d.bitsT, nb, s_bar);
-        if (ns) bulk_g2s(s_obj, g_obj, ns, s_bar);
+        if (ns) bulk_g2s(s_sw, g_obj, ns, s_bar);
         bulk_g2s(s_leader, d.leader, nl, s_bar);
         bulk_g2s(s_cs, d.consts, (uint32_t)sizeof(Consts), s_bar);
     }
     mbar_wait(s_bar, 0);
     if constexpr (has_oh_plane<Cfg>()) build_oh_plane<W, THREADS>(s_bits, s_leader, d.Ppad);
-    if constexpr (Cfg::kTrans) build_t_planes<W, THREADS>(s_sw, s_bits, s_leader, s_obj, d.Ppad);
+    if constexpr (Cfg::kTrans) build_t_planes<W, THREADS>(d, s_sw, s_z, s_bits, s_leader);
     rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
 
     Gen<W, false, Cfg::kTrans> gen;        // column-major kernels: compact generator code (same candidates)
@@ -506,13 +505,16 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                         for (int w = 0; w < W; ++w) rows[i][w] = 0;
                     }
                     if (it0 + lane < iters && idx < pp.idx_hi) tg.run(seed, round, idx, round_size, ps, rows);
+                    int pviol, pobj;
+                    patch_terms<W>(d, ps, rows, pviol, pobj);
                     uint32_t *mine = batch + lane * BS;
                     mine[0] = (uint32_t)ps.p[0]; mine[1] = (uint32_t)ps.p[1]; mine[2] = (uint32_t)ps.p[2];
                     mine[3] = (ps.ld[0] & 0xFFu) | ((ps.ld[1] & 0xFFu) << 8) | ((ps.ld[2] & 0xFFu) << 16) | ((uint32_t)ps.n << 24);
+                    mine[4] = (uint32_t)pviol; mine[5] = (uint32_t)pobj;
 #pragma unroll
                     for (int i = 0; i < kMaxOps; ++i)
 #pragma unroll
-                        for (int w = 0; w < W; ++w) mine[4 + i * W + w] = rows[i][w];
+                        for (int w = 0; w < W; ++w) mine[kBatchHdr + i * W + w] = rows[i][w];
                 }
                 __syncwarp();
                 const uint32_t nb = iters - it0 < 32u ? iters - it0 : 32u;
@@ -526,8 +528,10 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                         ps.p[0] = (int)hdr.x; ps.p[1] = (int)hdr.y; ps.p[2] = (int)hdr.z;
                         ps.ld[0] = hdr.w & 0xFFu; ps.ld[1] = (hdr.w >> 8) & 0xFFu; ps.ld[2] = (hdr.w >> 16) & 0xFFu;
                         ps.n = (int)(hdr.w >> 24);
+                        const uint2 terms = *reinterpret_cast<const uint2 *>(slot + 4);
                         int viol, obj;
-                        eval_candidate_t<Cfg, true>(d, s_sw, d.Ppad >> 5, s_bits, s_obj, s_cs, ps, slot + 4, lane, viol, obj);
+                        eval_candidate_t<Cfg, true>(d, s_sw, d.Ppad >> 5, s_bits, s_z, s_cs, ps, slot + kBatchHdr, (int)terms.x, (int)terms.y,
+                                                    lane, viol, obj);
                         const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
                         if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = key;
                         best = key < best ? key : best;
@@ -667,7 +671,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                             uint32_t newrow[W];
 #pragma unroll
                             for (int w = 0; w < W; ++w) newrow[w] = gen.prow[i * W + w];
-                            t_patch_row<W>(s_sw, d.Ppad >> 5, d.Ppad, ps.p[i], newrow, ps.ld[i], s_obj, lane);
+                            t_patch_row<W>(d, s_sw, s_z, d.Ppad >> 5, ps.p[i], newrow, ps.ld[i], lane);
                         }
                     }
                 }
@@ -714,9 +718,9 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 // Column-major kernels: X(sync, pop, threads) for every built schedule (kao_set_schedule); each is
 // instantiated for W = 1, 2 and for 32 partition words (compile-time offsets) / any word count.
 #define KAO_FOR_SCHEDULES(X) \
-    X(1, 0x22222, 640) X(1, 0x22233, 640) X(1, 0x11133, 640) X(1, 0x22222, 512) X(0, 0x22222, 640) X(1, 0x11111, 768)
+    X(1, 0x22, 640) X(1, 0x22, 768) X(1, 0x22, 1024) X(1, 0x11, 768) X(1, 0x33, 768) X(0, 0x22, 768)
 #define KAO_SCHEDULE_DEFAULT_SYNC 1
-#define KAO_SCHEDULE_DEFAULT_POP 0x22222
+#define KAO_SCHEDULE_DEFAULT_POP 0x22
 #define KAO_SCHEDULE_DEFAULT_THREADS 640
 #define KAO_PERSISTENT_KERNEL_T(W, NW, S, POP, T)                                                            \
     search_persistent_kernel<EvalCfgT<W, NW, S, POP, T>, T, false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \

@@ -14,17 +14,19 @@ using namespace kao;
 // shared-memory plan of the search kernel
 // ------------------------------------------------------------------------------------------
 struct SmemPlan {
-    uint32_t off_bits, off_sw, off_leader, off_consts, off_prow, off_red, off_bar, off_lists, off_totals, off_inv, total;
+    uint32_t off_bits, off_sw, off_z, off_leader, off_consts, off_prow, off_red, off_bar, off_lists, off_totals, off_inv, total;
     uint32_t cap_hold, cap_led;      // delta mode: capacity of the inverted lists (0 = not staged)
 };
 // Column-major kernels: the 32 lanes of a warp generate 32 candidates at once and park them in the warp's
-// scratch.  Words per candidate: 3 partitions, (leader slots | count << 24), 3 x W row words, 16-byte aligned.
-__host__ __device__ constexpr int batch_stride_words(int W) { return (4 + kMaxOps * W + 3) & ~3; }
+// scratch.  Words per candidate: 3 partitions, (leader slots | count << 24), the C1 / C7 terms and the objective
+// terms of the patched rows (patch_terms), 3 x W row words; 16-byte aligned.
+constexpr int kBatchHdr = 6;
+__host__ __device__ constexpr int batch_stride_words(int W) { return (kBatchHdr + kMaxOps * W + 3) & ~3; }
 
 // prow_words_per_warp: per-warp scratch for patched rows (kMaxOps * W), or a whole batch of candidates
 // lists: 1 stage the inverted lists of the per-thread generator if they fit, 0 never, -1 = for rows of up to 64 slots
 inline SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int P, int RF, bool oh_plane,
-                          int prow_words_per_warp = 0, int lists = -1)
+                          int prow_words_per_warp = 0, int lists = -1, int z_bytes = 0)
 {
     if (prow_words_per_warp <= 0) prow_words_per_warp = kMaxOps * W;
     SmemPlan s;
@@ -32,6 +34,7 @@ inline SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int
     s.off_bits = o;   o += (uint32_t)W * Ppad * 4;
     if (oh_plane) o += (uint32_t)W * Ppad * 4;            // leader one-hot plane, directly behind the bit-plane
     s.off_sw = o;     o += (uint32_t)obj_words_per_row * Ppad * 4;
+    s.off_z = o;      o += (uint32_t)z_bytes;               // term planes of the column-major evaluator
     s.off_leader = o; o += (uint32_t)Ppad;
     s.off_consts = o; o += (uint32_t)sizeof(Consts);
     o = (o + 15u) & ~15u;
@@ -57,17 +60,17 @@ inline SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int
     return s;
 }
 
-// shared-memory plan of a column-major kernel: transposed planes + row-major mask planes in place of the
+// shared-memory plan of a column-major kernel: the two transposed planes + the term planes in place of the
 // objective table, a batch of candidates per warp, the inverted lists of the per-thread generator
 inline SmemPlan make_plan_t(int W, int Ppad, int threads, int P, int RF)
 {
-    return make_plan(W, Ppad, threads / 32, (kTPlanes + kTMaskPlanes) * W, P, RF, false, 32 * batch_stride_words(W));
+    return make_plan(W, Ppad, threads / 32, kTPlanes * W, P, RF, false, 32 * batch_stride_words(W), -1, kZPlanes * (Ppad / 32) * 4);
 }
 // does the column-major evaluator cover this layout (kao_create; tests/emu asks the same question)
 inline bool column_major_fits(int W, int Ppad, int threads, int P, int RF)
 {
     const SmemPlan s = make_plan_t(W, Ppad, threads, P, RF);
-    return s.total <= 227u * 1024u && s.cap_hold > 0;
+    return s.total <= 227u * 1024u && s.cap_hold > 0 && Ppad <= 4096;      // <= 32 chunks of 128 partitions (patched_chunks)
 }
 
 // shared-memory plan of a delta kernel for rows wider than 64 slots: the base, the per-round tables and the

@@ -49,8 +49,8 @@ class EmuSession:
     def set_evaluator(self, mode):
         """0: row-major evaluator; 1: column-major evaluator (csrc/kao_device_t.cuh) as the engine picks it;
         2: its run-time-sized form even where the 32-word specialisation applies; 3: a POPC per word
-        (kPop = 0x00000); 4: kPop = 0x11122; 5: kPop = 0x11133 (Harley-Seal on the column / leader totals);
-        6: kPop = 0x22233.  False is returned for unsupported layouts."""
+        (kPop = 0x00); 4: kPop = 0x11; 5: kPop = 0x23 (Harley-Seal on the column totals); 6: kPop = 0x33
+        (Harley-Seal on both streams).  False is returned for unsupported layouts."""
         return lib().kao_emu_set_evaluator(self._h, C.c_int32(mode)) == 0
 
     def set_base(self, replicas):

@@ -37,7 +37,7 @@ struct Emu {
     bool trans_ok = false;
     int trans = 0;                       // 0 row-major evaluator, 1.. forms (schedules) of the column-major one
     int nW = 0;
-    std::vector<uint32_t> T;
+    std::vector<uint32_t> T, Z;          // transposed planes, term planes of the objective
     std::string err;
 };
 
@@ -48,7 +48,10 @@ template <int W> void build_T(Emu &e)
     for (int q = 0; q < kTPlanes; ++q)
         for (int s = 0; s < 32 * W; ++s)
             for (int w = 0; w < e.nW; ++w)
-                e.T[t_word(q, s, w, e.nW, 32 * W)] = t_gather<W>(q, s, w, e.bits.data(), e.leader.data(), m.planesT.data(), m.Ppad);
+                e.T[t_word(q, s, w, e.nW, 32 * W)] = t_gather<W>(q, s, w, e.bits.data(), e.leader.data(), m.Ppad);
+    e.Z.assign((size_t)kZPlanes * e.nW, 0);
+    for (int j = 0; j < kZPlanes; ++j)
+        for (int w = 0; w < e.nW; ++w) e.Z[(size_t)j * e.nW + w] = z_gather<W>(e.prm, j, w, e.bits.data(), e.leader.data());
 }
 
 uint32_t oh_word(uint32_t x, uint32_t ld, int w) { return ((int)(ld >> 5) == w) ? (x & (1u << (ld & 31u))) : 0u; }
@@ -114,20 +117,25 @@ template <class Cfg> struct Run {
             int viol, obj;
             if constexpr (W <= 2) {
                 // forms of the column-major evaluator: 1 as the engine picks it (32-word specialisation where it
-                // applies, default popcount streams), 2 run-time word count, 3 a POPC per word, 4 two POPC per four
-                // words on the totals, 5 Harley-Seal on the totals, 6 carry-save on every stream
+                // applies, default popcount streams), 2 run-time word count, 3 a POPC per word, 4 three POPC per four
+                // words, 5 Harley-Seal on the column totals, 6 Harley-Seal on both streams
                 const bool fixed = e.nW == 32;
-#define KAO_EMU_T(NW_, POP_) eval_candidate_t<EvalCfgT<W, NW_, 1, POP_>, true>(e.prm, e.T.data(), e.nW, e.bits.data(), e.prm.planesT, &e.cs, ps, e.prow.data(), lane, viol, obj)
-                if (e.trans == 1 && fixed) KAO_EMU_T(32, 0x11111);
-                else if (e.trans == 1 || e.trans == 2) KAO_EMU_T(0, 0x11111);
-                else if (e.trans == 3 && fixed) KAO_EMU_T(32, 0x00000);
-                else if (e.trans == 3) KAO_EMU_T(0, 0x00000);
-                else if (e.trans == 4 && fixed) KAO_EMU_T(32, 0x11122);
-                else if (e.trans == 4) KAO_EMU_T(0, 0x11122);
-                else if (e.trans == 5 && fixed) KAO_EMU_T(32, 0x11133);
-                else if (e.trans == 5) KAO_EMU_T(0, 0x11133);
-                else if (e.trans == 6 && fixed) KAO_EMU_T(32, 0x22233);
-                else if (e.trans == 6) KAO_EMU_T(0, 0x22233);
+                uint32_t prows[kMaxOps][W];
+                for (int i = 0; i < kMaxOps; ++i)
+                    for (int t = 0; t < W; ++t) prows[i][t] = ps.p[i] >= 0 ? e.prow[i * W + t] : 0u;
+                int pviol = 0, pobj = 0;
+                if (e.trans) patch_terms<W>(e.prm, ps, prows, pviol, pobj);      // per candidate, as the per-thread generator does
+#define KAO_EMU_T(NW_, POP_) eval_candidate_t<EvalCfgT<W, NW_, 1, POP_>, true>(e.prm, e.T.data(), e.nW, e.bits.data(), e.Z.data(), &e.cs, ps, e.prow.data(), pviol, pobj, lane, viol, obj)
+                if (e.trans == 1 && fixed) KAO_EMU_T(32, 0x22);
+                else if (e.trans == 1 || e.trans == 2) KAO_EMU_T(0, 0x22);
+                else if (e.trans == 3 && fixed) KAO_EMU_T(32, 0x00);
+                else if (e.trans == 3) KAO_EMU_T(0, 0x00);
+                else if (e.trans == 4 && fixed) KAO_EMU_T(32, 0x11);
+                else if (e.trans == 4) KAO_EMU_T(0, 0x11);
+                else if (e.trans == 5 && fixed) KAO_EMU_T(32, 0x23);
+                else if (e.trans == 5) KAO_EMU_T(0, 0x23);
+                else if (e.trans == 6 && fixed) KAO_EMU_T(32, 0x33);
+                else if (e.trans == 6) KAO_EMU_T(0, 0x33);
 #undef KAO_EMU_T
                 else eval_candidate<Cfg, true>(e.prm, e.bits.data(), e.leader.data(), objT, &e.cs, ps, e.prow.data(), lane, viol, obj);
             } else {
@@ -155,7 +163,7 @@ template <class Cfg> struct Run {
                     uint32_t newrow[W];
                     for (int w = 0; w < W; ++w) newrow[w] = e.prow[i * W + w];
                     for (int lane = 0; lane < 32; ++lane)
-                        t_patch_row<W>(e.T.data(), e.nW, Ppad, win.p[i], newrow, win.ld[i], e.prm.planesT, lane);
+                        t_patch_row<W>(e.prm, e.T.data(), e.Z.data(), e.nW, win.p[i], newrow, win.ld[i], lane);
                 }
             }
             for (int w = 0; w < W; ++w) {
@@ -240,8 +248,8 @@ void *kao_emu_create(const kao_problem *pb)
     e->obj = (m.W <= 2 && m.nplanes == 3) ? 3 : 0;
     e->oh = m.W <= 2 && e->obj > 0;
     // kao_set_evaluator: the column-major evaluator covers 8-slot rack fields with C7 = "at most one
-    // replica per rack" and three mask planes
-    e->trans_ok = m.W <= 2 && m.hi1 && m.log2S == 3 && m.nplanes == 3 && column_major_fits(m.W, m.Ppad, threads, m.P, m.RF);
+    // replica per rack" and an objective of up to eight term planes
+    e->trans_ok = m.W <= 2 && m.hi1 && m.log2S == 3 && m.z_ok && column_major_fits(m.W, m.Ppad, 1024, m.P, m.RF);
     e->nW = m.Ppad / 32;
     fill_consts(m, e->cs);
     Params &p = e->prm;
@@ -254,6 +262,8 @@ void *kao_emu_create(const kao_problem *pb)
     p.planesT = m.nplanes > 0 ? m.planesT.data() : nullptr;
     p.dense_w = m.dense ? m.dense_w.data() : nullptr;
     p.homeT = m.homeT.data();
+    p.nz = m.z_ok ? m.nz : 0; p.z_on_leader = m.z_on_leader; p.zslot = m.z_ok ? m.zslot.data() : nullptr;
+    for (int j = 0; j < 8; ++j) p.z_value[j] = m.z_value[j];
     p.consts = &e->cs;
     e->D.assign(m.Ppad, 0);
     e->DL.assign(m.Ppad, 0);
