@@ -51,14 +51,18 @@ struct EvalCfgT {
 constexpr int kTPlanes = 2;
 constexpr int kZPlanes = 8;          // term planes of the objective: [kZPlanes][nW] words behind the transposed planes
 
-// physical word of (plane q, slot s, partition word w).  Rows are rotated by 4 * (s & 7) words so
-// that the 128-bit column loads of a quarter warp (8 consecutive slots) hit 8 different bank groups;
-// the 32-bit row loads of a warp (32 consecutive words of one slot) stay conflict-free.
+// physical word of (plane q, slot s, partition word w).  The words of slot s are permuted inside every
+// aligned group of 32 by XOR with 4 * (s & 7), so that the 128-bit column loads of a quarter warp (8 consecutive
+// slots, same logical chunk) hit 8 different bank groups while the 32-bit row loads of a warp (32 consecutive
+// words of one slot) stay conflict-free; a lane finds logical chunk j of its slot at physical chunk j ^ (s & 7)
+// with one XOR.  (Fewer than 32 words per slot: not permuted.)
+__host__ __device__ __forceinline__ bool t_swizzled(int nW) { return nW >= 32 && (nW & 31) == 0; }
+// partition words per slot of the transposed planes and per term plane: Ppad / 32, rounded up to whole groups of
+// 32 words once there are more than 32 (the padding words stay empty)
+__host__ __device__ __forceinline__ int t_words(int Ppad) { const int n = Ppad >> 5; return n > 32 ? (n + 31) & ~31 : n; }
 __host__ __device__ __forceinline__ int t_word(int q, int s, int w, int nW, int NSL)
 {
-    int t = w + (nW >= 32 ? 4 * (s & 7) : 0);
-    t -= (t >= nW) ? nW : 0;
-    return (q * NSL + s) * nW + t;
+    return (q * NSL + s) * nW + (t_swizzled(nW) ? (w ^ (4 * (s & 7))) : w);
 }
 
 // C1 + C7 of one row held row-major (a patched row of the candidate, or a row the vertical pass
@@ -105,11 +109,7 @@ __device__ __forceinline__ int rows_vertical(const Params &d, const MemRef<kShar
         }
         int tk[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            int t = w + (nW >= 32 ? 4 * k : 0);
-            t -= (t >= nW) ? nW : 0;
-            tk[k] = t;
-        }
+        for (int k = 0; k < 8; ++k) tk[k] = t_swizzled(nW) ? (w ^ (4 * k)) : w;
         uint32_t any[NB], dup = 0;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -254,22 +254,33 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
     PopStream<(Cfg::kPop >> 0) & 15> cnt[W];
     PopStream<(Cfg::kPop >> 4) & 15> lcnt[W];
     const int nch = nW >> 2;                        // <= 32 chunks of 128 partitions (P <= 4096)
+    // the candidate's patched rows replace their partition's bit in this lane's columns: per patch the chunk,
+    // the word of the chunk, the bit and what this lane's slots hold there in the candidate
     uint32_t patched_chunks = 0;                    // bit j: a patched partition lies in chunk j
+    uint32_t sub_has[kMaxOps][W], sub_led[kMaxOps][W];
 #pragma unroll
-    for (int i = 0; i < kMaxOps; ++i) patched_chunks |= ps.p[i] >= 0 ? 1u << (ps.p[i] >> 7) : 0u;
-    int tw = nW >= 32 ? 4 * (lane & 7) : 0;        // physical word of logical word 0 (see t_word)
-#pragma unroll 1
-    for (int j = 0; j < nch; ++j) {
+    for (int i = 0; i < kMaxOps; ++i) {
+        const int pp = ps.p[i];
+        patched_chunks |= pp >= 0 ? 1u << (pp >> 7) : 0u;
+        const uint32_t bit = 1u << (pp & 31);
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const bool has = pp >= 0 && ((prow[i * W + t] >> lane) & 1u);
+            sub_has[i][t] = has ? bit : 0u;
+            sub_led[i][t] = (has && (int)ps.ld[i] == lane + 32 * t) ? bit : 0u;
+        }
+    }
+    const bool swz = t_swizzled(nW);
+    const uint32_t rot = swz ? 16u * (uint32_t)(lane & 7) : 0u;     // byte offset XORed into the chunk offset
+    auto chunk = [&](int j) {
+        const uint32_t off = ((uint32_t)j * 16u) ^ rot;             // logical chunk j of this lane's slots
         uint4 col[W], oh[W];
 #pragma unroll
         for (int t = 0; t < W; ++t) {
             const int s = lane + 32 * t;
-            col[t] = T.ld128((uint32_t)((0 * NSL + s) * nW + tw) * 4u);
-            oh[t] = T.ld128((uint32_t)((1 * NSL + s) * nW + tw) * 4u);
+            col[t] = T.ld128((uint32_t)((0 * NSL + s) * nW) * 4u + off);
+            oh[t] = T.ld128((uint32_t)((1 * NSL + s) * nW) * 4u + off);
         }
-        tw += 4;
-        tw -= (tw >= nW) ? nW : 0;
-        // the candidate's patched rows replace their partition's bit in this lane's columns
         if ((patched_chunks >> j) & 1u) {
 #pragma unroll
             for (int i = 0; i < kMaxOps; ++i) {
@@ -279,10 +290,8 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
                     const uint32_t bit = 1u << (pp & 31);
 #pragma unroll
                     for (int t = 0; t < W; ++t) {
-                        const bool has = (prow[i * W + t] >> lane) & 1u;
-                        const bool led = has && ((int)ps.ld[i] == lane + 32 * t);
-                        set_comp(col[t], k, bit, has ? bit : 0u);
-                        set_comp(oh[t], k, bit, led ? bit : 0u);
+                        set_comp(col[t], k, bit, sub_has[i][t]);
+                        set_comp(oh[t], k, bit, sub_led[i][t]);
                     }
                 }
             }
@@ -292,6 +301,13 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
             cnt[t].add4(col[t].x, col[t].y, col[t].z, col[t].w);
             lcnt[t].add4(oh[t].x, oh[t].y, oh[t].z, oh[t].w);
         }
+    };
+    if constexpr (kNW == 32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) chunk(j);
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < nch; ++j) chunk(j);
     }
     // ---- C3 / C4 on this lane's columns, C2/C5 as P - sum of valid leaders, C6 per 8-lane rack group
     // (rack totals: the W column totals of a lane travel packed in one word through three butterfly steps
@@ -330,6 +346,7 @@ __device__ __forceinline__ uint32_t t_gather(int q, int s, int w, const uint32_t
     const int sw = s >> 5, sb = s & 31;
     for (int b = 0; b < 32; ++b) {
         const int p = 32 * w + b;
+        if (p >= Ppad) break;                       // padding words of the plane (t_words)
         const uint32_t has = (bitsT[(size_t)sw * Ppad + p] >> sb) & 1u;
         const uint32_t led = has & ((int)leader[p] == s ? 1u : 0u);
         out |= (q == 0 ? has : led) << b;

@@ -79,7 +79,7 @@ template <int W, int THREADS>
 __device__ __forceinline__ void build_t_planes(const Params &d, uint32_t *T, uint32_t *Z, const uint32_t *s_bits, const uint8_t *s_leader)
 {
     constexpr int NSL = 32 * W;
-    const int nW = d.Ppad >> 5, total = kTPlanes * NSL * nW;
+    const int nW = t_words(d.Ppad), total = kTPlanes * NSL * nW;
     for (int o = threadIdx.x; o < total; o += THREADS) {
         const int w = o % nW, s = (o / nW) % NSL, q = o / (nW * NSL);
         T[t_word(q, s, w, nW, NSL)] = t_gather<W>(q, s, w, s_bits, s_leader, d.Ppad);
@@ -362,8 +362,8 @@ __device__ __forceinline__ void build_round_tables(const RoundTables &rt, const 
     }
     __syncthreads();
 }
-template <int W>
-__device__ __forceinline__ void bind_tables(Gen<W, true> &tg, const RoundTables &rt)
+template <int W, bool kSmall>
+__device__ __forceinline__ void bind_tables(Gen<W, true, kSmall> &tg, const RoundTables &rt)
 {
     tg.inv_ok = *rt.inv != 0; tg.hoff = rt.hoff; tg.loff = rt.loff; tg.hold = rt.hold; tg.led = rt.led;
 }
@@ -461,7 +461,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             Gen<W, true> tg;
             tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
             tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
-            bind_tables<W>(tg, rt);
+            bind_tables(tg, rt);
             const MemRef<kObjShared> m_obj(kObjShared ? s_sw : g_obj);
             const int base_viol = s_base[0], base_obj = s_base[1];
             const uint32_t tstride = gridDim.x * THREADS;
@@ -486,10 +486,10 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             // generator over the round's inverted lists), then evaluated in full one after the other by the warp
             const RoundTables rt = round_tables(smem, plan);
             build_round_tables<W, THREADS>(rt, plan, d, s_bits, s_leader);
-            Gen<W, true> tg;
+            Gen<W, true, true> tg;        // compact code (row_kth keeps its loop), same candidates
             tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
             tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
-            bind_tables<W>(tg, rt);
+            bind_tables(tg, rt);
             constexpr int BS = batch_stride<W>();
             uint32_t *batch = s_prow + (size_t)warp * 32 * BS;
             for (uint32_t it0 = 0; it0 < iters; it0 += 32) {
@@ -530,7 +530,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                         ps.n = (int)(hdr.w >> 24);
                         const uint2 terms = *reinterpret_cast<const uint2 *>(slot + 4);
                         int viol, obj;
-                        eval_candidate_t<Cfg, true>(d, s_sw, d.Ppad >> 5, s_bits, s_z, s_cs, ps, slot + kBatchHdr, (int)terms.x, (int)terms.y,
+                        eval_candidate_t<Cfg, true>(d, s_sw, t_words(d.Ppad), s_bits, s_z, s_cs, ps, slot + kBatchHdr, (int)terms.x, (int)terms.y,
                                                     lane, viol, obj);
                         const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
                         if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = key;
@@ -644,10 +644,10 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                 PatchSet ps;
                 if constexpr (Cfg::kTrans) {
                     // every lane re-materialises the same winner with the per-thread generator; lane 0 parks its rows
-                    Gen<W, true> tg;
+                    Gen<W, true, true> tg;        // compact code (row_kth keeps its loop), same candidates
                     tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
                     tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
-                    bind_tables<W>(tg, round_tables(smem, plan));
+                    bind_tables(tg, round_tables(smem, plan));
                     uint32_t rows[kMaxOps][W];
 #pragma unroll
                     for (int i = 0; i < kMaxOps; ++i)
@@ -671,7 +671,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                             uint32_t newrow[W];
 #pragma unroll
                             for (int w = 0; w < W; ++w) newrow[w] = gen.prow[i * W + w];
-                            t_patch_row<W>(d, s_sw, s_z, d.Ppad >> 5, ps.p[i], newrow, ps.ld[i], lane);
+                            t_patch_row<W>(d, s_sw, s_z, t_words(d.Ppad), ps.p[i], newrow, ps.ld[i], lane);
                         }
                     }
                 }
@@ -718,7 +718,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 // Column-major kernels: X(sync, pop, threads) for every built schedule (kao_set_schedule); each is
 // instantiated for W = 1, 2 and for 32 partition words (compile-time offsets) / any word count.
 #define KAO_FOR_SCHEDULES(X) \
-    X(1, 0x22, 640) X(1, 0x22, 768) X(1, 0x22, 1024) X(1, 0x11, 768) X(1, 0x33, 768) X(0, 0x22, 768)
+    X(1, 0x22, 640) X(1, 0x22, 768) X(1, 0x21, 640) X(1, 0x12, 640) X(1, 0x00, 640) X(0, 0x22, 640)
 #define KAO_SCHEDULE_DEFAULT_SYNC 1
 #define KAO_SCHEDULE_DEFAULT_POP 0x22
 #define KAO_SCHEDULE_DEFAULT_THREADS 640

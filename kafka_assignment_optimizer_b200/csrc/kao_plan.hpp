@@ -64,7 +64,12 @@ inline SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int
 // objective table, a batch of candidates per warp, the inverted lists of the per-thread generator
 inline SmemPlan make_plan_t(int W, int Ppad, int threads, int P, int RF)
 {
-    return make_plan(W, Ppad, threads / 32, kTPlanes * W, P, RF, false, 32 * batch_stride_words(W), -1, kZPlanes * (Ppad / 32) * 4);
+    // make_plan sizes the area at off_sw in words per partition of Ppad: the transposed planes hold t_words(Ppad)
+    // words per slot, which is Ppad / 32 or (more than 1024 partitions) up to 31 words more — one extra word per
+    // partition covers that for every Ppad the evaluator accepts
+    const int nW = t_words(Ppad);
+    const int per_row = (kTPlanes * W * 32 * nW + Ppad - 1) / Ppad;
+    return make_plan(W, Ppad, threads / 32, per_row, P, RF, false, 32 * batch_stride_words(W), -1, kZPlanes * nW * 4);
 }
 // does the column-major evaluator cover this layout (kao_create; tests/emu asks the same question)
 inline bool column_major_fits(int W, int Ppad, int threads, int P, int RF)

@@ -250,7 +250,7 @@ void *kao_emu_create(const kao_problem *pb)
     // kao_set_evaluator: the column-major evaluator covers 8-slot rack fields with C7 = "at most one
     // replica per rack" and an objective of up to eight term planes
     e->trans_ok = m.W <= 2 && m.hi1 && m.log2S == 3 && m.z_ok && column_major_fits(m.W, m.Ppad, 1024, m.P, m.RF);
-    e->nW = m.Ppad / 32;
+    e->nW = t_words(m.Ppad);
     fill_consts(m, e->cs);
     Params &p = e->prm;
     p.P = m.P; p.Ppad = m.Ppad; p.B = m.B; p.R = m.R; p.RF = m.RF; p.NS = m.NS; p.log2S = m.log2S;
