@@ -172,10 +172,10 @@ int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
 /* Full-evaluation kernel used by kao_search / kao_search_sharded / kao_candidate_keys of this session.
  * Both evaluate every row and column of every candidate (C1..C7 + objective, README.md:144-185) and
  * return bit-identical keys; they differ in how the base is laid out in shared memory:
- *   KAO_EVAL_COLUMN_MAJOR  also one bitmap over the partitions per broker slot; needs rows of up to 64
- *                          slots, racks of up to 8 brokers, C7 = at most one replica per rack, three
- *                          objective mask planes, and its planes in shared memory (P <= 2048 for two-word rows,
- *                          P <= 3840 for one-word rows);
+ *   KAO_EVAL_COLUMN_MAJOR  also one bitmap over the partitions per broker slot (replicas, leader one-hot) and the
+ *                          objective as term planes over the partitions; needs rows of up to 64 slots, racks of up
+ *                          to 8 brokers, C7 = at most one replica per rack, wL >= wF with the non-zero terms of the
+ *                          objective row (README.md:145-146) fitting 8 term planes (docs/MODEL.md 3.2), P <= 4096;
  *                          the DEFAULT wherever it applies; KAO_E_ARG when requested elsewhere
  *   KAO_EVAL_ROW_MAJOR     rows of the (partition x broker) bit-plane, column totals by bit-sliced
  *                          counters; every layout */
@@ -184,12 +184,12 @@ int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
 int kao_set_evaluator(kao_handle *h, int32_t evaluator);
 /* Schedule of the column-major evaluator: the same arithmetic, laid out differently in time.  sync: how
  * the warps of a CTA meet before an evaluation (0 block barrier, 1 warp only); pop: one hex digit per
- * popcount stream (column totals, leader totals, two follower-weight sums, leader bonus; lowest digit
- * first): 0 a POPC per word, 1 three per four words, 2 two, 3 one (carry-save adders do the rest);
- * threads per CTA: 768 or 512.  Only the combinations built into the library are accepted
- * (KAO_E_ARG otherwise); the default is the fastest one measured on a B200 (profiles/).  Results never
- * depend on it.  The environment variable KAO_SCHEDULE="sync,pop(hex),threads" sets it for every
- * session (and kao_solve); KAO_EVALUATOR=row forces the row-major evaluator. */
+ * popcount stream (column totals in the low digit, leader totals in the next): 0 a POPC per word, 1 three per
+ * four words, 2 two, 3 one (carry-save adders do the rest); threads per CTA: 640 or 768.  Only the six
+ * combinations built into the library are accepted (KAO_E_ARG otherwise); the default (1, 0x22, 640) is the
+ * fastest one measured on a B200 (profiles/).  Results never depend on it.  The environment variable
+ * KAO_SCHEDULE="sync,pop(hex),threads" sets it for every session (and kao_solve); KAO_EVALUATOR=row forces
+ * the row-major evaluator. */
 int kao_set_schedule(kao_handle *h, int32_t sync, int32_t pop, int32_t threads);
 /* what kao_search of this session runs right now: evaluator (KAO_EVAL_*) and the schedule of the column-major one */
 int kao_get_evaluator(kao_handle *h, int32_t *evaluator, int32_t *sync, int32_t *pop, int32_t *threads);
