@@ -260,6 +260,14 @@ def main():
         # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # host-side barriers (gloo): while rank 0 drives ALL GPUs through one kao_solve call (e2e), the other ranks
+        # must leave their GPUs idle — an NCCL barrier is a kernel that spins on the GPU, and a cooperative launch
+        # of another process on that GPU then has to wait for a time slice (measured: 50 ms instead of 12 ms per solve)
+        try:
+            host_group = dist.new_group(backend="gloo")
+        except Exception as e:                                    # no usable interface for gloo: fall back to NCCL barriers
+            print("bench: gloo group unavailable (%s); e2e at N > 1 will see time-slicing" % e, file=sys.stderr)
+            host_group = None
     dev = torch.device("cuda", local)
 
     pb = kao.synthetic_problem(*cfg_args)
@@ -296,6 +304,14 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            if host_group is not None:
+                dist.barrier(group=host_group)
+            else:
+                dist.barrier()
 
     # N > 1, untimed: the sharded search walks the single-GPU trajectory (the 2-GPU pytest is
     # skipped on a 1-GPU box, so the proof travels with the scaling run)
@@ -384,6 +400,7 @@ def main():
     # N > 1 rank 0 makes ONE kao_solve call with n_gpus = N; the other ranks wait at the barrier.
     e2e = None
     barrier()
+    host_barrier()                                                # every GPU idle from here until rank 0 is through
     if rank == 0:
         import dataclasses
 
@@ -422,6 +439,7 @@ def main():
                 "with_flow_bound": {"ms": r3.total_ms, "objective": int(r3.objective), "objective_bound": int(r3.objective_bound),
                                     "proven_optimal": bool(r3.optimal)},
                 "call": "kao_solve(%s), 1 GPU, host buffers" % ", ".join("%s=%s" % kv for kv in sorted(kw.items()))}
+    host_barrier()
     barrier()
 
     line = None

@@ -903,10 +903,22 @@ static int solve_gang(const kao_problem *pb, const kao_options *opt, kao_result 
     std::vector<double> ms(world, 0.0);
     Rendezvous meet(world);
     bool have = false;
+    static const bool trace = std::getenv("KAO_TRACE") != nullptr;       // stderr: where a multi-GPU solve spends its host time
+    const auto t_start = std::chrono::steady_clock::now();
     auto worker = [&](int i) {
+        int phase = 0;
         auto step = [&](int rc) {                     // record the first failure of this rank, then meet the others
             if (rc != KAO_OK && rcs[i] == KAO_OK) { rcs[i] = rc; errs[i] = g_err; }
-            return meet.arrive(rc == KAO_OK);
+            const auto t_a = std::chrono::steady_clock::now();
+            const bool all_ok = meet.arrive(rc == KAO_OK);
+            if (trace) {
+                const auto t_b = std::chrono::steady_clock::now();
+                std::fprintf(stderr, "[kao trace] gpu %d phase %d: reached at %.3f ms, waited %.3f ms for the others\n", devs[i], phase,
+                             std::chrono::duration<double, std::milli>(t_a - t_start).count(),
+                             std::chrono::duration<double, std::milli>(t_b - t_a).count());
+            }
+            ++phase;
+            return all_ok;
         };
         kao_handle *h = nullptr;
         bool ok = step(guarded([&] { return create_handle(pb, devs[i], &h); }));
@@ -952,6 +964,9 @@ static int solve_gang(const kao_problem *pb, const kao_options *opt, kao_result 
         }
         if (i == 0 && h) hm_out = h->hm;
         if (h) { const std::string keep = g_err; destroy_impl(h); g_err = keep; }
+        if (trace)
+            std::fprintf(stderr, "[kao trace] gpu %d destroyed at %.3f ms\n", devs[i],
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     };
     std::vector<std::thread> th;
     for (int i = 1; i < world; ++i) th.emplace_back(worker, i);
