@@ -154,6 +154,24 @@ template <int W, bool kSmall = false> __device__ __forceinline__ int row_kth(con
 __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t n) { return __umulhi(a, n); }
 
 // ------------------------------------------------------------------------------------------
+// layout of the transposed planes of the column-major evaluator (kao_device_t.cuh); the per-thread
+// generator below scans them too
+// ------------------------------------------------------------------------------------------
+// physical word of (plane q, slot s, partition word w).  The words of slot s are permuted inside every
+// aligned group of 32 by XOR with 4 * (s & 7), so that the 128-bit column loads of a quarter warp (8 consecutive
+// slots, same logical chunk) hit 8 different bank groups while the 32-bit row loads of a warp (32 consecutive
+// words of one slot) stay conflict-free; a lane finds logical chunk j of its slot at physical chunk j ^ (s & 7)
+// with one XOR.  (Fewer than 32 words per slot: not permuted.)
+__host__ __device__ __forceinline__ bool t_swizzled(int nW) { return nW >= 32 && (nW & 31) == 0; }
+// partition words per slot of the transposed planes and per term plane: Ppad / 32, rounded up to whole groups of
+// 32 words once there are more than 32 (the padding words stay empty)
+__host__ __device__ __forceinline__ int t_words(int Ppad) { const int n = Ppad >> 5; return n > 32 ? (n + 31) & ~31 : n; }
+__host__ __device__ __forceinline__ int t_word(int q, int s, int w, int nW, int NSL)
+{
+    return (q * NSL + s) * nW + (t_swizzled(nW) ? (w ^ (4 * (s & 7))) : w);
+}
+
+// ------------------------------------------------------------------------------------------
 // candidate generator (docs/MODEL.md §5): warp-uniform, every lane computes the same patches
 // ------------------------------------------------------------------------------------------
 struct PatchSet {
@@ -174,6 +192,13 @@ template <int W, bool kThread = false, bool kSmall = false> struct Gen {
     int lane;
     const uint16_t *D, *DL;  // displaced / leader-displaced partitions of the base (global or shared)
     int nD, nL;
+    // thread mode only, column-major kernels: the transposed planes of the base (kao_device_t.cuh: T0 replicas, T1 leader
+    // one-hot, tnW words per slot) — "the first partition from p0 on that holds / is led from / follows on slot s" is a
+    // scan for the next set bit of one plane row.  t_leaders_valid: every partition is led from one of its replicas, so
+    // that T1 (replica AND leader) also answers "is led from s"; else that question falls back to the scan of the leader bytes
+    const uint32_t *T = nullptr;
+    int tnW = 0;
+    bool t_leaders_valid = false;
     // thread mode only: per-slot inverted lists of the base (ascending partitions), or inv_ok = false
     bool inv_ok = false;
     const int *hoff = nullptr, *loff = nullptr;     // [slots + 1] offsets into hold / led
@@ -247,6 +272,29 @@ template <int W, bool kThread = false, bool kSmall = false> struct Gen {
         const uint32_t *col = bitsT + (size_t)(src >> 5) * d->Ppad;
         const uint32_t bit = 1u << (src & 31);
         if constexpr (kThread) {
+            if (T != nullptr && (KIND != 1 || t_leaders_valid)) {
+                // cyclic scan of one row of the transposed planes for the next set bit from p0 on, patched partitions
+                // masked out: word (p0 >> 5) from bit (p0 & 31), the following words, and the first word again below p0
+                constexpr int NSL = 32 * W;
+                const int nWq = (P + 31) >> 5;
+                const uint32_t *r0 = T + (size_t)src * tnW, *r1 = T + (size_t)(NSL + src) * tnW;
+                const int sw = t_swizzled(tnW) ? 4 * (src & 7) : 0;
+                int w = p0 >> 5;
+                uint32_t keep = ~0u << (p0 & 31);
+                for (int i = 0; i <= nWq; ++i) {
+                    const int pw = w ^ sw;
+                    uint32_t m = KIND == 1 ? r1[pw] : (KIND == 2 ? (r0[pw] & ~r1[pw]) : r0[pw]);
+                    m &= keep;
+                    if (i == nWq) m &= ~(~0u << (p0 & 31));
+#pragma unroll
+                    for (int j = 0; j < kMaxOps; ++j)       // unused patches hold -1: (-1 >> 5) never equals w
+                        if ((ps.p[j] >> 5) == w) m &= ~(1u << (ps.p[j] & 31));
+                    if (m) return 32 * w + __ffs(m) - 1;
+                    keep = ~0u;
+                    w = (w + 1 == nWq) ? 0 : w + 1;
+                }
+                return -1;
+            }
             if (inv_ok) {
                 // sorted list of the partitions that can match: lower_bound(p0), then walk cyclically
                 const uint16_t *L = (KIND == 1) ? led + loff[src] : hold + hoff[src];

@@ -51,20 +51,6 @@ struct EvalCfgT {
 constexpr int kTPlanes = 2;
 constexpr int kZPlanes = 8;          // term planes of the objective: [kZPlanes][nW] words behind the transposed planes
 
-// physical word of (plane q, slot s, partition word w).  The words of slot s are permuted inside every
-// aligned group of 32 by XOR with 4 * (s & 7), so that the 128-bit column loads of a quarter warp (8 consecutive
-// slots, same logical chunk) hit 8 different bank groups while the 32-bit row loads of a warp (32 consecutive
-// words of one slot) stay conflict-free; a lane finds logical chunk j of its slot at physical chunk j ^ (s & 7)
-// with one XOR.  (Fewer than 32 words per slot: not permuted.)
-__host__ __device__ __forceinline__ bool t_swizzled(int nW) { return nW >= 32 && (nW & 31) == 0; }
-// partition words per slot of the transposed planes and per term plane: Ppad / 32, rounded up to whole groups of
-// 32 words once there are more than 32 (the padding words stay empty)
-__host__ __device__ __forceinline__ int t_words(int Ppad) { const int n = Ppad >> 5; return n > 32 ? (n + 31) & ~31 : n; }
-__host__ __device__ __forceinline__ int t_word(int q, int s, int w, int nW, int NSL)
-{
-    return (q * NSL + s) * nW + (t_swizzled(nW) ? (w ^ (4 * (s & 7))) : w);
-}
-
 // C1 + C7 of one row held row-major (a patched row of the candidate, or a row the vertical pass
 // flagged): same terms as row_rack_terms<W, 3>
 template <int W> __device__ __forceinline__ int row_terms_hi1_s8(const uint32_t (&x)[W], int RF)

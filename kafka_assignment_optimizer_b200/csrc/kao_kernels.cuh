@@ -423,6 +423,19 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
     if constexpr (has_oh_plane<Cfg>()) build_oh_plane<W, THREADS>(s_bits, s_leader, d.Ppad);
     if constexpr (Cfg::kTrans) build_t_planes<W, THREADS>(d, s_sw, s_z, s_bits, s_leader);
     rebuild_lists<THREADS>(s_bits, s_leader, d.homeT, d.P, d.Ppad, s_D, s_DL, s_counts, s_scan);
+    if constexpr (Cfg::kTrans) {
+        // s_counts[2] = partitions whose leader slot is not one of their replicas (0 for every base the engine builds or
+        // reaches itself): while it is 0 the leader plane T1 also answers the generator's "is led from slot s"
+        if (tid == 0) s_counts[2] = 0;
+        __syncthreads();
+        int bad = 0;
+        for (int p = tid; p < d.P; p += THREADS) {
+            const int ld = s_leader[p];
+            bad += (ld < W * 32 && ((s_bits[(size_t)(ld >> 5) * d.Ppad + p] >> (ld & 31)) & 1u)) ? 0 : 1;
+        }
+        if (bad) atomicAdd(&s_counts[2], bad);
+        __syncthreads();
+    }
 
     Gen<W, false, Cfg::kTrans> gen;        // column-major kernels: compact generator code (same candidates)
     uint32_t no_rows[kMaxOps][W];          // warp mode keeps patched rows in shared memory instead
@@ -484,12 +497,10 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
         } else if constexpr (Cfg::kTrans) {
             // ---- column-major evaluator: candidates are generated 32 at a time, one per LANE (per-thread
             // generator over the round's inverted lists), then evaluated in full one after the other by the warp
-            const RoundTables rt = round_tables(smem, plan);
-            build_round_tables<W, THREADS>(rt, plan, d, s_bits, s_leader);
             Gen<W, true, true> tg;        // compact code (row_kth keeps its loop), same candidates
             tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
             tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
-            bind_tables(tg, rt);
+            tg.T = s_sw; tg.tnW = t_words(d.Ppad); tg.t_leaders_valid = s_counts[2] == 0;    // "first holder of slot s": plane scan
             constexpr int BS = batch_stride<W>();
             uint32_t *batch = s_prow + (size_t)warp * 32 * BS;
             for (uint32_t it0 = 0; it0 < iters; it0 += 32) {
@@ -647,7 +658,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                     Gen<W, true, true> tg;        // compact code (row_kth keeps its loop), same candidates
                     tg.bitsT = s_bits; tg.leader = s_leader; tg.cs = s_cs; tg.d = &d; tg.prow = nullptr; tg.lane = 0;
                     tg.D = s_D; tg.DL = s_DL; tg.nD = s_counts[0]; tg.nL = s_counts[1];
-                    bind_tables(tg, round_tables(smem, plan));
+                    tg.T = s_sw; tg.tnW = t_words(d.Ppad); tg.t_leaders_valid = s_counts[2] == 0;
                     uint32_t rows[kMaxOps][W];
 #pragma unroll
                     for (int i = 0; i < kMaxOps; ++i)
@@ -679,6 +690,12 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 #pragma unroll
                     for (int i = 0; i < kMaxOps; ++i) {
                         if (i < ps.n) {
+                            if constexpr (Cfg::kTrans) {            // leader validity of the partition, before and after
+                                const int lo = s_leader[ps.p[i]], ln = (int)ps.ld[i];
+                                const bool was = lo < W * 32 && ((s_bits[(size_t)(lo >> 5) * d.Ppad + ps.p[i]] >> (lo & 31)) & 1u);
+                                const bool is = ln < W * 32 && ((gen.prow[i * W + (ln >> 5)] >> (ln & 31)) & 1u);
+                                s_counts[2] += (was ? 0 : -1) + (is ? 0 : 1);
+                            }
                             for (int w = 0; w < W; ++w) {
                                 const uint32_t v = gen.prow[i * W + w];
                                 s_bits[(size_t)w * d.Ppad + ps.p[i]] = v;

@@ -61,7 +61,7 @@ inline SmemPlan make_plan(int W, int Ppad, int warps, int obj_words_per_row, int
 }
 
 // shared-memory plan of a column-major kernel: the two transposed planes + the term planes in place of the
-// objective table, a batch of candidates per warp, the inverted lists of the per-thread generator
+// objective table, a batch of candidates per warp (the per-thread generator scans the transposed planes: no inverted lists)
 inline SmemPlan make_plan_t(int W, int Ppad, int threads, int P, int RF)
 {
     // make_plan sizes the area at off_sw in words per partition of Ppad: the transposed planes hold t_words(Ppad)
@@ -69,13 +69,13 @@ inline SmemPlan make_plan_t(int W, int Ppad, int threads, int P, int RF)
     // partition covers that for every Ppad the evaluator accepts
     const int nW = t_words(Ppad);
     const int per_row = (kTPlanes * W * 32 * nW + Ppad - 1) / Ppad;
-    return make_plan(W, Ppad, threads / 32, per_row, P, RF, false, 32 * batch_stride_words(W), -1, kZPlanes * nW * 4);
+    return make_plan(W, Ppad, threads / 32, per_row, P, RF, false, 32 * batch_stride_words(W), 0, kZPlanes * nW * 4);
 }
 // does the column-major evaluator cover this layout (kao_create; tests/emu asks the same question)
 inline bool column_major_fits(int W, int Ppad, int threads, int P, int RF)
 {
     const SmemPlan s = make_plan_t(W, Ppad, threads, P, RF);
-    return s.total <= 227u * 1024u && s.cap_hold > 0 && Ppad <= 4096;      // <= 32 chunks of 128 partitions (patched_chunks)
+    return s.total <= 227u * 1024u && Ppad <= 4096;      // <= 32 chunks of 128 partitions (patched_chunks)
 }
 
 // shared-memory plan of a delta kernel for rows wider than 64 slots: the base, the per-round tables and the

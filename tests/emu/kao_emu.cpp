@@ -38,6 +38,7 @@ struct Emu {
     int trans = 0;                       // 0 row-major evaluator, 1.. forms (schedules) of the column-major one
     int nW = 0;
     std::vector<uint32_t> T, Z;          // transposed planes, term planes of the objective
+    int n_invalid = 0;                   // partitions led from a slot that holds none of their replicas (s_counts[2] of the kernel)
     std::string err;
 };
 
@@ -62,6 +63,11 @@ void rebuild_lists(Emu &e)
 {
     const HostModel &m = e.hm;
     e.nD = e.nL = 0;
+    e.n_invalid = 0;
+    for (int p = 0; p < m.P; ++p) {
+        const int ld = e.leader[p];
+        if (!(ld < 32 * m.W && ((e.bits[(size_t)(ld >> 5) * m.Ppad + p] >> (ld & 31)) & 1u))) ++e.n_invalid;
+    }
     for (int p = 0; p < m.P; ++p) {
         const uint32_t h4 = m.homeT[p];
         bool miss = false, ldis = false;
@@ -103,6 +109,22 @@ template <class Cfg> struct Run {
         g.D = e.D.data(); g.DL = e.DL.data(); g.nD = e.nD; g.nL = e.nL;
         return g;
     }
+    // the per-thread generator of the column-major kernels: every lane generates the candidate for itself ("first holder
+    // of slot s" = scan of the transposed planes), lane 0 parks the patched rows where the evaluator reads them
+    static void gen_thread(Emu &e, int lane, uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size, PatchSet &ps)
+    {
+        Gen<W, true, true> tg;
+        tg.bitsT = e.bits.data(); tg.leader = e.leader.data(); tg.cs = &e.cs; tg.d = &e.prm; tg.prow = nullptr; tg.lane = 0;
+        tg.D = e.D.data(); tg.DL = e.DL.data(); tg.nD = e.nD; tg.nL = e.nL;
+        tg.T = e.T.data(); tg.tnW = e.nW; tg.t_leaders_valid = e.n_invalid == 0;
+        uint32_t rows[kMaxOps][W];
+        for (int i = 0; i < kMaxOps; ++i)
+            for (int t = 0; t < W; ++t) rows[i][t] = 0;
+        tg.run(seed, round, idx, round_size, ps, rows);
+        if (lane == 0)
+            for (int i = 0; i < kMaxOps; ++i)
+                for (int t = 0; t < W; ++t) e.prow[i * W + t] = rows[i][t];
+    }
     // generate + evaluate in full, as one warp of the search kernels does
     static unsigned long long key(Emu &e, uint64_t seed, uint32_t round, uint32_t idx, uint32_t round_size)
     {
@@ -111,8 +133,12 @@ template <class Cfg> struct Run {
         emu::run_warp([&](int lane) {
             uint32_t no_rows[kMaxOps][W];
             PatchSet ps;
-            if (e.trans) make_gen<true>(e, lane).run(seed, round, idx, round_size, ps, no_rows);   // as the column-major kernels
-            else make_gen<false>(e, lane).run(seed, round, idx, round_size, ps, no_rows);
+            if constexpr (W <= 2) {
+                if (e.trans) gen_thread(e, lane, seed, round, idx, round_size, ps);               // as the column-major kernels
+                else make_gen<false>(e, lane).run(seed, round, idx, round_size, ps, no_rows);
+            } else {
+                make_gen<false>(e, lane).run(seed, round, idx, round_size, ps, no_rows);
+            }
             __syncwarp();                                     // __syncthreads() of the kernels
             int viol, obj;
             if constexpr (W <= 2) {
@@ -152,8 +178,12 @@ template <class Cfg> struct Run {
         emu::run_warp([&](int lane) {
             uint32_t no_rows[kMaxOps][W];
             PatchSet ps;
-            if (e.trans) make_gen<true>(e, lane).run(seed, round, idx, round_size, ps, no_rows);
-            else make_gen<false>(e, lane).run(seed, round, idx, round_size, ps, no_rows);
+            if constexpr (W <= 2) {
+                if (e.trans) gen_thread(e, lane, seed, round, idx, round_size, ps);
+                else make_gen<false>(e, lane).run(seed, round, idx, round_size, ps, no_rows);
+            } else {
+                make_gen<false>(e, lane).run(seed, round, idx, round_size, ps, no_rows);
+            }
             if (lane == 0) win = ps;
         });
         const int Ppad = e.hm.Ppad;
