@@ -15,11 +15,10 @@
 //   Z[j] bit p  <=>  term j of partition p holds in the base   =>   objective = sum_j z_value[j] * popc(Z[j]).
 // The evaluation walks the matrix twice, each time with all data of a constraint inside one lane:
 //   rows     (C1, C7, objective)  a lane owns 32 PARTITIONS (one word of every slot and of every term
-//            plane).  Per 8-slot rack field two words are formed, `any` (the field holds a replica) and
-//            `dup` (it holds two or more); a partition is fine when no field is doubled and exactly RF
-//            fields are in use, which is one bit-sliced sum of the `any` words against RF — no POPC per
-//            row.  Partitions that fail are charged |n - RF| + (n - z) from their row-major row, one by one
-//            (rare).  The objective is one POPC per term plane;
+//            plane).  Per 8-slot rack field one word `any` (the field holds a replica; 4 LOP3), their bit-sliced
+//            sum z = racks in use, and C1 + C7 of all rows together as sums: rows with z == RF cost
+//            2 n - z - RF each (n from the column totals), the few with z != RF are corrected one by one from
+//            the row-major base (rows_pass).  No popcount per row.  The objective is one POPC per term plane;
 //   columns  (C2-C6)  a lane owns one SLOT per row word: replica and leader totals of its columns are
 //            popcount sums over the partition words — no bit-sliced column counters, no cross-lane
 //            reduce-scatter.
@@ -68,11 +67,20 @@ template <int W> __device__ __forceinline__ int row_terms_hi1_s8(const uint32_t 
 inline long long emu_rows_charged_one_by_one = 0;
 #endif
 // ------------------------------------------------------------------------------------------
-// rows: C1 + C7 of every partition that is not patched, 32 partitions per lane
+// rows: C1 + C7 of every partition that is not patched, 32 partitions per lane — as sums, not row by row.
+// With "at most one replica per rack" a row of n replicas in z racks costs |n - RF| (C1) + (n - z) (C7).
+// Per 8-slot rack field one word `any` (the field holds a replica; 4 LOP3) and the bit-sliced sum z of these
+// words.  Rows with z == RF have n >= RF, so over them  sum |n - RF| + (n - z)  =  2 sum n - sum z - RF * #rows;
+// rows with z != RF (`flagged`, rare: short rows, rows with a doubled rack) are charged the difference to their
+// exact terms one by one from the row-major base.  sum n over the unpatched rows is (sum of the column totals) -
+// (replicas in the patched rows): the column pass has it anyway.  So this pass returns, per lane,
+//     - sum_b popc(any_b) - RF * popc(scored partitions)  +  for every flagged row  |n - RF| - n + RF
+// and the caller adds twice its column totals minus twice the replicas of the patched rows.  Exact for every
+// bit-plane (also rows with more than RF replicas); no popcount per row, no search for doubled fields.
 // ------------------------------------------------------------------------------------------
 template <int W, bool kShared, int kNW>
-__device__ __forceinline__ int rows_vertical(const Params &d, const MemRef<kShared> &T, const MemRef<kShared> &Z, const MemRef<kShared> &bitsT,
-                                             int nW_rt, int lane, const PatchSet &ps, int &obj)
+__device__ __forceinline__ int rows_pass(const Params &d, const MemRef<kShared> &T, const MemRef<kShared> &Z, const MemRef<kShared> &bitsT,
+                                         int nW_rt, int lane, const PatchSet &ps, int &obj)
 {
     const int Ppad = d.Ppad, P = d.P, RF = d.RF;
     const int nW = kNW ? kNW : nW_rt;
@@ -96,20 +104,19 @@ __device__ __forceinline__ int rows_vertical(const Params &d, const MemRef<kShar
         int tk[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) tk[k] = t_swizzled(nW) ? (w ^ (4 * k)) : w;
-        uint32_t any[NB], dup = 0;
+        uint32_t any[NB];
+        int racks = 0;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             uint32_t x[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) x[k] = T.ld32((uint32_t)((b * 8 + k) * nW + tk[k]) * 4u);
-            // 10 LOP3 per field: any = OR of the 8 words; dup = two of them share a bit (inside a triple, the
-            // pair, or across the three groups)
-            const uint32_t a1 = lop3<0xFE>(x[0], x[1], x[2]), a2 = lop3<0xFE>(x[3], x[4], x[5]), a3 = x[6] | x[7];
-            dup = lop3<0xFE>(dup, lop3<0xE8>(x[0], x[1], x[2]), lop3<0xE8>(x[3], x[4], x[5]));
-            dup = lop3<0xEA>(x[6], x[7], dup) | lop3<0xE8>(a1, a2, a3);
-            any[b] = lop3<0xFE>(a1, a2, a3);
+            // OR of the 8 words of the field, masked to the partitions this pass scores
+            any[b] = lop3<0xA8>(lop3<0xFE>(lop3<0xFE>(x[0], x[1], x[2]), lop3<0xFE>(x[3], x[4], x[5]), x[6]), x[7], valid);
+            racks += __popc(any[b]);
         }
-        // z = number of rack fields in use, bit-sliced (0..8); without a doubled field z is also the replica count
+        viol -= racks + RF * __popc(valid);
+        // z = number of rack fields in use, bit-sliced (0..8)
         uint32_t z1, z2, z4 = 0, z8 = 0;
         if constexpr (NB == 4) {
             uint32_t c1, s1;
@@ -131,17 +138,16 @@ __device__ __forceinline__ int rows_vertical(const Params &d, const MemRef<kShar
             z4 = e1 ^ e2;
             z8 = e1 & e2;
         }
-        uint32_t bad = dup | (z1 ^ rf0) | (z2 ^ rf1) | (z4 ^ rf2) | (z8 ^ rf3);
-        bad &= valid;
-        for (uint32_t m = bad; m; m &= m - 1) {     // rare: the exact terms of that row, from the row-major base
+        const uint32_t flagged = ((z1 ^ rf0) | (z2 ^ rf1) | (z4 ^ rf2) | (z8 ^ rf3)) & valid;    // z != RF
+        for (uint32_t m = flagged; m; m &= m - 1) { // rare: the row's exact C1 term in place of the n >= RF form
 #if defined(KAO_HOST_EMU)
             ++emu_rows_charged_one_by_one;          // tests/emu: a well-formed row must never come here
 #endif
             const int p = 32 * w + __ffs(m) - 1;
-            uint32_t x[W];
+            int n = 0;
 #pragma unroll
-            for (int t = 0; t < W; ++t) x[t] = bitsT.ld32((uint32_t)(t * Ppad + p) * 4u);
-            viol += row_terms_hi1_s8<W>(x, RF);
+            for (int t = 0; t < W; ++t) n += __popc(bitsT.ld32((uint32_t)(t * Ppad + p) * 4u));
+            viol += abs(n - RF) - n + RF;
         }
     }
     return viol;
@@ -199,14 +205,17 @@ template <int kLvl> struct PopStream {
 // the per-thread generator of the search kernels calls this for its own candidate)
 // ------------------------------------------------------------------------------------------
 template <int W>
-__device__ __forceinline__ void patch_terms(const Params &d, const PatchSet &ps, const uint32_t (&rows)[kMaxOps][W], int &pviol, int &pobj)
+__device__ __forceinline__ void patch_terms(const Params &d, const PatchSet &ps, const uint32_t (&rows)[kMaxOps][W], int &pviol, int &pobj,
+                                            int &pcount)
 {
     pviol = 0;
     pobj = 0;
+    pcount = 0;                                     // replicas in the patched rows (the column totals include them)
 #pragma unroll
     for (int i = 0; i < kMaxOps; ++i) {
         if (ps.p[i] < 0) continue;
         pviol += row_terms_hi1_s8<W>(rows[i], d.RF);
+        pcount += row_count<W>(rows[i]);
         const uint32_t *zs = reinterpret_cast<const uint32_t *>(d.zslot + (size_t)ps.p[i] * kZPlanes);
         const uint32_t z03 = zs[0], z47 = d.nz > 4 ? zs[1] : 0xFFFFFFFFu;
 #pragma unroll
@@ -225,7 +234,7 @@ __device__ __forceinline__ void patch_terms(const Params &d, const PatchSet &ps,
 // ------------------------------------------------------------------------------------------
 template <class Cfg, bool kShared>
 __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt, const uint32_t *bitsT, const uint32_t *Zp,
-                                 const Consts *cs, const PatchSet &ps, const uint32_t *prow, int pviol, int pobj, int lane,
+                                 const Consts *cs, const PatchSet &ps, const uint32_t *prow, int pviol, int pobj, int pcount, int lane,
                                  int &viol_out, int &obj_out)
 {
     constexpr int W = Cfg::W, kNW = Cfg::kNW;
@@ -234,8 +243,8 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
     const MemRef<kShared> T(Tp), B(bitsT), Z(Zp);
     // ---- rows: unpatched partitions from the transposed bit-plane and the term planes, patched ones from the patch
     int obj = 0;
-    int viol = rows_vertical<W, kShared, kNW>(d, T, Z, B, nW, lane, ps, obj);
-    if (lane == 0) { viol += pviol; obj += pobj; }
+    int viol = rows_pass<W, kShared, kNW>(d, T, Z, B, nW, lane, ps, obj);
+    if (lane == 0) { viol += pviol - 2 * pcount; obj += pobj; }    // the patched rows' own terms; their replicas are not the row pass's
     // ---- columns: this lane owns slot `lane` of every row word
     PopStream<(Cfg::kPop >> 0) & 15> cnt[W];
     PopStream<(Cfg::kPop >> 4) & 15> lcnt[W];
@@ -305,7 +314,7 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
         const int s = lane + 32 * t;
         const int c = cnt[t].total(), l = lcnt[t].total();
         packed |= (uint32_t)c << (16 * t);                      // c <= P < 8192: the sum of 8 lanes stays below 2^16
-        viol += band_violation(c, cs->bnd_rep[s]) + band_violation(l, cs->bnd_ldr[s]) - l;
+        viol += 2 * c + band_violation(c, cs->bnd_rep[s]) + band_violation(l, cs->bnd_ldr[s]) - l;     // 2 c: see rows_pass
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);

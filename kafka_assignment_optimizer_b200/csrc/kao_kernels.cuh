@@ -516,12 +516,12 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                         for (int w = 0; w < W; ++w) rows[i][w] = 0;
                     }
                     if (it0 + lane < iters && idx < pp.idx_hi) tg.run(seed, round, idx, round_size, ps, rows);
-                    int pviol, pobj;
-                    patch_terms<W>(d, ps, rows, pviol, pobj);
+                    int pviol, pobj, pcount;
+                    patch_terms<W>(d, ps, rows, pviol, pobj, pcount);
                     uint32_t *mine = batch + lane * BS;
                     mine[0] = (uint32_t)ps.p[0]; mine[1] = (uint32_t)ps.p[1]; mine[2] = (uint32_t)ps.p[2];
                     mine[3] = (ps.ld[0] & 0xFFu) | ((ps.ld[1] & 0xFFu) << 8) | ((ps.ld[2] & 0xFFu) << 16) | ((uint32_t)ps.n << 24);
-                    mine[4] = (uint32_t)pviol; mine[5] = (uint32_t)pobj;
+                    mine[4] = (uint32_t)pviol | ((uint32_t)pcount << 16); mine[5] = (uint32_t)pobj;       // pviol <= 3 * 128, pcount <= 3 * 64
 #pragma unroll
                     for (int i = 0; i < kMaxOps; ++i)
 #pragma unroll
@@ -541,8 +541,8 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                         ps.n = (int)(hdr.w >> 24);
                         const uint2 terms = *reinterpret_cast<const uint2 *>(slot + 4);
                         int viol, obj;
-                        eval_candidate_t<Cfg, true>(d, s_sw, t_words(d.Ppad), s_bits, s_z, s_cs, ps, slot + kBatchHdr, (int)terms.x, (int)terms.y,
-                                                    lane, viol, obj);
+                        eval_candidate_t<Cfg, true>(d, s_sw, t_words(d.Ppad), s_bits, s_z, s_cs, ps, slot + kBatchHdr, (int)(terms.x & 0xFFFFu),
+                                                    (int)terms.y, (int)(terms.x >> 16), lane, viol, obj);
                         const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
                         if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = key;
                         best = key < best ? key : best;
