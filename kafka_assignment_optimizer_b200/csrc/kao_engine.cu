@@ -996,10 +996,17 @@ static int solve_impl(const kao_problem *pb, const kao_options *opt, kao_result 
     std::vector<int32_t> reps((size_t)pb->P * pb->RF);
     double dev_ms_total = 0;
     HostModel hm;
+    static const bool trace = std::getenv("KAO_TRACE") != nullptr;
+    auto stamp = [&](const char *what) {
+        if (trace)
+            std::fprintf(stderr, "[kao trace] kao_solve: %s at %.3f ms\n", what,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
     if (world == 1) {
         kao_handle *h0 = nullptr;
         rc = create_handle(pb, devs[0], &h0);
         if (rc != KAO_OK) return rc;
+        stamp("session created (model built, tables uploaded, initial base)");
         struct Closer { kao_handle *h; ~Closer() { const std::string keep = g_err; destroy_impl(h); g_err = keep; } } closer{h0};
         h0->patience = opt->flags >> 16;                         // KAO_FLAG_PATIENCE(n)
         // the column-major evaluator is the default where the layout allows it; the flag selects the other full evaluator (same keys)
@@ -1010,10 +1017,12 @@ static int solve_impl(const kao_problem *pb, const kao_options *opt, kao_result 
             if (r && (rc = reset_impl(h0)) != KAO_OK) return rc;
             rc = search_impl(h0, opt->seed + 0x9E3779B97F4A7C15ull * r, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms, delta);
             if (rc != KAO_OK) return rc;
+            stamp("search done");
             int64_t viol = 0, obj = 0;
             int32_t moves = 0;
             rc = get_base_impl(h0, reps.data(), &viol, &obj, &moves);
             if (rc != KAO_OK) return rc;
+            stamp("result downloaded and evaluated");
             dev_ms_total += dev_ms;
             rounds_run += h0->last_rounds;
             if (!have || viol < res->violation || (viol == res->violation && obj > res->objective)) {
@@ -1028,6 +1037,7 @@ static int solve_impl(const kao_problem *pb, const kao_options *opt, kao_result 
         rc = solve_gang(pb, opt, res, devs, restarts, delta, keys, reps, rounds_run, dev_ms_total, hm);
         if (rc != KAO_OK) return rc;
     }
+    stamp("session destroyed");
     res->feasible = res->violation == 0;
     res->n_candidates = (uint64_t)rounds_run * opt->round_size;
     res->rounds_run = rounds_run;
@@ -1040,6 +1050,7 @@ static int solve_impl(const kao_problem *pb, const kao_options *opt, kao_result 
     res->key_obj_bits = hm.key_obj_bits;
     res->n_gpus = world;
     res->reserved = 0;
+    stamp("bound computed");
     res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (!res->feasible) { g_err = "no candidate satisfying C1..C7 was found"; return KAO_INFEASIBLE; }
     return KAO_OK;

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <utility>
 #include <vector>
@@ -40,6 +41,9 @@ struct HostModel {
     bool hi1 = false;                         // C7 is exactly "at most one replica per rack"
     int key_obj_bits = 24;                    // width of the cost field of a packed key (docs/MODEL.md 3)
     std::vector<uint32_t> dense_w;            // [P][NS] when dense
+    struct Cell { int p, b; uint32_t f, l; }; // a non-zero cell of the weight tables: follower / leader weight of (p, broker)
+    std::vector<Cell> cells;                  // all of them, by partition then broker
+    std::vector<int> cell_first;              // [P + 1] cells of partition p: cell_first[p] .. cell_first[p + 1]
     std::vector<uint32_t> homeT;              // [Ppad]
 };
 
@@ -104,20 +108,37 @@ inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &w
         if (m.rack_lo[r] < 0 || m.rack_lo[r] > m.rack_hi[r]) return bad("rack bounds must satisfy 0 <= lo <= hi");
     m.cur.assign(pb.cur, pb.cur + (size_t)pb.P * pb.RFcur);
     for (int32_t &b : m.cur) if (b < 0 || b >= pb.B) b = -1;
-    // weights: at most 4 non-zero cells per partition and 12-bit values -> packed entries staged
-    // in shared memory; anything else -> dense table in HBM
+    // weights.  The tables are P x B cells of which only the current placements are non-zero (README.md:145-146 lists
+    // just those): ONE scan collects the non-zero cells, everything below works on that short list (kao_solve builds
+    // the model once per call: at 1000 x 64 the scan is what its host-side set-up costs)
+    m.cell_first.assign((size_t)pb.P + 1, 0);
+    m.cells.clear();
+    for (int p = 0; p < pb.P; ++p) {
+        m.cell_first[p] = (int)m.cells.size();
+        const uint16_t *f = pb.wF + (size_t)p * pb.B, *l = pb.wL + (size_t)p * pb.B;
+        int b = 0;
+        for (; b + 4 <= pb.B; b += 4) {
+            uint64_t f4, l4;
+            std::memcpy(&f4, f + b, 8);
+            std::memcpy(&l4, l + b, 8);
+            if ((f4 | l4) == 0) continue;
+            for (int k = b; k < b + 4; ++k)
+                if (f[k] | l[k]) m.cells.push_back({p, k, f[k], l[k]});
+        }
+        for (; b < pb.B; ++b)
+            if (f[b] | l[b]) m.cells.push_back({p, b, f[b], l[b]});
+    }
+    m.cell_first[pb.P] = (int)m.cells.size();
+    // at most 4 non-zero cells per partition and 12-bit values -> packed entries staged in shared memory; anything
+    // else -> dense table in HBM
     uint32_t maxw = 0;
     bool sparse_ok = true;
-    for (int p = 0; p < pb.P && sparse_ok; ++p) {
-        int nnz = 0;
-        for (int b = 0; b < pb.B; ++b) {
-            const uint32_t f = pb.wF[(size_t)p * pb.B + b], l = pb.wL[(size_t)p * pb.B + b];
-            if (f | l) ++nnz;
-            if (f > 4095 || l > 4095) sparse_ok = false;
-        }
-        if (nnz > 4) sparse_ok = false;
+    for (const HostModel::Cell &c : m.cells) {
+        maxw = std::max<uint32_t>(maxw, std::max(c.f, c.l));
+        if (c.f > 4095 || c.l > 4095) sparse_ok = false;
     }
-    for (size_t i = 0; i < (size_t)pb.P * pb.B; ++i) maxw = std::max<uint32_t>(maxw, std::max(pb.wF[i], pb.wL[i]));
+    for (int p = 0; p < pb.P; ++p)
+        if (m.cell_first[p + 1] - m.cell_first[p] > 4) sparse_ok = false;
     if ((uint64_t)pb.P * pb.RF * maxw > 0xFFFFFFull) return bad("objective range exceeds 24 bits");
     // cost field of the packed key: just wide enough for the largest objective the model can reach, so
     // that the violation field gets the rest of the 63 bits (15 bits saturate at P = 8000)
@@ -125,37 +146,32 @@ inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &w
     while (((uint64_t)pb.P * pb.RF * maxw) >> m.key_obj_bits) ++m.key_obj_bits;
     m.dense = !sparse_ok;
     m.swT.assign((size_t)4 * m.Ppad, 0);
+    m.nentries = 0;
     if (m.dense) {
         m.dense_w.assign((size_t)pb.P * m.NS, 0);
-        for (int p = 0; p < pb.P; ++p)
-            for (int b = 0; b < pb.B; ++b)
-                m.dense_w[(size_t)p * m.NS + m.slot_of_broker[b]] =
-                    (uint32_t)pb.wF[(size_t)p * pb.B + b] | ((uint32_t)pb.wL[(size_t)p * pb.B + b] << 16);
+        for (const HostModel::Cell &c : m.cells)
+            m.dense_w[(size_t)c.p * m.NS + m.slot_of_broker[c.b]] = c.f | (c.l << 16);
     } else {
         for (int p = 0; p < pb.P; ++p) {
             int k = 0;
-            for (int b = 0; b < pb.B; ++b) {
-                const uint32_t f = pb.wF[(size_t)p * pb.B + b], l = pb.wL[(size_t)p * pb.B + b];
-                if (f | l) m.swT[(size_t)k++ * m.Ppad + p] = (uint32_t)m.slot_of_broker[b] | (f << 8) | (l << 20);
+            for (int i = m.cell_first[p]; i < m.cell_first[p + 1]; ++i, ++k) {
+                const HostModel::Cell &c = m.cells[i];
+                m.swT[(size_t)k * m.Ppad + p] = (uint32_t)m.slot_of_broker[c.b] | (c.f << 8) | (c.l << 20);
             }
+            m.nentries = std::max(m.nentries, k);
         }
     }
-    m.nentries = 0;
-    if (!m.dense)
-        for (int k = 0; k < 4; ++k)
-            for (int p = 0; p < pb.P; ++p)
-                if (m.swT[(size_t)k * m.Ppad + p]) m.nentries = k + 1;
     // mask planes: one per distinct follower weight (applied to the row) and one per distinct
     // leader bonus wL - wF (applied to the leader one-hot); needs wL >= wF everywhere, at most two
     // follower weights and one bonus value, and only pays off for narrow rows
     {
         std::vector<uint32_t> vf, vd;
         bool ok = (m.W <= 2);
-        for (size_t i = 0; ok && i < (size_t)pb.P * pb.B; ++i) {
-            const uint32_t f = pb.wF[i], l = pb.wL[i];
-            if (l < f) { ok = false; break; }
-            if (f && std::find(vf.begin(), vf.end(), f) == vf.end()) vf.push_back(f);
-            if (l - f && std::find(vd.begin(), vd.end(), l - f) == vd.end()) vd.push_back(l - f);
+        for (const HostModel::Cell &c : m.cells) {
+            if (!ok) break;
+            if (c.l < c.f) { ok = false; break; }
+            if (c.f && std::find(vf.begin(), vf.end(), c.f) == vf.end()) vf.push_back(c.f);
+            if (c.l - c.f && std::find(vd.begin(), vd.end(), c.l - c.f) == vd.end()) vd.push_back(c.l - c.f);
             if (vf.size() + vd.size() > 6) ok = false;
         }
         // kernels exist for 3 planes (2 row planes + 1 leader plane); empty planes pad; other weight
@@ -173,13 +189,10 @@ inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &w
                 const uint32_t val = on_leader ? vd[k] : vf[k];
                 m.plane_value[c] = (int)val;
                 if (on_leader) m.plane_on_leader |= 1 << c;
-                for (int p = 0; p < pb.P; ++p)
-                    for (int b = 0; b < pb.B; ++b) {
-                        const uint32_t f = pb.wF[(size_t)p * pb.B + b], l = pb.wL[(size_t)p * pb.B + b];
-                        if ((on_leader ? l - f : f) == val) {
-                            const int s = m.slot_of_broker[b];
-                            m.planesT[((size_t)c * m.W + (s >> 5)) * m.Ppad + p] |= 1u << (s & 31);
-                        }
+                for (const HostModel::Cell &cl : m.cells)
+                    if ((on_leader ? cl.l - cl.f : cl.f) == val) {
+                        const int s = m.slot_of_broker[cl.b];
+                        m.planesT[((size_t)c * m.W + (s >> 5)) * m.Ppad + cl.p] |= 1u << (s & 31);
                     }
             }
         }
@@ -189,51 +202,56 @@ inline bool build_host_model(const kao_problem &pb, HostModel &m, std::string &w
     {
         struct Term { int kind; uint32_t val; int slot; };
         std::vector<std::pair<int, uint32_t>> classes;
-        std::vector<std::vector<Term>> terms(pb.P);
         bool ok = true;
-        for (int p = 0; p < pb.P && ok; ++p)
-            for (int b = 0; b < pb.B; ++b) {
-                const uint32_t f = pb.wF[(size_t)p * pb.B + b], l = pb.wL[(size_t)p * pb.B + b];
-                if (l < f) { ok = false; break; }
-                if (f) terms[p].push_back({0, f, m.slot_of_broker[b]});
-                if (l - f) terms[p].push_back({1, l - f, m.slot_of_broker[b]});
-                if (terms[p].size() > 16) { ok = false; break; }
+        for (const HostModel::Cell &c : m.cells) {
+            if (c.l < c.f) { ok = false; break; }
+            for (int kind = 0; kind < 2; ++kind) {
+                const uint32_t v = kind ? c.l - c.f : c.f;
+                if (!v) continue;
+                const std::pair<int, uint32_t> cls(kind, v);
+                if (std::find(classes.begin(), classes.end(), cls) == classes.end()) classes.push_back(cls);
             }
-        if (ok) {
-            for (int p = 0; p < pb.P; ++p)
-                for (const Term &t : terms[p]) {
-                    const std::pair<int, uint32_t> c(t.kind, t.val);
-                    if (std::find(classes.begin(), classes.end(), c) == classes.end()) classes.push_back(c);
-                    if (classes.size() > 8) ok = false;
-                }
+            if (classes.size() > 8) { ok = false; break; }
         }
         if (ok) {
             std::sort(classes.begin(), classes.end());
-            std::vector<int> mult(classes.size(), 0), first(classes.size(), 0);
+            const size_t nc = classes.size();
+            auto class_of = [&](int kind, uint32_t v) { return (size_t)(std::find(classes.begin(), classes.end(), std::pair<int, uint32_t>(kind, v)) - classes.begin()); };
+            std::vector<int> mult(nc, 0), first(nc, 0), n(nc);
+            std::vector<Term> ts;
+            auto terms_of = [&](int p) {                // terms of partition p in ascending slot order
+                ts.clear();
+                for (int i = m.cell_first[p]; i < m.cell_first[p + 1]; ++i) {
+                    const HostModel::Cell &c = m.cells[i];
+                    if (c.f) ts.push_back({0, c.f, m.slot_of_broker[c.b]});
+                    if (c.l - c.f) ts.push_back({1, c.l - c.f, m.slot_of_broker[c.b]});
+                }
+                std::sort(ts.begin(), ts.end(), [](const Term &a, const Term &b) { return a.slot < b.slot; });
+            };
             for (int p = 0; p < pb.P; ++p) {
-                std::vector<int> n(classes.size(), 0);
-                for (const Term &t : terms[p]) {
-                    const size_t c = std::find(classes.begin(), classes.end(), std::pair<int, uint32_t>(t.kind, t.val)) - classes.begin();
-                    mult[c] = std::max(mult[c], ++n[c]);
+                std::fill(n.begin(), n.end(), 0);
+                for (int i = m.cell_first[p]; i < m.cell_first[p + 1]; ++i) {
+                    const HostModel::Cell &c = m.cells[i];
+                    if (c.f) { const size_t k = class_of(0, c.f); mult[k] = std::max(mult[k], ++n[k]); }
+                    if (c.l - c.f) { const size_t k = class_of(1, c.l - c.f); mult[k] = std::max(mult[k], ++n[k]); }
                 }
             }
             int J = 0;
-            for (size_t c = 0; c < classes.size(); ++c) { first[c] = J; J += mult[c]; }
+            for (size_t c = 0; c < nc; ++c) { first[c] = J; J += mult[c]; }
             if (J <= 8) {
                 m.z_ok = true;
                 m.nz = J;
                 m.zslot.assign((size_t)m.Ppad * 8, 0xFF);
-                for (size_t c = 0; c < classes.size(); ++c)
+                for (size_t c = 0; c < nc; ++c)
                     for (int k = 0; k < mult[c]; ++k) {
                         m.z_value[first[c] + k] = (int)classes[c].second;
                         if (classes[c].first) m.z_on_leader |= 1 << (first[c] + k);
                     }
                 for (int p = 0; p < pb.P; ++p) {
-                    std::vector<Term> ts = terms[p];
-                    std::sort(ts.begin(), ts.end(), [](const Term &a, const Term &b) { return a.slot < b.slot; });
-                    std::vector<int> n(classes.size(), 0);
+                    terms_of(p);
+                    std::fill(n.begin(), n.end(), 0);
                     for (const Term &t : ts) {
-                        const size_t c = std::find(classes.begin(), classes.end(), std::pair<int, uint32_t>(t.kind, t.val)) - classes.begin();
+                        const size_t c = class_of(t.kind, t.val);
                         m.zslot[(size_t)p * 8 + first[c] + n[c]++] = (uint8_t)t.slot;
                     }
                 }
@@ -353,27 +371,28 @@ inline int count_moves(const HostModel &m, const int32_t *replicas)
 // leader plus RF - 1 followers on distinct brokers, with the balance and rack constraints C3..C7
 // dropped.  A search result that reaches it is proven optimal (kao_result.optimal); otherwise the
 // optimum lp_solve would return (README.md:135-136) lies between the two.
-inline int64_t objective_upper_bound(const HostModel &m, const kao_problem &pb)
+inline int64_t objective_upper_bound(const HostModel &m, const kao_problem &)
 {
+    // per partition: the best leader plus the best RF - 1 followers among the other brokers, constraints C3..C7
+    // ignored.  Only the non-zero cells matter: every other broker weighs 0 as a follower and as a leader.
     int64_t total = 0;
     const int nf = m.RF - 1;
-    std::vector<std::pair<uint32_t, int>> top;           // the RF largest follower weights of the row
+    std::vector<std::pair<uint32_t, int>> top;           // follower weights of the row, largest first
     for (int p = 0; p < m.P; ++p) {
-        const uint16_t *wF = pb.wF + (size_t)p * m.B, *wL = pb.wL + (size_t)p * m.B;
+        const int lo = m.cell_first[p], hi = m.cell_first[p + 1];
         top.clear();
-        for (int b = 0; b < m.B; ++b) {
-            top.emplace_back(wF[b], b);
-            std::sort(top.begin(), top.end(), [](const auto &x, const auto &y) { return x.first > y.first; });
-            if ((int)top.size() > m.RF) top.pop_back();
-        }
+        for (int i = lo; i < hi; ++i)
+            if (m.cells[i].f) top.emplace_back(m.cells[i].f, m.cells[i].b);
+        std::sort(top.begin(), top.end(), [](const auto &x, const auto &y) { return x.first > y.first; });
         int64_t sum_nf = 0, sum_rf = 0;                  // sums of the nf / nf + 1 largest follower weights
-        for (int i = 0; i < (int)top.size(); ++i) { if (i < nf) sum_nf += top[i].first; sum_rf += top[i].first; }
-        int64_t best = 0;
-        for (int b = 0; b < m.B; ++b) {
+        for (int i = 0; i < (int)top.size() && i <= nf; ++i) { if (i < nf) sum_nf += top[i].first; sum_rf += top[i].first; }
+        int64_t best = hi - lo < m.B ? sum_nf : 0;       // led from a broker that weighs nothing
+        for (int i = lo; i < hi; ++i) {
+            const HostModel::Cell &c = m.cells[i];
             bool in_top = false;
-            for (int i = 0; i < nf && i < (int)top.size(); ++i) in_top |= top[i].second == b;
-            const int64_t followers = in_top ? sum_rf - wF[b] : sum_nf;     // the leader's broker cannot follow too
-            best = std::max(best, (int64_t)wL[b] + followers);
+            for (int k = 0; k < nf && k < (int)top.size(); ++k) in_top |= top[k].second == c.b;
+            const int64_t followers = in_top ? sum_rf - c.f : sum_nf;       // the leader's broker cannot follow too
+            best = std::max(best, (int64_t)c.l + followers);
         }
         total += best;
     }

@@ -46,6 +46,17 @@ def test_config2_is_solved_and_proven_optimal(optima):
     assert res.objective_bound == e["objective"] and res.optimal
 
 
+def test_config5_as_baseline_states_it_is_kept_and_proven_optimal():
+    """BASELINE config 5 literally (4096 x 256 x 16, RF 3, round-robin current assignment): the current assignment
+    already satisfies C1..C7, so nothing moves; every replica keeps its weight (4 + 2 + 1 per partition), which is the
+    per-partition upper bound — the engine returns it as PROVEN optimal without an exact solver."""
+    pb = kao.synthetic_problem(4096, 256, 16, 3)
+    res = kopt.solve(pb, seed=3, rounds=6, round_size=1 << 12)
+    assert res.feasible and res.moves == 0 and res.objective == 4096 * 7
+    assert res.objective_bound == res.objective and res.optimal
+    assert m.evaluate(m.synthetic_problem(4096, 256, 16, 3), res.replicas) == (0, 4096 * 7)
+
+
 def test_config5_full_size_keys_and_trajectory(ref_lib, optima):
     """BASELINE config 5 at size (4096 partitions x 256 brokers x 16 racks, W = 8 words per row, 2 % of the
     replicas re-placed): per-candidate keys of the first and the last candidates of a round and a short
