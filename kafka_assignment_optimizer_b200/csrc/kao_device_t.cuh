@@ -35,7 +35,8 @@ namespace kao {
 // shape: every shared-memory offset of the evaluator is then an immediate), 0 = read at run time.
 // The other parameters are SCHEDULES of the same arithmetic (kao_set_schedule; results identical):
 //   kSync      how the warps of a CTA meet before an evaluation: 0 block barrier (all warps walk the
-//              evaluator together), 1 warp only (one warp's generator overlaps another's evaluation)
+//              evaluator together), 1 warp only (one warp's generator overlaps another's evaluation), 2 warp only
+//              with the column loop kept a loop (a third less evaluator code for the instruction cache)
 //   kPop       how the two popcount streams (column totals, leader totals) trade POPC (XU pipe, 8 cycles
 //              a warp) for carry-save LOP3 (ALU pipe, 2 cycles): one hex digit per stream, 0 = a POPC per
 //              word, 1 = three per four words, 2 = two, 3 = one (Harley-Seal accumulators carried across
@@ -220,6 +221,7 @@ __device__ __forceinline__ void patch_terms(const Params &d, const PatchSet &ps,
         const uint32_t z03 = zs[0], z47 = d.nz > 4 ? zs[1] : 0xFFFFFFFFu;
 #pragma unroll
         for (int j = 0; j < kZPlanes; ++j) {
+            if (j >= 4 && d.nz <= 4) break;
             const int slot = (int)(((j < 4 ? z03 : z47) >> (8 * (j & 3))) & 0xFFu);      // 0xFF (no term) is never a slot of the row
             const bool has = row_has<W>(rows[i], slot);
             const bool on = ((d.z_on_leader >> j) & 1) ? (has && (int)ps.ld[i] == slot) : has;
@@ -297,7 +299,7 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
             lcnt[t].add4(oh[t].x, oh[t].y, oh[t].z, oh[t].w);
         }
     };
-    if constexpr (kNW == 32) {
+    if constexpr (kNW == 32 && Cfg::kSync != 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) chunk(j);
     } else {
