@@ -186,8 +186,8 @@ int kao_set_evaluator(kao_handle *h, int32_t evaluator);
  * the warps of a CTA meet before an evaluation (0 block barrier, 1 warp only, 2 warp only with the column loop
  * kept a loop); pop: one hex digit per
  * popcount stream (column totals in the low digit, leader totals in the next): 0 a POPC per word, 1 three per
- * four words, 2 two, 3 one (carry-save adders do the rest); threads per CTA: 640 or 768.  Only the six
- * combinations built into the library are accepted (KAO_E_ARG otherwise); the default (2, 0x22, 640) is the
+ * four words, 2 two, 3 one (carry-save adders do the rest); threads per CTA: 640, 768 or 896.  Only the six
+ * combinations built into the library are accepted (KAO_E_ARG otherwise); the default (2, 0x22, 768) is the
  * fastest one measured on a B200 (profiles/).  Results never depend on it.  The environment variable
  * KAO_SCHEDULE="sync,pop(hex),threads" sets it for every session (and kao_solve); KAO_EVALUATOR=row forces
  * the row-major evaluator. */

@@ -735,10 +735,10 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 // Column-major kernels: X(sync, pop, threads) for every built schedule (kao_set_schedule); each is
 // instantiated for W = 1, 2 and for 32 partition words (compile-time offsets) / any word count.
 #define KAO_FOR_SCHEDULES(X) \
-    X(2, 0x22, 640) X(1, 0x22, 640) X(2, 0x22, 768) X(2, 0x21, 640) X(2, 0x12, 640) X(0, 0x22, 640)
+    X(2, 0x22, 768) X(2, 0x22, 640) X(1, 0x22, 640) X(2, 0x22, 896) X(2, 0x12, 768) X(0, 0x22, 768)
 #define KAO_SCHEDULE_DEFAULT_SYNC 2
 #define KAO_SCHEDULE_DEFAULT_POP 0x22
-#define KAO_SCHEDULE_DEFAULT_THREADS 640
+#define KAO_SCHEDULE_DEFAULT_THREADS 768
 #define KAO_PERSISTENT_KERNEL_T(W, NW, S, POP, T)                                                            \
     search_persistent_kernel<EvalCfgT<W, NW, S, POP, T>, T, false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
                                                                     uint32_t, unsigned long long *, unsigned int *, P2P, \
