@@ -425,20 +425,26 @@ def main():
                "last_result": {"violation": int(res.violation), "objective": int(res.objective), "moves": int(res.moves),
                                "objective_bound": int(res.objective_bound), "proven_optimal": bool(res.optimal)}}
         if not args.no_extras and args.config in EXACT:
-            # the call a user makes to SOLVE: small rounds, early stop; must end feasible at the exact optimum
-            kw = dict(rounds=2000, round_size=1 << 14, patience=100, n_gpus=1)
-            if args.config in ("4", "5"):
-                kw.update(delta=True, rounds=20000, patience=3000)
-            r2 = kopt.solve(pb_host, SEED, device=0, **kw)
-            r3 = kopt.solve(pb_host, SEED, device=0, tight_bound=True, **kw)       # + the flow bound (host): optimality certificate
-            e2e["time_to_solution"] = {
-                "ms": r2.total_ms, "device_ms": r2.device_ms, "rounds_run": int(r2.rounds), "candidates": int(r2.n_candidates),
-                "violation": int(r2.violation), "objective": int(r2.objective), "moves": int(r2.moves),
-                "exact_objective": EXACT[args.config][0], "exact_moves": EXACT[args.config][1],
-                "reached_exact_optimum": bool(r2.violation == 0 and r2.objective == EXACT[args.config][0]),
-                "with_flow_bound": {"ms": r3.total_ms, "objective": int(r3.objective), "objective_bound": int(r3.objective_bound),
-                                    "proven_optimal": bool(r3.optimal)},
-                "call": "kao_solve(%s), 1 GPU, host buffers" % ", ".join("%s=%s" % kv for kv in sorted(kw.items()))}
+            def time_to_solution():
+                # the call a user makes to SOLVE: small rounds, early stop; must end feasible at the exact optimum
+                kw = dict(rounds=2000, round_size=1 << 14, patience=100, n_gpus=1)
+                if args.config in ("4", "5"):
+                    kw.update(delta=True, rounds=20000, patience=3000)
+                r2 = kopt.solve(pb_host, SEED, device=0, **kw)
+                r3 = kopt.solve(pb_host, SEED, device=0, tight_bound=True, **kw)   # + the flow bound (host): optimality certificate
+                return {
+                    "ms": r2.total_ms, "device_ms": r2.device_ms, "rounds_run": int(r2.rounds), "candidates": int(r2.n_candidates),
+                    "violation": int(r2.violation), "objective": int(r2.objective), "moves": int(r2.moves),
+                    "exact_objective": EXACT[args.config][0], "exact_moves": EXACT[args.config][1],
+                    "reached_exact_optimum": bool(r2.violation == 0 and r2.objective == EXACT[args.config][0]),
+                    "with_flow_bound": {"ms": r3.total_ms, "objective": int(r3.objective), "objective_bound": int(r3.objective_bound),
+                                        "proven_optimal": bool(r3.optimal)},
+                    "call": "kao_solve(%s), 1 GPU, host buffers" % ", ".join("%s=%s" % kv for kv in sorted(kw.items()))}
+
+            try:                                                  # an extra key must never cost the line itself
+                e2e["time_to_solution"] = time_to_solution()
+            except Exception as e:
+                e2e["time_to_solution"] = {"error": repr(e)}
     host_barrier()
     barrier()
 
@@ -476,44 +482,53 @@ def main():
                             "design; the physical bounds are the ALU / XU pipes (profiles/)"}
         extras = {}
         if not args.no_extras:
-            solo.profile_rounds(SEED, 19_000, 1, ROUND_SIZE)                      # load the per-round kernels (lazy module load)
-            pr_ms, ap_ms = solo.profile_rounds(SEED, 20_000, 8, ROUND_SIZE)       # per-round kernels (NCCL path)
-            roofline["per_round_kernels_ms"] = {"search_round_kernel": pr_ms / 8, "apply_winner_kernel": ap_ms / 8}
-            # SURVEY 8(f)3, reported separately: the same search with delta evaluation (NOT the headline metric)
-            if solo.stats()["words_per_row"] <= 2:
-                solo.search_delta(SEED, 30_000, ROUNDS, ROUND_SIZE)
-                _, d_ms = solo.search_delta(SEED, 31_000, ROUNDS, ROUND_SIZE)
-                extras["delta_evaluation"] = {
-                    "value": ROUNDS * ROUND_SIZE / (d_ms * 1e-3), "unit": "candidates/s", "kernel_ms_per_launch": d_ms,
-                    "note": "same candidate stream and keys, scored from base totals + patched rows (one thread per "
-                            "candidate); not a full evaluation per candidate, so not comparable with `value`"}
-            # the other single-GPU BASELINE configs as extra keys (device-timed, same kernel family)
-            if world == 1 and args.config == "3":
-                for c, rs, rn in (("2", 1 << 16, 32), ("4", ROUND_SIZE, 32), ("5", 1 << 14, 16)):
-                    pbc = kao.synthetic_problem(*CONFIGS[c][0])
-                    sc = kao.Session(pbc, device=local)
-                    sc.search(SEED, 0, 2, rs)
-                    _, c_ms = sc.search(SEED, 100, rn, rs)
-                    st = sc.stats()
-                    cab = algo_bytes(pbc.P, pbc.B)
-                    extras.setdefault("other_configs", {})["config" + c] = {
-                        "workload": CONFIGS[c][1], "rounds": rn, "round_size": rs, "kernel_ms": c_ms,
-                        "value": rn * rs / (c_ms * 1e-3), "unit": "candidates/s",
-                        "evaluator": "column-major" if st["column_major"] else "row-major",
-                        "algorithmic_bytes_per_candidate": cab,
-                        "roofline_frac": rn * rs / (c_ms * 1e-3) * cab / 1e9 / peak}
-                    sc.close()
+            def collect_extras():
+                solo.profile_rounds(SEED, 19_000, 1, ROUND_SIZE)                      # load the per-round kernels (lazy module load)
+                pr_ms, ap_ms = solo.profile_rounds(SEED, 20_000, 8, ROUND_SIZE)       # per-round kernels (NCCL path)
+                roofline["per_round_kernels_ms"] = {"search_round_kernel": pr_ms / 8, "apply_winner_kernel": ap_ms / 8}
+                # SURVEY 8(f)3, reported separately: the same search with delta evaluation (NOT the headline metric)
+                if solo.stats()["words_per_row"] <= 2:
+                    solo.search_delta(SEED, 30_000, ROUNDS, ROUND_SIZE)
+                    _, d_ms = solo.search_delta(SEED, 31_000, ROUNDS, ROUND_SIZE)
+                    extras["delta_evaluation"] = {
+                        "value": ROUNDS * ROUND_SIZE / (d_ms * 1e-3), "unit": "candidates/s", "kernel_ms_per_launch": d_ms,
+                        "note": "same candidate stream and keys, scored from base totals + patched rows (one thread per "
+                                "candidate); not a full evaluation per candidate, so not comparable with `value`"}
+                # the other single-GPU BASELINE configs as extra keys (device-timed, same kernel family)
+                if world == 1 and args.config == "3":
+                    for c, rs, rn in (("2", 1 << 16, 32), ("4", ROUND_SIZE, 32), ("5", 1 << 14, 16)):
+                        pbc = kao.synthetic_problem(*CONFIGS[c][0])
+                        sc = kao.Session(pbc, device=local)
+                        sc.search(SEED, 0, 2, rs)
+                        _, c_ms = sc.search(SEED, 100, rn, rs)
+                        st = sc.stats()
+                        cab = algo_bytes(pbc.P, pbc.B)
+                        extras.setdefault("other_configs", {})["config" + c] = {
+                            "workload": CONFIGS[c][1], "rounds": rn, "round_size": rs, "kernel_ms": c_ms,
+                            "value": rn * rs / (c_ms * 1e-3), "unit": "candidates/s",
+                            "evaluator": "column-major" if st["column_major"] else "row-major",
+                            "algorithmic_bytes_per_candidate": cab,
+                            "roofline_frac": rn * rs / (c_ms * 1e-3) * cab / 1e9 / peak}
+                        sc.close()
+
+            try:                                                  # extra keys must never cost the line itself
+                collect_extras()
+            except Exception as e:
+                extras["extras_error"] = repr(e)
         if solo is not sess:
             solo.close()
         cpu = None
         if not args.no_cpu_baseline and world == 1:         # reported at N=1 only
-            v, threads, sample, omp, port_build = cpu_port_rate(args.config)
-            cpu = {"value": v, "unit": "candidates/s", "cores": threads, "kind": "port", "sample": sample,
-                   "omp_max_threads": omp, "build": port_build, "host": host_cpu_info(),
-                   "note": "lp_solve (the reference's solver) is not installed here and cannot be timed; "
-                           "this is the plain-C/OpenMP restatement of the same path"}
-            if not args.no_extras and args.config in ("2", "3", "4"):
-                cpu["exact_solve"] = exact_solve(args.config, 150.0)
+            try:
+                v, threads, sample, omp, port_build = cpu_port_rate(args.config)
+                cpu = {"value": v, "unit": "candidates/s", "cores": threads, "kind": "port", "sample": sample,
+                       "omp_max_threads": omp, "build": port_build, "host": host_cpu_info(),
+                       "note": "lp_solve (the reference's solver) is not installed here and cannot be timed; "
+                               "this is the plain-C/OpenMP restatement of the same path"}
+                if not args.no_extras and args.config in ("2", "3", "4"):
+                    cpu["exact_solve"] = exact_solve(args.config, 150.0)
+            except Exception as e:
+                cpu = dict(cpu or {}, error=repr(e))
         line = {"metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitset / int32",
