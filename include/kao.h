@@ -175,7 +175,8 @@ int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
  *   KAO_EVAL_COLUMN_MAJOR  also one bitmap over the partitions per broker slot (replicas, leader one-hot) and the
  *                          objective as term planes over the partitions; needs rows of up to 64 slots, racks of up
  *                          to 8 brokers, C7 = at most one replica per rack, wL >= wF with the non-zero terms of the
- *                          objective row (README.md:145-146) fitting 8 term planes (docs/MODEL.md 3.2), P <= 4096;
+ *                          objective row (README.md:145-146) fitting 8 term planes (docs/MODEL.md 3.2), and the planes fitting the
+ *                          shared memory of an SM (e.g. 2,000 partitions x 64 slots, 8,160 x 32);
  *                          the DEFAULT wherever it applies; KAO_E_ARG when requested elsewhere
  *   KAO_EVAL_ROW_MAJOR     rows of the (partition x broker) bit-plane, column totals by bit-sliced
  *                          counters; every layout */
@@ -186,8 +187,8 @@ int kao_set_evaluator(kao_handle *h, int32_t evaluator);
  * the warps of a CTA meet before an evaluation (0 block barrier, 1 warp only, 2 warp only with the column loop
  * kept a loop); pop: one hex digit per
  * popcount stream (column totals in the low digit, leader totals in the next): 0 a POPC per word, 1 three per
- * four words, 2 two, 3 one (carry-save adders do the rest); threads per CTA: 640, 768 or 896.  Only the six
- * combinations built into the library are accepted (KAO_E_ARG otherwise); the default (2, 0x22, 768) is the
+ * four words, 2 two, 3 one (carry-save adders do the rest); threads per CTA: 640 .. 1024.  Only the six
+ * combinations built into the library are accepted (KAO_E_ARG otherwise); the default (2, 0x22, 896) is the
  * fastest one measured on a B200 (profiles/).  Results never depend on it.  The environment variable
  * KAO_SCHEDULE="sync,pop(hex),threads" sets it for every session (and kao_solve); KAO_EVALUATOR=row forces
  * the row-major evaluator. */

@@ -22,9 +22,11 @@
 //   columns  (C2-C6)  a lane owns one SLOT per row word: replica and leader totals of its columns are
 //            popcount sums over the partition words — no bit-sliced column counters, no cross-lane
 //            reduce-scatter.
-// The candidate's <= 3 patched rows are substituted while loading (columns) / masked out of the base and
-// scored from the patch itself (rows: C1 / C7 terms and objective terms of a patched row are computed from
-// the row when the candidate is generated, patch_terms), so every row of the candidate is evaluated, none
+// The candidate's <= 3 patched rows are scored from the patch itself by the thread that generated the candidate:
+// their C1 / C7 terms and objective terms (patch_terms) and, per slot, what they change in the column totals
+// (patch_column_deltas: replicas and valid leaderships of the patched rows of the candidate minus those of the same
+// rows of the base).  The row pass masks the patched partitions out of the base, the column pass sums the base's
+// planes in full and every lane adds the delta of its own slot — so every row of the candidate is evaluated, none
 // is taken from a previous evaluation.  Model: /root/reference/README.md:144-185.
 #pragma once
 #include "kao_device.cuh"
@@ -154,14 +156,6 @@ __device__ __forceinline__ int rows_pass(const Params &d, const MemRef<kShared> 
     return viol;
 }
 
-__device__ __forceinline__ void set_comp(uint4 &v, int k, uint32_t clear, uint32_t set)
-{
-    if (k == 0) v.x = (v.x & ~clear) | set;
-    else if (k == 1) v.y = (v.y & ~clear) | set;
-    else if (k == 2) v.z = (v.z & ~clear) | set;
-    else v.w = (v.w & ~clear) | set;
-}
-
 // One popcount stream of the column pass: words arrive four at a time (one 128-bit load), the total is
 // read once per candidate.  kLvl picks how many of the four popcounts are replaced by carry-save adders:
 //   0  popc(a) + popc(b) + popc(c) + popc(d)                                            4 POPC
@@ -231,12 +225,47 @@ __device__ __forceinline__ void patch_terms(const Params &d, const PatchSet &ps,
 }
 
 // ------------------------------------------------------------------------------------------
+// What the candidate's patched rows change in the column totals, per slot: one byte per slot, low nibble =
+// 4 + (replicas on the slot in the patched rows of the candidate) - (... in the same rows of the base), high
+// nibble = the same for valid leaderships (|net| <= kMaxOps).  Computed from the rows themselves by the thread
+// that generated the candidate (like patch_terms) and parked next to it; the column pass sums the base's planes
+// in full and every lane adds the byte of its own slot.  out: [32 * W] bytes, private to the calling thread.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kDeltaBias = 0x44444444u;
+template <int W>
+__device__ __forceinline__ void patch_column_deltas(const Params &d, const PatchSet &ps, const uint32_t (&rows)[kMaxOps][W],
+                                                    const uint32_t *bitsT, const uint8_t *leader, uint8_t *out)
+{
+    static_assert(kMaxOps <= 3, "a nibble holds 4 +- kMaxOps");
+    uint32_t *ow = reinterpret_cast<uint32_t *>(out);
+#pragma unroll
+    for (int k = 0; k < 8 * W; ++k) ow[k] = kDeltaBias;
+#pragma unroll
+    for (int i = 0; i < kMaxOps; ++i) {
+        const int p = ps.p[i];
+        if (p < 0) continue;
+        uint32_t old[W];
+#pragma unroll
+        for (int t = 0; t < W; ++t) old[t] = bitsT[(size_t)t * d.Ppad + p];
+        const int old_ld = leader[p], new_ld = (int)ps.ld[i];
+#pragma unroll
+        for (int t = 0; t < W; ++t)
+            for (uint32_t m = rows[i][t] ^ old[t]; m; m &= m - 1) {
+                const int s = 32 * t + __ffs(m) - 1;
+                out[s] = (uint8_t)(out[s] + (row_has<W>(rows[i], s) ? 1 : -1));
+            }
+        if (old_ld < 32 * W && row_has<W>(old, old_ld)) out[old_ld] = (uint8_t)(out[old_ld] - 0x10);
+        if (new_ld < 32 * W && row_has<W>(rows[i], new_ld)) out[new_ld] = (uint8_t)(out[new_ld] + 0x10);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // the whole candidate.  T: the two transposed planes; Z: the term planes [kZPlanes][nW]; bits: the row-major
-// base; prow: this candidate's patched rows [kMaxOps * W]; pviol / pobj: patch_terms of those rows
+// base; pdelta: patch_column_deltas of this candidate; pviol / pobj / pcount: patch_terms of its patched rows
 // ------------------------------------------------------------------------------------------
 template <class Cfg, bool kShared>
 __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt, const uint32_t *bitsT, const uint32_t *Zp,
-                                 const Consts *cs, const PatchSet &ps, const uint32_t *prow, int pviol, int pobj, int pcount, int lane,
+                                 const Consts *cs, const PatchSet &ps, const uint8_t *pdelta, int pviol, int pobj, int pcount, int lane,
                                  int &viol_out, int &obj_out)
 {
     constexpr int W = Cfg::W, kNW = Cfg::kNW;
@@ -247,52 +276,23 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
     int obj = 0;
     int viol = rows_pass<W, kShared, kNW>(d, T, Z, B, nW, lane, ps, obj);
     if (lane == 0) { viol += pviol - 2 * pcount; obj += pobj; }    // the patched rows' own terms; their replicas are not the row pass's
-    // ---- columns: this lane owns slot `lane` of every row word
+    // ---- columns: this lane owns slot `lane` of every row word.  The planes of the base are summed in full; what
+    // the candidate's patched rows change in this lane's columns is one byte of pdelta (patch_column_deltas)
     PopStream<(Cfg::kPop >> 0) & 15> cnt[W];
     PopStream<(Cfg::kPop >> 4) & 15> lcnt[W];
-    const int nch = nW >> 2;                        // <= 32 chunks of 128 partitions (P <= 4096)
-    // the candidate's patched rows replace their partition's bit in this lane's columns: per patch the chunk,
-    // the word of the chunk, the bit and what this lane's slots hold there in the candidate
-    uint32_t patched_chunks = 0;                    // bit j: a patched partition lies in chunk j
-    uint32_t sub_has[kMaxOps][W], sub_led[kMaxOps][W];
-#pragma unroll
-    for (int i = 0; i < kMaxOps; ++i) {
-        const int pp = ps.p[i];
-        patched_chunks |= pp >= 0 ? 1u << (pp >> 7) : 0u;
-        const uint32_t bit = 1u << (pp & 31);
-#pragma unroll
-        for (int t = 0; t < W; ++t) {
-            const bool has = pp >= 0 && ((prow[i * W + t] >> lane) & 1u);
-            sub_has[i][t] = has ? bit : 0u;
-            sub_led[i][t] = (has && (int)ps.ld[i] == lane + 32 * t) ? bit : 0u;
-        }
-    }
+    const int nch = nW >> 2;                        // chunks of 128 partitions
     const bool swz = t_swizzled(nW);
     const uint32_t rot = swz ? 16u * (uint32_t)(lane & 7) : 0u;     // byte offset XORed into the chunk offset
-    auto chunk = [&](int j) {
+    auto load = [&](int j, uint4 (&col)[W], uint4 (&oh)[W]) {
         const uint32_t off = ((uint32_t)j * 16u) ^ rot;             // logical chunk j of this lane's slots
-        uint4 col[W], oh[W];
 #pragma unroll
         for (int t = 0; t < W; ++t) {
             const int s = lane + 32 * t;
             col[t] = T.ld128((uint32_t)((0 * NSL + s) * nW) * 4u + off);
             oh[t] = T.ld128((uint32_t)((1 * NSL + s) * nW) * 4u + off);
         }
-        if ((patched_chunks >> j) & 1u) {
-#pragma unroll
-            for (int i = 0; i < kMaxOps; ++i) {
-                const int pp = ps.p[i];
-                if ((pp >> 7) == j) {
-                    const int k = (pp >> 5) & 3;
-                    const uint32_t bit = 1u << (pp & 31);
-#pragma unroll
-                    for (int t = 0; t < W; ++t) {
-                        set_comp(col[t], k, bit, sub_has[i][t]);
-                        set_comp(oh[t], k, bit, sub_led[i][t]);
-                    }
-                }
-            }
-        }
+    };
+    auto add = [&](const uint4 (&col)[W], const uint4 (&oh)[W]) {
 #pragma unroll
         for (int t = 0; t < W; ++t) {
             cnt[t].add4(col[t].x, col[t].y, col[t].z, col[t].w);
@@ -301,10 +301,10 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
     };
     if constexpr (kNW == 32 && Cfg::kSync != 2) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) chunk(j);
+        for (int j = 0; j < 8; ++j) { uint4 c[W], o[W]; load(j, c, o); add(c, o); }
     } else {
 #pragma unroll 1
-        for (int j = 0; j < nch; ++j) chunk(j);
+        for (int j = 0; j < nch; ++j) { uint4 c[W], o[W]; load(j, c, o); add(c, o); }
     }
     // ---- C3 / C4 on this lane's columns, C2/C5 as P - sum of valid leaders, C6 per 8-lane rack group
     // (rack totals: the W column totals of a lane travel packed in one word through three butterfly steps
@@ -314,7 +314,8 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
 #pragma unroll
     for (int t = 0; t < W; ++t) {
         const int s = lane + 32 * t;
-        const int c = cnt[t].total(), l = lcnt[t].total();
+        const int pd = pdelta[s];
+        const int c = cnt[t].total() + (pd & 15) - 4, l = lcnt[t].total() + (pd >> 4) - 4;
         packed |= (uint32_t)c << (16 * t);                      // c <= P < 8192: the sum of 8 lanes stays below 2^16
         viol += 2 * c + band_violation(c, cs->bnd_rep[s]) + band_violation(l, cs->bnd_ldr[s]) - l;     // 2 c: see rows_pass
     }

@@ -519,13 +519,11 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                     int pviol, pobj, pcount;
                     patch_terms<W>(d, ps, rows, pviol, pobj, pcount);
                     uint32_t *mine = batch + lane * BS;
-                    mine[0] = (uint32_t)ps.p[0]; mine[1] = (uint32_t)ps.p[1]; mine[2] = (uint32_t)ps.p[2];
-                    mine[3] = (ps.ld[0] & 0xFFu) | ((ps.ld[1] & 0xFFu) << 8) | ((ps.ld[2] & 0xFFu) << 16) | ((uint32_t)ps.n << 24);
-                    mine[4] = (uint32_t)pviol | ((uint32_t)pcount << 16); mine[5] = (uint32_t)pobj;       // pviol <= 3 * 128, pcount <= 3 * 64
-#pragma unroll
-                    for (int i = 0; i < kMaxOps; ++i)
-#pragma unroll
-                        for (int w = 0; w < W; ++w) mine[kBatchHdr + i * W + w] = rows[i][w];
+                    // pviol <= 3 * 128, pcount <= 3 * 64, partitions < 8192 (0xFFFF = unused patch)
+                    mine[0] = ((uint32_t)ps.p[0] & 0xFFFFu) | ((uint32_t)ps.p[1] << 16);
+                    mine[1] = ((uint32_t)ps.p[2] & 0xFFFFu) | ((uint32_t)pcount << 16);
+                    mine[2] = (uint32_t)pviol; mine[3] = (uint32_t)pobj;
+                    patch_column_deltas<W>(d, ps, rows, s_bits, s_leader, reinterpret_cast<uint8_t *>(mine + kBatchHdr));
                 }
                 __syncwarp();
                 const uint32_t nb = iters - it0 < 32u ? iters - it0 : 32u;
@@ -536,13 +534,12 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                         const uint32_t *slot = batch + j * BS;
                         const uint4 hdr = *reinterpret_cast<const uint4 *>(slot);
                         PatchSet ps;
-                        ps.p[0] = (int)hdr.x; ps.p[1] = (int)hdr.y; ps.p[2] = (int)hdr.z;
-                        ps.ld[0] = hdr.w & 0xFFu; ps.ld[1] = (hdr.w >> 8) & 0xFFu; ps.ld[2] = (hdr.w >> 16) & 0xFFu;
-                        ps.n = (int)(hdr.w >> 24);
-                        const uint2 terms = *reinterpret_cast<const uint2 *>(slot + 4);
+                        ps.p[0] = (int)(int16_t)(hdr.x & 0xFFFFu); ps.p[1] = (int)(int16_t)(hdr.x >> 16); ps.p[2] = (int)(int16_t)(hdr.y & 0xFFFFu);
+                        ps.n = 0;                                           // the evaluator reads the partitions only
+                        ps.ld[0] = ps.ld[1] = ps.ld[2] = 0xFF;
                         int viol, obj;
-                        eval_candidate_t<Cfg, true>(d, s_sw, t_words(d.Ppad), s_bits, s_z, s_cs, ps, slot + kBatchHdr, (int)(terms.x & 0xFFFFu),
-                                                    (int)terms.y, (int)(terms.x >> 16), lane, viol, obj);
+                        eval_candidate_t<Cfg, true>(d, s_sw, t_words(d.Ppad), s_bits, s_z, s_cs, ps, reinterpret_cast<const uint8_t *>(slot + kBatchHdr),
+                                                    (int)hdr.z, (int)hdr.w, (int)(hdr.y >> 16), lane, viol, obj);
                         const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
                         if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = key;
                         best = key < best ? key : best;
@@ -735,10 +732,10 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 // Column-major kernels: X(sync, pop, threads) for every built schedule (kao_set_schedule); each is
 // instantiated for W = 1, 2 and for 32 partition words (compile-time offsets) / any word count.
 #define KAO_FOR_SCHEDULES(X) \
-    X(2, 0x22, 768) X(2, 0x22, 640) X(1, 0x22, 640) X(2, 0x22, 896) X(2, 0x12, 768) X(0, 0x22, 768)
+    X(2, 0x22, 896) X(2, 0x22, 768) X(2, 0x22, 1024) X(2, 0x22, 640) X(1, 0x22, 768) X(2, 0x12, 896)
 #define KAO_SCHEDULE_DEFAULT_SYNC 2
 #define KAO_SCHEDULE_DEFAULT_POP 0x22
-#define KAO_SCHEDULE_DEFAULT_THREADS 768
+#define KAO_SCHEDULE_DEFAULT_THREADS 896
 #define KAO_PERSISTENT_KERNEL_T(W, NW, S, POP, T)                                                            \
     search_persistent_kernel<EvalCfgT<W, NW, S, POP, T>, T, false>(Params, SmemPlan, uint64_t, uint32_t, uint32_t, \
                                                                     uint32_t, unsigned long long *, unsigned int *, P2P, \

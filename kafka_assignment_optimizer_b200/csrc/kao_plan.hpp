@@ -18,10 +18,13 @@ struct SmemPlan {
     uint32_t cap_hold, cap_led;      // delta mode: capacity of the inverted lists (0 = not staged)
 };
 // Column-major kernels: the 32 lanes of a warp generate 32 candidates at once and park them in the warp's
-// scratch.  Words per candidate: 3 partitions, (leader slots | count << 24), the C1 / C7 terms and the objective
-// terms of the patched rows (patch_terms), 3 x W row words; 16-byte aligned.
-constexpr int kBatchHdr = 6;
-__host__ __device__ constexpr int batch_stride_words(int W) { return (kBatchHdr + kMaxOps * W + 3) & ~3; }
+// scratch.  Per candidate: 4 header words — (partition 0 | partition 1 << 16), (partition 2 | replicas in the patched
+// rows << 16), the C1 / C7 terms and the objective terms of the patched rows (patch_terms); 0xFFFF = no patch —
+// then 32 * W bytes, one per slot: what the patched rows change in the column totals (patch_column_deltas).
+// 16-byte aligned; the stride is an odd multiple of 4 words (the lanes' stores spread over 8 banks).
+constexpr int kBatchHdr = 4;
+__host__ __device__ constexpr int batch_stride_words(int W) { return kBatchHdr + 8 * W; }
+static_assert(batch_stride_words(1) % 8 == 4 && batch_stride_words(2) % 8 == 4, "odd multiple of 4 words");
 
 // prow_words_per_warp: per-warp scratch for patched rows (kMaxOps * W), or a whole batch of candidates
 // lists: 1 stage the inverted lists of the per-thread generator if they fit, 0 never, -1 = for rows of up to 64 slots
@@ -75,7 +78,7 @@ inline SmemPlan make_plan_t(int W, int Ppad, int threads, int P, int RF)
 inline bool column_major_fits(int W, int Ppad, int threads, int P, int RF)
 {
     const SmemPlan s = make_plan_t(W, Ppad, threads, P, RF);
-    return s.total <= 227u * 1024u && Ppad <= 4096;      // <= 32 chunks of 128 partitions (patched_chunks)
+    return s.total <= 227u * 1024u;
 }
 
 // shared-memory plan of a delta kernel for rows wider than 64 slots: the base, the per-round tables and the

@@ -122,6 +122,7 @@ COLUMN_MAJOR = {
     "r8_b61": lambda: m.synthetic_problem(96, 61, 8, 3),                   # unequal racks, padding slots
     "p1100": lambda: m.synthetic_problem(1100, 64, 8, 3, remove=2),        # 40 partition words: two per lane
     "cfg3": lambda: m.synthetic_problem(1000, 64, 8, 3),                   # the headline shape, 32 words
+    "max_rows": SHAPES["max_rows"],                                        # 8160 partitions: 256 words per slot, 64 chunks per column
 }
 
 
@@ -225,7 +226,7 @@ def test_column_major_forms_on_a_malformed_base(emu, ref_lib, name):
 
 def test_column_major_evaluator_refuses_other_layouts(emu):
     # general rack bounds, whole-word racks, wide rows, dense weights, C7 lower bound, planes too large for shared memory
-    for name in ["readme", "s32", "w8_s16", "dense_small", "rf_up", "max_rows"]:
+    for name in ["readme", "s32", "w8_s16", "dense_small", "rf_up", "w2_rows6000"]:
         sess = emu.EmuSession(product(SHAPES[name]()))
         assert not sess.set_evaluator(1)
         sess.close()

@@ -63,9 +63,10 @@ def test_keys_and_trajectory_vs_restatement_both_evaluators(ref_lib, name, colum
     sess.close()
 
 
-@pytest.mark.parametrize("shape", [(3800, 32, 4, 3, 1), (2000, 64, 8, 3, 0), (1100, 64, 8, 3, 2)])
+@pytest.mark.parametrize("shape", [(3800, 32, 4, 3, 1), (2000, 64, 8, 3, 0), (1100, 64, 8, 3, 2), (8160, 16, 4, 2, 1)])
 def test_large_shapes_column_major(ref_lib, shape):
-    """120 / 64 / 40 partition words per slot: several words per lane in the row pass, rotated rows that wrap."""
+    """120 / 64 / 40 / 256 partition words per slot: several words per lane in the row pass, rotated rows that wrap,
+    64 chunks per column (the largest row count the engine accepts)."""
     P, B, R, RF, rm = shape
     pb = m.synthetic_problem(P, B, R, RF, remove=rm)
     r = ref_lib.Ref(pb)
@@ -122,7 +123,7 @@ def test_config3_same_winner_both_evaluators():
 
 
 def test_unsupported_layouts_are_refused():
-    for name in ["readme", "w8_s16", "dense_small", "max_rows"]:      # max_rows: the planes do not fit in shared memory
+    for name in ["readme", "w8_s16", "dense_small", "w2_rows6000"]:   # w2_rows6000: the planes do not fit in shared memory
         sess = kao.Session(product(SHAPES[name]()))
         assert not sess.set_evaluator(True)
         sess.close()
