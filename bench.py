@@ -428,8 +428,10 @@ def main():
             def time_to_solution():
                 # the call a user makes to SOLVE: small rounds, early stop; must end feasible at the exact optimum
                 kw = dict(rounds=2000, round_size=1 << 14, patience=100, n_gpus=1)
-                if args.config in ("4", "5"):
-                    kw.update(delta=True, rounds=20000, patience=3000)
+                if args.config == "4":                          # local optima of the 3-row neighbourhood: many short searches
+                    kw = dict(rounds=400, round_size=1 << 12, patience=150, restarts=12, n_gpus=1)
+                if args.config == "5":
+                    kw.update(delta=True, rounds=20000, round_size=1 << 15, patience=3000)
                 r2 = kopt.solve(pb_host, SEED, device=0, **kw)
                 r3 = kopt.solve(pb_host, SEED, device=0, tight_bound=True, **kw)   # + the flow bound (host): optimality certificate
                 return {

@@ -19,6 +19,9 @@
 namespace kao {
 
 constexpr int kMaxOps = 3;
+// control word of a candidate in a cycle round (docs/MODEL.md 5): three ops (bits 0-1), REPLACE first (bit 2 clear),
+// guided (bit 3), op 2 = R-pull (bits 4-5 = 1), op 3 = R-push (bits 7-8 = 0) with close (bit 9)
+constexpr uint32_t kCycleSet = 0x21Bu, kCycleClear = 0x4u | 0x20u | 0x80u | 0x100u;
 constexpr uint32_t kIdxBits = 24;
 constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1;
 constexpr int kKeyBits = 63;                // keys < 2^63: same order as signed int64 (NCCL min)
@@ -365,8 +368,15 @@ template <int W, bool kThread = false, bool kSmall = false> struct Gen {
         const int P = d->P, B = d->B;
         uint32_t r[4], s[4];
         philox4x32_10(idx, round, 0u, kTag, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-        const uint32_t ctl = r[0];
+        // every fourth round (round mod 4 = 3) is a CYCLE round: every candidate is a closed three-step replica cycle — a displaced partition
+        // returns to a missing home broker (guided REPLACE), a random partition moves a replica onto the broker that
+        // one left (R-pull), and a holder of the now over-full home broker moves to the broker the second one left
+        // (R-push, close); bits 11 / 13 ask the later steps to move a replica of the same ROLE (leader / follower) as
+        // the step before, which keeps the leader totals of the three brokers as they are
+        const bool cycle = (round & 3u) == 3u;
+        const uint32_t ctl = cycle ? ((r[0] & ~kCycleClear) | kCycleSet) : r[0];
         const int nops = (ctl & 3u) == 0 ? 1 : ((ctl & 3u) == 3 ? 3 : 2);
+        bool moved_leader = false;                               // the last REPLACE moved a leader replica
         const bool first_leader = (ctl >> 2) & 1u, gbit = (ctl >> 3) & 1u;
         uint32_t row[W], ld;
         int lo, hi;
@@ -406,6 +416,7 @@ template <int W, bool kThread = false, bool kSmall = false> struct Gen {
                     if (nn > 0) a = row_kth<W, kSmall>(nonhome, (int)mulhi32(r[2], (uint32_t)nn));
                 }
             }
+            moved_leader = (int)ld == a;
             hi = replace(row, ld, a, o);
             lo = a;
             push(ps, p, row, ld, rows);
@@ -420,10 +431,13 @@ template <int W, bool kThread = false, bool kSmall = false> struct Gen {
             int olo = (lo >= 0 && lo < 256) ? (int)cs->order_of_slot[lo] : 0xFF;
             if (olo >= B) olo = 0;
             uint32_t rq[W], lq;
+            const bool match = cycle && ((ctl >> (11 + 2 * (k - 1))) & 1u);
             if (link == 0) {                                   // R-push
-                const int q = find_from<0>(ps, start, hi);
+                const int q = !match ? find_from<0>(ps, start, hi) : (moved_leader ? find_from<1>(ps, start, hi) : find_from<2>(ps, start, hi));
                 if (q < 0) return;
                 read_row(q, rq, lq);
+                if (!row_has<W>(rq, hi)) return;               // led from hi without a replica there (malformed base)
+                moved_leader = (int)lq == hi;
                 hi = replace(rq, lq, hi, close ? olo : (int)mulhi32(rb, (uint32_t)B));
                 push(ps, q, rq, lq, rows);
             } else if (link == 1) {                            // R-pull
@@ -436,7 +450,19 @@ template <int W, bool kThread = false, bool kSmall = false> struct Gen {
                 const int nq = row_count<W>(rq);
                 if (nq == 0) return;
                 int src = row_kth<W, kSmall>(rq, (int)mulhi32(rb, (uint32_t)nq));
-                if (close && (int)lq < W * 32 && row_has<W>(rq, (int)lq)) src = (int)lq;
+                const bool led = (int)lq < W * 32 && row_has<W>(rq, (int)lq);
+                if (close && led) src = (int)lq;
+                if (match && led) {                            // same role as the replica that left `lo`
+                    if (moved_leader) src = (int)lq;
+                    else if (nq > 1) {
+                        uint32_t fol[W];
+#pragma unroll
+                        for (int t = 0; t < W; ++t) fol[t] = rq[t];
+                        row_flip<W>(fol, (int)lq);
+                        src = row_kth<W, kSmall>(fol, (int)mulhi32(rb, (uint32_t)(nq - 1)));
+                    }
+                }
+                moved_leader = (int)lq == src;
                 replace(rq, lq, src, olo);
                 lo = src;
                 push(ps, q, rq, lq, rows);

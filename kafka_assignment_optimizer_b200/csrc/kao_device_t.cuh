@@ -14,9 +14,10 @@
 // per plane, and
 //   Z[j] bit p  <=>  term j of partition p holds in the base   =>   objective = sum_j z_value[j] * popc(Z[j]).
 // The evaluation walks the matrix twice, each time with all data of a constraint inside one lane:
-//   rows     (C1, C7, objective)  a lane owns 32 PARTITIONS (one word of every slot and of every term
-//            plane).  Per 8-slot rack field one word `any` (the field holds a replica; 4 LOP3), their bit-sliced
-//            sum z = racks in use, and C1 + C7 of all rows together as sums: rows with z == RF cost
+//   rows     (C1, C7, objective)  a lane owns 32 PARTITIONS (one word of every rack-field plane and of every term
+//            plane).  Next to T and Z the base is kept as RACK-FIELD PLANES A[b] (bit p <=> partition p holds a
+//            replica in the 8-slot rack field b: the (partition x rack) occupancy matrix).  From the words A[b][w] the
+//            bit-sliced sum z = racks in use, and C1 + C7 of all rows together as sums: rows with z == RF cost
 //            2 n - z - RF each (n from the column totals), the few with z != RF are corrected one by one from
 //            the row-major base (rows_pass).  No popcount per row.  The objective is one POPC per term plane;
 //   columns  (C2-C6)  a lane owns one SLOT per row word: replica and leader totals of its columns are
@@ -52,6 +53,7 @@ struct EvalCfgT {
 };
 constexpr int kTPlanes = 2;
 constexpr int kZPlanes = 8;          // term planes of the objective: [kZPlanes][nW] words behind the transposed planes
+template <int W> __host__ __device__ constexpr int kAPlanes() { return 4 * W; }     // rack-field planes behind the term planes
 
 // C1 + C7 of one row held row-major (a patched row of the candidate, or a row the vertical pass
 // flagged): same terms as row_rack_terms<W, 3>
@@ -72,7 +74,7 @@ inline long long emu_rows_charged_one_by_one = 0;
 // ------------------------------------------------------------------------------------------
 // rows: C1 + C7 of every partition that is not patched, 32 partitions per lane — as sums, not row by row.
 // With "at most one replica per rack" a row of n replicas in z racks costs |n - RF| (C1) + (n - z) (C7).
-// Per 8-slot rack field one word `any` (the field holds a replica; 4 LOP3) and the bit-sliced sum z of these
+// Per 8-slot rack field one word `any` (the field holds a replica: the rack-field planes) and the bit-sliced sum z of these
 // words.  Rows with z == RF have n >= RF, so over them  sum |n - RF| + (n - z)  =  2 sum n - sum z - RF * #rows;
 // rows with z != RF (`flagged`, rare: short rows, rows with a doubled rack) are charged the difference to their
 // exact terms one by one from the row-major base.  sum n over the unpatched rows is (sum of the column totals) -
@@ -82,7 +84,7 @@ inline long long emu_rows_charged_one_by_one = 0;
 // bit-plane (also rows with more than RF replicas); no popcount per row, no search for doubled fields.
 // ------------------------------------------------------------------------------------------
 template <int W, bool kShared, int kNW>
-__device__ __forceinline__ int rows_pass(const Params &d, const MemRef<kShared> &T, const MemRef<kShared> &Z, const MemRef<kShared> &bitsT,
+__device__ __forceinline__ int rows_pass(const Params &d, const MemRef<kShared> &Z, const MemRef<kShared> &bitsT,
                                          int nW_rt, int lane, const PatchSet &ps, int &obj)
 {
     const int Ppad = d.Ppad, P = d.P, RF = d.RF;
@@ -104,18 +106,13 @@ __device__ __forceinline__ int rows_pass(const Params &d, const MemRef<kShared> 
 #pragma unroll
             for (int j = 4; j < kZPlanes; ++j) obj += __popc(Z.ld32((uint32_t)(j * nW + w) * 4u) & valid) * d.z_value[j];
         }
-        int tk[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) tk[k] = t_swizzled(nW) ? (w ^ (4 * k)) : w;
+        // rack-field planes of the base (behind the term planes): bit p of A[b][w] <=> partition p holds a replica in
+        // rack field b — the (partition x rack) occupancy matrix, kept in step with the base like T and Z
         uint32_t any[NB];
         int racks = 0;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            uint32_t x[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = T.ld32((uint32_t)((b * 8 + k) * nW + tk[k]) * 4u);
-            // OR of the 8 words of the field, masked to the partitions this pass scores
-            any[b] = lop3<0xA8>(lop3<0xFE>(lop3<0xFE>(x[0], x[1], x[2]), lop3<0xFE>(x[3], x[4], x[5]), x[6]), x[7], valid);
+            any[b] = Z.ld32((uint32_t)((kZPlanes + b) * nW + w) * 4u) & valid;
             racks += __popc(any[b]);
         }
         viol -= racks + RF * __popc(valid);
@@ -274,7 +271,7 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
     const MemRef<kShared> T(Tp), B(bitsT), Z(Zp);
     // ---- rows: unpatched partitions from the transposed bit-plane and the term planes, patched ones from the patch
     int obj = 0;
-    int viol = rows_pass<W, kShared, kNW>(d, T, Z, B, nW, lane, ps, obj);
+    int viol = rows_pass<W, kShared, kNW>(d, Z, B, nW, lane, ps, obj);
     if (lane == 0) { viol += pviol - 2 * pcount; obj += pobj; }    // the patched rows' own terms; their replicas are not the row pass's
     // ---- columns: this lane owns slot `lane` of every row word.  The planes of the base are summed in full; what
     // the candidate's patched rows change in this lane's columns is one byte of pdelta (patch_column_deltas)
@@ -374,9 +371,21 @@ __device__ __forceinline__ uint32_t z_gather(const Params &d, int j, int w, cons
     }
     return out;
 }
+// one word (32 partitions) of rack-field plane b: the partition holds a replica in the 8-slot field b
+template <int W>
+__device__ __forceinline__ uint32_t a_gather(int b, int w, const uint32_t *bitsT, int Ppad)
+{
+    uint32_t out = 0;
+    for (int i = 0; i < 32; ++i) {
+        const int p = 32 * w + i;
+        if (p >= Ppad) break;
+        out |= (((bitsT[(size_t)(b >> 2) * Ppad + p] >> (8 * (b & 3))) & 0xFFu) ? 1u : 0u) << i;
+    }
+    return out;
+}
 // Row p of the base becomes (newrow, newld): every lane rewrites bit p of its own slots' words in both
-// transposed planes, lanes 0..7 bit p of one term plane each (the whole warp calls this; the row-major base
-// itself is patched by the caller).
+// transposed planes, lanes 0..7 bit p of one term plane each, the next 4 W lanes bit p of one rack-field plane each
+// (the whole warp calls this; the row-major base itself is patched by the caller).
 template <int W>
 __device__ __forceinline__ void t_patch_row(const Params &d, uint32_t *T, uint32_t *Z, int nW, int p, const uint32_t (&newrow)[W],
                                             uint32_t newld, int lane)
@@ -399,6 +408,10 @@ __device__ __forceinline__ void t_patch_row(const Params &d, uint32_t *T, uint32
     if (lane < kZPlanes) {
         uint32_t &word = Z[lane * nW + w];
         word = z_term_holds<W>(d, lane, p, newrow, newld) ? (word | bit) : (word & ~bit);
+    } else if (lane < kZPlanes + kAPlanes<W>()) {
+        const int b = lane - kZPlanes;
+        uint32_t &word = Z[lane * nW + w];
+        word = ((newrow[b >> 2] >> (8 * (b & 3))) & 0xFFu) ? (word | bit) : (word & ~bit);
     }
 }
 

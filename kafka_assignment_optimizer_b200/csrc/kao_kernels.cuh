@@ -85,6 +85,7 @@ __device__ __forceinline__ void build_t_planes(const Params &d, uint32_t *T, uin
         T[t_word(q, s, w, nW, NSL)] = t_gather<W>(q, s, w, s_bits, s_leader, d.Ppad);
     }
     for (int o = threadIdx.x; o < kZPlanes * nW; o += THREADS) Z[o] = z_gather<W>(d, o / nW, o % nW, s_bits, s_leader);
+    for (int o = threadIdx.x; o < kAPlanes<W>() * nW; o += THREADS) Z[kZPlanes * nW + o] = a_gather<W>(o / nW, o % nW, s_bits, d.Ppad);
     __syncthreads();
 }
 

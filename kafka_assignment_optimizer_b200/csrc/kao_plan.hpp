@@ -72,7 +72,7 @@ inline SmemPlan make_plan_t(int W, int Ppad, int threads, int P, int RF)
     // partition covers that for every Ppad the evaluator accepts
     const int nW = t_words(Ppad);
     const int per_row = (kTPlanes * W * 32 * nW + Ppad - 1) / Ppad;
-    return make_plan(W, Ppad, threads / 32, per_row, P, RF, false, 32 * batch_stride_words(W), 0, kZPlanes * nW * 4);
+    return make_plan(W, Ppad, threads / 32, per_row, P, RF, false, 32 * batch_stride_words(W), 0, (kZPlanes + 4 * W) * nW * 4);      // term planes + rack-field planes
 }
 // does the column-major evaluator cover this layout (kao_create; tests/emu asks the same question)
 inline bool column_major_fits(int W, int Ppad, int threads, int P, int RF)

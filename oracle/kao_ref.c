@@ -436,8 +436,11 @@ static void gen_patches(const ref_problem *pb, const ref_layout *L, const ref_au
     uint32_t r[4], s[4];
     kao_ref_philox(c0, key, r);
     kao_ref_philox(c1, key, s);
-    const uint32_t ctl = r[0];
+    /* every fourth round (round mod 4 = 3) is a cycle round: three ops, guided REPLACE first, R-pull, R-push with close */
+    const int cycle = (round & 3u) == 3u;
+    const uint32_t ctl = cycle ? ((r[0] & ~(0x4u | 0x20u | 0x80u | 0x100u)) | 0x21Bu) : r[0];
     const int nops = (ctl & 3u) == 0 ? 1 : ((ctl & 3u) == 3 ? 3 : 2);
+    int moved_leader = 0;                                  /* the last REPLACE moved a leader replica */
     const int first_leader = (ctl >> 2) & 1u, gbit = (ctl >> 3) & 1u;
     uint32_t row[KAO_MAX_W]; int ld;
     int lo, hi;
@@ -465,6 +468,7 @@ static void gen_patches(const ref_problem *pb, const ref_layout *L, const ref_au
                 if (nn > 0) a = row_kth(nonhome, W, (int)mulhi32(r[2], (uint32_t)nn));
             }
         }
+        moved_leader = (ld == a);
         if (!op_replace(pb, L, bits, leader, ps, p, a, o, &hi)) return;
         lo = a;
     }
@@ -475,9 +479,15 @@ static void gen_patches(const ref_problem *pb, const ref_layout *L, const ref_au
         const int start = (int)mulhi32(ra, (uint32_t)P);
         int olo = (lo < KAO_MAX_SLOTS) ? L->order_of_slot[lo] : -1;
         if (olo < 0) olo = 0;
+        /* cycle rounds, bits 11 / 13: the op moves a replica of the same role (leader / follower) as the one before */
+        const int match = cycle && ((ctl >> (11 + 2 * (k - 1))) & 1u);
         if (link == 0) {                                   /* R-push */
-            int q = find_holder(pb, W, bits, ps, start, hi), t;
+            int q, t;
+            if (!match) q = find_holder(pb, W, bits, ps, start, hi);
+            else q = moved_leader ? find_led_by(pb, leader, ps, start, hi) : find_follower(pb, W, bits, leader, ps, start, hi);
             if (q < 0) return;
+            if (hi < 0 || hi >= W * 32 || !row_has(bits + (size_t)q * W, hi)) return;
+            moved_leader = (leader[q] == hi);
             if (!op_replace(pb, L, bits, leader, ps, q, hi, close ? olo : (int)mulhi32(rb, (uint32_t)B), &t)) return;
             hi = t;
         } else if (link == 1) {                            /* R-pull */
@@ -488,7 +498,18 @@ static void gen_patches(const ref_problem *pb, const ref_layout *L, const ref_au
             const int nq = row_count(rq, W);
             if (nq == 0) return;
             int src = row_kth(rq, W, (int)mulhi32(rb, (uint32_t)nq));
-            if (close && lq < W * 32 && row_has(rq, lq)) src = lq;
+            const int led = lq < W * 32 && row_has(rq, lq);
+            if (close && led) src = lq;
+            if (match && led) {
+                if (moved_leader) src = lq;
+                else if (nq > 1) {
+                    uint32_t fol[KAO_MAX_W];
+                    memcpy(fol, rq, (size_t)W * 4);
+                    row_clr(fol, lq);
+                    src = row_kth(fol, W, (int)mulhi32(rb, (uint32_t)(nq - 1)));
+                }
+            }
+            moved_leader = (src == lq);
             if (!op_replace(pb, L, bits, leader, ps, q, src, olo, &t)) return;
             lo = src;
         } else if (link == 2) {                            /* L-push */

@@ -50,9 +50,11 @@ template <int W> void build_T(Emu &e)
         for (int s = 0; s < 32 * W; ++s)
             for (int w = 0; w < e.nW; ++w)
                 e.T[t_word(q, s, w, e.nW, 32 * W)] = t_gather<W>(q, s, w, e.bits.data(), e.leader.data(), m.Ppad);
-    e.Z.assign((size_t)kZPlanes * e.nW, 0);
+    e.Z.assign((size_t)(kZPlanes + kAPlanes<W>()) * e.nW, 0);
     for (int j = 0; j < kZPlanes; ++j)
         for (int w = 0; w < e.nW; ++w) e.Z[(size_t)j * e.nW + w] = z_gather<W>(e.prm, j, w, e.bits.data(), e.leader.data());
+    for (int b = 0; b < kAPlanes<W>(); ++b)
+        for (int w = 0; w < e.nW; ++w) e.Z[(size_t)(kZPlanes + b) * e.nW + w] = a_gather<W>(b, w, e.bits.data(), m.Ppad);
 }
 
 uint32_t oh_word(uint32_t x, uint32_t ld, int w) { return ((int)(ld >> 5) == w) ? (x & (1u << (ld & 31u))) : 0u; }

@@ -37,7 +37,8 @@ def optima():
 
 
 def streams():
-    """keys of the first 192 candidates + identity of round 2, and an 8-round trajectory, per shape
+    """keys of the first 192 candidates + identity of round 2 (a free round) and of the first 192 candidates of round 3
+    (a cycle round, docs/MODEL.md 5), and an 8-round trajectory, per shape
     (packed with the per-problem key layout of docs/MODEL.md 3: obj_bits is stored next to them)"""
     out = {}
     for name in sorted(SHAPES):
@@ -48,10 +49,12 @@ def streams():
         v, o = r.evaluate(bits, ld)
         keys = r.candidate_keys(bits, ld, 0xC0FFEE, 2, 1024, 0, 192)
         last = r.candidate_keys(bits, ld, 0xC0FFEE, 2, 1024, 1023, 1)
+        keys3 = r.candidate_keys(bits, ld, 0xC0FFEE, 3, 1024, 0, 192)
         b2, l2 = bits.copy(), ld.copy()
         _, traj = r.search(b2, l2, 0xC0FFEE, 0, 8, 512)
         out[name] = {"W": r.W, "obj_bits": r.obj_bits, "init_base": base.tolist(), "init_eval": [v, o],
                      "keys_round2": [int(k) for k in keys], "identity_key": int(last[0]),
+                     "keys_round3": [int(k) for k in keys3],
                      "trajectory": [int(k) for k in traj], "final_base": r.decode(b2, l2).tolist()}
     return out
 

@@ -46,6 +46,7 @@ def test_device_code_reproduces_golden_streams(emu, golden_streams, name):
     assert base.tolist() == g["init_base"] and [v, o] == g["init_eval"]
     nkeys = 48 if name in BIG else 192
     assert [int(k) for k in sess.candidate_keys(0xC0FFEE, 2, 1024, 0, nkeys)] == g["keys_round2"][:nkeys]
+    assert [int(k) for k in sess.candidate_keys(0xC0FFEE, 3, 1024, 0, nkeys)] == g["keys_round3"][:nkeys]      # a cycle round
     assert int(sess.candidate_keys(0xC0FFEE, 2, 1024, 1023, 1)[0]) == g["identity_key"]
     if name not in BIG:
         rounds = 8 if name in FULL_TRAJECTORY else 2
@@ -135,6 +136,7 @@ def test_column_major_evaluator_reproduces_golden_streams(emu, golden_streams, n
     assert base.tolist() == g["init_base"] and [v, o] == g["init_eval"]
     nkeys = 64 if name in BIG else 192
     assert [int(k) for k in sess.candidate_keys(0xC0FFEE, 2, 1024, 0, nkeys)] == g["keys_round2"][:nkeys]
+    assert [int(k) for k in sess.candidate_keys(0xC0FFEE, 3, 1024, 0, nkeys)] == g["keys_round3"][:nkeys]      # a cycle round
     assert int(sess.candidate_keys(0xC0FFEE, 2, 1024, 1023, 1)[0]) == g["identity_key"]
     if name not in BIG:
         keys = sess.search(0xC0FFEE, 0, 8, 512)          # winners also patch the transposed planes

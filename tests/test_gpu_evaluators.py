@@ -35,6 +35,7 @@ def test_golden_streams_both_evaluators(golden_streams, name, column_major):
     sess = kao.Session(product(SHAPES[name]()))
     assert sess.set_evaluator(column_major)
     assert [int(k) for k in sess.candidate_keys(0xC0FFEE, 2, 1024, 0, 192)] == g["keys_round2"]
+    assert [int(k) for k in sess.candidate_keys(0xC0FFEE, 3, 1024, 0, 192)] == g["keys_round3"]      # a cycle round
     assert int(sess.candidate_keys(0xC0FFEE, 2, 1024, 1023, 1)[0]) == g["identity_key"]
     keys, _ = sess.search(0xC0FFEE, 0, 8, 512)
     assert [int(k) for k in keys] == g["trajectory"]

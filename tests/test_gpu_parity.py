@@ -61,6 +61,7 @@ def test_golden_streams(golden_streams, name):
     base, v, o, _ = sess.get_base()
     assert base.tolist() == g["init_base"] and [v, o] == g["init_eval"]
     assert [int(k) for k in sess.candidate_keys(0xC0FFEE, 2, 1024, 0, 192)] == g["keys_round2"]
+    assert [int(k) for k in sess.candidate_keys(0xC0FFEE, 3, 1024, 0, 192)] == g["keys_round3"]      # a cycle round
     assert int(sess.candidate_keys(0xC0FFEE, 2, 1024, 1023, 1)[0]) == g["identity_key"]
     keys, _ = sess.search(0xC0FFEE, 0, 8, 512)
     assert [int(k) for k in keys] == g["trajectory"]
