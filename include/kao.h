@@ -92,6 +92,10 @@ typedef struct kao_options {
                                          column-major one applies (see kao_set_evaluator); same keys, same result */
 #define KAO_FLAG_BOUND 0x400u         /* kao_result.objective_bound from the flow relaxations of kao_objective_bound (host work
                                          after the search, milliseconds at config 3) instead of the per-partition bound */
+#define KAO_FLAG_SPREAD_RESTARTS 0x800u /* n_gpus > 1: run the restarts side by side, restart r on GPU r mod N as an ordinary
+                                         single-GPU search (nothing is exchanged between the GPUs), instead of sharding every
+                                         round of every restart; same result as one GPU.  The way to use several GPUs for
+                                         the recipe that finds optima: many short independent searches */
 #define KAO_FLAG_PATIENCE(n) ((uint32_t)(n) << 16)  /* stop a search after n (<= 65535) rounds without a better key */
 
 typedef struct kao_result {

@@ -977,6 +977,81 @@ static int solve_gang(const kao_problem *pb, const kao_options *opt, kao_result 
     return KAO_OK;
 }
 
+// KAO_FLAG_SPREAD_RESTARTS: the restarts of one kao_solve side by side on the GPUs of the call — restart r runs on
+// GPU r mod N as an ordinary single-GPU search (no exchange between the GPUs at all), one host thread per GPU; the
+// best final assignment wins, ties go to the lowest restart index: exactly what one GPU returns for the same call.
+static int solve_spread(const kao_problem *pb, const kao_options *opt, kao_result *res, const std::vector<int> &devs,
+                        uint32_t restarts, bool delta, uint32_t &rounds_run, double &dev_ms_total, HostModel &hm_out)
+{
+    const int world = (int)devs.size();
+    struct Best {
+        bool have = false;
+        int64_t viol = 0, obj = 0;
+        int32_t moves = 0;
+        uint32_t restart = 0, rounds = 0;
+        uint64_t key = kKeyNone;
+        double dev_ms = 0;
+        std::vector<int32_t> reps;
+        HostModel hm;
+    };
+    std::vector<Best> best(world);
+    std::vector<int> rcs(world, KAO_OK);
+    std::vector<std::string> errs(world);
+    auto worker = [&](int i) {
+        Best &b = best[i];
+        rcs[i] = guarded([&]() -> int {
+            kao_handle *h = nullptr;
+            int rc = create_handle(pb, devs[i], &h);
+            if (rc != KAO_OK) return rc;
+            struct Closer { kao_handle *h; ~Closer() { const std::string keep = g_err; destroy_impl(h); g_err = keep; } } closer{h};
+            h->patience = opt->flags >> 16;
+            if (opt->flags & KAO_FLAG_ROW_MAJOR) h->evaluator = KAO_EVAL_ROW_MAJOR;
+            b.hm = h->hm;
+            std::vector<uint64_t> keys(opt->rounds ? opt->rounds : 1, kKeyNone);
+            std::vector<int32_t> reps((size_t)pb->P * pb->RF);
+            bool first = true;
+            for (uint32_t r = (uint32_t)i; r < restarts; r += (uint32_t)world) {
+                double dev_ms = 0;
+                if (!first && (rc = reset_impl(h)) != KAO_OK) return rc;
+                first = false;
+                rc = search_impl(h, opt->seed + 0x9E3779B97F4A7C15ull * r, 0, opt->rounds, opt->round_size, keys.data(), &dev_ms, delta);
+                if (rc != KAO_OK) return rc;
+                int64_t viol = 0, obj = 0;
+                int32_t moves = 0;
+                rc = get_base_impl(h, reps.data(), &viol, &obj, &moves);
+                if (rc != KAO_OK) return rc;
+                b.dev_ms += dev_ms;
+                b.rounds += h->last_rounds;
+                if (!b.have || viol < b.viol || (viol == b.viol && obj > b.obj)) {
+                    b.have = true; b.viol = viol; b.obj = obj; b.moves = moves; b.restart = r;
+                    b.key = h->last_rounds ? keys[h->last_rounds - 1] : kKeyNone;
+                    b.reps = reps;
+                }
+            }
+            return KAO_OK;
+        });
+        if (rcs[i] != KAO_OK) errs[i] = g_err;
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < world; ++i) th.emplace_back(worker, i);
+    worker(0);
+    for (auto &t : th) t.join();
+    for (int i = 0; i < world; ++i)
+        if (rcs[i] != KAO_OK) return fail(rcs[i], "GPU " + std::to_string(devs[i]) + ": " + errs[i]);
+    const Best *win = nullptr;
+    for (const Best &b : best) {
+        if (!b.have) continue;                        // more GPUs than restarts
+        rounds_run += b.rounds;
+        dev_ms_total = b.dev_ms > dev_ms_total ? b.dev_ms : dev_ms_total;
+        if (!win || b.viol < win->viol || (b.viol == win->viol && (b.obj > win->obj || (b.obj == win->obj && b.restart < win->restart)))) win = &b;
+    }
+    if (!win) return fail(KAO_E_STATE, "no restart ran");
+    std::memcpy(res->replicas, win->reps.data(), win->reps.size() * 4);
+    res->violation = win->viol; res->objective = win->obj; res->moves = win->moves; res->key = win->key;
+    hm_out = best[0].hm;
+    return KAO_OK;
+}
+
 static int solve_impl(const kao_problem *pb, const kao_options *opt, kao_result *res)
 {
     if (!pb || !opt || !res || !res->replicas) return fail(KAO_E_ARG, "null argument");
@@ -1033,6 +1108,9 @@ static int solve_impl(const kao_problem *pb, const kao_options *opt, kao_result 
             }
         }
         hm = h0->hm;
+    } else if (opt->flags & KAO_FLAG_SPREAD_RESTARTS) {
+        rc = solve_spread(pb, opt, res, devs, restarts, delta, rounds_run, dev_ms_total, hm);
+        if (rc != KAO_OK) return rc;
     } else {
         rc = solve_gang(pb, opt, res, devs, restarts, delta, keys, reps, rounds_run, dev_ms_total, hm);
         if (rc != KAO_OK) return rc;

@@ -295,14 +295,15 @@ class Session:
 def solve(pb: Problem, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15,
           device: int = 0, require_feasible: bool = False, restarts: int = 1, delta: bool = False,
           patience: int = 0, row_major: bool = False, n_gpus: int = 1, device_mask: int = 0,
-          tight_bound: bool = False) -> SolveResult:
+          tight_bound: bool = False, spread_restarts: bool = False) -> SolveResult:
     """One blocking kao_solve from host buffers (tables up, winner down).  n_gpus > 1: every round is sharded
-    over that many GPUs of this process (devices device .. device+n_gpus-1, or those of device_mask); the
-    result is the same as on one GPU with the same round_size."""
+    over that many GPUs of this process (devices device .. device+n_gpus-1, or those of device_mask), or with
+    spread_restarts the restarts run side by side, one single-GPU search per GPU at a time; either way the
+    result is the same as on one GPU with the same arguments."""
     lib = load_library()
     cp = _CProblem(pb)
     reps = np.full((pb.P, pb.RF), -1, np.int32)
-    flags = (max(1, min(255, restarts)) | (0x100 if delta else 0) | (0x200 if row_major else 0) | (0x400 if tight_bound else 0) |
+    flags = (max(1, min(255, restarts)) | (0x100 if delta else 0) | (0x200 if row_major else 0) | (0x400 if tight_bound else 0) | (0x800 if spread_restarts else 0) |
              (max(0, min(65535, patience)) << 16))
     opt = _KaoOptions(seed & (2 ** 64 - 1), rounds, round_size, device, flags, n_gpus, device_mask)
     res = _KaoResult()

@@ -102,6 +102,14 @@ def test_kao_solve_gives_the_same_answer_on_any_number_of_gpus():
     a = kopt.solve(pb, seed=5, rounds=30, round_size=4096, restarts=3)
     b = kopt.solve(pb, seed=5, rounds=30, round_size=4096, restarts=3, n_gpus=0, device_mask=0b11)
     assert b.n_gpus == 2 and (a.replicas == b.replicas).all() and a.key == b.key
+    # KAO_FLAG_SPREAD_RESTARTS: the restarts side by side, one single-GPU search per GPU at a time — same winner
+    # (ties go to the lowest restart), same number of rounds in all, also with more GPUs than restarts
+    for restarts in (1, 5):
+        kw = dict(seed=9, rounds=120, round_size=2048, patience=40, restarts=restarts)
+        a = kopt.solve(pb, **kw)
+        b = kopt.solve(pb, n_gpus=2, spread_restarts=True, **kw)
+        assert b.n_gpus == 2 and (a.replicas == b.replicas).all()
+        assert (a.violation, a.objective, a.moves, a.key, a.rounds) == (b.violation, b.objective, b.moves, b.key, b.rounds)
     with pytest.raises(kao.KaoError):
         kopt.solve(pb, rounds=1, round_size=64, n_gpus=ndev + 1)            # more GPUs than the box has
     with pytest.raises(kao.KaoError):

@@ -198,6 +198,8 @@ def test_restarts_keep_the_best_assignment(golden_optima):
     assert four.n_candidates == 4 * one.n_candidates
     assert (four.violation, -four.objective) <= (one.violation, -one.objective)
     assert m.evaluate(m.synthetic_problem(*e["args"]), four.replicas) == (four.violation, four.objective)
+    same = kopt.solve(pb, seed=11, rounds=60, round_size=2048, restarts=4, spread_restarts=True)     # one GPU: the flag changes nothing
+    assert (same.replicas == four.replicas).all() and (same.key, same.rounds) == (four.key, four.rounds)
 
 
 def test_patience_stops_early_with_the_same_answer(golden_optima):
