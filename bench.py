@@ -54,22 +54,31 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the query loop is started before the
+    warm-up (nvidia-smi takes ~100 ms to come up), every line is stamped on arrival, and only the lines that arrived
+    between mark_begin() and mark_end() count (all of them if the region was shorter than one sampling period)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.lines, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+            threading.Thread(target=lambda: [self.lines.append((time.monotonic(), l)) for l in self.proc.stdout], daemon=True).start()
         except Exception:
             self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.monotonic()
+
+    def mark_end(self):
+        self.t1 = time.monotonic()
 
     def stop(self):
         if self.proc:
@@ -78,9 +87,11 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
+        inside = [l for t, l in self.lines if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.02]
+        used = inside or [l for _, l in self.lines]
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for l in used:
             f = [t.strip() for t in l.split(",")]
             if len(f) < 6:
                 continue
@@ -93,7 +104,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
 def host_cpu_info():
@@ -334,21 +345,23 @@ def main():
         sharded_equals_single = bool(flag.item()) and same_everywhere
         sess.reset()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                      # up and sampling by the time the warm-up is through
     for w in range(args.warmup):
         step(w)
     barrier()
     launches0 = sess.stats()["kernel_launches"]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    sampler.mark_begin()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                                # L2 flush between timed steps (outside the events)
         ev[k][0].record()
         step(args.warmup + k)
         ev[k][1].record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)

@@ -109,13 +109,8 @@ __device__ __forceinline__ int rows_pass(const Params &d, const MemRef<kShared> 
         // rack-field planes of the base (behind the term planes): bit p of A[b][w] <=> partition p holds a replica in
         // rack field b — the (partition x rack) occupancy matrix, kept in step with the base like T and Z
         uint32_t any[NB];
-        int racks = 0;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            any[b] = Z.ld32((uint32_t)((kZPlanes + b) * nW + w) * 4u) & valid;
-            racks += __popc(any[b]);
-        }
-        viol -= racks + RF * __popc(valid);
+        for (int b = 0; b < NB; ++b) any[b] = Z.ld32((uint32_t)((kZPlanes + b) * nW + w) * 4u) & valid;
         // z = number of rack fields in use, bit-sliced (0..8)
         uint32_t z1, z2, z4 = 0, z8 = 0;
         if constexpr (NB == 4) {
@@ -138,6 +133,8 @@ __device__ __forceinline__ int rows_pass(const Params &d, const MemRef<kShared> 
             z4 = e1 ^ e2;
             z8 = e1 & e2;
         }
+        // sum of z over the scored rows = racks in use, from the bit planes of z (4 popcounts instead of one per field)
+        viol -= __popc(z1) + 2 * __popc(z2) + 4 * __popc(z4) + 8 * __popc(z8) + RF * __popc(valid);
         const uint32_t flagged = ((z1 ^ rf0) | (z2 ^ rf1) | (z4 ^ rf2) | (z8 ^ rf3)) & valid;    // z != RF
         for (uint32_t m = flagged; m; m &= m - 1) { // rare: the row's exact C1 term in place of the n >= RF form
 #if defined(KAO_HOST_EMU)
