@@ -54,25 +54,43 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the query loop is started before the
-    warm-up (nvidia-smi takes ~100 ms to come up), every line is stamped on arrival, and only the lines that arrived
-    between mark_begin() and mark_end() count (all of them if the region was shorter than one sampling period)."""
+    """SM clock and throttle reasons sampled DURING the timed region, through NVML (what nvidia-smi reads: its
+    own output arrives block-buffered through a pipe, i.e. too late) from a thread of this process every 5 ms;
+    only the samples taken between mark_begin() and mark_end() count (all of them if there were none)."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.lines, self.proc, self.index = [], None, index
+        self.samples, self.index, self.thread = [], index, None
         self.t0 = self.t1 = None
+        self.running = False
+        self.error = None
+
+    def _loop(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:                                          # NVML counts physical devices
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    pass
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while self.running:
+                self.samples.append((time.monotonic(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx, int(get_reasons(h))))
+                time.sleep(0.005)
+        except Exception as e:                               # no NVML: the line says so instead of inventing clocks
+            self.error = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: [self.lines.append((time.monotonic(), l)) for l in self.proc.stdout], daemon=True).start()
-        except Exception:
-            self.proc = None
+        self.running = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def mark_begin(self):
         self.t0 = time.monotonic()
@@ -81,30 +99,22 @@ class ClockSampler:
         self.t1 = time.monotonic()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                pass
-        inside = [l for t, l in self.lines if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.02]
-        used = inside or [l for _, l in self.lines]
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in used:
-            f = [t.strip() for t in l.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx = max(mx, float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
+        self.running = False
+        if self.thread:
+            self.thread.join(timeout=2)
+        inside = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1]
+        used = inside or self.samples
+        sm = sorted(x[1] for x in used)
+        reasons = set()
+        for x in used:
+            for bit, name in self.REASONS.items():
+                if x[3] & bit:
+                    reasons.add(name)
+        out = {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(used[0][2]) if used else None,
+               "reasons": sorted(reasons), "samples": len(used), "samples_in_timed_region": len(inside), "source": "NVML, 5 ms period"}
+        if self.error:
+            out["error"] = self.error
+        return out
 
 
 def host_cpu_info():

@@ -253,14 +253,32 @@ __device__ __forceinline__ void patch_column_deltas(const Params &d, const Patch
     }
 }
 
+// The bounds a lane checks its own columns against, read once per launch: C3 / C4 of slots `lane` and `lane + 32`,
+// and (used by the first lane of every 8-lane rack group) C6 of those slots' racks as lo | hi << 16 — a rack field
+// beyond R gets 0 | 0xFFFF, which no total violates (totals stay below 2^16).
+template <int W> struct LaneBounds {
+    int rep_lo[W], rep_hi[W], ldr_lo[W], ldr_hi[W];
+    uint32_t rack[W];
+    __device__ __forceinline__ void load(const Consts *cs, int lane, int R)
+    {
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const int s = lane + 32 * t, rk = s >> 3;
+            rep_lo[t] = (int)(cs->bnd_rep[s] & 0xFFFFu); rep_hi[t] = (int)(cs->bnd_rep[s] >> 16);
+            ldr_lo[t] = (int)(cs->bnd_ldr[s] & 0xFFFFu); ldr_hi[t] = (int)(cs->bnd_ldr[s] >> 16);
+            rack[t] = rk < R ? ((uint32_t)cs->rack_lo[rk] | ((uint32_t)cs->rack_hi[rk] << 16)) : 0xFFFF0000u;
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // the whole candidate.  T: the two transposed planes; Z: the term planes [kZPlanes][nW]; bits: the row-major
-// base; pdelta: patch_column_deltas of this candidate; pviol / pobj / pcount: patch_terms of its patched rows
+// base; lb: this lane's bounds; pdelta: patch_column_deltas of this candidate; pviol / pobj / pcount: patch_terms of its patched rows
 // ------------------------------------------------------------------------------------------
 template <class Cfg, bool kShared>
 __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt, const uint32_t *bitsT, const uint32_t *Zp,
-                                 const Consts *cs, const PatchSet &ps, const uint8_t *pdelta, int pviol, int pobj, int pcount, int lane,
-                                 int &viol_out, int &obj_out)
+                                 const LaneBounds<Cfg::W> &lb, const PatchSet &ps, const uint8_t *pdelta, int pviol, int pobj, int pcount,
+                                 int lane, int &viol_out, int &obj_out)
 {
     constexpr int W = Cfg::W, kNW = Cfg::kNW;
     constexpr int NSL = 32 * W;
@@ -311,16 +329,15 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
         const int pd = pdelta[s];
         const int c = cnt[t].total() + (pd & 15) - 4, l = lcnt[t].total() + (pd >> 4) - 4;
         packed |= (uint32_t)c << (16 * t);                      // c <= P < 8192: the sum of 8 lanes stays below 2^16
-        viol += 2 * c + band_violation(c, cs->bnd_rep[s]) + band_violation(l, cs->bnd_ldr[s]) - l;     // 2 c: see rows_pass
+        viol += 2 * c - l + max(c - lb.rep_hi[t], 0) + max(lb.rep_lo[t] - c, 0) + max(l - lb.ldr_hi[t], 0) + max(lb.ldr_lo[t] - l, 0);   // 2 c: see rows_pass
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
     if ((lane & 7) == 0) {
 #pragma unroll
         for (int t = 0; t < W; ++t) {
-            const int rk = (lane + 32 * t) >> 3;
             const int tot = (int)((packed >> (16 * t)) & 0xFFFFu);
-            if (rk < d.R) viol += max(tot - cs->rack_hi[rk], 0) + max(cs->rack_lo[rk] - tot, 0);
+            viol += max(tot - (int)(lb.rack[t] >> 16), 0) + max((int)(lb.rack[t] & 0xFFFFu) - tot, 0);
         }
     }
     viol_out = __reduce_add_sync(0xFFFFFFFFu, viol) + d.P;

@@ -504,6 +504,8 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             tg.T = s_sw; tg.tnW = t_words(d.Ppad); tg.t_leaders_valid = s_counts[2] == 0;    // "first holder of slot s": plane scan
             constexpr int BS = batch_stride<W>();
             uint32_t *batch = s_prow + (size_t)warp * 32 * BS;
+            LaneBounds<W> lb;
+            lb.load(s_cs, lane, d.R);
             for (uint32_t it0 = 0; it0 < iters; it0 += 32) {
                 {
                     const uint32_t idx = first + warp + (it0 + lane) * stride;
@@ -539,7 +541,7 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                         ps.n = 0;                                           // the evaluator reads the partitions only
                         ps.ld[0] = ps.ld[1] = ps.ld[2] = 0xFF;
                         int viol, obj;
-                        eval_candidate_t<Cfg, true>(d, s_sw, t_words(d.Ppad), s_bits, s_z, s_cs, ps, reinterpret_cast<const uint8_t *>(slot + kBatchHdr),
+                        eval_candidate_t<Cfg, true>(d, s_sw, t_words(d.Ppad), s_bits, s_z, lb, ps, reinterpret_cast<const uint8_t *>(slot + kBatchHdr),
                                                     (int)hdr.z, (int)hdr.w, (int)(hdr.y >> 16), lane, viol, obj);
                         const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
                         if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = key;

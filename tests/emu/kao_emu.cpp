@@ -152,12 +152,14 @@ template <class Cfg> struct Run {
                 for (int i = 0; i < kMaxOps; ++i)
                     for (int t = 0; t < W; ++t) prows[i][t] = ps.p[i] >= 0 ? e.prow[i * W + t] : 0u;
                 int pviol = 0, pobj = 0, pcount = 0;
+                LaneBounds<W> lb;
+                lb.load(&e.cs, lane, e.prm.R);
                 alignas(16) uint8_t pdelta[32 * W];                                      // every fiber keeps its own copy (the kernel: the warp's batch)
                 if (e.trans) {                                                           // per candidate, as the per-thread generator does
                     patch_terms<W>(e.prm, ps, prows, pviol, pobj, pcount);
                     patch_column_deltas<W>(e.prm, ps, prows, e.bits.data(), e.leader.data(), pdelta);
                 }
-#define KAO_EMU_T(NW_, POP_) eval_candidate_t<EvalCfgT<W, NW_, 1, POP_>, true>(e.prm, e.T.data(), e.nW, e.bits.data(), e.Z.data(), &e.cs, ps, pdelta, pviol, pobj, pcount, lane, viol, obj)
+#define KAO_EMU_T(NW_, POP_) eval_candidate_t<EvalCfgT<W, NW_, 1, POP_>, true>(e.prm, e.T.data(), e.nW, e.bits.data(), e.Z.data(), lb, ps, pdelta, pviol, pobj, pcount, lane, viol, obj)
                 if (e.trans == 1 && fixed) KAO_EMU_T(32, 0x22);
                 else if (e.trans == 1 || e.trans == 2) KAO_EMU_T(0, 0x22);
                 else if (e.trans == 3 && fixed) KAO_EMU_T(32, 0x00);
