@@ -253,12 +253,11 @@ __device__ __forceinline__ void patch_column_deltas(const Params &d, const Patch
     }
 }
 
-// The bounds a lane checks its own columns against, read once per launch: C3 / C4 of slots `lane` and `lane + 32`,
-// and (used by the first lane of every 8-lane rack group) C6 of those slots' racks as lo | hi << 16 — a rack field
-// beyond R gets 0 | 0xFFFF, which no total violates (totals stay below 2^16).
+// The bounds a lane checks its own columns against, read once per round: C3 / C4 of slots `lane` and `lane + 32`,
+// and (used by the first lane of every 8-lane rack group) C6 of those slots' racks — a rack field beyond R gets
+// [0, INT_MAX], which no total violates.  Rack bounds are whatever the caller passed (any int32), so they stay whole words.
 template <int W> struct LaneBounds {
-    int rep_lo[W], rep_hi[W], ldr_lo[W], ldr_hi[W];
-    uint32_t rack[W];
+    int rep_lo[W], rep_hi[W], ldr_lo[W], ldr_hi[W], rack_lo[W], rack_hi[W];
     __device__ __forceinline__ void load(const Consts *cs, int lane, int R)
     {
 #pragma unroll
@@ -266,7 +265,8 @@ template <int W> struct LaneBounds {
             const int s = lane + 32 * t, rk = s >> 3;
             rep_lo[t] = (int)(cs->bnd_rep[s] & 0xFFFFu); rep_hi[t] = (int)(cs->bnd_rep[s] >> 16);
             ldr_lo[t] = (int)(cs->bnd_ldr[s] & 0xFFFFu); ldr_hi[t] = (int)(cs->bnd_ldr[s] >> 16);
-            rack[t] = rk < R ? ((uint32_t)cs->rack_lo[rk] | ((uint32_t)cs->rack_hi[rk] << 16)) : 0xFFFF0000u;
+            rack_lo[t] = rk < R ? cs->rack_lo[rk] : 0;
+            rack_hi[t] = rk < R ? cs->rack_hi[rk] : 0x7FFFFFFF;
         }
     }
 };
@@ -337,7 +337,7 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
 #pragma unroll
         for (int t = 0; t < W; ++t) {
             const int tot = (int)((packed >> (16 * t)) & 0xFFFFu);
-            viol += max(tot - (int)(lb.rack[t] >> 16), 0) + max((int)(lb.rack[t] & 0xFFFFu) - tot, 0);
+            viol += max(tot - lb.rack_hi[t], 0) + max(lb.rack_lo[t] - tot, 0);
         }
     }
     viol_out = __reduce_add_sync(0xFFFFFFFFu, viol) + d.P;

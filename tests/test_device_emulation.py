@@ -226,6 +226,22 @@ def test_column_major_forms_on_a_malformed_base(emu, ref_lib, name):
     sess.close()
 
 
+def test_column_major_evaluator_with_wide_open_rack_bounds(emu, ref_lib):
+    """C6 bounds are plain int32 of the caller: "no upper bound" as 10^6 (above 16 bits) and a lower bound no rack
+    can reach must be charged exactly as the restatement charges them."""
+    import dataclasses
+
+    base = COLUMN_MAJOR["cfg2_rm2"]()
+    for lo, hi in [(0, 1_000_000), (70_000, 1_000_000), (3, 5)]:
+        pb = dataclasses.replace(base, rack_lo=np.full(base.R, lo, np.int32), rack_hi=np.full(base.R, hi, np.int32))
+        r = ref_lib.Ref(pb)
+        bits, ld = r.init_base()
+        sess = emu.EmuSession(product(pb))
+        assert sess.set_evaluator(1)
+        assert (r.candidate_keys(bits, ld, 5, 1, 256, 0, 64) == sess.candidate_keys(5, 1, 256, 0, 64)).all(), (lo, hi)
+        sess.close()
+
+
 def test_column_major_evaluator_refuses_other_layouts(emu):
     # general rack bounds, whole-word racks, wide rows, dense weights, C7 lower bound, planes too large for shared memory
     for name in ["readme", "s32", "w8_s16", "dense_small", "rf_up", "w2_rows6000"]:

@@ -123,6 +123,24 @@ def test_config3_same_winner_both_evaluators():
     assert (r1.replicas == r2.replicas).all() and (r1.violation, r1.objective, r1.key) == (r2.violation, r2.objective, r2.key)
 
 
+def test_wide_open_rack_bounds_both_evaluators(ref_lib):
+    """C6 bounds are plain int32 of the caller ("no upper bound" as 10^6, a lower bound no rack can reach): both
+    full evaluators charge them exactly as the restatement does."""
+    import dataclasses
+
+    base = SHAPES["cfg2_rm2"]()
+    for lo, hi in [(0, 1_000_000), (70_000, 1_000_000), (3, 5)]:
+        pb = dataclasses.replace(base, rack_lo=np.full(base.R, lo, np.int32), rack_hi=np.full(base.R, hi, np.int32))
+        r = ref_lib.Ref(pb)
+        bits, ld = r.init_base()
+        want = r.candidate_keys(bits, ld, 5, 1, 2048, 0, 512)
+        for column_major in (True, False):
+            sess = kao.Session(product(pb))
+            assert sess.set_evaluator(column_major)
+            assert (want == sess.candidate_keys(5, 1, 2048, 0, 512)).all(), (lo, hi, column_major)
+            sess.close()
+
+
 def test_unsupported_layouts_are_refused():
     for name in ["readme", "w8_s16", "dense_small", "w2_rows6000"]:   # w2_rows6000: the planes do not fit in shared memory
         sess = kao.Session(product(SHAPES[name]()))
