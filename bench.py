@@ -55,8 +55,9 @@ def measured_peak():
 
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region, through NVML (what nvidia-smi reads: its
-    own output arrives block-buffered through a pipe, i.e. too late) from a thread of this process every 5 ms;
-    only the samples taken between mark_begin() and mark_end() count (all of them if there were none)."""
+    own output arrives block-buffered through a pipe, i.e. too late) from a thread of this process every 5 ms
+    (start() returns once the first sample is in); only the samples taken between mark_begin() and mark_end()
+    count (all of them if there were none)."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
@@ -65,6 +66,7 @@ class ClockSampler:
         self.t0 = self.t1 = None
         self.running = False
         self.error = None
+        self.ready = threading.Event()                       # set after NVML is up and the first sample is in
 
     def _loop(self):
         try:
@@ -83,14 +85,17 @@ class ClockSampler:
             get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
             while self.running:
                 self.samples.append((time.monotonic(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx, int(get_reasons(h))))
+                self.ready.set()
                 time.sleep(0.005)
         except Exception as e:                               # no NVML: the line says so instead of inventing clocks
             self.error = repr(e)
+            self.ready.set()
 
     def start(self):
         self.running = True
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
+        self.ready.wait(timeout=10.0)                        # nvmlInit can take longer than a whole short bench run
 
     def mark_begin(self):
         self.t0 = time.monotonic()

@@ -188,11 +188,11 @@ int kao_set_patience(kao_handle *h, uint32_t rounds_without_improvement);
 #define KAO_EVAL_COLUMN_MAJOR 1
 int kao_set_evaluator(kao_handle *h, int32_t evaluator);
 /* Schedule of the column-major evaluator: the same arithmetic, laid out differently in time.  sync: how
- * the warps of a CTA meet before an evaluation (0 block barrier, 1 warp only, 2 warp only with the column loop
- * kept a loop); pop: one hex digit per
+ * the warps of a CTA meet before an evaluation and how the column loop is laid out (0 block barrier, 1 warp only with
+ * the loop fully unrolled, 2 warp only with the loop kept a loop, 4 that loop unrolled by four); pop: one hex digit per
  * popcount stream (column totals in the low digit, leader totals in the next): 0 a POPC per word, 1 three per
  * four words, 2 two, 3 one (carry-save adders do the rest); threads per CTA: 640 .. 1024.  Only the six
- * combinations built into the library are accepted (KAO_E_ARG otherwise); the default (2, 0x22, 896) is the
+ * combinations built into the library are accepted (KAO_E_ARG otherwise); the default (4, 0x22, 896) is the
  * fastest one measured on a B200 (profiles/).  Results never depend on it.  The environment variable
  * KAO_SCHEDULE="sync,pop(hex),threads" sets it for every session (and kao_solve); KAO_EVALUATOR=row forces
  * the row-major evaluator. */

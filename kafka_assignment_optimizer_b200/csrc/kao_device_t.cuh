@@ -39,7 +39,8 @@ namespace kao {
 // The other parameters are SCHEDULES of the same arithmetic (kao_set_schedule; results identical):
 //   kSync      how the warps of a CTA meet before an evaluation: 0 block barrier (all warps walk the
 //              evaluator together), 1 warp only (one warp's generator overlaps another's evaluation), 2 warp only
-//              with the column loop kept a loop (a third less evaluator code for the instruction cache)
+//              with the column loop kept a loop (a third less evaluator code for the instruction cache), 3 / 4 that loop
+//              unrolled by 2 / 4
 //   kPop       how the two popcount streams (column totals, leader totals) trade POPC (XU pipe, 8 cycles
 //              a warp) for carry-save LOP3 (ALU pipe, 2 cycles): one hex digit per stream, 0 = a POPC per
 //              word, 1 = three per four words, 2 = two, 3 = one (Harley-Seal accumulators carried across
@@ -311,9 +312,15 @@ __device__ void eval_candidate_t(const Params &d, const uint32_t *Tp, int nW_rt,
             lcnt[t].add4(oh[t].x, oh[t].y, oh[t].z, oh[t].w);
         }
     };
-    if constexpr (kNW == 32 && Cfg::kSync != 2) {
+    if constexpr (kNW == 32 && Cfg::kSync < 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { uint4 c[W], o[W]; load(j, c, o); add(c, o); }
+    } else if constexpr (Cfg::kSync == 3) {          // nch is even (t_words rounds to whole groups of 8 words)
+#pragma unroll 2
+        for (int j = 0; j < nch; ++j) { uint4 c[W], o[W]; load(j, c, o); add(c, o); }
+    } else if constexpr (Cfg::kSync == 4) {
+#pragma unroll 4
+        for (int j = 0; j < nch; ++j) { uint4 c[W], o[W]; load(j, c, o); add(c, o); }
     } else {
 #pragma unroll 1
         for (int j = 0; j < nch; ++j) { uint4 c[W], o[W]; load(j, c, o); add(c, o); }

@@ -506,6 +506,10 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
             uint32_t *batch = s_prow + (size_t)warp * 32 * BS;
             LaneBounds<W> lb;
             lb.load(s_cs, lane, d.R);
+            // the warp's best candidate of the round as (violation, cost, index) — the fields of the packed key, compared
+            // field by field and packed once per round (indices rise within a warp: the first of equals stays)
+            const uint32_t vcap32 = (uint32_t)key_viol_cap(d.key_obj_bits), omax = (1u << d.key_obj_bits) - 1u;
+            uint32_t bv = 0xFFFFFFFFu, bc = 0, bi = 0;              // bv: no candidate yet (a violation field never exceeds 2^31 - 1)
             for (uint32_t it0 = 0; it0 < iters; it0 += 32) {
                 {
                     const uint32_t idx = first + warp + (it0 + lane) * stride;
@@ -543,13 +547,16 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
                         int viol, obj;
                         eval_candidate_t<Cfg, true>(d, s_sw, t_words(d.Ppad), s_bits, s_z, lb, ps, reinterpret_cast<const uint8_t *>(slot + kBatchHdr),
                                                     (int)hdr.z, (int)hdr.w, (int)(hdr.y >> 16), lane, viol, obj);
-                        const unsigned long long key = pack_key(viol, obj, idx, d.key_obj_bits);
-                        if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = key;
-                        best = key < best ? key : best;
+                        if (all_keys && lane == 0) all_keys[idx - pp.idx_lo] = pack_key(viol, obj, idx, d.key_obj_bits);
+                        const uint32_t v = min((uint32_t)max(viol, 0), vcap32);
+                        const uint32_t c = (uint32_t)obj > omax ? 0u : omax - (uint32_t)obj;
+                        if (v < bv || (v == bv && c < bc)) { bv = v; bc = c; bi = idx; }
                     }
                 }
                 __syncwarp();                                               // the batch is consumed before it is refilled
             }
+            if (bv != 0xFFFFFFFFu)
+                best = ((unsigned long long)bv << (kIdxBits + d.key_obj_bits)) | ((unsigned long long)bc << kIdxBits) | (unsigned long long)(bi & kIdxMask);
             if (all_keys) return;                                           // key dump only: the base stays as it is
         } else {
         for (uint32_t it = 0; it < iters; ++it) {
@@ -735,8 +742,8 @@ search_persistent_kernel(Params d, SmemPlan plan, uint64_t seed, uint32_t first_
 // Column-major kernels: X(sync, pop, threads) for every built schedule (kao_set_schedule); each is
 // instantiated for W = 1, 2 and for 32 partition words (compile-time offsets) / any word count.
 #define KAO_FOR_SCHEDULES(X) \
-    X(2, 0x22, 896) X(2, 0x22, 768) X(2, 0x22, 1024) X(2, 0x22, 640) X(1, 0x22, 768) X(2, 0x12, 896)
-#define KAO_SCHEDULE_DEFAULT_SYNC 2
+    X(4, 0x22, 896) X(1, 0x22, 896) X(4, 0x22, 1024) X(4, 0x22, 768) X(4, 0x12, 896) X(2, 0x22, 896)
+#define KAO_SCHEDULE_DEFAULT_SYNC 4
 #define KAO_SCHEDULE_DEFAULT_POP 0x22
 #define KAO_SCHEDULE_DEFAULT_THREADS 896
 #define KAO_PERSISTENT_KERNEL_T(W, NW, S, POP, T)                                                            \

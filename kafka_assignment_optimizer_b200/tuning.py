@@ -12,7 +12,7 @@ from __future__ import annotations
 import json
 
 # (sync, pop, threads) — the variants csrc/kao_kernels.cuh builds (KAO_FOR_SCHEDULES); the first is the default
-SCHEDULES = [(2, 0x22, 896), (2, 0x22, 768), (2, 0x22, 1024), (2, 0x22, 640), (1, 0x22, 768), (2, 0x12, 896)]
+SCHEDULES = [(4, 0x22, 896), (1, 0x22, 896), (4, 0x22, 1024), (4, 0x22, 768), (4, 0x12, 896), (2, 0x22, 896)]
 DEFAULT_SCHEDULE = SCHEDULES[0]
 SCHEDULE_FIELDS = ("sync", "pop", "threads")
 

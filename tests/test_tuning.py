@@ -16,7 +16,7 @@ def test_schedule_list_matches_the_kernel_header():
                int(re.search(r"#define KAO_SCHEDULE_DEFAULT_THREADS (\d+)", src).group(1)))
     assert default == tuning.DEFAULT_SCHEDULE == built[0]
     for sync, pop, threads in built:
-        assert sync in (0, 1, 2) and threads in (512, 640, 768, 896, 1024)
+        assert sync in (0, 1, 2, 3, 4) and threads in (512, 640, 768, 896, 1024)
         assert all(0 <= (pop >> (4 * i)) & 15 <= 3 for i in range(5)) and pop >> 20 == 0
 
 
