@@ -46,3 +46,26 @@ def test_host_emulation_stays_out_of_the_product():
     if os.path.exists(so):
         syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
         assert "kao_emu" not in syms and "kao_solve" in syms
+
+
+def test_bench_clock_sampler_says_so_when_there_is_no_nvml():
+    """bench.py samples clocks through NVML during the timed region; without a driver it must neither hang nor
+    invent numbers: no samples, an `error` field."""
+    import importlib.util
+    import time
+
+    spec = importlib.util.spec_from_file_location("kao_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    t0 = time.time()
+    s.start()
+    s.mark_begin()
+    time.sleep(0.03)
+    s.mark_end()
+    out = s.stop()
+    assert time.time() - t0 < 15.0
+    if out["samples"] == 0:                      # this container: no GPU, no libnvidia-ml
+        assert out["sm_mhz"] is None and out["reasons"] == [] and "error" in out
+    else:                                        # a GPU box: real samples, all of them inside or around the region
+        assert out["sm_mhz"] and out["sm_max_mhz"] and out["samples_in_timed_region"] <= out["samples"]
