@@ -12,9 +12,14 @@ from oracle import model as m
 from test_host import README_CURRENT
 
 
+SEEN = {}
+
+
 def oracle_solver(pb, **kw):
+    SEEN.update(kw)                                   # what the façade passed on
     sol = m.solve_exact(m.Problem(**{f: getattr(pb, f) for f in m.Problem.__dataclass_fields__}))
-    return SolveResult(sol.replicas, sol.objective, 0, sol.moves, True, 0, 0, 0, 0.0, 0.0)
+    return SolveResult(sol.replicas, sol.objective, 0, sol.moves, True, 0, 0, 0, 0.0, 0.0,
+                       objective_bound=sol.objective, optimal=bool(kw.get("tight_bound")))
 
 
 def test_submit_round_trip_over_http():
@@ -52,6 +57,12 @@ def test_submit_refuses_unbounded_requests():
         with pytest.raises(ValueError):
             service.handle_submit(dict(base, **bad), solver=oracle_solver)
     assert service.handle_submit(dict(base, rounds=0), solver=oracle_solver)["feasible"]
+    for bad in ({"gpus": 0}, {"gpus": 9}):
+        with pytest.raises(ValueError):
+            service.handle_submit(dict(base, **bad), solver=oracle_solver)
+    out = service.handle_submit(dict(base, gpus=2, spread_restarts=True, restarts=4, certificate=True), solver=oracle_solver)
+    assert (SEEN["n_gpus"], SEEN["spread_restarts"], SEEN["restarts"], SEEN["tight_bound"]) == (2, True, 4, True)
+    assert out["objective_bound"] == out["objective"] == 58 and out["proven_optimal"]
 
 
 def test_duplicate_broker_ids_are_one_broker():
