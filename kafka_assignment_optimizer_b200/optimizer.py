@@ -334,8 +334,10 @@ class AssignmentOptimizer:
     """Operator-level mirror of the reference: feed it what `kafka-reassign-partitions --generate`
     printed plus the target broker list and topology, get the reassignment JSON back."""
 
-    def __init__(self, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15, device: int = 0):
+    def __init__(self, seed: int = 0x5EED, rounds: int = 256, round_size: int = 1 << 15, device: int = 0, **solve_options):
+        """solve_options: anything else `solve` takes (restarts, patience, delta, n_gpus, spread_restarts, tight_bound)."""
         self.seed, self.rounds, self.round_size, self.device = seed, rounds, round_size, device
+        self.solve_options = solve_options
 
     def optimize(self, assignment_json, broker_list, rack_map, rf: Optional[int] = None):
         rows, topics = parse_assignment_json(assignment_json)
@@ -344,5 +346,5 @@ class AssignmentOptimizer:
         if rf is None:
             rf = max(len(r) for r in rows)
         pb = build_problem(rows, brokers, racks, rf, topics)
-        res = solve(pb, self.seed, self.rounds, self.round_size, self.device)
+        res = solve(pb, self.seed, self.rounds, self.round_size, self.device, **self.solve_options)
         return reassignment_json(pb, res.replicas), res
