@@ -60,12 +60,18 @@ struct Params {
     int nz;                      // planes in use (0..8)
     int z_on_leader;             // bit j set: plane j counts leaderships (bonus wL - wF), else replicas (wF)
     int z_value[8];              // value of a term of plane j
+    uint32_t rf_mask[4];         // bit k of RF spread over a word (all ones / zero): the row pass compares bit-sliced counts with RF
     const uint8_t *zslot;        // [Ppad][8] slot of partition p's term in plane j, 0xFF = none
     uint16_t *D;                 // displaced partitions of the base, ascending
     uint16_t *DL;                // leader-displaced partitions of the base, ascending
     int *nD;                     // [0] = |D|, [1] = |DL|
     const Consts *consts;
 };
+
+inline void set_rf_masks(Params &p)
+{
+    for (int k = 0; k < 4; ++k) p.rf_mask[k] = ((p.RF >> k) & 1) ? 0xFFFFFFFFu : 0u;
+}
 
 // ------------------------------------------------------------------------------------------
 // small helpers

@@ -92,7 +92,7 @@ __device__ __forceinline__ int rows_pass(const Params &d, const MemRef<kShared> 
     const int nW = kNW ? kNW : nW_rt;
     constexpr int NB = 4 * W;                       // 8-slot blocks = rack fields
     int viol = 0;
-    const uint32_t rf0 = (RF & 1) ? ~0u : 0u, rf1 = (RF & 2) ? ~0u : 0u, rf2 = (RF & 4) ? ~0u : 0u, rf3 = (RF & 8) ? ~0u : 0u;
+    const uint32_t rf0 = d.rf_mask[0], rf1 = d.rf_mask[1], rf2 = d.rf_mask[2], rf3 = d.rf_mask[3];   // kernel parameters: constant-bank operands
 #pragma unroll 1
     for (int w = lane; w < nW; w += 32) {
         const int left = P - 32 * w;                // partitions of this word that exist

@@ -461,6 +461,7 @@ static int create_impl(const kao_problem *pb, int32_t device, kao_handle *h)
     CUDA_TRY(cudaEventCreate(&h->ev1));
     Params &p = h->prm;
     p.P = m.P; p.Ppad = Ppad; p.B = m.B; p.R = m.R; p.RF = m.RF; p.NS = m.NS; p.log2S = m.log2S;
+    set_rf_masks(p);
     p.ppr_lo = m.ppr_lo; p.ppr_hi = m.ppr_hi; p.dense = m.dense ? 1 : 0;
     p.key_obj_bits = m.key_obj_bits;
     p.nentries = m.nentries; p.nplanes = m.nplanes; p.plane_on_leader = m.plane_on_leader;

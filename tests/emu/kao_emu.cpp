@@ -292,6 +292,7 @@ void *kao_emu_create(const kao_problem *pb)
     fill_consts(m, e->cs);
     Params &p = e->prm;
     p.P = m.P; p.Ppad = m.Ppad; p.B = m.B; p.R = m.R; p.RF = m.RF; p.NS = m.NS; p.log2S = m.log2S;
+    set_rf_masks(p);
     p.key_obj_bits = m.key_obj_bits;
     p.ppr_lo = m.ppr_lo; p.ppr_hi = m.ppr_hi; p.dense = m.dense ? 1 : 0;
     p.nentries = m.nentries; p.nplanes = m.nplanes; p.plane_on_leader = m.plane_on_leader;
