@@ -99,6 +99,30 @@ def test_c_search_reaches_exact_optimum(ref_lib, name):
     assert all((a[0], -a[1]) >= (b[0], -b[1]) for a, b in zip(ks, ks[1:]))   # monotone descent
 
 
+def test_cycle_rounds_draw_closed_exchanges(ref_lib):
+    """docs/MODEL.md 5: every fourth round (round mod 4 = 3) draws one family of candidates — a displaced partition
+    returns home, a second partition moves onto the broker it left, a holder of the home broker moves to where the
+    second one came from: three patched partitions, every broker's replica total as before (unless a target was
+    already in use and REPLACE stepped on).  Free rounds draw such an exchange a few times in a hundred."""
+    pb = m.synthetic_problem(512, 64, 8, 3, 0, 0.03, 5)                # tight bounds: 24 replicas on every broker
+    r = ref_lib.Ref(pb)
+    bits, ld = r.init_base()
+    r.search(bits, ld, 1, 0, 200, 2048)                                # a feasible base with displaced partitions left
+    assert r.evaluate(bits, ld)[0] == 0
+    base_totals = np.bincount(r.decode(bits, ld).reshape(-1), minlength=pb.B)
+    for rnd in (2, 3, 6, 7):
+        three = closed = 0
+        for idx in range(200):
+            cb, cl = r.gen(bits, ld, 9, rnd, idx, 4096)
+            if int(((cb != bits).any(axis=1) | (cl != ld)).sum()) == 3:
+                three += 1
+                closed += int((np.bincount(r.decode(cb, cl).reshape(-1), minlength=pb.B) == base_totals).all())
+        if rnd % 4 == 3:
+            assert three >= 180 and closed >= 150, (rnd, three, closed)
+        else:
+            assert three <= 100 and closed <= 40, (rnd, three, closed)
+
+
 def test_golden_optima_file_is_consistent():
     """tests/golden/optima.json holds HiGHS optima of the BASELINE.json configs (generated by
     tests/golden/make_golden.py); spot-check the small ones by re-solving."""
