@@ -77,3 +77,65 @@ def test_two_gloo_ranks_walk_the_single_process_trajectory():
     for rank, keys, final in got:
         assert keys == [int(k) for k in want], rank          # identical winners on every rank
         assert final == want_final
+
+
+def _restart_worker(rank, world, port, restarts, q):
+    from oracle import model as m, ref
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pb = m.synthetic_problem(256, 32, 4, 3, remove=2)
+    r = ref.Ref(pb)
+
+    def solve_one(seed):                                   # one short search; the restatement stands in for kao_solve
+        bits, ld = r.init_base()
+        last, _ = r.search(bits, ld, seed, 0, 12, 512, nthreads=1)
+        v, o, _ = r.unpack_key(last)
+        return v, o, r.decode(bits, ld).tolist()
+
+    def all_gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    def broadcast(obj, src):
+        box = [obj]
+        dist.broadcast_object_list(box, src=src)
+        return box[0]
+
+    q.put((rank,) + kd.spread_restarts(solve_one, restarts, 5, rank, world, all_gather, broadcast))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("restarts", [1, 5])
+def test_restarts_side_by_side_return_what_one_rank_returns(restarts):
+    """kd.spread_restarts (KAO_FLAG_SPREAD_RESTARTS for one process per GPU): two gloo ranks take the restarts in
+    turn; both end with the result a single rank gets from the same restarts in sequence — also with more ranks
+    than restarts."""
+    from oracle import model as m, ref
+
+    pb = m.synthetic_problem(256, 32, 4, 3, remove=2)
+    r = ref.Ref(pb)
+
+    def solve_one(seed):
+        bits, ld = r.init_base()
+        last, _ = r.search(bits, ld, seed, 0, 12, 512, nthreads=1)
+        v, o, _ = r.unpack_key(last)
+        return v, o, r.decode(bits, ld).tolist()
+
+    want = kd.spread_restarts(solve_one, restarts, 5, 0, 1)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_restart_worker, args=(rk, 2, port, restarts, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for g in got:
+        assert tuple(g[1:]) == tuple(want), g[0]
